@@ -1,0 +1,524 @@
+// cook_oracle.cpp — CPU restatement of Cook's per-cycle scheduling hot path.
+//
+// *** TEST INFRASTRUCTURE ONLY. ***  Only tests/, __graft_entry__.smoke() and
+// bench.py's cpu_baseline / --impl reference legs may load this library.  The
+// product path (cook_b200/, libcookgpu.so) never links or calls it and has no
+// CPU fallback.
+//
+// Parity status: the reference (Clojure on the JVM + Netflix Fenzo 0.10.0)
+// cannot run in this container (no JVM, no Maven cache).  This
+// file is a line-by-line restatement of the cited Clojure sources, PINNED
+// against the reference's own known-answer tests transcribed in tests/golden/
+// (K1-K22).  The Fenzo rules (section "FENZO" below) are restated from the
+// published Netflix/Fenzo 0.10.0 algorithm; they are pinned by Cook's
+// set-level tests only (K10, K12, K13, K15): job->host parity with a real
+// Fenzo is UNPINNED (no test in the reference reads hostnames of multi-host
+// matches), and the equal-fitness tie-break (lowest hostname) is OURS.
+//
+// All citations are relative to /root/reference/scheduler/src/cook/.
+//
+// Build: see oracle/Makefile  (g++ -O2 -shared -fPIC, -ffp-contract=off).
+
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <limits>
+#include <map>
+#include <queue>
+#include <set>
+#include <vector>
+
+#include "../include/cook_gpu.h"
+
+namespace {
+
+struct Usage {
+  double count = 0, cpus = 0, mem = 0, gpus = 0;
+};
+
+// tools.clj:876-881 below-quota?: every usage key <= quota key (missing => 0,
+// which the host shim materialises as 0.0 in the dense tables).  `gpus` only
+// participates when some job contributed a :gpus key (tools.clj:883-889);
+// with gpus == 0.0 and quota >= 0 the comparison is vacuous, so the 4-vector
+// form is equivalent.
+inline bool below_quota(double qc, double qcpu, double qmem, double qgpu, const Usage& u) {
+  return u.count <= qc && u.cpus <= qcpu && u.mem <= qmem && u.gpus <= qgpu;
+}
+inline bool below_quota(const cook_pool_quota* q, const Usage& u) {
+  return below_quota(q->count, q->cpus, q->mem, q->gpus, u);
+}
+
+// merge-with + : (+ acc x) left fold (dru.clj:43-48, scheduler.clj:2063).
+inline void add_usage(Usage& acc, double cpus, double mem, double gpus) {
+  acc.count = acc.count + 1.0;
+  acc.cpus = acc.cpus + cpus;
+  acc.mem = acc.mem + mem;
+  acc.gpus = acc.gpus + gpus;
+}
+
+struct TaskView {  // running ++ pending, combined index space
+  const cook_tasks_soa* r;
+  const cook_tasks_soa* p;
+  int R, J;
+  int user(int i) const { return i < R ? r->user[i] : p->user[i - R]; }
+  int prio(int i) const { return i < R ? r->priority[i] : p->priority[i - R]; }
+  int64_t start(int i) const { return i < R ? r->start_time[i] : p->start_time[i - R]; }
+  int64_t tid(int i) const { return i < R ? r->task_id[i] : p->task_id[i - R]; }
+  int64_t jid(int i) const { return i < R ? r->job_id[i] : p->job_id[i - R]; }
+  double cpus(int i) const { return i < R ? r->cpus[i] : p->cpus[i - R]; }
+  double mem(int i) const { return i < R ? r->mem[i] : p->mem[i - R]; }
+  double gpus(int i) const { return i < R ? r->gpus[i] : p->gpus[i - R]; }
+};
+
+// tools.clj:614-641: compare of [-priority start-time task-id job-id] vectors.
+inline bool task_less(const TaskView& v, int a, int b) {
+  int pa = -v.prio(a), pb = -v.prio(b);
+  if (pa != pb) return pa < pb;
+  if (v.start(a) != v.start(b)) return v.start(a) < v.start(b);
+  if (v.tid(a) != v.tid(b)) return v.tid(a) < v.tid(b);
+  return v.jid(a) < v.jid(b);
+}
+
+int g_naive_merge = 0;
+
+}  // namespace
+
+extern "C" {
+
+// Test knob: 1 => dru.clj:82-104 sorted-merge restated literally (stable
+// re-sort of all heads per emitted task, O(N*U log U)); 0 => heap with the
+// equivalent key (dru asc, arrival desc, name asc).  tests compare both.
+void oracle_set_naive_merge(int on) { g_naive_merge = on; }
+
+const char* oracle_version(void) { return "cook_oracle 1 (CPU restatement; test infrastructure)"; }
+
+// ---------------------------------------------------------------------------
+// RANK  (scheduler.clj:2057-2194, dru.clj, tools.clj:614-668, :876-933)
+// ---------------------------------------------------------------------------
+int32_t oracle_rank(int32_t dru_mode, const cook_tasks_soa* running,
+                    const cook_tasks_soa* pending, const cook_user_table* users,
+                    const cook_pool_quota* pool_quota, const cook_pool_quota* group_quota,
+                    const double* group_usage, const cook_rank_params* params,
+                    int32_t* out_ranked_idx, int32_t* out_n, double* out_dru,
+                    int32_t* out_order, int32_t* out_order_n) {
+  if (!running || !pending || !users || !params || !out_ranked_idx || !out_n) return COOK_E_BADARG;
+  TaskView v{running, pending, running->n, pending->n};
+  const int R = v.R, J = v.J, N = R + J, U = users->n_users;
+  const double NaN = std::numeric_limits<double>::quiet_NaN();
+
+  // scheduler.clj:2080-2083 group-by user, sort with same-user-task-comparator
+  std::vector<std::vector<int>> by_user(U);
+  for (int i = 0; i < N; i++) {
+    int u = v.user(i);
+    if (u < 0 || u >= U) return COOK_E_BADARG;
+    by_user[u].push_back(i);
+  }
+  std::vector<double> dru(N, NaN);
+  for (int u = 0; u < U; u++) {
+    auto& ts = by_user[u];
+    std::stable_sort(ts.begin(), ts.end(), [&](int a, int b) { return task_less(v, a, b); });
+    // scheduler.clj:2057-2071 limit-over-quota-jobs
+    Usage total;
+    int over = 0;
+    size_t kept = 0;
+    for (; kept < ts.size(); kept++) {
+      int t = ts[kept];
+      add_usage(total, v.cpus(t), v.mem(t), v.gpus(t));
+      if (!below_quota(users->quota_count[u], users->quota_cpus[u], users->quota_mem[u],
+                       users->quota_gpus[u], total))
+        over++;
+      if (over > params->max_over_quota_jobs) break;
+    }
+    ts.resize(kept);
+    // dru.clj:50-66 / :68-80 cumulative sums (left fold) then one divide each
+    double cm = 0.0, cc = 0.0, cg = 0.0;
+    for (int t : ts) {
+      cm = cm + v.mem(t);
+      cc = cc + v.cpus(t);
+      cg = cg + v.gpus(t);
+      if (dru_mode == 0) {
+        double a = cm / users->div_mem[u], b = cc / users->div_cpus[u];
+        dru[t] = a > b ? a : b;  // clojure.core/max
+      } else {
+        dru[t] = cg / users->div_gpus[u];
+      }
+    }
+  }
+  if (out_dru) std::memcpy(out_dru, dru.data(), sizeof(double) * N);
+
+  // dru.clj:82-126: k-way merge by ascending dru.  Users first ordered by name
+  // (`(sort-by first)` :123; GPU mode has no such sort in the reference =>
+  // hash order, unspecified: we use the same name order).  Each step stable-
+  // sorts the remaining per-user seqs by head key and pops the first; the
+  // popped user's remainder is consed to the FRONT (:94) => among equal heads
+  // the most recently emitted user wins, else earlier relative order.
+  std::vector<int> order;
+  order.reserve(N);
+  std::vector<int> users_by_name(U);
+  for (int u = 0; u < U; u++) users_by_name[u] = u;
+  std::sort(users_by_name.begin(), users_by_name.end(),
+            [&](int a, int b) { return users->name_rank[a] < users->name_rank[b]; });
+  if (g_naive_merge) {
+    struct Seq { int u; size_t pos; };
+    std::vector<Seq> colls;
+    for (int u : users_by_name)
+      if (!by_user[u].empty()) colls.push_back({u, 0});
+    while (!colls.empty()) {
+      std::stable_sort(colls.begin(), colls.end(), [&](const Seq& a, const Seq& b) {
+        return dru[by_user[a.u][a.pos]] < dru[by_user[b.u][b.pos]];
+      });
+      Seq s = colls.front();
+      order.push_back(by_user[s.u][s.pos]);
+      colls.erase(colls.begin());
+      if (s.pos + 1 < by_user[s.u].size()) colls.insert(colls.begin(), Seq{s.u, s.pos + 1});
+    }
+  } else {
+    struct Head { double d; int64_t arrival; int nrank; int u; size_t pos; };
+    auto cmp = [](const Head& a, const Head& b) {  // "greater" => min-heap
+      if (a.d != b.d) return a.d > b.d;
+      if (a.arrival != b.arrival) return a.arrival < b.arrival;  // later arrival first
+      return a.nrank > b.nrank;
+    };
+    std::priority_queue<Head, std::vector<Head>, decltype(cmp)> heap(cmp);
+    for (int u : users_by_name)
+      if (!by_user[u].empty()) heap.push({dru[by_user[u][0]], 0, users->name_rank[u], u, 0});
+    int64_t step = 0;
+    while (!heap.empty()) {
+      Head h = heap.top();
+      heap.pop();
+      step++;
+      order.push_back(by_user[h.u][h.pos]);
+      if (h.pos + 1 < by_user[h.u].size())
+        heap.push({dru[by_user[h.u][h.pos + 1]], step, h.nrank, h.u, h.pos + 1});
+    }
+  }
+  if (out_order) {
+    for (size_t i = 0; i < order.size(); i++) out_order[i] = order[i];
+  }
+  if (out_order_n) *out_order_n = (int32_t)order.size();
+
+  // scheduler.clj:2089-2090 keep pending only, task -> job
+  std::vector<int> queue;
+  queue.reserve(J);
+  for (int t : order)
+    if (t >= R) queue.push_back(t - R);
+
+  // scheduler.clj:2134-2157 filter-based-on-quota -> tools.clj:917-933 with
+  // filter-sequential (tools.clj:654-668): state advances for rejected jobs too.
+  auto pool_filter = [&](const cook_pool_quota* q, Usage init) {
+    if (!q || !q->enabled) return;
+    std::vector<int> keep;
+    Usage u = init;
+    for (int j : queue) {
+      add_usage(u, pending->cpus[j], pending->mem[j], pending->gpus[j]);
+      if (below_quota(q, u)) keep.push_back(j);
+    }
+    queue.swap(keep);
+  };
+  Usage pool_usage;  // scheduler.clj:2118-2123 task-ents->usage of running tasks
+  for (int i = 0; i < R; i++) add_usage(pool_usage, running->cpus[i], running->mem[i], running->gpus[i]);
+  pool_filter(pool_quota, pool_usage);
+  if (group_quota && group_quota->enabled && group_usage) {
+    Usage gu;
+    gu.count = group_usage[0]; gu.cpus = group_usage[1]; gu.mem = group_usage[2]; gu.gpus = group_usage[3];
+    pool_filter(group_quota, gu);
+  }
+  // scheduler.clj:2198-2229 filter-offensive-jobs
+  int n = 0;
+  for (int j : queue) {
+    if (params->filter_offensive &&
+        (pending->mem[j] > params->offensive_max_mem_mb || pending->cpus[j] > params->offensive_max_cpus))
+      continue;
+    out_ranked_idx[n++] = j;
+  }
+  *out_n = n;
+  return COOK_OK;
+}
+
+// ---------------------------------------------------------------------------
+// MATCH  (scheduler.clj:617-762, tools.clj:903-973, constraints.clj, FENZO)
+// ---------------------------------------------------------------------------
+namespace {
+
+struct MatchState {
+  const cook_jobs_soa* jobs;
+  const cook_offers_soa* of;
+  const cook_groups* groups;
+  const cook_match_params* prm;
+  std::vector<double> asg_cpus, asg_mem;  // Σ assigned this cycle per VM
+  std::vector<int> asg_count, ports_used, ports_total;
+  // cotasks placed this cycle per group: (hostname id, vm index)
+  std::vector<std::vector<int>> group_vms;
+};
+
+inline double csr_lookup(const int32_t* off, const int32_t* key, const double* val, int v, int k) {
+  if (!off) return 0.0;
+  for (int i = off[v]; i < off[v + 1]; i++)
+    if (key[i] == k) return val[i];
+  return 0.0;
+}
+
+// One (job, VM) evaluation = Fenzo AssignableVirtualMachine.tryRequest:
+// resource fit, hard constraints, fitness (FENZO rules 3-4).  Returns fitness
+// (> 0) or 0.0 on failure; *res_fail set when the failure was a resource.
+double eval_pair(const MatchState& s, int j, int v, bool* res_fail) {
+  const cook_jobs_soa* jb = s.jobs;
+  const cook_offers_soa* of = s.of;
+  *res_fail = true;
+  // FENZO 3a: used-this-cycle + request > lease total => fail
+  if (s.asg_cpus[v] + jb->cpus[j] > of->cpus[v]) return 0.0;
+  if (s.asg_mem[v] + jb->mem[j] > of->mem[v]) return 0.0;
+  int want_ports = jb->ports ? jb->ports[j] : 0;
+  if (want_ports > s.ports_total[v] - s.ports_used[v]) return 0.0;
+  *res_fail = false;
+  // FENZO 3b hard constraints, Cook's effective order (scheduler.clj:493-501,
+  // constraints.clj:487-495): checkpoint-locality, estimated-completion,
+  // user-defined, disk, gpu, novel-host, max-tasks-per-host, reservation, groups
+  if (jb->ckpt_location && jb->ckpt_location[j] >= 0) {  // constraints.clj:201-240
+    int loc = of->location ? of->location[v] : -1;
+    if (loc != jb->ckpt_location[j]) return 0.0;
+  }
+  if (jb->est_end_ms && jb->est_end_ms[j] >= 0 && of->host_start_time &&
+      of->host_start_time[v] >= 0) {  // constraints.clj:385-401
+    int64_t death = 1000 * of->host_start_time[v] + (int64_t)60 * 1000 * s.prm->host_lifetime_mins;
+    if (!(jb->est_end_ms[j] < death)) return 0.0;
+  }
+  if (jb->attr_off) {  // constraints.clj:355-376 user-defined EQUALS
+    for (int k = jb->attr_off[j]; k < jb->attr_off[j + 1]; k++) {
+      int col = jb->attr_col[k], val = jb->attr_val[k];
+      if (col < 0 || col >= of->n_attr_cols) return 0.0;
+      int hv = of->attr[(size_t)col * of->n + v];
+      if (val <= 0 || hv != val) return 0.0;
+    }
+  }
+  bool k8s = of->is_k8s && of->is_k8s[v];
+  if (jb->disk_request && jb->disk_request[j] >= 0.0 && k8s) {  // constraints.clj:164-186
+    double space = csr_lookup(of->disk_off, of->disk_type, of->disk_space, v,
+                              jb->disk_type ? jb->disk_type[j] : -1);
+    if (!(space >= jb->disk_request[j])) return 0.0;
+  }
+  {  // constraints.clj:122-157 gpu-host-constraint (always built)
+    double g = jb->gpus ? jb->gpus[j] : 0.0;
+    if (k8s) {
+      if (g > 0.0) {
+        double have = csr_lookup(of->gpu_off, of->gpu_model, of->gpu_count, v,
+                                 jb->gpu_model ? jb->gpu_model[j] : -1);
+        int on_vm = (of->run_count ? of->run_count[v] : 0) + s.asg_count[v];
+        if (!(have == g && on_vm == 0)) return 0.0;
+      } else {
+        int nmodels = of->gpu_off ? of->gpu_off[v + 1] - of->gpu_off[v] : 0;
+        if (nmodels != 0) return 0.0;
+      }
+    } else if (!(g == 0.0)) {
+      return 0.0;
+    }
+  }
+  if (jb->novel_off) {  // constraints.clj:68-94
+    for (int k = jb->novel_off[j]; k < jb->novel_off[j + 1]; k++)
+      if (jb->novel_host[k] == of->hostname_id[v]) return 0.0;
+  }
+  if (of->max_tasks && of->max_tasks[v] >= 0) {  // constraints.clj:433-456
+    int total = (of->num_tasks ? of->num_tasks[v] : 0) + s.asg_count[v];
+    if (!(total < of->max_tasks[v])) return 0.0;
+  }
+  if (of->reserved && of->reserved[v]) {  // constraints.clj:242-252, scheduler.clj:645-653
+    int mine = jb->reserved_host ? jb->reserved_host[j] : -1;
+    if (mine != of->hostname_id[v]) return 0.0;
+  }
+  if (jb->group_off && s.groups) {  // constraints.clj:586-678
+    const cook_groups* gr = s.groups;
+    for (int k = jb->group_off[j]; k < jb->group_off[j + 1]; k++) {
+      int g = jb->group_idx[k];
+      int kind = gr->kind[g];
+      const std::vector<int>& placed = s.group_vms[g];
+      if (kind == COOK_GROUP_UNIQUE) {
+        int h = of->hostname_id[v];
+        for (int c = gr->cot_off[g]; c < gr->cot_off[g + 1]; c++)
+          if (gr->cot_hostname_id[c] == h) return 0.0;
+        for (int pv : placed)
+          if (of->hostname_id[pv] == h) return 0.0;
+      } else {
+        int col = gr->attr_col[g];
+        auto vm_attr = [&](int vm) { return (col >= 0 && col < of->n_attr_cols) ? of->attr[(size_t)col * of->n + vm] : 0; };
+        int target = vm_attr(v);
+        std::map<int, int> freq;  // value id (0 = nil) -> count
+        for (int c = gr->cot_off[g]; c < gr->cot_off[g + 1]; c++) freq[gr->cot_attr_val[c]]++;
+        for (int pv : placed) freq[vm_attr(pv)]++;
+        if (kind == COOK_GROUP_BALANCED) {
+          if (!freq.empty()) {
+            auto it = freq.find(target);
+            if (it != freq.end()) {
+              int mn = std::numeric_limits<int>::max(), mx = 0;
+              for (auto& kv : freq) { mn = std::min(mn, kv.second); mx = std::max(mx, kv.second); }
+              if (gr->minimum[g] > (int)freq.size()) mn = 0;
+              if (!(mn == mx || it->second < mx)) return 0.0;
+            }
+          }
+        } else {  // attribute-equals
+          if (!freq.empty() && freq.find(target) == freq.end()) return 0.0;
+        }
+      }
+    }
+  }
+  // FENZO 4: cpuMemBinPacker = (cpuFit + memFit) / 2,
+  // xFit = (req + Σassigned-this-cycle + Σrunning) / (leaseTotal + Σrunning)
+  double rc = of->run_cpus ? of->run_cpus[v] : 0.0, rm = of->run_mem ? of->run_mem[v] : 0.0;
+  double cpu_fit = ((jb->cpus[j] + s.asg_cpus[v]) + rc) / (of->cpus[v] + rc);
+  double mem_fit = ((jb->mem[j] + s.asg_mem[v]) + rm) / (of->mem[v] + rm);
+  return (cpu_fit + mem_fit) / 2.0;
+}
+
+}  // namespace
+
+// M0: pending-jobs->considerable-jobs (scheduler.clj:729-762) =
+// filter-based-on-user-quota (tools.clj:903-915) -> ratelimit (:940-959) ->
+// filter-based-on-pool-quota (:917-933) -> allowed -> launch plugin -> take N.
+int32_t oracle_considerable(const int32_t* ranked_idx, int32_t n_ranked,
+                            const cook_jobs_soa* jobs, const cook_user_table* users,
+                            const cook_pool_quota* pool_quota,
+                            const cook_match_params* params, int32_t* out_considerable,
+                            int32_t* out_n) {
+  const int U = users->n_users;
+  std::vector<Usage> usage(U);
+  Usage pool_usage;  // tools.clj:969 (reduce (partial merge-with +) (vals user->usage))
+  for (int u = 0; u < U; u++) {
+    if (users->usage_count) {
+      usage[u].count = users->usage_count[u]; usage[u].cpus = users->usage_cpus[u];
+      usage[u].mem = users->usage_mem[u]; usage[u].gpus = users->usage_gpus[u];
+    }
+    pool_usage.count = pool_usage.count + usage[u].count;
+    pool_usage.cpus = pool_usage.cpus + usage[u].cpus;
+    pool_usage.mem = pool_usage.mem + usage[u].mem;
+    pool_usage.gpus = pool_usage.gpus + usage[u].gpus;
+  }
+  std::vector<int> seen(U, 0);
+  int n = 0;
+  for (int i = 0; i < n_ranked && n < params->num_considerable; i++) {
+    int j = ranked_idx[i];
+    if (j < 0 || j >= jobs->n) return COOK_E_BADARG;
+    int u = jobs->user[j];
+    double g = jobs->gpus ? jobs->gpus[j] : 0.0;
+    // user quota: state advances whether or not the job is kept
+    add_usage(usage[u], jobs->cpus[j], jobs->mem[j], g);
+    if (!below_quota(users->quota_count[u], users->quota_cpus[u], users->quota_mem[u],
+                     users->quota_gpus[u], usage[u]))
+      continue;
+    // launch-rate limit: k-th surviving job of the user passes iff k <= tokens
+    seen[u]++;
+    bool limited = users->tokens ? (seen[u] > users->tokens[u]) : false;
+    if (limited && params->enforce_rate_limit) continue;
+    // pool quota over survivors
+    if (pool_quota && pool_quota->enabled) {
+      add_usage(pool_usage, jobs->cpus[j], jobs->mem[j], g);
+      if (!below_quota(pool_quota, pool_usage)) continue;
+    }
+    if (jobs->allowed && !jobs->allowed[j]) continue;
+    if (jobs->plugin_accept && !jobs->plugin_accept[j]) continue;
+    out_considerable[n++] = j;
+  }
+  *out_n = n;
+  return COOK_OK;
+}
+
+// ---------------------------------------------------------------------------
+// FENZO restatement (com.netflix.fenzo/fenzo-core 0.10.0, project.clj:50; not
+// vendored in /root/reference).  Rules:
+//  F1 every hostname with a live lease is one assignable VM; available = Σ leases.
+//  F3 for each request IN LIST ORDER every VM is tried: resource fit against
+//     (available - assigned this cycle), then hard constraints, then fitness;
+//     fitness == 0.0 is a failure.
+//  F4 cpuMemBinPacker (config.clj:108).
+//  F5 good-enough-fitness >= 1.0 (zz_simulator.clj:84) => all VMs evaluated,
+//     winner = max fitness; equal fitness => LOWEST hostname (OUR fixed
+//     tie-break; Fenzo's is hash-order, unspecified).
+//  F6 on success the VM's assigned cpus/mem/ports/count advance; ports are the
+//     first n free ports scanning ranges in lease order.
+// ---------------------------------------------------------------------------
+int32_t oracle_match(const int32_t* ranked_idx, int32_t n_ranked, const cook_jobs_soa* jobs,
+                     const cook_offers_soa* offers, const cook_groups* groups,
+                     const cook_user_table* users, const cook_pool_quota* pool_quota,
+                     const cook_match_params* params, int32_t* out_considerable,
+                     int32_t* out_assign, int32_t* out_ports, int32_t max_ports,
+                     uint8_t* out_fail_reason, cook_match_stats* st) {
+  if (!ranked_idx || !jobs || !offers || !users || !params || !out_considerable || !out_assign)
+    return COOK_E_BADARG;
+  if (params->good_enough_fitness < 1.0) return COOK_E_BADARG;
+  if (params->fitness_kind != 0) return COOK_E_UNSUPPORTED_CONSTRAINT;
+  int32_t nc = 0;
+  int32_t rc = oracle_considerable(ranked_idx, n_ranked, jobs, users, pool_quota, params,
+                                   out_considerable, &nc);
+  if (rc != COOK_OK) return rc;
+  const int O = offers->n;
+  MatchState s;
+  s.jobs = jobs; s.of = offers; s.groups = groups; s.prm = params;
+  s.asg_cpus.assign(O, 0.0); s.asg_mem.assign(O, 0.0);
+  s.asg_count.assign(O, 0); s.ports_used.assign(O, 0); s.ports_total.assign(O, 0);
+  if (offers->port_off)
+    for (int v = 0; v < O; v++)
+      for (int k = offers->port_off[v]; k < offers->port_off[v + 1]; k++)
+        s.ports_total[v] += offers->port_end[k] - offers->port_begin[k] + 1;
+  if (groups) s.group_vms.resize(groups->n_groups);
+  int n_matched = 0;
+  for (int k = 0; k < nc; k++) {
+    int j = out_considerable[k];
+    int best = -1;
+    double best_fit = 0.0;
+    bool any_res_ok = false;
+    for (int v = 0; v < O; v++) {
+      bool res_fail;
+      double f = eval_pair(s, j, v, &res_fail);
+      if (!res_fail) any_res_ok = true;
+      if (f == 0.0) continue;  // FENZO 3c
+      if (best < 0 || f > best_fit ||
+          (f == best_fit && offers->name_rank[v] < offers->name_rank[best])) {
+        best = v; best_fit = f;
+      }
+    }
+    out_assign[k] = best;
+    if (out_fail_reason)
+      out_fail_reason[k] = best >= 0 ? COOK_FAIL_NONE
+                           : (O == 0 ? COOK_FAIL_NO_OFFERS
+                                     : (any_res_ok ? COOK_FAIL_CONSTRAINT : COOK_FAIL_RESOURCES));
+    if (best >= 0) {
+      n_matched++;
+      s.asg_cpus[best] = s.asg_cpus[best] + jobs->cpus[j];
+      s.asg_mem[best] = s.asg_mem[best] + jobs->mem[j];
+      s.asg_count[best]++;
+      int want = jobs->ports ? jobs->ports[j] : 0;
+      if (out_ports && max_ports > 0)
+        for (int p = 0; p < max_ports; p++) out_ports[(size_t)k * max_ports + p] = -1;
+      if (want > 0) {  // FENZO F6
+        int skip = s.ports_used[best], got = 0;
+        for (int r = offers->port_off[best]; r < offers->port_off[best + 1] && got < want; r++) {
+          int len = offers->port_end[r] - offers->port_begin[r] + 1;
+          if (skip >= len) { skip -= len; continue; }
+          for (int p = offers->port_begin[r] + skip; p <= offers->port_end[r] && got < want; p++) {
+            if (out_ports && got < max_ports) out_ports[(size_t)k * max_ports + got] = p;
+            got++;
+          }
+          skip = 0;
+        }
+        s.ports_used[best] += want;
+      }
+      if (jobs->group_off && groups)
+        for (int g = jobs->group_off[j]; g < jobs->group_off[j + 1]; g++)
+          s.group_vms[jobs->group_idx[g]].push_back(best);
+    } else if (out_ports && max_ports > 0) {
+      for (int p = 0; p < max_ports; p++) out_ports[(size_t)k * max_ports + p] = -1;
+    }
+  }
+  if (st) {
+    std::memset(st, 0, sizeof(*st));
+    st->n_considerable = nc;
+    st->n_matched = n_matched;
+    st->head_matched = (nc > 0 && out_assign[0] >= 0) ? 1 : 0;
+    int used = 0;
+    for (int v = 0; v < O; v++) used += s.asg_count[v] > 0;
+    st->n_offers_used = used;
+    st->evals = (int64_t)nc * O;
+  }
+  return COOK_OK;
+}
+
+}  // extern "C"
