@@ -1,0 +1,105 @@
+// common.cuh — handles, error plumbing and the device arena of libcookgpu.so.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/cook_gpu.h"
+
+struct cook_ctx {
+  std::vector<int> devices;
+};
+
+// Grow-only device arena: one cudaMalloc per high-water mark, carved per call.
+struct Arena {
+  char* base = nullptr;
+  size_t cap = 0, off = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (base) cudaFree(base);
+    base = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 4 + (1 << 20);
+    cudaError_t e = cudaMalloc(&base, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void reset() { off = 0; }
+  template <class T>
+  T* take(size_t n) {
+    size_t bytes = (n * sizeof(T) + 255) & ~size_t(255);
+    if (off + bytes > cap) return nullptr;
+    T* p = reinterpret_cast<T*>(base + off);
+    off += bytes;
+    return p;
+  }
+  void release() {
+    if (base) cudaFree(base);
+    base = nullptr;
+    cap = off = 0;
+  }
+};
+
+// Sizing pass helper: mirrors Arena::take without memory.
+struct Sizer {
+  size_t off = 0;
+  template <class T>
+  void add(size_t n) { off += (n * sizeof(T) + 255) & ~size_t(255); }
+};
+
+struct cook_pool {
+  cook_ctx* ctx = nullptr;
+  std::string name;
+  int dru_mode = 0;
+  int device = 0;
+  int sm_count = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[8] = {};
+  Arena arena;
+  void* pinned = nullptr;  // small pinned scratch for result scalars
+  size_t pinned_cap = 0;
+  char err[512] = {0};
+};
+
+inline int32_t set_err(cook_pool* p, int32_t code, const char* fmt, ...) {
+  if (p) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(p->err, sizeof(p->err), fmt, ap);
+    va_end(ap);
+  }
+  return code;
+}
+
+#define CK(pool, call)                                                                    \
+  do {                                                                                    \
+    cudaError_t _e = (call);                                                              \
+    if (_e != cudaSuccess)                                                                \
+      return set_err(pool, _e == cudaErrorMemoryAllocation ? COOK_E_OOM : COOK_E_CUDA,   \
+                     "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(_e)); \
+  } while (0)
+
+// Upload a host column (may be NULL => returns nullptr without copying).
+template <class T>
+inline cudaError_t upload(Arena& a, cudaStream_t s, const T* host, size_t n, T** out) {
+  *out = nullptr;
+  if (!host || n == 0) {
+    if (host) *out = a.take<T>(1);
+    return cudaSuccess;
+  }
+  T* d = a.take<T>(n);
+  if (!d) return cudaErrorMemoryAllocation;
+  *out = d;
+  return cudaMemcpyAsync(d, host, n * sizeof(T), cudaMemcpyHostToDevice, s);
+}
+
+inline float ev_ms(cudaEvent_t a, cudaEvent_t b) {
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, a, b);
+  return ms;
+}

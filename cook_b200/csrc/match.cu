@@ -1,0 +1,1059 @@
+// match.cu — considerable-job filter (M0) and the exact greedy best-fit matcher
+// (M3/M4) on the GPU.  Replaces pending-jobs->considerable-jobs
+// (scheduler/scheduler.clj:729-762, tools.clj:903-973) and Fenzo's
+// TaskScheduler.scheduleOnce as Cook calls it (scheduler.clj:665-671) with
+// good-enough-fitness >= 1.0 (every VM evaluated for every task).
+//
+// Exactness on a parallel machine.  Fenzo places requests one at a
+// time; each placement mutates one VM and may change every later argmax.  The
+// kernel keeps that order but splits the work:
+//
+//   evaluators (all CTAs but #0): for a block of B jobs, one warp per job scans
+//     ALL offers against a SNAPSHOT of the dynamic VM state and keeps, per lane
+//     (= chunk of offers v == lane mod 32), the best two (fitness, v) pairs.
+//   resolver (warp 0 of CTA 0): walks the jobs in rank order.  VMs touched since
+//     the snapshot ("dirty", <= 2B of them, state in shared memory) are
+//     re-evaluated exactly; every other VM is unchanged, so the row's best
+//     clean candidate per chunk is still exact.  If a chunk's two candidates
+//     are both dirty, its remaining VMs are bounded above by the second
+//     candidate's fitness; the chunk is re-scanned only when that bound could
+//     beat the winner.  Jobs whose constraints depend on same-cycle placements
+//     of other jobs (groups) take a full re-scan against current state.
+//
+//   The two roles are software-pipelined: while the resolver places block t the
+//   evaluators score block t+1 against the state published after block t-1
+//   (double-buffered), one grid barrier per block.
+//
+// Tie-break: equal fitness => lowest hostname (offers are index-sorted by
+// name_rank on upload, so "lowest v").  All f64 ops are IEEE (div.rn.f64,
+// -fmad=false): identical to oracle/cook_oracle.cpp eval_pair bit for bit.
+#include <cooperative_groups.h>
+
+#include <algorithm>
+#include <numeric>
+
+#include "common.cuh"
+#include "sort.cuh"
+
+namespace {
+
+constexpr int RES_THREADS = 256;   // threads per CTA of the match kernel
+constexpr int MAXB = 256;          // max jobs per block
+constexpr int MAXD = 2 * MAXB;     // dirty list capacity (two blocks)
+
+struct JobDev {   // columns in ORIGINAL job index space (may be null)
+  const int32_t* user;
+  const double* cpus;
+  const double* mem;
+  const double* gpus;
+  const int32_t* ports;
+  const uint8_t* allowed;
+  const uint8_t* plugin;
+  const int32_t* novel_off; const int32_t* novel_host;
+  const int32_t* gpu_model;
+  const double* disk_request; const int32_t* disk_type;
+  const int32_t* attr_off; const int32_t* attr_col; const int32_t* attr_val;
+  const int64_t* est_end_ms;
+  const int32_t* ckpt_location;
+  const int32_t* reserved_host;
+  const int32_t* group_off; const int32_t* group_idx;
+};
+
+struct OfferDev {
+  int O;
+  // hot columns, gathered into rank-sorted index space v
+  const double *lease_c, *lease_m, *run_c, *run_m;
+  const int32_t* perm;  // v -> original offer index
+  // constraint columns, ORIGINAL index space (may be null)
+  const int32_t* hostname_id;
+  const int32_t* run_count;
+  const int32_t* ports_total;  // computed on device; null when no ports
+  const int32_t* port_off; const int32_t* port_begin; const int32_t* port_end;
+  const uint8_t* is_k8s;
+  const int32_t* location;
+  const int32_t* gpu_off; const int32_t* gpu_model; const double* gpu_count;
+  const int32_t* disk_off; const int32_t* disk_type; const double* disk_space;
+  const int32_t* max_tasks; const int32_t* num_tasks;
+  const int64_t* host_start;
+  int n_attr_cols; const int32_t* attr;
+  const uint8_t* reserved;
+};
+
+struct GroupDev {
+  int n_groups;
+  const int32_t* kind; const int32_t* attr_col; const int32_t* minimum;
+  const int32_t* cot_off; const int32_t* cot_host; const int32_t* cot_attr;
+  const int32_t* gp_off;  // capacity offsets of per-group placed lists
+  int32_t* gp_n;          // dynamic count per group
+  int32_t* gp_vm;         // placed VM (v space)
+};
+
+struct DynBuf {  // dynamic per-VM state, index space v, double buffered
+  double* asg_c[2];
+  double* asg_m[2];
+  int32_t* asg_n[2];
+  int32_t* ports_used[2];
+};
+
+struct MatchArgs {
+  JobDev jb;
+  OfferDev of;
+  GroupDev gr;
+  DynBuf dyn;
+  int n_cons;
+  const int32_t* cons;     // k -> job index
+  const double* kc;        // gathered cpus per k
+  const double* km;        // gathered mem per k
+  const uint8_t* kflags;   // bit0: has groups
+  int B;                   // jobs per block
+  int host_lifetime_mins;
+  double* row_f;           // [2][B][2][32]
+  int32_t* row_v;          // [2][B][2][32]
+  int32_t* assign;         // [n_cons] v (rank space) or -1
+  int32_t* ports_start;    // [n_cons] ports_used of the VM before assignment
+  uint8_t* fail;           // [n_cons]
+  unsigned* barrier;       // grid barrier counter
+  unsigned long long* stats;  // [0]=fast [1]=chunk rescans [2]=full rescans [3]=matched [4]=offers used
+};
+
+// ------------------------------------------------------------------ helpers
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// One barrier per pipeline slot.  Monotonic counter: epoch e completes when
+// counter == e * gridDim.x.  All CTAs are co-resident (cooperative launch).
+__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& epoch) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    epoch++;
+    __threadfence();
+    atomicAdd(counter, 1u);
+    const unsigned target = epoch * gridDim.x;
+    while (ld_acquire_u32(counter) < target) __nanosleep(64);
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+struct JobRegs {  // per-job values the hot loop keeps in registers
+  double c, m, g;
+  int j, ports;
+};
+
+template <bool CONSTR>
+__device__ __forceinline__ JobRegs load_job(const MatchArgs& a, int k) {
+  JobRegs r;
+  r.c = a.kc[k]; r.m = a.km[k];
+  r.j = a.cons[k];
+  r.g = 0.0; r.ports = 0;
+  if (CONSTR) {
+    r.g = a.jb.gpus ? a.jb.gpus[r.j] : 0.0;
+    r.ports = a.jb.ports ? a.jb.ports[r.j] : 0;
+  }
+  return r;
+}
+
+__device__ __forceinline__ double csr_lookup(const int32_t* off, const int32_t* key,
+                                             const double* val, int o, int k) {
+  if (!off) return 0.0;
+  for (int i = off[o]; i < off[o + 1]; i++)
+    if (key[i] == k) return val[i];
+  return 0.0;
+}
+
+// Static + count-dependent hard constraints of one (job, VM) pair, in Cook's
+// evaluation order (see oracle eval_pair; constraints.clj).  Group constraints
+// are handled by group_pass().  `an` = tasks assigned to the VM this cycle.
+__device__ bool constraints_pass(const MatchArgs& a, const JobRegs& r, int v, int an) {
+  const JobDev& jb = a.jb;
+  const OfferDev& of = a.of;
+  const int o = of.perm[v];
+  const int j = r.j;
+  if (jb.ckpt_location && jb.ckpt_location[j] >= 0) {
+    int loc = of.location ? of.location[o] : -1;
+    if (loc != jb.ckpt_location[j]) return false;
+  }
+  if (jb.est_end_ms && jb.est_end_ms[j] >= 0 && of.host_start && of.host_start[o] >= 0) {
+    long long death = 1000LL * of.host_start[o] + 60000LL * a.host_lifetime_mins;
+    if (!(jb.est_end_ms[j] < death)) return false;
+  }
+  if (jb.attr_off) {
+    for (int k = jb.attr_off[j]; k < jb.attr_off[j + 1]; k++) {
+      int col = jb.attr_col[k], val = jb.attr_val[k];
+      if (col < 0 || col >= of.n_attr_cols) return false;
+      int hv = of.attr[(size_t)col * of.O + o];
+      if (val <= 0 || hv != val) return false;
+    }
+  }
+  const bool k8s = of.is_k8s && of.is_k8s[o];
+  if (jb.disk_request && jb.disk_request[j] >= 0.0 && k8s) {
+    double space = csr_lookup(of.disk_off, of.disk_type, of.disk_space, o,
+                              jb.disk_type ? jb.disk_type[j] : -1);
+    if (!(space >= jb.disk_request[j])) return false;
+  }
+  if (k8s) {
+    if (r.g > 0.0) {
+      double have = csr_lookup(of.gpu_off, of.gpu_model, of.gpu_count, o,
+                               jb.gpu_model ? jb.gpu_model[j] : -1);
+      int on_vm = (of.run_count ? of.run_count[o] : 0) + an;
+      if (!(have == r.g && on_vm == 0)) return false;
+    } else {
+      int nmodels = of.gpu_off ? of.gpu_off[o + 1] - of.gpu_off[o] : 0;
+      if (nmodels != 0) return false;
+    }
+  } else if (!(r.g == 0.0)) {
+    return false;
+  }
+  if (jb.novel_off) {
+    int h = of.hostname_id[o];
+    for (int k = jb.novel_off[j]; k < jb.novel_off[j + 1]; k++)
+      if (jb.novel_host[k] == h) return false;
+  }
+  if (of.max_tasks && of.max_tasks[o] >= 0) {
+    int total = (of.num_tasks ? of.num_tasks[o] : 0) + an;
+    if (!(total < of.max_tasks[o])) return false;
+  }
+  if (of.reserved && of.reserved[o]) {
+    int mine = jb.reserved_host ? jb.reserved_host[j] : -1;
+    if (mine != of.hostname_id[o]) return false;
+  }
+  return true;
+}
+
+__device__ __forceinline__ int vm_attr(const OfferDev& of, int col, int v) {
+  return (col >= 0 && col < of.n_attr_cols) ? of.attr[(size_t)col * of.O + of.perm[v]] : 0;
+}
+
+// Group constraints (constraints.clj:586-678) against the CURRENT group state
+// (running cotasks known to Fenzo + cotasks placed earlier in this cycle).
+__device__ bool group_pass(const MatchArgs& a, const JobRegs& r, int v) {
+  const JobDev& jb = a.jb;
+  const GroupDev& gr = a.gr;
+  const OfferDev& of = a.of;
+  for (int k = jb.group_off[r.j]; k < jb.group_off[r.j + 1]; k++) {
+    const int g = jb.group_idx[k];
+    const int kind = gr.kind[g];
+    const int c0 = gr.cot_off[g], c1 = gr.cot_off[g + 1];
+    const int p0 = gr.gp_off[g], pn = __ldcg(gr.gp_n + g);
+    if (kind == COOK_GROUP_UNIQUE) {
+      const int h = of.hostname_id[of.perm[v]];
+      for (int c = c0; c < c1; c++)
+        if (gr.cot_host[c] == h) return false;
+      for (int p = 0; p < pn; p++)
+        if (__ldcg(gr.gp_vm + p0 + p) == v) return false;
+    } else {
+      const int col = gr.attr_col[g];
+      const int target = vm_attr(of, col, v);
+      const int n = (c1 - c0) + pn;
+      if (n == 0) continue;
+      auto val_at = [&](int i) { return i < c1 - c0 ? gr.cot_attr[c0 + i] : vm_attr(of, col, __ldcg(gr.gp_vm + p0 + i - (c1 - c0))); };
+      int tf = 0;
+      for (int i = 0; i < n; i++) tf += (val_at(i) == target);
+      if (kind == COOK_GROUP_ATTR_EQUALS) {
+        if (tf == 0) return false;
+      } else {  // balanced
+        if (tf == 0) continue;  // (nil? target-freq) => passes
+        int mn = 0x7fffffff, mx = 0, distinct = 0;
+        for (int i = 0; i < n; i++) {
+          int vi = val_at(i), f = 0;
+          bool first = true;
+          for (int q = 0; q < n; q++) {
+            int vq = val_at(q);
+            if (vq == vi) { f++; if (q < i) first = false; }
+          }
+          if (first) { distinct++; mn = min(mn, f); mx = max(mx, f); }
+        }
+        if (gr.minimum[g] > distinct) mn = 0;
+        if (!(mn == mx || tf < mx)) return false;
+      }
+    }
+  }
+  return true;
+}
+
+// FENZO 3a + 4 (see oracle): resource fit then cpuMemBinPacker fitness.
+__device__ __forceinline__ double fit_fitness(double jc, double jm, double ac, double am,
+                                              double lc, double lm, double rc, double rm) {
+  if (ac + jc > lc) return 0.0;
+  if (am + jm > lm) return 0.0;
+  double cpu_fit = ((jc + ac) + rc) / (lc + rc);
+  double mem_fit = ((jm + am) + rm) / (lm + rm);
+  return (cpu_fit + mem_fit) / 2.0;
+}
+
+// Full evaluation of (job, VM v) with explicit dynamic state.
+template <bool CONSTR>
+__device__ __forceinline__ double eval_vm(const MatchArgs& a, const JobRegs& r, int v, double ac,
+                                          double am, int an, int pu, double lc, double lm,
+                                          double rc, double rm, bool with_groups) {
+  if (CONSTR) {
+    if (ac + r.c > lc) return 0.0;
+    if (am + r.m > lm) return 0.0;
+    if (r.ports > 0) {
+      int tot = a.of.ports_total ? a.of.ports_total[a.of.perm[v]] : 0;
+      if (r.ports > tot - pu) return 0.0;
+    }
+    if (!constraints_pass(a, r, v, an)) return 0.0;
+    if (with_groups && !group_pass(a, r, v)) return 0.0;
+  }
+  return fit_fitness(r.c, r.m, ac, am, lc, lm, rc, rm);
+}
+
+// ------------------------------------------------------------- evaluators
+template <bool CONSTR>
+__device__ void evaluate_block(const MatchArgs& a, int blk, int snap, int warp_id, int n_warps) {
+  const int lane = threadIdx.x & 31;
+  const int k0 = blk * a.B;
+  const int k1 = min(k0 + a.B, a.n_cons);
+  const int par = blk & 1;
+  const double* asg_c = a.dyn.asg_c[snap];
+  const double* asg_m = a.dyn.asg_m[snap];
+  const int32_t* asg_n = a.dyn.asg_n[snap];
+  const int32_t* pus = a.dyn.ports_used[snap];
+  for (int k = k0 + warp_id; k < k1; k += n_warps) {
+    double f1 = 0.0, f2 = 0.0;
+    int v1 = -1, v2 = -1;
+    const bool grp = CONSTR && (a.kflags[k] & 1);
+    if (!grp) {
+      JobRegs r = load_job<CONSTR>(a, k);
+#pragma unroll 2
+      for (int v = lane; v < a.of.O; v += 32) {
+        double f = eval_vm<CONSTR>(a, r, v, __ldcg(asg_c + v), __ldcg(asg_m + v),
+                                   CONSTR ? __ldcg(asg_n + v) : 0, CONSTR ? __ldcg(pus + v) : 0,
+                                   __ldg(a.of.lease_c + v), __ldg(a.of.lease_m + v),
+                                   __ldg(a.of.run_c + v), __ldg(a.of.run_m + v), false);
+        if (f > f1) { f2 = f1; v2 = v1; f1 = f; v1 = v; }
+        else if (f > f2) { f2 = f; v2 = v; }
+      }
+    }
+    const size_t base = ((size_t)par * a.B + (k - k0)) * 64;
+    a.row_f[base + lane] = f1;
+    a.row_f[base + 32 + lane] = f2;
+    a.row_v[base + lane] = v1;
+    a.row_v[base + 32 + lane] = v2;
+  }
+}
+
+// --------------------------------------------------------------- resolver
+struct ResolverShared {
+  double d_ac[MAXD], d_am[MAXD];
+  double d_lc[MAXD], d_lm[MAXD], d_rc[MAXD], d_rm[MAXD];
+  int32_t d_vm[MAXD], d_an[MAXD], d_pu[MAXD], d_touch[MAXD];
+};
+
+__device__ __forceinline__ double warp_max_f64(double f) {  // f >= 0
+  unsigned hi = (unsigned)__double2hiint(f);
+  unsigned mh = __reduce_max_sync(0xffffffffu, hi);
+  unsigned lo = hi == mh ? (unsigned)__double2loint(f) : 0u;
+  unsigned ml = __reduce_max_sync(0xffffffffu, lo);
+  return __hiloint2double((int)mh, (int)ml);
+}
+
+template <bool CONSTR>
+__device__ void resolve_block(const MatchArgs& a, int blk, ResolverShared& S, unsigned* bitmap,
+                              int& nD, unsigned long long* lstats) {
+  const int lane = threadIdx.x & 31;
+  const int k0 = blk * a.B;
+  const int k1 = min(k0 + a.B, a.n_cons);
+  const int par = blk & 1;
+  const int snap = blk & 1;  // rows of block t were scored (in slot t-1) against S_{t-2} = buffer (t-2)&1
+  const double* s_asg_c = a.dyn.asg_c[snap];
+  const double* s_asg_m = a.dyn.asg_m[snap];
+  const int32_t* s_asg_n = a.dyn.asg_n[snap];
+  const int32_t* s_pus = a.dyn.ports_used[snap];
+
+  // drop dirty entries not touched in the previous block: they are part of the
+  // snapshot this block's rows were scored against.
+  {
+    int keep_n = 0;
+    for (int base = 0; base < nD; base += 32) {
+      int d = base + lane;
+      bool keep = d < nD && S.d_touch[d] >= blk - 1;
+      unsigned kb = __ballot_sync(0xffffffffu, keep);
+      int vm = 0, an = 0, pu = 0, tc = 0; double ac = 0, am = 0, lc = 0, lm = 0, rc = 0, rm = 0;
+      if (d < nD) {
+        vm = S.d_vm[d]; an = S.d_an[d]; pu = S.d_pu[d]; tc = S.d_touch[d];
+        ac = S.d_ac[d]; am = S.d_am[d]; lc = S.d_lc[d]; lm = S.d_lm[d]; rc = S.d_rc[d]; rm = S.d_rm[d];
+        if (!keep) atomicAnd(&bitmap[vm >> 5], ~(1u << (vm & 31)));
+      }
+      __syncwarp();
+      if (keep) {
+        int t = keep_n + __popc(kb & ((1u << lane) - 1u));
+        S.d_vm[t] = vm; S.d_an[t] = an; S.d_pu[t] = pu; S.d_touch[t] = tc;
+        S.d_ac[t] = ac; S.d_am[t] = am; S.d_lc[t] = lc; S.d_lm[t] = lm; S.d_rc[t] = rc; S.d_rm[t] = rm;
+      }
+      keep_n += __popc(kb);
+      __syncwarp();
+    }
+    nD = keep_n;
+  }
+
+  for (int k = k0; k < k1; k++) {
+    const size_t base = ((size_t)par * a.B + (k - k0)) * 64;
+    const double f1 = __ldcg(a.row_f + base + lane), f2 = __ldcg(a.row_f + base + 32 + lane);
+    const int v1 = __ldcg(a.row_v + base + lane), v2 = __ldcg(a.row_v + base + 32 + lane);
+    const JobRegs r = load_job<CONSTR>(a, k);
+    const bool grp = CONSTR && (a.kflags[k] & 1);
+
+    double cf = 0.0, bound = 0.0;
+    int cv = 0x7fffffff, cslot = -1;
+    if (!grp) {
+      if (__ballot_sync(0xffffffffu, f1 > 0.0) == 0u) {
+        // nothing fit at the snapshot; resources/constraints only tighten
+        // within a cycle for non-group jobs => unplaceable now too.
+        if (lane == 0) { a.assign[k] = -1; a.fail[k] = COOK_FAIL_RESOURCES; }
+        lstats[0]++;
+        continue;
+      }
+      if (f1 > 0.0) {
+        if (!((bitmap[v1 >> 5] >> (v1 & 31)) & 1u)) { cf = f1; cv = v1; }
+        else if (f2 > 0.0) {
+          if (!((bitmap[v2 >> 5] >> (v2 & 31)) & 1u)) { cf = f2; cv = v2; }
+          else bound = f2;
+        }
+      }
+    }
+    // exact re-evaluation of dirty VMs against their current state
+    for (int d = lane; d < nD; d += 32) {
+      double f = eval_vm<CONSTR>(a, r, S.d_vm[d], S.d_ac[d], S.d_am[d], S.d_an[d], S.d_pu[d],
+                                 S.d_lc[d], S.d_lm[d], S.d_rc[d], S.d_rm[d], grp);
+      int v = S.d_vm[d];
+      if (f > cf || (f == cf && f > 0.0 && v < cv)) { cf = f; cv = v; cslot = d; }
+    }
+    bool did_rescan = false;
+    if (grp) {
+      // full re-scan of clean VMs against current group state
+      for (int v = lane; v < a.of.O; v += 32) {
+        if ((bitmap[v >> 5] >> (v & 31)) & 1u) continue;
+        double f = eval_vm<CONSTR>(a, r, v, __ldcg(s_asg_c + v), __ldcg(s_asg_m + v),
+                                   CONSTR ? __ldcg(s_asg_n + v) : 0, CONSTR ? __ldcg(s_pus + v) : 0,
+                                   a.of.lease_c[v], a.of.lease_m[v], a.of.run_c[v], a.of.run_m[v], true);
+        if (f > cf || (f == cf && f > 0.0 && v < cv)) { cf = f; cv = v; cslot = -1; }
+      }
+      lstats[2]++;
+    } else {
+      double wf0 = warp_max_f64(cf);
+      double mb = warp_max_f64(bound);
+      if (mb > 0.0 && mb >= wf0) {
+        unsigned need = __ballot_sync(0xffffffffu, bound > 0.0 && bound >= wf0);
+        did_rescan = true;
+        while (need) {
+          int c = __ffs(need) - 1;
+          need &= need - 1;
+          for (int v = c + 32 * lane; v < a.of.O; v += 32 * 32) {
+            if ((bitmap[v >> 5] >> (v & 31)) & 1u) continue;
+            double f = eval_vm<CONSTR>(a, r, v, __ldcg(s_asg_c + v), __ldcg(s_asg_m + v),
+                                       CONSTR ? __ldcg(s_asg_n + v) : 0, CONSTR ? __ldcg(s_pus + v) : 0,
+                                       a.of.lease_c[v], a.of.lease_m[v], a.of.run_c[v], a.of.run_m[v],
+                                       false);
+            if (f > cf || (f == cf && f > 0.0 && v < cv)) { cf = f; cv = v; cslot = -1; }
+          }
+          lstats[1]++;
+        }
+      }
+    }
+    // argmax over lanes: max fitness, then lowest v
+    const double wf = warp_max_f64(cf);
+    int wv = -1;
+    if (wf > 0.0) {
+      unsigned key = (cf == wf) ? (unsigned)cv : 0xffffffffu;
+      unsigned mv = __reduce_min_sync(0xffffffffu, key);
+      wv = (int)mv;
+      const int wl = __ffs(__ballot_sync(0xffffffffu, key == mv)) - 1;
+      int slot = __shfl_sync(0xffffffffu, cslot, wl);
+      // commit (all lanes hold identical values; lane 0 writes)
+      if (slot < 0) {
+        slot = nD;
+        if (lane == 0) {
+          S.d_vm[slot] = wv;
+          S.d_ac[slot] = __ldcg(s_asg_c + wv); S.d_am[slot] = __ldcg(s_asg_m + wv);
+          S.d_an[slot] = CONSTR ? __ldcg(s_asg_n + wv) : 0; S.d_pu[slot] = CONSTR ? __ldcg(s_pus + wv) : 0;
+          S.d_lc[slot] = a.of.lease_c[wv]; S.d_lm[slot] = a.of.lease_m[wv];
+          S.d_rc[slot] = a.of.run_c[wv]; S.d_rm[slot] = a.of.run_m[wv];
+          bitmap[wv >> 5] |= 1u << (wv & 31);
+        }
+        nD++;
+      }
+      if (lane == 0) {
+        a.ports_start[k] = S.d_pu[slot];
+        S.d_ac[slot] = S.d_ac[slot] + r.c;
+        S.d_am[slot] = S.d_am[slot] + r.m;
+        S.d_an[slot] += 1;
+        S.d_pu[slot] += r.ports;
+        S.d_touch[slot] = blk;
+        a.assign[k] = wv;
+        a.fail[k] = COOK_FAIL_NONE;
+        if (CONSTR && grp) {
+          for (int q = a.jb.group_off[r.j]; q < a.jb.group_off[r.j + 1]; q++) {
+            int g = a.jb.group_idx[q];
+            int n = __ldcg(a.gr.gp_n + g);
+            a.gr.gp_vm[a.gr.gp_off[g] + n] = wv;
+            __threadfence_block();
+            a.gr.gp_n[g] = n + 1;
+          }
+        }
+      }
+      lstats[3]++;
+      __syncwarp();
+    } else {
+      if (lane == 0) { a.assign[k] = -1; a.fail[k] = COOK_FAIL_CONSTRAINT; }
+    }
+    if (!did_rescan && !grp) lstats[0]++;
+  }
+  // publish every dirty entry (touched in this or the previous block) into the
+  // buffer the evaluators read in the next slot.
+  {
+    const int pub = blk & 1;
+    for (int d = lane; d < nD; d += 32) {
+      int v = S.d_vm[d];
+      a.dyn.asg_c[pub][v] = S.d_ac[d];
+      a.dyn.asg_m[pub][v] = S.d_am[d];
+      a.dyn.asg_n[pub][v] = S.d_an[d];
+      a.dyn.ports_used[pub][v] = S.d_pu[d];
+    }
+  }
+  __syncwarp();
+}
+
+// Pipeline: slot t in [-1, nblk): resolver places block t (rows scored against
+// buffer (t-2)&1 == t&1 ... see below), evaluators score block t+1 against the
+// state published after block t-1, i.e. buffer (t-1)&1.
+template <bool CONSTR>
+__global__ void __launch_bounds__(RES_THREADS, 1) match_kernel(MatchArgs a) {
+  extern __shared__ unsigned char smem_raw[];
+  ResolverShared& S = *reinterpret_cast<ResolverShared*>(smem_raw);
+  unsigned* bitmap = reinterpret_cast<unsigned*>(smem_raw + sizeof(ResolverShared));
+  const int nblk = (a.n_cons + a.B - 1) / a.B;
+  unsigned epoch = 0;
+  int nD = 0;
+  unsigned long long lstats[4] = {0, 0, 0, 0};
+  const bool is_res = blockIdx.x == 0;
+  const int warps_per_cta = RES_THREADS / 32;
+  const int n_eval_warps = (gridDim.x - 1) * warps_per_cta;
+  const int eval_warp = (blockIdx.x - 1) * warps_per_cta + (threadIdx.x >> 5);
+  if (is_res) {
+    const int words = (a.of.O + 31) / 32;
+    for (int i = threadIdx.x; i < words; i += RES_THREADS) bitmap[i] = 0u;
+  }
+  __syncthreads();
+  for (int t = -1; t < nblk; t++) {
+    if (is_res) {
+      if (t >= 0 && threadIdx.x < 32) resolve_block<CONSTR>(a, t, S, bitmap, nD, lstats);
+    } else if (t + 1 < nblk) {
+      // rows of block t+1 are scored against S_{t-1} = buffer (t-1)&1 = (t+1)&1
+      evaluate_block<CONSTR>(a, t + 1, (t + 1) & 1, eval_warp, n_eval_warps);
+    }
+    grid_barrier(a.barrier, epoch);
+  }
+  if (is_res && threadIdx.x == 0) {
+    a.stats[0] = lstats[0]; a.stats[1] = lstats[1]; a.stats[2] = lstats[2]; a.stats[3] = lstats[3];
+  }
+}
+
+// ------------------------------------------------------------ considerable
+struct ConsArgs {
+  const int32_t* ranked; int n_ranked;
+  JobDev jb;
+  int n_users;
+  const double *q_count, *q_cpus, *q_mem, *q_gpus;
+  const double *u_count, *u_cpus, *u_mem, *u_gpus;
+  const int32_t* tokens;
+  int enforce_rate_limit;
+  cook_pool_quota pool_q;
+  int num_considerable;
+};
+
+struct LessUserPos {
+  const int32_t* ranked;
+  const int32_t* user;
+  __device__ bool operator()(int32_t a, int32_t b) const {
+    int ua = user[ranked[a]], ub = user[ranked[b]];
+    if (ua != ub) return ua < ub;
+    return a < b;
+  }
+};
+
+__global__ void iota_k(int32_t* p, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = i;
+}
+
+__global__ void cons_seg_kernel(const int32_t* pos_by_user, const int32_t* ranked,
+                                const int32_t* user, int n, int32_t* seg_start, int32_t* seg_end) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  int u = user[ranked[pos_by_user[p]]];
+  if (p == 0 || user[ranked[pos_by_user[p - 1]]] != u) seg_start[u] = p;
+  if (p == n - 1 || user[ranked[pos_by_user[p + 1]]] != u) seg_end[u] = p + 1;
+}
+
+// tools.clj:903-915 + :940-959: warp per user, lane-serial left fold over the
+// user's queued jobs in queue order, starting from the user's running usage.
+__global__ void __launch_bounds__(128) cons_user_kernel(ConsArgs a, const int32_t* pos_by_user,
+                                                        const int32_t* seg_start,
+                                                        const int32_t* seg_end, uint8_t* keep) {
+  const int u = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (u >= a.n_users) return;
+  const int s = seg_start[u], e = seg_end[u];
+  if (e <= s) return;
+  double an = a.u_count ? a.u_count[u] : 0.0, ac = a.u_cpus ? a.u_cpus[u] : 0.0;
+  double am = a.u_mem ? a.u_mem[u] : 0.0, ag = a.u_gpus ? a.u_gpus[u] : 0.0;
+  const double qn = a.q_count[u], qc = a.q_cpus[u], qm = a.q_mem[u], qg = a.q_gpus[u];
+  const int tokens = a.tokens ? a.tokens[u] : 0x7fffffff;
+  int seen = 0;
+  for (int base = s; base < e; base += 32) {
+    int p = base + lane;
+    double xc = 0, xm = 0, xg = 0;
+    int pos = -1;
+    if (p < e) {
+      pos = pos_by_user[p];
+      int j = a.ranked[pos];
+      xc = a.jb.cpus[j]; xm = a.jb.mem[j]; xg = a.jb.gpus ? a.jb.gpus[j] : 0.0;
+    }
+    double mc = 0, mm = 0, mg = 0, mn = 0;
+    int cntn = min(32, e - base);
+    for (int l = 0; l < cntn; l++) {
+      an = an + 1.0;
+      ac = ac + __shfl_sync(0xffffffffu, xc, l);
+      am = am + __shfl_sync(0xffffffffu, xm, l);
+      ag = ag + __shfl_sync(0xffffffffu, xg, l);
+      if (lane == l) { mn = an; mc = ac; mm = am; mg = ag; }
+    }
+    bool ok = (p < e) && (mn <= qn && mc <= qc && mm <= qm && mg <= qg);
+    unsigned ob = __ballot_sync(0xffffffffu, ok);
+    int kth = seen + __popc(ob & (0xffffffffu >> (31 - lane)));  // k-th surviving job of the user
+    bool limited = kth > tokens;
+    if (ok && limited && a.enforce_rate_limit) ok = false;
+    if (p < e) keep[pos] = ok ? 1 : 0;
+    seen += __popc(ob);
+  }
+}
+
+// Queue-order pass (single warp): pool quota over survivors (tools.clj:917-933),
+// allowed + launch-plugin masks (scheduler.clj:749-750), take N (:751);
+// gathers the per-k hot columns.
+__global__ void cons_queue_kernel(ConsArgs a, const uint8_t* keep, int32_t* cons, double* kc,
+                                  double* km, uint8_t* kflags, int32_t* out_n) {
+  const int lane = threadIdx.x;
+  double pn = 0, pc = 0, pm = 0, pg = 0;
+  if (a.pool_q.enabled) {  // (reduce (partial merge-with +) (vals user->usage)), tools.clj:969
+    for (int base = 0; base < a.n_users; base += 32) {
+      int u = base + lane;
+      double xn = (u < a.n_users && a.u_count) ? a.u_count[u] : 0.0;
+      double xc = (u < a.n_users && a.u_cpus) ? a.u_cpus[u] : 0.0;
+      double xm = (u < a.n_users && a.u_mem) ? a.u_mem[u] : 0.0;
+      double xg = (u < a.n_users && a.u_gpus) ? a.u_gpus[u] : 0.0;
+      int cntn = min(32, a.n_users - base);
+      for (int l = 0; l < cntn; l++) {
+        pn = pn + __shfl_sync(0xffffffffu, xn, l);
+        pc = pc + __shfl_sync(0xffffffffu, xc, l);
+        pm = pm + __shfl_sync(0xffffffffu, xm, l);
+        pg = pg + __shfl_sync(0xffffffffu, xg, l);
+      }
+    }
+  }
+  int n_out = 0;
+  for (int base = 0; base < a.n_ranked && n_out < a.num_considerable; base += 32) {
+    int i = base + lane;
+    bool k = i < a.n_ranked && keep[i];
+    int j = i < a.n_ranked ? a.ranked[i] : 0;
+    double xc = 0, xm = 0, xg = 0;
+    if (k) { xc = a.jb.cpus[j]; xm = a.jb.mem[j]; xg = a.jb.gpus ? a.jb.gpus[j] : 0.0; }
+    if (a.pool_q.enabled) {
+      unsigned mask = __ballot_sync(0xffffffffu, k);
+      double mc = 0, mm = 0, mg = 0, mn = 0;
+      while (mask) {
+        int l = __ffs(mask) - 1;
+        mask &= mask - 1;
+        pn = pn + 1.0;
+        pc = pc + __shfl_sync(0xffffffffu, xc, l);
+        pm = pm + __shfl_sync(0xffffffffu, xm, l);
+        pg = pg + __shfl_sync(0xffffffffu, xg, l);
+        if (lane == l) { mn = pn; mc = pc; mm = pm; mg = pg; }
+      }
+      if (k) k = mn <= a.pool_q.count && mc <= a.pool_q.cpus && mm <= a.pool_q.mem && mg <= a.pool_q.gpus;
+    }
+    if (k && a.jb.allowed && !a.jb.allowed[j]) k = false;
+    if (k && a.jb.plugin && !a.jb.plugin[j]) k = false;
+    unsigned kb = __ballot_sync(0xffffffffu, k);
+    int slot = n_out + __popc(kb & ((1u << lane) - 1u));
+    if (k && slot < a.num_considerable) {
+      cons[slot] = j;
+      kc[slot] = a.jb.cpus[j];
+      km[slot] = a.jb.mem[j];
+      uint8_t fl = 0;
+      if (a.jb.group_off && a.jb.group_off[j + 1] > a.jb.group_off[j]) fl |= 1;
+      kflags[slot] = fl;
+    }
+    n_out += __popc(kb);
+  }
+  if (lane == 0) *out_n = min(n_out, a.num_considerable);
+}
+
+// ------------------------------------------------------------------ setup
+__global__ void gather_offers_kernel(const int32_t* perm, int O, const double* c, const double* m,
+                                     const double* rc, const double* rm, double* oc, double* om,
+                                     double* orc, double* orm) {
+  int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= O) return;
+  int o = perm[v];
+  oc[v] = c[o]; om[v] = m[o];
+  orc[v] = rc ? rc[o] : 0.0; orm[v] = rm ? rm[o] : 0.0;
+}
+
+__global__ void ports_total_kernel(const int32_t* off, const int32_t* b, const int32_t* e, int O,
+                                   int32_t* total) {
+  int o = blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= O) return;
+  int t = 0;
+  for (int k = off[o]; k < off[o + 1]; k++) t += e[k] - b[k] + 1;
+  total[o] = t;
+}
+
+// assign (rank space) -> original offer index; assigned port numbers
+// (FENZO F6: first n free ports scanning ranges in lease order).
+__global__ void finalize_kernel(MatchArgs a, int32_t* out_assign, int32_t* out_ports, int max_ports,
+                                int32_t* used_flag) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= a.n_cons) return;
+  int v = a.assign[k];
+  int o = v >= 0 ? a.of.perm[v] : -1;
+  out_assign[k] = o;
+  if (v >= 0) used_flag[v] = 1;
+  if (out_ports && max_ports > 0) {
+    for (int p = 0; p < max_ports; p++) out_ports[(size_t)k * max_ports + p] = -1;
+    int want = (o >= 0 && a.jb.ports) ? a.jb.ports[a.cons[k]] : 0;
+    if (want > 0 && a.of.port_off) {
+      int skip = a.ports_start[k], got = 0;
+      for (int r = a.of.port_off[o]; r < a.of.port_off[o + 1] && got < want; r++) {
+        int len = a.of.port_end[r] - a.of.port_begin[r] + 1;
+        if (skip >= len) { skip -= len; continue; }
+        for (int p = a.of.port_begin[r] + skip; p <= a.of.port_end[r] && got < want; p++) {
+          if (got < max_ports) out_ports[(size_t)k * max_ports + got] = p;
+          got++;
+        }
+        skip = 0;
+      }
+    }
+  }
+}
+
+__global__ void count_flags_kernel(const int32_t* flags, int n, int32_t* out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int v = (i < n && flags[i]) ? 1 : 0;
+  unsigned b = __ballot_sync(0xffffffffu, v);
+  if ((threadIdx.x & 31) == 0 && b) atomicAdd(out, __popc(b));
+}
+
+}  // namespace
+
+#define UP(dst, src, n) CK(pool, upload(ar, st, (src), (size_t)(n), &(dst)))
+
+extern "C" int32_t cook_match(cook_pool* pool, const int32_t* ranked_idx, int32_t n_ranked,
+                              const cook_jobs_soa* jobs, const cook_offers_soa* offers,
+                              const cook_groups* groups, const cook_user_table* users,
+                              const cook_pool_quota* pool_quota, const cook_match_params* params,
+                              int32_t* out_considerable, int32_t* out_assign, int32_t* out_ports,
+                              int32_t max_ports, uint8_t* out_fail_reason,
+                              cook_match_stats* out_stats) {
+  if (!pool) return COOK_E_BADARG;
+  if (!ranked_idx || !jobs || !offers || !users || !params || !out_considerable || !out_assign)
+    return set_err(pool, COOK_E_BADARG, "cook_match: null argument");
+  if (params->good_enough_fitness < 1.0)
+    return set_err(pool, COOK_E_BADARG,
+                   "cook_match: good_enough_fitness < 1.0 is Fenzo's racy early-exit mode; "
+                   "only the deterministic mode (>= 1.0) is supported");
+  if (params->fitness_kind != 0)
+    return set_err(pool, COOK_E_UNSUPPORTED_CONSTRAINT, "cook_match: only cpuMemBinPacker");
+  const int J = jobs->n, O = offers->n, U = users->n_users;
+  const int NC = params->num_considerable;
+  if (J < 0 || O < 0 || U <= 0 || n_ranked < 0 || NC < 0)
+    return set_err(pool, COOK_E_BADARG, "cook_match: bad sizes");
+  if (out_stats) memset(out_stats, 0, sizeof(*out_stats));
+  if (n_ranked == 0 || NC == 0) return COOK_OK;
+  CK(pool, cudaSetDevice(pool->device));
+  cudaStream_t st = pool->stream;
+  Arena& ar = pool->arena;
+
+  // host-side prep: offers sorted by hostname rank (tie-break order)
+  std::vector<int32_t> perm(O);
+  std::iota(perm.begin(), perm.end(), 0);
+  std::sort(perm.begin(), perm.end(),
+            [&](int32_t x, int32_t y) { return offers->name_rank[x] < offers->name_rank[y]; });
+  // per-group capacity of the placed list = #member jobs
+  const int G = groups ? groups->n_groups : 0;
+  std::vector<int32_t> gp_off(G + 1, 0);
+  size_t n_memb = 0;
+  if (G && jobs->group_off) {
+    n_memb = jobs->group_off[J];
+    for (size_t i = 0; i < n_memb; i++) {
+      int g = jobs->group_idx[i];
+      if (g < 0 || g >= G) return set_err(pool, COOK_E_BADARG, "cook_match: bad group index");
+      gp_off[g + 1]++;
+    }
+    for (int g = 0; g < G; g++) gp_off[g + 1] += gp_off[g];
+  }
+  // The cpu+mem-only kernel is used when no constraint column can affect a
+  // placement (all-zero ports/gpus columns count as absent).
+  bool constr_eff = jobs->novel_off || jobs->gpu_model || jobs->disk_request || jobs->attr_off ||
+                    jobs->est_end_ms || jobs->ckpt_location || jobs->reserved_host ||
+                    (jobs->group_off && G) || offers->is_k8s || offers->max_tasks ||
+                    offers->reserved || offers->gpu_off;
+  if (!constr_eff && jobs->gpus)
+    for (int j = 0; j < J && !constr_eff; j++) constr_eff = jobs->gpus[j] != 0.0;
+  if (!constr_eff && jobs->ports)
+    for (int j = 0; j < J && !constr_eff; j++) constr_eff = jobs->ports[j] != 0;
+
+  const int B = std::min(MAXB, 128);
+  Sizer sz;
+  sz.add<int32_t>(n_ranked);
+  for (int k = 0; k < 3; k++) sz.add<double>(J + 1);
+  sz.add<int32_t>(J + 1); sz.add<int32_t>(J + 1);
+  sz.add<uint8_t>(J + 1); sz.add<uint8_t>(J + 1);
+  size_t csr_j = (jobs->novel_off ? jobs->novel_off[J] : 0) + 2 * (size_t)(jobs->attr_off ? jobs->attr_off[J] : 0) + n_memb;
+  sz.add<int32_t>(4 * (J + 2) + csr_j + 64);
+  sz.add<double>(J + 1); sz.add<int32_t>(3 * (J + 1)); sz.add<int64_t>(J + 1);
+  sz.add<int32_t>(O + 1);
+  for (int k = 0; k < 8; k++) sz.add<double>(O + 1);
+  sz.add<int32_t>(12 * (size_t)(O + 2));
+  size_t csr_o = (offers->port_off ? 2 * (size_t)offers->port_off[O] : 0) +
+                 (offers->gpu_off ? (size_t)offers->gpu_off[O] : 0) +
+                 (offers->disk_off ? (size_t)offers->disk_off[O] : 0);
+  sz.add<int32_t>(csr_o + 64); sz.add<double>(csr_o + 64);
+  sz.add<int64_t>(O + 1); sz.add<uint8_t>(2 * (size_t)(O + 1));
+  sz.add<int32_t>((size_t)offers->n_attr_cols * O + 1);
+  if (G) {
+    sz.add<int32_t>(6 * (size_t)(G + 2));
+    sz.add<int32_t>(2 * (size_t)(groups->cot_off ? groups->cot_off[G] : 0) + 64);
+    sz.add<int32_t>(n_memb + 64);
+  }
+  for (int k = 0; k < 9; k++) sz.add<double>(U);
+  sz.add<int32_t>(U);
+  for (int k = 0; k < 4; k++) sz.add<double>(O + 1);
+  for (int k = 0; k < 4; k++) sz.add<int32_t>(O + 1);
+  for (int k = 0; k < 6; k++) sz.add<int32_t>(n_ranked + 1);
+  sz.add<uint8_t>(n_ranked + 1);
+  sz.add<int32_t>(NC + 1); sz.add<double>(NC + 1); sz.add<double>(NC + 1); sz.add<uint8_t>(NC + 1);
+  sz.add<double>((size_t)2 * B * 64); sz.add<int32_t>((size_t)2 * B * 64);
+  sz.add<int32_t>(NC + 1); sz.add<int32_t>(NC + 1); sz.add<uint8_t>(NC + 1);
+  sz.add<int32_t>(NC + 1); sz.add<int32_t>((size_t)NC * std::max(max_ports, 1) + 1);
+  sz.add<int32_t>(O + 1);
+  sz.add<unsigned long long>(16); sz.add<int32_t>(16);
+  CK(pool, ar.reserve(sz.off + (1 << 16)));
+  ar.reset();
+
+  CK(pool, cudaEventRecord(pool->ev[0], st));
+  // ---- uploads
+  ConsArgs ca;
+  memset(&ca, 0, sizeof(ca));
+  int32_t* d_ranked; UP(d_ranked, ranked_idx, n_ranked);
+  JobDev jb;
+  memset(&jb, 0, sizeof(jb));
+  { int32_t* p; UP(p, jobs->user, J); jb.user = p; }
+  { double* p; UP(p, jobs->cpus, J); jb.cpus = p; UP(p, jobs->mem, J); jb.mem = p;
+    UP(p, jobs->gpus, J); jb.gpus = p; }
+  { int32_t* p; UP(p, jobs->ports, J); jb.ports = p; }
+  { uint8_t* p; UP(p, jobs->allowed, J); jb.allowed = p; UP(p, jobs->plugin_accept, J); jb.plugin = p; }
+  if (jobs->novel_off) { int32_t* p; UP(p, jobs->novel_off, J + 1); jb.novel_off = p;
+    UP(p, jobs->novel_host, std::max(1, jobs->novel_off[J])); jb.novel_host = p; }
+  { int32_t* p; UP(p, jobs->gpu_model, J); jb.gpu_model = p; }
+  { double* p; UP(p, jobs->disk_request, J); jb.disk_request = p; }
+  { int32_t* p; UP(p, jobs->disk_type, J); jb.disk_type = p; }
+  if (jobs->attr_off) { int32_t* p; UP(p, jobs->attr_off, J + 1); jb.attr_off = p;
+    int na = std::max(1, jobs->attr_off[J]);
+    UP(p, jobs->attr_col, na); jb.attr_col = p; UP(p, jobs->attr_val, na); jb.attr_val = p; }
+  { int64_t* p; UP(p, jobs->est_end_ms, J); jb.est_end_ms = p; }
+  { int32_t* p; UP(p, jobs->ckpt_location, J); jb.ckpt_location = p;
+    UP(p, jobs->reserved_host, J); jb.reserved_host = p; }
+  if (jobs->group_off && G) { int32_t* p; UP(p, jobs->group_off, J + 1); jb.group_off = p;
+    UP(p, jobs->group_idx, std::max<size_t>(1, n_memb)); jb.group_idx = p; }
+
+  OfferDev of;
+  memset(&of, 0, sizeof(of));
+  of.O = O;
+  int32_t* d_perm; UP(d_perm, perm.data(), O); of.perm = d_perm;
+  double *d_oc, *d_om, *d_orc, *d_orm;
+  UP(d_oc, offers->cpus, O); UP(d_om, offers->mem, O);
+  UP(d_orc, offers->run_cpus, O); UP(d_orm, offers->run_mem, O);
+  double* g_lc = ar.take<double>(O + 1); double* g_lm = ar.take<double>(O + 1);
+  double* g_rc = ar.take<double>(O + 1); double* g_rm = ar.take<double>(O + 1);
+  of.lease_c = g_lc; of.lease_m = g_lm; of.run_c = g_rc; of.run_m = g_rm;
+  { int32_t* p; UP(p, offers->hostname_id, O); of.hostname_id = p;
+    UP(p, offers->run_count, O); of.run_count = p; }
+  int32_t* d_ports_total = nullptr;
+  if (offers->port_off) { int32_t* p; UP(p, offers->port_off, O + 1); of.port_off = p;
+    int np = std::max(1, offers->port_off[O]);
+    UP(p, offers->port_begin, np); of.port_begin = p; UP(p, offers->port_end, np); of.port_end = p;
+    d_ports_total = ar.take<int32_t>(O + 1); of.ports_total = d_ports_total; }
+  { uint8_t* p; UP(p, offers->is_k8s, O); of.is_k8s = p; UP(p, offers->reserved, O); of.reserved = p; }
+  { int32_t* p; UP(p, offers->location, O); of.location = p; }
+  if (offers->gpu_off) { int32_t* p; UP(p, offers->gpu_off, O + 1); of.gpu_off = p;
+    int ng = std::max(1, offers->gpu_off[O]); UP(p, offers->gpu_model, ng); of.gpu_model = p;
+    double* q; UP(q, offers->gpu_count, ng); of.gpu_count = q; }
+  if (offers->disk_off) { int32_t* p; UP(p, offers->disk_off, O + 1); of.disk_off = p;
+    int nd = std::max(1, offers->disk_off[O]); UP(p, offers->disk_type, nd); of.disk_type = p;
+    double* q; UP(q, offers->disk_space, nd); of.disk_space = q; }
+  { int32_t* p; UP(p, offers->max_tasks, O); of.max_tasks = p; UP(p, offers->num_tasks, O); of.num_tasks = p; }
+  { int64_t* p; UP(p, offers->host_start_time, O); of.host_start = p; }
+  of.n_attr_cols = offers->attr ? offers->n_attr_cols : 0;
+  if (of.n_attr_cols > 0) { int32_t* p; UP(p, offers->attr, (size_t)of.n_attr_cols * O); of.attr = p; }
+  if ((jb.novel_off || of.reserved || (G && jb.group_off)) && !of.hostname_id)
+    return set_err(pool, COOK_E_BADARG, "cook_match: hostname_id column required by constraints");
+
+  GroupDev gr;
+  memset(&gr, 0, sizeof(gr));
+  if (G && jb.group_off) {
+    gr.n_groups = G;
+    int32_t* p;
+    UP(p, groups->kind, G); gr.kind = p;
+    UP(p, groups->attr_col, G); gr.attr_col = p;
+    UP(p, groups->minimum, G); gr.minimum = p;
+    UP(p, groups->cot_off, G + 1); gr.cot_off = p;
+    int nc = std::max(1, groups->cot_off ? groups->cot_off[G] : 0);
+    UP(p, groups->cot_hostname_id, nc); gr.cot_host = p;
+    UP(p, groups->cot_attr_val, nc); gr.cot_attr = p;
+    UP(p, gp_off.data(), G + 1); gr.gp_off = p;
+    gr.gp_n = ar.take<int32_t>(G + 1);
+    gr.gp_vm = ar.take<int32_t>(n_memb + 1);
+    CK(pool, cudaMemsetAsync(gr.gp_n, 0, sizeof(int32_t) * (G + 1), st));
+    if (!gr.cot_off || !gr.kind) return set_err(pool, COOK_E_BADARG, "cook_match: incomplete cook_groups");
+  }
+  ca.ranked = d_ranked; ca.n_ranked = n_ranked; ca.jb = jb; ca.n_users = U;
+  { double* p;
+    UP(p, users->quota_count, U); ca.q_count = p; UP(p, users->quota_cpus, U); ca.q_cpus = p;
+    UP(p, users->quota_mem, U); ca.q_mem = p; UP(p, users->quota_gpus, U); ca.q_gpus = p;
+    UP(p, users->usage_count, U); ca.u_count = p; UP(p, users->usage_cpus, U); ca.u_cpus = p;
+    UP(p, users->usage_mem, U); ca.u_mem = p; UP(p, users->usage_gpus, U); ca.u_gpus = p; }
+  { int32_t* p; UP(p, users->tokens, U); ca.tokens = p; }
+  ca.enforce_rate_limit = params->enforce_rate_limit;
+  cook_pool_quota qoff{0, 0, 0, 0, 0};
+  ca.pool_q = pool_quota ? *pool_quota : qoff;
+  ca.num_considerable = NC;
+
+  DynBuf dyn;
+  for (int b = 0; b < 2; b++) {
+    dyn.asg_c[b] = ar.take<double>(O + 1); dyn.asg_m[b] = ar.take<double>(O + 1);
+    dyn.asg_n[b] = ar.take<int32_t>(O + 1); dyn.ports_used[b] = ar.take<int32_t>(O + 1);
+  }
+  int32_t* d_pos = ar.take<int32_t>(n_ranked + 1);
+  int32_t* d_tmp = ar.take<int32_t>(n_ranked + 1);
+  int32_t* d_seg_s = ar.take<int32_t>(U + 1);
+  int32_t* d_seg_e = ar.take<int32_t>(U + 1);
+  uint8_t* d_keep = ar.take<uint8_t>(n_ranked + 1);
+  int32_t* d_cons = ar.take<int32_t>(NC + 1);
+  double* d_kc = ar.take<double>(NC + 1);
+  double* d_km = ar.take<double>(NC + 1);
+  uint8_t* d_kflags = ar.take<uint8_t>(NC + 1);
+  double* d_row_f = ar.take<double>((size_t)2 * B * 64);
+  int32_t* d_row_v = ar.take<int32_t>((size_t)2 * B * 64);
+  int32_t* d_assign = ar.take<int32_t>(NC + 1);
+  int32_t* d_ports_start = ar.take<int32_t>(NC + 1);
+  uint8_t* d_fail = ar.take<uint8_t>(NC + 1);
+  int32_t* d_out_assign = ar.take<int32_t>(NC + 1);
+  int32_t* d_out_ports = ar.take<int32_t>((size_t)NC * std::max(max_ports, 1) + 1);
+  int32_t* d_used = ar.take<int32_t>(O + 1);
+  unsigned long long* d_stats = ar.take<unsigned long long>(16);
+  int32_t* d_counters = ar.take<int32_t>(16);
+  if (!d_counters) return set_err(pool, COOK_E_OOM, "cook_match: arena exhausted");
+  for (int b = 0; b < 2; b++) {
+    CK(pool, cudaMemsetAsync(dyn.asg_c[b], 0, sizeof(double) * (O + 1), st));
+    CK(pool, cudaMemsetAsync(dyn.asg_m[b], 0, sizeof(double) * (O + 1), st));
+    CK(pool, cudaMemsetAsync(dyn.asg_n[b], 0, sizeof(int32_t) * (O + 1), st));
+    CK(pool, cudaMemsetAsync(dyn.ports_used[b], 0, sizeof(int32_t) * (O + 1), st));
+  }
+  CK(pool, cudaMemsetAsync(d_seg_s, 0, sizeof(int32_t) * (U + 1), st));
+  CK(pool, cudaMemsetAsync(d_seg_e, 0, sizeof(int32_t) * (U + 1), st));
+  CK(pool, cudaMemsetAsync(d_used, 0, sizeof(int32_t) * (O + 1), st));
+  CK(pool, cudaMemsetAsync(d_stats, 0, sizeof(unsigned long long) * 16, st));
+  CK(pool, cudaMemsetAsync(d_counters, 0, sizeof(int32_t) * 16, st));
+  CK(pool, cudaEventRecord(pool->ev[1], st));
+
+  // ---- M0 considerable
+  const int TB = 256;
+  if (O > 0) {
+    gather_offers_kernel<<<(O + TB - 1) / TB, TB, 0, st>>>(d_perm, O, d_oc, d_om, d_orc, d_orm, g_lc,
+                                                           g_lm, g_rc, g_rm);
+    if (d_ports_total)
+      ports_total_kernel<<<(O + TB - 1) / TB, TB, 0, st>>>(of.port_off, of.port_begin, of.port_end,
+                                                           O, d_ports_total);
+  }
+  iota_k<<<(n_ranked + TB - 1) / TB, TB, 0, st>>>(d_pos, n_ranked);
+  CK(pool, csort::sort_indices(d_pos, d_tmp, n_ranked, LessUserPos{d_ranked, jb.user}, st));
+  cons_seg_kernel<<<(n_ranked + TB - 1) / TB, TB, 0, st>>>(d_pos, d_ranked, jb.user, n_ranked, d_seg_s,
+                                                           d_seg_e);
+  cons_user_kernel<<<(U + 3) / 4, 128, 0, st>>>(ca, d_pos, d_seg_s, d_seg_e, d_keep);
+  cons_queue_kernel<<<1, 32, 0, st>>>(ca, d_keep, d_cons, d_kc, d_km, d_kflags, d_counters);
+  CK(pool, cudaGetLastError());
+  int32_t n_cons = 0;
+  CK(pool, cudaMemcpyAsync(&n_cons, d_counters, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  CK(pool, cudaEventRecord(pool->ev[2], st));
+  CK(pool, cudaStreamSynchronize(st));
+
+  // ---- M3 matcher
+  MatchArgs ma;
+  memset(&ma, 0, sizeof(ma));
+  ma.jb = jb; ma.of = of; ma.gr = gr; ma.dyn = dyn;
+  ma.n_cons = n_cons; ma.cons = d_cons; ma.kc = d_kc; ma.km = d_km; ma.kflags = d_kflags;
+  ma.B = B; ma.host_lifetime_mins = params->host_lifetime_mins;
+  ma.row_f = d_row_f; ma.row_v = d_row_v; ma.assign = d_assign; ma.ports_start = d_ports_start;
+  ma.fail = d_fail; ma.barrier = reinterpret_cast<unsigned*>(d_counters + 8); ma.stats = d_stats;
+  int n_matched = 0, n_used = 0;
+  unsigned long long hstats[4] = {0, 0, 0, 0};
+  if (n_cons > 0) {
+    if (O == 0) {
+      CK(pool, cudaMemsetAsync(d_assign, 0xff, sizeof(int32_t) * n_cons, st));
+      CK(pool, cudaMemsetAsync(d_fail, COOK_FAIL_NO_OFFERS, n_cons, st));
+    } else {
+      size_t smem = sizeof(ResolverShared) + sizeof(unsigned) * ((O + 31) / 32) + 16;
+      if (smem > 220 * 1024)
+        return set_err(pool, COOK_E_BADARG, "cook_match: too many offers for the resolver bitmap (%d)", O);
+      void* kfn = constr_eff ? (void*)match_kernel<true> : (void*)match_kernel<false>;
+      CK(pool, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      int grid = pool->sm_count;
+      int occ = 0;
+      CK(pool, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kfn, RES_THREADS, smem));
+      if (occ < 1) return set_err(pool, COOK_E_CUDA, "cook_match: kernel does not fit on an SM");
+      if (grid < 2) grid = 2;
+      void* kargs[] = {&ma};
+      CK(pool, cudaLaunchCooperativeKernel(kfn, dim3(grid), dim3(RES_THREADS), kargs, smem, st));
+    }
+    finalize_kernel<<<(n_cons + TB - 1) / TB, TB, 0, st>>>(ma, d_out_assign, out_ports ? d_out_ports : nullptr,
+                                                           max_ports, d_used);
+    count_flags_kernel<<<(O + TB) / TB, TB, 0, st>>>(d_used, O, d_counters + 1);
+    CK(pool, cudaGetLastError());
+  }
+  CK(pool, cudaEventRecord(pool->ev[3], st));
+  if (n_cons > 0) {
+    CK(pool, cudaMemcpyAsync(out_considerable, d_cons, sizeof(int32_t) * n_cons, cudaMemcpyDeviceToHost, st));
+    CK(pool, cudaMemcpyAsync(out_assign, d_out_assign, sizeof(int32_t) * n_cons, cudaMemcpyDeviceToHost, st));
+    if (out_ports && max_ports > 0)
+      CK(pool, cudaMemcpyAsync(out_ports, d_out_ports, sizeof(int32_t) * (size_t)n_cons * max_ports,
+                               cudaMemcpyDeviceToHost, st));
+    if (out_fail_reason)
+      CK(pool, cudaMemcpyAsync(out_fail_reason, d_fail, n_cons, cudaMemcpyDeviceToHost, st));
+    CK(pool, cudaMemcpyAsync(hstats, d_stats, sizeof(hstats), cudaMemcpyDeviceToHost, st));
+    CK(pool, cudaMemcpyAsync(&n_used, d_counters + 1, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  }
+  CK(pool, cudaEventRecord(pool->ev[4], st));
+  CK(pool, cudaStreamSynchronize(st));
+  n_matched = (int)hstats[3];
+  if (out_stats) {
+    out_stats->n_considerable = n_cons;
+    out_stats->n_matched = n_matched;
+    out_stats->head_matched = (n_cons > 0 && out_assign[0] >= 0) ? 1 : 0;
+    out_stats->n_offers_used = n_used;
+    out_stats->evals = (int64_t)n_cons * O;
+    out_stats->n_fast = (int64_t)hstats[0];
+    out_stats->n_chunk_rescan = (int64_t)hstats[1];
+    out_stats->n_full_rescan = (int64_t)hstats[2];
+    out_stats->ms_h2d = ev_ms(pool->ev[0], pool->ev[1]);
+    out_stats->ms_considerable = ev_ms(pool->ev[1], pool->ev[2]);
+    out_stats->ms_match = ev_ms(pool->ev[2], pool->ev[3]);
+    out_stats->ms_d2h = ev_ms(pool->ev[3], pool->ev[4]);
+  }
+  return COOK_OK;
+}

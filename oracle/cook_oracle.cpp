@@ -28,6 +28,8 @@
 #include <queue>
 #include <set>
 #include <vector>
+#include <atomic>
+#include <thread>
 
 #include "../include/cook_gpu.h"
 
@@ -435,12 +437,12 @@ int32_t oracle_considerable(const int32_t* ranked_idx, int32_t n_ranked,
 //  F6 on success the VM's assigned cpus/mem/ports/count advance; ports are the
 //     first n free ports scanning ranges in lease order.
 // ---------------------------------------------------------------------------
-int32_t oracle_match(const int32_t* ranked_idx, int32_t n_ranked, const cook_jobs_soa* jobs,
+static int32_t oracle_match_impl(const int32_t* ranked_idx, int32_t n_ranked, const cook_jobs_soa* jobs,
                      const cook_offers_soa* offers, const cook_groups* groups,
                      const cook_user_table* users, const cook_pool_quota* pool_quota,
                      const cook_match_params* params, int32_t* out_considerable,
                      int32_t* out_assign, int32_t* out_ports, int32_t max_ports,
-                     uint8_t* out_fail_reason, cook_match_stats* st) {
+                     uint8_t* out_fail_reason, cook_match_stats* st, int n_threads) {
   if (!ranked_idx || !jobs || !offers || !users || !params || !out_considerable || !out_assign)
     return COOK_E_BADARG;
   if (params->good_enough_fitness < 1.0) return COOK_E_BADARG;
@@ -460,12 +462,12 @@ int32_t oracle_match(const int32_t* ranked_idx, int32_t n_ranked, const cook_job
         s.ports_total[v] += offers->port_end[k] - offers->port_begin[k] + 1;
   if (groups) s.group_vms.resize(groups->n_groups);
   int n_matched = 0;
-  for (int k = 0; k < nc; k++) {
-    int j = out_considerable[k];
-    int best = -1;
-    double best_fit = 0.0;
-    bool any_res_ok = false;
-    for (int v = 0; v < O; v++) {
+  // The per-task VM loop is the only thing Fenzo itself runs on a thread pool;
+  // n_threads > 1 splits exactly that loop (used by bench.py --impl reference).
+  struct Partial { int best; double fit; bool res_ok; char pad[64]; };
+  auto scan = [&](int j, int v0, int v1, Partial& out) {
+    int best = -1; double best_fit = 0.0; bool any_res_ok = false;
+    for (int v = v0; v < v1; v++) {
       bool res_fail;
       double f = eval_pair(s, j, v, &res_fail);
       if (!res_fail) any_res_ok = true;
@@ -473,6 +475,48 @@ int32_t oracle_match(const int32_t* ranked_idx, int32_t n_ranked, const cook_job
       if (best < 0 || f > best_fit ||
           (f == best_fit && offers->name_rank[v] < offers->name_rank[best])) {
         best = v; best_fit = f;
+      }
+    }
+    out.best = best; out.fit = best_fit; out.res_ok = any_res_ok;
+  };
+  const int T = std::max(1, std::min(n_threads, 64));
+  std::vector<Partial> parts(T);
+  std::atomic<int> gen{0}, done{0}, cur_job{-1};
+  std::atomic<bool> stop{false};
+  std::vector<std::thread> workers;
+  for (int t = 1; t < T; t++)
+    workers.emplace_back([&, t]() {
+      int seen = 0;
+      while (true) {
+        while (gen.load(std::memory_order_acquire) == seen) {
+          if (stop.load(std::memory_order_relaxed)) return;
+        }
+        seen++;
+        int j = cur_job.load(std::memory_order_relaxed);
+        scan(j, (int)((long long)O * t / T), (int)((long long)O * (t + 1) / T), parts[t]);
+        done.fetch_add(1, std::memory_order_release);
+      }
+    });
+  for (int k = 0; k < nc; k++) {
+    int j = out_considerable[k];
+    if (T > 1) {
+      done.store(0, std::memory_order_relaxed);
+      cur_job.store(j, std::memory_order_relaxed);
+      gen.fetch_add(1, std::memory_order_release);
+    }
+    scan(j, 0, (int)((long long)O * 1 / T), parts[0]);
+    if (T > 1)
+      while (done.load(std::memory_order_acquire) != T - 1) {}
+    int best = -1;
+    double best_fit = 0.0;
+    bool any_res_ok = false;
+    for (int t = 0; t < T; t++) {
+      any_res_ok = any_res_ok || parts[t].res_ok;
+      int v = parts[t].best;
+      if (v < 0) continue;
+      if (best < 0 || parts[t].fit > best_fit ||
+          (parts[t].fit == best_fit && offers->name_rank[v] < offers->name_rank[best])) {
+        best = v; best_fit = parts[t].fit;
       }
     }
     out_assign[k] = best;
@@ -508,6 +552,8 @@ int32_t oracle_match(const int32_t* ranked_idx, int32_t n_ranked, const cook_job
       for (int p = 0; p < max_ports; p++) out_ports[(size_t)k * max_ports + p] = -1;
     }
   }
+  stop.store(true);
+  for (auto& w : workers) w.join();
   if (st) {
     std::memset(st, 0, sizeof(*st));
     st->n_considerable = nc;
@@ -519,6 +565,27 @@ int32_t oracle_match(const int32_t* ranked_idx, int32_t n_ranked, const cook_job
     st->evals = (int64_t)nc * O;
   }
   return COOK_OK;
+}
+
+int32_t oracle_match(const int32_t* ranked_idx, int32_t n_ranked, const cook_jobs_soa* jobs,
+                     const cook_offers_soa* offers, const cook_groups* groups,
+                     const cook_user_table* users, const cook_pool_quota* pool_quota,
+                     const cook_match_params* params, int32_t* out_considerable,
+                     int32_t* out_assign, int32_t* out_ports, int32_t max_ports,
+                     uint8_t* out_fail_reason, cook_match_stats* st) {
+  return oracle_match_impl(ranked_idx, n_ranked, jobs, offers, groups, users, pool_quota, params,
+                           out_considerable, out_assign, out_ports, max_ports, out_fail_reason, st, 1);
+}
+
+int32_t oracle_match_mt(const int32_t* ranked_idx, int32_t n_ranked, const cook_jobs_soa* jobs,
+                        const cook_offers_soa* offers, const cook_groups* groups,
+                        const cook_user_table* users, const cook_pool_quota* pool_quota,
+                        const cook_match_params* params, int32_t* out_considerable,
+                        int32_t* out_assign, int32_t* out_ports, int32_t max_ports,
+                        uint8_t* out_fail_reason, cook_match_stats* st, int32_t n_threads) {
+  return oracle_match_impl(ranked_idx, n_ranked, jobs, offers, groups, users, pool_quota, params,
+                           out_considerable, out_assign, out_ports, max_ports, out_fail_reason, st,
+                           n_threads);
 }
 
 }  // extern "C"

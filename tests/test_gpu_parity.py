@@ -1,0 +1,82 @@
+"""-m gpu parity tests: CUDA path (through the C ABI) vs the CPU oracle, bit-exact."""
+import numpy as np
+import pytest
+
+from cook_b200 import abi, traces
+
+pytestmark = pytest.mark.gpu
+
+
+def _same_dru(a, b):
+    return np.array_equal(np.nan_to_num(a, nan=-1.0), np.nan_to_num(b, nan=-1.0))
+
+
+@pytest.mark.parametrize("seed,nj,no,nu,nr", [
+    (11, 50, 7, 3, 10), (12, 1000, 100, 4, 0), (13, 5000, 333, 50, 2000),
+    (14, 20000, 1000, 200, 5000), (15, 4096, 2048, 7, 4096), (16, 1, 1, 1, 0),
+    (17, 3000, 33, 1000, 100),
+])
+def test_rank_and_match_parity_random(gpu, oracle, seed, nj, no, nu, nr):
+    t = traces.gen_pool(seed, nj, no, nu, nr)
+    rg = gpu.rank(t["running"], t["pending"], t["users"])
+    ro = oracle.rank(t["running"], t["pending"], t["users"])
+    assert np.array_equal(rg["order"], ro["order"])
+    assert np.array_equal(rg["ranked"], ro["ranked"])
+    assert _same_dru(rg["dru"], ro["dru"])
+    prm = traces.match_params(nj)
+    mg = gpu.match(rg["ranked"], t["jobs"], t["offers"], t["users"], prm)
+    mo = oracle.match(ro["ranked"], t["jobs"], t["offers"], t["users"], prm)
+    assert np.array_equal(mg["considerable"], mo["considerable"])
+    assert np.array_equal(mg["assign"], mo["assign"])
+    for k in ("n_considerable", "n_matched", "head_matched", "n_offers_used", "evals"):
+        assert mg["stats"][k] == mo["stats"][k], k
+
+
+def test_c1_simulator_trace(gpu, oracle):
+    t = traces.gen_c1()
+    rg = gpu.rank(t["running"], t["pending"], t["users"])
+    ro = oracle.rank(t["running"], t["pending"], t["users"])
+    assert np.array_equal(rg["ranked"], ro["ranked"])
+    prm = traces.match_params(1000)
+    mg = gpu.match(rg["ranked"], t["jobs"], t["offers"], t["users"], prm)
+    mo = oracle.match(ro["ranked"], t["jobs"], t["offers"], t["users"], prm)
+    assert np.array_equal(mg["assign"], mo["assign"])
+
+
+def test_c2_full_size_bit_identical(gpu, oracle):
+    """BASELINE config #2: 100k jobs x 5k offers — assignments bit-identical."""
+    t = traces.gen_c2()
+    rg = gpu.rank(t["running"], t["pending"], t["users"])
+    ro = oracle.rank(t["running"], t["pending"], t["users"])
+    assert np.array_equal(rg["ranked"], ro["ranked"])
+    assert _same_dru(rg["dru"], ro["dru"])
+    prm = traces.match_params(100_000)
+    mg = gpu.match(rg["ranked"], t["jobs"], t["offers"], t["users"], prm)
+    mo = oracle.match(ro["ranked"], t["jobs"], t["offers"], t["users"], prm)
+    assert np.array_equal(mg["considerable"], mo["considerable"])
+    assert np.array_equal(mg["assign"], mo["assign"])
+    assert mg["stats"]["evals"] == 500_000_000
+
+
+def test_quota_and_rate_limit_considerable(gpu, oracle):
+    rng = np.random.default_rng(5)
+    t = traces.gen_pool(21, 4000, 100, 30, 1000)
+    nu = 30
+    quota = {"count": rng.integers(5, 60, nu).astype(float), "cpus": rng.integers(10, 200, nu).astype(float),
+             "mem": rng.integers(20000, 900000, nu).astype(float), "gpus": np.full(nu, 1e9)}
+    usage = {k: t["users"].col("usage_" + k) for k in ("count", "cpus", "mem", "gpus")}
+    users = abi.make_users(nu, name_rank=t["users"].col("name_rank"), div_mem=t["users"].col("div_mem"),
+                           div_cpus=t["users"].col("div_cpus"), quota=quota, usage=usage,
+                           tokens=rng.integers(0, 40, nu).astype(np.int32))
+    pq = abi.make_pool_quota({"count": 1500, "cpus": 4000, "mem": 2.0e7, "gpus": 1e9})
+    rank_prm = abi.RankParams(5, 1, 30000.0, 6.0)
+    rg = gpu.rank(t["running"], t["pending"], users, pool_quota=pq, params=rank_prm)
+    ro = oracle.rank(t["running"], t["pending"], users, pool_quota=pq, params=rank_prm)
+    assert np.array_equal(rg["ranked"], ro["ranked"])
+    assert _same_dru(rg["dru"], ro["dru"])
+    for enforce in (0, 1):
+        prm = traces.match_params(700, enforce_rate_limit=enforce)
+        mg = gpu.match(ro["ranked"], t["jobs"], t["offers"], users, prm, pool_quota=pq)
+        mo = oracle.match(ro["ranked"], t["jobs"], t["offers"], users, prm, pool_quota=pq)
+        assert np.array_equal(mg["considerable"], mo["considerable"])
+        assert np.array_equal(mg["assign"], mo["assign"])
