@@ -112,7 +112,8 @@ class Groups(_SoA):
 class MatchParams(C.Structure):
     _fields_ = [("num_considerable", C.c_int32), ("enforce_rate_limit", C.c_int32),
                 ("host_lifetime_mins", C.c_int32), ("fitness_kind", C.c_int32),
-                ("good_enough_fitness", C.c_double)]
+                ("good_enough_fitness", C.c_double), ("reuse_resident", C.c_int32),
+                ("reserved0", C.c_int32)]
 
 
 class MatchStats(C.Structure):
@@ -120,7 +121,9 @@ class MatchStats(C.Structure):
                 ("head_matched", C.c_int32), ("n_offers_used", C.c_int32),
                 ("evals", C.c_int64), ("n_fast", C.c_int64), ("n_chunk_rescan", C.c_int64),
                 ("n_full_rescan", C.c_int64), ("ms_considerable", C.c_double),
-                ("ms_match", C.c_double), ("ms_h2d", C.c_double), ("ms_d2h", C.c_double)]
+                ("ms_match", C.c_double), ("ms_h2d", C.c_double), ("ms_d2h", C.c_double),
+                ("ms_match_kernel", C.c_double), ("h2d_bytes", C.c_int64),
+                ("d2h_bytes", C.c_int64), ("n_launches", C.c_int32), ("reserved0", C.c_int32)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

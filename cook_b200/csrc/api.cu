@@ -65,6 +65,7 @@ int32_t cook_pool_close(cook_pool* p) {
   cudaSetDevice(p->device);
   if (p->stream) cudaStreamSynchronize(p->stream);
   p->arena.release();
+  if (p->match_plan && p->match_plan_free) p->match_plan_free(p->match_plan);
   for (auto& e : p->ev)
     if (e) cudaEventDestroy(e);
   if (p->stream) cudaStreamDestroy(p->stream);

@@ -63,6 +63,8 @@ struct cook_pool {
   Arena arena;
   void* pinned = nullptr;  // small pinned scratch for result scalars
   size_t pinned_cap = 0;
+  void* match_plan = nullptr;            // MatchPlan (match.cu), resident inputs
+  void (*match_plan_free)(void*) = nullptr;
   char err[512] = {0};
 };
 

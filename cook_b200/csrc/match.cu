@@ -751,34 +751,54 @@ __global__ void count_flags_kernel(const int32_t* flags, int n, int32_t* out) {
 
 }  // namespace
 
-#define UP(dst, src, n) CK(pool, upload(ar, st, (src), (size_t)(n), &(dst)))
+// ------------------------------------------------------------------ host side
+// A MatchPlan is the device-resident image of one cook_match call's inputs plus
+// all scratch.  With params->reuse_resident the upload stage is skipped (the
+// inputs of the previous call on this handle are still in HBM) and only the
+// kernels + result download run — the "inputs already resident" measurement.
+struct MatchPlan {
+  Arena arena;
+  bool valid = false;
+  int J = 0, O = 0, U = 0, n_ranked = 0, NC = 0, max_ports = 0, G = 0, B = 0;
+  bool constr = false;
+  size_t n_memb = 0;
+  int64_t h2d_bytes = 0;
+  ConsArgs ca;
+  MatchArgs ma;
+  // scratch
+  int32_t *d_perm = nullptr, *d_pos = nullptr, *d_tmp = nullptr, *d_seg_s = nullptr, *d_seg_e = nullptr;
+  uint8_t* d_keep = nullptr;
+  double *d_oc = nullptr, *d_om = nullptr, *d_orc = nullptr, *d_orm = nullptr;
+  double *g_lc = nullptr, *g_lm = nullptr, *g_rc = nullptr, *g_rm = nullptr;
+  int32_t* d_ports_total = nullptr;
+  int32_t *d_cons = nullptr, *d_out_assign = nullptr, *d_out_ports = nullptr, *d_used = nullptr;
+  double *d_kc = nullptr, *d_km = nullptr;
+  uint8_t* d_kflags = nullptr;
+  unsigned long long* d_stats = nullptr;
+  int32_t* d_counters = nullptr;
+};
 
-extern "C" int32_t cook_match(cook_pool* pool, const int32_t* ranked_idx, int32_t n_ranked,
-                              const cook_jobs_soa* jobs, const cook_offers_soa* offers,
-                              const cook_groups* groups, const cook_user_table* users,
-                              const cook_pool_quota* pool_quota, const cook_match_params* params,
-                              int32_t* out_considerable, int32_t* out_assign, int32_t* out_ports,
-                              int32_t max_ports, uint8_t* out_fail_reason,
-                              cook_match_stats* out_stats) {
-  if (!pool) return COOK_E_BADARG;
-  if (!ranked_idx || !jobs || !offers || !users || !params || !out_considerable || !out_assign)
-    return set_err(pool, COOK_E_BADARG, "cook_match: null argument");
-  if (params->good_enough_fitness < 1.0)
-    return set_err(pool, COOK_E_BADARG,
-                   "cook_match: good_enough_fitness < 1.0 is Fenzo's racy early-exit mode; "
-                   "only the deterministic mode (>= 1.0) is supported");
-  if (params->fitness_kind != 0)
-    return set_err(pool, COOK_E_UNSUPPORTED_CONSTRAINT, "cook_match: only cpuMemBinPacker");
-  const int J = jobs->n, O = offers->n, U = users->n_users;
-  const int NC = params->num_considerable;
-  if (J < 0 || O < 0 || U <= 0 || n_ranked < 0 || NC < 0)
-    return set_err(pool, COOK_E_BADARG, "cook_match: bad sizes");
-  if (out_stats) memset(out_stats, 0, sizeof(*out_stats));
-  if (n_ranked == 0 || NC == 0) return COOK_OK;
-  CK(pool, cudaSetDevice(pool->device));
+static void plan_free(void* p) {
+  MatchPlan* mp = static_cast<MatchPlan*>(p);
+  if (mp) { mp->arena.release(); delete mp; }
+}
+
+#define UP(dst, src, n)                                                   \
+  do {                                                                    \
+    CK(pool, upload(ar, st, (src), (size_t)(n), &(dst)));                 \
+    if (src) mp->h2d_bytes += (int64_t)sizeof(*(src)) * (int64_t)(n);     \
+  } while (0)
+
+static int32_t build_plan(cook_pool* pool, MatchPlan* mp, const int32_t* ranked_idx,
+                          int32_t n_ranked, const cook_jobs_soa* jobs,
+                          const cook_offers_soa* offers, const cook_groups* groups,
+                          const cook_user_table* users, const cook_pool_quota* pool_quota,
+                          const cook_match_params* params, int32_t max_ports) {
   cudaStream_t st = pool->stream;
-  Arena& ar = pool->arena;
-
+  Arena& ar = mp->arena;
+  const int J = jobs->n, O = offers->n, U = users->n_users, NC = params->num_considerable;
+  mp->valid = false;
+  mp->h2d_bytes = 0;
   // host-side prep: offers sorted by hostname rank (tie-break order)
   std::vector<int32_t> perm(O);
   std::iota(perm.begin(), perm.end(), 0);
@@ -808,15 +828,15 @@ extern "C" int32_t cook_match(cook_pool* pool, const int32_t* ranked_idx, int32_
   if (!constr_eff && jobs->ports)
     for (int j = 0; j < J && !constr_eff; j++) constr_eff = jobs->ports[j] != 0;
 
-  const int B = std::min(MAXB, 128);
+  const int B = 128;
   Sizer sz;
   sz.add<int32_t>(n_ranked);
   for (int k = 0; k < 3; k++) sz.add<double>(J + 1);
   sz.add<int32_t>(J + 1); sz.add<int32_t>(J + 1);
   sz.add<uint8_t>(J + 1); sz.add<uint8_t>(J + 1);
   size_t csr_j = (jobs->novel_off ? jobs->novel_off[J] : 0) + 2 * (size_t)(jobs->attr_off ? jobs->attr_off[J] : 0) + n_memb;
-  sz.add<int32_t>(4 * (J + 2) + csr_j + 64);
-  sz.add<double>(J + 1); sz.add<int32_t>(3 * (J + 1)); sz.add<int64_t>(J + 1);
+  sz.add<int32_t>(4 * (size_t)(J + 2) + csr_j + 64);
+  sz.add<double>(J + 1); sz.add<int32_t>(3 * (size_t)(J + 1)); sz.add<int64_t>(J + 1);
   sz.add<int32_t>(O + 1);
   for (int k = 0; k < 8; k++) sz.add<double>(O + 1);
   sz.add<int32_t>(12 * (size_t)(O + 2));
@@ -843,12 +863,10 @@ extern "C" int32_t cook_match(cook_pool* pool, const int32_t* ranked_idx, int32_
   sz.add<int32_t>(NC + 1); sz.add<int32_t>((size_t)NC * std::max(max_ports, 1) + 1);
   sz.add<int32_t>(O + 1);
   sz.add<unsigned long long>(16); sz.add<int32_t>(16);
-  CK(pool, ar.reserve(sz.off + (1 << 16)));
+  CK(pool, ar.reserve(sz.off + (1 << 18)));
   ar.reset();
 
-  CK(pool, cudaEventRecord(pool->ev[0], st));
-  // ---- uploads
-  ConsArgs ca;
+  ConsArgs& ca = mp->ca;
   memset(&ca, 0, sizeof(ca));
   int32_t* d_ranked; UP(d_ranked, ranked_idx, n_ranked);
   JobDev jb;
@@ -875,20 +893,19 @@ extern "C" int32_t cook_match(cook_pool* pool, const int32_t* ranked_idx, int32_
   OfferDev of;
   memset(&of, 0, sizeof(of));
   of.O = O;
-  int32_t* d_perm; UP(d_perm, perm.data(), O); of.perm = d_perm;
-  double *d_oc, *d_om, *d_orc, *d_orm;
-  UP(d_oc, offers->cpus, O); UP(d_om, offers->mem, O);
-  UP(d_orc, offers->run_cpus, O); UP(d_orm, offers->run_mem, O);
-  double* g_lc = ar.take<double>(O + 1); double* g_lm = ar.take<double>(O + 1);
-  double* g_rc = ar.take<double>(O + 1); double* g_rm = ar.take<double>(O + 1);
-  of.lease_c = g_lc; of.lease_m = g_lm; of.run_c = g_rc; of.run_m = g_rm;
+  { const int32_t* hp = perm.data(); UP(mp->d_perm, hp, O); of.perm = mp->d_perm; }
+  UP(mp->d_oc, offers->cpus, O); UP(mp->d_om, offers->mem, O);
+  UP(mp->d_orc, offers->run_cpus, O); UP(mp->d_orm, offers->run_mem, O);
+  mp->g_lc = ar.take<double>(O + 1); mp->g_lm = ar.take<double>(O + 1);
+  mp->g_rc = ar.take<double>(O + 1); mp->g_rm = ar.take<double>(O + 1);
+  of.lease_c = mp->g_lc; of.lease_m = mp->g_lm; of.run_c = mp->g_rc; of.run_m = mp->g_rm;
   { int32_t* p; UP(p, offers->hostname_id, O); of.hostname_id = p;
     UP(p, offers->run_count, O); of.run_count = p; }
-  int32_t* d_ports_total = nullptr;
+  mp->d_ports_total = nullptr;
   if (offers->port_off) { int32_t* p; UP(p, offers->port_off, O + 1); of.port_off = p;
     int np = std::max(1, offers->port_off[O]);
     UP(p, offers->port_begin, np); of.port_begin = p; UP(p, offers->port_end, np); of.port_end = p;
-    d_ports_total = ar.take<int32_t>(O + 1); of.ports_total = d_ports_total; }
+    mp->d_ports_total = ar.take<int32_t>(O + 1); of.ports_total = mp->d_ports_total; }
   { uint8_t* p; UP(p, offers->is_k8s, O); of.is_k8s = p; UP(p, offers->reserved, O); of.reserved = p; }
   { int32_t* p; UP(p, offers->location, O); of.location = p; }
   if (offers->gpu_off) { int32_t* p; UP(p, offers->gpu_off, O + 1); of.gpu_off = p;
@@ -916,10 +933,9 @@ extern "C" int32_t cook_match(cook_pool* pool, const int32_t* ranked_idx, int32_
     int nc = std::max(1, groups->cot_off ? groups->cot_off[G] : 0);
     UP(p, groups->cot_hostname_id, nc); gr.cot_host = p;
     UP(p, groups->cot_attr_val, nc); gr.cot_attr = p;
-    UP(p, gp_off.data(), G + 1); gr.gp_off = p;
+    { const int32_t* hp = gp_off.data(); UP(p, hp, G + 1); gr.gp_off = p; }
     gr.gp_n = ar.take<int32_t>(G + 1);
     gr.gp_vm = ar.take<int32_t>(n_memb + 1);
-    CK(pool, cudaMemsetAsync(gr.gp_n, 0, sizeof(int32_t) * (G + 1), st));
     if (!gr.cot_off || !gr.kind) return set_err(pool, COOK_E_BADARG, "cook_match: incomplete cook_groups");
   }
   ca.ranked = d_ranked; ca.n_ranked = n_ranked; ca.jb = jb; ca.n_users = U;
@@ -934,84 +950,108 @@ extern "C" int32_t cook_match(cook_pool* pool, const int32_t* ranked_idx, int32_
   ca.pool_q = pool_quota ? *pool_quota : qoff;
   ca.num_considerable = NC;
 
-  DynBuf dyn;
+  MatchArgs& ma = mp->ma;
+  memset(&ma, 0, sizeof(ma));
   for (int b = 0; b < 2; b++) {
-    dyn.asg_c[b] = ar.take<double>(O + 1); dyn.asg_m[b] = ar.take<double>(O + 1);
-    dyn.asg_n[b] = ar.take<int32_t>(O + 1); dyn.ports_used[b] = ar.take<int32_t>(O + 1);
+    ma.dyn.asg_c[b] = ar.take<double>(O + 1); ma.dyn.asg_m[b] = ar.take<double>(O + 1);
+    ma.dyn.asg_n[b] = ar.take<int32_t>(O + 1); ma.dyn.ports_used[b] = ar.take<int32_t>(O + 1);
   }
-  int32_t* d_pos = ar.take<int32_t>(n_ranked + 1);
-  int32_t* d_tmp = ar.take<int32_t>(n_ranked + 1);
-  int32_t* d_seg_s = ar.take<int32_t>(U + 1);
-  int32_t* d_seg_e = ar.take<int32_t>(U + 1);
-  uint8_t* d_keep = ar.take<uint8_t>(n_ranked + 1);
-  int32_t* d_cons = ar.take<int32_t>(NC + 1);
-  double* d_kc = ar.take<double>(NC + 1);
-  double* d_km = ar.take<double>(NC + 1);
-  uint8_t* d_kflags = ar.take<uint8_t>(NC + 1);
-  double* d_row_f = ar.take<double>((size_t)2 * B * 64);
-  int32_t* d_row_v = ar.take<int32_t>((size_t)2 * B * 64);
-  int32_t* d_assign = ar.take<int32_t>(NC + 1);
-  int32_t* d_ports_start = ar.take<int32_t>(NC + 1);
-  uint8_t* d_fail = ar.take<uint8_t>(NC + 1);
-  int32_t* d_out_assign = ar.take<int32_t>(NC + 1);
-  int32_t* d_out_ports = ar.take<int32_t>((size_t)NC * std::max(max_ports, 1) + 1);
-  int32_t* d_used = ar.take<int32_t>(O + 1);
-  unsigned long long* d_stats = ar.take<unsigned long long>(16);
-  int32_t* d_counters = ar.take<int32_t>(16);
-  if (!d_counters) return set_err(pool, COOK_E_OOM, "cook_match: arena exhausted");
+  mp->d_pos = ar.take<int32_t>(n_ranked + 1);
+  mp->d_tmp = ar.take<int32_t>(n_ranked + 1);
+  mp->d_seg_s = ar.take<int32_t>(U + 1);
+  mp->d_seg_e = ar.take<int32_t>(U + 1);
+  mp->d_keep = ar.take<uint8_t>(n_ranked + 1);
+  mp->d_cons = ar.take<int32_t>(NC + 1);
+  mp->d_kc = ar.take<double>(NC + 1);
+  mp->d_km = ar.take<double>(NC + 1);
+  mp->d_kflags = ar.take<uint8_t>(NC + 1);
+  ma.row_f = ar.take<double>((size_t)2 * B * 64);
+  ma.row_v = ar.take<int32_t>((size_t)2 * B * 64);
+  ma.assign = ar.take<int32_t>(NC + 1);
+  ma.ports_start = ar.take<int32_t>(NC + 1);
+  ma.fail = ar.take<uint8_t>(NC + 1);
+  mp->d_out_assign = ar.take<int32_t>(NC + 1);
+  mp->d_out_ports = ar.take<int32_t>((size_t)NC * std::max(max_ports, 1) + 1);
+  mp->d_used = ar.take<int32_t>(O + 1);
+  mp->d_stats = ar.take<unsigned long long>(16);
+  mp->d_counters = ar.take<int32_t>(16);
+  if (!mp->d_counters) return set_err(pool, COOK_E_OOM, "cook_match: arena exhausted");
+  ma.jb = jb; ma.of = of; ma.gr = gr;
+  ma.cons = mp->d_cons; ma.kc = mp->d_kc; ma.km = mp->d_km; ma.kflags = mp->d_kflags;
+  ma.B = B; ma.host_lifetime_mins = params->host_lifetime_mins;
+  ma.barrier = reinterpret_cast<unsigned*>(mp->d_counters + 8); ma.stats = mp->d_stats;
+  mp->J = J; mp->O = O; mp->U = U; mp->n_ranked = n_ranked; mp->NC = NC; mp->max_ports = max_ports;
+  mp->G = G; mp->B = B; mp->constr = constr_eff; mp->n_memb = n_memb;
+  mp->valid = true;
+  return COOK_OK;
+}
+
+static int32_t run_plan(cook_pool* pool, MatchPlan* mp, int32_t* out_considerable,
+                        int32_t* out_assign, int32_t* out_ports, uint8_t* out_fail_reason,
+                        cook_match_stats* out_stats, bool uploaded) {
+  cudaStream_t st = pool->stream;
+  const int O = mp->O, U = mp->U, n_ranked = mp->n_ranked, max_ports = mp->max_ports;
+  MatchArgs& ma = mp->ma;
+  ConsArgs& ca = mp->ca;
+  int launches = 0;
+  // ---- reset of per-cycle dynamic state
   for (int b = 0; b < 2; b++) {
-    CK(pool, cudaMemsetAsync(dyn.asg_c[b], 0, sizeof(double) * (O + 1), st));
-    CK(pool, cudaMemsetAsync(dyn.asg_m[b], 0, sizeof(double) * (O + 1), st));
-    CK(pool, cudaMemsetAsync(dyn.asg_n[b], 0, sizeof(int32_t) * (O + 1), st));
-    CK(pool, cudaMemsetAsync(dyn.ports_used[b], 0, sizeof(int32_t) * (O + 1), st));
+    CK(pool, cudaMemsetAsync(ma.dyn.asg_c[b], 0, sizeof(double) * (O + 1), st));
+    CK(pool, cudaMemsetAsync(ma.dyn.asg_m[b], 0, sizeof(double) * (O + 1), st));
+    CK(pool, cudaMemsetAsync(ma.dyn.asg_n[b], 0, sizeof(int32_t) * (O + 1), st));
+    CK(pool, cudaMemsetAsync(ma.dyn.ports_used[b], 0, sizeof(int32_t) * (O + 1), st));
   }
-  CK(pool, cudaMemsetAsync(d_seg_s, 0, sizeof(int32_t) * (U + 1), st));
-  CK(pool, cudaMemsetAsync(d_seg_e, 0, sizeof(int32_t) * (U + 1), st));
-  CK(pool, cudaMemsetAsync(d_used, 0, sizeof(int32_t) * (O + 1), st));
-  CK(pool, cudaMemsetAsync(d_stats, 0, sizeof(unsigned long long) * 16, st));
-  CK(pool, cudaMemsetAsync(d_counters, 0, sizeof(int32_t) * 16, st));
+  if (ma.gr.gp_n) CK(pool, cudaMemsetAsync(ma.gr.gp_n, 0, sizeof(int32_t) * (mp->G + 1), st));
+  CK(pool, cudaMemsetAsync(mp->d_seg_s, 0, sizeof(int32_t) * (U + 1), st));
+  CK(pool, cudaMemsetAsync(mp->d_seg_e, 0, sizeof(int32_t) * (U + 1), st));
+  CK(pool, cudaMemsetAsync(mp->d_used, 0, sizeof(int32_t) * (O + 1), st));
+  CK(pool, cudaMemsetAsync(mp->d_stats, 0, sizeof(unsigned long long) * 16, st));
+  CK(pool, cudaMemsetAsync(mp->d_counters, 0, sizeof(int32_t) * 16, st));
   CK(pool, cudaEventRecord(pool->ev[1], st));
 
   // ---- M0 considerable
   const int TB = 256;
   if (O > 0) {
-    gather_offers_kernel<<<(O + TB - 1) / TB, TB, 0, st>>>(d_perm, O, d_oc, d_om, d_orc, d_orm, g_lc,
-                                                           g_lm, g_rc, g_rm);
-    if (d_ports_total)
-      ports_total_kernel<<<(O + TB - 1) / TB, TB, 0, st>>>(of.port_off, of.port_begin, of.port_end,
-                                                           O, d_ports_total);
+    gather_offers_kernel<<<(O + TB - 1) / TB, TB, 0, st>>>(mp->d_perm, O, mp->d_oc, mp->d_om, mp->d_orc,
+                                                           mp->d_orm, mp->g_lc, mp->g_lm, mp->g_rc,
+                                                           mp->g_rm);
+    launches++;
+    if (mp->d_ports_total) {
+      ports_total_kernel<<<(O + TB - 1) / TB, TB, 0, st>>>(ma.of.port_off, ma.of.port_begin,
+                                                           ma.of.port_end, O, mp->d_ports_total);
+      launches++;
+    }
   }
-  iota_k<<<(n_ranked + TB - 1) / TB, TB, 0, st>>>(d_pos, n_ranked);
-  CK(pool, csort::sort_indices(d_pos, d_tmp, n_ranked, LessUserPos{d_ranked, jb.user}, st));
-  cons_seg_kernel<<<(n_ranked + TB - 1) / TB, TB, 0, st>>>(d_pos, d_ranked, jb.user, n_ranked, d_seg_s,
-                                                           d_seg_e);
-  cons_user_kernel<<<(U + 3) / 4, 128, 0, st>>>(ca, d_pos, d_seg_s, d_seg_e, d_keep);
-  cons_queue_kernel<<<1, 32, 0, st>>>(ca, d_keep, d_cons, d_kc, d_km, d_kflags, d_counters);
+  iota_k<<<(n_ranked + TB - 1) / TB, TB, 0, st>>>(mp->d_pos, n_ranked);
+  CK(pool, csort::sort_indices(mp->d_pos, mp->d_tmp, n_ranked, LessUserPos{ca.ranked, ca.jb.user}, st));
+  launches += 2;
+  for (long long w = csort::TILE; w < n_ranked; w <<= 1) launches++;
+  cons_seg_kernel<<<(n_ranked + TB - 1) / TB, TB, 0, st>>>(mp->d_pos, ca.ranked, ca.jb.user, n_ranked,
+                                                           mp->d_seg_s, mp->d_seg_e);
+  cons_user_kernel<<<(U + 3) / 4, 128, 0, st>>>(ca, mp->d_pos, mp->d_seg_s, mp->d_seg_e, mp->d_keep);
+  cons_queue_kernel<<<1, 32, 0, st>>>(ca, mp->d_keep, mp->d_cons, mp->d_kc, mp->d_km, mp->d_kflags,
+                                      mp->d_counters);
+  launches += 3;
   CK(pool, cudaGetLastError());
   int32_t n_cons = 0;
-  CK(pool, cudaMemcpyAsync(&n_cons, d_counters, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  CK(pool, cudaMemcpyAsync(&n_cons, mp->d_counters, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   CK(pool, cudaEventRecord(pool->ev[2], st));
   CK(pool, cudaStreamSynchronize(st));
 
   // ---- M3 matcher
-  MatchArgs ma;
-  memset(&ma, 0, sizeof(ma));
-  ma.jb = jb; ma.of = of; ma.gr = gr; ma.dyn = dyn;
-  ma.n_cons = n_cons; ma.cons = d_cons; ma.kc = d_kc; ma.km = d_km; ma.kflags = d_kflags;
-  ma.B = B; ma.host_lifetime_mins = params->host_lifetime_mins;
-  ma.row_f = d_row_f; ma.row_v = d_row_v; ma.assign = d_assign; ma.ports_start = d_ports_start;
-  ma.fail = d_fail; ma.barrier = reinterpret_cast<unsigned*>(d_counters + 8); ma.stats = d_stats;
-  int n_matched = 0, n_used = 0;
+  ma.n_cons = n_cons;
+  int n_used = 0;
   unsigned long long hstats[4] = {0, 0, 0, 0};
+  CK(pool, cudaEventRecord(pool->ev[5], st));
   if (n_cons > 0) {
     if (O == 0) {
-      CK(pool, cudaMemsetAsync(d_assign, 0xff, sizeof(int32_t) * n_cons, st));
-      CK(pool, cudaMemsetAsync(d_fail, COOK_FAIL_NO_OFFERS, n_cons, st));
+      CK(pool, cudaMemsetAsync(ma.assign, 0xff, sizeof(int32_t) * n_cons, st));
+      CK(pool, cudaMemsetAsync(ma.fail, COOK_FAIL_NO_OFFERS, n_cons, st));
     } else {
       size_t smem = sizeof(ResolverShared) + sizeof(unsigned) * ((O + 31) / 32) + 16;
       if (smem > 220 * 1024)
         return set_err(pool, COOK_E_BADARG, "cook_match: too many offers for the resolver bitmap (%d)", O);
-      void* kfn = constr_eff ? (void*)match_kernel<true> : (void*)match_kernel<false>;
+      void* kfn = mp->constr ? (void*)match_kernel<true> : (void*)match_kernel<false>;
       CK(pool, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       int grid = pool->sm_count;
       int occ = 0;
@@ -1020,40 +1060,92 @@ extern "C" int32_t cook_match(cook_pool* pool, const int32_t* ranked_idx, int32_
       if (grid < 2) grid = 2;
       void* kargs[] = {&ma};
       CK(pool, cudaLaunchCooperativeKernel(kfn, dim3(grid), dim3(RES_THREADS), kargs, smem, st));
+      launches++;
     }
-    finalize_kernel<<<(n_cons + TB - 1) / TB, TB, 0, st>>>(ma, d_out_assign, out_ports ? d_out_ports : nullptr,
-                                                           max_ports, d_used);
-    count_flags_kernel<<<(O + TB) / TB, TB, 0, st>>>(d_used, O, d_counters + 1);
+  }
+  CK(pool, cudaEventRecord(pool->ev[6], st));
+  if (n_cons > 0) {
+    finalize_kernel<<<(n_cons + TB - 1) / TB, TB, 0, st>>>(ma, mp->d_out_assign,
+                                                           out_ports ? mp->d_out_ports : nullptr,
+                                                           max_ports, mp->d_used);
+    count_flags_kernel<<<(O + TB) / TB, TB, 0, st>>>(mp->d_used, O, mp->d_counters + 1);
+    launches += 2;
     CK(pool, cudaGetLastError());
   }
   CK(pool, cudaEventRecord(pool->ev[3], st));
   if (n_cons > 0) {
-    CK(pool, cudaMemcpyAsync(out_considerable, d_cons, sizeof(int32_t) * n_cons, cudaMemcpyDeviceToHost, st));
-    CK(pool, cudaMemcpyAsync(out_assign, d_out_assign, sizeof(int32_t) * n_cons, cudaMemcpyDeviceToHost, st));
+    CK(pool, cudaMemcpyAsync(out_considerable, mp->d_cons, sizeof(int32_t) * n_cons, cudaMemcpyDeviceToHost, st));
+    CK(pool, cudaMemcpyAsync(out_assign, mp->d_out_assign, sizeof(int32_t) * n_cons, cudaMemcpyDeviceToHost, st));
     if (out_ports && max_ports > 0)
-      CK(pool, cudaMemcpyAsync(out_ports, d_out_ports, sizeof(int32_t) * (size_t)n_cons * max_ports,
+      CK(pool, cudaMemcpyAsync(out_ports, mp->d_out_ports, sizeof(int32_t) * (size_t)n_cons * max_ports,
                                cudaMemcpyDeviceToHost, st));
     if (out_fail_reason)
-      CK(pool, cudaMemcpyAsync(out_fail_reason, d_fail, n_cons, cudaMemcpyDeviceToHost, st));
-    CK(pool, cudaMemcpyAsync(hstats, d_stats, sizeof(hstats), cudaMemcpyDeviceToHost, st));
-    CK(pool, cudaMemcpyAsync(&n_used, d_counters + 1, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+      CK(pool, cudaMemcpyAsync(out_fail_reason, ma.fail, n_cons, cudaMemcpyDeviceToHost, st));
+    CK(pool, cudaMemcpyAsync(hstats, mp->d_stats, sizeof(hstats), cudaMemcpyDeviceToHost, st));
+    CK(pool, cudaMemcpyAsync(&n_used, mp->d_counters + 1, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   }
   CK(pool, cudaEventRecord(pool->ev[4], st));
   CK(pool, cudaStreamSynchronize(st));
-  n_matched = (int)hstats[3];
   if (out_stats) {
     out_stats->n_considerable = n_cons;
-    out_stats->n_matched = n_matched;
+    out_stats->n_matched = (int)hstats[3];
     out_stats->head_matched = (n_cons > 0 && out_assign[0] >= 0) ? 1 : 0;
     out_stats->n_offers_used = n_used;
     out_stats->evals = (int64_t)n_cons * O;
     out_stats->n_fast = (int64_t)hstats[0];
     out_stats->n_chunk_rescan = (int64_t)hstats[1];
     out_stats->n_full_rescan = (int64_t)hstats[2];
-    out_stats->ms_h2d = ev_ms(pool->ev[0], pool->ev[1]);
+    out_stats->ms_h2d = uploaded ? ev_ms(pool->ev[0], pool->ev[1]) : 0.0;
     out_stats->ms_considerable = ev_ms(pool->ev[1], pool->ev[2]);
     out_stats->ms_match = ev_ms(pool->ev[2], pool->ev[3]);
+    out_stats->ms_match_kernel = ev_ms(pool->ev[5], pool->ev[6]);
     out_stats->ms_d2h = ev_ms(pool->ev[3], pool->ev[4]);
+    out_stats->n_launches = launches;
+    out_stats->h2d_bytes = uploaded ? mp->h2d_bytes : 0;
+    out_stats->d2h_bytes = (int64_t)n_cons * (8 + (out_fail_reason ? 1 : 0) +
+                                               (out_ports ? 4 * (int64_t)max_ports : 0)) + 44;
   }
   return COOK_OK;
+}
+
+extern "C" int32_t cook_match(cook_pool* pool, const int32_t* ranked_idx, int32_t n_ranked,
+                              const cook_jobs_soa* jobs, const cook_offers_soa* offers,
+                              const cook_groups* groups, const cook_user_table* users,
+                              const cook_pool_quota* pool_quota, const cook_match_params* params,
+                              int32_t* out_considerable, int32_t* out_assign, int32_t* out_ports,
+                              int32_t max_ports, uint8_t* out_fail_reason,
+                              cook_match_stats* out_stats) {
+  if (!pool) return COOK_E_BADARG;
+  if (!ranked_idx || !jobs || !offers || !users || !params || !out_considerable || !out_assign)
+    return set_err(pool, COOK_E_BADARG, "cook_match: null argument");
+  if (params->good_enough_fitness < 1.0)
+    return set_err(pool, COOK_E_BADARG,
+                   "cook_match: good_enough_fitness < 1.0 is Fenzo's racy early-exit mode; "
+                   "only the deterministic mode (>= 1.0) is supported");
+  if (params->fitness_kind != 0)
+    return set_err(pool, COOK_E_UNSUPPORTED_CONSTRAINT, "cook_match: only cpuMemBinPacker");
+  const int J = jobs->n, O = offers->n, U = users->n_users;
+  const int NC = params->num_considerable;
+  if (J < 0 || O < 0 || U <= 0 || n_ranked < 0 || NC < 0 || max_ports < 0)
+    return set_err(pool, COOK_E_BADARG, "cook_match: bad sizes");
+  if (out_stats) memset(out_stats, 0, sizeof(*out_stats));
+  if (n_ranked == 0 || NC == 0) return COOK_OK;
+  CK(pool, cudaSetDevice(pool->device));
+  if (!pool->match_plan) {
+    pool->match_plan = new MatchPlan();
+    pool->match_plan_free = plan_free;
+  }
+  MatchPlan* mp = static_cast<MatchPlan*>(pool->match_plan);
+  const bool reuse = params->reuse_resident && mp->valid && mp->J == J && mp->O == O && mp->U == U &&
+                     mp->n_ranked == n_ranked && mp->NC == NC && mp->max_ports == max_ports;
+  if (params->reuse_resident && !reuse)
+    return set_err(pool, COOK_E_BADARG,
+                   "cook_match: reuse_resident set but no matching resident inputs on this handle");
+  CK(pool, cudaEventRecord(pool->ev[0], pool->stream));
+  if (!reuse) {
+    int32_t rc = build_plan(pool, mp, ranked_idx, n_ranked, jobs, offers, groups, users, pool_quota,
+                            params, max_ports);
+    if (rc != COOK_OK) { mp->valid = false; return rc; }
+  }
+  return run_plan(pool, mp, out_considerable, out_assign, out_ports, out_fail_reason, out_stats, !reuse);
 }

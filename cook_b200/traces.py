@@ -110,6 +110,6 @@ def gen_c2(seed=2, n_jobs=100_000, n_offers=5_000, n_users=1_000, n_running=20_0
     return gen_pool(seed, n_jobs, n_offers, n_users, n_running)
 
 
-def match_params(num_considerable, enforce_rate_limit=0, host_lifetime_mins=0):
+def match_params(num_considerable, enforce_rate_limit=0, host_lifetime_mins=0, reuse_resident=0):
     return abi.MatchParams(int(num_considerable), int(enforce_rate_limit), int(host_lifetime_mins),
-                           0, 1.0)
+                           0, 1.0, int(reuse_resident), 0)

@@ -240,6 +240,11 @@ typedef struct {
   int32_t host_lifetime_mins;    /* estimated-completion config                 */
   int32_t fitness_kind;          /* 0 = cpuMemBinPacker (config.clj:108)        */
   double good_enough_fitness;    /* must be >= 1.0 (deterministic mode, F3)     */
+  int32_t reuse_resident;        /* 1: inputs are unchanged since the previous
+                                    cook_match on this handle and still in HBM:
+                                    skip the upload stage (columnar-mirror mode,
+                                    SURVEY §8f-1); error if nothing is resident */
+  int32_t reserved0;
 } cook_match_params;
 
 enum { /* out_fail_reason codes (first failing check on the LAST VM evaluated
@@ -262,6 +267,11 @@ typedef struct {
   double ms_match;
   double ms_h2d;
   double ms_d2h;
+  double ms_match_kernel; /* the persistent matcher kernel alone               */
+  int64_t h2d_bytes;      /* bytes uploaded by this call                       */
+  int64_t d2h_bytes;      /* bytes downloaded by this call                     */
+  int32_t n_launches;     /* kernels launched by this call                     */
+  int32_t reserved0;
 } cook_match_stats;
 
 /* M0-M6: one call per match cycle per pool.  Replaces

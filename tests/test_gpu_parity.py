@@ -80,3 +80,23 @@ def test_quota_and_rate_limit_considerable(gpu, oracle):
         mo = oracle.match(ro["ranked"], t["jobs"], t["offers"], users, prm, pool_quota=pq)
         assert np.array_equal(mg["considerable"], mo["considerable"])
         assert np.array_equal(mg["assign"], mo["assign"])
+
+
+def test_resident_inputs_same_result(gpu, oracle):
+    """reuse_resident skips the upload stage; results must not change, and asking
+    for it without resident inputs must fail loudly."""
+    from cook_b200.engine import CookError
+    t = traces.gen_pool(31, 6000, 400, 40, 1500)
+    ranked = oracle.rank(t["running"], t["pending"], t["users"])["ranked"]
+    mo = oracle.match(ranked, t["jobs"], t["offers"], t["users"], traces.match_params(6000))
+    m1 = gpu.match(ranked, t["jobs"], t["offers"], t["users"], traces.match_params(6000))
+    assert m1["stats"]["h2d_bytes"] > 0
+    for _ in range(2):
+        m2 = gpu.match(ranked, t["jobs"], t["offers"], t["users"],
+                       traces.match_params(6000, reuse_resident=1))
+        assert m2["stats"]["h2d_bytes"] == 0
+        assert np.array_equal(m2["assign"], mo["assign"])
+    assert np.array_equal(m1["assign"], mo["assign"])
+    with pytest.raises(CookError):
+        gpu.match(ranked[:100], t["jobs"], t["offers"], t["users"],
+                  traces.match_params(6000, reuse_resident=1))
