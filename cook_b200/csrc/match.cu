@@ -40,6 +40,7 @@ namespace {
 constexpr int RES_THREADS = 256;   // threads per CTA of the match kernel
 constexpr int MAXB = 256;          // max jobs per block
 constexpr int MAXD = 2 * MAXB;     // dirty list capacity (two blocks)
+constexpr int TOPK = 8;            // candidates kept per (job, chunk)
 
 struct JobDev {   // columns in ORIGINAL job index space (may be null)
   const int32_t* user;
@@ -107,12 +108,14 @@ struct MatchArgs {
   const uint8_t* kflags;   // bit0: has groups
   int B;                   // jobs per block
   int host_lifetime_mins;
-  double* row_f;           // [2][B][2][32]
-  int32_t* row_v;          // [2][B][2][32]
+  double* row_f;           // [2][B][TOPK][32]
+  int32_t* row_v;          // [2][B][TOPK][32]
+  uint8_t* feas;           // [2][B] any feasible VM at the snapshot
+  unsigned* rows_ready;    // [nblk] rows scored per block
+  unsigned* published;     // # blocks resolved and published
   int32_t* assign;         // [n_cons] v (rank space) or -1
   int32_t* ports_start;    // [n_cons] ports_used of the VM before assignment
   uint8_t* fail;           // [n_cons]
-  unsigned* barrier;       // grid barrier counter
   unsigned long long* stats;  // [0]=fast [1]=chunk rescans [2]=full rescans [3]=matched [4]=offers used
 };
 
@@ -121,21 +124,6 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
   unsigned v;
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
-}
-
-// One barrier per pipeline slot.  Monotonic counter: epoch e completes when
-// counter == e * gridDim.x.  All CTAs are co-resident (cooperative launch).
-__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& epoch) {
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    epoch++;
-    __threadfence();
-    atomicAdd(counter, 1u);
-    const unsigned target = epoch * gridDim.x;
-    while (ld_acquire_u32(counter) < target) __nanosleep(64);
-    __threadfence();
-  }
-  __syncthreads();
 }
 
 struct JobRegs {  // per-job values the hot loop keeps in registers
@@ -303,37 +291,93 @@ __device__ __forceinline__ double eval_vm(const MatchArgs& a, const JobRegs& r, 
 }
 
 // ------------------------------------------------------------- evaluators
-template <bool CONSTR>
-__device__ void evaluate_block(const MatchArgs& a, int blk, int snap, int warp_id, int n_warps) {
-  const int lane = threadIdx.x & 31;
-  const int k0 = blk * a.B;
-  const int k1 = min(k0 + a.B, a.n_cons);
-  const int par = blk & 1;
+// One CTA scores one job against ALL offers (snapshot state).  Thread t scans
+// v = t, t+256, ... (coalesced); v mod 32 == lane, so every thread's VMs belong
+// to chunk `lane`.  Each thread keeps its best TOPK (fitness desc, v asc); the 8
+// warps' lists are merged per lane through shared memory into the row.
+struct EvalShared {
+  double f[RES_THREADS / 32][TOPK][32];
+  int32_t v[RES_THREADS / 32][TOPK][32];
+};
+
+__device__ __forceinline__ bool better(double f, int v, double g, int w) {
+  return f > g || (f == g && v < w);
+}
+
+template <bool CONSTR, bool PROF>
+__device__ void evaluate_row(const MatchArgs& a, int k, int blk, EvalShared& E, unsigned long long* ep) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  long long e0 = PROF ? clock64() : 0;
+  const int snap = blk & 1;  // rows of block b are scored against S_{b-2} = buffer b&1
   const double* asg_c = a.dyn.asg_c[snap];
   const double* asg_m = a.dyn.asg_m[snap];
   const int32_t* asg_n = a.dyn.asg_n[snap];
   const int32_t* pus = a.dyn.ports_used[snap];
-  for (int k = k0 + warp_id; k < k1; k += n_warps) {
-    double f1 = 0.0, f2 = 0.0;
-    int v1 = -1, v2 = -1;
-    const bool grp = CONSTR && (a.kflags[k] & 1);
-    if (!grp) {
-      JobRegs r = load_job<CONSTR>(a, k);
-#pragma unroll 2
-      for (int v = lane; v < a.of.O; v += 32) {
-        double f = eval_vm<CONSTR>(a, r, v, __ldcg(asg_c + v), __ldcg(asg_m + v),
-                                   CONSTR ? __ldcg(asg_n + v) : 0, CONSTR ? __ldcg(pus + v) : 0,
-                                   __ldg(a.of.lease_c + v), __ldg(a.of.lease_m + v),
-                                   __ldg(a.of.run_c + v), __ldg(a.of.run_m + v), false);
-        if (f > f1) { f2 = f1; v2 = v1; f1 = f; v1 = v; }
-        else if (f > f2) { f2 = f; v2 = v; }
+  double f[TOPK];
+  int vv[TOPK];
+#pragma unroll
+  for (int i = 0; i < TOPK; i++) { f[i] = 0.0; vv[i] = -1; }
+  const bool grp = CONSTR && (a.kflags[k] & 1);
+  if (!grp) {
+    const JobRegs r = load_job<CONSTR>(a, k);
+#pragma unroll 4
+    for (int v = tid; v < a.of.O; v += RES_THREADS) {
+      double x = eval_vm<CONSTR>(a, r, v, __ldcg(asg_c + v), __ldcg(asg_m + v),
+                                 CONSTR ? __ldcg(asg_n + v) : 0, CONSTR ? __ldcg(pus + v) : 0,
+                                 __ldg(a.of.lease_c + v), __ldg(a.of.lease_m + v),
+                                 __ldg(a.of.run_c + v), __ldg(a.of.run_m + v), false);
+      if (x > f[TOPK - 1]) {  // v ascends within a thread: strict > keeps the lower v on ties
+        f[TOPK - 1] = x; vv[TOPK - 1] = v;
+#pragma unroll
+        for (int i = TOPK - 1; i > 0; i--) {
+          if (f[i] > f[i - 1]) {
+            double tf = f[i]; f[i] = f[i - 1]; f[i - 1] = tf;
+            int tv = vv[i]; vv[i] = vv[i - 1]; vv[i - 1] = tv;
+          }
+        }
       }
     }
-    const size_t base = ((size_t)par * a.B + (k - k0)) * 64;
-    a.row_f[base + lane] = f1;
-    a.row_f[base + 32 + lane] = f2;
-    a.row_v[base + lane] = v1;
-    a.row_v[base + 32 + lane] = v2;
+  }
+  long long e1 = PROF ? clock64() : 0;
+#pragma unroll
+  for (int i = 0; i < TOPK; i++) { E.f[warp][i][lane] = f[i]; E.v[warp][i][lane] = vv[i]; }
+  __syncthreads();
+  long long e2 = PROF ? clock64() : 0;
+  if (warp == 0) {
+    for (int w = 1; w < RES_THREADS / 32; w++) {
+#pragma unroll 1
+      for (int i = 0; i < TOPK; i++) {
+        double x = E.f[w][i][lane];
+        int xv = E.v[w][i][lane];
+        if (!(x > 0.0) || !better(x, xv, f[TOPK - 1], vv[TOPK - 1])) break;  // lists are sorted
+        f[TOPK - 1] = x; vv[TOPK - 1] = xv;
+#pragma unroll
+        for (int q = TOPK - 1; q > 0; q--) {
+          if (better(f[q], vv[q], f[q - 1], vv[q - 1])) {
+            double tf = f[q]; f[q] = f[q - 1]; f[q - 1] = tf;
+            int tv = vv[q]; vv[q] = vv[q - 1]; vv[q - 1] = tv;
+          }
+        }
+      }
+    }
+    const size_t base = ((size_t)(blk & 1) * a.B + (k - blk * a.B)) * (TOPK * 32);
+#pragma unroll
+    for (int i = 0; i < TOPK; i++) {
+      __stcg(a.row_f + base + i * 32 + lane, f[i]);
+      __stcg(a.row_v + base + i * 32 + lane, vv[i]);
+    }
+    unsigned any = __ballot_sync(0xffffffffu, f[0] > 0.0);
+    if (lane == 0) {
+      __stcg(a.feas + (size_t)(blk & 1) * a.B + (k - blk * a.B), (uint8_t)((any != 0u || grp) ? 1 : 0));
+      __threadfence();
+      atomicAdd(a.rows_ready + blk, 1u);
+    }
+  }
+  __syncthreads();
+  if (PROF) {
+    long long e3 = clock64();
+    ep[0] += (unsigned long long)(e1 - e0); ep[1] += (unsigned long long)(e2 - e1);
+    ep[2] += (unsigned long long)(e3 - e2);
   }
 }
 
@@ -342,6 +386,7 @@ struct ResolverShared {
   double d_ac[MAXD], d_am[MAXD];
   double d_lc[MAXD], d_lm[MAXD], d_rc[MAXD], d_rm[MAXD];
   int32_t d_vm[MAXD], d_an[MAXD], d_pu[MAXD], d_touch[MAXD];
+  int16_t feas_list[MAXB];
 };
 
 __device__ __forceinline__ double warp_max_f64(double f) {  // f >= 0
@@ -352,19 +397,191 @@ __device__ __forceinline__ double warp_max_f64(double f) {  // f >= 0
   return __hiloint2double((int)mh, (int)ml);
 }
 
+struct Row {
+  double f[TOPK];
+  int v[TOPK];
+  JobRegs r;  // the job's request, prefetched with its row
+};
+
 template <bool CONSTR>
-__device__ void resolve_block(const MatchArgs& a, int blk, ResolverShared& S, unsigned* bitmap,
-                              int& nD, unsigned long long* lstats) {
+__device__ __forceinline__ void load_row(const MatchArgs& a, int blk, int k, int lane, Row& r) {
+  r.r = load_job<CONSTR>(a, k);
+  const size_t base = ((size_t)(blk & 1) * a.B + (k - blk * a.B)) * (TOPK * 32);
+#pragma unroll
+  for (int i = 0; i < TOPK; i++) {
+    r.f[i] = __ldcg(a.row_f + base + i * 32 + lane);
+    r.v[i] = __ldcg(a.row_v + base + i * 32 + lane);
+  }
+}
+
+template <bool CONSTR, bool PROF>
+__device__ void resolve_job(const MatchArgs& a, int blk, int k, const Row& row, ResolverShared& S,
+                            unsigned* bitmap, int& nD, unsigned long long* lstats,
+                            unsigned long long* prof, long long& tp0) {
   const int lane = threadIdx.x & 31;
-  const int k0 = blk * a.B;
-  const int k1 = min(k0 + a.B, a.n_cons);
-  const int par = blk & 1;
-  const int snap = blk & 1;  // rows of block t were scored (in slot t-1) against S_{t-2} = buffer (t-2)&1
+  const int snap = blk & 1;
   const double* s_asg_c = a.dyn.asg_c[snap];
   const double* s_asg_m = a.dyn.asg_m[snap];
   const int32_t* s_asg_n = a.dyn.asg_n[snap];
   const int32_t* s_pus = a.dyn.ports_used[snap];
+  long long tp1 = 0;
+#define PROF_LAP(i) do { if (PROF) { tp1 = clock64(); prof[i] += (unsigned long long)(tp1 - tp0); tp0 = tp1; } } while (0)
+  const JobRegs r = row.r;
+  const bool grp = CONSTR && (a.kflags[k] & 1);
+  double cf = 0.0, bound = 0.0;
+  int cv = 0x7fffffff, cslot = -1;
+  if (!grp) {
+    // first clean candidate of my chunk; if all TOPK are dirty the rest of the
+    // chunk is bounded above by the last one's fitness.  All dirty bits are
+    // fetched at once (independent shared loads), then scanned.
+    unsigned dirty_bits = 0u, live_bits = 0u;
+#pragma unroll
+    for (int i = 0; i < TOPK; i++) {
+      const bool live = row.f[i] > 0.0;
+      const int vi = live ? row.v[i] : 0;
+      const unsigned w = bitmap[vi >> 5];
+      live_bits |= (live ? 1u : 0u) << i;
+      dirty_bits |= (((w >> (vi & 31)) & 1u) & (live ? 1u : 0u)) << i;
+    }
+    // entries are sorted: live_bits is a prefix mask.  first live&clean entry:
+    const unsigned clean = live_bits & ~dirty_bits;
+    if (clean) {
+      const int i = __ffs(clean) - 1;
+#pragma unroll
+      for (int q = 0; q < TOPK; q++)
+        if (q == i) { cf = row.f[q]; cv = row.v[q]; }
+    } else if (live_bits == ((1u << TOPK) - 1u)) {
+      bound = row.f[TOPK - 1];  // full list, all dirty
+    }
+  }
+  // prefetch the snapshot state of my clean candidate: if it wins, the commit
+  // needs it (new dirty entry) and must not wait for L2 then.
+  double p_ac = 0.0, p_am = 0.0, p_lc = 0.0, p_lm = 0.0, p_rc = 0.0, p_rm = 0.0;
+  int p_an = 0, p_pu = 0;
+  if (cv != 0x7fffffff) {
+    p_ac = __ldcg(s_asg_c + cv); p_am = __ldcg(s_asg_m + cv);
+    if (CONSTR) { p_an = __ldcg(s_asg_n + cv); p_pu = __ldcg(s_pus + cv); }
+    p_lc = __ldg(a.of.lease_c + cv); p_lm = __ldg(a.of.lease_m + cv);
+    p_rc = __ldg(a.of.run_c + cv); p_rm = __ldg(a.of.run_m + cv);
+  }
+  PROF_LAP(1);
+  if (PROF) prof[6] += nD;
+  // exact re-evaluation of dirty VMs against their current state
+  for (int d = lane; d < nD; d += 32) {
+    double f = eval_vm<CONSTR>(a, r, S.d_vm[d], S.d_ac[d], S.d_am[d], S.d_an[d], S.d_pu[d],
+                               S.d_lc[d], S.d_lm[d], S.d_rc[d], S.d_rm[d], grp);
+    int v = S.d_vm[d];
+    if (f > cf || (f == cf && f > 0.0 && v < cv)) { cf = f; cv = v; cslot = d; }
+  }
+  bool did_rescan = false;
+  __syncwarp();
+  PROF_LAP(2);
+  if (grp) {
+    // full re-scan of clean VMs against current group state
+    for (int v = lane; v < a.of.O; v += 32) {
+      if ((bitmap[v >> 5] >> (v & 31)) & 1u) continue;
+      double f = eval_vm<CONSTR>(a, r, v, __ldcg(s_asg_c + v), __ldcg(s_asg_m + v),
+                                 CONSTR ? __ldcg(s_asg_n + v) : 0, CONSTR ? __ldcg(s_pus + v) : 0,
+                                 a.of.lease_c[v], a.of.lease_m[v], a.of.run_c[v], a.of.run_m[v], true);
+      if (f > cf || (f == cf && f > 0.0 && v < cv)) { cf = f; cv = v; cslot = -2; }
+    }
+    lstats[2]++;
+  } else {
+    double wf0 = warp_max_f64(cf);
+    double mb = warp_max_f64(bound);
+    if (mb > 0.0 && mb >= wf0) {
+      unsigned need = __ballot_sync(0xffffffffu, bound > 0.0 && bound >= wf0);
+      did_rescan = true;
+      while (need) {
+        int c = __ffs(need) - 1;
+        need &= need - 1;
+        for (int v = c + 32 * lane; v < a.of.O; v += 32 * 32) {
+          if ((bitmap[v >> 5] >> (v & 31)) & 1u) continue;
+          double f = eval_vm<CONSTR>(a, r, v, __ldcg(s_asg_c + v), __ldcg(s_asg_m + v),
+                                     CONSTR ? __ldcg(s_asg_n + v) : 0, CONSTR ? __ldcg(s_pus + v) : 0,
+                                     a.of.lease_c[v], a.of.lease_m[v], a.of.run_c[v], a.of.run_m[v],
+                                     false);
+          if (f > cf || (f == cf && f > 0.0 && v < cv)) { cf = f; cv = v; cslot = -2; }
+        }
+        lstats[1]++;
+      }
+    }
+  }
+  __syncwarp();
+  PROF_LAP(3);
+  // argmax over lanes: max fitness, then lowest v
+  const double wf = warp_max_f64(cf);
+  if (wf > 0.0) {
+    unsigned key = (cf == wf) ? (unsigned)cv : 0xffffffffu;
+    unsigned mv = __reduce_min_sync(0xffffffffu, key);
+    const int wv = (int)mv;
+    const int wl = __ffs(__ballot_sync(0xffffffffu, key == mv)) - 1;
+    int slot = __shfl_sync(0xffffffffu, cslot, wl);
+    // commit (all lanes hold identical values; lane 0 writes).  slot -1: clean
+    // candidate with prefetched state in the winner lane; -2: found by a re-scan.
+    if (slot < 0) {
+      const bool pre = slot == -1;
+      double n_ac = __shfl_sync(0xffffffffu, p_ac, wl), n_am = __shfl_sync(0xffffffffu, p_am, wl);
+      double n_lc = __shfl_sync(0xffffffffu, p_lc, wl), n_lm = __shfl_sync(0xffffffffu, p_lm, wl);
+      double n_rc = __shfl_sync(0xffffffffu, p_rc, wl), n_rm = __shfl_sync(0xffffffffu, p_rm, wl);
+      int n_an = __shfl_sync(0xffffffffu, p_an, wl), n_pu = __shfl_sync(0xffffffffu, p_pu, wl);
+      slot = nD;
+      if (lane == 0) {
+        if (!pre) {
+          n_ac = __ldcg(s_asg_c + wv); n_am = __ldcg(s_asg_m + wv);
+          n_an = CONSTR ? __ldcg(s_asg_n + wv) : 0; n_pu = CONSTR ? __ldcg(s_pus + wv) : 0;
+          n_lc = a.of.lease_c[wv]; n_lm = a.of.lease_m[wv]; n_rc = a.of.run_c[wv]; n_rm = a.of.run_m[wv];
+        }
+        S.d_vm[slot] = wv;
+        S.d_ac[slot] = n_ac; S.d_am[slot] = n_am; S.d_an[slot] = n_an; S.d_pu[slot] = n_pu;
+        S.d_lc[slot] = n_lc; S.d_lm[slot] = n_lm; S.d_rc[slot] = n_rc; S.d_rm[slot] = n_rm;
+        bitmap[wv >> 5] |= 1u << (wv & 31);
+      }
+      nD++;
+    }
+    if (lane == 0) {
+      a.ports_start[k] = S.d_pu[slot];
+      S.d_ac[slot] = S.d_ac[slot] + r.c;
+      S.d_am[slot] = S.d_am[slot] + r.m;
+      S.d_an[slot] += 1;
+      S.d_pu[slot] += r.ports;
+      S.d_touch[slot] = blk;
+      a.assign[k] = wv;
+      a.fail[k] = COOK_FAIL_NONE;
+      if (CONSTR && grp) {
+        for (int q = a.jb.group_off[r.j]; q < a.jb.group_off[r.j + 1]; q++) {
+          int g = a.jb.group_idx[q];
+          int n = __ldcg(a.gr.gp_n + g);
+          a.gr.gp_vm[a.gr.gp_off[g] + n] = wv;
+          __threadfence_block();
+          a.gr.gp_n[g] = n + 1;
+        }
+      }
+    }
+    lstats[3]++;
+    __syncwarp();
+  } else {
+    if (lane == 0) { a.assign[k] = -1; a.fail[k] = COOK_FAIL_CONSTRAINT; }
+  }
+  if (!did_rescan && !grp) lstats[0]++;
+  PROF_LAP(4);
+#undef PROF_LAP
+}
 
+template <bool CONSTR, bool PROF>
+__device__ void resolve_block(const MatchArgs& a, int blk, ResolverShared& S, unsigned* bitmap,
+                              int& nD, unsigned long long* lstats, unsigned long long* prof) {
+  const int lane = threadIdx.x & 31;
+  const int k0 = blk * a.B;
+  const int k1 = min(k0 + a.B, a.n_cons);
+  const int nj = k1 - k0;
+  long long tp0 = PROF ? clock64() : 0, tp1;
+#define PROF_LAP(i) do { if (PROF) { tp1 = clock64(); prof[i] += (unsigned long long)(tp1 - tp0); tp0 = tp1; } } while (0)
+  // rows of this block ready?
+  if (lane == 0)
+    while (ld_acquire_u32(a.rows_ready + blk) < (unsigned)nj) __nanosleep(20);
+  __syncwarp();
+  PROF_LAP(9);
   // drop dirty entries not touched in the previous block: they are part of the
   // snapshot this block's rows were scored against.
   {
@@ -390,166 +607,109 @@ __device__ void resolve_block(const MatchArgs& a, int blk, ResolverShared& S, un
     }
     nD = keep_n;
   }
-
-  for (int k = k0; k < k1; k++) {
-    const size_t base = ((size_t)par * a.B + (k - k0)) * 64;
-    const double f1 = __ldcg(a.row_f + base + lane), f2 = __ldcg(a.row_f + base + 32 + lane);
-    const int v1 = __ldcg(a.row_v + base + lane), v2 = __ldcg(a.row_v + base + 32 + lane);
-    const JobRegs r = load_job<CONSTR>(a, k);
-    const bool grp = CONSTR && (a.kflags[k] & 1);
-
-    double cf = 0.0, bound = 0.0;
-    int cv = 0x7fffffff, cslot = -1;
-    if (!grp) {
-      if (__ballot_sync(0xffffffffu, f1 > 0.0) == 0u) {
-        // nothing fit at the snapshot; resources/constraints only tighten
-        // within a cycle for non-group jobs => unplaceable now too.
-        if (lane == 0) { a.assign[k] = -1; a.fail[k] = COOK_FAIL_RESOURCES; }
-        lstats[0]++;
-        continue;
-      }
-      if (f1 > 0.0) {
-        if (!((bitmap[v1 >> 5] >> (v1 & 31)) & 1u)) { cf = f1; cv = v1; }
-        else if (f2 > 0.0) {
-          if (!((bitmap[v2 >> 5] >> (v2 & 31)) & 1u)) { cf = f2; cv = v2; }
-          else bound = f2;
-        }
-      }
+  PROF_LAP(0);
+  // jobs with no feasible VM at the snapshot are unplaceable now too (resources
+  // and count constraints only tighten within a cycle): skip them wholesale.
+  const uint8_t* feas = a.feas + (size_t)(blk & 1) * a.B;
+  int nfeas = 0;
+  for (int base = 0; base < nj; base += 32) {
+    const int i = base + lane;
+    const bool valid = i < nj;
+    const bool fz = valid && __ldcg(feas + i) != 0;
+    if (valid && !fz) { a.assign[k0 + i] = -1; a.fail[k0 + i] = COOK_FAIL_RESOURCES; }
+    const unsigned mask = __ballot_sync(0xffffffffu, fz);
+    const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+    const int nskip = __popc(vmask & ~mask);
+    lstats[0] += nskip;
+    if (PROF) prof[7] += nskip;
+    if (fz) S.feas_list[nfeas + __popc(mask & ((1u << lane) - 1u))] = (int16_t)i;
+    nfeas += __popc(mask);
+  }
+  __syncwarp();
+  {
+    Row cur, nxt, nx2;
+    if (nfeas > 0) load_row<CONSTR>(a, blk, k0 + S.feas_list[0], lane, cur);
+    if (nfeas > 1) load_row<CONSTR>(a, blk, k0 + S.feas_list[1], lane, nxt);
+    PROF_LAP(1);
+    for (int q = 0; q < nfeas; q++) {
+      const int kcur = k0 + S.feas_list[q];
+      if (q + 2 < nfeas) load_row<CONSTR>(a, blk, k0 + S.feas_list[q + 2], lane, nx2);
+      resolve_job<CONSTR, PROF>(a, blk, kcur, cur, S, bitmap, nD, lstats, prof, tp0);
+      cur = nxt;
+      nxt = nx2;
     }
-    // exact re-evaluation of dirty VMs against their current state
-    for (int d = lane; d < nD; d += 32) {
-      double f = eval_vm<CONSTR>(a, r, S.d_vm[d], S.d_ac[d], S.d_am[d], S.d_an[d], S.d_pu[d],
-                                 S.d_lc[d], S.d_lm[d], S.d_rc[d], S.d_rm[d], grp);
-      int v = S.d_vm[d];
-      if (f > cf || (f == cf && f > 0.0 && v < cv)) { cf = f; cv = v; cslot = d; }
-    }
-    bool did_rescan = false;
-    if (grp) {
-      // full re-scan of clean VMs against current group state
-      for (int v = lane; v < a.of.O; v += 32) {
-        if ((bitmap[v >> 5] >> (v & 31)) & 1u) continue;
-        double f = eval_vm<CONSTR>(a, r, v, __ldcg(s_asg_c + v), __ldcg(s_asg_m + v),
-                                   CONSTR ? __ldcg(s_asg_n + v) : 0, CONSTR ? __ldcg(s_pus + v) : 0,
-                                   a.of.lease_c[v], a.of.lease_m[v], a.of.run_c[v], a.of.run_m[v], true);
-        if (f > cf || (f == cf && f > 0.0 && v < cv)) { cf = f; cv = v; cslot = -1; }
-      }
-      lstats[2]++;
-    } else {
-      double wf0 = warp_max_f64(cf);
-      double mb = warp_max_f64(bound);
-      if (mb > 0.0 && mb >= wf0) {
-        unsigned need = __ballot_sync(0xffffffffu, bound > 0.0 && bound >= wf0);
-        did_rescan = true;
-        while (need) {
-          int c = __ffs(need) - 1;
-          need &= need - 1;
-          for (int v = c + 32 * lane; v < a.of.O; v += 32 * 32) {
-            if ((bitmap[v >> 5] >> (v & 31)) & 1u) continue;
-            double f = eval_vm<CONSTR>(a, r, v, __ldcg(s_asg_c + v), __ldcg(s_asg_m + v),
-                                       CONSTR ? __ldcg(s_asg_n + v) : 0, CONSTR ? __ldcg(s_pus + v) : 0,
-                                       a.of.lease_c[v], a.of.lease_m[v], a.of.run_c[v], a.of.run_m[v],
-                                       false);
-            if (f > cf || (f == cf && f > 0.0 && v < cv)) { cf = f; cv = v; cslot = -1; }
-          }
-          lstats[1]++;
-        }
-      }
-    }
-    // argmax over lanes: max fitness, then lowest v
-    const double wf = warp_max_f64(cf);
-    int wv = -1;
-    if (wf > 0.0) {
-      unsigned key = (cf == wf) ? (unsigned)cv : 0xffffffffu;
-      unsigned mv = __reduce_min_sync(0xffffffffu, key);
-      wv = (int)mv;
-      const int wl = __ffs(__ballot_sync(0xffffffffu, key == mv)) - 1;
-      int slot = __shfl_sync(0xffffffffu, cslot, wl);
-      // commit (all lanes hold identical values; lane 0 writes)
-      if (slot < 0) {
-        slot = nD;
-        if (lane == 0) {
-          S.d_vm[slot] = wv;
-          S.d_ac[slot] = __ldcg(s_asg_c + wv); S.d_am[slot] = __ldcg(s_asg_m + wv);
-          S.d_an[slot] = CONSTR ? __ldcg(s_asg_n + wv) : 0; S.d_pu[slot] = CONSTR ? __ldcg(s_pus + wv) : 0;
-          S.d_lc[slot] = a.of.lease_c[wv]; S.d_lm[slot] = a.of.lease_m[wv];
-          S.d_rc[slot] = a.of.run_c[wv]; S.d_rm[slot] = a.of.run_m[wv];
-          bitmap[wv >> 5] |= 1u << (wv & 31);
-        }
-        nD++;
-      }
-      if (lane == 0) {
-        a.ports_start[k] = S.d_pu[slot];
-        S.d_ac[slot] = S.d_ac[slot] + r.c;
-        S.d_am[slot] = S.d_am[slot] + r.m;
-        S.d_an[slot] += 1;
-        S.d_pu[slot] += r.ports;
-        S.d_touch[slot] = blk;
-        a.assign[k] = wv;
-        a.fail[k] = COOK_FAIL_NONE;
-        if (CONSTR && grp) {
-          for (int q = a.jb.group_off[r.j]; q < a.jb.group_off[r.j + 1]; q++) {
-            int g = a.jb.group_idx[q];
-            int n = __ldcg(a.gr.gp_n + g);
-            a.gr.gp_vm[a.gr.gp_off[g] + n] = wv;
-            __threadfence_block();
-            a.gr.gp_n[g] = n + 1;
-          }
-        }
-      }
-      lstats[3]++;
-      __syncwarp();
-    } else {
-      if (lane == 0) { a.assign[k] = -1; a.fail[k] = COOK_FAIL_CONSTRAINT; }
-    }
-    if (!did_rescan && !grp) lstats[0]++;
   }
   // publish every dirty entry (touched in this or the previous block) into the
-  // buffer the evaluators read in the next slot.
+  // buffer the evaluators read for block blk+2.
   {
     const int pub = blk & 1;
     for (int d = lane; d < nD; d += 32) {
       int v = S.d_vm[d];
-      a.dyn.asg_c[pub][v] = S.d_ac[d];
-      a.dyn.asg_m[pub][v] = S.d_am[d];
-      a.dyn.asg_n[pub][v] = S.d_an[d];
-      a.dyn.ports_used[pub][v] = S.d_pu[d];
+      __stcg(a.dyn.asg_c[pub] + v, S.d_ac[d]);
+      __stcg(a.dyn.asg_m[pub] + v, S.d_am[d]);
+      __stcg(a.dyn.asg_n[pub] + v, S.d_an[d]);
+      __stcg(a.dyn.ports_used[pub] + v, S.d_pu[d]);
     }
+    __syncwarp();
+    if (lane == 0) {
+      __threadfence();
+      asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(a.published), "r"((unsigned)(blk + 1)) : "memory");
+    }
+    __syncwarp();
   }
-  __syncwarp();
+  PROF_LAP(5);
+#undef PROF_LAP
 }
 
-// Pipeline: slot t in [-1, nblk): resolver places block t (rows scored against
-// buffer (t-2)&1 == t&1 ... see below), evaluators score block t+1 against the
-// state published after block t-1, i.e. buffer (t-1)&1.
-template <bool CONSTR>
+// Pipeline.  The resolver (warp 0 of CTA 0) places block t while the evaluator
+// CTAs score block t+1 against the state published after block t-1 (buffer
+// (t+1)&1).  Synchronisation is by two monotone counters only:
+//   rows_ready[b]  evaluators -> resolver (one arrival per scored row)
+//   published      resolver -> evaluators (# blocks resolved and published)
+template <bool CONSTR, bool PROF>
 __global__ void __launch_bounds__(RES_THREADS, 1) match_kernel(MatchArgs a) {
   extern __shared__ unsigned char smem_raw[];
-  ResolverShared& S = *reinterpret_cast<ResolverShared*>(smem_raw);
-  unsigned* bitmap = reinterpret_cast<unsigned*>(smem_raw + sizeof(ResolverShared));
   const int nblk = (a.n_cons + a.B - 1) / a.B;
-  unsigned epoch = 0;
-  int nD = 0;
-  unsigned long long lstats[4] = {0, 0, 0, 0};
-  const bool is_res = blockIdx.x == 0;
-  const int warps_per_cta = RES_THREADS / 32;
-  const int n_eval_warps = (gridDim.x - 1) * warps_per_cta;
-  const int eval_warp = (blockIdx.x - 1) * warps_per_cta + (threadIdx.x >> 5);
-  if (is_res) {
+  if (blockIdx.x == 0) {
+    ResolverShared& S = *reinterpret_cast<ResolverShared*>(smem_raw);
+    unsigned* bitmap = reinterpret_cast<unsigned*>(smem_raw + sizeof(ResolverShared));
     const int words = (a.of.O + 31) / 32;
     for (int i = threadIdx.x; i < words; i += RES_THREADS) bitmap[i] = 0u;
-  }
-  __syncthreads();
-  for (int t = -1; t < nblk; t++) {
-    if (is_res) {
-      if (t >= 0 && threadIdx.x < 32) resolve_block<CONSTR>(a, t, S, bitmap, nD, lstats);
-    } else if (t + 1 < nblk) {
-      // rows of block t+1 are scored against S_{t-1} = buffer (t-1)&1 = (t+1)&1
-      evaluate_block<CONSTR>(a, t + 1, (t + 1) & 1, eval_warp, n_eval_warps);
+    __syncthreads();
+    if (threadIdx.x >= 32) return;
+    int nD = 0;
+    unsigned long long lstats[4] = {0, 0, 0, 0};
+    unsigned long long prof[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    long long t0 = clock64();
+    for (int t = 0; t < nblk; t++) resolve_block<CONSTR, PROF>(a, t, S, bitmap, nD, lstats, prof);
+    prof[8] = (unsigned long long)(clock64() - t0);
+    if (threadIdx.x == 0) {
+      a.stats[0] = lstats[0]; a.stats[1] = lstats[1]; a.stats[2] = lstats[2]; a.stats[3] = lstats[3];
+      for (int i = 0; i < 10; i++) a.stats[4 + i] = prof[i];
     }
-    grid_barrier(a.barrier, epoch);
-  }
-  if (is_res && threadIdx.x == 0) {
-    a.stats[0] = lstats[0]; a.stats[1] = lstats[1]; a.stats[2] = lstats[2]; a.stats[3] = lstats[3];
+  } else {
+    EvalShared& E = *reinterpret_cast<EvalShared*>(smem_raw);
+    const int n_eval = gridDim.x - 1;
+    unsigned long long work = 0, wait = 0;
+    unsigned long long ep[3] = {0, 0, 0};
+    for (int b = 0; b < nblk; b++) {
+      const int k0 = b * a.B, k1 = min(k0 + a.B, a.n_cons);
+      long long w0 = clock64();
+      // rows of block b need S_{b-2}: published >= b-1
+      if (b >= 2) {
+        if (threadIdx.x == 0)
+          while ((int)ld_acquire_u32(a.published) < b - 1) __nanosleep(32);
+        __syncthreads();
+      }
+      long long w1 = clock64();
+      for (int k = k0 + (int)blockIdx.x - 1; k < k1; k += n_eval) evaluate_row<CONSTR, PROF>(a, k, b, E, ep);
+      wait += (unsigned long long)(w1 - w0);
+      work += (unsigned long long)(clock64() - w1);
+    }
+    if (blockIdx.x == 1 && threadIdx.x == 0) {
+      a.stats[14] = work; a.stats[15] = wait;
+      if (PROF) { a.stats[16] = ep[0]; a.stats[17] = ep[1]; a.stats[18] = ep[2]; }
+    }
   }
 }
 
@@ -828,7 +988,8 @@ static int32_t build_plan(cook_pool* pool, MatchPlan* mp, const int32_t* ranked_
   if (!constr_eff && jobs->ports)
     for (int j = 0; j < J && !constr_eff; j++) constr_eff = jobs->ports[j] != 0;
 
-  const int B = 128;
+  int B = 128;
+  if (const char* eb = getenv("COOK_MATCH_B")) { int v = atoi(eb); if (v >= 8 && v <= MAXB) B = v; }
   Sizer sz;
   sz.add<int32_t>(n_ranked);
   for (int k = 0; k < 3; k++) sz.add<double>(J + 1);
@@ -858,11 +1019,12 @@ static int32_t build_plan(cook_pool* pool, MatchPlan* mp, const int32_t* ranked_
   for (int k = 0; k < 6; k++) sz.add<int32_t>(n_ranked + 1);
   sz.add<uint8_t>(n_ranked + 1);
   sz.add<int32_t>(NC + 1); sz.add<double>(NC + 1); sz.add<double>(NC + 1); sz.add<uint8_t>(NC + 1);
-  sz.add<double>((size_t)2 * B * 64); sz.add<int32_t>((size_t)2 * B * 64);
+  sz.add<double>((size_t)2 * B * TOPK * 32); sz.add<int32_t>((size_t)2 * B * TOPK * 32);
+  sz.add<uint8_t>(2 * B + 16); sz.add<unsigned>((size_t)NC / B + 16);
   sz.add<int32_t>(NC + 1); sz.add<int32_t>(NC + 1); sz.add<uint8_t>(NC + 1);
   sz.add<int32_t>(NC + 1); sz.add<int32_t>((size_t)NC * std::max(max_ports, 1) + 1);
   sz.add<int32_t>(O + 1);
-  sz.add<unsigned long long>(16); sz.add<int32_t>(16);
+  sz.add<unsigned long long>(32); sz.add<int32_t>(16);
   CK(pool, ar.reserve(sz.off + (1 << 18)));
   ar.reset();
 
@@ -965,21 +1127,23 @@ static int32_t build_plan(cook_pool* pool, MatchPlan* mp, const int32_t* ranked_
   mp->d_kc = ar.take<double>(NC + 1);
   mp->d_km = ar.take<double>(NC + 1);
   mp->d_kflags = ar.take<uint8_t>(NC + 1);
-  ma.row_f = ar.take<double>((size_t)2 * B * 64);
-  ma.row_v = ar.take<int32_t>((size_t)2 * B * 64);
+  ma.row_f = ar.take<double>((size_t)2 * B * TOPK * 32);
+  ma.row_v = ar.take<int32_t>((size_t)2 * B * TOPK * 32);
+  ma.feas = ar.take<uint8_t>(2 * B + 16);
+  ma.rows_ready = ar.take<unsigned>((size_t)NC / B + 16);
   ma.assign = ar.take<int32_t>(NC + 1);
   ma.ports_start = ar.take<int32_t>(NC + 1);
   ma.fail = ar.take<uint8_t>(NC + 1);
   mp->d_out_assign = ar.take<int32_t>(NC + 1);
   mp->d_out_ports = ar.take<int32_t>((size_t)NC * std::max(max_ports, 1) + 1);
   mp->d_used = ar.take<int32_t>(O + 1);
-  mp->d_stats = ar.take<unsigned long long>(16);
+  mp->d_stats = ar.take<unsigned long long>(32);
   mp->d_counters = ar.take<int32_t>(16);
   if (!mp->d_counters) return set_err(pool, COOK_E_OOM, "cook_match: arena exhausted");
   ma.jb = jb; ma.of = of; ma.gr = gr;
   ma.cons = mp->d_cons; ma.kc = mp->d_kc; ma.km = mp->d_km; ma.kflags = mp->d_kflags;
   ma.B = B; ma.host_lifetime_mins = params->host_lifetime_mins;
-  ma.barrier = reinterpret_cast<unsigned*>(mp->d_counters + 8); ma.stats = mp->d_stats;
+  ma.published = reinterpret_cast<unsigned*>(mp->d_counters + 8); ma.stats = mp->d_stats;
   mp->J = J; mp->O = O; mp->U = U; mp->n_ranked = n_ranked; mp->NC = NC; mp->max_ports = max_ports;
   mp->G = G; mp->B = B; mp->constr = constr_eff; mp->n_memb = n_memb;
   mp->valid = true;
@@ -1005,8 +1169,9 @@ static int32_t run_plan(cook_pool* pool, MatchPlan* mp, int32_t* out_considerabl
   CK(pool, cudaMemsetAsync(mp->d_seg_s, 0, sizeof(int32_t) * (U + 1), st));
   CK(pool, cudaMemsetAsync(mp->d_seg_e, 0, sizeof(int32_t) * (U + 1), st));
   CK(pool, cudaMemsetAsync(mp->d_used, 0, sizeof(int32_t) * (O + 1), st));
-  CK(pool, cudaMemsetAsync(mp->d_stats, 0, sizeof(unsigned long long) * 16, st));
+  CK(pool, cudaMemsetAsync(mp->d_stats, 0, sizeof(unsigned long long) * 32, st));
   CK(pool, cudaMemsetAsync(mp->d_counters, 0, sizeof(int32_t) * 16, st));
+  CK(pool, cudaMemsetAsync(ma.rows_ready, 0, sizeof(unsigned) * ((size_t)mp->NC / mp->B + 16), st));
   CK(pool, cudaEventRecord(pool->ev[1], st));
 
   // ---- M0 considerable
@@ -1041,17 +1206,20 @@ static int32_t run_plan(cook_pool* pool, MatchPlan* mp, int32_t* out_considerabl
   // ---- M3 matcher
   ma.n_cons = n_cons;
   int n_used = 0;
-  unsigned long long hstats[4] = {0, 0, 0, 0};
+  unsigned long long hstats[32] = {0};
+  const bool prof_on = getenv("COOK_PROF") != nullptr;
   CK(pool, cudaEventRecord(pool->ev[5], st));
   if (n_cons > 0) {
     if (O == 0) {
       CK(pool, cudaMemsetAsync(ma.assign, 0xff, sizeof(int32_t) * n_cons, st));
       CK(pool, cudaMemsetAsync(ma.fail, COOK_FAIL_NO_OFFERS, n_cons, st));
     } else {
-      size_t smem = sizeof(ResolverShared) + sizeof(unsigned) * ((O + 31) / 32) + 16;
+      size_t smem = std::max(sizeof(ResolverShared) + sizeof(unsigned) * ((O + 31) / 32) + 16,
+                             sizeof(EvalShared));
       if (smem > 220 * 1024)
         return set_err(pool, COOK_E_BADARG, "cook_match: too many offers for the resolver bitmap (%d)", O);
-      void* kfn = mp->constr ? (void*)match_kernel<true> : (void*)match_kernel<false>;
+      void* kfn = mp->constr ? (prof_on ? (void*)match_kernel<true, true> : (void*)match_kernel<true, false>)
+                             : (prof_on ? (void*)match_kernel<false, true> : (void*)match_kernel<false, false>);
       CK(pool, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       int grid = pool->sm_count;
       int occ = 0;
@@ -1086,6 +1254,12 @@ static int32_t run_plan(cook_pool* pool, MatchPlan* mp, int32_t* out_considerabl
   }
   CK(pool, cudaEventRecord(pool->ev[4], st));
   CK(pool, cudaStreamSynchronize(st));
+  if (prof_on) {
+    const char* nm[15] = {"compact", "row+cand", "dirty_eval", "rescan", "reduce+commit", "publish",
+                          "sum_nD", "n_shortcut", "res_total", "res_wait_rows", "eval_work", "eval_wait",
+                          "eval_loop", "eval_sync", "eval_merge"};
+    for (int i = 0; i < 15; i++) fprintf(stderr, "[cook_prof] %-14s %llu\n", nm[i], hstats[4 + i]);
+  }
   if (out_stats) {
     out_stats->n_considerable = n_cons;
     out_stats->n_matched = (int)hstats[3];
