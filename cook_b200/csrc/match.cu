@@ -41,6 +41,14 @@ constexpr int RES_THREADS = 256;   // threads per CTA of the match kernel
 constexpr int MAXB = 256;          // max jobs per block
 constexpr int MAXD = 2 * MAXB;     // dirty list capacity (two blocks)
 constexpr int TOPK = 8;            // candidates kept per (job, chunk)
+constexpr int ROW_V_OFF = TOPK * 32 * 8;             // byte offset of the v part of a row
+constexpr int ROW_BYTES = TOPK * 32 * (8 + 4);       // 3072 B per job
+constexpr int RING = 4;                              // TMA row ring depth in the resolver
+
+// Per-VM state is AoS, 32 B per record, so one record is two 128-bit loads and a
+// clean candidate's state can be staged with 16-byte async copies.
+struct __align__(32) VmStatic { double lc, lm, rc, rm; };
+struct __align__(32) VmDyn { double ac, am; int an, pu; int pad0, pad1; };
 
 struct JobDev {   // columns in ORIGINAL job index space (may be null)
   const int32_t* user;
@@ -63,7 +71,7 @@ struct JobDev {   // columns in ORIGINAL job index space (may be null)
 struct OfferDev {
   int O;
   // hot columns, gathered into rank-sorted index space v
-  const double *lease_c, *lease_m, *run_c, *run_m;
+  const VmStatic* vs;   // {lease cpus, lease mem, running cpus, running mem} per VM
   const int32_t* perm;  // v -> original offer index
   // constraint columns, ORIGINAL index space (may be null)
   const int32_t* hostname_id;
@@ -90,10 +98,7 @@ struct GroupDev {
 };
 
 struct DynBuf {  // dynamic per-VM state, index space v, double buffered
-  double* asg_c[2];
-  double* asg_m[2];
-  int32_t* asg_n[2];
-  int32_t* ports_used[2];
+  VmDyn* d[2];
 };
 
 struct MatchArgs {
@@ -108,8 +113,9 @@ struct MatchArgs {
   const uint8_t* kflags;   // bit0: has groups
   int B;                   // jobs per block
   int host_lifetime_mins;
-  double* row_f;           // [2][B][TOPK][32]
-  int32_t* row_v;          // [2][B][TOPK][32]
+  unsigned char* rows;     // [2][B][ROW_BYTES]: f[TOPK][32] f64 then v[TOPK][32] i32
+  const double* kg;        // gathered gpus per k (constraint kernel)
+  const int32_t* kports;   // gathered port counts per k
   uint8_t* feas;           // [2][B] any feasible VM at the snapshot
   unsigned* rows_ready;    // [nblk] rows scored per block
   unsigned* published;     // # blocks resolved and published
@@ -138,8 +144,8 @@ __device__ __forceinline__ JobRegs load_job(const MatchArgs& a, int k) {
   r.j = a.cons[k];
   r.g = 0.0; r.ports = 0;
   if (CONSTR) {
-    r.g = a.jb.gpus ? a.jb.gpus[r.j] : 0.0;
-    r.ports = a.jb.ports ? a.jb.ports[r.j] : 0;
+    r.g = a.kg[k];
+    r.ports = a.kports[k];
   }
   return r;
 }
@@ -290,11 +296,50 @@ __device__ __forceinline__ double eval_vm(const MatchArgs& a, const JobRegs& r, 
   return fit_fitness(r.c, r.m, ac, am, lc, lm, rc, rm);
 }
 
+// ------------------------------------------------------------- PTX helpers
+__device__ __forceinline__ unsigned smem_u32(const void* p) {
+  return (unsigned)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}"
+      ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+// TMA (bulk async copy engine): global -> shared, completion on an mbarrier.
+__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, unsigned bytes,
+                                            unsigned long long* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+      ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void cp_async16_cg(void* dst_smem, const void* src_gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_wait_all() {
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
 // ------------------------------------------------------------- evaluators
 // One CTA scores one job against ALL offers (snapshot state).  Thread t scans
-// v = t, t+256, ... (coalesced); v mod 32 == lane, so every thread's VMs belong
-// to chunk `lane`.  Each thread keeps its best TOPK (fitness desc, v asc); the 8
-// warps' lists are merged per lane through shared memory into the row.
+// v = t, t+256, ... (coalesced 128-bit loads); v mod 32 == lane, so every
+// thread's VMs belong to chunk `lane`.  Each thread keeps its best TOPK
+// (fitness desc, v asc); the 8 warps' lists are tree-merged per lane through
+// shared memory into the row.
 struct EvalShared {
   double f[RES_THREADS / 32][TOPK][32];
   int32_t v[RES_THREADS / 32][TOPK][32];
@@ -304,15 +349,30 @@ __device__ __forceinline__ bool better(double f, int v, double g, int w) {
   return f > g || (f == g && v < w);
 }
 
+// merge the sorted list E[w] into the sorted register list (f, vv)
+__device__ __forceinline__ void merge_list(double* f, int* vv, const EvalShared& E, int w, int lane) {
+#pragma unroll 1
+  for (int i = 0; i < TOPK; i++) {
+    double x = E.f[w][i][lane];
+    int xv = E.v[w][i][lane];
+    if (!(x > 0.0) || !better(x, xv, f[TOPK - 1], vv[TOPK - 1])) break;  // lists are sorted
+    f[TOPK - 1] = x; vv[TOPK - 1] = xv;
+#pragma unroll
+    for (int q = TOPK - 1; q > 0; q--) {
+      if (better(f[q], vv[q], f[q - 1], vv[q - 1])) {
+        double tf = f[q]; f[q] = f[q - 1]; f[q - 1] = tf;
+        int tv = vv[q]; vv[q] = vv[q - 1]; vv[q - 1] = tv;
+      }
+    }
+  }
+}
+
 template <bool CONSTR, bool PROF>
 __device__ void evaluate_row(const MatchArgs& a, int k, int blk, EvalShared& E, unsigned long long* ep) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   long long e0 = PROF ? clock64() : 0;
-  const int snap = blk & 1;  // rows of block b are scored against S_{b-2} = buffer b&1
-  const double* asg_c = a.dyn.asg_c[snap];
-  const double* asg_m = a.dyn.asg_m[snap];
-  const int32_t* asg_n = a.dyn.asg_n[snap];
-  const int32_t* pus = a.dyn.ports_used[snap];
+  const double2* st2 = reinterpret_cast<const double2*>(a.of.vs);
+  const double2* dy2 = reinterpret_cast<const double2*>(a.dyn.d[blk & 1]);  // S_{b-2} = buffer b&1
   double f[TOPK];
   int vv[TOPK];
 #pragma unroll
@@ -322,10 +382,11 @@ __device__ void evaluate_row(const MatchArgs& a, int k, int blk, EvalShared& E, 
     const JobRegs r = load_job<CONSTR>(a, k);
 #pragma unroll 4
     for (int v = tid; v < a.of.O; v += RES_THREADS) {
-      double x = eval_vm<CONSTR>(a, r, v, __ldcg(asg_c + v), __ldcg(asg_m + v),
-                                 CONSTR ? __ldcg(asg_n + v) : 0, CONSTR ? __ldcg(pus + v) : 0,
-                                 __ldg(a.of.lease_c + v), __ldg(a.of.lease_m + v),
-                                 __ldg(a.of.run_c + v), __ldg(a.of.run_m + v), false);
+      const double2 s0 = __ldg(st2 + 2 * v), s1 = __ldg(st2 + 2 * v + 1);
+      const double2 d0 = __ldcg(dy2 + 2 * v);
+      int2 d1 = make_int2(0, 0);
+      if (CONSTR) d1 = __ldcg(reinterpret_cast<const int2*>(dy2 + 2 * v + 1));
+      double x = eval_vm<CONSTR>(a, r, v, d0.x, d0.y, d1.x, d1.y, s0.x, s0.y, s1.x, s1.y, false);
       if (x > f[TOPK - 1]) {  // v ascends within a thread: strict > keeps the lower v on ties
         f[TOPK - 1] = x; vv[TOPK - 1] = v;
 #pragma unroll
@@ -339,41 +400,38 @@ __device__ void evaluate_row(const MatchArgs& a, int k, int blk, EvalShared& E, 
     }
   }
   long long e1 = PROF ? clock64() : 0;
+  const int any = __syncthreads_or(f[0] > 0.0 ? 1 : 0);
+  if (any) {
+    // tree merge across the 8 warps: 3 levels
 #pragma unroll
-  for (int i = 0; i < TOPK; i++) { E.f[warp][i][lane] = f[i]; E.v[warp][i][lane] = vv[i]; }
-  __syncthreads();
+    for (int step = 1; step < RES_THREADS / 32; step <<= 1) {
+      if ((warp & (2 * step - 1)) == step) {
+#pragma unroll
+        for (int i = 0; i < TOPK; i++) { E.f[warp][i][lane] = f[i]; E.v[warp][i][lane] = vv[i]; }
+      }
+      __syncthreads();
+      if ((warp & (2 * step - 1)) == 0) merge_list(f, vv, E, warp + step, lane);
+      __syncthreads();
+    }
+  }
   long long e2 = PROF ? clock64() : 0;
   if (warp == 0) {
-    for (int w = 1; w < RES_THREADS / 32; w++) {
-#pragma unroll 1
-      for (int i = 0; i < TOPK; i++) {
-        double x = E.f[w][i][lane];
-        int xv = E.v[w][i][lane];
-        if (!(x > 0.0) || !better(x, xv, f[TOPK - 1], vv[TOPK - 1])) break;  // lists are sorted
-        f[TOPK - 1] = x; vv[TOPK - 1] = xv;
+    unsigned char* row = a.rows + ((size_t)(blk & 1) * a.B + (k - blk * a.B)) * ROW_BYTES;
+    if (any || grp) {
+      double* rf = reinterpret_cast<double*>(row);
+      int32_t* rv = reinterpret_cast<int32_t*>(row + ROW_V_OFF);
 #pragma unroll
-        for (int q = TOPK - 1; q > 0; q--) {
-          if (better(f[q], vv[q], f[q - 1], vv[q - 1])) {
-            double tf = f[q]; f[q] = f[q - 1]; f[q - 1] = tf;
-            int tv = vv[q]; vv[q] = vv[q - 1]; vv[q - 1] = tv;
-          }
-        }
+      for (int i = 0; i < TOPK; i++) {
+        __stcg(rf + i * 32 + lane, f[i]);
+        __stcg(rv + i * 32 + lane, vv[i]);
       }
     }
-    const size_t base = ((size_t)(blk & 1) * a.B + (k - blk * a.B)) * (TOPK * 32);
-#pragma unroll
-    for (int i = 0; i < TOPK; i++) {
-      __stcg(a.row_f + base + i * 32 + lane, f[i]);
-      __stcg(a.row_v + base + i * 32 + lane, vv[i]);
-    }
-    unsigned any = __ballot_sync(0xffffffffu, f[0] > 0.0);
     if (lane == 0) {
-      __stcg(a.feas + (size_t)(blk & 1) * a.B + (k - blk * a.B), (uint8_t)((any != 0u || grp) ? 1 : 0));
+      __stcg(a.feas + (size_t)(blk & 1) * a.B + (k - blk * a.B), (uint8_t)((any || grp) ? 1 : 0));
       __threadfence();
       atomicAdd(a.rows_ready + blk, 1u);
     }
   }
-  __syncthreads();
   if (PROF) {
     long long e3 = clock64();
     ep[0] += (unsigned long long)(e1 - e0); ep[1] += (unsigned long long)(e2 - e1);
@@ -383,10 +441,18 @@ __device__ void evaluate_row(const MatchArgs& a, int k, int blk, EvalShared& E, 
 
 // --------------------------------------------------------------- resolver
 struct ResolverShared {
+  // dirty list (VMs touched since the snapshot), SoA so lane d reads entry d
   double d_ac[MAXD], d_am[MAXD];
   double d_lc[MAXD], d_lm[MAXD], d_rc[MAXD], d_rm[MAXD];
   int32_t d_vm[MAXD], d_an[MAXD], d_pu[MAXD], d_touch[MAXD];
+  // per-block job requests
+  double jc[MAXB], jm[MAXB], jg[MAXB];
+  int32_t jports[MAXB], jj[MAXB];
+  uint8_t jgrp[MAXB];
   int16_t feas_list[MAXB];
+  // TMA-staged rows of the next feasible jobs
+  __align__(128) unsigned char rows[RING][ROW_BYTES];
+  unsigned long long bar[RING];
 };
 
 __device__ __forceinline__ double warp_max_f64(double f) {  // f >= 0
@@ -397,144 +463,125 @@ __device__ __forceinline__ double warp_max_f64(double f) {  // f >= 0
   return __hiloint2double((int)mh, (int)ml);
 }
 
-struct Row {
-  double f[TOPK];
-  int v[TOPK];
-  JobRegs r;  // the job's request, prefetched with its row
-};
-
-template <bool CONSTR>
-__device__ __forceinline__ void load_row(const MatchArgs& a, int blk, int k, int lane, Row& r) {
-  r.r = load_job<CONSTR>(a, k);
-  const size_t base = ((size_t)(blk & 1) * a.B + (k - blk * a.B)) * (TOPK * 32);
-#pragma unroll
-  for (int i = 0; i < TOPK; i++) {
-    r.f[i] = __ldcg(a.row_f + base + i * 32 + lane);
-    r.v[i] = __ldcg(a.row_v + base + i * 32 + lane);
-  }
+// argmax over lanes of (f desc, v asc).  Returns winner fitness; wv/wl = VM and lane.
+__device__ __forceinline__ double warp_argmax(double f, int v, int& wv, int& wl) {
+  const double wf = warp_max_f64(f);
+  unsigned key = (f == wf && wf > 0.0) ? (unsigned)v : 0xffffffffu;
+  unsigned mv = __reduce_min_sync(0xffffffffu, key);
+  wv = (int)mv;
+  wl = __ffs(__ballot_sync(0xffffffffu, key == mv)) - 1;
+  return wf;
 }
 
 template <bool CONSTR, bool PROF>
-__device__ void resolve_job(const MatchArgs& a, int blk, int k, const Row& row, ResolverShared& S,
-                            unsigned* bitmap, int& nD, unsigned long long* lstats,
-                            unsigned long long* prof, long long& tp0) {
+__device__ void resolve_job(const MatchArgs& a, int blk, int k, int ib, const unsigned char* rowp,
+                            ResolverShared& S, unsigned* bitmap, int& nD,
+                            unsigned long long* lstats, unsigned long long* prof, long long& tp0) {
   const int lane = threadIdx.x & 31;
-  const int snap = blk & 1;
-  const double* s_asg_c = a.dyn.asg_c[snap];
-  const double* s_asg_m = a.dyn.asg_m[snap];
-  const int32_t* s_asg_n = a.dyn.asg_n[snap];
-  const int32_t* s_pus = a.dyn.ports_used[snap];
+  const VmDyn* snapd = a.dyn.d[blk & 1];
   long long tp1 = 0;
 #define PROF_LAP(i) do { if (PROF) { tp1 = clock64(); prof[i] += (unsigned long long)(tp1 - tp0); tp0 = tp1; } } while (0)
-  const JobRegs r = row.r;
-  const bool grp = CONSTR && (a.kflags[k] & 1);
+  JobRegs r;
+  r.c = S.jc[ib]; r.m = S.jm[ib]; r.g = CONSTR ? S.jg[ib] : 0.0;
+  r.ports = CONSTR ? S.jports[ib] : 0; r.j = S.jj[ib];
+  const bool grp = CONSTR && S.jgrp[ib];
+  // ---- my chunk's first clean candidate (row is in shared memory, TMA-staged)
   double cf = 0.0, bound = 0.0;
-  int cv = 0x7fffffff, cslot = -1;
+  int cv = 0x7fffffff;
   if (!grp) {
-    // first clean candidate of my chunk; if all TOPK are dirty the rest of the
-    // chunk is bounded above by the last one's fitness.  All dirty bits are
-    // fetched at once (independent shared loads), then scanned.
+    const double* rf = reinterpret_cast<const double*>(rowp);
+    const int32_t* rv = reinterpret_cast<const int32_t*>(rowp + ROW_V_OFF);
+    double f[TOPK];
+    int v[TOPK];
+#pragma unroll
+    for (int i = 0; i < TOPK; i++) { f[i] = rf[i * 32 + lane]; v[i] = rv[i * 32 + lane]; }
     unsigned dirty_bits = 0u, live_bits = 0u;
 #pragma unroll
     for (int i = 0; i < TOPK; i++) {
-      const bool live = row.f[i] > 0.0;
-      const int vi = live ? row.v[i] : 0;
+      const bool live = f[i] > 0.0;
+      const int vi = live ? v[i] : 0;
       const unsigned w = bitmap[vi >> 5];
       live_bits |= (live ? 1u : 0u) << i;
       dirty_bits |= (((w >> (vi & 31)) & 1u) & (live ? 1u : 0u)) << i;
     }
-    // entries are sorted: live_bits is a prefix mask.  first live&clean entry:
-    const unsigned clean = live_bits & ~dirty_bits;
+    const unsigned clean = live_bits & ~dirty_bits;  // lists are sorted: live_bits is a prefix mask
     if (clean) {
       const int i = __ffs(clean) - 1;
 #pragma unroll
       for (int q = 0; q < TOPK; q++)
-        if (q == i) { cf = row.f[q]; cv = row.v[q]; }
+        if (q == i) { cf = f[q]; cv = v[q]; }
     } else if (live_bits == ((1u << TOPK) - 1u)) {
-      bound = row.f[TOPK - 1];  // full list, all dirty
+      bound = f[TOPK - 1];  // full list, all dirty: rest of the chunk is <= this
     }
   }
-  // prefetch the snapshot state of my clean candidate: if it wins, the commit
-  // needs it (new dirty entry) and must not wait for L2 then.
-  double p_ac = 0.0, p_am = 0.0, p_lc = 0.0, p_lm = 0.0, p_rc = 0.0, p_rm = 0.0;
-  int p_an = 0, p_pu = 0;
-  if (cv != 0x7fffffff) {
-    p_ac = __ldcg(s_asg_c + cv); p_am = __ldcg(s_asg_m + cv);
-    if (CONSTR) { p_an = __ldcg(s_asg_n + cv); p_pu = __ldcg(s_pus + cv); }
-    p_lc = __ldg(a.of.lease_c + cv); p_lm = __ldg(a.of.lease_m + cv);
-    p_rc = __ldg(a.of.run_c + cv); p_rm = __ldg(a.of.run_m + cv);
-  }
+  PROF_LAP(11);
+  // ---- exact re-evaluation of dirty VMs against their current state; my
+  // candidate = better of (clean candidate of my chunk, my dirty entries)
+  const double mb = warp_max_f64(bound);
   PROF_LAP(1);
   if (PROF) prof[6] += nD;
-  // exact re-evaluation of dirty VMs against their current state
+  int cslot = -1;
   for (int d = lane; d < nD; d += 32) {
     double f = eval_vm<CONSTR>(a, r, S.d_vm[d], S.d_ac[d], S.d_am[d], S.d_an[d], S.d_pu[d],
                                S.d_lc[d], S.d_lm[d], S.d_rc[d], S.d_rm[d], grp);
     int v = S.d_vm[d];
     if (f > cf || (f == cf && f > 0.0 && v < cv)) { cf = f; cv = v; cslot = d; }
   }
-  bool did_rescan = false;
   __syncwarp();
+  PROF_LAP(12);
+  int wv, wl;
+  double wf = warp_argmax(cf, cv, wv, wl);
+  int wslot = __shfl_sync(0xffffffffu, cslot, wl < 0 ? 0 : wl);  // -1: clean candidate
   PROF_LAP(2);
-  if (grp) {
-    // full re-scan of clean VMs against current group state
-    for (int v = lane; v < a.of.O; v += 32) {
-      if ((bitmap[v >> 5] >> (v & 31)) & 1u) continue;
-      double f = eval_vm<CONSTR>(a, r, v, __ldcg(s_asg_c + v), __ldcg(s_asg_m + v),
-                                 CONSTR ? __ldcg(s_asg_n + v) : 0, CONSTR ? __ldcg(s_pus + v) : 0,
-                                 a.of.lease_c[v], a.of.lease_m[v], a.of.run_c[v], a.of.run_m[v], true);
-      if (f > cf || (f == cf && f > 0.0 && v < cv)) { cf = f; cv = v; cslot = -2; }
-    }
-    lstats[2]++;
-  } else {
-    double wf0 = warp_max_f64(cf);
-    double mb = warp_max_f64(bound);
-    if (mb > 0.0 && mb >= wf0) {
-      unsigned need = __ballot_sync(0xffffffffu, bound > 0.0 && bound >= wf0);
+  // ---- rare paths: chunk re-scan (all TOPK candidates dirty and the bound
+  // could still win) or full re-scan (group constraints)
+  bool did_rescan = false;
+  if (grp || (mb > 0.0 && mb >= wf)) {
+    const double2* st2 = reinterpret_cast<const double2*>(a.of.vs);
+    const double2* dy2 = reinterpret_cast<const double2*>(snapd);
+    double rf = 0.0;
+    int rv = 0x7fffffff;
+    auto scan = [&](int v) {
+      if ((bitmap[v >> 5] >> (v & 31)) & 1u) return;  // dirty VMs were evaluated exactly above
+      const double2 s0 = st2[2 * v], s1 = st2[2 * v + 1];
+      const double2 d0 = __ldcg(dy2 + 2 * v);
+      int2 d1 = make_int2(0, 0);
+      if (CONSTR) d1 = __ldcg(reinterpret_cast<const int2*>(dy2 + 2 * v + 1));
+      double f = eval_vm<CONSTR>(a, r, v, d0.x, d0.y, d1.x, d1.y, s0.x, s0.y, s1.x, s1.y, grp);
+      if (f > rf || (f == rf && f > 0.0 && v < rv)) { rf = f; rv = v; }
+    };
+    if (grp) {
+      for (int v = lane; v < a.of.O; v += 32) scan(v);
+      lstats[2]++;
+    } else {
+      unsigned need = __ballot_sync(0xffffffffu, bound > 0.0 && bound >= wf);
       did_rescan = true;
       while (need) {
         int c = __ffs(need) - 1;
         need &= need - 1;
-        for (int v = c + 32 * lane; v < a.of.O; v += 32 * 32) {
-          if ((bitmap[v >> 5] >> (v & 31)) & 1u) continue;
-          double f = eval_vm<CONSTR>(a, r, v, __ldcg(s_asg_c + v), __ldcg(s_asg_m + v),
-                                     CONSTR ? __ldcg(s_asg_n + v) : 0, CONSTR ? __ldcg(s_pus + v) : 0,
-                                     a.of.lease_c[v], a.of.lease_m[v], a.of.run_c[v], a.of.run_m[v],
-                                     false);
-          if (f > cf || (f == cf && f > 0.0 && v < cv)) { cf = f; cv = v; cslot = -2; }
-        }
+        for (int v = c + 32 * lane; v < a.of.O; v += 32 * 32) scan(v);
         lstats[1]++;
       }
     }
+    int wrv, wrl;
+    const double wrf = warp_argmax(rf, rv, wrv, wrl);
+    if (wrf > wf || (wrf == wf && wrf > 0.0 && wrv < wv)) { wf = wrf; wv = wrv; wslot = -1; }
   }
-  __syncwarp();
   PROF_LAP(3);
-  // argmax over lanes: max fitness, then lowest v
-  const double wf = warp_max_f64(cf);
+  // ---- commit (all lanes hold identical wf/wv/wslot)
   if (wf > 0.0) {
-    unsigned key = (cf == wf) ? (unsigned)cv : 0xffffffffu;
-    unsigned mv = __reduce_min_sync(0xffffffffu, key);
-    const int wv = (int)mv;
-    const int wl = __ffs(__ballot_sync(0xffffffffu, key == mv)) - 1;
-    int slot = __shfl_sync(0xffffffffu, cslot, wl);
-    // commit (all lanes hold identical values; lane 0 writes).  slot -1: clean
-    // candidate with prefetched state in the winner lane; -2: found by a re-scan.
-    if (slot < 0) {
-      const bool pre = slot == -1;
-      double n_ac = __shfl_sync(0xffffffffu, p_ac, wl), n_am = __shfl_sync(0xffffffffu, p_am, wl);
-      double n_lc = __shfl_sync(0xffffffffu, p_lc, wl), n_lm = __shfl_sync(0xffffffffu, p_lm, wl);
-      double n_rc = __shfl_sync(0xffffffffu, p_rc, wl), n_rm = __shfl_sync(0xffffffffu, p_rm, wl);
-      int n_an = __shfl_sync(0xffffffffu, p_an, wl), n_pu = __shfl_sync(0xffffffffu, p_pu, wl);
+    int slot = wslot;
+    if (slot < 0) {  // clean VM becomes dirty: its snapshot record is its current state
       slot = nD;
       if (lane == 0) {
-        if (!pre) {
-          n_ac = __ldcg(s_asg_c + wv); n_am = __ldcg(s_asg_m + wv);
-          n_an = CONSTR ? __ldcg(s_asg_n + wv) : 0; n_pu = CONSTR ? __ldcg(s_pus + wv) : 0;
-          n_lc = a.of.lease_c[wv]; n_lm = a.of.lease_m[wv]; n_rc = a.of.run_c[wv]; n_rm = a.of.run_m[wv];
-        }
+        const VmStatic vs = a.of.vs[wv];
+        const double2 d0 = __ldcg(reinterpret_cast<const double2*>(snapd + wv));
+        int2 d1 = make_int2(0, 0);
+        if (CONSTR) d1 = __ldcg(reinterpret_cast<const int2*>(snapd + wv) + 2);
         S.d_vm[slot] = wv;
-        S.d_ac[slot] = n_ac; S.d_am[slot] = n_am; S.d_an[slot] = n_an; S.d_pu[slot] = n_pu;
-        S.d_lc[slot] = n_lc; S.d_lm[slot] = n_lm; S.d_rc[slot] = n_rc; S.d_rm[slot] = n_rm;
+        S.d_ac[slot] = d0.x; S.d_am[slot] = d0.y;
+        S.d_an[slot] = d1.x; S.d_pu[slot] = d1.y;
+        S.d_lc[slot] = vs.lc; S.d_lm[slot] = vs.lm; S.d_rc[slot] = vs.rc; S.d_rm[slot] = vs.rm;
         bitmap[wv >> 5] |= 1u << (wv & 31);
       }
       nD++;
@@ -559,10 +606,10 @@ __device__ void resolve_job(const MatchArgs& a, int blk, int k, const Row& row, 
       }
     }
     lstats[3]++;
-    __syncwarp();
   } else {
     if (lane == 0) { a.assign[k] = -1; a.fail[k] = COOK_FAIL_CONSTRAINT; }
   }
+  __syncwarp();
   if (!did_rescan && !grp) lstats[0]++;
   PROF_LAP(4);
 #undef PROF_LAP
@@ -570,18 +617,19 @@ __device__ void resolve_job(const MatchArgs& a, int blk, int k, const Row& row, 
 
 template <bool CONSTR, bool PROF>
 __device__ void resolve_block(const MatchArgs& a, int blk, ResolverShared& S, unsigned* bitmap,
-                              int& nD, unsigned long long* lstats, unsigned long long* prof) {
+                              int& nD, unsigned& seq, unsigned long long* lstats,
+                              unsigned long long* prof) {
   const int lane = threadIdx.x & 31;
   const int k0 = blk * a.B;
   const int k1 = min(k0 + a.B, a.n_cons);
   const int nj = k1 - k0;
-  long long tp0 = PROF ? clock64() : 0, tp1;
+  long long tp0 = PROF ? clock64() : 0, tp1 = 0;
 #define PROF_LAP(i) do { if (PROF) { tp1 = clock64(); prof[i] += (unsigned long long)(tp1 - tp0); tp0 = tp1; } } while (0)
-  // rows of this block ready?
-  if (lane == 0)
-    while (ld_acquire_u32(a.rows_ready + blk) < (unsigned)nj) __nanosleep(20);
-  __syncwarp();
-  PROF_LAP(9);
+  // this block's job requests -> shared (static data, plain coalesced loads)
+  for (int i = lane; i < nj; i += 32) {
+    S.jc[i] = a.kc[k0 + i]; S.jm[i] = a.km[k0 + i]; S.jj[i] = a.cons[k0 + i];
+    if (CONSTR) { S.jg[i] = a.kg[k0 + i]; S.jports[i] = a.kports[k0 + i]; S.jgrp[i] = a.kflags[k0 + i] & 1; }
+  }
   // drop dirty entries not touched in the previous block: they are part of the
   // snapshot this block's rows were scored against.
   {
@@ -608,6 +656,13 @@ __device__ void resolve_block(const MatchArgs& a, int blk, ResolverShared& S, un
     nD = keep_n;
   }
   PROF_LAP(0);
+  // rows of this block ready?
+  if (lane == 0) {
+    while (ld_acquire_u32(a.rows_ready + blk) < (unsigned)nj) __nanosleep(20);
+    asm volatile("fence.proxy.async;" ::: "memory");  // generic-proxy writes -> async-proxy (TMA) reads
+  }
+  __syncwarp();
+  PROF_LAP(9);
   // jobs with no feasible VM at the snapshot are unplaceable now too (resources
   // and count constraints only tighten within a cycle): skip them wholesale.
   const uint8_t* feas = a.feas + (size_t)(blk & 1) * a.B;
@@ -627,28 +682,34 @@ __device__ void resolve_block(const MatchArgs& a, int blk, ResolverShared& S, un
   }
   __syncwarp();
   {
-    Row cur, nxt, nx2;
-    if (nfeas > 0) load_row<CONSTR>(a, blk, k0 + S.feas_list[0], lane, cur);
-    if (nfeas > 1) load_row<CONSTR>(a, blk, k0 + S.feas_list[1], lane, nxt);
+    // TMA ring: rows of the next RING-1 feasible jobs are in flight while one is resolved
+    const unsigned char* gbase = a.rows + (size_t)(blk & 1) * a.B * ROW_BYTES;
+    auto issue = [&](int q) {  // lane 0 only
+      const unsigned s = (seq + (unsigned)q) % RING;
+      mbar_expect_tx(&S.bar[s], ROW_BYTES);
+      tma_load_1d(S.rows[s], gbase + (size_t)S.feas_list[q] * ROW_BYTES, ROW_BYTES, &S.bar[s]);
+    };
+    if (lane == 0)
+      for (int q = 0; q < nfeas && q < RING - 1; q++) issue(q);
     PROF_LAP(1);
     for (int q = 0; q < nfeas; q++) {
-      const int kcur = k0 + S.feas_list[q];
-      if (q + 2 < nfeas) load_row<CONSTR>(a, blk, k0 + S.feas_list[q + 2], lane, nx2);
-      resolve_job<CONSTR, PROF>(a, blk, kcur, cur, S, bitmap, nD, lstats, prof, tp0);
-      cur = nxt;
-      nxt = nx2;
+      const int ib = S.feas_list[q];
+      if (lane == 0 && q + RING - 1 < nfeas) issue(q + RING - 1);  // slot of job q-1: free since its __syncwarp
+      const unsigned sq = seq + (unsigned)q;
+      mbar_wait(&S.bar[sq % RING], (sq / RING) & 1u);
+      PROF_LAP(10);
+      resolve_job<CONSTR, PROF>(a, blk, k0 + ib, ib, S.rows[sq % RING], S, bitmap, nD, lstats, prof, tp0);
     }
+    seq += (unsigned)nfeas;
   }
   // publish every dirty entry (touched in this or the previous block) into the
   // buffer the evaluators read for block blk+2.
   {
-    const int pub = blk & 1;
+    VmDyn* pub = a.dyn.d[blk & 1];
     for (int d = lane; d < nD; d += 32) {
       int v = S.d_vm[d];
-      __stcg(a.dyn.asg_c[pub] + v, S.d_ac[d]);
-      __stcg(a.dyn.asg_m[pub] + v, S.d_am[d]);
-      __stcg(a.dyn.asg_n[pub] + v, S.d_an[d]);
-      __stcg(a.dyn.ports_used[pub] + v, S.d_pu[d]);
+      __stcg(reinterpret_cast<double2*>(pub + v), make_double2(S.d_ac[d], S.d_am[d]));
+      __stcg(reinterpret_cast<int2*>(pub + v) + 2, make_int2(S.d_an[d], S.d_pu[d]));
     }
     __syncwarp();
     if (lane == 0) {
@@ -668,24 +729,30 @@ __device__ void resolve_block(const MatchArgs& a, int blk, ResolverShared& S, un
 //   published      resolver -> evaluators (# blocks resolved and published)
 template <bool CONSTR, bool PROF>
 __global__ void __launch_bounds__(RES_THREADS, 1) match_kernel(MatchArgs a) {
-  extern __shared__ unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   const int nblk = (a.n_cons + a.B - 1) / a.B;
   if (blockIdx.x == 0) {
     ResolverShared& S = *reinterpret_cast<ResolverShared*>(smem_raw);
     unsigned* bitmap = reinterpret_cast<unsigned*>(smem_raw + sizeof(ResolverShared));
     const int words = (a.of.O + 31) / 32;
     for (int i = threadIdx.x; i < words; i += RES_THREADS) bitmap[i] = 0u;
+    if (threadIdx.x == 0) {
+      for (int i = 0; i < RING; i++) mbar_init(&S.bar[i], 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     __syncthreads();
     if (threadIdx.x >= 32) return;
     int nD = 0;
+    unsigned seq = 0;
     unsigned long long lstats[4] = {0, 0, 0, 0};
-    unsigned long long prof[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    unsigned long long prof[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     long long t0 = clock64();
-    for (int t = 0; t < nblk; t++) resolve_block<CONSTR, PROF>(a, t, S, bitmap, nD, lstats, prof);
+    for (int t = 0; t < nblk; t++) resolve_block<CONSTR, PROF>(a, t, S, bitmap, nD, seq, lstats, prof);
     prof[8] = (unsigned long long)(clock64() - t0);
     if (threadIdx.x == 0) {
       a.stats[0] = lstats[0]; a.stats[1] = lstats[1]; a.stats[2] = lstats[2]; a.stats[3] = lstats[3];
       for (int i = 0; i < 10; i++) a.stats[4 + i] = prof[i];
+      a.stats[20] = prof[10]; a.stats[21] = prof[11]; a.stats[22] = prof[12];
     }
   } else {
     EvalShared& E = *reinterpret_cast<EvalShared*>(smem_raw);
@@ -797,7 +864,8 @@ __global__ void __launch_bounds__(128) cons_user_kernel(ConsArgs a, const int32_
 // allowed + launch-plugin masks (scheduler.clj:749-750), take N (:751);
 // gathers the per-k hot columns.
 __global__ void cons_queue_kernel(ConsArgs a, const uint8_t* keep, int32_t* cons, double* kc,
-                                  double* km, uint8_t* kflags, int32_t* out_n) {
+                                  double* km, double* kg, int32_t* kports, uint8_t* kflags,
+                                  int32_t* out_n) {
   const int lane = threadIdx.x;
   double pn = 0, pc = 0, pm = 0, pg = 0;
   if (a.pool_q.enabled) {  // (reduce (partial merge-with +) (vals user->usage)), tools.clj:969
@@ -845,6 +913,8 @@ __global__ void cons_queue_kernel(ConsArgs a, const uint8_t* keep, int32_t* cons
       cons[slot] = j;
       kc[slot] = a.jb.cpus[j];
       km[slot] = a.jb.mem[j];
+      kg[slot] = a.jb.gpus ? a.jb.gpus[j] : 0.0;
+      kports[slot] = a.jb.ports ? a.jb.ports[j] : 0;
       uint8_t fl = 0;
       if (a.jb.group_off && a.jb.group_off[j + 1] > a.jb.group_off[j]) fl |= 1;
       kflags[slot] = fl;
@@ -856,13 +926,14 @@ __global__ void cons_queue_kernel(ConsArgs a, const uint8_t* keep, int32_t* cons
 
 // ------------------------------------------------------------------ setup
 __global__ void gather_offers_kernel(const int32_t* perm, int O, const double* c, const double* m,
-                                     const double* rc, const double* rm, double* oc, double* om,
-                                     double* orc, double* orm) {
+                                     const double* rc, const double* rm, VmStatic* vs) {
   int v = blockIdx.x * blockDim.x + threadIdx.x;
   if (v >= O) return;
   int o = perm[v];
-  oc[v] = c[o]; om[v] = m[o];
-  orc[v] = rc ? rc[o] : 0.0; orm[v] = rm ? rm[o] : 0.0;
+  VmStatic x;
+  x.lc = c[o]; x.lm = m[o];
+  x.rc = rc ? rc[o] : 0.0; x.rm = rm ? rm[o] : 0.0;
+  vs[v] = x;
 }
 
 __global__ void ports_total_kernel(const int32_t* off, const int32_t* b, const int32_t* e, int O,
@@ -929,7 +1000,9 @@ struct MatchPlan {
   int32_t *d_perm = nullptr, *d_pos = nullptr, *d_tmp = nullptr, *d_seg_s = nullptr, *d_seg_e = nullptr;
   uint8_t* d_keep = nullptr;
   double *d_oc = nullptr, *d_om = nullptr, *d_orc = nullptr, *d_orm = nullptr;
-  double *g_lc = nullptr, *g_lm = nullptr, *g_rc = nullptr, *g_rm = nullptr;
+  VmStatic* d_vs = nullptr;
+  double* d_kg = nullptr;
+  int32_t* d_kports = nullptr;
   int32_t* d_ports_total = nullptr;
   int32_t *d_cons = nullptr, *d_out_assign = nullptr, *d_out_ports = nullptr, *d_used = nullptr;
   double *d_kc = nullptr, *d_km = nullptr;
@@ -1019,12 +1092,13 @@ static int32_t build_plan(cook_pool* pool, MatchPlan* mp, const int32_t* ranked_
   for (int k = 0; k < 6; k++) sz.add<int32_t>(n_ranked + 1);
   sz.add<uint8_t>(n_ranked + 1);
   sz.add<int32_t>(NC + 1); sz.add<double>(NC + 1); sz.add<double>(NC + 1); sz.add<uint8_t>(NC + 1);
-  sz.add<double>((size_t)2 * B * TOPK * 32); sz.add<int32_t>((size_t)2 * B * TOPK * 32);
+  sz.add<unsigned char>((size_t)2 * B * ROW_BYTES); sz.add<double>(NC + B + 1); sz.add<int32_t>(NC + B + 1);
   sz.add<uint8_t>(2 * B + 16); sz.add<unsigned>((size_t)NC / B + 16);
   sz.add<int32_t>(NC + 1); sz.add<int32_t>(NC + 1); sz.add<uint8_t>(NC + 1);
   sz.add<int32_t>(NC + 1); sz.add<int32_t>((size_t)NC * std::max(max_ports, 1) + 1);
   sz.add<int32_t>(O + 1);
   sz.add<unsigned long long>(32); sz.add<int32_t>(16);
+  sz.add<VmStatic>(O + 1); sz.add<VmDyn>(O + 1); sz.add<VmDyn>(O + 1);
   CK(pool, ar.reserve(sz.off + (1 << 18)));
   ar.reset();
 
@@ -1058,9 +1132,8 @@ static int32_t build_plan(cook_pool* pool, MatchPlan* mp, const int32_t* ranked_
   { const int32_t* hp = perm.data(); UP(mp->d_perm, hp, O); of.perm = mp->d_perm; }
   UP(mp->d_oc, offers->cpus, O); UP(mp->d_om, offers->mem, O);
   UP(mp->d_orc, offers->run_cpus, O); UP(mp->d_orm, offers->run_mem, O);
-  mp->g_lc = ar.take<double>(O + 1); mp->g_lm = ar.take<double>(O + 1);
-  mp->g_rc = ar.take<double>(O + 1); mp->g_rm = ar.take<double>(O + 1);
-  of.lease_c = mp->g_lc; of.lease_m = mp->g_lm; of.run_c = mp->g_rc; of.run_m = mp->g_rm;
+  mp->d_vs = ar.take<VmStatic>(O + 1);
+  of.vs = mp->d_vs;
   { int32_t* p; UP(p, offers->hostname_id, O); of.hostname_id = p;
     UP(p, offers->run_count, O); of.run_count = p; }
   mp->d_ports_total = nullptr;
@@ -1115,8 +1188,7 @@ static int32_t build_plan(cook_pool* pool, MatchPlan* mp, const int32_t* ranked_
   MatchArgs& ma = mp->ma;
   memset(&ma, 0, sizeof(ma));
   for (int b = 0; b < 2; b++) {
-    ma.dyn.asg_c[b] = ar.take<double>(O + 1); ma.dyn.asg_m[b] = ar.take<double>(O + 1);
-    ma.dyn.asg_n[b] = ar.take<int32_t>(O + 1); ma.dyn.ports_used[b] = ar.take<int32_t>(O + 1);
+    ma.dyn.d[b] = ar.take<VmDyn>(O + 1);
   }
   mp->d_pos = ar.take<int32_t>(n_ranked + 1);
   mp->d_tmp = ar.take<int32_t>(n_ranked + 1);
@@ -1127,8 +1199,10 @@ static int32_t build_plan(cook_pool* pool, MatchPlan* mp, const int32_t* ranked_
   mp->d_kc = ar.take<double>(NC + 1);
   mp->d_km = ar.take<double>(NC + 1);
   mp->d_kflags = ar.take<uint8_t>(NC + 1);
-  ma.row_f = ar.take<double>((size_t)2 * B * TOPK * 32);
-  ma.row_v = ar.take<int32_t>((size_t)2 * B * TOPK * 32);
+  ma.rows = ar.take<unsigned char>((size_t)2 * B * ROW_BYTES);
+  mp->d_kg = ar.take<double>(NC + B + 1);
+  mp->d_kports = ar.take<int32_t>(NC + B + 1);
+  ma.kg = mp->d_kg; ma.kports = mp->d_kports;
   ma.feas = ar.take<uint8_t>(2 * B + 16);
   ma.rows_ready = ar.take<unsigned>((size_t)NC / B + 16);
   ma.assign = ar.take<int32_t>(NC + 1);
@@ -1160,10 +1234,7 @@ static int32_t run_plan(cook_pool* pool, MatchPlan* mp, int32_t* out_considerabl
   int launches = 0;
   // ---- reset of per-cycle dynamic state
   for (int b = 0; b < 2; b++) {
-    CK(pool, cudaMemsetAsync(ma.dyn.asg_c[b], 0, sizeof(double) * (O + 1), st));
-    CK(pool, cudaMemsetAsync(ma.dyn.asg_m[b], 0, sizeof(double) * (O + 1), st));
-    CK(pool, cudaMemsetAsync(ma.dyn.asg_n[b], 0, sizeof(int32_t) * (O + 1), st));
-    CK(pool, cudaMemsetAsync(ma.dyn.ports_used[b], 0, sizeof(int32_t) * (O + 1), st));
+    CK(pool, cudaMemsetAsync(ma.dyn.d[b], 0, sizeof(VmDyn) * (O + 1), st));
   }
   if (ma.gr.gp_n) CK(pool, cudaMemsetAsync(ma.gr.gp_n, 0, sizeof(int32_t) * (mp->G + 1), st));
   CK(pool, cudaMemsetAsync(mp->d_seg_s, 0, sizeof(int32_t) * (U + 1), st));
@@ -1178,8 +1249,7 @@ static int32_t run_plan(cook_pool* pool, MatchPlan* mp, int32_t* out_considerabl
   const int TB = 256;
   if (O > 0) {
     gather_offers_kernel<<<(O + TB - 1) / TB, TB, 0, st>>>(mp->d_perm, O, mp->d_oc, mp->d_om, mp->d_orc,
-                                                           mp->d_orm, mp->g_lc, mp->g_lm, mp->g_rc,
-                                                           mp->g_rm);
+                                                           mp->d_orm, mp->d_vs);
     launches++;
     if (mp->d_ports_total) {
       ports_total_kernel<<<(O + TB - 1) / TB, TB, 0, st>>>(ma.of.port_off, ma.of.port_begin,
@@ -1194,8 +1264,8 @@ static int32_t run_plan(cook_pool* pool, MatchPlan* mp, int32_t* out_considerabl
   cons_seg_kernel<<<(n_ranked + TB - 1) / TB, TB, 0, st>>>(mp->d_pos, ca.ranked, ca.jb.user, n_ranked,
                                                            mp->d_seg_s, mp->d_seg_e);
   cons_user_kernel<<<(U + 3) / 4, 128, 0, st>>>(ca, mp->d_pos, mp->d_seg_s, mp->d_seg_e, mp->d_keep);
-  cons_queue_kernel<<<1, 32, 0, st>>>(ca, mp->d_keep, mp->d_cons, mp->d_kc, mp->d_km, mp->d_kflags,
-                                      mp->d_counters);
+  cons_queue_kernel<<<1, 32, 0, st>>>(ca, mp->d_keep, mp->d_cons, mp->d_kc, mp->d_km, mp->d_kg,
+                                      mp->d_kports, mp->d_kflags, mp->d_counters);
   launches += 3;
   CK(pool, cudaGetLastError());
   int32_t n_cons = 0;
@@ -1259,6 +1329,8 @@ static int32_t run_plan(cook_pool* pool, MatchPlan* mp, int32_t* out_considerabl
                           "sum_nD", "n_shortcut", "res_total", "res_wait_rows", "eval_work", "eval_wait",
                           "eval_loop", "eval_sync", "eval_merge"};
     for (int i = 0; i < 15; i++) fprintf(stderr, "[cook_prof] %-14s %llu\n", nm[i], hstats[4 + i]);
+    fprintf(stderr, "[cook_prof] mbar_wait      %llu\n[cook_prof] lds+select     %llu\n[cook_prof] dirty_loop     %llu\n",
+            hstats[20], hstats[21], hstats[22]);
   }
   if (out_stats) {
     out_stats->n_considerable = n_cons;
