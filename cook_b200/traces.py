@@ -113,3 +113,127 @@ def gen_c2(seed=2, n_jobs=100_000, n_offers=5_000, n_users=1_000, n_running=20_0
 def match_params(num_considerable, enforce_rate_limit=0, host_lifetime_mins=0, reuse_resident=0):
     return abi.MatchParams(int(num_considerable), int(enforce_rate_limit), int(host_lifetime_mins),
                            0, 1.0, int(reuse_resident), 0)
+
+
+def add_constraints(t, seed, *, n_attr_cols=8, attr_card=(3, 6, 24, 2, 2, 4, 5, 7), frac_attr=0.30,
+                    frac_gpu_nodes=0.05, frac_gpu_jobs=0.02, frac_port_jobs=0.03,
+                    frac_port_nodes=0.25, frac_group_jobs=0.05, group_size=(4, 24),
+                    frac_novel=0.10, max_tasks=110, frac_k8s=0.75, frac_reserved=0.01,
+                    frac_est=0.05, frac_ckpt=0.02, frac_disk=0.05, n_models=2, n_locations=3,
+                    host_lifetime_mins=1440, n_running_cotasks=3):
+    """Adds SURVEY §8d config-#3 style constraint columns to a gen_pool() trace, in
+    place: 8 attribute columns, GPU nodes/jobs (models x counts), ports on the
+    Mesos-type nodes, unique/balanced/attribute-equals groups, novel-host lists,
+    max-tasks-per-host, reservations, estimated completion, checkpoint locality,
+    disk.  Returns the cook_groups struct (or None)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    jobs, offers = t["jobs"], t["offers"]
+    J, O = jobs.n, offers.n
+    # ---- offers
+    is_k8s = (rng.random(O) < frac_k8s).astype(np.uint8)
+    attr = np.zeros((n_attr_cols, O), np.int32)
+    for c in range(n_attr_cols):
+        attr[c] = rng.integers(1, attr_card[c % len(attr_card)] + 1, O)
+        attr[c][rng.random(O) < 0.05] = 0  # attribute absent on some hosts
+    gpu_node = (rng.random(O) < frac_gpu_nodes) & (is_k8s == 1)
+    gpu_lists_m = [[int(rng.integers(0, n_models))] if g else [] for g in gpu_node]
+    gpu_lists_c = [[float(rng.choice([1, 2, 4, 8]))] if g else [] for g in gpu_node]
+    gpu_off, gpu_model = abi.csr(gpu_lists_m)
+    _, gpu_count = abi.csr(gpu_lists_c, np.float64)
+    port_node = (rng.random(O) < frac_port_nodes) & (is_k8s == 0)
+    pb = [[31000, 31500] if p else [] for p in port_node]
+    pe = [[31009, 31504] if p else [] for p in port_node]
+    port_off, port_begin = abi.csr(pb)
+    _, port_end = abi.csr(pe)
+    disk_t = [[0, 1] if k else [] for k in is_k8s]
+    disk_s = [[float(rng.integers(10, 200) * 1024), float(rng.integers(0, 50) * 1024)] if k else [] for k in is_k8s]
+    disk_off, disk_type = abi.csr(disk_t)
+    _, disk_space = abi.csr(disk_s, np.float64)
+    num_tasks = rng.integers(0, max_tasks + 5, O).astype(np.int32)
+    max_t = np.where(rng.random(O) < 0.9, max_tasks, -1).astype(np.int32)
+    location = rng.integers(0, n_locations, O).astype(np.int32)
+    host_start = np.where(rng.random(O) < 0.7, 1_600_000_000 + rng.integers(0, 86400, O), -1).astype(np.int64)
+    reserved = (rng.random(O) < frac_reserved).astype(np.uint8)
+    hostname_id = offers.col("hostname_id")
+    cols = {n: offers.col(n) for n in ("hostname_id", "name_rank", "cpus", "mem", "run_cpus", "run_mem", "run_count")}
+    t["offers"] = abi.OffersSoA(n=O, **cols, port_off=port_off, port_begin=port_begin, port_end=port_end,
+                                is_k8s=is_k8s, location=location, gpu_off=gpu_off, gpu_model=gpu_model,
+                                gpu_count=gpu_count, disk_off=disk_off, disk_type=disk_type,
+                                disk_space=disk_space, max_tasks=max_t, num_tasks=num_tasks,
+                                host_start_time=host_start, n_attr_cols=n_attr_cols,
+                                attr=attr.reshape(-1), reserved=reserved)
+    # ---- jobs
+    gpus = np.where(rng.random(J) < frac_gpu_jobs, rng.choice([1.0, 2.0, 4.0, 8.0], J), 0.0)
+    gmodel = np.where(gpus > 0, rng.integers(0, n_models, J), -1).astype(np.int32)
+    ports = np.where(rng.random(J) < frac_port_jobs, rng.integers(1, 3, J), 0).astype(np.int32)
+    attr_l_c, attr_l_v = [], []
+    for j in range(J):
+        if rng.random() < frac_attr:
+            k = int(rng.integers(1, 3))
+            cs = rng.choice(n_attr_cols, size=k, replace=False)
+            attr_l_c.append([int(c) for c in cs])
+            attr_l_v.append([int(rng.integers(1, attr_card[int(c) % len(attr_card)] + 1)) if rng.random() < 0.97 else -1 for c in cs])
+        else:
+            attr_l_c.append([])
+            attr_l_v.append([])
+    attr_off, attr_col = abi.csr(attr_l_c)
+    _, attr_val = abi.csr(attr_l_v)
+    novel = [[int(x) for x in rng.choice(hostname_id, size=int(rng.integers(1, 4)), replace=False)]
+             if rng.random() < frac_novel else [] for _ in range(J)]
+    novel_off, novel_host = abi.csr(novel)
+    now_ms = 1_600_050_000_000
+    est = np.where(rng.random(J) < frac_est, now_ms + rng.integers(1, 48 * 3600_000, J), -1).astype(np.int64)
+    ckpt = np.where(rng.random(J) < frac_ckpt, rng.integers(0, n_locations, J), -1).astype(np.int32)
+    res_hosts = hostname_id[reserved == 1]
+    reserved_host = np.full(J, -1, np.int32)
+    if len(res_hosts):
+        pick = rng.random(J) < 0.01
+        reserved_host[pick] = rng.choice(res_hosts, size=int(pick.sum()))
+    disk_req = np.where(rng.random(J) < frac_disk, rng.integers(1, 64, J) * 1024.0, -1.0)
+    disk_typ = rng.integers(0, 2, J).astype(np.int32)
+    # groups
+    n_gj = int(J * frac_group_jobs)
+    members = rng.permutation(J)[:n_gj]
+    grp_lists = [[] for _ in range(J)]
+    kinds, acols, mins, cot_h, cot_a = [], [], [], [], []
+    g = 0
+    i = 0
+    while i < n_gj:
+        sz = int(rng.integers(group_size[0], group_size[1] + 1))
+        r = rng.random()
+        kind = abi.GROUP_UNIQUE if r < 0.6 else (abi.GROUP_BALANCED if r < 0.85 else abi.GROUP_ATTR_EQUALS)
+        col = int(rng.integers(0, min(3, n_attr_cols)))
+        for j in members[i:i + sz]:
+            grp_lists[j].append(g)
+        kinds.append(kind); acols.append(col); mins.append(int(rng.integers(1, 4)))
+        nc = int(rng.integers(0, n_running_cotasks + 1))
+        hs = [int(x) for x in rng.choice(hostname_id, size=nc, replace=False)] if nc else []
+        cot_h.append(hs)
+        cot_a.append([int(attr[col][np.where(hostname_id == h)[0][0]]) for h in hs])
+        g += 1
+        i += sz
+    group_off, group_idx = abi.csr(grp_lists)
+    base = {n: jobs.col(n) for n in ("user", "cpus", "mem", "allowed", "plugin_accept")}
+    t["jobs"] = abi.JobsSoA(n=J, **base, gpus=gpus, ports=ports, novel_off=novel_off, novel_host=novel_host,
+                            gpu_model=gmodel, disk_request=disk_req, disk_type=disk_typ,
+                            attr_off=attr_off, attr_col=attr_col, attr_val=attr_val, est_end_ms=est,
+                            ckpt_location=ckpt, reserved_host=reserved_host,
+                            group_off=group_off, group_idx=group_idx)
+    t["host_lifetime_mins"] = host_lifetime_mins
+    if g == 0:
+        t["groups"] = None
+        return None
+    cot_off, cot_host = abi.csr(cot_h)
+    _, cot_attr = abi.csr(cot_a)
+    t["groups"] = abi.Groups(n_groups=g, kind=np.array(kinds, np.int32), attr_col=np.array(acols, np.int32),
+                             minimum=np.array(mins, np.int32), cot_off=cot_off,
+                             cot_hostname_id=cot_host, cot_attr_val=cot_attr)
+    return t["groups"]
+
+
+def gen_c3_pool(seed=3, n_jobs=20_000, n_offers=1_000, n_users=200, n_running=4_000, **kw):
+    """One pool of BASELINE config #3's shape (scaled by the caller): host-placement
+    + gpu/ports constraints, groups, novel hosts, max-tasks-per-host."""
+    t = gen_pool(seed, n_jobs, n_offers, n_users, n_running)
+    add_constraints(t, seed + 1000, **kw)
+    return t

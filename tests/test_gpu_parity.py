@@ -100,3 +100,27 @@ def test_resident_inputs_same_result(gpu, oracle):
     with pytest.raises(CookError):
         gpu.match(ranked[:100], t["jobs"], t["offers"], t["users"],
                   traces.match_params(6000, reuse_resident=1))
+
+
+@pytest.mark.parametrize("seed,nj,no,nu,nr,kw", [
+    (41, 5000, 300, 50, 1000, {}),
+    (42, 8000, 1000, 100, 2000, {"frac_group_jobs": 0.0}),
+    (43, 3000, 97, 20, 500, {"frac_group_jobs": 0.3, "group_size": (2, 9), "frac_gpu_jobs": 0.2,
+                             "frac_gpu_nodes": 0.4, "frac_port_jobs": 0.3}),
+    (44, 2000, 64, 10, 100, {"frac_k8s": 0.0, "frac_port_nodes": 0.9, "frac_port_jobs": 0.5,
+                             "max_tasks": 3}),
+])
+def test_constraint_kernel_parity(gpu, oracle, seed, nj, no, nu, nr, kw):
+    """Config-#3 style constraints (attributes, gpu, ports, groups, novel hosts,
+    max-tasks, reservation, est-completion, checkpoint, disk): assignments, ports
+    and considerable sets bit-identical to the oracle."""
+    t = traces.gen_c3_pool(seed, nj, no, nu, nr, **kw)
+    ranked = oracle.rank(t["running"], t["pending"], t["users"])["ranked"]
+    prm = traces.match_params(nj, host_lifetime_mins=t["host_lifetime_mins"])
+    mo = oracle.match(ranked, t["jobs"], t["offers"], t["users"], prm, groups=t["groups"], max_ports=2)
+    mg = gpu.match(ranked, t["jobs"], t["offers"], t["users"], prm, groups=t["groups"], max_ports=2)
+    assert np.array_equal(mg["considerable"], mo["considerable"])
+    assert np.array_equal(mg["assign"], mo["assign"])
+    assert np.array_equal(mg["ports"], mo["ports"])
+    assert np.array_equal(mg["fail"] == 0, mo["fail"] == 0)
+    assert mg["stats"]["n_matched"] == mo["stats"]["n_matched"] > 0
