@@ -589,3 +589,268 @@ int32_t oracle_match_mt(const int32_t* ranked_idx, int32_t n_ranked, const cook_
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------
+// REBALANCE  (rebalancer.clj:144-467, dru.clj:128-144, constraints.clj:504-515,
+// :680-697).  Default DRU mode only: in GPU mode the reference's
+// compute-preemption-decision dereferences (:dru <number>) = nil and throws
+// (rebalancer.clj:339-349 over the [task cumulative-gpus] pairs of :245-247),
+// so there is no reference behaviour to restate.
+// ---------------------------------------------------------------------------
+namespace {
+
+struct RTask {
+  int user, prio, host;
+  int64_t start, tid, jid;
+  double cpus, mem, gpus, dru;
+  bool alive;
+};
+
+struct RebState {
+  std::vector<RTask> tasks;                 // running, then synthetic tasks of decisions
+  std::vector<std::vector<int>> by_user;    // sorted (tools.clj:614-641)
+  std::vector<uint8_t> has_spare;
+  std::vector<double> spare_cpus, spare_mem, spare_gpus;
+  std::vector<int> preempted_hosts;         // hosts of tasks preempted so far (constraints.clj:690-692)
+};
+
+inline bool rtask_less(const RTask& a, const RTask& b) {
+  if (-a.prio != -b.prio) return -a.prio < -b.prio;
+  if (a.start != b.start) return a.start < b.start;
+  if (a.tid != b.tid) return a.tid < b.tid;
+  return a.jid < b.jid;
+}
+
+// dru.clj:50-66 for one user (next-task->scored-task re-scores changed users)
+void rescore_user(RebState& st, const cook_user_table* users, int u) {
+  double cm = 0.0, cc = 0.0;
+  for (int t : st.by_user[u]) {
+    cm = cm + st.tasks[t].mem;
+    cc = cc + st.tasks[t].cpus;
+    double a = cm / users->div_mem[u], b = cc / users->div_cpus[u];
+    st.tasks[t].dru = a > b ? a : b;
+  }
+}
+
+// The six job-constraint-constructors evaluated on the cached agent attributes
+// of `h` (constraints.clj:504-515); `have_attrs` is false when the host has no
+// task in task->scored-task (preemptable-host->slave-id lookup yields nil,
+// rebalancer.clj:371-377), i.e. every attribute reads as nil.
+bool reb_host_passes(const cook_jobs_soa* jb, int j, const cook_host_table* ht, int h, bool have_attrs,
+                     const cook_rebalance_params* prm) {
+  // novel-host: (get nil "HOSTNAME") => nil => passes
+  if (have_attrs && jb->novel_off)
+    for (int k = jb->novel_off[j]; k < jb->novel_off[j + 1]; k++)
+      if (jb->novel_host[k] == ht->hostname_id[h]) return false;
+  bool k8s = have_attrs && ht->is_k8s && ht->is_k8s[h];
+  double g = jb->gpus ? jb->gpus[j] : 0.0;
+  if (k8s) {  // gpu-host 3-arity: vm-tasks-assigned = []
+    if (g > 0.0) {
+      double have = csr_lookup(ht->gpu_off, ht->gpu_model, ht->gpu_count, h, jb->gpu_model ? jb->gpu_model[j] : -1);
+      if (!(have == g)) return false;
+    } else {
+      int nm = ht->gpu_off ? ht->gpu_off[h + 1] - ht->gpu_off[h] : 0;
+      if (nm != 0) return false;
+    }
+  } else if (!(g == 0.0)) {
+    return false;
+  }
+  if (jb->disk_request && jb->disk_request[j] >= 0.0 && k8s) {
+    double space = csr_lookup(ht->disk_off, ht->disk_type, ht->disk_space, h, jb->disk_type ? jb->disk_type[j] : -1);
+    if (!(space >= jb->disk_request[j])) return false;
+  }
+  if (jb->attr_off)
+    for (int k = jb->attr_off[j]; k < jb->attr_off[j + 1]; k++) {
+      int col = jb->attr_col[k], val = jb->attr_val[k];
+      if (!have_attrs || col < 0 || col >= ht->n_attr_cols) return false;
+      int hv = ht->attr[(size_t)col * ht->n + h];
+      if (val <= 0 || hv != val) return false;
+    }
+  if (jb->est_end_ms && jb->est_end_ms[j] >= 0 && have_attrs && ht->host_start_time && ht->host_start_time[h] >= 0) {
+    int64_t death = 1000 * ht->host_start_time[h] + (int64_t)60 * 1000 * prm->host_lifetime_mins;
+    if (!(jb->est_end_ms[j] < death)) return false;
+  }
+  if (jb->ckpt_location && jb->ckpt_location[j] >= 0) {
+    int loc = (have_attrs && ht->location) ? ht->location[h] : -1;
+    if (loc != jb->ckpt_location[j]) return false;
+  }
+  return true;
+}
+
+}  // namespace
+
+extern "C" int32_t oracle_rebalance(int32_t dru_mode, const cook_running_soa* running,
+                                    const cook_jobs_soa* pending, const int64_t* pending_job_id,
+                                    const int32_t* pending_priority, const cook_host_table* hosts,
+                                    const cook_groups* groups, const cook_user_table* users,
+                                    const cook_rebalance_params* prm, cook_decision* out_dec,
+                                    int32_t* out_victims, int32_t* out_n) {
+  if (!running || !pending || !hosts || !users || !prm || !out_dec || !out_victims || !out_n) return COOK_E_BADARG;
+  if (dru_mode != 0) return COOK_E_UNSUPPORTED_CONSTRAINT;
+  const int R = running->t.n, H = hosts->n, U = users->n_users;
+  RebState st;
+  st.tasks.resize(R);
+  st.by_user.resize(U);
+  for (int i = 0; i < R; i++) {
+    const cook_tasks_soa& t = running->t;
+    st.tasks[i] = RTask{t.user[i], t.priority[i], running->host[i], t.start_time[i], t.task_id[i], t.job_id[i],
+                        t.cpus[i], t.mem[i], t.gpus ? t.gpus[i] : 0.0, 0.0, true};
+    st.by_user[t.user[i]].push_back(i);
+  }
+  for (int u = 0; u < U; u++) {  // rebalancer.clj:237-243 sorted-set-by same-user-task-comparator
+    std::stable_sort(st.by_user[u].begin(), st.by_user[u].end(),
+                     [&](int a, int b) { return rtask_less(st.tasks[a], st.tasks[b]); });
+    rescore_user(st, users, u);
+  }
+  st.has_spare.assign(H, 0); st.spare_cpus.assign(H, 0.0); st.spare_mem.assign(H, 0.0); st.spare_gpus.assign(H, 0.0);
+  for (int h = 0; h < H; h++)
+    if (hosts->has_spare && hosts->has_spare[h]) {
+      st.has_spare[h] = 1; st.spare_cpus[h] = hosts->spare_cpus[h]; st.spare_mem[h] = hosts->spare_mem[h];
+      st.spare_gpus[h] = hosts->spare_gpus ? hosts->spare_gpus[h] : 0.0;
+    }
+  std::vector<int> hosts_by_name(H);  // (sort-by first) rebalancer.clj:383
+  for (int h = 0; h < H; h++) hosts_by_name[h] = h;
+  std::sort(hosts_by_name.begin(), hosts_by_name.end(),
+            [&](int a, int b) { return hosts->name_rank[a] < hosts->name_rank[b]; });
+  const double DMAX = std::numeric_limits<double>::max();
+  int n_dec = 0, n_vict = 0;
+  // rebalancer.clj:442-458: walk the pending jobs while preemptions remain
+  for (int p = 0; p < pending->n && n_dec < prm->max_preemption; p++) {
+    const int pu = pending->user[p];
+    const double pmem = pending->mem[p], pcpus = pending->cpus[p], pgpus = pending->gpus ? pending->gpus[p] : 0.0;
+    // job-below-quota :210-220
+    Usage fu;
+    add_usage(fu, pcpus, pmem, pgpus);
+    for (int t : st.by_user[pu]) add_usage(fu, st.tasks[t].cpus, st.tasks[t].mem, st.tasks[t].gpus);
+    const bool below = below_quota(users->quota_count[pu], users->quota_cpus[pu], users->quota_mem[pu],
+                                   users->quota_gpus[pu], fu);
+    // compute-pending-default-job-dru :182-208: nearest = last task <= synthetic pending task
+    RTask synth{pu, pending_priority[p], -1, std::numeric_limits<int64_t>::max(), -1, pending_job_id[p],
+                pcpus, pmem, pgpus, 0.0, true};
+    double nearest = 0.0;
+    for (int t : st.by_user[pu]) {
+      if (rtask_less(synth, st.tasks[t])) break;  // t > synth
+      nearest = st.tasks[t].dru;
+    }
+    const double pd_mem = nearest + pmem / users->div_mem[pu], pd_cpu = nearest + pcpus / users->div_cpus[pu];
+    const double pending_dru = pd_mem > pd_cpu ? pd_mem : pd_cpu;
+    // victims in priority-map order: (-dru, user) ascending (:252-256); equal
+    // (dru, user) is unordered in the reference => OURS: later same-user position first
+    std::vector<int> order;
+    for (size_t t = 0; t < st.tasks.size(); t++)
+      if (st.tasks[t].alive) order.push_back((int)t);
+    std::vector<int> pos_in_user(st.tasks.size(), 0);
+    for (int u = 0; u < U; u++)
+      for (size_t i = 0; i < st.by_user[u].size(); i++) pos_in_user[st.by_user[u][i]] = (int)i;
+    std::sort(order.begin(), order.end(), [&](int a, int b) {
+      const RTask &x = st.tasks[a], &y = st.tasks[b];
+      if (x.dru != y.dru) return x.dru > y.dru;
+      if (x.user != y.user) return users->name_rank[x.user] < users->name_rank[y.user];
+      return pos_in_user[a] > pos_in_user[b];
+    });
+    std::vector<std::vector<int>> host_victims(H);
+    std::vector<uint8_t> host_has_task(H, 0);
+    for (int t : order) {
+      const RTask& x = st.tasks[t];
+      host_has_task[x.host] = 1;
+      if (!(below || x.user == pu)) continue;
+      if (x.dru < prm->safe_dru_threshold) continue;
+      if (!((x.dru - pending_dru) > prm->min_dru_diff)) continue;
+      host_victims[x.host].push_back(t);
+    }
+    // group cohosts: running cotasks + hosts of everything preempted so far
+    auto group_ok = [&](int h, bool have_attrs) {
+      if (!pending->group_off || !groups) return true;
+      for (int k = pending->group_off[p]; k < pending->group_off[p + 1]; k++) {
+        int g = pending->group_idx[k];
+        int kind = groups->kind[g];
+        int col = groups->attr_col ? groups->attr_col[g] : -1;
+        auto host_attr = [&](int hh) { return (col >= 0 && col < hosts->n_attr_cols) ? hosts->attr[(size_t)col * H + hh] : 0; };
+        if (kind == COOK_GROUP_UNIQUE) {
+          if (!have_attrs) return false;  // (and target-hostname ...) with nil hostname
+          int hn = hosts->hostname_id[h];
+          for (int ph : st.preempted_hosts) if (hosts->hostname_id[ph] == hn) return false;
+          for (int c = groups->cot_off[g]; c < groups->cot_off[g + 1]; c++)
+            if (groups->cot_hostname_id[c] == hn) return false;
+        } else {
+          std::map<int, int> freq;
+          for (int ph : st.preempted_hosts) freq[host_attr(ph)]++;
+          for (int c = groups->cot_off[g]; c < groups->cot_off[g + 1]; c++) freq[groups->cot_attr_val[c]]++;
+          int target = have_attrs ? host_attr(h) : 0;
+          if (freq.empty()) continue;
+          auto it = freq.find(target);
+          if (kind == COOK_GROUP_ATTR_EQUALS) { if (it == freq.end()) return false; }
+          else if (it != freq.end()) {
+            int mn = std::numeric_limits<int>::max(), mx = 0;
+            for (auto& kv : freq) { mn = std::min(mn, kv.second); mx = std::max(mx, kv.second); }
+            if (groups->minimum[g] > (int)freq.size()) mn = 0;
+            if (!(mn == mx || it->second < mx)) return false;
+          }
+        }
+      }
+      return true;
+    };
+    // :380-404 per host (name order): [spare ; victims desc dru], prefix sums,
+    // keep sufficient prefixes, max-key :dru with ties -> LAST
+    bool found = false;
+    double best_dru = 0.0, best_mem = 0, best_cpus = 0, best_gpus = 0;  // (fnil :dru {:dru 0.0}) nil
+    int best_host = -1;
+    std::vector<int> best_tasks;
+    for (int h : hosts_by_name) {
+      if (!st.has_spare[h] && host_victims[h].empty()) continue;
+      const bool have_attrs = host_has_task[h];
+      if (!reb_host_passes(pending, p, hosts, h, have_attrs, prm)) continue;
+      if (!group_ok(h, have_attrs)) continue;
+      double sm = 0.0, sc = 0.0, sg = 0.0;
+      std::vector<int> prefix;
+      auto consider = [&](double dru) {
+        if (sm >= pmem && sc >= pcpus && (pgpus > 0.0 ? sg >= pgpus : true)) {
+          if (dru >= best_dru) {  // max-key: >= keeps the LAST of equal keys; nil counts as 0.0
+            found = true; best_dru = dru; best_host = h; best_tasks = prefix;
+            best_mem = sm; best_cpus = sc; best_gpus = sg;
+          }
+        }
+      };
+      if (st.has_spare[h]) {
+        sg = sg + st.spare_gpus[h]; sm = sm + st.spare_mem[h]; sc = sc + st.spare_cpus[h];
+        consider(DMAX);
+      }
+      for (int t : host_victims[h]) {
+        sg = sg + st.tasks[t].gpus; sm = sm + st.tasks[t].mem; sc = sc + st.tasks[t].cpus;
+        prefix.push_back(t);
+        consider(st.tasks[t].dru);
+      }
+    }
+    if (!found) continue;
+    // ---- next-state :270-309
+    cook_decision& d = out_dec[n_dec];
+    d.pending_idx = p; d.host = best_host; d.dru = best_dru; d.mem = best_mem; d.cpus = best_cpus; d.gpus = best_gpus;
+    d.victim_begin = n_vict; d.victim_count = (int)best_tasks.size();
+    for (int i = (int)best_tasks.size() - 1; i >= 0; i--) out_victims[n_vict++] = best_tasks[i];  // conj onto list => ascending dru
+    std::set<int> changed;
+    changed.insert(pu);
+    for (int t : best_tasks) {
+      RTask& x = st.tasks[t];
+      x.alive = false;
+      auto& lst = st.by_user[x.user];
+      lst.erase(std::find(lst.begin(), lst.end(), t));
+      changed.insert(x.user);
+      st.preempted_hosts.push_back(x.host);
+    }
+    RTask nt = synth;
+    nt.host = best_host;
+    st.tasks.push_back(nt);
+    const int nti = (int)st.tasks.size() - 1;
+    auto& lst = st.by_user[pu];
+    lst.insert(std::upper_bound(lst.begin(), lst.end(), nti,
+                                [&](int a, int b) { return rtask_less(st.tasks[a], st.tasks[b]); }), nti);
+    for (int u : changed) rescore_user(st, users, u);
+    st.has_spare[best_host] = 1;
+    st.spare_mem[best_host] = best_mem - pmem;
+    st.spare_gpus[best_host] = best_gpus - pgpus;
+    st.spare_cpus[best_host] = best_cpus - pcpus;
+    n_dec++;
+  }
+  *out_n = n_dec;
+  return COOK_OK;
+}

@@ -68,3 +68,62 @@ def check_rank_case(case, engine_factory):
         drus = [out["dru"][t] for t in out["order"]]
         assert np.allclose(drus, case["expect_drus"], rtol=1e-12, atol=0), (case["name"], drus)
     return out
+
+
+def rebalance_inputs(case):
+    """spare: host -> (mem, cpus).  Pending job ids continue after the running
+    jobs' ids (creation order); pending priority 50."""
+    run, pend = case["running"], case["pending"]
+    names = sorted({j["user"] for j in run} | {j["user"] for j in pend})
+    uid = {n: i for i, n in enumerate(names)}
+    nu = len(names)
+    div = {k: np.full(nu, case["share"][k]) for k in ("mem", "cpus")}
+    for u, sh in case["shares"].items():
+        for k, v in sh.items():
+            div[k][uid[u]] = v
+    users = abi.make_users(nu, name_rank=np.arange(nu, dtype=np.int32), div_mem=div["mem"],
+                           div_cpus=div["cpus"], div_gpus=np.full(nu, 1.0))
+    hostnames = sorted({j["host"] for j in run} | set(case["spare"].keys()))
+    hid = {h: i for i, h in enumerate(hostnames)}
+    nh = len(hostnames)
+    R = len(run)
+    t = abi.make_tasks(user=np.array([uid[j["user"]] for j in run], np.int32),
+                       priority=np.full(R, 50, np.int32), start_time=np.full(R, T0, np.int64),
+                       task_id=np.arange(1000, 1000 + R, dtype=np.int64),
+                       job_id=np.arange(1, R + 1, dtype=np.int64),
+                       cpus=np.array([j["cpus"] for j in run]), mem=np.array([j["mem"] for j in run]))
+    running = abi.RunningSoA(t=t, host=np.array([hid[j["host"]] for j in run], np.int32))
+    P = len(pend)
+    jobs = abi.JobsSoA(n=P, user=np.array([uid[j["user"]] for j in pend], np.int32),
+                       cpus=np.array([j["cpus"] for j in pend]), mem=np.array([j["mem"] for j in pend]),
+                       gpus=np.zeros(P))
+    has_spare = np.zeros(nh, np.uint8)
+    sc, sm = np.zeros(nh), np.zeros(nh)
+    for h, (m, c) in case["spare"].items():
+        has_spare[hid[h]] = 1
+        sm[hid[h]] = m
+        sc[hid[h]] = c
+    hosts = abi.HostTable(n=nh, hostname_id=np.arange(nh, dtype=np.int32),
+                          name_rank=np.arange(nh, dtype=np.int32), has_spare=has_spare,
+                          spare_cpus=sc, spare_mem=sm, spare_gpus=np.zeros(nh), n_attr_cols=0)
+    p = case["params"]
+    params = abi.RebalanceParams(p["max_preemption"], p["min_dru_diff"], p["safe_dru_threshold"], 0)
+    return dict(running=running, pending=jobs, pending_job_id=np.arange(R + 1, R + 1 + P, dtype=np.int64),
+                pending_priority=np.full(P, 50, np.int32), hosts=hosts, users=users, params=params,
+                hostnames=hostnames)
+
+
+def check_rebalance_case(case, eng):
+    inp = rebalance_inputs(case)
+    out = eng.rebalance(inp["running"], inp["pending"], inp["pending_job_id"], inp["pending_priority"],
+                        inp["hosts"], inp["users"], inp["params"])
+    if "expect" in case:
+        assert len(out) == len(case["expect"]), (case["name"], out)
+        for d, e in zip(out, case["expect"]):
+            assert inp["hostnames"][d["host"]] == e["host"], (case["name"], d)
+            assert d["dru"] == e["dru"] or abs(d["dru"] - e["dru"]) <= 1e-12 * abs(e["dru"]), (case["name"], d)
+            assert d["victims"] == e["victims"] and d["mem"] == e["mem"] and d["cpus"] == e["cpus"], (case["name"], d)
+    else:
+        assert [d["pending_idx"] for d in out] == case["expect_run"], (case["name"], out)
+        assert [v for d in out for v in d["victims"]] == case["expect_preempt"], (case["name"], out)
+    return out

@@ -26,3 +26,14 @@ def test_rank_golden(case, naive):
         check_rank_case(case, factory)
     finally:
         OracleEngine().set_naive_merge(0)
+
+
+with open(os.path.join(HERE, "golden", "rebalance_golden.json")) as f:
+    REB_CASES = json.load(f)
+
+
+@pytest.mark.parametrize("case", REB_CASES, ids=[c["name"] for c in REB_CASES])
+def test_rebalance_golden(case):
+    from golden_util import check_rebalance_case
+    from oracle.pyoracle import OracleEngine
+    check_rebalance_case(case, OracleEngine())
