@@ -1,11 +1,605 @@
-// rebalance.cu — rebalancer preemption-victim search.
-// Placeholder until the kernels land: returns an explicit error (never a CPU
-// fallback).
+// rebalance.cu — rebalancer preemption-victim search on the GPU.
+//
+// Replaces init-state (rebalancer.clj:222-266), compute-pending-default-job-dru
+// (:182-208), compute-preemption-decision (:320-407), next-state (:270-309) and
+// the rebalance loop (:434-467).  Decisions are inherently sequential (H6); the
+// work INSIDE a decision is data-parallel over the running tasks and hosts:
+//
+//   per state change (init + after every decision):
+//     S1 comparator sort of live tasks by (user name, -priority, start, task id,
+//        job id)                                  -> per-user order (tools.clj:614-641)
+//     S2 warp-per-user left fold                  -> cumulative DRU (dru.clj:50-66)
+//     S3 comparator sort by (host name, dru desc, user name, position desc)
+//                                                 -> per-host victim order (:252-256, :349)
+//   per pending job:
+//     P1 warp fold over the job's user            -> job-below-quota, nearest dru
+//     P2 host kernel                              -> constraints per host (:358-377)
+//     P3 thread-per-host segment walk             -> [spare ; victims] prefix sums,
+//        best sufficient prefix per host (:380-403)
+//     P4 argmax over hosts (max dru, ties -> greatest hostname = `max-key` last wins)
+//     P5 apply (single thread)                    -> next-state
+//
+// GPU DRU mode is rejected: the reference itself throws there (see oracle).
 #include "common.cuh"
+#include "sort.cuh"
 
-extern "C" int32_t cook_rebalance(cook_pool* pool, const cook_running_soa*, const cook_jobs_soa*,
-                                  const int64_t*, const int32_t*, const cook_host_table*,
-                                  const cook_groups*, const cook_user_table*,
-                                  const cook_rebalance_params*, cook_decision*, int32_t*, int32_t*) {
-  return set_err(pool, COOK_E_UNSUPPORTED_CONSTRAINT, "cook_rebalance: not implemented yet");
+namespace {
+
+struct RTasks {  // capacity R + max_preemption; synthetic tasks appended
+  int32_t* user; int32_t* prio; int64_t* start; int64_t* tid; int64_t* jid;
+  double* cpus; double* mem; double* gpus; int32_t* host; uint8_t* alive; double* dru;
+  int32_t* pos;  // position inside the user's sorted list
+};
+
+struct LessUser {
+  RTasks t;
+  const int32_t* name_rank;
+  __device__ bool operator()(int32_t a, int32_t b) const {
+    bool la = t.alive[a], lb = t.alive[b];
+    if (la != lb) return la;  // dead tasks last
+    int ua = name_rank[t.user[a]], ub = name_rank[t.user[b]];
+    if (ua != ub) return ua < ub;
+    int pa = -t.prio[a], pb = -t.prio[b];
+    if (pa != pb) return pa < pb;
+    if (t.start[a] != t.start[b]) return t.start[a] < t.start[b];
+    if (t.tid[a] != t.tid[b]) return t.tid[a] < t.tid[b];
+    if (t.jid[a] != t.jid[b]) return t.jid[a] < t.jid[b];
+    return a < b;
+  }
+};
+
+// (sort-by first) over hosts, then priority-map order inside a host:
+// (-dru, user name); equal (dru, user): later same-user position first (ours).
+struct LessHostDru {
+  RTasks t;
+  const int32_t* user_rank;
+  const int32_t* host_rank;
+  __device__ bool operator()(int32_t a, int32_t b) const {
+    bool la = t.alive[a], lb = t.alive[b];
+    if (la != lb) return la;
+    if (!la) return a < b;
+    int ha = host_rank[t.host[a]], hb = host_rank[t.host[b]];
+    if (ha != hb) return ha < hb;
+    double da = t.dru[a], db = t.dru[b];
+    if (da != db) return da > db;
+    int ua = user_rank[t.user[a]], ub = user_rank[t.user[b]];
+    if (ua != ub) return ua < ub;
+    if (t.pos[a] != t.pos[b]) return t.pos[a] > t.pos[b];
+    return a < b;
+  }
+};
+
+__global__ void iota_r(int32_t* p, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = i;
+}
+
+__global__ void user_seg_kernel(const int32_t* ord, RTasks t, int n, int32_t* seg_start, int32_t* seg_end) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  int i = ord[p];
+  if (!t.alive[i]) return;
+  int u = t.user[i];
+  bool first = p == 0 || t.user[ord[p - 1]] != u;
+  bool last = p == n - 1 || !t.alive[ord[p + 1]] || t.user[ord[p + 1]] != u;
+  if (first) seg_start[u] = p;
+  if (last) seg_end[u] = p + 1;
+}
+
+// dru.clj:50-66 for every user: lane-serial left fold (exact association).
+__global__ void __launch_bounds__(128) user_dru_kernel(const int32_t* ord, RTasks t, const double* div_mem,
+                                                       const double* div_cpus, const int32_t* seg_start,
+                                                       const int32_t* seg_end, int n_users) {
+  const int u = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (u >= n_users) return;
+  const int s = seg_start[u], e = seg_end[u];
+  if (e <= s) return;
+  const double md = div_mem[u], cd = div_cpus[u];
+  double am = 0.0, ac = 0.0;
+  for (int base = s; base < e; base += 32) {
+    int p = base + lane;
+    int i = p < e ? ord[p] : -1;
+    double xm = i >= 0 ? t.mem[i] : 0.0, xc = i >= 0 ? t.cpus[i] : 0.0;
+    double mym = 0.0, myc = 0.0;
+    int cntn = min(32, e - base);
+    for (int l = 0; l < cntn; l++) {
+      am = am + __shfl_sync(0xffffffffu, xm, l);
+      ac = ac + __shfl_sync(0xffffffffu, xc, l);
+      if (lane == l) { mym = am; myc = ac; }
+    }
+    if (i >= 0) {
+      double a = mym / md, b = myc / cd;
+      t.dru[i] = a > b ? a : b;
+      t.pos[i] = p - s;
+    }
+  }
+}
+
+struct HostCols {
+  int H;
+  const int32_t* hostname_id; const int32_t* name_rank;
+  uint8_t* has_spare; double* spare_cpus; double* spare_mem; double* spare_gpus;
+  const uint8_t* is_k8s; const int32_t* location;
+  const int32_t* gpu_off; const int32_t* gpu_model; const double* gpu_count;
+  const int32_t* disk_off; const int32_t* disk_type; const double* disk_space;
+  const int64_t* host_start; int n_attr_cols; const int32_t* attr;
+};
+
+struct PendCols {
+  const int32_t* user; const double* cpus; const double* mem; const double* gpus;
+  const int64_t* jid; const int32_t* prio;
+  const int32_t* novel_off; const int32_t* novel_host; const int32_t* gpu_model;
+  const double* disk_request; const int32_t* disk_type;
+  const int32_t* attr_off; const int32_t* attr_col; const int32_t* attr_val;
+  const int64_t* est_end_ms; const int32_t* ckpt_location;
+  const int32_t* group_off; const int32_t* group_idx;
+};
+
+struct GroupCols {
+  int n; const int32_t* kind; const int32_t* attr_col; const int32_t* minimum;
+  const int32_t* cot_off; const int32_t* cot_host; const int32_t* cot_attr;
+};
+
+struct PendScalars {  // per pending job, device resident
+  int below_quota;
+  double pending_dru;
+};
+
+// P1: job-below-quota (:210-220) and pending dru (:182-208) for pending job p.
+__global__ void pending_kernel(const int32_t* ord, RTasks t, PendCols pc, int p, const int32_t* seg_start,
+                               const int32_t* seg_end, const double* q_count, const double* q_cpus,
+                               const double* q_mem, const double* q_gpus, const double* div_mem,
+                               const double* div_cpus, PendScalars* out) {
+  const int lane = threadIdx.x;
+  const int u = pc.user[p];
+  const int s = seg_start[u], e = seg_end[u];
+  const double pm = pc.mem[p], pcpu = pc.cpus[p], pg = pc.gpus ? pc.gpus[p] : 0.0;
+  double an = 1.0, ac = pcpu, am = pm, ag = pg;  // (conj running-jobs p): p first
+  double nearest = 0.0;
+  const int pprio = -pc.prio[p];
+  const long long pj = pc.jid[p];
+  for (int base = s; base < e; base += 32) {
+    int q = base + lane;
+    int i = q < e ? ord[q] : -1;
+    double xc = i >= 0 ? t.cpus[i] : 0.0, xm = i >= 0 ? t.mem[i] : 0.0, xg = i >= 0 ? t.gpus[i] : 0.0;
+    int cntn = min(32, e - base);
+    for (int l = 0; l < cntn; l++) {
+      an = an + 1.0;
+      ac = ac + __shfl_sync(0xffffffffu, xc, l);
+      am = am + __shfl_sync(0xffffffffu, xm, l);
+      ag = ag + __shfl_sync(0xffffffffu, xg, l);
+    }
+    // task <= synthetic pending task [-prio, Long/MAX, nil(-1), job id] ?
+    bool le = false;
+    if (i >= 0) {
+      int tp = -t.prio[i];
+      if (tp != pprio) le = tp < pprio;
+      else if (t.start[i] != 0x7fffffffffffffffLL) le = true;
+      else if (t.tid[i] != -1) le = false;  // nil < any id
+      else le = t.jid[i] <= pj;
+    }
+    unsigned m = __ballot_sync(0xffffffffu, le);
+    if (m) {
+      int last = 31 - __clz(m);
+      nearest = __shfl_sync(0xffffffffu, i >= 0 ? t.dru[i] : 0.0, last);
+    }
+  }
+  if (lane == 0) {
+    out->below_quota = (an <= q_count[u] && ac <= q_cpus[u] && am <= q_mem[u] && ag <= q_gpus[u]) ? 1 : 0;
+    double a = nearest + pm / div_mem[u], b = nearest + pcpu / div_cpus[u];
+    out->pending_dru = a > b ? a : b;
+  }
+}
+
+__device__ __forceinline__ double csr_get(const int32_t* off, const int32_t* key, const double* val, int o, int k) {
+  if (!off) return 0.0;
+  for (int i = off[o]; i < off[o + 1]; i++)
+    if (key[i] == k) return val[i];
+  return 0.0;
+}
+
+// host has at least one live task? (preemptable-host->slave-id, :371-377)
+__global__ void host_has_task_kernel(RTasks t, int n, uint8_t* has_task) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && t.alive[i]) has_task[t.host[i]] = 1;
+}
+
+// P2: constraints of pending job p on every host (constraints.clj:504-515, :680-697)
+__global__ void host_ok_kernel(PendCols pc, int p, HostCols hc, GroupCols gc, const uint8_t* has_task,
+                               const int32_t* preempted_hosts, const int32_t* n_preempted,
+                               int host_lifetime_mins, uint8_t* ok) {
+  int h = blockIdx.x * blockDim.x + threadIdx.x;
+  if (h >= hc.H) return;
+  const bool have = has_task[h] != 0;
+  bool pass = true;
+  if (have && pc.novel_off)
+    for (int k = pc.novel_off[p]; k < pc.novel_off[p + 1]; k++)
+      if (pc.novel_host[k] == hc.hostname_id[h]) pass = false;
+  const bool k8s = have && hc.is_k8s && hc.is_k8s[h];
+  const double g = pc.gpus ? pc.gpus[p] : 0.0;
+  if (k8s) {
+    if (g > 0.0) {
+      double hv = csr_get(hc.gpu_off, hc.gpu_model, hc.gpu_count, h, pc.gpu_model ? pc.gpu_model[p] : -1);
+      if (!(hv == g)) pass = false;
+    } else {
+      int nm = hc.gpu_off ? hc.gpu_off[h + 1] - hc.gpu_off[h] : 0;
+      if (nm != 0) pass = false;
+    }
+  } else if (!(g == 0.0)) {
+    pass = false;
+  }
+  if (pc.disk_request && pc.disk_request[p] >= 0.0 && k8s) {
+    double space = csr_get(hc.disk_off, hc.disk_type, hc.disk_space, h, pc.disk_type ? pc.disk_type[p] : -1);
+    if (!(space >= pc.disk_request[p])) pass = false;
+  }
+  if (pc.attr_off)
+    for (int k = pc.attr_off[p]; k < pc.attr_off[p + 1]; k++) {
+      int col = pc.attr_col[k], val = pc.attr_val[k];
+      if (!have || col < 0 || col >= hc.n_attr_cols) { pass = false; continue; }
+      int hv = hc.attr[(size_t)col * hc.H + h];
+      if (val <= 0 || hv != val) pass = false;
+    }
+  if (pc.est_end_ms && pc.est_end_ms[p] >= 0 && have && hc.host_start && hc.host_start[h] >= 0) {
+    long long death = 1000LL * hc.host_start[h] + 60000LL * host_lifetime_mins;
+    if (!(pc.est_end_ms[p] < death)) pass = false;
+  }
+  if (pc.ckpt_location && pc.ckpt_location[p] >= 0) {
+    int loc = (have && hc.location) ? hc.location[h] : -1;
+    if (loc != pc.ckpt_location[p]) pass = false;
+  }
+  if (pass && pc.group_off && gc.n > 0) {
+    const int np = *n_preempted;
+    for (int k = pc.group_off[p]; k < pc.group_off[p + 1] && pass; k++) {
+      const int gi = pc.group_idx[k];
+      const int kind = gc.kind[gi];
+      const int col = gc.attr_col ? gc.attr_col[gi] : -1;
+      const int c0 = gc.cot_off[gi], c1 = gc.cot_off[gi + 1];
+      auto hattr = [&](int hh) { return (col >= 0 && col < hc.n_attr_cols) ? hc.attr[(size_t)col * hc.H + hh] : 0; };
+      if (kind == COOK_GROUP_UNIQUE) {
+        if (!have) { pass = false; break; }
+        const int hn = hc.hostname_id[h];
+        for (int q = 0; q < np; q++) if (hc.hostname_id[preempted_hosts[q]] == hn) pass = false;
+        for (int c = c0; c < c1; c++) if (gc.cot_host[c] == hn) pass = false;
+      } else {
+        const int n = np + (c1 - c0);
+        if (n == 0) continue;
+        auto val_at = [&](int i) { return i < np ? hattr(preempted_hosts[i]) : gc.cot_attr[c0 + i - np]; };
+        const int target = have ? hattr(h) : 0;
+        int tf = 0;
+        for (int i = 0; i < n; i++) tf += (val_at(i) == target);
+        if (kind == COOK_GROUP_ATTR_EQUALS) { if (tf == 0) pass = false; }
+        else if (tf != 0) {
+          int mn = 0x7fffffff, mx = 0, distinct = 0;
+          for (int i = 0; i < n; i++) {
+            int vi = val_at(i), f = 0; bool first = true;
+            for (int q = 0; q < n; q++) { int vq = val_at(q); if (vq == vi) { f++; if (q < i) first = false; } }
+            if (first) { distinct++; mn = min(mn, f); mx = max(mx, f); }
+          }
+          if (gc.minimum[gi] > distinct) mn = 0;
+          if (!(mn == mx || tf < mx)) pass = false;
+        }
+      }
+    }
+  }
+  ok[h] = pass ? 1 : 0;
+}
+
+// host segments of the (host, dru desc) order
+__global__ void host_seg_kernel(const int32_t* hord, RTasks t, int n, int32_t* hs, int32_t* he) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  int i = hord[p];
+  if (!t.alive[i]) return;
+  int h = t.host[i];
+  bool first = p == 0 || t.host[hord[p - 1]] != h;
+  bool last = p == n - 1 || !t.alive[hord[p + 1]] || t.host[hord[p + 1]] != h;
+  if (first) hs[h] = p;
+  if (last) he[h] = p + 1;
+}
+
+struct HostBest {  // best sufficient prefix of one host
+  double dru, mem, cpus, gpus;
+  int32_t n_victims;  // -1: no candidate
+};
+
+// P3: thread per host.  [spare ; victims by desc dru] prefix sums in the
+// reference's left-fold order; first sufficient prefix has the highest dru of the
+// host; longer prefixes with the SAME dru win the max-key tie (last wins).
+__global__ void host_best_kernel(const int32_t* hord, RTasks t, HostCols hc, PendCols pc, int p,
+                                 const PendScalars* ps, const uint8_t* ok, const int32_t* hs,
+                                 const int32_t* he, double min_diff, double safe, HostBest* out) {
+  int h = blockIdx.x * blockDim.x + threadIdx.x;
+  if (h >= hc.H) return;
+  HostBest b;
+  b.dru = 0.0; b.mem = b.cpus = b.gpus = 0.0; b.n_victims = -1;
+  if (ok[h]) {
+    const double pm = pc.mem[p], pcpu = pc.cpus[p], pg = pc.gpus ? pc.gpus[p] : 0.0;
+    const int pu = pc.user[p];
+    const bool below = ps->below_quota != 0;
+    const double pend = ps->pending_dru;
+    double sm = 0.0, sc = 0.0, sg = 0.0;
+    int nv = 0;
+    bool have = false;
+    double cur = 0.0;
+    auto consider = [&](double dru) {
+      if (sm >= pm && sc >= pcpu && (pg > 0.0 ? sg >= pg : true)) {
+        if (!have || dru >= cur) { have = true; cur = dru; b.dru = dru; b.mem = sm; b.cpus = sc; b.gpus = sg; b.n_victims = nv; }
+      }
+    };
+    if (hc.has_spare[h]) {
+      sg = sg + hc.spare_gpus[h]; sm = sm + hc.spare_mem[h]; sc = sc + hc.spare_cpus[h];
+      consider(1.7976931348623157e308);
+    }
+    for (int q = hs[h]; q < he[h]; q++) {
+      int i = hord[q];
+      double d = t.dru[i];
+      if (!(below || t.user[i] == pu)) continue;
+      if (d < safe) continue;
+      if (!((d - pend) > min_diff)) continue;
+      if (have && d < cur) break;  // later prefixes only have smaller dru
+      sg = sg + t.gpus[i]; sm = sm + t.mem[i]; sc = sc + t.cpus[i];
+      nv++;
+      consider(d);
+    }
+  }
+  out[h] = b;
+}
+
+struct ApplyArgs {
+  RTasks t; HostCols hc; PendCols pc;
+  const int32_t* hord; const int32_t* hs; const int32_t* he;
+  const PendScalars* ps; const HostBest* best;
+  double min_diff, safe;
+  int32_t* n_tasks;        // live + dead task count (grows by one per decision)
+  int32_t* n_dec; int32_t* n_vict; int32_t* preempted_hosts; int32_t* n_preempted;
+  cook_decision* dec; int32_t* victims;
+  int32_t* changed;        // out: 1 if a decision was made
+};
+
+// P4 + P5: argmax over hosts (max dru; ties -> greatest hostname) and next-state.
+__global__ void apply_kernel(ApplyArgs a, int p) {
+  __shared__ double s_dru[256];
+  __shared__ int s_rank[256];
+  __shared__ int s_host[256];
+  const int tid = threadIdx.x;
+  double bd = -1.0; int br = -1, bh = -1;
+  for (int h = tid; h < a.hc.H; h += blockDim.x) {
+    if (a.best[h].n_victims < 0) continue;
+    double d = a.best[h].dru; int r = a.hc.name_rank[h];
+    if (d > bd || (d == bd && r > br)) { bd = d; br = r; bh = h; }
+  }
+  s_dru[tid] = bd; s_rank[tid] = br; s_host[tid] = bh;
+  __syncthreads();
+  for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+    if (tid < s) {
+      double d = s_dru[tid + s]; int r = s_rank[tid + s];
+      if (d > s_dru[tid] || (d == s_dru[tid] && r > s_rank[tid])) { s_dru[tid] = d; s_rank[tid] = r; s_host[tid] = s_host[tid + s]; }
+    }
+    __syncthreads();
+  }
+  if (tid != 0) return;
+  const int h = s_host[0];
+  *a.changed = 0;
+  if (h < 0) return;
+  const HostBest b = a.best[h];
+  const int di = *a.n_dec;
+  cook_decision d;
+  d.pending_idx = p; d.host = h; d.dru = b.dru; d.mem = b.mem; d.cpus = b.cpus; d.gpus = b.gpus;
+  d.victim_begin = *a.n_vict; d.victim_count = b.n_victims;
+  // collect the victims again (same filter, same order), store ascending dru
+  const int pu = a.pc.user[p];
+  const bool below = a.ps->below_quota != 0;
+  int got = 0;
+  for (int q = a.hs[h]; q < a.he[h] && got < b.n_victims; q++) {
+    int i = a.hord[q];
+    double dr = a.t.dru[i];
+    if (!(below || a.t.user[i] == pu)) continue;
+    if (dr < a.safe) continue;
+    if (!((dr - a.ps->pending_dru) > a.min_diff)) continue;
+    a.victims[d.victim_begin + (b.n_victims - 1 - got)] = i;
+    a.t.alive[i] = 0;
+    a.preempted_hosts[(*a.n_preempted)++] = a.t.host[i];
+    got++;
+  }
+  *a.n_vict += b.n_victims;
+  a.dec[di] = d;
+  *a.n_dec = di + 1;
+  // synthetic running task of the pending job on host h (create-task-ent :hostname)
+  const int ni = (*a.n_tasks)++;
+  a.t.user[ni] = pu; a.t.prio[ni] = a.pc.prio[p]; a.t.start[ni] = 0x7fffffffffffffffLL;
+  a.t.tid[ni] = -1; a.t.jid[ni] = a.pc.jid[p];
+  a.t.cpus[ni] = a.pc.cpus[p]; a.t.mem[ni] = a.pc.mem[p]; a.t.gpus[ni] = a.pc.gpus ? a.pc.gpus[p] : 0.0;
+  a.t.host[ni] = h; a.t.alive[ni] = 1; a.t.dru[ni] = 0.0; a.t.pos[ni] = 0;
+  a.hc.has_spare[h] = 1;
+  a.hc.spare_mem[h] = b.mem - a.pc.mem[p];
+  a.hc.spare_gpus[h] = b.gpus - (a.pc.gpus ? a.pc.gpus[p] : 0.0);
+  a.hc.spare_cpus[h] = b.cpus - a.pc.cpus[p];
+  *a.changed = 1;
+}
+
+}  // namespace
+
+#define RUP(dst, src, n) CK(pool, upload(ar, st, (src), (size_t)(n), &(dst)))
+
+extern "C" int32_t cook_rebalance(cook_pool* pool, const cook_running_soa* running,
+                                  const cook_jobs_soa* pending, const int64_t* pending_job_id,
+                                  const int32_t* pending_priority, const cook_host_table* hosts,
+                                  const cook_groups* groups, const cook_user_table* users,
+                                  const cook_rebalance_params* prm, cook_decision* out_decisions,
+                                  int32_t* out_victims, int32_t* out_n) {
+  if (!pool) return COOK_E_BADARG;
+  if (!running || !pending || !pending_job_id || !pending_priority || !hosts || !users || !prm ||
+      !out_decisions || !out_victims || !out_n)
+    return set_err(pool, COOK_E_BADARG, "cook_rebalance: null argument");
+  if (pool->dru_mode != 0)
+    return set_err(pool, COOK_E_UNSUPPORTED_CONSTRAINT,
+                   "cook_rebalance: GPU DRU mode has no reference behaviour (rebalancer.clj:339-349 throws)");
+  const int R = running->t.n, P = pending->n, H = hosts->n, U = users->n_users;
+  const int MP = prm->max_preemption;
+  *out_n = 0;
+  if (P <= 0 || MP <= 0 || H <= 0) return COOK_OK;
+  CK(pool, cudaSetDevice(pool->device));
+  cudaStream_t st = pool->stream;
+  Arena& ar = pool->arena;
+  const int CAP = R + MP + 1;
+  const int G = groups ? groups->n_groups : 0;
+  Sizer sz;
+  for (int k = 0; k < 6; k++) sz.add<int64_t>(CAP);  // generous: covers int32/int64/double columns
+  for (int k = 0; k < 8; k++) sz.add<double>(CAP);
+  for (int k = 0; k < 8; k++) sz.add<int32_t>(CAP);
+  for (int k = 0; k < 12; k++) sz.add<double>(std::max(U, H) + 1);
+  for (int k = 0; k < 16; k++) sz.add<int32_t>(std::max(U, H) + 2);
+  size_t csr_h = (hosts->gpu_off ? hosts->gpu_off[H] : 0) + (hosts->disk_off ? hosts->disk_off[H] : 0);
+  sz.add<double>(csr_h + 64); sz.add<int32_t>(csr_h + 64);
+  sz.add<int32_t>((size_t)hosts->n_attr_cols * H + 1);
+  sz.add<int64_t>(H + 1);
+  for (int k = 0; k < 8; k++) sz.add<double>(P + 1);
+  for (int k = 0; k < 12; k++) sz.add<int32_t>(P + 2);
+  size_t csr_p = (pending->novel_off ? pending->novel_off[P] : 0) + 2 * (size_t)(pending->attr_off ? pending->attr_off[P] : 0) +
+                 (pending->group_off ? pending->group_off[P] : 0);
+  sz.add<int32_t>(csr_p + 64); sz.add<int64_t>(P + 1);
+  if (G) { sz.add<int32_t>(6 * (size_t)(G + 2)); sz.add<int32_t>(2 * (size_t)(groups->cot_off ? groups->cot_off[G] : 0) + 64); }
+  sz.add<HostBest>(H + 1); sz.add<cook_decision>(MP + 1); sz.add<int32_t>(CAP + MP);
+  sz.add<PendScalars>(4); sz.add<int32_t>(64);
+  CK(pool, ar.reserve(sz.off + (1 << 16)));
+  ar.reset();
+
+  RTasks t;
+  t.user = ar.take<int32_t>(CAP); t.prio = ar.take<int32_t>(CAP); t.start = ar.take<int64_t>(CAP);
+  t.tid = ar.take<int64_t>(CAP); t.jid = ar.take<int64_t>(CAP); t.cpus = ar.take<double>(CAP);
+  t.mem = ar.take<double>(CAP); t.gpus = ar.take<double>(CAP); t.host = ar.take<int32_t>(CAP);
+  t.alive = ar.take<uint8_t>(CAP); t.dru = ar.take<double>(CAP); t.pos = ar.take<int32_t>(CAP);
+  if (!t.pos) return set_err(pool, COOK_E_OOM, "cook_rebalance: arena exhausted");
+  const cook_tasks_soa& rt = running->t;
+#define CPY(dst, src, T) if (R) CK(pool, cudaMemcpyAsync(dst, src, sizeof(T) * R, cudaMemcpyHostToDevice, st))
+  CPY(t.user, rt.user, int32_t); CPY(t.prio, rt.priority, int32_t); CPY(t.start, rt.start_time, int64_t);
+  CPY(t.tid, rt.task_id, int64_t); CPY(t.jid, rt.job_id, int64_t); CPY(t.cpus, rt.cpus, double);
+  CPY(t.mem, rt.mem, double); CPY(t.host, running->host, int32_t);
+  if (rt.gpus) { CPY(t.gpus, rt.gpus, double); } else CK(pool, cudaMemsetAsync(t.gpus, 0, sizeof(double) * CAP, st));
+#undef CPY
+  CK(pool, cudaMemsetAsync(t.alive, 0, CAP, st));
+  if (R) CK(pool, cudaMemsetAsync(t.alive, 1, R, st));
+  CK(pool, cudaMemsetAsync(t.dru, 0, sizeof(double) * CAP, st));
+
+  int32_t* d_urank; double *d_divm, *d_divc, *d_qn, *d_qc, *d_qm, *d_qg;
+  RUP(d_urank, users->name_rank, U); RUP(d_divm, users->div_mem, U); RUP(d_divc, users->div_cpus, U);
+  RUP(d_qn, users->quota_count, U); RUP(d_qc, users->quota_cpus, U); RUP(d_qm, users->quota_mem, U);
+  RUP(d_qg, users->quota_gpus, U);
+
+  HostCols hc;
+  memset(&hc, 0, sizeof(hc));
+  hc.H = H;
+  { int32_t* p; RUP(p, hosts->hostname_id, H); hc.hostname_id = p; RUP(p, hosts->name_rank, H); hc.name_rank = p; }
+  hc.has_spare = ar.take<uint8_t>(H + 1); hc.spare_cpus = ar.take<double>(H + 1);
+  hc.spare_mem = ar.take<double>(H + 1); hc.spare_gpus = ar.take<double>(H + 1);
+  CK(pool, cudaMemsetAsync(hc.has_spare, 0, H + 1, st));
+  CK(pool, cudaMemsetAsync(hc.spare_cpus, 0, sizeof(double) * (H + 1), st));
+  CK(pool, cudaMemsetAsync(hc.spare_mem, 0, sizeof(double) * (H + 1), st));
+  CK(pool, cudaMemsetAsync(hc.spare_gpus, 0, sizeof(double) * (H + 1), st));
+  if (hosts->has_spare) CK(pool, cudaMemcpyAsync(hc.has_spare, hosts->has_spare, H, cudaMemcpyHostToDevice, st));
+  if (hosts->spare_cpus) CK(pool, cudaMemcpyAsync(hc.spare_cpus, hosts->spare_cpus, sizeof(double) * H, cudaMemcpyHostToDevice, st));
+  if (hosts->spare_mem) CK(pool, cudaMemcpyAsync(hc.spare_mem, hosts->spare_mem, sizeof(double) * H, cudaMemcpyHostToDevice, st));
+  if (hosts->spare_gpus) CK(pool, cudaMemcpyAsync(hc.spare_gpus, hosts->spare_gpus, sizeof(double) * H, cudaMemcpyHostToDevice, st));
+  { uint8_t* p; RUP(p, hosts->is_k8s, H); hc.is_k8s = p; }
+  { int32_t* p; RUP(p, hosts->location, H); hc.location = p; }
+  if (hosts->gpu_off) { int32_t* p; RUP(p, hosts->gpu_off, H + 1); hc.gpu_off = p;
+    int n = std::max(1, hosts->gpu_off[H]); RUP(p, hosts->gpu_model, n); hc.gpu_model = p;
+    double* q; RUP(q, hosts->gpu_count, n); hc.gpu_count = q; }
+  if (hosts->disk_off) { int32_t* p; RUP(p, hosts->disk_off, H + 1); hc.disk_off = p;
+    int n = std::max(1, hosts->disk_off[H]); RUP(p, hosts->disk_type, n); hc.disk_type = p;
+    double* q; RUP(q, hosts->disk_space, n); hc.disk_space = q; }
+  { int64_t* p; RUP(p, hosts->host_start_time, H); hc.host_start = p; }
+  hc.n_attr_cols = hosts->attr ? hosts->n_attr_cols : 0;
+  if (hc.n_attr_cols > 0) { int32_t* p; RUP(p, hosts->attr, (size_t)hc.n_attr_cols * H); hc.attr = p; }
+
+  PendCols pc;
+  memset(&pc, 0, sizeof(pc));
+  { int32_t* p; RUP(p, pending->user, P); pc.user = p; RUP(p, pending_priority, P); pc.prio = p; }
+  { double* p; RUP(p, pending->cpus, P); pc.cpus = p; RUP(p, pending->mem, P); pc.mem = p; RUP(p, pending->gpus, P); pc.gpus = p; }
+  { int64_t* p; RUP(p, pending_job_id, P); pc.jid = p; RUP(p, pending->est_end_ms, P); pc.est_end_ms = p; }
+  if (pending->novel_off) { int32_t* p; RUP(p, pending->novel_off, P + 1); pc.novel_off = p;
+    RUP(p, pending->novel_host, std::max(1, pending->novel_off[P])); pc.novel_host = p; }
+  { int32_t* p; RUP(p, pending->gpu_model, P); pc.gpu_model = p; RUP(p, pending->disk_type, P); pc.disk_type = p;
+    RUP(p, pending->ckpt_location, P); pc.ckpt_location = p; }
+  { double* p; RUP(p, pending->disk_request, P); pc.disk_request = p; }
+  if (pending->attr_off) { int32_t* p; RUP(p, pending->attr_off, P + 1); pc.attr_off = p;
+    int n = std::max(1, pending->attr_off[P]); RUP(p, pending->attr_col, n); pc.attr_col = p;
+    RUP(p, pending->attr_val, n); pc.attr_val = p; }
+  GroupCols gc;
+  memset(&gc, 0, sizeof(gc));
+  if (G && pending->group_off) {
+    int32_t* p; RUP(p, pending->group_off, P + 1); pc.group_off = p;
+    RUP(p, pending->group_idx, std::max(1, pending->group_off[P])); pc.group_idx = p;
+    gc.n = G;
+    RUP(p, groups->kind, G); gc.kind = p; RUP(p, groups->attr_col, G); gc.attr_col = p;
+    RUP(p, groups->minimum, G); gc.minimum = p; RUP(p, groups->cot_off, G + 1); gc.cot_off = p;
+    int n = std::max(1, groups->cot_off ? groups->cot_off[G] : 0);
+    RUP(p, groups->cot_hostname_id, n); gc.cot_host = p; RUP(p, groups->cot_attr_val, n); gc.cot_attr = p;
+    if (!gc.cot_off || !gc.kind) return set_err(pool, COOK_E_BADARG, "cook_rebalance: incomplete cook_groups");
+  }
+
+  int32_t* d_ord = ar.take<int32_t>(CAP); int32_t* d_hord = ar.take<int32_t>(CAP);
+  int32_t* d_tmp = ar.take<int32_t>(CAP);
+  int32_t* d_us = ar.take<int32_t>(U + 1); int32_t* d_ue = ar.take<int32_t>(U + 1);
+  int32_t* d_hs = ar.take<int32_t>(H + 1); int32_t* d_he = ar.take<int32_t>(H + 1);
+  uint8_t* d_has_task = ar.take<uint8_t>(H + 1); uint8_t* d_ok = ar.take<uint8_t>(H + 1);
+  HostBest* d_best = ar.take<HostBest>(H + 1);
+  cook_decision* d_dec = ar.take<cook_decision>(MP + 1);
+  int32_t* d_vict = ar.take<int32_t>(CAP + MP);
+  int32_t* d_pre = ar.take<int32_t>(CAP + MP);
+  PendScalars* d_ps = ar.take<PendScalars>(4);
+  int32_t* d_cnt = ar.take<int32_t>(64);  // [0] n_tasks [1] n_dec [2] n_vict [3] n_preempted [4] changed
+  if (!d_cnt) return set_err(pool, COOK_E_OOM, "cook_rebalance: arena exhausted");
+  int32_t h_cnt[8] = {R, 0, 0, 0, 1, 0, 0, 0};
+  CK(pool, cudaMemcpyAsync(d_cnt, h_cnt, sizeof(h_cnt), cudaMemcpyHostToDevice, st));
+
+  const int TB = 256;
+  int n_tasks = R, n_dec = 0;
+  bool dirty = true;
+  for (int p = 0; p < P && n_dec < MP; p++) {
+    if (dirty) {  // S1-S3: state changed => per-user order, DRU, per-host victim order
+      const int n = n_tasks;
+      CK(pool, cudaMemsetAsync(d_us, 0, sizeof(int32_t) * (U + 1), st));
+      CK(pool, cudaMemsetAsync(d_ue, 0, sizeof(int32_t) * (U + 1), st));
+      CK(pool, cudaMemsetAsync(d_hs, 0, sizeof(int32_t) * (H + 1), st));
+      CK(pool, cudaMemsetAsync(d_he, 0, sizeof(int32_t) * (H + 1), st));
+      CK(pool, cudaMemsetAsync(d_has_task, 0, H + 1, st));
+      if (n > 0) {
+        iota_r<<<(n + TB - 1) / TB, TB, 0, st>>>(d_ord, n);
+        CK(pool, csort::sort_indices(d_ord, d_tmp, n, LessUser{t, d_urank}, st));
+        user_seg_kernel<<<(n + TB - 1) / TB, TB, 0, st>>>(d_ord, t, n, d_us, d_ue);
+        user_dru_kernel<<<(U + 3) / 4, 128, 0, st>>>(d_ord, t, d_divm, d_divc, d_us, d_ue, U);
+        iota_r<<<(n + TB - 1) / TB, TB, 0, st>>>(d_hord, n);
+        CK(pool, csort::sort_indices(d_hord, d_tmp, n, LessHostDru{t, d_urank, hc.name_rank}, st));
+        host_seg_kernel<<<(n + TB - 1) / TB, TB, 0, st>>>(d_hord, t, n, d_hs, d_he);
+        host_has_task_kernel<<<(n + TB - 1) / TB, TB, 0, st>>>(t, n, d_has_task);
+      }
+      dirty = false;
+    }
+    pending_kernel<<<1, 32, 0, st>>>(d_ord, t, pc, p, d_us, d_ue, d_qn, d_qc, d_qm, d_qg, d_divm, d_divc, d_ps);
+    host_ok_kernel<<<(H + TB - 1) / TB, TB, 0, st>>>(pc, p, hc, gc, d_has_task, d_pre, d_cnt + 3,
+                                                     prm->host_lifetime_mins, d_ok);
+    host_best_kernel<<<(H + TB - 1) / TB, TB, 0, st>>>(d_hord, t, hc, pc, p, d_ps, d_ok, d_hs, d_he,
+                                                       prm->min_dru_diff, prm->safe_dru_threshold, d_best);
+    ApplyArgs aa;
+    aa.t = t; aa.hc = hc; aa.pc = pc; aa.hord = d_hord; aa.hs = d_hs; aa.he = d_he; aa.ps = d_ps;
+    aa.best = d_best; aa.min_diff = prm->min_dru_diff; aa.safe = prm->safe_dru_threshold;
+    aa.n_tasks = d_cnt; aa.n_dec = d_cnt + 1; aa.n_vict = d_cnt + 2; aa.preempted_hosts = d_pre;
+    aa.n_preempted = d_cnt + 3; aa.dec = d_dec; aa.victims = d_vict; aa.changed = d_cnt + 4;
+    apply_kernel<<<1, 256, 0, st>>>(aa, p);
+    CK(pool, cudaGetLastError());
+    CK(pool, cudaMemcpyAsync(h_cnt, d_cnt, sizeof(int32_t) * 5, cudaMemcpyDeviceToHost, st));
+    CK(pool, cudaStreamSynchronize(st));
+    n_tasks = h_cnt[0]; n_dec = h_cnt[1];
+    dirty = h_cnt[4] != 0;
+  }
+  if (n_dec > 0) {
+    CK(pool, cudaMemcpyAsync(out_decisions, d_dec, sizeof(cook_decision) * n_dec, cudaMemcpyDeviceToHost, st));
+    if (h_cnt[2] > 0)
+      CK(pool, cudaMemcpyAsync(out_victims, d_vict, sizeof(int32_t) * h_cnt[2], cudaMemcpyDeviceToHost, st));
+    CK(pool, cudaStreamSynchronize(st));
+  }
+  *out_n = n_dec;
+  return COOK_OK;
 }

@@ -237,3 +237,62 @@ def gen_c3_pool(seed=3, n_jobs=20_000, n_offers=1_000, n_users=200, n_running=4_
     t = gen_pool(seed, n_jobs, n_offers, n_users, n_running)
     add_constraints(t, seed + 1000, **kw)
     return t
+
+
+def gen_rebalance(seed, n_running, n_pending, n_hosts, n_users, *, max_preemption=64,
+                  min_dru_diff=0.5, safe_dru_threshold=1.0, constraints=True):
+    """BASELINE config #4 style rebalancer input: running tasks skewed so that some
+    users sit far above their share, a few hosts with spare resources, pending jobs
+    of under-served users; optional host attributes / novel-host / group constraints."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    owners = _zipf_owner(rng, n_running, n_users, 1.3)
+    run = _tasks(rng, n_running, owners, True, 1, (0.5, 1, 2, 4), lambda r, n: (512.0 * r.integers(1, 33, size=n)))
+    host = rng.integers(0, n_hosts, n_running).astype(np.int32)
+    running = abi.RunningSoA(t=abi.make_tasks(**run), host=host)
+    pu = rng.integers(n_users // 2, n_users, n_pending).astype(np.int32)  # tail users are under-served
+    pend = _tasks(rng, n_pending, pu, False, 10_000_000, (1, 2, 4, 8), lambda r, n: (1024.0 * r.integers(1, 33, size=n)))
+    name_rank = rng.permutation(n_users).astype(np.int32)
+    tot_c = np.zeros(n_users); tot_m = np.zeros(n_users)
+    np.add.at(tot_c, owners, run["cpus"]); np.add.at(tot_m, owners, run["mem"])
+    share_c = np.maximum(8.0, np.round(np.median(tot_c[tot_c > 0]) if (tot_c > 0).any() else 8.0))
+    share_m = np.maximum(4096.0, np.round(np.median(tot_m[tot_m > 0]) if (tot_m > 0).any() else 4096.0))
+    quota = {"count": np.where(rng.random(n_users) < 0.2, rng.integers(5, 200, n_users), 1e12).astype(float)}
+    users = abi.make_users(n_users, name_rank=name_rank, div_mem=np.full(n_users, share_m),
+                           div_cpus=np.full(n_users, share_c), div_gpus=np.full(n_users, 1.0), quota=quota)
+    has_spare = (rng.random(n_hosts) < 0.05).astype(np.uint8)
+    hostname_id = np.arange(n_hosts, dtype=np.int32)
+    hkw = dict(n=n_hosts, hostname_id=hostname_id, name_rank=rng.permutation(n_hosts).astype(np.int32),
+               has_spare=has_spare, spare_cpus=np.where(has_spare, rng.integers(0, 9, n_hosts), 0).astype(float),
+               spare_mem=np.where(has_spare, 1024.0 * rng.integers(0, 17, n_hosts), 0.0),
+               spare_gpus=np.zeros(n_hosts), n_attr_cols=0)
+    jkw = dict(n=n_pending, user=pu, cpus=pend["cpus"], mem=pend["mem"], gpus=np.zeros(n_pending))
+    groups = None
+    if constraints:
+        ncol = 3
+        attr = rng.integers(0, 4, (ncol, n_hosts)).astype(np.int32)
+        hkw.update(n_attr_cols=ncol, attr=attr.reshape(-1), is_k8s=(rng.random(n_hosts) < 0.5).astype(np.uint8),
+                   location=rng.integers(0, 2, n_hosts).astype(np.int32))
+        al_c = [[int(rng.integers(0, ncol))] if rng.random() < 0.3 else [] for _ in range(n_pending)]
+        al_v = [[int(rng.integers(1, 4))] if c else [] for c in al_c]
+        attr_off, attr_col = abi.csr(al_c)
+        _, attr_val = abi.csr(al_v)
+        novel = [[int(x) for x in rng.choice(hostname_id, size=2, replace=False)] if rng.random() < 0.3 else []
+                 for _ in range(n_pending)]
+        novel_off, novel_host = abi.csr(novel)
+        ng = max(1, n_pending // 8)
+        gl = [[int(rng.integers(0, ng))] if rng.random() < 0.3 else [] for _ in range(n_pending)]
+        group_off, group_idx = abi.csr(gl)
+        kinds = rng.integers(0, 3, ng).astype(np.int32)
+        acol = rng.integers(0, ncol, ng).astype(np.int32)
+        cot_h = [[int(x) for x in rng.choice(hostname_id, size=int(rng.integers(0, 3)), replace=False)] for _ in range(ng)]
+        cot_a = [[int(attr[acol[g]][h]) for h in cot_h[g]] for g in range(ng)]
+        cot_off, cot_host = abi.csr(cot_h)
+        _, cot_attr = abi.csr(cot_a)
+        groups = abi.Groups(n_groups=ng, kind=kinds, attr_col=acol, minimum=rng.integers(1, 4, ng).astype(np.int32),
+                            cot_off=cot_off, cot_hostname_id=cot_host, cot_attr_val=cot_attr)
+        jkw.update(attr_off=attr_off, attr_col=attr_col, attr_val=attr_val, novel_off=novel_off,
+                   novel_host=novel_host, group_off=group_off, group_idx=group_idx,
+                   ckpt_location=np.where(rng.random(n_pending) < 0.1, rng.integers(0, 2, n_pending), -1).astype(np.int32))
+    return dict(running=running, pending=abi.JobsSoA(**jkw), pending_job_id=pend["job_id"],
+                pending_priority=pend["priority"], hosts=abi.HostTable(**hkw), users=users, groups=groups,
+                params=abi.RebalanceParams(max_preemption, min_dru_diff, safe_dru_threshold, 0))

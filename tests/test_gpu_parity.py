@@ -124,3 +124,27 @@ def test_constraint_kernel_parity(gpu, oracle, seed, nj, no, nu, nr, kw):
     assert np.array_equal(mg["ports"], mo["ports"])
     assert np.array_equal(mg["fail"] == 0, mo["fail"] == 0)
     assert mg["stats"]["n_matched"] == mo["stats"]["n_matched"] > 0
+
+
+def test_rebalance_golden_on_gpu(gpu):
+    """The reference's own rebalancer known answers (K19, K22) through the CUDA path."""
+    import json
+    import os
+    from golden_util import check_rebalance_case
+    here = os.path.dirname(os.path.abspath(__file__))
+    with open(os.path.join(here, "golden", "rebalance_golden.json")) as f:
+        cases = json.load(f)
+    for case in cases:
+        check_rebalance_case(case, gpu)
+
+
+@pytest.mark.parametrize("seed,nr,np_,nh,nu", [(51, 2000, 64, 100, 20), (52, 20000, 128, 500, 100),
+                                               (53, 500, 40, 10, 5)])
+def test_rebalance_parity_random(gpu, oracle, seed, nr, np_, nh, nu):
+    t = traces.gen_rebalance(seed, nr, np_, nh, nu)
+    args = (t["running"], t["pending"], t["pending_job_id"], t["pending_priority"], t["hosts"],
+            t["users"], t["params"])
+    do = oracle.rebalance(*args, groups=t["groups"])
+    dg = gpu.rebalance(*args, groups=t["groups"])
+    assert len(do) > 0
+    assert dg == do
