@@ -1,0 +1,112 @@
+"""CPU tests of the host side: ABI surface, handle errors, multi-rank exchange (gloo)."""
+import ctypes as C
+import os
+import re
+import socket
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    src = open(os.path.join(ROOT, "include", "cook_gpu.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(cook_[a-z_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    """No compute calls without a GPU: only dlopen + dlsym of the C ABI."""
+    import __graft_entry__ as ge
+    ge.build()
+    lib = C.CDLL(os.path.join(ROOT, "cook_b200", "libcookgpu.so"))
+    names = _declared_symbols()
+    assert {"cook_gpu_init", "cook_rank", "cook_match", "cook_rebalance", "cook_allgather_usage",
+            "cook_pool_open", "cook_pool_close", "cook_last_error", "cook_gpu_version"} <= set(names)
+    for n in names:
+        assert hasattr(lib, n), n
+    lib.cook_gpu_version.restype = C.c_char_p
+    assert b"sm_100a" in lib.cook_gpu_version()
+
+
+def test_no_cpu_fallback_without_device():
+    """On a box without a GPU the product refuses to start instead of falling back."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from cook_b200.engine import CookError, GpuEngine
+    with pytest.raises(CookError):
+        GpuEngine()
+
+
+def test_product_does_not_import_the_oracle():
+    for fn in os.listdir(os.path.join(ROOT, "cook_b200")):
+        if fn.endswith(".py"):
+            assert "oracle" not in open(os.path.join(ROOT, "cook_b200", fn)).read().replace(
+                "oracle/pyoracle.py", "").replace("the oracle", "").replace("CPU oracle", ""), fn
+    for fn in os.listdir(os.path.join(ROOT, "cook_b200", "csrc")):
+        if not fn.endswith((".cu", ".cuh")):
+            continue
+        txt = open(os.path.join(ROOT, "cook_b200", "csrc", fn)).read()
+        assert "cook_oracle" not in txt.replace("oracle/cook_oracle.cpp", "") and "#include \"../../oracle" not in txt
+
+
+def test_lpt_assignment():
+    from cook_b200.sharding import assign_pools_lpt
+    costs = [40, 30, 20, 10]
+    assert assign_pools_lpt(costs, 4) == [0, 1, 2, 3]
+    a = assign_pools_lpt([9, 8, 7, 3, 2, 1], 2)
+    loads = [sum(c for c, g in zip([9, 8, 7, 3, 2, 1], a) if g == k) for k in range(2)]
+    assert sorted(loads) == [15, 15]
+    assert assign_pools_lpt([5] * 16, 8).count(0) == 2
+
+
+def test_quota_group_aggregation_matches_reference_test():
+    """test/cook/test/scheduler/scheduler.clj:222-230 (aggregate-quota-groups)."""
+    from cook_b200.sharding import aggregate_quota_groups
+    out = aggregate_quota_groups({"a": [100, 10, 1, 0], "b": [200, 20, 2, 0], "c": [400, 40, 4, 0],
+                                  "d": [800, 80, 8, 0]}, {"a": "s", "b": "s"})
+    assert list(out) == ["s"] and list(out["s"]) == [300, 30, 3, 0]
+
+
+def _worker(rank, world, port, q):
+    import torch.distributed as dist
+    from cook_b200 import traces
+    from cook_b200.sharding import exchange_usage, usage_delta
+    from oracle.pyoracle import OracleEngine
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    t = traces.gen_pool(100 + rank, 800, 40, 10, 100)   # rank r owns pool r
+    o = OracleEngine()
+    ranked = o.rank(t["running"], t["pending"], t["users"])["ranked"]
+    m = o.match(ranked, t["jobs"], t["offers"], t["users"], traces.match_params(800))
+    jb = t["jobs"]
+    d = usage_delta(m["considerable"], m["assign"], jb.col("user"), jb.col("cpus"), jb.col("mem"),
+                    jb.col("gpus"), 10)
+    allv = exchange_usage(d)
+    q.put((rank, d, allv))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_usage_exchange_two_ranks_gloo():
+    """world_size 2 on CPU: both ranks end up with both pools' usage deltas."""
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    ps = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in range(2)], key=lambda x: x[0])
+    for p in ps:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (_, d0, all0), (_, d1, all1) = res
+    assert all0.shape == (2, 10, 4)
+    assert np.array_equal(all0, all1)
+    assert np.array_equal(all0[0], d0) and np.array_equal(all0[1], d1)
+    assert d0[:, 0].sum() > 0 and not np.array_equal(d0, d1)
