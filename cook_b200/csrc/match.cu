@@ -924,6 +924,100 @@ __global__ void cons_queue_kernel(ConsArgs a, const uint8_t* keep, int32_t* cons
   if (lane == 0) *out_n = min(n_out, a.num_considerable);
 }
 
+// Parallel form of the queue-order pass for the common case of NO global pool
+// quota (tools.clj:923 `(if (nil? quota) queue ...)`): the filters are then
+// element-wise and "take N" is a stable compaction => three-kernel scan.
+constexpr int SCAN_TB = 256;
+constexpr int SCAN_ITEMS = 4;  // elements per thread
+
+__device__ __forceinline__ bool cons_flag(const ConsArgs& a, const uint8_t* keep, int i) {
+  if (i >= a.n_ranked || !keep[i]) return false;
+  const int j = a.ranked[i];
+  if (a.jb.allowed && !a.jb.allowed[j]) return false;
+  if (a.jb.plugin && !a.jb.plugin[j]) return false;
+  return true;
+}
+
+__global__ void __launch_bounds__(SCAN_TB) cons_count_kernel(ConsArgs a, const uint8_t* keep,
+                                                             int32_t* block_sums) {
+  __shared__ int warp_sums[SCAN_TB / 32];
+  const int base = (blockIdx.x * SCAN_TB + threadIdx.x) * SCAN_ITEMS;
+  int c = 0;
+#pragma unroll
+  for (int q = 0; q < SCAN_ITEMS; q++) c += cons_flag(a, keep, base + q) ? 1 : 0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0) warp_sums[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int w = 0; w < SCAN_TB / 32; w++) t += warp_sums[w];
+    block_sums[blockIdx.x] = t;
+  }
+}
+
+__global__ void cons_scan_blocks_kernel(int32_t* block_sums, int nblocks, int32_t* out_n, int cap) {
+  // single warp, sequential over chunks of 32 block sums (nblocks <= ~10k)
+  const int lane = threadIdx.x;
+  int carry = 0;
+  for (int base = 0; base < nblocks; base += 32) {
+    int i = base + lane;
+    int v = i < nblocks ? block_sums[i] : 0;
+    int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int n = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += n;
+    }
+    if (i < nblocks) block_sums[i] = carry + incl - v;  // exclusive
+    carry += __shfl_sync(0xffffffffu, incl, 31);
+  }
+  if (lane == 0) *out_n = min(carry, cap);
+}
+
+__global__ void __launch_bounds__(SCAN_TB) cons_scatter_kernel(ConsArgs a, const uint8_t* keep,
+                                                               const int32_t* block_off, int32_t* cons,
+                                                               double* kc, double* km, double* kg,
+                                                               int32_t* kports, uint8_t* kflags) {
+  __shared__ int warp_off[SCAN_TB / 32];
+  const int base = (blockIdx.x * SCAN_TB + threadIdx.x) * SCAN_ITEMS;
+  bool f[SCAN_ITEMS];
+  int c = 0;
+#pragma unroll
+  for (int q = 0; q < SCAN_ITEMS; q++) { f[q] = cons_flag(a, keep, base + q); c += f[q] ? 1 : 0; }
+  int incl = c;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int n = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += n;
+  }
+  if (lane == 31) warp_off[warp] = incl;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int w = 0; w < SCAN_TB / 32; w++) { int x = warp_off[w]; warp_off[w] = t; t += x; }
+  }
+  __syncthreads();
+  int slot = block_off[blockIdx.x] + warp_off[warp] + incl - c;
+#pragma unroll
+  for (int q = 0; q < SCAN_ITEMS; q++) {
+    if (!f[q]) continue;
+    if (slot < a.num_considerable) {
+      const int j = a.ranked[base + q];
+      cons[slot] = j;
+      kc[slot] = a.jb.cpus[j];
+      km[slot] = a.jb.mem[j];
+      kg[slot] = a.jb.gpus ? a.jb.gpus[j] : 0.0;
+      kports[slot] = a.jb.ports ? a.jb.ports[j] : 0;
+      uint8_t fl = 0;
+      if (a.jb.group_off && a.jb.group_off[j + 1] > a.jb.group_off[j]) fl |= 1;
+      kflags[slot] = fl;
+    }
+    slot++;
+  }
+}
+
 // ------------------------------------------------------------------ setup
 __global__ void gather_offers_kernel(const int32_t* perm, int O, const double* c, const double* m,
                                      const double* rc, const double* rm, VmStatic* vs) {
@@ -1264,9 +1358,21 @@ static int32_t run_plan(cook_pool* pool, MatchPlan* mp, int32_t* out_considerabl
   cons_seg_kernel<<<(n_ranked + TB - 1) / TB, TB, 0, st>>>(mp->d_pos, ca.ranked, ca.jb.user, n_ranked,
                                                            mp->d_seg_s, mp->d_seg_e);
   cons_user_kernel<<<(U + 3) / 4, 128, 0, st>>>(ca, mp->d_pos, mp->d_seg_s, mp->d_seg_e, mp->d_keep);
-  cons_queue_kernel<<<1, 32, 0, st>>>(ca, mp->d_keep, mp->d_cons, mp->d_kc, mp->d_km, mp->d_kg,
-                                      mp->d_kports, mp->d_kflags, mp->d_counters);
-  launches += 3;
+  if (ca.pool_q.enabled) {
+    // global pool quota: an order-dependent f64 left fold over the survivors
+    // (filter-sequential) => exact single-warp pass
+    cons_queue_kernel<<<1, 32, 0, st>>>(ca, mp->d_keep, mp->d_cons, mp->d_kc, mp->d_km, mp->d_kg,
+                                        mp->d_kports, mp->d_kflags, mp->d_counters);
+    launches += 3;
+  } else {
+    const int per_block = SCAN_TB * SCAN_ITEMS;
+    const int nsb = (n_ranked + per_block - 1) / per_block;
+    cons_count_kernel<<<nsb, SCAN_TB, 0, st>>>(ca, mp->d_keep, mp->d_tmp);
+    cons_scan_blocks_kernel<<<1, 32, 0, st>>>(mp->d_tmp, nsb, mp->d_counters, ca.num_considerable);
+    cons_scatter_kernel<<<nsb, SCAN_TB, 0, st>>>(ca, mp->d_keep, mp->d_tmp, mp->d_cons, mp->d_kc, mp->d_km,
+                                                 mp->d_kg, mp->d_kports, mp->d_kflags);
+    launches += 5;
+  }
   CK(pool, cudaGetLastError());
   int32_t n_cons = 0;
   CK(pool, cudaMemcpyAsync(&n_cons, mp->d_counters, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
