@@ -43,7 +43,6 @@ constexpr int MAXD = 2 * MAXB;     // dirty list capacity (two blocks)
 constexpr int TOPK = 8;            // candidates kept per (job, chunk)
 constexpr int ROW_V_OFF = TOPK * 32 * 8;             // byte offset of the v part of a row
 constexpr int ROW_BYTES = TOPK * 32 * (8 + 4);       // 3072 B per job
-constexpr int RING = 4;                              // TMA row ring depth in the resolver
 
 // Per-VM state is AoS, 32 B per record, so one record is two 128-bit loads and a
 // clean candidate's state can be staged with 16-byte async copies.
@@ -440,6 +439,33 @@ __device__ void evaluate_row(const MatchArgs& a, int k, int blk, EvalShared& E, 
 }
 
 // --------------------------------------------------------------- resolver
+// CTA 0.  Jobs are resolved in ROUNDS of up to SPEC_W consecutive feasible jobs:
+//   P  (parallel, one warp per job): exact best and runner-up VM of the job
+//      against the ROUND-START state = clean chunk candidates from its row +
+//      exact re-evaluation of all dirty VMs (+ rare chunk re-scans).
+//   C  (chain): job i consumes the commits of jobs 0..i-1 of the round in order;
+//      a commit changes ONE VM, so job i re-evaluates just that VM and updates
+//      its (best, runner-up) pair; when commit i-1 is in, its best is exact and
+//      it publishes its own commit.  If a job loses its best and does not know
+//      its exact runner-up any more it aborts: the round is truncated there and
+//      the job restarts the next round (where it has no predecessors).
+//   A  (warp 0): commits are applied to the dirty list, outputs written.
+constexpr int SPEC_W = RES_THREADS / 32;
+constexpr int ROW_RING = 2 * SPEC_W;
+
+struct VmRec {  // state of one VM as seen by the resolver
+  double ac, am, lc, lm, rc, rm;
+  int an, pu, slot, pad;  // slot: index in the dirty list, -1 if clean at round start
+};
+
+struct CommitRec {
+  VmRec st;      // state AFTER this job's placement
+  int vm;        // -1: job not placed
+  int aborted;
+  int pu_before;
+  int pad;
+};
+
 struct ResolverShared {
   // dirty list (VMs touched since the snapshot), SoA so lane d reads entry d
   double d_ac[MAXD], d_am[MAXD];
@@ -451,8 +477,18 @@ struct ResolverShared {
   uint8_t jgrp[MAXB];
   int16_t feas_list[MAXB];
   // TMA-staged rows of the next feasible jobs
-  __align__(128) unsigned char rows[RING][ROW_BYTES];
-  unsigned long long bar[RING];
+  __align__(128) unsigned char rows[ROW_RING][ROW_BYTES];
+  unsigned long long bar[ROW_RING];
+  CommitRec commits[SPEC_W];
+  volatile int commit_flag[SPEC_W];
+  // round header (written by warp 0 between the two CTA barriers)
+  volatile int r_mode;   // 0 = speculative round, 1 = exit
+  volatile int r_n;      // jobs in the round
+  volatile int r_q0;     // index of the round's first job in feas_list
+  volatile int r_seq;    // round sequence number (commit_flag target)
+  volatile int r_blk, r_k0, r_nD;
+  volatile unsigned r_gq0;  // global feasible-job counter of the round's first job (row ring position)
+  unsigned long long n_rescan;
 };
 
 __device__ __forceinline__ double warp_max_f64(double f) {  // f >= 0
@@ -473,22 +509,55 @@ __device__ __forceinline__ double warp_argmax(double f, int v, int& wv, int& wl)
   return wf;
 }
 
-template <bool CONSTR, bool PROF>
-__device__ void resolve_job(const MatchArgs& a, int blk, int k, int ib, const unsigned char* rowp,
-                            ResolverShared& S, unsigned* bitmap, int& nD,
-                            unsigned long long* lstats, unsigned long long* prof, long long& tp0) {
+struct Top2 {  // a lane's two best candidates (distinct VMs)
+  double f1, f2;
+  int v1, v2, s1, s2;
+  __device__ __forceinline__ void init() { f1 = f2 = 0.0; v1 = v2 = 0x7fffffff; s1 = s2 = -1; }
+  __device__ __forceinline__ void ins(double f, int v, int s) {
+    if (!(f > 0.0)) return;
+    if (better(f, v, f1, v1)) { f2 = f1; v2 = v1; s2 = s1; f1 = f; v1 = v; s1 = s; }
+    else if (better(f, v, f2, v2)) { f2 = f; v2 = v; s2 = s; }
+  }
+};
+
+__device__ __forceinline__ VmRec load_rec(const MatchArgs& a, const ResolverShared& S, const VmDyn* snapd,
+                                          int v, int slot, bool constr) {
+  VmRec r;
+  r.slot = slot; r.pad = 0;
+  if (slot >= 0) {
+    r.ac = S.d_ac[slot]; r.am = S.d_am[slot]; r.lc = S.d_lc[slot]; r.lm = S.d_lm[slot];
+    r.rc = S.d_rc[slot]; r.rm = S.d_rm[slot]; r.an = S.d_an[slot]; r.pu = S.d_pu[slot];
+  } else {
+    const double2* st2 = reinterpret_cast<const double2*>(a.of.vs + v);
+    const double2 s0 = __ldg(st2), s1 = __ldg(st2 + 1);
+    const double2 d0 = __ldcg(reinterpret_cast<const double2*>(snapd + v));
+    int2 d1 = make_int2(0, 0);
+    if (constr) d1 = __ldcg(reinterpret_cast<const int2*>(snapd + v) + 2);
+    r.ac = d0.x; r.am = d0.y; r.an = d1.x; r.pu = d1.y;
+    r.lc = s0.x; r.lm = s0.y; r.rc = s1.x; r.rm = s1.y;
+  }
+  return r;
+}
+
+struct SpecResult {
+  double bf, sf;
+  int bv, sv;          // -1: none
+  VmRec brec, srec;
+};
+
+// P phase for one job: exact best + runner-up against the round-start state.
+template <bool CONSTR>
+__device__ void spec_phase(const MatchArgs& a, int blk, int ib, const unsigned char* rowp,
+                           ResolverShared& S, const unsigned* bitmap, int nD, SpecResult& out,
+                           JobRegs& r) {
   const int lane = threadIdx.x & 31;
   const VmDyn* snapd = a.dyn.d[blk & 1];
-  long long tp1 = 0;
-#define PROF_LAP(i) do { if (PROF) { tp1 = clock64(); prof[i] += (unsigned long long)(tp1 - tp0); tp0 = tp1; } } while (0)
-  JobRegs r;
   r.c = S.jc[ib]; r.m = S.jm[ib]; r.g = CONSTR ? S.jg[ib] : 0.0;
   r.ports = CONSTR ? S.jports[ib] : 0; r.j = S.jj[ib];
-  const bool grp = CONSTR && S.jgrp[ib];
-  // ---- my chunk's first clean candidate (row is in shared memory, TMA-staged)
-  double cf = 0.0, bound = 0.0;
-  int cv = 0x7fffffff;
-  if (!grp) {
+  Top2 t;
+  t.init();
+  double bound = 0.0;
+  {
     const double* rf = reinterpret_cast<const double*>(rowp);
     const int32_t* rv = reinterpret_cast<const int32_t*>(rowp + ROW_V_OFF);
     double f[TOPK];
@@ -504,84 +573,176 @@ __device__ void resolve_job(const MatchArgs& a, int blk, int k, int ib, const un
       live_bits |= (live ? 1u : 0u) << i;
       dirty_bits |= (((w >> (vi & 31)) & 1u) & (live ? 1u : 0u)) << i;
     }
-    const unsigned clean = live_bits & ~dirty_bits;  // lists are sorted: live_bits is a prefix mask
-    if (clean) {
-      const int i = __ffs(clean) - 1;
+    unsigned clean = live_bits & ~dirty_bits;  // sorted list: live_bits is a prefix mask
+    int nclean = 0;
 #pragma unroll
-      for (int q = 0; q < TOPK; q++)
-        if (q == i) { cf = f[q]; cv = v[q]; }
-    } else if (live_bits == ((1u << TOPK) - 1u)) {
-      bound = f[TOPK - 1];  // full list, all dirty: rest of the chunk is <= this
+    for (int pick = 0; pick < 2; pick++) {
+      if (clean) {
+        const int i = __ffs(clean) - 1;
+        clean &= clean - 1;
+#pragma unroll
+        for (int q = 0; q < TOPK; q++)
+          if (q == i) t.ins(f[q], v[q], -1);
+        nclean++;
+      }
     }
+    // fewer than two clean entries out of a FULL list: the rest of the chunk is
+    // only known to be <= the last entry
+    if (nclean < 2 && live_bits == ((1u << TOPK) - 1u)) bound = f[TOPK - 1];
   }
-  PROF_LAP(11);
-  // ---- exact re-evaluation of dirty VMs against their current state; my
-  // candidate = better of (clean candidate of my chunk, my dirty entries)
-  const double mb = warp_max_f64(bound);
-  PROF_LAP(1);
-  if (PROF) prof[6] += nD;
-  int cslot = -1;
+  // exact re-evaluation of dirty VMs against their round-start state
   for (int d = lane; d < nD; d += 32) {
     double f = eval_vm<CONSTR>(a, r, S.d_vm[d], S.d_ac[d], S.d_am[d], S.d_an[d], S.d_pu[d],
-                               S.d_lc[d], S.d_lm[d], S.d_rc[d], S.d_rm[d], grp);
+                               S.d_lc[d], S.d_lm[d], S.d_rc[d], S.d_rm[d], false);
+    t.ins(f, S.d_vm[d], d);
+  }
+  int bv, bl, sv, sl;
+  double bf = warp_argmax(t.f1, t.v1, bv, bl);
+  // runner-up: the winner lane offers its second candidate instead
+  double sf = warp_argmax(lane == bl ? t.f2 : t.f1, lane == bl ? t.v2 : t.v1, sv, sl);
+  const double mb = warp_max_f64(bound);
+  if (mb > 0.0 && mb >= sf) {
+    // rare: a chunk whose listed candidates are (almost) all dirty could still
+    // hold the best or the runner-up => exact re-scan of those chunks
+    unsigned need = __ballot_sync(0xffffffffu, bound > 0.0 && bound >= sf);
+    const double2* st2 = reinterpret_cast<const double2*>(a.of.vs);
+    const double2* dy2 = reinterpret_cast<const double2*>(snapd);
+    while (need) {
+      const int c = __ffs(need) - 1;
+      need &= need - 1;
+      for (int v = c + 32 * lane; v < a.of.O; v += 32 * 32) {
+        if ((bitmap[v >> 5] >> (v & 31)) & 1u) continue;
+        if (v == t.v1 || v == t.v2) continue;  // already a candidate of this lane
+        const double2 s0 = st2[2 * v], s1 = st2[2 * v + 1];
+        const double2 d0 = __ldcg(dy2 + 2 * v);
+        int2 d1 = make_int2(0, 0);
+        if (CONSTR) d1 = __ldcg(reinterpret_cast<const int2*>(dy2 + 2 * v + 1));
+        t.ins(eval_vm<CONSTR>(a, r, v, d0.x, d0.y, d1.x, d1.y, s0.x, s0.y, s1.x, s1.y, false), v, -1);
+      }
+      if (lane == 0) S.n_rescan++;
+    }
+    // a re-scanned VM may also sit in another lane's list (lane c's own clean
+    // entries): duplicates are harmless for the max, but the runner-up must be a
+    // DIFFERENT VM than the winner, so mask the winner VM explicitly.
+    bf = warp_argmax(t.f1, t.v1, bv, bl);
+    const bool a1 = t.v1 != bv;
+    sf = warp_argmax(a1 ? t.f1 : t.f2, a1 ? t.v1 : t.v2, sv, sl);
+  }
+  out.bf = bf; out.sf = sf;
+  out.bv = bf > 0.0 ? bv : -1;
+  out.sv = sf > 0.0 ? sv : -1;
+  if (out.bv >= 0) {
+    const int slot = __shfl_sync(0xffffffffu, t.s1, bl);
+    out.brec = load_rec(a, S, snapd, out.bv, slot, CONSTR);
+  }
+  if (out.sv >= 0) {
+    int slot = __shfl_sync(0xffffffffu, (t.v1 == out.sv) ? t.s1 : t.s2, sl);
+    out.srec = load_rec(a, S, snapd, out.sv, slot, CONSTR);
+  }
+}
+
+// C phase: consume predecessors' commits in order, then publish own commit.
+template <bool CONSTR>
+__device__ void chain_phase(const MatchArgs& a, ResolverShared& S, int wi, int seq, const JobRegs& r,
+                            SpecResult& sp) {
+  const int lane = threadIdx.x & 31;
+  bool second_known = true;
+  bool aborted = false;
+  for (int j = 0; j < wi && !aborted; j++) {
+    while (S.commit_flag[j] != seq) __nanosleep(20);
+    __threadfence_block();
+    const CommitRec& c = S.commits[j];
+    if (c.aborted) { aborted = true; break; }
+    const int x = c.vm;
+    if (x < 0) continue;
+    const VmRec st = c.st;
+    const double f = eval_vm<CONSTR>(a, r, x, st.ac, st.am, st.an, st.pu, st.lc, st.lm, st.rc, st.rm, false);
+    if (x == sp.bv) {
+      if (f > 0.0) { sp.bf = f; sp.brec = st; }  // fuller => fitness grew, still the best
+      else if (second_known) {                    // my best no longer fits
+        sp.bf = sp.sf; sp.bv = sp.sv; sp.brec = sp.srec;
+        sp.sf = 0.0; sp.sv = -1;
+        second_known = sp.bv < 0;  // nothing left at all => trivially known
+      } else aborted = true;
+    } else if (x == sp.sv) {
+      if (f > 0.0) {
+        sp.sf = f; sp.srec = st;
+        if (better(sp.sf, sp.sv, sp.bf, sp.bv)) {
+          double tf = sp.bf; sp.bf = sp.sf; sp.sf = tf;
+          int tv = sp.bv; sp.bv = sp.sv; sp.sv = tv;
+          VmRec tr = sp.brec; sp.brec = sp.srec; sp.srec = tr;
+        }
+      } else { sp.sf = 0.0; sp.sv = -1; second_known = false; }
+    } else if (f > 0.0) {
+      if (sp.bv < 0 || better(f, x, sp.bf, sp.bv)) {
+        if (sp.bv >= 0) { sp.sf = sp.bf; sp.sv = sp.bv; sp.srec = sp.brec; second_known = true; }
+        sp.bf = f; sp.bv = x; sp.brec = st;
+      } else if (second_known && (sp.sv < 0 || better(f, x, sp.sf, sp.sv))) {
+        sp.sf = f; sp.sv = x; sp.srec = st;
+      }
+    }
+  }
+  if (lane == 0) {
+    CommitRec& m = S.commits[wi];
+    m.aborted = aborted ? 1 : 0;
+    m.vm = -1;
+    m.pu_before = 0;
+    if (!aborted && sp.bv >= 0 && sp.bf > 0.0) {
+      VmRec st = sp.brec;
+      m.pu_before = st.pu;
+      st.ac = st.ac + r.c;
+      st.am = st.am + r.m;
+      st.an += 1;
+      st.pu += r.ports;
+      m.st = st;
+      m.vm = sp.bv;
+    }
+    __threadfence_block();
+    S.commit_flag[wi] = seq;
+  }
+  __syncwarp();
+}
+
+// Single-warp exact resolution of one job against live state (group jobs).
+template <bool CONSTR>
+__device__ void resolve_group_job(const MatchArgs& a, int blk, int k, int ib, ResolverShared& S,
+                                  unsigned* bitmap, int& nD, unsigned long long* lstats) {
+  const int lane = threadIdx.x & 31;
+  const VmDyn* snapd = a.dyn.d[blk & 1];
+  JobRegs r;
+  r.c = S.jc[ib]; r.m = S.jm[ib]; r.g = CONSTR ? S.jg[ib] : 0.0;
+  r.ports = CONSTR ? S.jports[ib] : 0; r.j = S.jj[ib];
+  double cf = 0.0;
+  int cv = 0x7fffffff, cslot = -1;
+  for (int d = lane; d < nD; d += 32) {
+    double f = eval_vm<CONSTR>(a, r, S.d_vm[d], S.d_ac[d], S.d_am[d], S.d_an[d], S.d_pu[d],
+                               S.d_lc[d], S.d_lm[d], S.d_rc[d], S.d_rm[d], true);
     int v = S.d_vm[d];
     if (f > cf || (f == cf && f > 0.0 && v < cv)) { cf = f; cv = v; cslot = d; }
   }
-  __syncwarp();
-  PROF_LAP(12);
-  int wv, wl;
-  double wf = warp_argmax(cf, cv, wv, wl);
-  int wslot = __shfl_sync(0xffffffffu, cslot, wl < 0 ? 0 : wl);  // -1: clean candidate
-  PROF_LAP(2);
-  // ---- rare paths: chunk re-scan (all TOPK candidates dirty and the bound
-  // could still win) or full re-scan (group constraints)
-  bool did_rescan = false;
-  if (grp || (mb > 0.0 && mb >= wf)) {
-    const double2* st2 = reinterpret_cast<const double2*>(a.of.vs);
-    const double2* dy2 = reinterpret_cast<const double2*>(snapd);
-    double rf = 0.0;
-    int rv = 0x7fffffff;
-    auto scan = [&](int v) {
-      if ((bitmap[v >> 5] >> (v & 31)) & 1u) return;  // dirty VMs were evaluated exactly above
-      const double2 s0 = st2[2 * v], s1 = st2[2 * v + 1];
-      const double2 d0 = __ldcg(dy2 + 2 * v);
-      int2 d1 = make_int2(0, 0);
-      if (CONSTR) d1 = __ldcg(reinterpret_cast<const int2*>(dy2 + 2 * v + 1));
-      double f = eval_vm<CONSTR>(a, r, v, d0.x, d0.y, d1.x, d1.y, s0.x, s0.y, s1.x, s1.y, grp);
-      if (f > rf || (f == rf && f > 0.0 && v < rv)) { rf = f; rv = v; }
-    };
-    if (grp) {
-      for (int v = lane; v < a.of.O; v += 32) scan(v);
-      lstats[2]++;
-    } else {
-      unsigned need = __ballot_sync(0xffffffffu, bound > 0.0 && bound >= wf);
-      did_rescan = true;
-      while (need) {
-        int c = __ffs(need) - 1;
-        need &= need - 1;
-        for (int v = c + 32 * lane; v < a.of.O; v += 32 * 32) scan(v);
-        lstats[1]++;
-      }
-    }
-    int wrv, wrl;
-    const double wrf = warp_argmax(rf, rv, wrv, wrl);
-    if (wrf > wf || (wrf == wf && wrf > 0.0 && wrv < wv)) { wf = wrf; wv = wrv; wslot = -1; }
+  const double2* st2 = reinterpret_cast<const double2*>(a.of.vs);
+  const double2* dy2 = reinterpret_cast<const double2*>(snapd);
+  for (int v = lane; v < a.of.O; v += 32) {
+    if ((bitmap[v >> 5] >> (v & 31)) & 1u) continue;
+    const double2 s0 = st2[2 * v], s1 = st2[2 * v + 1];
+    const double2 d0 = __ldcg(dy2 + 2 * v);
+    int2 d1 = make_int2(0, 0);
+    if (CONSTR) d1 = __ldcg(reinterpret_cast<const int2*>(dy2 + 2 * v + 1));
+    double f = eval_vm<CONSTR>(a, r, v, d0.x, d0.y, d1.x, d1.y, s0.x, s0.y, s1.x, s1.y, true);
+    if (f > cf || (f == cf && f > 0.0 && v < cv)) { cf = f; cv = v; cslot = -1; }
   }
-  PROF_LAP(3);
-  // ---- commit (all lanes hold identical wf/wv/wslot)
+  lstats[2]++;
+  int wv, wl;
+  const double wf = warp_argmax(cf, cv, wv, wl);
   if (wf > 0.0) {
-    int slot = wslot;
-    if (slot < 0) {  // clean VM becomes dirty: its snapshot record is its current state
+    int slot = __shfl_sync(0xffffffffu, cslot, wl);
+    if (slot < 0) {
       slot = nD;
       if (lane == 0) {
-        const VmStatic vs = a.of.vs[wv];
-        const double2 d0 = __ldcg(reinterpret_cast<const double2*>(snapd + wv));
-        int2 d1 = make_int2(0, 0);
-        if (CONSTR) d1 = __ldcg(reinterpret_cast<const int2*>(snapd + wv) + 2);
+        const VmRec rec = load_rec(a, S, snapd, wv, -1, CONSTR);
         S.d_vm[slot] = wv;
-        S.d_ac[slot] = d0.x; S.d_am[slot] = d0.y;
-        S.d_an[slot] = d1.x; S.d_pu[slot] = d1.y;
-        S.d_lc[slot] = vs.lc; S.d_lm[slot] = vs.lm; S.d_rc[slot] = vs.rc; S.d_rm[slot] = vs.rm;
+        S.d_ac[slot] = rec.ac; S.d_am[slot] = rec.am; S.d_an[slot] = rec.an; S.d_pu[slot] = rec.pu;
+        S.d_lc[slot] = rec.lc; S.d_lm[slot] = rec.lm; S.d_rc[slot] = rec.rc; S.d_rm[slot] = rec.rm;
         bitmap[wv >> 5] |= 1u << (wv & 31);
       }
       nD++;
@@ -595,7 +756,7 @@ __device__ void resolve_job(const MatchArgs& a, int blk, int k, int ib, const un
       S.d_touch[slot] = blk;
       a.assign[k] = wv;
       a.fail[k] = COOK_FAIL_NONE;
-      if (CONSTR && grp) {
+      if (CONSTR) {
         for (int q = a.jb.group_off[r.j]; q < a.jb.group_off[r.j + 1]; q++) {
           int g = a.jb.group_idx[q];
           int n = __ldcg(a.gr.gp_n + g);
@@ -606,26 +767,75 @@ __device__ void resolve_job(const MatchArgs& a, int blk, int k, int ib, const un
       }
     }
     lstats[3]++;
-  } else {
-    if (lane == 0) { a.assign[k] = -1; a.fail[k] = COOK_FAIL_CONSTRAINT; }
+  } else if (lane == 0) {
+    a.assign[k] = -1; a.fail[k] = COOK_FAIL_CONSTRAINT;
   }
   __syncwarp();
-  if (!did_rescan && !grp) lstats[0]++;
-  PROF_LAP(4);
-#undef PROF_LAP
 }
 
+// A phase (warp 0): apply the round's commits to the dirty list; returns the
+// number of jobs of the round that are final.
+__device__ int apply_round(const MatchArgs& a, ResolverShared& S, unsigned* bitmap, int& nD, int blk,
+                           int k0, int q0, int n, unsigned long long* lstats) {
+  const int lane = threadIdx.x & 31;
+  const bool in = lane < n;
+  const int ab = in ? S.commits[lane].aborted : 0;
+  const unsigned abm = __ballot_sync(0xffffffffu, in && ab);
+  const int n_done = abm ? (__ffs(abm) - 1) : n;
+  const bool act = lane < n_done;
+  const int vm = act ? S.commits[lane].vm : -1;
+  int slot = (act && vm >= 0) ? S.commits[lane].st.slot : -1;
+  // first / last commit of each distinct VM inside the round
+  bool first = act && vm >= 0, last = act && vm >= 0;
+  int first_lane = lane;
+  for (int j = 0; j < SPEC_W; j++) {
+    const int vj = __shfl_sync(0xffffffffu, vm, j);
+    if (vm >= 0 && vj == vm) {
+      if (j < lane) { first = false; if (j < first_lane) first_lane = j; }
+      if (j > lane) last = false;
+    }
+  }
+  // new dirty slots for VMs that were clean at round start
+  const unsigned newm = __ballot_sync(0xffffffffu, first && slot < 0);
+  if (first && slot < 0) slot = nD + __popc(newm & ((1u << lane) - 1u));
+  // a later commit of the same VM carries the slot of the first one
+  const int fslot = __shfl_sync(0xffffffffu, slot, first_lane);
+  if (act && vm >= 0 && !first) slot = fslot;
+  if (last) {
+    const VmRec st = S.commits[lane].st;
+    S.d_vm[slot] = vm; S.d_ac[slot] = st.ac; S.d_am[slot] = st.am; S.d_an[slot] = st.an;
+    S.d_pu[slot] = st.pu; S.d_lc[slot] = st.lc; S.d_lm[slot] = st.lm; S.d_rc[slot] = st.rc;
+    S.d_rm[slot] = st.rm; S.d_touch[slot] = blk;
+  }
+  if (first && S.commits[lane].st.slot < 0) atomicOr(&bitmap[vm >> 5], 1u << (vm & 31));
+  if (act) {
+    const int k = k0 + S.feas_list[q0 + lane];
+    a.assign[k] = vm;
+    a.fail[k] = vm >= 0 ? COOK_FAIL_NONE : COOK_FAIL_CONSTRAINT;
+    if (vm >= 0) a.ports_start[k] = S.commits[lane].pu_before;
+  }
+  nD += __popc(newm);
+  lstats[3] += __popc(__ballot_sync(0xffffffffu, act && vm >= 0));
+  lstats[0] += n_done;
+  __syncwarp();
+  return n_done;
+}
+
+// Warp 0 between rounds: block transitions (publish, wait for rows, compaction,
+// feasibility list), TMA row issue, next round header.
 template <bool CONSTR, bool PROF>
-__device__ void resolve_block(const MatchArgs& a, int blk, ResolverShared& S, unsigned* bitmap,
-                              int& nD, unsigned& seq, unsigned long long* lstats,
-                              unsigned long long* prof) {
+struct Driver {
+  int blk, nblk, k0, nj, nfeas, qdone, qissued, nD;
+  unsigned gq;  // global feasible counter at qdone
+};
+
+template <bool CONSTR>
+__device__ void begin_block(const MatchArgs& a, ResolverShared& S, unsigned* bitmap, int blk, int& nD,
+                            int& nfeas, unsigned long long* lstats) {
   const int lane = threadIdx.x & 31;
   const int k0 = blk * a.B;
   const int k1 = min(k0 + a.B, a.n_cons);
   const int nj = k1 - k0;
-  long long tp0 = PROF ? clock64() : 0, tp1 = 0;
-#define PROF_LAP(i) do { if (PROF) { tp1 = clock64(); prof[i] += (unsigned long long)(tp1 - tp0); tp0 = tp1; } } while (0)
-  // this block's job requests -> shared (static data, plain coalesced loads)
   for (int i = lane; i < nj; i += 32) {
     S.jc[i] = a.kc[k0 + i]; S.jm[i] = a.km[k0 + i]; S.jj[i] = a.cons[k0 + i];
     if (CONSTR) { S.jg[i] = a.kg[k0 + i]; S.jports[i] = a.kports[k0 + i]; S.jgrp[i] = a.kflags[k0 + i] & 1; }
@@ -655,18 +865,16 @@ __device__ void resolve_block(const MatchArgs& a, int blk, ResolverShared& S, un
     }
     nD = keep_n;
   }
-  PROF_LAP(0);
   // rows of this block ready?
   if (lane == 0) {
     while (ld_acquire_u32(a.rows_ready + blk) < (unsigned)nj) __nanosleep(20);
     asm volatile("fence.proxy.async;" ::: "memory");  // generic-proxy writes -> async-proxy (TMA) reads
   }
   __syncwarp();
-  PROF_LAP(9);
   // jobs with no feasible VM at the snapshot are unplaceable now too (resources
   // and count constraints only tighten within a cycle): skip them wholesale.
   const uint8_t* feas = a.feas + (size_t)(blk & 1) * a.B;
-  int nfeas = 0;
+  nfeas = 0;
   for (int base = 0; base < nj; base += 32) {
     const int i = base + lane;
     const bool valid = i < nj;
@@ -674,57 +882,34 @@ __device__ void resolve_block(const MatchArgs& a, int blk, ResolverShared& S, un
     if (valid && !fz) { a.assign[k0 + i] = -1; a.fail[k0 + i] = COOK_FAIL_RESOURCES; }
     const unsigned mask = __ballot_sync(0xffffffffu, fz);
     const unsigned vmask = __ballot_sync(0xffffffffu, valid);
-    const int nskip = __popc(vmask & ~mask);
-    lstats[0] += nskip;
-    if (PROF) prof[7] += nskip;
+    lstats[0] += __popc(vmask & ~mask);
     if (fz) S.feas_list[nfeas + __popc(mask & ((1u << lane) - 1u))] = (int16_t)i;
     nfeas += __popc(mask);
   }
   __syncwarp();
-  {
-    // TMA ring: rows of the next RING-1 feasible jobs are in flight while one is resolved
-    const unsigned char* gbase = a.rows + (size_t)(blk & 1) * a.B * ROW_BYTES;
-    auto issue = [&](int q) {  // lane 0 only
-      const unsigned s = (seq + (unsigned)q) % RING;
-      mbar_expect_tx(&S.bar[s], ROW_BYTES);
-      tma_load_1d(S.rows[s], gbase + (size_t)S.feas_list[q] * ROW_BYTES, ROW_BYTES, &S.bar[s]);
-    };
-    if (lane == 0)
-      for (int q = 0; q < nfeas && q < RING - 1; q++) issue(q);
-    PROF_LAP(1);
-    for (int q = 0; q < nfeas; q++) {
-      const int ib = S.feas_list[q];
-      if (lane == 0 && q + RING - 1 < nfeas) issue(q + RING - 1);  // slot of job q-1: free since its __syncwarp
-      const unsigned sq = seq + (unsigned)q;
-      mbar_wait(&S.bar[sq % RING], (sq / RING) & 1u);
-      PROF_LAP(10);
-      resolve_job<CONSTR, PROF>(a, blk, k0 + ib, ib, S.rows[sq % RING], S, bitmap, nD, lstats, prof, tp0);
-    }
-    seq += (unsigned)nfeas;
-  }
-  // publish every dirty entry (touched in this or the previous block) into the
-  // buffer the evaluators read for block blk+2.
-  {
-    VmDyn* pub = a.dyn.d[blk & 1];
-    for (int d = lane; d < nD; d += 32) {
-      int v = S.d_vm[d];
-      __stcg(reinterpret_cast<double2*>(pub + v), make_double2(S.d_ac[d], S.d_am[d]));
-      __stcg(reinterpret_cast<int2*>(pub + v) + 2, make_int2(S.d_an[d], S.d_pu[d]));
-    }
-    __syncwarp();
-    if (lane == 0) {
-      __threadfence();
-      asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(a.published), "r"((unsigned)(blk + 1)) : "memory");
-    }
-    __syncwarp();
-  }
-  PROF_LAP(5);
-#undef PROF_LAP
 }
 
-// Pipeline.  The resolver (warp 0 of CTA 0) places block t while the evaluator
-// CTAs score block t+1 against the state published after block t-1 (buffer
-// (t+1)&1).  Synchronisation is by two monotone counters only:
+__device__ void end_block(const MatchArgs& a, ResolverShared& S, int blk, int nD) {
+  // publish every dirty entry (touched in this or the previous block) into the
+  // buffer the evaluators read for block blk+2.
+  const int lane = threadIdx.x & 31;
+  VmDyn* pub = a.dyn.d[blk & 1];
+  for (int d = lane; d < nD; d += 32) {
+    int v = S.d_vm[d];
+    __stcg(reinterpret_cast<double2*>(pub + v), make_double2(S.d_ac[d], S.d_am[d]));
+    __stcg(reinterpret_cast<int2*>(pub + v) + 2, make_int2(S.d_an[d], S.d_pu[d]));
+  }
+  __syncwarp();
+  if (lane == 0) {
+    __threadfence();
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(a.published), "r"((unsigned)(blk + 1)) : "memory");
+  }
+  __syncwarp();
+}
+
+// Pipeline.  The resolver CTA places block t while the evaluator CTAs score
+// block t+1 against the state published after block t-1 (buffer (t+1)&1).
+// Synchronisation is by two monotone counters only:
 //   rows_ready[b]  evaluators -> resolver (one arrival per scored row)
 //   published      resolver -> evaluators (# blocks resolved and published)
 template <bool CONSTR, bool PROF>
@@ -735,24 +920,102 @@ __global__ void __launch_bounds__(RES_THREADS, 1) match_kernel(MatchArgs a) {
     ResolverShared& S = *reinterpret_cast<ResolverShared*>(smem_raw);
     unsigned* bitmap = reinterpret_cast<unsigned*>(smem_raw + sizeof(ResolverShared));
     const int words = (a.of.O + 31) / 32;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int i = threadIdx.x; i < words; i += RES_THREADS) bitmap[i] = 0u;
     if (threadIdx.x == 0) {
-      for (int i = 0; i < RING; i++) mbar_init(&S.bar[i], 1);
+      for (int i = 0; i < ROW_RING; i++) mbar_init(&S.bar[i], 1);
+      for (int i = 0; i < SPEC_W; i++) S.commit_flag[i] = 0;
+      S.n_rescan = 0;
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    if (threadIdx.x >= 32) return;
-    int nD = 0;
-    unsigned seq = 0;
+    // ---- driver state (warp 0 only)
+    int blk = 0, k0 = 0, nfeas = 0, qdone = 0, qissued = 0, nD = 0, seq = 0;
+    unsigned gq = 0;  // global feasible-job counter at qdone (row ring position)
+    bool open = false;  // a block is open
     unsigned long long lstats[4] = {0, 0, 0, 0};
-    unsigned long long prof[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-    long long t0 = clock64();
-    for (int t = 0; t < nblk; t++) resolve_block<CONSTR, PROF>(a, t, S, bitmap, nD, seq, lstats, prof);
-    prof[8] = (unsigned long long)(clock64() - t0);
+    unsigned long long prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long t_start = clock64();
+    while (true) {
+      if (warp == 0) {
+        long long td0 = PROF ? clock64() : 0;
+        // advance to a state where a round can be issued (or exit)
+        int mode = 0, n = 0;
+        while (true) {
+          if (!open) {
+            if (blk >= nblk) { mode = 1; break; }
+            k0 = blk * a.B;
+            begin_block<CONSTR>(a, S, bitmap, blk, nD, nfeas, lstats);
+            qdone = 0; qissued = 0;
+            open = true;
+          }
+          // keep the row ring full
+          if (lane == 0) {
+            const unsigned char* gbase = a.rows + (size_t)(blk & 1) * a.B * ROW_BYTES;
+            while (qissued < nfeas && qissued < qdone + ROW_RING) {
+              const unsigned s = (gq + (unsigned)(qissued - qdone)) % ROW_RING;
+              mbar_expect_tx(&S.bar[s], ROW_BYTES);
+              tma_load_1d(S.rows[s], gbase + (size_t)S.feas_list[qissued] * ROW_BYTES, ROW_BYTES, &S.bar[s]);
+              qissued++;
+            }
+          }
+          qissued = __shfl_sync(0xffffffffu, qissued, 0);
+          if (qdone >= nfeas) {  // block finished
+            end_block(a, S, blk, nD);
+            open = false;
+            blk++;
+            continue;
+          }
+          // group-constrained jobs are resolved one at a time against live state
+          if (CONSTR && S.jgrp[S.feas_list[qdone]]) {
+            const int ib = S.feas_list[qdone];
+            // its (unused) row slot still has to be consumed to keep the ring in phase
+            mbar_wait(&S.bar[gq % ROW_RING], (gq / ROW_RING) & 1u);
+            resolve_group_job<CONSTR>(a, blk, k0 + ib, ib, S, bitmap, nD, lstats);
+            qdone++; gq++;
+            continue;
+          }
+          n = 0;
+          while (n < SPEC_W && qdone + n < nfeas && !(CONSTR && S.jgrp[S.feas_list[qdone + n]])) n++;
+          break;
+        }
+        seq++;
+        if (lane == 0) {
+          S.r_mode = mode; S.r_n = n; S.r_q0 = qdone; S.r_seq = seq; S.r_blk = blk; S.r_k0 = k0;
+          S.r_nD = nD; S.r_gq0 = gq;
+        }
+        if (PROF) prof[0] += (unsigned long long)(clock64() - td0);
+      }
+      __syncthreads();  // (A) round header visible
+      if (S.r_mode == 1) break;
+      const int rn = S.r_n;
+      long long tr0 = PROF ? clock64() : 0;
+      if (warp < rn) {
+        const int rq0 = S.r_q0, rblk = S.r_blk, rseq = S.r_seq, rnD = S.r_nD;
+        const unsigned g = S.r_gq0 + (unsigned)warp;
+        const int ib = S.feas_list[rq0 + warp];
+        mbar_wait(&S.bar[g % ROW_RING], (g / ROW_RING) & 1u);
+        SpecResult sp;
+        JobRegs r;
+        spec_phase<CONSTR>(a, rblk, ib, S.rows[g % ROW_RING], S, bitmap, rnD, sp, r);
+        if (PROF && warp == 0) prof[1] += (unsigned long long)(clock64() - tr0);
+        chain_phase<CONSTR>(a, S, warp, rseq, r, sp);
+      }
+      long long tr1 = PROF ? clock64() : 0;
+      __syncthreads();  // (B) all commits of the round published
+      if (warp == 0) {
+        if (PROF) { prof[2] += (unsigned long long)(clock64() - tr1); prof[4]++; }
+        long long ta0 = PROF ? clock64() : 0;
+        const int n_done = apply_round(a, S, bitmap, nD, blk, k0, qdone, rn, lstats);
+        qdone += n_done;
+        gq += (unsigned)n_done;
+        if (PROF) { prof[3] += (unsigned long long)(clock64() - ta0); prof[5] += (unsigned long long)(rn - n_done); }
+      }
+    }
     if (threadIdx.x == 0) {
-      a.stats[0] = lstats[0]; a.stats[1] = lstats[1]; a.stats[2] = lstats[2]; a.stats[3] = lstats[3];
-      for (int i = 0; i < 10; i++) a.stats[4 + i] = prof[i];
-      a.stats[20] = prof[10]; a.stats[21] = prof[11]; a.stats[22] = prof[12];
+      a.stats[0] = lstats[0]; a.stats[1] = S.n_rescan; a.stats[2] = lstats[2]; a.stats[3] = lstats[3];
+      for (int i = 0; i < 6; i++) a.stats[4 + i] = prof[i];
+      a.stats[12] = (unsigned long long)(clock64() - t_start);
     }
   } else {
     EvalShared& E = *reinterpret_cast<EvalShared*>(smem_raw);
@@ -1431,12 +1694,10 @@ static int32_t run_plan(cook_pool* pool, MatchPlan* mp, int32_t* out_considerabl
   CK(pool, cudaEventRecord(pool->ev[4], st));
   CK(pool, cudaStreamSynchronize(st));
   if (prof_on) {
-    const char* nm[15] = {"compact", "row+cand", "dirty_eval", "rescan", "reduce+commit", "publish",
-                          "sum_nD", "n_shortcut", "res_total", "res_wait_rows", "eval_work", "eval_wait",
+    const char* nm[15] = {"driver", "spec_phase_w0", "chain_wait_w0", "apply", "rounds", "aborted_jobs",
+                          "-", "-", "res_total", "-", "eval_work", "eval_wait",
                           "eval_loop", "eval_sync", "eval_merge"};
     for (int i = 0; i < 15; i++) fprintf(stderr, "[cook_prof] %-14s %llu\n", nm[i], hstats[4 + i]);
-    fprintf(stderr, "[cook_prof] mbar_wait      %llu\n[cook_prof] lds+select     %llu\n[cook_prof] dirty_loop     %llu\n",
-            hstats[20], hstats[21], hstats[22]);
   }
   if (out_stats) {
     out_stats->n_considerable = n_cons;
