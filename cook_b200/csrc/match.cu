@@ -37,9 +37,7 @@
 
 namespace {
 
-constexpr int RES_THREADS = 256;   // threads per CTA of the match kernel
-constexpr int MAXB = 256;          // max jobs per block
-constexpr int MAXD = 2 * MAXB;     // dirty list capacity (two blocks)
+constexpr int RES_THREADS = 512;   // threads per CTA of the match kernel
 constexpr int TOPK = 8;            // candidates kept per (job, chunk)
 constexpr int ROW_V_OFF = TOPK * 32 * 8;             // byte offset of the v part of a row
 constexpr int ROW_BYTES = TOPK * 32 * (8 + 4);       // 3072 B per job
@@ -110,7 +108,9 @@ struct MatchArgs {
   const double* kc;        // gathered cpus per k
   const double* km;        // gathered mem per k
   const uint8_t* kflags;   // bit0: has groups
-  int B;                   // jobs per block
+  int B;                   // jobs per block at the start (blocks 0 and 1)
+  int bmin, bmax, btarget; // adaptive blocks: bounds and target placements per block
+  int32_t* bk0;            // [max blocks + 4] first job of block b (bk0[b+1] = end); resolver writes ahead
   int host_lifetime_mins;
   unsigned char* rows;     // [2][B][ROW_BYTES]: f[TOPK][32] f64 then v[TOPK][32] i32
   const double* kg;        // gathered gpus per k (constraint kernel)
@@ -121,7 +121,11 @@ struct MatchArgs {
   int32_t* assign;         // [n_cons] v (rank space) or -1
   int32_t* ports_start;    // [n_cons] ports_used of the VM before assignment
   uint8_t* fail;           // [n_cons]
-  unsigned long long* stats;  // [0]=fast [1]=chunk rescans [2]=full rescans [3]=matched [4]=offers used
+  unsigned long long* stats;  // [0]=fast [1]=chunk rescans [2]=group jobs [3]=matched [4]=fallbacks [5]=truncated specs [6]=skipped
+  int* latest_global;         // newest-log-entry table when it does not fit in shared memory
+  int isolate_commit;         // keep the warps that share the commit warp's scheduler idle
+  int lookahead;              // queue entries in flight (<= RING)
+  int poll_ns;                // back-off of the resolver's shared-memory polling loops
 };
 
 // ------------------------------------------------------------------ helpers
@@ -367,7 +371,7 @@ __device__ __forceinline__ void merge_list(double* f, int* vv, const EvalShared&
 }
 
 template <bool CONSTR, bool PROF>
-__device__ void evaluate_row(const MatchArgs& a, int k, int blk, EvalShared& E, unsigned long long* ep) {
+__device__ void evaluate_row(const MatchArgs& a, int k, int blk, int ib, EvalShared& E, unsigned long long* ep) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   long long e0 = PROF ? clock64() : 0;
   const double2* st2 = reinterpret_cast<const double2*>(a.of.vs);
@@ -415,7 +419,7 @@ __device__ void evaluate_row(const MatchArgs& a, int k, int blk, EvalShared& E, 
   }
   long long e2 = PROF ? clock64() : 0;
   if (warp == 0) {
-    unsigned char* row = a.rows + ((size_t)(blk & 1) * a.B + (k - blk * a.B)) * ROW_BYTES;
+    unsigned char* row = a.rows + ((size_t)(blk & 1) * a.bmax + ib) * ROW_BYTES;
     if (any || grp) {
       double* rf = reinterpret_cast<double*>(row);
       int32_t* rv = reinterpret_cast<int32_t*>(row + ROW_V_OFF);
@@ -426,7 +430,7 @@ __device__ void evaluate_row(const MatchArgs& a, int k, int blk, EvalShared& E, 
       }
     }
     if (lane == 0) {
-      __stcg(a.feas + (size_t)(blk & 1) * a.B + (k - blk * a.B), (uint8_t)((any || grp) ? 1 : 0));
+      __stcg(a.feas + (size_t)(blk & 1) * a.bmax + ib, (uint8_t)((any || grp) ? 1 : 0));
       __threadfence();
       atomicAdd(a.rows_ready + blk, 1u);
     }
@@ -439,56 +443,89 @@ __device__ void evaluate_row(const MatchArgs& a, int k, int blk, EvalShared& E, 
 }
 
 // --------------------------------------------------------------- resolver
-// CTA 0.  Jobs are resolved in ROUNDS of up to SPEC_W consecutive feasible jobs:
-//   P  (parallel, one warp per job): exact best and runner-up VM of the job
-//      against the ROUND-START state = clean chunk candidates from its row +
-//      exact re-evaluation of all dirty VMs (+ rare chunk re-scans).
-//   C  (chain): job i consumes the commits of jobs 0..i-1 of the round in order;
-//      a commit changes ONE VM, so job i re-evaluates just that VM and updates
-//      its (best, runner-up) pair; when commit i-1 is in, its best is exact and
-//      it publishes its own commit.  If a job loses its best and does not know
-//      its exact runner-up any more it aborts: the round is truncated there and
-//      the job restarts the next round (where it has no predecessors).
-//   A  (warp 0): commits are applied to the dirty list, outputs written.
-constexpr int SPEC_W = RES_THREADS / 32;
-constexpr int ROW_RING = 2 * SPEC_W;
+// CTA 0 resolves the jobs in rank order, exactly, as a three-role pipeline:
+//
+//   driver (warp 1)   turns the evaluators' per-block feasibility flags into an
+//                     in-order QUEUE of entries (JOB / END-of-block / EXIT); at
+//                     most RING entries are in flight.
+//   spec (warps 2..)  each takes the next queue ticket and computes, against the
+//                     state at some VERSION s (= number of commits it saw), the
+//                     job's sorted top-KC candidate VMs with their states:
+//                     clean chunk candidates from the job's row merged with an
+//                     exact re-evaluation of every VM committed since the row's
+//                     snapshot (the commit LOG, an append-only ring).
+//   commit (warp 0)   consumes results in queue order.  For job i with version
+//                     s_i and c commits so far, the VMs changed since s_i are
+//                     exactly log[s_i, c) (<= RING-1 < 32 entries): one lane
+//                     re-evaluates each; the first candidate of the list that is
+//                     unchanged is the exact best among all unchanged VMs; argmax
+//                     of the two is Fenzo's choice.  It appends the placement to
+//                     the log.  If every listed candidate changed (and the list
+//                     is not complete) the commit warp recomputes the job at
+//                     version c itself (exact, rare).
+//
+// Validity of a log entry e for VM x is `latest[x] == e` (latest[] = index of
+// the newest entry per VM, monotone), so nothing is ever cleared: a VM is dirty
+// with respect to a block's snapshot iff latest[x] >= lo, lo = log size at the
+// start of the previous block.
+constexpr int MAXB = 512;             // max jobs per block
+constexpr int LOGN = 2 * MAXB;        // commit-log ring (entries of two blocks)
+constexpr int RING = 32;              // queue entries / spec results in flight
+constexpr int KC = 16;                // candidates per spec result
+constexpr int LK = 8;                 // entries a lane keeps while building a result
+constexpr int NWARPS = RES_THREADS / 32;
 
-struct VmRec {  // state of one VM as seen by the resolver
-  double ac, am, lc, lm, rc, rm;
-  int an, pu, slot, pad;  // slot: index in the dirty list, -1 if clean at round start
+enum { Q_JOB = 0, Q_END = 1, Q_EXIT = 2 };
+
+// newest log entry per VM: in shared memory when it fits (the usual case), else global
+struct Latest {
+  int* s;  // shared (derived from the dynamic shared base so loads/stores stay LDS/STS)
+  int* g;  // global fallback
+  __device__ __forceinline__ int get(int v) const { return g ? g[v] : s[v]; }
+  __device__ __forceinline__ void set(int v, int e) const { if (g) g[v] = e; else s[v] = e; }
 };
 
-struct CommitRec {
-  VmRec st;      // state AFTER this job's placement
-  int vm;        // -1: job not placed
-  int aborted;
-  int pu_before;
-  int pad;
+__device__ __forceinline__ void fence_cta() { asm volatile("fence.acq_rel.cta;" ::: "memory"); }
+// Readers of the resolver's shared flags: shared-memory loads of one warp complete in
+// program order, so polling needs no hardware fence - only the compiler must not move
+// the data loads above the (volatile) flag load.
+__device__ __forceinline__ void compiler_barrier() { asm volatile("" ::: "memory"); }
+
+struct QEntry {
+  int type, blk, k, lo;
+  double jc, jm, jg;
+  int jports, jj, grp, row;   // row: index of the job inside its block
+};
+
+struct Cand {  // one candidate VM with its state at the result's version
+  double f, ac, am, lc, lm, rc, rm;
+  int vm, e, an, pu;
+};
+
+struct SpecOut {
+  int type, s, n, complete;  // type: Q_JOB / Q_END / Q_EXIT (the commit warp waits on the result flag only)
+  Cand c[KC];
 };
 
 struct ResolverShared {
-  // dirty list (VMs touched since the snapshot), SoA so lane d reads entry d
-  double d_ac[MAXD], d_am[MAXD];
-  double d_lc[MAXD], d_lm[MAXD], d_rc[MAXD], d_rm[MAXD];
-  int32_t d_vm[MAXD], d_an[MAXD], d_pu[MAXD], d_touch[MAXD];
-  // per-block job requests
-  double jc[MAXB], jm[MAXB], jg[MAXB];
-  int32_t jports[MAXB], jj[MAXB];
-  uint8_t jgrp[MAXB];
-  int16_t feas_list[MAXB];
-  // TMA-staged rows of the next feasible jobs
-  __align__(128) unsigned char rows[ROW_RING][ROW_BYTES];
-  unsigned long long bar[ROW_RING];
-  CommitRec commits[SPEC_W];
-  volatile int commit_flag[SPEC_W];
-  // round header (written by warp 0 between the two CTA barriers)
-  volatile int r_mode;   // 0 = speculative round, 1 = exit
-  volatile int r_n;      // jobs in the round
-  volatile int r_q0;     // index of the round's first job in feas_list
-  volatile int r_seq;    // round sequence number (commit_flag target)
-  volatile int r_blk, r_k0, r_nD;
-  volatile unsigned r_gq0;  // global feasible-job counter of the round's first job (row ring position)
-  unsigned long long n_rescan;
+  // commit log, SoA
+  int32_t l_vm[LOGN];
+  double l_ac[LOGN], l_am[LOGN], l_lc[LOGN], l_lm[LOGN], l_rc[LOGN], l_rm[LOGN];
+  int32_t l_an[LOGN], l_pu[LOGN];
+  int32_t l_k[LOGN], l_pu0[LOGN];   // considerable index of the placed job, ports used before it
+  QEntry q[RING];
+  SpecOut res[RING + 1];          // [RING] = the commit warp's own fallback slot
+  volatile int q_seq[RING];       // g+1 once queue entry g is filled
+  volatile int res_seq[RING];     // g+1 once the result of entry g is ready
+  volatile int ncommit;           // log entries written
+  volatile int gdone;             // queue entries consumed by the commit warp
+  volatile int exit_g;            // queue index of the EXIT entry (-1 while running)
+  int ticket;                     // next queue entry for the spec warps
+  volatile int lo_ring[4];        // lo_ring[b & 3] = log size at the start of block b
+  volatile int bk_ring[8];        // bk_ring[b & 7] = first job of block b
+  volatile int bk_known;          // blocks 0..bk_known have their first job recorded
+  volatile int out_done, blk_c0, last_b;  // END bookkeeping shared by the commit warps
+  unsigned long long n_rescan, n_trunc;
 };
 
 __device__ __forceinline__ double warp_max_f64(double f) {  // f >= 0
@@ -499,546 +536,611 @@ __device__ __forceinline__ double warp_max_f64(double f) {  // f >= 0
   return __hiloint2double((int)mh, (int)ml);
 }
 
-// argmax over lanes of (f desc, v asc).  Returns winner fitness; wv/wl = VM and lane.
-__device__ __forceinline__ double warp_argmax(double f, int v, int& wv, int& wl) {
+// argmax over lanes of (f desc, key asc); key < 0xffffffff.  Returns the winning
+// fitness (0 => nobody), wk = its key, wl = its lane.
+__device__ __forceinline__ double warp_argmax(double f, unsigned key, unsigned& wk, int& wl) {
   const double wf = warp_max_f64(f);
-  unsigned key = (f == wf && wf > 0.0) ? (unsigned)v : 0xffffffffu;
-  unsigned mv = __reduce_min_sync(0xffffffffu, key);
-  wv = (int)mv;
-  wl = __ffs(__ballot_sync(0xffffffffu, key == mv)) - 1;
+  const unsigned k2 = (f == wf && wf > 0.0) ? key : 0xffffffffu;
+  wk = __reduce_min_sync(0xffffffffu, k2);
+  wl = __ffs(__ballot_sync(0xffffffffu, k2 == wk)) - 1;
   return wf;
 }
 
-struct Top2 {  // a lane's two best candidates (distinct VMs)
-  double f1, f2;
-  int v1, v2, s1, s2;
-  __device__ __forceinline__ void init() { f1 = f2 = 0.0; v1 = v2 = 0x7fffffff; s1 = s2 = -1; }
-  __device__ __forceinline__ void ins(double f, int v, int s) {
-    if (!(f > 0.0)) return;
-    if (better(f, v, f1, v1)) { f2 = f1; v2 = v1; s2 = s1; f1 = f; v1 = v; s1 = s; }
-    else if (better(f, v, f2, v2)) { f2 = f; v2 = v; s2 = s; }
+// A lane's working set during a spec: a sorted list of candidates plus two
+// "sentinels" that bound everything the lane is responsible for but does not
+// list: cb = the row's last entry (the rest of the lane's chunk is strictly
+// worse), db = the best entry ever dropped from the list.
+struct LaneList {
+  double f[LK];
+  int v[LK], e[LK];
+  double cbf, dbf;
+  int cbv, dbv;
+  __device__ __forceinline__ void init() {
+#pragma unroll
+    for (int i = 0; i < LK; i++) { f[i] = 0.0; v[i] = 0x7fffffff; e[i] = -1; }
+    cbf = dbf = 0.0; cbv = dbv = 0x7fffffff;
+  }
+  // x is better than every listed entry (row entries are pushed worst first)
+  __device__ __forceinline__ void push_front(double x, int xv, int xe) {
+#pragma unroll
+    for (int i = LK - 1; i > 0; i--) { f[i] = f[i - 1]; v[i] = v[i - 1]; e[i] = e[i - 1]; }
+    f[0] = x; v[0] = xv; e[0] = xe;
+  }
+  __device__ __forceinline__ void insert(double x, int xv, int xe) {
+    if (!(x > 0.0)) return;
+    if (!better(x, xv, f[LK - 1], v[LK - 1])) {  // not listed => dropped
+      if (better(x, xv, dbf, dbv)) { dbf = x; dbv = xv; }
+      return;
+    }
+    if (f[LK - 1] > 0.0 && better(f[LK - 1], v[LK - 1], dbf, dbv)) { dbf = f[LK - 1]; dbv = v[LK - 1]; }
+    f[LK - 1] = x; v[LK - 1] = xv; e[LK - 1] = xe;
+#pragma unroll
+    for (int i = LK - 1; i > 0; i--) {
+      if (better(f[i], v[i], f[i - 1], v[i - 1])) {
+        double tf = f[i]; f[i] = f[i - 1]; f[i - 1] = tf;
+        int tv = v[i]; v[i] = v[i - 1]; v[i - 1] = tv;
+        int te = e[i]; e[i] = e[i - 1]; e[i - 1] = te;
+      }
+    }
+  }
+  __device__ __forceinline__ void pop() {
+#pragma unroll
+    for (int i = 0; i < LK - 1; i++) { f[i] = f[i + 1]; v[i] = v[i + 1]; e[i] = e[i + 1]; }
+    f[LK - 1] = 0.0; v[LK - 1] = 0x7fffffff; e[LK - 1] = -1;
   }
 };
 
-__device__ __forceinline__ VmRec load_rec(const MatchArgs& a, const ResolverShared& S, const VmDyn* snapd,
-                                          int v, int slot, bool constr) {
-  VmRec r;
-  r.slot = slot; r.pad = 0;
-  if (slot >= 0) {
-    r.ac = S.d_ac[slot]; r.am = S.d_am[slot]; r.lc = S.d_lc[slot]; r.lm = S.d_lm[slot];
-    r.rc = S.d_rc[slot]; r.rm = S.d_rm[slot]; r.an = S.d_an[slot]; r.pu = S.d_pu[slot];
-  } else {
-    const double2* st2 = reinterpret_cast<const double2*>(a.of.vs + v);
-    const double2 s0 = __ldg(st2), s1 = __ldg(st2 + 1);
-    const double2 d0 = __ldcg(reinterpret_cast<const double2*>(snapd + v));
-    int2 d1 = make_int2(0, 0);
-    if (constr) d1 = __ldcg(reinterpret_cast<const int2*>(snapd + v) + 2);
-    r.ac = d0.x; r.am = d0.y; r.an = d1.x; r.pu = d1.y;
-    r.lc = s0.x; r.lm = s0.y; r.rc = s1.x; r.rm = s1.y;
-  }
-  return r;
+template <bool CONSTR>
+__device__ __forceinline__ double eval_log(const MatchArgs& a, const JobRegs& r, const ResolverShared& S,
+                                           int idx, int vm) {
+  return eval_vm<CONSTR>(a, r, vm, S.l_ac[idx], S.l_am[idx], S.l_an[idx], S.l_pu[idx], S.l_lc[idx],
+                         S.l_lm[idx], S.l_rc[idx], S.l_rm[idx], false);
 }
 
-struct SpecResult {
-  double bf, sf;
-  int bv, sv;          // -1: none
-  VmRec brec, srec;
-};
-
-// P phase for one job: exact best + runner-up against the round-start state.
+// Sorted top-`depth` candidates of one job against the state at version s
+// (warp-wide).  Sentinel hits in the first `exact_rounds` rounds are resolved by
+// an exact chunk re-scan; later ones truncate the list (complete = 0).
 template <bool CONSTR>
-__device__ void spec_phase(const MatchArgs& a, int blk, int ib, const unsigned char* rowp,
-                           ResolverShared& S, const unsigned* bitmap, int nD, SpecResult& out,
-                           JobRegs& r) {
+__device__ __forceinline__ void spec_job(const MatchArgs& a, ResolverShared& S, const Latest latest, const QEntry& qe,
+                                         const int s, const int depth, const int exact_rounds, SpecOut& out) {
   const int lane = threadIdx.x & 31;
+  JobRegs r;
+  r.c = qe.jc; r.m = qe.jm; r.g = qe.jg; r.ports = qe.jports; r.j = qe.jj;
+  const int lo = qe.lo, blk = qe.blk;
   const VmDyn* snapd = a.dyn.d[blk & 1];
-  r.c = S.jc[ib]; r.m = S.jm[ib]; r.g = CONSTR ? S.jg[ib] : 0.0;
-  r.ports = CONSTR ? S.jports[ib] : 0; r.j = S.jj[ib];
-  Top2 t;
-  t.init();
-  double bound = 0.0;
+  const unsigned char* rowp = a.rows + ((size_t)(blk & 1) * a.bmax + qe.row) * ROW_BYTES;
+  LaneList L;
+  L.init();
   {
     const double* rf = reinterpret_cast<const double*>(rowp);
     const int32_t* rv = reinterpret_cast<const int32_t*>(rowp + ROW_V_OFF);
     double f[TOPK];
     int v[TOPK];
 #pragma unroll
-    for (int i = 0; i < TOPK; i++) { f[i] = rf[i * 32 + lane]; v[i] = rv[i * 32 + lane]; }
-    unsigned dirty_bits = 0u, live_bits = 0u;
+    for (int i = 0; i < TOPK; i++) { f[i] = __ldcg(rf + i * 32 + lane); v[i] = __ldcg(rv + i * 32 + lane); }
+    if (f[TOPK - 1] > 0.0) { L.cbf = f[TOPK - 1]; L.cbv = v[TOPK - 1]; }  // full list: the rest is worse
+    static_assert(LK >= TOPK, "a lane's list must hold its whole row chunk");
 #pragma unroll
-    for (int i = 0; i < TOPK; i++) {
+    for (int i = TOPK - 1; i >= 0; i--) {  // worst first: every push lands in front
       const bool live = f[i] > 0.0;
       const int vi = live ? v[i] : 0;
-      const unsigned w = bitmap[vi >> 5];
-      live_bits |= (live ? 1u : 0u) << i;
-      dirty_bits |= (((w >> (vi & 31)) & 1u) & (live ? 1u : 0u)) << i;
+      if (live && latest.get(vi) < lo) L.push_front(f[i], vi, -1);
     }
-    unsigned clean = live_bits & ~dirty_bits;  // sorted list: live_bits is a prefix mask
-    int nclean = 0;
-#pragma unroll
-    for (int pick = 0; pick < 2; pick++) {
-      if (clean) {
-        const int i = __ffs(clean) - 1;
-        clean &= clean - 1;
-#pragma unroll
-        for (int q = 0; q < TOPK; q++)
-          if (q == i) t.ins(f[q], v[q], -1);
-        nclean++;
-      }
-    }
-    // fewer than two clean entries out of a FULL list: the rest of the chunk is
-    // only known to be <= the last entry
-    if (nclean < 2 && live_bits == ((1u << TOPK) - 1u)) bound = f[TOPK - 1];
   }
-  // exact re-evaluation of dirty VMs against their round-start state
-  for (int d = lane; d < nD; d += 32) {
-    double f = eval_vm<CONSTR>(a, r, S.d_vm[d], S.d_ac[d], S.d_am[d], S.d_an[d], S.d_pu[d],
-                               S.d_lc[d], S.d_lm[d], S.d_rc[d], S.d_rm[d], false);
-    t.ins(f, S.d_vm[d], d);
+  // every VM committed since the snapshot, at its state as of version s
+  for (int e = lo + lane; e < s; e += 32) {
+    const int idx = e & (LOGN - 1);
+    const int vm = S.l_vm[idx];
+    if (latest.get(vm) == e) L.insert(eval_log<CONSTR>(a, r, S, idx, vm), vm, e);
   }
-  int bv, bl, sv, sl;
-  double bf = warp_argmax(t.f1, t.v1, bv, bl);
-  // runner-up: the winner lane offers its second candidate instead
-  double sf = warp_argmax(lane == bl ? t.f2 : t.f1, lane == bl ? t.v2 : t.v1, sv, sl);
-  const double mb = warp_max_f64(bound);
-  if (mb > 0.0 && mb >= sf) {
-    // rare: a chunk whose listed candidates are (almost) all dirty could still
-    // hold the best or the runner-up => exact re-scan of those chunks
-    unsigned need = __ballot_sync(0xffffffffu, bound > 0.0 && bound >= sf);
-    const double2* st2 = reinterpret_cast<const double2*>(a.of.vs);
-    const double2* dy2 = reinterpret_cast<const double2*>(snapd);
-    while (need) {
-      const int c = __ffs(need) - 1;
-      need &= need - 1;
-      for (int v = c + 32 * lane; v < a.of.O; v += 32 * 32) {
-        if ((bitmap[v >> 5] >> (v & 31)) & 1u) continue;
-        if (v == t.v1 || v == t.v2) continue;  // already a candidate of this lane
-        const double2 s0 = st2[2 * v], s1 = st2[2 * v + 1];
+  int n = 0, complete = 0;
+  double cf = 0.0;
+  int cv = 0, ce = -1;  // lane q keeps candidate q
+  for (int round = 0; round < depth;) {
+    // a lane exposes its head unless one of its sentinels is strictly better
+    double hf = L.f[0];
+    int hv = L.v[0];
+    bool sent = false, is_cb = false;
+    if (L.cbf > 0.0 && better(L.cbf, L.cbv, hf, hv)) { hf = L.cbf; hv = L.cbv; sent = true; is_cb = true; }
+    if (L.dbf > 0.0 && better(L.dbf, L.dbv, hf, hv)) { hf = L.dbf; hv = L.dbv; sent = true; is_cb = false; }
+    // key: sentinels win ties against real candidates of the same (f, v)
+    const unsigned key = ((unsigned)hv << 1) | (sent ? 0u : 1u);
+    unsigned wk;
+    int wl;
+    const double wf = warp_argmax(hf, key, wk, wl);
+    if (!(wf > 0.0)) { complete = 1; break; }
+    if ((wk & 1u) == 0u) {  // a sentinel wins
+      const bool wcb = __shfl_sync(0xffffffffu, is_cb ? 1 : 0, wl) != 0;
+      if (!wcb || round >= exact_rounds) { if (lane == 0) atomicAdd(&S.n_trunc, 1ull); break; }
+      // exact re-scan of chunk wl: clean VMs strictly worse than its row's last entry
+      const double bf = __shfl_sync(0xffffffffu, L.cbf, wl);
+      const int bv = __shfl_sync(0xffffffffu, L.cbv, wl);
+      if (lane == wl) { L.cbf = 0.0; L.cbv = 0x7fffffff; }
+      const double2* st2 = reinterpret_cast<const double2*>(a.of.vs);
+      const double2* dy2 = reinterpret_cast<const double2*>(snapd);
+      for (int v = wl + 32 * lane; v < a.of.O; v += 32 * 32) {
+        if (latest.get(v) >= lo) continue;
+        const double2 s0 = __ldg(st2 + 2 * v), s1 = __ldg(st2 + 2 * v + 1);
         const double2 d0 = __ldcg(dy2 + 2 * v);
         int2 d1 = make_int2(0, 0);
         if (CONSTR) d1 = __ldcg(reinterpret_cast<const int2*>(dy2 + 2 * v + 1));
-        t.ins(eval_vm<CONSTR>(a, r, v, d0.x, d0.y, d1.x, d1.y, s0.x, s0.y, s1.x, s1.y, false), v, -1);
+        const double x = eval_vm<CONSTR>(a, r, v, d0.x, d0.y, d1.x, d1.y, s0.x, s0.y, s1.x, s1.y, false);
+        if (x > 0.0 && better(bf, bv, x, v)) L.insert(x, v, -1);
       }
-      if (lane == 0) S.n_rescan++;
+      if (lane == 0) atomicAdd(&S.n_rescan, 1ull);
+      continue;  // same round again
     }
-    // a re-scanned VM may also sit in another lane's list (lane c's own clean
-    // entries): duplicates are harmless for the max, but the runner-up must be a
-    // DIFFERENT VM than the winner, so mask the winner VM explicitly.
-    bf = warp_argmax(t.f1, t.v1, bv, bl);
-    const bool a1 = t.v1 != bv;
-    sf = warp_argmax(a1 ? t.f1 : t.f2, a1 ? t.v1 : t.v2, sv, sl);
+    const double xf = __shfl_sync(0xffffffffu, L.f[0], wl);
+    const int xv = __shfl_sync(0xffffffffu, L.v[0], wl);
+    const int xe = __shfl_sync(0xffffffffu, L.e[0], wl);
+    if (lane == n) { cf = xf; cv = xv; ce = xe; }
+    if (lane == wl) L.pop();
+    n++;
+    round++;
   }
-  out.bf = bf; out.sf = sf;
-  out.bv = bf > 0.0 ? bv : -1;
-  out.sv = sf > 0.0 ? sv : -1;
-  if (out.bv >= 0) {
-    const int slot = __shfl_sync(0xffffffffu, t.s1, bl);
-    out.brec = load_rec(a, S, snapd, out.bv, slot, CONSTR);
-  }
-  if (out.sv >= 0) {
-    int slot = __shfl_sync(0xffffffffu, (t.v1 == out.sv) ? t.s1 : t.s2, sl);
-    out.srec = load_rec(a, S, snapd, out.sv, slot, CONSTR);
-  }
-}
-
-// C phase: consume predecessors' commits in order, then publish own commit.
-template <bool CONSTR>
-__device__ void chain_phase(const MatchArgs& a, ResolverShared& S, int wi, int seq, const JobRegs& r,
-                            SpecResult& sp) {
-  const int lane = threadIdx.x & 31;
-  bool second_known = true;
-  bool aborted = false;
-  for (int j = 0; j < wi && !aborted; j++) {
-    while (S.commit_flag[j] != seq) __nanosleep(20);
-    __threadfence_block();
-    const CommitRec& c = S.commits[j];
-    if (c.aborted) { aborted = true; break; }
-    const int x = c.vm;
-    if (x < 0) continue;
-    const VmRec st = c.st;
-    const double f = eval_vm<CONSTR>(a, r, x, st.ac, st.am, st.an, st.pu, st.lc, st.lm, st.rc, st.rm, false);
-    if (x == sp.bv) {
-      if (f > 0.0) { sp.bf = f; sp.brec = st; }  // fuller => fitness grew, still the best
-      else if (second_known) {                    // my best no longer fits
-        sp.bf = sp.sf; sp.bv = sp.sv; sp.brec = sp.srec;
-        sp.sf = 0.0; sp.sv = -1;
-        second_known = sp.bv < 0;  // nothing left at all => trivially known
-      } else aborted = true;
-    } else if (x == sp.sv) {
-      if (f > 0.0) {
-        sp.sf = f; sp.srec = st;
-        if (better(sp.sf, sp.sv, sp.bf, sp.bv)) {
-          double tf = sp.bf; sp.bf = sp.sf; sp.sf = tf;
-          int tv = sp.bv; sp.bv = sp.sv; sp.sv = tv;
-          VmRec tr = sp.brec; sp.brec = sp.srec; sp.srec = tr;
-        }
-      } else { sp.sf = 0.0; sp.sv = -1; second_known = false; }
-    } else if (f > 0.0) {
-      if (sp.bv < 0 || better(f, x, sp.bf, sp.bv)) {
-        if (sp.bv >= 0) { sp.sf = sp.bf; sp.sv = sp.bv; sp.srec = sp.brec; second_known = true; }
-        sp.bf = f; sp.bv = x; sp.brec = st;
-      } else if (second_known && (sp.sv < 0 || better(f, x, sp.sf, sp.sv))) {
-        sp.sf = f; sp.sv = x; sp.srec = st;
-      }
+  if (lane < n) {
+    Cand& c = out.c[lane];
+    c.f = cf; c.vm = cv; c.e = ce;
+    if (ce >= 0) {
+      const int idx = ce & (LOGN - 1);
+      c.ac = S.l_ac[idx]; c.am = S.l_am[idx]; c.lc = S.l_lc[idx]; c.lm = S.l_lm[idx];
+      c.rc = S.l_rc[idx]; c.rm = S.l_rm[idx]; c.an = S.l_an[idx]; c.pu = S.l_pu[idx];
+    } else {
+      const double2* st2 = reinterpret_cast<const double2*>(a.of.vs + cv);
+      const double2 s0 = __ldg(st2), s1 = __ldg(st2 + 1);
+      const double2 d0 = __ldcg(reinterpret_cast<const double2*>(snapd + cv));
+      int2 d1 = make_int2(0, 0);
+      if (CONSTR) d1 = __ldcg(reinterpret_cast<const int2*>(snapd + cv) + 2);
+      c.ac = d0.x; c.am = d0.y; c.an = d1.x; c.pu = d1.y;
+      c.lc = s0.x; c.lm = s0.y; c.rc = s1.x; c.rm = s1.y;
     }
   }
-  if (lane == 0) {
-    CommitRec& m = S.commits[wi];
-    m.aborted = aborted ? 1 : 0;
-    m.vm = -1;
-    m.pu_before = 0;
-    if (!aborted && sp.bv >= 0 && sp.bf > 0.0) {
-      VmRec st = sp.brec;
-      m.pu_before = st.pu;
-      st.ac = st.ac + r.c;
-      st.am = st.am + r.m;
-      st.an += 1;
-      st.pu += r.ports;
-      m.st = st;
-      m.vm = sp.bv;
-    }
-    __threadfence_block();
-    S.commit_flag[wi] = seq;
-  }
+  if (lane == 0) { out.type = Q_JOB; out.s = s; out.n = n; out.complete = complete; }
   __syncwarp();
 }
 
-// Single-warp exact resolution of one job against live state (group jobs).
+// Exact placement of a group-constrained job against the live state (commit warp).
+// Returns the winning VM (or -1); the winner's pre-placement state lands in `w`.
 template <bool CONSTR>
-__device__ void resolve_group_job(const MatchArgs& a, int blk, int k, int ib, ResolverShared& S,
-                                  unsigned* bitmap, int& nD, unsigned long long* lstats) {
+__device__ __noinline__ int resolve_group_job(const MatchArgs& a, ResolverShared& S, const Latest latest,
+                                 const QEntry& qe, Cand& w) {
   const int lane = threadIdx.x & 31;
-  const VmDyn* snapd = a.dyn.d[blk & 1];
   JobRegs r;
-  r.c = S.jc[ib]; r.m = S.jm[ib]; r.g = CONSTR ? S.jg[ib] : 0.0;
-  r.ports = CONSTR ? S.jports[ib] : 0; r.j = S.jj[ib];
-  double cf = 0.0;
-  int cv = 0x7fffffff, cslot = -1;
-  for (int d = lane; d < nD; d += 32) {
-    double f = eval_vm<CONSTR>(a, r, S.d_vm[d], S.d_ac[d], S.d_am[d], S.d_an[d], S.d_pu[d],
-                               S.d_lc[d], S.d_lm[d], S.d_rc[d], S.d_rm[d], true);
-    int v = S.d_vm[d];
-    if (f > cf || (f == cf && f > 0.0 && v < cv)) { cf = f; cv = v; cslot = d; }
-  }
+  r.c = qe.jc; r.m = qe.jm; r.g = qe.jg; r.ports = qe.jports; r.j = qe.jj;
+  const VmDyn* snapd = a.dyn.d[qe.blk & 1];
   const double2* st2 = reinterpret_cast<const double2*>(a.of.vs);
   const double2* dy2 = reinterpret_cast<const double2*>(snapd);
+  double cf = 0.0;
+  int cv = 0x7fffffff, ce = -1;
   for (int v = lane; v < a.of.O; v += 32) {
-    if ((bitmap[v >> 5] >> (v & 31)) & 1u) continue;
-    const double2 s0 = st2[2 * v], s1 = st2[2 * v + 1];
-    const double2 d0 = __ldcg(dy2 + 2 * v);
-    int2 d1 = make_int2(0, 0);
-    if (CONSTR) d1 = __ldcg(reinterpret_cast<const int2*>(dy2 + 2 * v + 1));
-    double f = eval_vm<CONSTR>(a, r, v, d0.x, d0.y, d1.x, d1.y, s0.x, s0.y, s1.x, s1.y, true);
-    if (f > cf || (f == cf && f > 0.0 && v < cv)) { cf = f; cv = v; cslot = -1; }
+    const int e = latest.get(v);
+    double f;
+    if (e >= qe.lo) {
+      const int idx = e & (LOGN - 1);
+      f = eval_vm<CONSTR>(a, r, v, S.l_ac[idx], S.l_am[idx], S.l_an[idx], S.l_pu[idx], S.l_lc[idx],
+                          S.l_lm[idx], S.l_rc[idx], S.l_rm[idx], true);
+    } else {
+      const double2 s0 = __ldg(st2 + 2 * v), s1 = __ldg(st2 + 2 * v + 1);
+      const double2 d0 = __ldcg(dy2 + 2 * v);
+      int2 d1 = make_int2(0, 0);
+      if (CONSTR) d1 = __ldcg(reinterpret_cast<const int2*>(dy2 + 2 * v + 1));
+      f = eval_vm<CONSTR>(a, r, v, d0.x, d0.y, d1.x, d1.y, s0.x, s0.y, s1.x, s1.y, true);
+    }
+    if (f > cf) { cf = f; cv = v; ce = e >= qe.lo ? e : -1; }  // v ascends per lane: strict > keeps the lowest
   }
-  lstats[2]++;
-  int wv, wl;
-  const double wf = warp_argmax(cf, cv, wv, wl);
-  if (wf > 0.0) {
-    int slot = __shfl_sync(0xffffffffu, cslot, wl);
-    if (slot < 0) {
-      slot = nD;
-      if (lane == 0) {
-        const VmRec rec = load_rec(a, S, snapd, wv, -1, CONSTR);
-        S.d_vm[slot] = wv;
-        S.d_ac[slot] = rec.ac; S.d_am[slot] = rec.am; S.d_an[slot] = rec.an; S.d_pu[slot] = rec.pu;
-        S.d_lc[slot] = rec.lc; S.d_lm[slot] = rec.lm; S.d_rc[slot] = rec.rc; S.d_rm[slot] = rec.rm;
-        bitmap[wv >> 5] |= 1u << (wv & 31);
+  unsigned wk;
+  int wl;
+  const double wf = warp_argmax(cf, (unsigned)cv, wk, wl);
+  if (!(wf > 0.0)) return -1;
+  const int wv = (int)wk;
+  const int we = __shfl_sync(0xffffffffu, ce, wl);
+  w.f = wf; w.vm = wv; w.e = we;
+  if (we >= 0) {
+    const int idx = we & (LOGN - 1);
+    w.ac = S.l_ac[idx]; w.am = S.l_am[idx]; w.lc = S.l_lc[idx]; w.lm = S.l_lm[idx];
+    w.rc = S.l_rc[idx]; w.rm = S.l_rm[idx]; w.an = S.l_an[idx]; w.pu = S.l_pu[idx];
+  } else {
+    const double2 s0 = __ldg(st2 + 2 * wv), s1 = __ldg(st2 + 2 * wv + 1);
+    const double2 d0 = __ldcg(dy2 + 2 * wv);
+    int2 d1 = make_int2(0, 0);
+    if (CONSTR) d1 = __ldcg(reinterpret_cast<const int2*>(dy2 + 2 * wv + 1));
+    w.ac = d0.x; w.am = d0.y; w.an = d1.x; w.pu = d1.y;
+    w.lc = s0.x; w.lm = s0.y; w.rc = s1.x; w.rm = s1.y;
+  }
+  return wv;
+}
+
+// the commit warp's rare exact recomputation, kept out of its hot loop
+template <bool CONSTR>
+__device__ __noinline__ void spec_job_fallback(const MatchArgs& a, ResolverShared& S, const Latest latest,
+                                               const QEntry& qe, const int s) {
+  spec_job<CONSTR>(a, S, latest, qe, s, 1, 1, S.res[RING]);
+}
+
+// ---- driver warp: feasibility flags -> in-order queue
+template <bool CONSTR>
+__device__ void driver_warp(const MatchArgs& a, ResolverShared& S) {
+  const int lane = threadIdx.x & 31;
+  int g = 0;
+  unsigned long long skipped = 0;
+  auto wait_slot = [&](int gi) {  // slot of gi is free once entry gi - RING is consumed
+    while (S.gdone <= gi - a.lookahead) __nanosleep(a.poll_ns);
+  };
+  for (int b = 0;; b++) {
+    while (S.bk_known < b + 1) __nanosleep(20);  // block b's bounds are set two block ends ahead
+    const int k0 = S.bk_ring[b & 7];
+    if (k0 >= a.n_cons) break;
+    const int nj = min(S.bk_ring[(b + 1) & 7], a.n_cons) - k0;
+    if (lane == 0)
+      while (ld_acquire_u32(a.rows_ready + b) < (unsigned)nj) __nanosleep(20);
+    __syncwarp();
+    // rows b ready => END(b-2) was processed => the start of block b-1 is recorded
+    const int lo = b == 0 ? 0 : S.lo_ring[(b - 1) & 3];
+    const uint8_t* feas = a.feas + (size_t)(b & 1) * a.bmax;
+    for (int base = 0; base < nj; base += 32) {
+      const int i = base + lane;
+      const bool valid = i < nj;
+      const bool fz = valid && __ldcg(feas + i) != 0;
+      // jobs with no feasible VM at the snapshot are unplaceable now too (resources
+      // and count constraints only tighten within a cycle): skip them wholesale.
+      if (valid && !fz) { a.assign[k0 + i] = -1; a.fail[k0 + i] = COOK_FAIL_RESOURCES; }
+      const unsigned mask = __ballot_sync(0xffffffffu, fz);
+      skipped += __popc(__ballot_sync(0xffffffffu, valid && !fz));
+      if (fz) {
+        const int gi = g + __popc(mask & ((1u << lane) - 1u));
+        const int k = k0 + i;
+        QEntry q;
+        q.type = Q_JOB; q.blk = b; q.k = k; q.lo = lo;
+        q.jc = a.kc[k]; q.jm = a.km[k]; q.jj = a.cons[k];
+        q.jg = CONSTR ? a.kg[k] : 0.0;
+        q.jports = CONSTR ? a.kports[k] : 0;
+        q.grp = CONSTR ? (a.kflags[k] & 1) : 0;
+        q.row = i;
+        wait_slot(gi);
+        S.q[gi & (RING - 1)] = q;
+        fence_cta();
+        S.q_seq[gi & (RING - 1)] = gi + 1;
       }
-      nD++;
+      g += __popc(mask);
+      __syncwarp();
     }
     if (lane == 0) {
-      a.ports_start[k] = S.d_pu[slot];
-      S.d_ac[slot] = S.d_ac[slot] + r.c;
-      S.d_am[slot] = S.d_am[slot] + r.m;
-      S.d_an[slot] += 1;
-      S.d_pu[slot] += r.ports;
-      S.d_touch[slot] = blk;
-      a.assign[k] = wv;
-      a.fail[k] = COOK_FAIL_NONE;
-      if (CONSTR) {
-        for (int q = a.jb.group_off[r.j]; q < a.jb.group_off[r.j + 1]; q++) {
-          int g = a.jb.group_idx[q];
-          int n = __ldcg(a.gr.gp_n + g);
-          a.gr.gp_vm[a.gr.gp_off[g] + n] = wv;
-          __threadfence_block();
-          a.gr.gp_n[g] = n + 1;
+      wait_slot(g);
+      QEntry& q = S.q[g & (RING - 1)];
+      q.type = Q_END; q.blk = b; q.k = -1; q.lo = lo; q.grp = 0;
+      S.res[g & (RING - 1)].type = Q_END;
+      fence_cta();
+      S.q_seq[g & (RING - 1)] = g + 1;
+      S.res_seq[g & (RING - 1)] = g + 1;
+    }
+    g++;
+    __syncwarp();
+  }
+  if (lane == 0) {
+    wait_slot(g);
+    S.q[g & (RING - 1)].type = Q_EXIT;
+    S.res[g & (RING - 1)].type = Q_EXIT;
+    fence_cta();
+    S.q_seq[g & (RING - 1)] = g + 1;
+    S.res_seq[g & (RING - 1)] = g + 1;
+    S.exit_g = g;
+    a.stats[6] = skipped;
+  }
+}
+
+// ---- spec warps
+template <bool CONSTR>
+__device__ void spec_warp(const MatchArgs& a, ResolverShared& S, const Latest latest) {
+  const int lane = threadIdx.x & 31;
+  while (true) {
+    int g = 0;
+    if (lane == 0) g = atomicAdd(&S.ticket, 1);
+    g = __shfl_sync(0xffffffffu, g, 0);
+    const int slot = g & (RING - 1);
+    bool quit = false;
+    while (S.q_seq[slot] != g + 1) {
+      const int xg = S.exit_g;
+      if (xg >= 0 && g > xg) { quit = true; break; }
+      __nanosleep(a.poll_ns);
+    }
+    if (quit) return;
+    fence_cta();
+    const QEntry qe = S.q[slot];
+    if (qe.type == Q_EXIT) return;
+    if (qe.type != Q_JOB) continue;
+    if (qe.grp) {  // resolved by the commit warp against live group state
+      if (lane == 0) { S.res[slot].type = Q_JOB; S.res[slot].n = 0; S.res[slot].complete = 0; S.res[slot].s = 0; }
+      fence_cta();
+      if (lane == 0) S.res_seq[slot] = g + 1;
+      continue;
+    }
+    const int s = S.ncommit;
+    fence_cta();
+    spec_job<CONSTR>(a, S, latest, qe, s, KC, 2, S.res[slot]);
+    fence_cta();
+    if (lane == 0) S.res_seq[slot] = g + 1;
+  }
+}
+
+// ---- commit warp
+// argmax over lanes of (f desc, v asc) with an early exit when the high words
+// of the fitness already single out one lane (the common case).
+__device__ __forceinline__ double warp_argmax_fast(double f, int v, int& wv, int& wl) {
+  const unsigned hi = (unsigned)__double2hiint(f);
+  const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
+  unsigned cand = __ballot_sync(0xffffffffu, hi == mh);
+  if (mh == 0u) { wv = 0x7fffffff; wl = 0; return 0.0; }  // f in (0, 1] has a non-zero high word
+  if (__popc(cand) > 1) {
+    const unsigned lo = hi == mh ? (unsigned)__double2loint(f) : 0u;
+    const unsigned ml = __reduce_max_sync(0xffffffffu, lo);
+    cand = __ballot_sync(0xffffffffu, hi == mh && lo == ml);
+    if (__popc(cand) > 1) {
+      const unsigned key = ((cand >> (threadIdx.x & 31)) & 1u) ? (unsigned)v : 0xffffffffu;
+      const unsigned mk = __reduce_min_sync(0xffffffffu, key);
+      cand = __ballot_sync(0xffffffffu, key == mk);
+    }
+  }
+  wl = __ffs(cand) - 1;
+  wv = __shfl_sync(0xffffffffu, v, wl);
+  return __shfl_sync(0xffffffffu, f, wl);
+}
+
+// NCW commit warps share the serial chain: entry g belongs to warp g % NCW.  While
+// its predecessors are still being decided the owner already re-evaluates every
+// VM committed since its result's version (one lane per log entry), so at its
+// turn only the newest entry is left: per-job latency on the chain = one fitness
+// evaluation + one warp argmax + the log append.
+constexpr int NCW = 4;
+
+template <bool CONSTR, bool PROF>
+__device__ void commit_warp(const MatchArgs& a, ResolverShared& S, const Latest latest, const int cw) {
+  const int lane = threadIdx.x & 31;
+  unsigned long long n_fast = 0, n_group = 0, n_matched = 0, n_fallback = 0;
+  unsigned long long prof[6] = {0, 0, 0, 0, 0, 0};
+  const long long t_start = clock64();
+  for (int g = cw;; g += NCW) {
+    const int slot = g & (RING - 1);
+    long long t0 = PROF ? clock64() : 0;
+    bool quit = false;
+    while (S.res_seq[slot] != g + 1) {
+      const int xg = S.exit_g;
+      if (xg >= 0 && g > xg) { quit = true; break; }
+      __nanosleep(a.poll_ns);
+    }
+    if (quit) break;
+    compiler_barrier();
+    const SpecOut* R = &S.res[slot];
+    const int type = R->type;
+    if (PROF) prof[0] += (unsigned long long)(clock64() - t0);
+    if (type == Q_EXIT) {
+      while (S.gdone != g) __nanosleep(20);
+      if (lane == 0) a.stats[14] = (unsigned long long)(clock64() - t_start);
+      break;
+    }
+    if (type == Q_END) {
+      while (S.gdone != g) __nanosleep(20);
+      compiler_barrier();
+      long long t4 = PROF ? clock64() : 0;
+      // publish the newest state of every VM touched in this or the previous block
+      // into the buffer the evaluators read for block blk+2; write the block's results
+      const int b = S.q[slot].blk, lo = S.q[slot].lo;
+      const int c = S.ncommit, out_done = S.out_done;
+      VmDyn* pub = a.dyn.d[b & 1];
+      for (int e = lo + lane; e < c; e += 32) {
+        const int idx = e & (LOGN - 1);
+        const int vm = S.l_vm[idx];
+        if (latest.get(vm) == e) {
+          __stcg(reinterpret_cast<double2*>(pub + vm), make_double2(S.l_ac[idx], S.l_am[idx]));
+          __stcg(reinterpret_cast<int2*>(pub + vm) + 2, make_int2(S.l_an[idx], S.l_pu[idx]));
+        }
+        if (e >= out_done) {  // results of this block's placements
+          const int k = S.l_k[idx];
+          a.assign[k] = vm;
+          a.fail[k] = COOK_FAIL_NONE;
+          a.ports_start[k] = S.l_pu0[idx];
+        }
+      }
+      __syncwarp();
+      if (lane == 0) {
+        S.out_done = c;
+        S.lo_ring[(b + 1) & 3] = c;
+        // size of block b+2 from this block's placement rate: about btarget placements per
+        // block keeps the log ranges short while the cluster fills and the blocks long after
+        const int nb = S.bk_ring[(b + 1) & 7] - S.bk_ring[b & 7];
+        const int placed = c - S.blk_c0;
+        long long want = placed > 0 ? ((long long)a.btarget * nb + placed - 1) / placed : a.bmax;
+        want = min(want, (long long)min(a.bmax, 2 * S.last_b));
+        const int nbn = max((int)want, a.bmin);
+        S.last_b = nbn;
+        S.blk_c0 = c;
+        const int end2 = S.bk_ring[(b + 2) & 7] + nbn;   // = first job of block b+3
+        S.bk_ring[(b + 3) & 7] = end2;
+        __stcg(a.bk0 + b + 3, end2);
+        fence_cta();
+        S.bk_known = b + 3;
+        __threadfence();
+        asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(a.published), "r"((unsigned)(b + 1)) : "memory");
+        S.gdone = g + 1;
+      }
+      __syncwarp();
+      if (PROF) prof[4] += (unsigned long long)(clock64() - t4);
+      continue;
+    }
+    const QEntry& qe = S.q[slot];
+    JobRegs r;
+    r.c = qe.jc; r.m = qe.jm; r.g = CONSTR ? qe.jg : 0.0; r.ports = CONSTR ? qe.jports : 0; r.j = qe.jj;
+    const int k = qe.k;
+    const bool grp = CONSTR && qe.grp;
+    // The lane that holds the winner's pre-placement state appends the log entry.
+    int wv = -1, writer = 0, c = 0;
+    Cand w;
+    w.ac = w.am = w.lc = w.lm = w.rc = w.rm = 0.0; w.an = w.pu = 0;
+    long long t2 = 0;
+    if (grp) {
+      while (S.gdone != g) __nanosleep(20);
+      compiler_barrier();
+      t2 = PROF ? clock64() : 0;
+      c = S.ncommit;
+      const QEntry q2 = qe;
+      wv = resolve_group_job<CONSTR>(a, S, latest, q2, w);  // w uniform across lanes
+      n_group++;
+    } else {
+      const int s = R->s, n = R->n;
+      const int el = s + lane;
+      Cand y = R->c[lane & (KC - 1)];  // this lane's listed candidate
+      static_assert(KC <= 32 && (KC & (KC - 1)) == 0, "one candidate per lane");
+      Cand x;                          // this lane's log entry (VM changed since s)
+      x.vm = 0; x.ac = x.am = x.lc = x.lm = x.rc = x.rm = 0.0; x.an = x.pu = 0;
+      double xf = 0.0;
+      int c_seen = s;
+      long long t1 = PROF ? clock64() : 0;
+      // (1) follow the log until it is this entry's turn
+      while (true) {
+        const int gd = S.gdone;  // the turn flag is read BEFORE the log size
+        const bool mine = gd == g;
+        const int c_now = S.ncommit;
+        compiler_barrier();
+        if (gd < g - 1 && c_now == c_seen) { __nanosleep(60); continue; }  // only the next in line polls hard
+        if (c_now > c_seen) {
+          if (el >= c_seen && el < c_now) {
+            const int idx = el & (LOGN - 1);
+            x.vm = S.l_vm[idx];
+            x.ac = S.l_ac[idx]; x.am = S.l_am[idx]; x.lc = S.l_lc[idx]; x.lm = S.l_lm[idx];
+            x.rc = S.l_rc[idx]; x.rm = S.l_rm[idx]; x.an = S.l_an[idx]; x.pu = S.l_pu[idx];
+            xf = eval_vm<CONSTR>(a, r, x.vm, x.ac, x.am, x.an, x.pu, x.lc, x.lm, x.rc, x.rm, false);
+          }
+          c_seen = c_now;
+        }
+        if (mine) break;
+      }
+      c = c_seen;
+      t2 = PROF ? clock64() : 0;
+      if (PROF) prof[1] += (unsigned long long)(t2 - t1);
+      // (2) decide: newest valid log entry per VM, or an unchanged listed candidate
+      const bool xin = el < c && xf > 0.0 && latest.get(x.vm) == el;
+      const bool ok = lane < n && latest.get(y.vm) < s;
+      const bool use_y = ok && (!xin || better(y.f, y.vm, xf, x.vm));
+      const double lf = use_y ? y.f : (xin ? xf : 0.0);
+      const int lv = use_y ? y.vm : (xin ? x.vm : 0x7fffffff);
+      int xv, wl;
+      const double wf = warp_argmax_fast(lf, lv, xv, wl);
+      // everything unlisted and unchanged is worse than the list's last entry: the
+      // winner is exact when the list is complete or it is no worse than that entry
+      bool need_fallback = !R->complete;
+      if (need_fallback && n > 0 && wf > 0.0) {
+        const double zf = __shfl_sync(0xffffffffu, y.f, n - 1);
+        const int zv = __shfl_sync(0xffffffffu, y.vm, n - 1);
+        if (!better(zf, zv, wf, xv)) need_fallback = false;
+      }
+      if (need_fallback) {
+        // recompute at the current version (exact): its first candidate is the answer
+        const QEntry q2 = qe;
+        spec_job_fallback<CONSTR>(a, S, latest, q2, c);
+        if (S.res[RING].n > 0) { w = S.res[RING].c[0]; wv = w.vm; writer = 0; }
+        n_fallback++;
+      } else {
+        n_fast++;
+        if (wf > 0.0) {
+          wv = xv; writer = wl;
+          const bool wy = __shfl_sync(0xffffffffu, use_y ? 1 : 0, wl) != 0;
+          w = wy ? y : x;
         }
       }
     }
-    lstats[3]++;
-  } else if (lane == 0) {
-    a.assign[k] = -1; a.fail[k] = COOK_FAIL_CONSTRAINT;
-  }
-  __syncwarp();
-}
-
-// A phase (warp 0): apply the round's commits to the dirty list; returns the
-// number of jobs of the round that are final.
-__device__ int apply_round(const MatchArgs& a, ResolverShared& S, unsigned* bitmap, int& nD, int blk,
-                           int k0, int q0, int n, unsigned long long* lstats) {
-  const int lane = threadIdx.x & 31;
-  const bool in = lane < n;
-  const int ab = in ? S.commits[lane].aborted : 0;
-  const unsigned abm = __ballot_sync(0xffffffffu, in && ab);
-  const int n_done = abm ? (__ffs(abm) - 1) : n;
-  const bool act = lane < n_done;
-  const int vm = act ? S.commits[lane].vm : -1;
-  int slot = (act && vm >= 0) ? S.commits[lane].st.slot : -1;
-  // first / last commit of each distinct VM inside the round
-  bool first = act && vm >= 0, last = act && vm >= 0;
-  int first_lane = lane;
-  for (int j = 0; j < SPEC_W; j++) {
-    const int vj = __shfl_sync(0xffffffffu, vm, j);
-    if (vm >= 0 && vj == vm) {
-      if (j < lane) { first = false; if (j < first_lane) first_lane = j; }
-      if (j > lane) last = false;
-    }
-  }
-  // new dirty slots for VMs that were clean at round start
-  const unsigned newm = __ballot_sync(0xffffffffu, first && slot < 0);
-  if (first && slot < 0) slot = nD + __popc(newm & ((1u << lane) - 1u));
-  // a later commit of the same VM carries the slot of the first one
-  const int fslot = __shfl_sync(0xffffffffu, slot, first_lane);
-  if (act && vm >= 0 && !first) slot = fslot;
-  if (last) {
-    const VmRec st = S.commits[lane].st;
-    S.d_vm[slot] = vm; S.d_ac[slot] = st.ac; S.d_am[slot] = st.am; S.d_an[slot] = st.an;
-    S.d_pu[slot] = st.pu; S.d_lc[slot] = st.lc; S.d_lm[slot] = st.lm; S.d_rc[slot] = st.rc;
-    S.d_rm[slot] = st.rm; S.d_touch[slot] = blk;
-  }
-  if (first && S.commits[lane].st.slot < 0) atomicOr(&bitmap[vm >> 5], 1u << (vm & 31));
-  if (act) {
-    const int k = k0 + S.feas_list[q0 + lane];
-    a.assign[k] = vm;
-    a.fail[k] = vm >= 0 ? COOK_FAIL_NONE : COOK_FAIL_CONSTRAINT;
-    if (vm >= 0) a.ports_start[k] = S.commits[lane].pu_before;
-  }
-  nD += __popc(newm);
-  lstats[3] += __popc(__ballot_sync(0xffffffffu, act && vm >= 0));
-  lstats[0] += n_done;
-  __syncwarp();
-  return n_done;
-}
-
-// Warp 0 between rounds: block transitions (publish, wait for rows, compaction,
-// feasibility list), TMA row issue, next round header.
-template <bool CONSTR, bool PROF>
-struct Driver {
-  int blk, nblk, k0, nj, nfeas, qdone, qissued, nD;
-  unsigned gq;  // global feasible counter at qdone
-};
-
-template <bool CONSTR>
-__device__ void begin_block(const MatchArgs& a, ResolverShared& S, unsigned* bitmap, int blk, int& nD,
-                            int& nfeas, unsigned long long* lstats) {
-  const int lane = threadIdx.x & 31;
-  const int k0 = blk * a.B;
-  const int k1 = min(k0 + a.B, a.n_cons);
-  const int nj = k1 - k0;
-  for (int i = lane; i < nj; i += 32) {
-    S.jc[i] = a.kc[k0 + i]; S.jm[i] = a.km[k0 + i]; S.jj[i] = a.cons[k0 + i];
-    if (CONSTR) { S.jg[i] = a.kg[k0 + i]; S.jports[i] = a.kports[k0 + i]; S.jgrp[i] = a.kflags[k0 + i] & 1; }
-  }
-  // drop dirty entries not touched in the previous block: they are part of the
-  // snapshot this block's rows were scored against.
-  {
-    int keep_n = 0;
-    for (int base = 0; base < nD; base += 32) {
-      int d = base + lane;
-      bool keep = d < nD && S.d_touch[d] >= blk - 1;
-      unsigned kb = __ballot_sync(0xffffffffu, keep);
-      int vm = 0, an = 0, pu = 0, tc = 0; double ac = 0, am = 0, lc = 0, lm = 0, rc = 0, rm = 0;
-      if (d < nD) {
-        vm = S.d_vm[d]; an = S.d_an[d]; pu = S.d_pu[d]; tc = S.d_touch[d];
-        ac = S.d_ac[d]; am = S.d_am[d]; lc = S.d_lc[d]; lm = S.d_lm[d]; rc = S.d_rc[d]; rm = S.d_rm[d];
-        if (!keep) atomicAnd(&bitmap[vm >> 5], ~(1u << (vm & 31)));
+    if (wv >= 0) {
+      if (lane == writer) {
+        const int idx = c & (LOGN - 1);
+        S.l_vm[idx] = wv;
+        S.l_ac[idx] = w.ac + r.c; S.l_am[idx] = w.am + r.m;
+        S.l_lc[idx] = w.lc; S.l_lm[idx] = w.lm; S.l_rc[idx] = w.rc; S.l_rm[idx] = w.rm;
+        S.l_an[idx] = w.an + 1; S.l_pu[idx] = w.pu + r.ports;
+        S.l_k[idx] = k; S.l_pu0[idx] = w.pu;
+        latest.set(wv, c);
+        fence_cta();
+        S.ncommit = c + 1;
+        if (grp) {
+          for (int q = a.jb.group_off[r.j]; q < a.jb.group_off[r.j + 1]; q++) {
+            const int gi = a.jb.group_idx[q];
+            const int n = __ldcg(a.gr.gp_n + gi);
+            __stcg(a.gr.gp_vm + a.gr.gp_off[gi] + n, wv);
+            __stcg(a.gr.gp_n + gi, n + 1);
+          }
+          __threadfence();  // the next group job may run on another commit warp
+        }
+        fence_cta();
+        S.gdone = g + 1;
       }
-      __syncwarp();
-      if (keep) {
-        int t = keep_n + __popc(kb & ((1u << lane) - 1u));
-        S.d_vm[t] = vm; S.d_an[t] = an; S.d_pu[t] = pu; S.d_touch[t] = tc;
-        S.d_ac[t] = ac; S.d_am[t] = am; S.d_lc[t] = lc; S.d_lm[t] = lm; S.d_rc[t] = rc; S.d_rm[t] = rm;
-      }
-      keep_n += __popc(kb);
-      __syncwarp();
+      n_matched++;
+    } else if (lane == 0) {
+      S.gdone = g + 1;  // assign / fail keep their defaults (-1, COOK_FAIL_CONSTRAINT)
     }
-    nD = keep_n;
+    __syncwarp();
+    if (PROF) prof[2] += (unsigned long long)(clock64() - t2);
   }
-  // rows of this block ready?
   if (lane == 0) {
-    while (ld_acquire_u32(a.rows_ready + blk) < (unsigned)nj) __nanosleep(20);
-    asm volatile("fence.proxy.async;" ::: "memory");  // generic-proxy writes -> async-proxy (TMA) reads
+    atomicAdd(a.stats + 0, n_fast); atomicAdd(a.stats + 2, n_group); atomicAdd(a.stats + 3, n_matched);
+    atomicAdd(a.stats + 4, n_fallback);
+    if (cw == 0) { a.stats[1] = S.n_rescan; a.stats[5] = S.n_trunc; }
+    for (int i = 0; i < 6; i++) atomicAdd(a.stats + 8 + i, prof[i]);
   }
-  __syncwarp();
-  // jobs with no feasible VM at the snapshot are unplaceable now too (resources
-  // and count constraints only tighten within a cycle): skip them wholesale.
-  const uint8_t* feas = a.feas + (size_t)(blk & 1) * a.B;
-  nfeas = 0;
-  for (int base = 0; base < nj; base += 32) {
-    const int i = base + lane;
-    const bool valid = i < nj;
-    const bool fz = valid && __ldcg(feas + i) != 0;
-    if (valid && !fz) { a.assign[k0 + i] = -1; a.fail[k0 + i] = COOK_FAIL_RESOURCES; }
-    const unsigned mask = __ballot_sync(0xffffffffu, fz);
-    const unsigned vmask = __ballot_sync(0xffffffffu, valid);
-    lstats[0] += __popc(vmask & ~mask);
-    if (fz) S.feas_list[nfeas + __popc(mask & ((1u << lane) - 1u))] = (int16_t)i;
-    nfeas += __popc(mask);
-  }
-  __syncwarp();
-}
-
-__device__ void end_block(const MatchArgs& a, ResolverShared& S, int blk, int nD) {
-  // publish every dirty entry (touched in this or the previous block) into the
-  // buffer the evaluators read for block blk+2.
-  const int lane = threadIdx.x & 31;
-  VmDyn* pub = a.dyn.d[blk & 1];
-  for (int d = lane; d < nD; d += 32) {
-    int v = S.d_vm[d];
-    __stcg(reinterpret_cast<double2*>(pub + v), make_double2(S.d_ac[d], S.d_am[d]));
-    __stcg(reinterpret_cast<int2*>(pub + v) + 2, make_int2(S.d_an[d], S.d_pu[d]));
-  }
-  __syncwarp();
-  if (lane == 0) {
-    __threadfence();
-    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(a.published), "r"((unsigned)(blk + 1)) : "memory");
-  }
-  __syncwarp();
 }
 
 // Pipeline.  The resolver CTA places block t while the evaluator CTAs score
 // block t+1 against the state published after block t-1 (buffer (t+1)&1).
-// Synchronisation is by two monotone counters only:
+// Synchronisation across CTAs is by two monotone counters only:
 //   rows_ready[b]  evaluators -> resolver (one arrival per scored row)
 //   published      resolver -> evaluators (# blocks resolved and published)
 template <bool CONSTR, bool PROF>
 __global__ void __launch_bounds__(RES_THREADS, 1) match_kernel(MatchArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  const int nblk = (a.n_cons + a.B - 1) / a.B;
   if (blockIdx.x == 0) {
     ResolverShared& S = *reinterpret_cast<ResolverShared*>(smem_raw);
-    unsigned* bitmap = reinterpret_cast<unsigned*>(smem_raw + sizeof(ResolverShared));
-    const int words = (a.of.O + 31) / 32;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int i = threadIdx.x; i < words; i += RES_THREADS) bitmap[i] = 0u;
+    Latest latest;
+    latest.s = reinterpret_cast<int*>(smem_raw + ((sizeof(ResolverShared) + 15) & ~size_t(15)));
+    latest.g = a.latest_global;
+    const int warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < a.of.O; i += RES_THREADS) latest.set(i, -1);
+    if (threadIdx.x < RING) { S.q_seq[threadIdx.x] = 0; S.res_seq[threadIdx.x] = 0; }
+    for (int i = threadIdx.x; i < LOGN; i += RES_THREADS) S.l_vm[i] = 0;
     if (threadIdx.x == 0) {
-      for (int i = 0; i < ROW_RING; i++) mbar_init(&S.bar[i], 1);
-      for (int i = 0; i < SPEC_W; i++) S.commit_flag[i] = 0;
-      S.n_rescan = 0;
-      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      S.ncommit = 0; S.gdone = 0; S.exit_g = -1; S.ticket = 0;
+      S.lo_ring[0] = S.lo_ring[1] = S.lo_ring[2] = S.lo_ring[3] = 0;
+      S.bk_ring[0] = 0; S.bk_ring[1] = a.B; S.bk_ring[2] = 2 * a.B; S.bk_known = 2;  // = host-initialised bk0[0..2]
+      S.out_done = 0; S.blk_c0 = 0; S.last_b = a.B;
+      S.n_rescan = 0; S.n_trunc = 0;
     }
     __syncthreads();
-    // ---- driver state (warp 0 only)
-    int blk = 0, k0 = 0, nfeas = 0, qdone = 0, qissued = 0, nD = 0, seq = 0;
-    unsigned gq = 0;  // global feasible-job counter at qdone (row ring position)
-    bool open = false;  // a block is open
-    unsigned long long lstats[4] = {0, 0, 0, 0};
-    unsigned long long prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    long long t_start = clock64();
-    while (true) {
-      if (warp == 0) {
-        long long td0 = PROF ? clock64() : 0;
-        // advance to a state where a round can be issued (or exit)
-        int mode = 0, n = 0;
-        while (true) {
-          if (!open) {
-            if (blk >= nblk) { mode = 1; break; }
-            k0 = blk * a.B;
-            begin_block<CONSTR>(a, S, bitmap, blk, nD, nfeas, lstats);
-            qdone = 0; qissued = 0;
-            open = true;
-          }
-          // keep the row ring full
-          if (lane == 0) {
-            const unsigned char* gbase = a.rows + (size_t)(blk & 1) * a.B * ROW_BYTES;
-            while (qissued < nfeas && qissued < qdone + ROW_RING) {
-              const unsigned s = (gq + (unsigned)(qissued - qdone)) % ROW_RING;
-              mbar_expect_tx(&S.bar[s], ROW_BYTES);
-              tma_load_1d(S.rows[s], gbase + (size_t)S.feas_list[qissued] * ROW_BYTES, ROW_BYTES, &S.bar[s]);
-              qissued++;
-            }
-          }
-          qissued = __shfl_sync(0xffffffffu, qissued, 0);
-          if (qdone >= nfeas) {  // block finished
-            end_block(a, S, blk, nD);
-            open = false;
-            blk++;
-            continue;
-          }
-          // group-constrained jobs are resolved one at a time against live state
-          if (CONSTR && S.jgrp[S.feas_list[qdone]]) {
-            const int ib = S.feas_list[qdone];
-            // its (unused) row slot still has to be consumed to keep the ring in phase
-            mbar_wait(&S.bar[gq % ROW_RING], (gq / ROW_RING) & 1u);
-            resolve_group_job<CONSTR>(a, blk, k0 + ib, ib, S, bitmap, nD, lstats);
-            qdone++; gq++;
-            continue;
-          }
-          n = 0;
-          while (n < SPEC_W && qdone + n < nfeas && !(CONSTR && S.jgrp[S.feas_list[qdone + n]])) n++;
-          break;
-        }
-        seq++;
-        if (lane == 0) {
-          S.r_mode = mode; S.r_n = n; S.r_q0 = qdone; S.r_seq = seq; S.r_blk = blk; S.r_k0 = k0;
-          S.r_nD = nD; S.r_gq0 = gq;
-        }
-        if (PROF) prof[0] += (unsigned long long)(clock64() - td0);
-      }
-      __syncthreads();  // (A) round header visible
-      if (S.r_mode == 1) break;
-      const int rn = S.r_n;
-      long long tr0 = PROF ? clock64() : 0;
-      if (warp < rn) {
-        const int rq0 = S.r_q0, rblk = S.r_blk, rseq = S.r_seq, rnD = S.r_nD;
-        const unsigned g = S.r_gq0 + (unsigned)warp;
-        const int ib = S.feas_list[rq0 + warp];
-        mbar_wait(&S.bar[g % ROW_RING], (g / ROW_RING) & 1u);
-        SpecResult sp;
-        JobRegs r;
-        spec_phase<CONSTR>(a, rblk, ib, S.rows[g % ROW_RING], S, bitmap, rnD, sp, r);
-        if (PROF && warp == 0) prof[1] += (unsigned long long)(clock64() - tr0);
-        chain_phase<CONSTR>(a, S, warp, rseq, r, sp);
-      }
-      long long tr1 = PROF ? clock64() : 0;
-      __syncthreads();  // (B) all commits of the round published
-      if (warp == 0) {
-        if (PROF) { prof[2] += (unsigned long long)(clock64() - tr1); prof[4]++; }
-        long long ta0 = PROF ? clock64() : 0;
-        const int n_done = apply_round(a, S, bitmap, nD, blk, k0, qdone, rn, lstats);
-        qdone += n_done;
-        gq += (unsigned)n_done;
-        if (PROF) { prof[3] += (unsigned long long)(clock64() - ta0); prof[5] += (unsigned long long)(rn - n_done); }
-      }
-    }
-    if (threadIdx.x == 0) {
-      a.stats[0] = lstats[0]; a.stats[1] = S.n_rescan; a.stats[2] = lstats[2]; a.stats[3] = lstats[3];
-      for (int i = 0; i < 6; i++) a.stats[4 + i] = prof[i];
-      a.stats[12] = (unsigned long long)(clock64() - t_start);
-    }
+    // warps 0, 4, 8, 12 share one scheduler (warp id mod 4): the commit warps keep it to themselves
+    if ((warp & 3) == 0 && (warp >> 2) < NCW) commit_warp<CONSTR, PROF>(a, S, latest, warp >> 2);
+    else if (warp == 1) driver_warp<CONSTR>(a, S);
+    else spec_warp<CONSTR>(a, S, latest);
   } else {
     EvalShared& E = *reinterpret_cast<EvalShared*>(smem_raw);
     const int n_eval = gridDim.x - 1;
-    unsigned long long work = 0, wait = 0;
+    unsigned long long work = 0, wait = 0, work_q1 = 0, rows_q1 = 0, nblk_seen = 0;
     unsigned long long ep[3] = {0, 0, 0};
-    for (int b = 0; b < nblk; b++) {
-      const int k0 = b * a.B, k1 = min(k0 + a.B, a.n_cons);
+    for (int b = 0;; b++) {
       long long w0 = clock64();
-      // rows of block b need S_{b-2}: published >= b-1
+      // rows of block b need S_{b-2}: published >= b-1 (which also covers bk0[b], bk0[b+1])
       if (b >= 2) {
         if (threadIdx.x == 0)
           while ((int)ld_acquire_u32(a.published) < b - 1) __nanosleep(32);
         __syncthreads();
       }
+      const int k0 = __ldcg(a.bk0 + b);
+      if (k0 >= a.n_cons) break;
+      const int k1 = min(__ldcg(a.bk0 + b + 1), a.n_cons);
       long long w1 = clock64();
-      for (int k = k0 + (int)blockIdx.x - 1; k < k1; k += n_eval) evaluate_row<CONSTR, PROF>(a, k, b, E, ep);
+      for (int k = k0 + (int)blockIdx.x - 1; k < k1; k += n_eval)
+        evaluate_row<CONSTR, PROF>(a, k, b, k - k0, E, ep);
       wait += (unsigned long long)(w1 - w0);
-      work += (unsigned long long)(clock64() - w1);
+      const unsigned long long dt = (unsigned long long)(clock64() - w1);
+      work += dt;
+      if (PROF) { if (k0 < a.n_cons / 4) { work_q1 += dt; rows_q1 += (k1 - k0 + n_eval - 1) / n_eval; } nblk_seen++; }
     }
     if (blockIdx.x == 1 && threadIdx.x == 0) {
-      a.stats[14] = work; a.stats[15] = wait;
-      if (PROF) { a.stats[16] = ep[0]; a.stats[17] = ep[1]; a.stats[18] = ep[2]; }
+      a.stats[16] = work; a.stats[17] = wait;
+      if (PROF) { a.stats[18] = ep[0]; a.stats[19] = ep[1]; a.stats[20] = ep[2]; a.stats[21] = work_q1; a.stats[22] = rows_q1; a.stats[23] = nblk_seen; }
     }
   }
 }
@@ -1366,6 +1468,9 @@ struct MatchPlan {
   uint8_t* d_kflags = nullptr;
   unsigned long long* d_stats = nullptr;
   int32_t* d_counters = nullptr;
+  int* d_latest = nullptr;
+  size_t max_blocks = 0;
+  int32_t bk_init[3] = {0, 0, 0};
 };
 
 static void plan_free(void* p) {
@@ -1418,8 +1523,14 @@ static int32_t build_plan(cook_pool* pool, MatchPlan* mp, const int32_t* ranked_
   if (!constr_eff && jobs->ports)
     for (int j = 0; j < J && !constr_eff; j++) constr_eff = jobs->ports[j] != 0;
 
-  int B = 128;
+  // blocks: B jobs at the start, then sized by the resolver to ~btarget placements per block
+  int B = 64, bmin = 64, bmax = MAXB, btarget = 48;
   if (const char* eb = getenv("COOK_MATCH_B")) { int v = atoi(eb); if (v >= 8 && v <= MAXB) B = v; }
+  if (const char* eb = getenv("COOK_MATCH_BMIN")) { int v = atoi(eb); if (v >= 8 && v <= MAXB) bmin = v; }
+  if (const char* eb = getenv("COOK_MATCH_BMAX")) { int v = atoi(eb); if (v >= 8 && v <= MAXB) bmax = v; }
+  if (const char* eb = getenv("COOK_MATCH_TARGET")) { int v = atoi(eb); if (v >= 1) btarget = v; }
+  bmax = std::max(bmax, std::max(B, bmin));
+  const size_t max_blocks = (size_t)NC / std::min(B, bmin) + 8;
   Sizer sz;
   sz.add<int32_t>(n_ranked);
   for (int k = 0; k < 3; k++) sz.add<double>(J + 1);
@@ -1449,13 +1560,13 @@ static int32_t build_plan(cook_pool* pool, MatchPlan* mp, const int32_t* ranked_
   for (int k = 0; k < 6; k++) sz.add<int32_t>(n_ranked + 1);
   sz.add<uint8_t>(n_ranked + 1);
   sz.add<int32_t>(NC + 1); sz.add<double>(NC + 1); sz.add<double>(NC + 1); sz.add<uint8_t>(NC + 1);
-  sz.add<unsigned char>((size_t)2 * B * ROW_BYTES); sz.add<double>(NC + B + 1); sz.add<int32_t>(NC + B + 1);
-  sz.add<uint8_t>(2 * B + 16); sz.add<unsigned>((size_t)NC / B + 16);
+  sz.add<unsigned char>((size_t)2 * bmax * ROW_BYTES); sz.add<double>(NC + bmax + 1); sz.add<int32_t>(NC + bmax + 1);
+  sz.add<uint8_t>(2 * bmax + 16); sz.add<unsigned>(max_blocks + 8); sz.add<int32_t>(max_blocks + 8);
   sz.add<int32_t>(NC + 1); sz.add<int32_t>(NC + 1); sz.add<uint8_t>(NC + 1);
   sz.add<int32_t>(NC + 1); sz.add<int32_t>((size_t)NC * std::max(max_ports, 1) + 1);
   sz.add<int32_t>(O + 1);
   sz.add<unsigned long long>(32); sz.add<int32_t>(16);
-  sz.add<VmStatic>(O + 1); sz.add<VmDyn>(O + 1); sz.add<VmDyn>(O + 1);
+  sz.add<VmStatic>(O + 1); sz.add<VmDyn>(O + 1); sz.add<VmDyn>(O + 1); sz.add<int>(O + 1);
   CK(pool, ar.reserve(sz.off + (1 << 18)));
   ar.reset();
 
@@ -1556,12 +1667,14 @@ static int32_t build_plan(cook_pool* pool, MatchPlan* mp, const int32_t* ranked_
   mp->d_kc = ar.take<double>(NC + 1);
   mp->d_km = ar.take<double>(NC + 1);
   mp->d_kflags = ar.take<uint8_t>(NC + 1);
-  ma.rows = ar.take<unsigned char>((size_t)2 * B * ROW_BYTES);
-  mp->d_kg = ar.take<double>(NC + B + 1);
-  mp->d_kports = ar.take<int32_t>(NC + B + 1);
+  ma.rows = ar.take<unsigned char>((size_t)2 * bmax * ROW_BYTES);
+  mp->d_kg = ar.take<double>(NC + bmax + 1);
+  mp->d_kports = ar.take<int32_t>(NC + bmax + 1);
   ma.kg = mp->d_kg; ma.kports = mp->d_kports;
-  ma.feas = ar.take<uint8_t>(2 * B + 16);
-  ma.rows_ready = ar.take<unsigned>((size_t)NC / B + 16);
+  ma.feas = ar.take<uint8_t>(2 * bmax + 16);
+  ma.rows_ready = ar.take<unsigned>(max_blocks + 8);
+  ma.bk0 = ar.take<int32_t>(max_blocks + 8);
+  mp->max_blocks = max_blocks;
   ma.assign = ar.take<int32_t>(NC + 1);
   ma.ports_start = ar.take<int32_t>(NC + 1);
   ma.fail = ar.take<uint8_t>(NC + 1);
@@ -1570,11 +1683,19 @@ static int32_t build_plan(cook_pool* pool, MatchPlan* mp, const int32_t* ranked_
   mp->d_used = ar.take<int32_t>(O + 1);
   mp->d_stats = ar.take<unsigned long long>(32);
   mp->d_counters = ar.take<int32_t>(16);
-  if (!mp->d_counters) return set_err(pool, COOK_E_OOM, "cook_match: arena exhausted");
+  mp->d_latest = ar.take<int>(O + 1);
+  if (!mp->d_counters || !mp->d_latest) return set_err(pool, COOK_E_OOM, "cook_match: arena exhausted");
   ma.jb = jb; ma.of = of; ma.gr = gr;
   ma.cons = mp->d_cons; ma.kc = mp->d_kc; ma.km = mp->d_km; ma.kflags = mp->d_kflags;
-  ma.B = B; ma.host_lifetime_mins = params->host_lifetime_mins;
+  ma.B = B; ma.bmin = bmin; ma.bmax = bmax; ma.btarget = btarget;
+  ma.host_lifetime_mins = params->host_lifetime_mins;
   ma.published = reinterpret_cast<unsigned*>(mp->d_counters + 8); ma.stats = mp->d_stats;
+  ma.isolate_commit = 1;
+  if (const char* ei = getenv("COOK_ISOLATE")) ma.isolate_commit = atoi(ei);
+  ma.lookahead = 16;
+  ma.poll_ns = 200;
+  if (const char* ep = getenv("COOK_POLL_NS")) ma.poll_ns = atoi(ep);
+  if (const char* el = getenv("COOK_LOOKAHEAD")) { int v = atoi(el); if (v >= 2 && v <= RING) ma.lookahead = v; }
   mp->J = J; mp->O = O; mp->U = U; mp->n_ranked = n_ranked; mp->NC = NC; mp->max_ports = max_ports;
   mp->G = G; mp->B = B; mp->constr = constr_eff; mp->n_memb = n_memb;
   mp->valid = true;
@@ -1599,7 +1720,11 @@ static int32_t run_plan(cook_pool* pool, MatchPlan* mp, int32_t* out_considerabl
   CK(pool, cudaMemsetAsync(mp->d_used, 0, sizeof(int32_t) * (O + 1), st));
   CK(pool, cudaMemsetAsync(mp->d_stats, 0, sizeof(unsigned long long) * 32, st));
   CK(pool, cudaMemsetAsync(mp->d_counters, 0, sizeof(int32_t) * 16, st));
-  CK(pool, cudaMemsetAsync(ma.rows_ready, 0, sizeof(unsigned) * ((size_t)mp->NC / mp->B + 16), st));
+  CK(pool, cudaMemsetAsync(ma.rows_ready, 0, sizeof(unsigned) * (mp->max_blocks + 8), st));
+  {  // first three block bounds; the resolver appends the rest while it runs
+    mp->bk_init[0] = 0; mp->bk_init[1] = mp->B; mp->bk_init[2] = 2 * mp->B;
+    CK(pool, cudaMemcpyAsync(ma.bk0, mp->bk_init, sizeof(mp->bk_init), cudaMemcpyHostToDevice, st));
+  }
   CK(pool, cudaEventRecord(pool->ev[1], st));
 
   // ---- M0 considerable
@@ -1653,10 +1778,15 @@ static int32_t run_plan(cook_pool* pool, MatchPlan* mp, int32_t* out_considerabl
       CK(pool, cudaMemsetAsync(ma.assign, 0xff, sizeof(int32_t) * n_cons, st));
       CK(pool, cudaMemsetAsync(ma.fail, COOK_FAIL_NO_OFFERS, n_cons, st));
     } else {
-      size_t smem = std::max(sizeof(ResolverShared) + sizeof(unsigned) * ((O + 31) / 32) + 16,
-                             sizeof(EvalShared));
-      if (smem > 220 * 1024)
-        return set_err(pool, COOK_E_BADARG, "cook_match: too many offers for the resolver bitmap (%d)", O);
+      // defaults for feasible-but-unplaced jobs; the kernel overwrites placed and skipped ones
+      CK(pool, cudaMemsetAsync(ma.assign, 0xff, sizeof(int32_t) * n_cons, st));
+      CK(pool, cudaMemsetAsync(ma.fail, COOK_FAIL_CONSTRAINT, n_cons, st));
+      // resolver CTA: shared structures + the per-VM newest-log-entry table (global when too big)
+      const size_t res_base = (sizeof(ResolverShared) + 15) & ~size_t(15);
+      size_t smem = std::max(res_base, sizeof(EvalShared));
+      ma.latest_global = nullptr;
+      if (res_base + sizeof(int) * (size_t)O <= 200 * 1024) smem = std::max(smem, res_base + sizeof(int) * (size_t)O);
+      else ma.latest_global = mp->d_latest;
       void* kfn = mp->constr ? (prof_on ? (void*)match_kernel<true, true> : (void*)match_kernel<true, false>)
                              : (prof_on ? (void*)match_kernel<false, true> : (void*)match_kernel<false, false>);
       CK(pool, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1694,10 +1824,11 @@ static int32_t run_plan(cook_pool* pool, MatchPlan* mp, int32_t* out_considerabl
   CK(pool, cudaEventRecord(pool->ev[4], st));
   CK(pool, cudaStreamSynchronize(st));
   if (prof_on) {
-    const char* nm[15] = {"driver", "spec_phase_w0", "chain_wait_w0", "apply", "rounds", "aborted_jobs",
-                          "-", "-", "res_total", "-", "eval_work", "eval_wait",
-                          "eval_loop", "eval_sync", "eval_merge"};
-    for (int i = 0; i < 15; i++) fprintf(stderr, "[cook_prof] %-14s %llu\n", nm[i], hstats[4 + i]);
+    const char* nm[24] = {"fast", "chunk_rescan", "group_jobs", "matched", "fallbacks", "trunc_specs",
+                          "skipped", "-", "c_wait_result", "c_follow_log", "c_decide_commit", "-",
+                          "c_end_block", "-", "res_total", "-", "eval_work", "eval_wait",
+                          "eval_loop", "eval_sync", "eval_merge", "eval_work_q1", "eval_rowslots_q1", "blocks"};
+    for (int i = 0; i < 24; i++) fprintf(stderr, "[cook_prof] %-14s %llu\n", nm[i], hstats[i]);
   }
   if (out_stats) {
     out_stats->n_considerable = n_cons;
@@ -1705,8 +1836,8 @@ static int32_t run_plan(cook_pool* pool, MatchPlan* mp, int32_t* out_considerabl
     out_stats->head_matched = (n_cons > 0 && out_assign[0] >= 0) ? 1 : 0;
     out_stats->n_offers_used = n_used;
     out_stats->evals = (int64_t)n_cons * O;
-    out_stats->n_fast = (int64_t)hstats[0];
-    out_stats->n_chunk_rescan = (int64_t)hstats[1];
+    out_stats->n_fast = (int64_t)(hstats[0] + hstats[6]);
+    out_stats->n_chunk_rescan = (int64_t)(hstats[1] + hstats[4]);
     out_stats->n_full_rescan = (int64_t)hstats[2];
     out_stats->ms_h2d = uploaded ? ev_ms(pool->ev[0], pool->ev[1]) : 0.0;
     out_stats->ms_considerable = ev_ms(pool->ev[1], pool->ev[2]);
