@@ -115,7 +115,8 @@ struct MatchArgs {
   unsigned char* rows;     // [2][B][ROW_BYTES]: f[TOPK][32] f64 then v[TOPK][32] i32
   const double* kg;        // gathered gpus per k (constraint kernel)
   const int32_t* kports;   // gathered port counts per k
-  uint8_t* feas;           // [2][B] any feasible VM at the snapshot
+  int32_t* feas;           // [2][bmax] block + 1 once any VM is feasible for the row at the snapshot
+  int vs_in_smem;          // evaluators keep the static VM table in shared memory
   unsigned* rows_ready;    // [nblk] rows scored per block
   unsigned* published;     // # blocks resolved and published
   int32_t* assign;         // [n_cons] v (rank space) or -1
@@ -126,9 +127,15 @@ struct MatchArgs {
   int isolate_commit;         // keep the warps that share the commit warp's scheduler idle
   int lookahead;              // queue entries in flight (<= RING)
   int poll_ns;                // back-off of the resolver's shared-memory polling loops
+  int max_spec_warp;          // spec warps are the non-commit, non-driver warps below this id
 };
 
 // ------------------------------------------------------------------ helpers
+__device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
   unsigned v;
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -338,107 +345,143 @@ __device__ __forceinline__ void cp_async_commit_wait_all() {
 }
 
 // ------------------------------------------------------------- evaluators
-// One CTA scores one job against ALL offers (snapshot state).  Thread t scans
-// v = t, t+256, ... (coalesced 128-bit loads); v mod 32 == lane, so every
-// thread's VMs belong to chunk `lane`.  Each thread keeps its best TOPK
-// (fitness desc, v asc); the 8 warps' lists are tree-merged per lane through
-// shared memory into the row.
-struct EvalShared {
-  double f[RES_THREADS / 32][TOPK][32];
-  int32_t v[RES_THREADS / 32][TOPK][32];
-};
+// One CTA scores one job against ALL offers of a snapshot.  The offers are cut
+// into tiles of 32 consecutive VMs; tile t belongs to CHUNK t mod 32 and a warp
+// owns whole chunks (warp w: chunks w, w + NW, ...), so the per-chunk top-TOPK
+// lists of a row need no cross-warp merge and no CTA barrier: lane i of the
+// owning warp scores VM 32*t + i of every tile of the chunk, keeps its own
+// sorted top-TOPK, and TOPK warp-argmax rounds emit the chunk's list.
+//   row[k]: f[TOPK][32 chunks] f64 then v[TOPK][32 chunks] i32, sorted per chunk
+//   feas[k] = generation stamp (block + 1) once any VM is feasible for the job
+// The static VM table {lease cpus/mem, running cpus/mem} lives in shared memory
+// (SoA, loaded once per CTA) when it fits; the dynamic state is read from L2 with
+// all loads of a batch in flight.
+constexpr int NW = RES_THREADS / 32;
+static_assert(32 % NW == 0, "a warp owns 32 / NW chunks");
+constexpr int CPW = 32 / NW;  // chunks per warp
 
 __device__ __forceinline__ bool better(double f, int v, double g, int w) {
   return f > g || (f == g && v < w);
 }
 
-// merge the sorted list E[w] into the sorted register list (f, vv)
-__device__ __forceinline__ void merge_list(double* f, int* vv, const EvalShared& E, int w, int lane) {
-#pragma unroll 1
-  for (int i = 0; i < TOPK; i++) {
-    double x = E.f[w][i][lane];
-    int xv = E.v[w][i][lane];
-    if (!(x > 0.0) || !better(x, xv, f[TOPK - 1], vv[TOPK - 1])) break;  // lists are sorted
-    f[TOPK - 1] = x; vv[TOPK - 1] = xv;
-#pragma unroll
-    for (int q = TOPK - 1; q > 0; q--) {
-      if (better(f[q], vv[q], f[q - 1], vv[q - 1])) {
-        double tf = f[q]; f[q] = f[q - 1]; f[q - 1] = tf;
-        int tv = vv[q]; vv[q] = vv[q - 1]; vv[q - 1] = tv;
-      }
-    }
-  }
+__device__ __forceinline__ double warp_max_f64(double f) {  // f >= 0
+  unsigned hi = (unsigned)__double2hiint(f);
+  unsigned mh = __reduce_max_sync(0xffffffffu, hi);
+  unsigned lo = hi == mh ? (unsigned)__double2loint(f) : 0u;
+  unsigned ml = __reduce_max_sync(0xffffffffu, lo);
+  return __hiloint2double((int)mh, (int)ml);
 }
 
+// argmax over lanes of (f desc, key asc); key < 0xffffffff.  Returns the winning
+// fitness (0 => nobody), wk = its key, wl = its lane.
+__device__ __forceinline__ double warp_argmax(double f, unsigned key, unsigned& wk, int& wl) {
+  const double wf = warp_max_f64(f);
+  const unsigned k2 = (f == wf && wf > 0.0) ? key : 0xffffffffu;
+  wk = __reduce_min_sync(0xffffffffu, k2);
+  wl = __ffs(__ballot_sync(0xffffffffu, k2 == wk)) - 1;
+  return wf;
+}
+
+
+struct EvalStatic {  // static VM table in shared memory (SoA), or null => global
+  const double* lc; const double* lm; const double* rc; const double* rm;
+};
+
 template <bool CONSTR, bool PROF>
-__device__ void evaluate_row(const MatchArgs& a, int k, int blk, int ib, EvalShared& E, unsigned long long* ep) {
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+__device__ void evaluate_row(const MatchArgs& a, int k, int blk, int ib, const EvalStatic& es,
+                             unsigned long long* ep) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   long long e0 = PROF ? clock64() : 0;
   const double2* st2 = reinterpret_cast<const double2*>(a.of.vs);
   const double2* dy2 = reinterpret_cast<const double2*>(a.dyn.d[blk & 1]);  // S_{b-2} = buffer b&1
-  double f[TOPK];
-  int vv[TOPK];
-#pragma unroll
-  for (int i = 0; i < TOPK; i++) { f[i] = 0.0; vv[i] = -1; }
   const bool grp = CONSTR && (a.kflags[k] & 1);
+  unsigned char* row = a.rows + ((size_t)(blk & 1) * a.bmax + ib) * ROW_BYTES;
+  double* rf = reinterpret_cast<double*>(row);
+  int32_t* rv = reinterpret_cast<int32_t*>(row + ROW_V_OFF);
+  bool any = grp;  // group jobs are resolved against live group state, their rows stay empty
   if (!grp) {
     const JobRegs r = load_job<CONSTR>(a, k);
-#pragma unroll 4
-    for (int v = tid; v < a.of.O; v += RES_THREADS) {
-      const double2 s0 = __ldg(st2 + 2 * v), s1 = __ldg(st2 + 2 * v + 1);
-      const double2 d0 = __ldcg(dy2 + 2 * v);
-      int2 d1 = make_int2(0, 0);
-      if (CONSTR) d1 = __ldcg(reinterpret_cast<const int2*>(dy2 + 2 * v + 1));
-      double x = eval_vm<CONSTR>(a, r, v, d0.x, d0.y, d1.x, d1.y, s0.x, s0.y, s1.x, s1.y, false);
-      if (x > f[TOPK - 1]) {  // v ascends within a thread: strict > keeps the lower v on ties
-        f[TOPK - 1] = x; vv[TOPK - 1] = v;
+    const int O = a.of.O;
+#pragma unroll 1
+    for (int ci = 0; ci < CPW; ci++) {
+      const int c = warp + ci * NW;
+      double f[TOPK];
+      int vv[TOPK];
 #pragma unroll
-        for (int i = TOPK - 1; i > 0; i--) {
-          if (f[i] > f[i - 1]) {
-            double tf = f[i]; f[i] = f[i - 1]; f[i - 1] = tf;
-            int tv = vv[i]; vv[i] = vv[i - 1]; vv[i - 1] = tv;
+      for (int i = 0; i < TOPK; i++) { f[i] = 0.0; vv[i] = 0x7fffffff; }
+      constexpr int U = 5;  // VMs in flight per lane
+      for (int v0 = 32 * c + lane; v0 < O; v0 += U * 1024) {
+        double2 d0[U];
+        int2 d1[U];
+        double lc[U], lm[U], rc[U], rm[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+          const int v = v0 + u * 1024;
+          d0[u] = make_double2(0.0, 0.0);
+          d1[u] = make_int2(0, 0);
+          lc[u] = lm[u] = rc[u] = rm[u] = 0.0;
+          if (v < O) {
+            d0[u] = __ldcg(dy2 + 2 * v);
+            if (CONSTR) d1[u] = __ldcg(reinterpret_cast<const int2*>(dy2 + 2 * v + 1));
+            if (es.lc) { lc[u] = es.lc[v]; lm[u] = es.lm[v]; rc[u] = es.rc[v]; rm[u] = es.rm[v]; }
+            else {
+              const double2 s0 = __ldg(st2 + 2 * v), s1 = __ldg(st2 + 2 * v + 1);
+              lc[u] = s0.x; lm[u] = s0.y; rc[u] = s1.x; rm[u] = s1.y;
+            }
           }
         }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+          const int v = v0 + u * 1024;
+          if (v >= O) break;
+          const double x = eval_vm<CONSTR>(a, r, v, d0[u].x, d0[u].y, d1[u].x, d1[u].y, lc[u], lm[u],
+                                           rc[u], rm[u], false);
+          if (x > f[TOPK - 1]) {  // v ascends within a lane: strict > keeps the lower v on ties
+            f[TOPK - 1] = x; vv[TOPK - 1] = v;
+#pragma unroll
+            for (int i = TOPK - 1; i > 0; i--) {
+              if (f[i] > f[i - 1]) {
+                double tf = f[i]; f[i] = f[i - 1]; f[i - 1] = tf;
+                int tv = vv[i]; vv[i] = vv[i - 1]; vv[i - 1] = tv;
+              }
+            }
+          }
+        }
+      }
+      // the chunk's sorted top-TOPK: lane i ends up with entry i
+      double of = 0.0;
+      int ov = -1;
+#pragma unroll 1
+      for (int i = 0; i < TOPK; i++) {
+        unsigned wk;
+        int wl;
+        const double wf = warp_argmax(f[0], (unsigned)vv[0], wk, wl);
+        if (!(wf > 0.0)) break;
+        any = true;
+        if (lane == i) { of = wf; ov = (int)wk; }
+        if (lane == wl) {
+#pragma unroll
+          for (int q = 0; q < TOPK - 1; q++) { f[q] = f[q + 1]; vv[q] = vv[q + 1]; }
+          f[TOPK - 1] = 0.0; vv[TOPK - 1] = 0x7fffffff;
+        }
+      }
+      if (lane < TOPK) {
+        __stcg(rf + lane * 32 + c, of);
+        __stcg(rv + lane * 32 + c, ov);
       }
     }
   }
   long long e1 = PROF ? clock64() : 0;
-  const int any = __syncthreads_or(f[0] > 0.0 ? 1 : 0);
-  if (any) {
-    // tree merge across the 8 warps: 3 levels
-#pragma unroll
-    for (int step = 1; step < RES_THREADS / 32; step <<= 1) {
-      if ((warp & (2 * step - 1)) == step) {
-#pragma unroll
-        for (int i = 0; i < TOPK; i++) { E.f[warp][i][lane] = f[i]; E.v[warp][i][lane] = vv[i]; }
-      }
-      __syncthreads();
-      if ((warp & (2 * step - 1)) == 0) merge_list(f, vv, E, warp + step, lane);
-      __syncthreads();
-    }
-  }
-  long long e2 = PROF ? clock64() : 0;
-  if (warp == 0) {
-    unsigned char* row = a.rows + ((size_t)(blk & 1) * a.bmax + ib) * ROW_BYTES;
-    if (any || grp) {
-      double* rf = reinterpret_cast<double*>(row);
-      int32_t* rv = reinterpret_cast<int32_t*>(row + ROW_V_OFF);
-#pragma unroll
-      for (int i = 0; i < TOPK; i++) {
-        __stcg(rf + i * 32 + lane, f[i]);
-        __stcg(rv + i * 32 + lane, vv[i]);
-      }
-    }
-    if (lane == 0) {
-      __stcg(a.feas + (size_t)(blk & 1) * a.bmax + ib, (uint8_t)((any || grp) ? 1 : 0));
-      __threadfence();
-      atomicAdd(a.rows_ready + blk, 1u);
-    }
+  __syncwarp();
+  if (lane == 0) {
+    // feasibility stamp: block + 1 (stale stamps of the buffer's previous blocks are smaller)
+    if (any) atomicMax(a.feas + (size_t)(blk & 1) * a.bmax + ib, blk + 1);
+    __threadfence();
+    atomicAdd(a.rows_ready + blk, 1u);  // one arrival per (row, warp)
   }
   if (PROF) {
     long long e3 = clock64();
-    ep[0] += (unsigned long long)(e1 - e0); ep[1] += (unsigned long long)(e2 - e1);
-    ep[2] += (unsigned long long)(e3 - e2);
+    ep[0] += (unsigned long long)(e1 - e0); ep[2] += (unsigned long long)(e3 - e1);
   }
 }
 
@@ -504,7 +547,9 @@ struct Cand {  // one candidate VM with its state at the result's version
 
 struct SpecOut {
   int type, s, n, complete;  // type: Q_JOB / Q_END / Q_EXIT (the commit warp waits on the result flag only)
-  Cand c[KC];
+  double zf;                 // bound: every unchanged VM outside c[] is no better than (zf, zv)
+  int zv, pad;
+  Cand c[KC];                // unsorted
 };
 
 struct ResolverShared {
@@ -527,24 +572,6 @@ struct ResolverShared {
   volatile int out_done, blk_c0, last_b;  // END bookkeeping shared by the commit warps
   unsigned long long n_rescan, n_trunc;
 };
-
-__device__ __forceinline__ double warp_max_f64(double f) {  // f >= 0
-  unsigned hi = (unsigned)__double2hiint(f);
-  unsigned mh = __reduce_max_sync(0xffffffffu, hi);
-  unsigned lo = hi == mh ? (unsigned)__double2loint(f) : 0u;
-  unsigned ml = __reduce_max_sync(0xffffffffu, lo);
-  return __hiloint2double((int)mh, (int)ml);
-}
-
-// argmax over lanes of (f desc, key asc); key < 0xffffffff.  Returns the winning
-// fitness (0 => nobody), wk = its key, wl = its lane.
-__device__ __forceinline__ double warp_argmax(double f, unsigned key, unsigned& wk, int& wl) {
-  const double wf = warp_max_f64(f);
-  const unsigned k2 = (f == wf && wf > 0.0) ? key : 0xffffffffu;
-  wk = __reduce_min_sync(0xffffffffu, k2);
-  wl = __ffs(__ballot_sync(0xffffffffu, k2 == wk)) - 1;
-  return wf;
-}
 
 // A lane's working set during a spec: a sorted list of candidates plus two
 // "sentinels" that bound everything the lane is responsible for but does not
@@ -633,32 +660,43 @@ __device__ __forceinline__ void spec_job(const MatchArgs& a, ResolverShared& S, 
     const int vm = S.l_vm[idx];
     if (latest.get(vm) == e) L.insert(eval_log<CONSTR>(a, r, S, idx, vm), vm, e);
   }
+  // Candidate set: up to `depth` VMs such that everything left out is worse than the
+  // bound z (the best entry or sentinel still exposed by some lane).  The set is NOT
+  // sorted: heads that beat everything any lane keeps back are taken all at once.
   int n = 0, complete = 0;
   double cf = 0.0;
   int cv = 0, ce = -1;  // lane q keeps candidate q
-  for (int round = 0; round < depth;) {
-    // a lane exposes its head unless one of its sentinels is strictly better
-    double hf = L.f[0];
-    int hv = L.v[0];
-    bool sent = false, is_cb = false;
-    if (L.cbf > 0.0 && better(L.cbf, L.cbv, hf, hv)) { hf = L.cbf; hv = L.cbv; sent = true; is_cb = true; }
-    if (L.dbf > 0.0 && better(L.dbf, L.dbv, hf, hv)) { hf = L.dbf; hv = L.dbv; sent = true; is_cb = false; }
-    // key: sentinels win ties against real candidates of the same (f, v)
-    const unsigned key = ((unsigned)hv << 1) | (sent ? 0u : 1u);
-    unsigned wk;
-    int wl;
-    const double wf = warp_argmax(hf, key, wk, wl);
-    if (!(wf > 0.0)) { complete = 1; break; }
-    if ((wk & 1u) == 0u) {  // a sentinel wins
-      const bool wcb = __shfl_sync(0xffffffffu, is_cb ? 1 : 0, wl) != 0;
-      if (!wcb || round >= exact_rounds) { if (lane == 0) atomicAdd(&S.n_trunc, 1ull); break; }
+  while (n < depth) {
+    const double hf = L.f[0];
+    const int hv = L.v[0];
+    // the lane's better sentinel
+    double sf = L.cbf;
+    int sv = L.cbv;
+    bool s_cb = true;
+    if (L.dbf > 0.0 && better(L.dbf, L.dbv, sf, sv)) { sf = L.dbf; sv = L.dbv; s_cb = false; }
+    const bool head_sent = sf > 0.0 && better(sf, sv, hf, hv);  // head hidden behind a sentinel
+    // what the lane keeps back when its head is taken
+    double rf = sf;
+    int rv = sv;
+    if (!head_sent && L.f[1] > 0.0 && better(L.f[1], L.v[1], rf, rv)) { rf = L.f[1]; rv = L.v[1]; }
+    const double mf = warp_max_f64(rf);
+    const int mv = (int)__reduce_min_sync(0xffffffffu, (rf == mf && mf > 0.0) ? (unsigned)rv : 0xffffffffu);
+    const bool qual = !head_sent && hf > 0.0 && (!(mf > 0.0) || better(hf, hv, mf, mv));
+    unsigned q = __ballot_sync(0xffffffffu, qual);
+    if (q == 0u) {
+      const unsigned anyh = __ballot_sync(0xffffffffu, hf > 0.0 || sf > 0.0);
+      if (anyh == 0u) { complete = 1; break; }
+      // a sentinel dominates every head: the lane that holds it
+      const int wl = __ffs(__ballot_sync(0xffffffffu, rf == mf && rv == mv)) - 1;
+      const bool wcb = __shfl_sync(0xffffffffu, (s_cb && rf == sf && rv == sv) ? 1 : 0, wl) != 0;
+      if (!wcb || n >= exact_rounds) { if (lane == 0) atomicAdd(&S.n_trunc, 1ull); break; }
       // exact re-scan of chunk wl: clean VMs strictly worse than its row's last entry
       const double bf = __shfl_sync(0xffffffffu, L.cbf, wl);
       const int bv = __shfl_sync(0xffffffffu, L.cbv, wl);
       if (lane == wl) { L.cbf = 0.0; L.cbv = 0x7fffffff; }
       const double2* st2 = reinterpret_cast<const double2*>(a.of.vs);
       const double2* dy2 = reinterpret_cast<const double2*>(snapd);
-      for (int v = wl + 32 * lane; v < a.of.O; v += 32 * 32) {
+      for (int v = 32 * wl + lane; v < a.of.O; v += 32 * 32) {  // tiles wl, wl + 32, ...
         if (latest.get(v) >= lo) continue;
         const double2 s0 = __ldg(st2 + 2 * v), s1 = __ldg(st2 + 2 * v + 1);
         const double2 d0 = __ldcg(dy2 + 2 * v);
@@ -668,15 +706,37 @@ __device__ __forceinline__ void spec_job(const MatchArgs& a, ResolverShared& S, 
         if (x > 0.0 && better(bf, bv, x, v)) L.insert(x, v, -1);
       }
       if (lane == 0) atomicAdd(&S.n_rescan, 1ull);
-      continue;  // same round again
+      continue;
     }
-    const double xf = __shfl_sync(0xffffffffu, L.f[0], wl);
-    const int xv = __shfl_sync(0xffffffffu, L.v[0], wl);
-    const int xe = __shfl_sync(0xffffffffu, L.e[0], wl);
-    if (lane == n) { cf = xf; cv = xv; ce = xe; }
-    if (lane == wl) L.pop();
-    n++;
-    round++;
+    int cnt = __popc(q);
+    if (cnt > depth - n) {
+      // more heads qualify than fit: take the single best of them (keeps depth == 1 exact)
+      unsigned wk;
+      int wl;
+      warp_argmax(qual ? hf : 0.0, (unsigned)hv, wk, wl);
+      q = 1u << wl;
+      cnt = 1;
+    }
+    const int t = lane - n;  // receiver t takes the head of the (t+1)-th qualifying lane
+    const int src = (t >= 0 && t < cnt) ? (int)__fns(q, 0, t + 1) : 0;
+    const double xf = __shfl_sync(0xffffffffu, hf, src);
+    const int xv = __shfl_sync(0xffffffffu, hv, src);
+    const int xe = __shfl_sync(0xffffffffu, L.e[0], src);
+    if (t >= 0 && t < cnt) { cf = xf; cv = xv; ce = xe; }
+    if ((q >> lane) & 1u) L.pop();
+    n += cnt;
+  }
+  // bound: the best entry or sentinel still exposed
+  double zf;
+  int zv;
+  {
+    double ef = L.f[0];
+    int ev = L.v[0];
+    if (L.cbf > 0.0 && better(L.cbf, L.cbv, ef, ev)) { ef = L.cbf; ev = L.cbv; }
+    if (L.dbf > 0.0 && better(L.dbf, L.dbv, ef, ev)) { ef = L.dbf; ev = L.dbv; }
+    zf = warp_max_f64(ef);
+    zv = (int)__reduce_min_sync(0xffffffffu, (ef == zf && zf > 0.0) ? (unsigned)ev : 0xffffffffu);
+    if (!(zf > 0.0)) complete = 1;
   }
   if (lane < n) {
     Cand& c = out.c[lane];
@@ -695,7 +755,7 @@ __device__ __forceinline__ void spec_job(const MatchArgs& a, ResolverShared& S, 
       c.lc = s0.x; c.lm = s0.y; c.rc = s1.x; c.rm = s1.y;
     }
   }
-  if (lane == 0) { out.type = Q_JOB; out.s = s; out.n = n; out.complete = complete; }
+  if (lane == 0) { out.type = Q_JOB; out.s = s; out.n = n; out.complete = complete; out.zf = zf; out.zv = zv; }
   __syncwarp();
 }
 
@@ -772,15 +832,15 @@ __device__ void driver_warp(const MatchArgs& a, ResolverShared& S) {
     if (k0 >= a.n_cons) break;
     const int nj = min(S.bk_ring[(b + 1) & 7], a.n_cons) - k0;
     if (lane == 0)
-      while (ld_acquire_u32(a.rows_ready + b) < (unsigned)nj) __nanosleep(20);
+      while (ld_acquire_u32(a.rows_ready + b) < (unsigned)nj * NW) __nanosleep(20);
     __syncwarp();
     // rows b ready => END(b-2) was processed => the start of block b-1 is recorded
     const int lo = b == 0 ? 0 : S.lo_ring[(b - 1) & 3];
-    const uint8_t* feas = a.feas + (size_t)(b & 1) * a.bmax;
+    const int32_t* feas = a.feas + (size_t)(b & 1) * a.bmax;
     for (int base = 0; base < nj; base += 32) {
       const int i = base + lane;
       const bool valid = i < nj;
-      const bool fz = valid && __ldcg(feas + i) != 0;
+      const bool fz = valid && __ldcg(feas + i) == b + 1;
       // jobs with no feasible VM at the snapshot are unplaceable now too (resources
       // and count constraints only tighten within a cycle): skip them wholesale.
       if (valid && !fz) { a.assign[k0 + i] = -1; a.fail[k0 + i] = COOK_FAIL_RESOURCES; }
@@ -973,8 +1033,11 @@ __device__ void commit_warp(const MatchArgs& a, ResolverShared& S, const Latest 
     const bool grp = CONSTR && qe.grp;
     // The lane that holds the winner's pre-placement state appends the log entry.
     int wv = -1, writer = 0, c = 0;
-    Cand w;
-    w.ac = w.am = w.lc = w.lm = w.rc = w.rm = 0.0; w.an = w.pu = 0;
+    bool from_y = true;
+    Cand y;  // this lane's listed candidate (or the uniform winner of the slow paths)
+    Cand x;  // this lane's log entry (VM changed since the result's version)
+    x.vm = 0; x.ac = x.am = x.lc = x.lm = x.rc = x.rm = 0.0; x.an = x.pu = 0;
+    y = x;
     long long t2 = 0;
     if (grp) {
       while (S.gdone != g) __nanosleep(20);
@@ -982,15 +1045,16 @@ __device__ void commit_warp(const MatchArgs& a, ResolverShared& S, const Latest 
       t2 = PROF ? clock64() : 0;
       c = S.ncommit;
       const QEntry q2 = qe;
-      wv = resolve_group_job<CONSTR>(a, S, latest, q2, w);  // w uniform across lanes
+      wv = resolve_group_job<CONSTR>(a, S, latest, q2, y);  // y uniform across lanes
       n_group++;
     } else {
       const int s = R->s, n = R->n;
+      const bool r_complete = R->complete != 0;
+      const double r_zf = R->zf;
+      const int r_zv = R->zv;
       const int el = s + lane;
-      Cand y = R->c[lane & (KC - 1)];  // this lane's listed candidate
+      y = R->c[lane & (KC - 1)];
       static_assert(KC <= 32 && (KC & (KC - 1)) == 0, "one candidate per lane");
-      Cand x;                          // this lane's log entry (VM changed since s)
-      x.vm = 0; x.ac = x.am = x.lc = x.lm = x.rc = x.rm = 0.0; x.an = x.pu = 0;
       double xf = 0.0;
       int c_seen = s;
       long long t1 = PROF ? clock64() : 0;
@@ -1024,37 +1088,34 @@ __device__ void commit_warp(const MatchArgs& a, ResolverShared& S, const Latest 
       const int lv = use_y ? y.vm : (xin ? x.vm : 0x7fffffff);
       int xv, wl;
       const double wf = warp_argmax_fast(lf, lv, xv, wl);
-      // everything unlisted and unchanged is worse than the list's last entry: the
-      // winner is exact when the list is complete or it is no worse than that entry
-      bool need_fallback = !R->complete;
-      if (need_fallback && n > 0 && wf > 0.0) {
-        const double zf = __shfl_sync(0xffffffffu, y.f, n - 1);
-        const int zv = __shfl_sync(0xffffffffu, y.vm, n - 1);
-        if (!better(zf, zv, wf, xv)) need_fallback = false;
-      }
-      if (need_fallback) {
-        // recompute at the current version (exact): its first candidate is the answer
+      // every unchanged VM outside the candidate set is no better than the bound z:
+      // the winner is exact when the set is complete or it beats z
+      const bool exact = r_complete || (wf > 0.0 && better(wf, xv, r_zf, r_zv));
+      if (exact) {
+        n_fast++;
+        if (wf > 0.0) { wv = xv; writer = wl; from_y = use_y; }
+      } else {
+        // recompute at the current version (exact): its one candidate is the answer
         const QEntry q2 = qe;
         spec_job_fallback<CONSTR>(a, S, latest, q2, c);
-        if (S.res[RING].n > 0) { w = S.res[RING].c[0]; wv = w.vm; writer = 0; }
+        if (S.res[RING].n > 0) { y = S.res[RING].c[0]; wv = y.vm; writer = 0; from_y = true; }
         n_fallback++;
-      } else {
-        n_fast++;
-        if (wf > 0.0) {
-          wv = xv; writer = wl;
-          const bool wy = __shfl_sync(0xffffffffu, use_y ? 1 : 0, wl) != 0;
-          w = wy ? y : x;
-        }
       }
     }
     if (wv >= 0) {
       if (lane == writer) {
         const int idx = c & (LOGN - 1);
         S.l_vm[idx] = wv;
-        S.l_ac[idx] = w.ac + r.c; S.l_am[idx] = w.am + r.m;
-        S.l_lc[idx] = w.lc; S.l_lm[idx] = w.lm; S.l_rc[idx] = w.rc; S.l_rm[idx] = w.rm;
-        S.l_an[idx] = w.an + 1; S.l_pu[idx] = w.pu + r.ports;
-        S.l_k[idx] = k; S.l_pu0[idx] = w.pu;
+        if (from_y) {
+          S.l_ac[idx] = y.ac + r.c; S.l_am[idx] = y.am + r.m;
+          S.l_lc[idx] = y.lc; S.l_lm[idx] = y.lm; S.l_rc[idx] = y.rc; S.l_rm[idx] = y.rm;
+          S.l_an[idx] = y.an + 1; S.l_pu[idx] = y.pu + r.ports; S.l_pu0[idx] = y.pu;
+        } else {
+          S.l_ac[idx] = x.ac + r.c; S.l_am[idx] = x.am + r.m;
+          S.l_lc[idx] = x.lc; S.l_lm[idx] = x.lm; S.l_rc[idx] = x.rc; S.l_rm[idx] = x.rm;
+          S.l_an[idx] = x.an + 1; S.l_pu[idx] = x.pu + r.ports; S.l_pu0[idx] = x.pu;
+        }
+        S.l_k[idx] = k;
         latest.set(wv, c);
         fence_cta();
         S.ncommit = c + 1;
@@ -1113,26 +1174,45 @@ __global__ void __launch_bounds__(RES_THREADS, 1) match_kernel(MatchArgs a) {
     // warps 0, 4, 8, 12 share one scheduler (warp id mod 4): the commit warps keep it to themselves
     if ((warp & 3) == 0 && (warp >> 2) < NCW) commit_warp<CONSTR, PROF>(a, S, latest, warp >> 2);
     else if (warp == 1) driver_warp<CONSTR>(a, S);
-    else spec_warp<CONSTR>(a, S, latest);
+    else if (warp < a.max_spec_warp) spec_warp<CONSTR>(a, S, latest);
   } else {
-    EvalShared& E = *reinterpret_cast<EvalShared*>(smem_raw);
+    EvalStatic es;
+    es.lc = es.lm = es.rc = es.rm = nullptr;
+    if (a.vs_in_smem) {  // static VM table -> shared memory, SoA (conflict-free 64-bit reads)
+      double* base = reinterpret_cast<double*>(smem_raw);
+      const size_t O = (size_t)a.of.O;
+      double* lc = base; double* lm = base + O; double* rc = base + 2 * O; double* rm = base + 3 * O;
+      for (int v = threadIdx.x; v < a.of.O; v += RES_THREADS) {
+        const VmStatic x = a.of.vs[v];
+        lc[v] = x.lc; lm[v] = x.lm; rc[v] = x.rc; rm[v] = x.rm;
+      }
+      __syncthreads();
+      es.lc = lc; es.lm = lm; es.rc = rc; es.rm = rm;
+    }
+    __shared__ int bk_s[2];
     const int n_eval = gridDim.x - 1;
     unsigned long long work = 0, wait = 0, work_q1 = 0, rows_q1 = 0, nblk_seen = 0;
     unsigned long long ep[3] = {0, 0, 0};
     for (int b = 0;; b++) {
       long long w0 = clock64();
       // rows of block b need S_{b-2}: published >= b-1 (which also covers bk0[b], bk0[b+1])
-      if (b >= 2) {
-        if (threadIdx.x == 0)
-          while ((int)ld_acquire_u32(a.published) < b - 1) __nanosleep(32);
-        __syncthreads();
+      if (threadIdx.x == 0) {
+        if (b >= 2) {
+          // relaxed polling (an acquire load would invalidate L1 on every poll), one fence after
+          while ((int)ld_relaxed_u32(a.published) < b - 1) __nanosleep(32);
+          __threadfence();
+        }
+        bk_s[0] = __ldcg(a.bk0 + b);
+        bk_s[1] = __ldcg(a.bk0 + b + 1);
       }
-      const int k0 = __ldcg(a.bk0 + b);
+      __syncthreads();
+      const int k0 = bk_s[0];
+      const int k1 = min(bk_s[1], a.n_cons);
+      __syncthreads();  // bk_s is rewritten for the next block
       if (k0 >= a.n_cons) break;
-      const int k1 = min(__ldcg(a.bk0 + b + 1), a.n_cons);
       long long w1 = clock64();
       for (int k = k0 + (int)blockIdx.x - 1; k < k1; k += n_eval)
-        evaluate_row<CONSTR, PROF>(a, k, b, k - k0, E, ep);
+        evaluate_row<CONSTR, PROF>(a, k, b, k - k0, es, ep);
       wait += (unsigned long long)(w1 - w0);
       const unsigned long long dt = (unsigned long long)(clock64() - w1);
       work += dt;
@@ -1561,7 +1641,7 @@ static int32_t build_plan(cook_pool* pool, MatchPlan* mp, const int32_t* ranked_
   sz.add<uint8_t>(n_ranked + 1);
   sz.add<int32_t>(NC + 1); sz.add<double>(NC + 1); sz.add<double>(NC + 1); sz.add<uint8_t>(NC + 1);
   sz.add<unsigned char>((size_t)2 * bmax * ROW_BYTES); sz.add<double>(NC + bmax + 1); sz.add<int32_t>(NC + bmax + 1);
-  sz.add<uint8_t>(2 * bmax + 16); sz.add<unsigned>(max_blocks + 8); sz.add<int32_t>(max_blocks + 8);
+  sz.add<int32_t>(2 * bmax + 16); sz.add<unsigned>(max_blocks + 8); sz.add<int32_t>(max_blocks + 8);
   sz.add<int32_t>(NC + 1); sz.add<int32_t>(NC + 1); sz.add<uint8_t>(NC + 1);
   sz.add<int32_t>(NC + 1); sz.add<int32_t>((size_t)NC * std::max(max_ports, 1) + 1);
   sz.add<int32_t>(O + 1);
@@ -1671,7 +1751,7 @@ static int32_t build_plan(cook_pool* pool, MatchPlan* mp, const int32_t* ranked_
   mp->d_kg = ar.take<double>(NC + bmax + 1);
   mp->d_kports = ar.take<int32_t>(NC + bmax + 1);
   ma.kg = mp->d_kg; ma.kports = mp->d_kports;
-  ma.feas = ar.take<uint8_t>(2 * bmax + 16);
+  ma.feas = ar.take<int32_t>(2 * bmax + 16);
   ma.rows_ready = ar.take<unsigned>(max_blocks + 8);
   ma.bk0 = ar.take<int32_t>(max_blocks + 8);
   mp->max_blocks = max_blocks;
@@ -1694,6 +1774,8 @@ static int32_t build_plan(cook_pool* pool, MatchPlan* mp, const int32_t* ranked_
   if (const char* ei = getenv("COOK_ISOLATE")) ma.isolate_commit = atoi(ei);
   ma.lookahead = 16;
   ma.poll_ns = 200;
+  ma.max_spec_warp = RES_THREADS / 32;
+  if (const char* ew = getenv("COOK_MAX_SPEC_WARP")) ma.max_spec_warp = atoi(ew);
   if (const char* ep = getenv("COOK_POLL_NS")) ma.poll_ns = atoi(ep);
   if (const char* el = getenv("COOK_LOOKAHEAD")) { int v = atoi(el); if (v >= 2 && v <= RING) ma.lookahead = v; }
   mp->J = J; mp->O = O; mp->U = U; mp->n_ranked = n_ranked; mp->NC = NC; mp->max_ports = max_ports;
@@ -1721,6 +1803,7 @@ static int32_t run_plan(cook_pool* pool, MatchPlan* mp, int32_t* out_considerabl
   CK(pool, cudaMemsetAsync(mp->d_stats, 0, sizeof(unsigned long long) * 32, st));
   CK(pool, cudaMemsetAsync(mp->d_counters, 0, sizeof(int32_t) * 16, st));
   CK(pool, cudaMemsetAsync(ma.rows_ready, 0, sizeof(unsigned) * (mp->max_blocks + 8), st));
+  CK(pool, cudaMemsetAsync(ma.feas, 0, sizeof(int32_t) * (2 * (size_t)mp->ma.bmax + 16), st));
   {  // first three block bounds; the resolver appends the rest while it runs
     mp->bk_init[0] = 0; mp->bk_init[1] = mp->B; mp->bk_init[2] = 2 * mp->B;
     CK(pool, cudaMemcpyAsync(ma.bk0, mp->bk_init, sizeof(mp->bk_init), cudaMemcpyHostToDevice, st));
@@ -1783,10 +1866,14 @@ static int32_t run_plan(cook_pool* pool, MatchPlan* mp, int32_t* out_considerabl
       CK(pool, cudaMemsetAsync(ma.fail, COOK_FAIL_CONSTRAINT, n_cons, st));
       // resolver CTA: shared structures + the per-VM newest-log-entry table (global when too big)
       const size_t res_base = (sizeof(ResolverShared) + 15) & ~size_t(15);
-      size_t smem = std::max(res_base, sizeof(EvalShared));
+      size_t smem = res_base;
       ma.latest_global = nullptr;
       if (res_base + sizeof(int) * (size_t)O <= 200 * 1024) smem = std::max(smem, res_base + sizeof(int) * (size_t)O);
       else ma.latest_global = mp->d_latest;
+      // evaluator CTAs: the static VM table (4 f64 per VM, SoA) when it fits
+      ma.vs_in_smem = (size_t)O * 32 <= 220 * 1024 ? 1 : 0;
+      if (getenv("COOK_NO_SMEM_STATIC")) ma.vs_in_smem = 0;
+      if (ma.vs_in_smem) smem = std::max(smem, (size_t)O * 32);
       void* kfn = mp->constr ? (prof_on ? (void*)match_kernel<true, true> : (void*)match_kernel<true, false>)
                              : (prof_on ? (void*)match_kernel<false, true> : (void*)match_kernel<false, false>);
       CK(pool, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1825,8 +1912,8 @@ static int32_t run_plan(cook_pool* pool, MatchPlan* mp, int32_t* out_considerabl
   CK(pool, cudaStreamSynchronize(st));
   if (prof_on) {
     const char* nm[24] = {"fast", "chunk_rescan", "group_jobs", "matched", "fallbacks", "trunc_specs",
-                          "skipped", "-", "c_wait_result", "c_follow_log", "c_decide_commit", "-",
-                          "c_end_block", "-", "res_total", "-", "eval_work", "eval_wait",
+                          "skipped", "-", "c_wait_result", "c_follow_log", "c_decide_commit", "c_to_argmax",
+                          "c_end_block", "c_to_select", "res_total", "-", "eval_work", "eval_wait",
                           "eval_loop", "eval_sync", "eval_merge", "eval_work_q1", "eval_rowslots_q1", "blocks"};
     for (int i = 0; i < 24; i++) fprintf(stderr, "[cook_prof] %-14s %llu\n", nm[i], hstats[i]);
   }
