@@ -45,7 +45,18 @@ constexpr int ROW_BYTES = TOPK * 32 * (8 + 4);       // 3072 B per job
 // Per-VM state is AoS, 32 B per record, so one record is two 128-bit loads and a
 // clean candidate's state can be staged with 16-byte async copies.
 struct __align__(32) VmStatic { double lc, lm, rc, rm; };
-struct __align__(32) VmDyn { double ac, am; int an, pu; int pad0, pad1; };
+// Dynamic record: cpus/mem assigned this cycle + the (static) correctly rounded
+// reciprocals of the fitness denominators, yc = RN(1/(lc+rc)), ym = RN(1/(lm+rm)):
+// x/den is then q0 = x*y, q = fma(fma(-den, q0, x), y, q0) == RN(x/den) (Markstein's
+// correction; checked against IEEE division in tests/test_fastdiv.py); y == 0 marks
+// denominators outside the safe range (true division is used for those).
+struct __align__(32) VmDyn { double ac, am, yc, ym; };
+struct __align__(8) VmCnt { int an, pu; };  // tasks assigned this cycle, ports used (constraint kernel)
+
+struct VmState {  // everything one fit evaluation needs about a VM
+  double ac, am, lc, lm, rc, rm, yc, ym;
+  int an, pu;
+};
 
 struct JobDev {   // columns in ORIGINAL job index space (may be null)
   const int32_t* user;
@@ -96,6 +107,7 @@ struct GroupDev {
 
 struct DynBuf {  // dynamic per-VM state, index space v, double buffered
   VmDyn* d[2];
+  VmCnt* n[2];
 };
 
 struct MatchArgs {
@@ -278,32 +290,58 @@ __device__ bool group_pass(const MatchArgs& a, const JobRegs& r, int v) {
   return true;
 }
 
-// FENZO 3a + 4 (see oracle): resource fit then cpuMemBinPacker fitness.
-__device__ __forceinline__ double fit_fitness(double jc, double jm, double ac, double am,
-                                              double lc, double lm, double rc, double rm) {
-  if (ac + jc > lc) return 0.0;
-  if (am + jm > lm) return 0.0;
-  double cpu_fit = ((jc + ac) + rc) / (lc + rc);
-  double mem_fit = ((jm + am) + rm) / (lm + rm);
-  return (cpu_fit + mem_fit) / 2.0;
+// x / den with y = RN(1 / den) (or 0 => plain division): three dependent f64 ops
+// instead of the ~10 of div.rn.f64, same correctly rounded result.
+__device__ __forceinline__ double div_y(double x, double den, double y) {
+  if (y == 0.0) return x / den;
+  const double q0 = x * y;
+  return fma(fma(-den, q0, x), y, q0);
+}
+__device__ __forceinline__ double safe_rcp(double den) {
+  return (den > 1e-100 && den < 1e100) ? 1.0 / den : 0.0;
 }
 
-// Full evaluation of (job, VM v) with explicit dynamic state.
+// FENZO 3a + 4 (see oracle): resource fit then cpuMemBinPacker fitness.
+__device__ __forceinline__ double fit_fitness(double jc, double jm, const VmState& st) {
+  const bool no = (st.ac + jc > st.lc) | (st.am + jm > st.lm);
+  const double cpu_fit = div_y((jc + st.ac) + st.rc, st.lc + st.rc, st.yc);
+  const double mem_fit = div_y((jm + st.am) + st.rm, st.lm + st.rm, st.ym);
+  return no ? 0.0 : (cpu_fit + mem_fit) * 0.5;
+}
+
+// Full evaluation of (job, VM v) against an explicit VM state.
 template <bool CONSTR>
-__device__ __forceinline__ double eval_vm(const MatchArgs& a, const JobRegs& r, int v, double ac,
-                                          double am, int an, int pu, double lc, double lm,
-                                          double rc, double rm, bool with_groups) {
+__device__ __forceinline__ double eval_vm(const MatchArgs& a, const JobRegs& r, int v, const VmState& st,
+                                          bool with_groups) {
   if (CONSTR) {
-    if (ac + r.c > lc) return 0.0;
-    if (am + r.m > lm) return 0.0;
+    if (st.ac + r.c > st.lc) return 0.0;
+    if (st.am + r.m > st.lm) return 0.0;
     if (r.ports > 0) {
       int tot = a.of.ports_total ? a.of.ports_total[a.of.perm[v]] : 0;
-      if (r.ports > tot - pu) return 0.0;
+      if (r.ports > tot - st.pu) return 0.0;
     }
-    if (!constraints_pass(a, r, v, an)) return 0.0;
+    if (!constraints_pass(a, r, v, st.an)) return 0.0;
     if (with_groups && !group_pass(a, r, v)) return 0.0;
   }
-  return fit_fitness(r.c, r.m, ac, am, lc, lm, rc, rm);
+  return fit_fitness(r.c, r.m, st);
+}
+
+// state of VM v at the snapshot of block blk (global memory / L2)
+template <bool CONSTR>
+__device__ __forceinline__ VmState load_snap(const MatchArgs& a, int blk, int v) {
+  const double2* st2 = reinterpret_cast<const double2*>(a.of.vs + v);
+  const double2* dy2 = reinterpret_cast<const double2*>(a.dyn.d[blk & 1] + v);
+  const double2 s0 = __ldg(st2), s1 = __ldg(st2 + 1);
+  const double2 d0 = __ldcg(dy2), d1 = __ldcg(dy2 + 1);
+  VmState st;
+  st.ac = d0.x; st.am = d0.y; st.yc = d1.x; st.ym = d1.y;
+  st.lc = s0.x; st.lm = s0.y; st.rc = s1.x; st.rm = s1.y;
+  st.an = 0; st.pu = 0;
+  if (CONSTR) {
+    const int2 c = __ldcg(reinterpret_cast<const int2*>(a.dyn.n[blk & 1] + v));
+    st.an = c.x; st.pu = c.y;
+  }
+  return st;
 }
 
 // ------------------------------------------------------------- PTX helpers
@@ -388,19 +426,17 @@ struct EvalStatic {  // static VM table in shared memory (SoA), or null => globa
 };
 
 template <bool CONSTR, bool PROF>
-__device__ void evaluate_row(const MatchArgs& a, int k, int blk, int ib, const EvalStatic& es,
-                             unsigned long long* ep) {
+__device__ void evaluate_row(const MatchArgs& a, const JobRegs& r, const bool grp, int blk, int ib,
+                             const EvalStatic& es, unsigned long long* ep) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   long long e0 = PROF ? clock64() : 0;
   const double2* st2 = reinterpret_cast<const double2*>(a.of.vs);
   const double2* dy2 = reinterpret_cast<const double2*>(a.dyn.d[blk & 1]);  // S_{b-2} = buffer b&1
-  const bool grp = CONSTR && (a.kflags[k] & 1);
   unsigned char* row = a.rows + ((size_t)(blk & 1) * a.bmax + ib) * ROW_BYTES;
   double* rf = reinterpret_cast<double*>(row);
   int32_t* rv = reinterpret_cast<int32_t*>(row + ROW_V_OFF);
   bool any = grp;  // group jobs are resolved against live group state, their rows stay empty
   if (!grp) {
-    const JobRegs r = load_job<CONSTR>(a, k);
     const int O = a.of.O;
 #pragma unroll 1
     for (int ci = 0; ci < CPW; ci++) {
@@ -409,24 +445,25 @@ __device__ void evaluate_row(const MatchArgs& a, int k, int blk, int ib, const E
       int vv[TOPK];
 #pragma unroll
       for (int i = 0; i < TOPK; i++) { f[i] = 0.0; vv[i] = 0x7fffffff; }
-      constexpr int U = 5;  // VMs in flight per lane
+      constexpr int U = 4;  // VMs in flight per lane
       for (int v0 = 32 * c + lane; v0 < O; v0 += U * 1024) {
-        double2 d0[U];
-        int2 d1[U];
-        double lc[U], lm[U], rc[U], rm[U];
+        VmState st[U];
 #pragma unroll
         for (int u = 0; u < U; u++) {
           const int v = v0 + u * 1024;
-          d0[u] = make_double2(0.0, 0.0);
-          d1[u] = make_int2(0, 0);
-          lc[u] = lm[u] = rc[u] = rm[u] = 0.0;
+          st[u].ac = st[u].am = st[u].yc = st[u].ym = st[u].lc = st[u].lm = st[u].rc = st[u].rm = 0.0;
+          st[u].an = st[u].pu = 0;
           if (v < O) {
-            d0[u] = __ldcg(dy2 + 2 * v);
-            if (CONSTR) d1[u] = __ldcg(reinterpret_cast<const int2*>(dy2 + 2 * v + 1));
-            if (es.lc) { lc[u] = es.lc[v]; lm[u] = es.lm[v]; rc[u] = es.rc[v]; rm[u] = es.rm[v]; }
+            const double2 d0 = __ldcg(dy2 + 2 * v), d1 = __ldcg(dy2 + 2 * v + 1);
+            st[u].ac = d0.x; st[u].am = d0.y; st[u].yc = d1.x; st[u].ym = d1.y;
+            if (CONSTR) {
+              const int2 cn = __ldcg(reinterpret_cast<const int2*>(a.dyn.n[blk & 1] + v));
+              st[u].an = cn.x; st[u].pu = cn.y;
+            }
+            if (es.lc) { st[u].lc = es.lc[v]; st[u].lm = es.lm[v]; st[u].rc = es.rc[v]; st[u].rm = es.rm[v]; }
             else {
               const double2 s0 = __ldg(st2 + 2 * v), s1 = __ldg(st2 + 2 * v + 1);
-              lc[u] = s0.x; lm[u] = s0.y; rc[u] = s1.x; rm[u] = s1.y;
+              st[u].lc = s0.x; st[u].lm = s0.y; st[u].rc = s1.x; st[u].rm = s1.y;
             }
           }
         }
@@ -434,8 +471,7 @@ __device__ void evaluate_row(const MatchArgs& a, int k, int blk, int ib, const E
         for (int u = 0; u < U; u++) {
           const int v = v0 + u * 1024;
           if (v >= O) break;
-          const double x = eval_vm<CONSTR>(a, r, v, d0[u].x, d0[u].y, d1[u].x, d1[u].y, lc[u], lm[u],
-                                           rc[u], rm[u], false);
+          const double x = eval_vm<CONSTR>(a, r, v, st[u], false);
           if (x > f[TOPK - 1]) {  // v ascends within a lane: strict > keeps the lower v on ties
             f[TOPK - 1] = x; vv[TOPK - 1] = v;
 #pragma unroll
@@ -476,8 +512,9 @@ __device__ void evaluate_row(const MatchArgs& a, int k, int blk, int ib, const E
   if (lane == 0) {
     // feasibility stamp: block + 1 (stale stamps of the buffer's previous blocks are smaller)
     if (any) atomicMax(a.feas + (size_t)(blk & 1) * a.bmax + ib, blk + 1);
-    __threadfence();
-    atomicAdd(a.rows_ready + blk, 1u);  // one arrival per (row, warp)
+    // one arrival per (row, warp); the release orders the warp's row stores (made
+    // visible to this lane by the __syncwarp above) before the count
+    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(a.rows_ready + blk), "r"(1u) : "memory");
   }
   if (PROF) {
     long long e3 = clock64();
@@ -486,37 +523,35 @@ __device__ void evaluate_row(const MatchArgs& a, int k, int blk, int ib, const E
 }
 
 // --------------------------------------------------------------- resolver
-// CTA 0 resolves the jobs in rank order, exactly, as a three-role pipeline:
+// CTA 0 resolves the jobs in rank order, exactly, as a pipeline of warp roles:
 //
-//   driver (warp 1)   turns the evaluators' per-block feasibility flags into an
+//   driver (warp 1)   turns the evaluators' per-block feasibility stamps into an
 //                     in-order QUEUE of entries (JOB / END-of-block / EXIT); at
-//                     most RING entries are in flight.
-//   spec (warps 2..)  each takes the next queue ticket and computes, against the
-//                     state at some VERSION s (= number of commits it saw), the
-//                     job's sorted top-KC candidate VMs with their states:
-//                     clean chunk candidates from the job's row merged with an
-//                     exact re-evaluation of every VM committed since the row's
-//                     snapshot (the commit LOG, an append-only ring).
-//   commit (warp 0)   consumes results in queue order.  For job i with version
-//                     s_i and c commits so far, the VMs changed since s_i are
-//                     exactly log[s_i, c) (<= RING-1 < 32 entries): one lane
-//                     re-evaluates each; the first candidate of the list that is
-//                     unchanged is the exact best among all unchanged VMs; argmax
-//                     of the two is Fenzo's choice.  It appends the placement to
-//                     the log.  If every listed candidate changed (and the list
-//                     is not complete) the commit warp recomputes the job at
-//                     version c itself (exact, rare).
+//                     most `lookahead` entries are in flight.
+//   spec (most warps) each takes the next queue ticket and computes, against the
+//                     state at some VERSION s (= commits it saw), a candidate set of
+//                     the job: clean chunk candidates from the job's row merged with
+//                     an exact re-evaluation of every VM committed since the row's
+//                     snapshot (the commit LOG, an append-only ring), plus a bound z
+//                     on everything left out.
+//   commit (warps 0,4,8,12) own the entries round-robin and form the serial chain.
+//                     Before its turn the owner re-evaluates the VMs committed since
+//                     s (one lane per log entry) and reduces its lanes' items to the
+//                     best two (b1, b2).  At its turn exactly the newest log entry is
+//                     new: every lane evaluates it redundantly, the winner is the
+//                     better of it and b1 (b2 if the entry re-used b1's VM) - no warp
+//                     collective on the chain - and is appended to the log.
 //
 // Validity of a log entry e for VM x is `latest[x] == e` (latest[] = index of
 // the newest entry per VM, monotone), so nothing is ever cleared: a VM is dirty
 // with respect to a block's snapshot iff latest[x] >= lo, lo = log size at the
 // start of the previous block.
-constexpr int MAXB = 512;             // max jobs per block
+constexpr int MAXB = 256;             // max jobs per block
 constexpr int LOGN = 2 * MAXB;        // commit-log ring (entries of two blocks)
 constexpr int RING = 32;              // queue entries / spec results in flight
 constexpr int KC = 16;                // candidates per spec result
 constexpr int LK = 8;                 // entries a lane keeps while building a result
-constexpr int NWARPS = RES_THREADS / 32;
+constexpr int NCW = 4;                // commit warps
 
 enum { Q_JOB = 0, Q_END = 1, Q_EXIT = 2 };
 
@@ -540,30 +575,34 @@ struct QEntry {
   int jports, jj, grp, row;   // row: index of the job inside its block
 };
 
+// One log entry, 80 B: a lane reads it with five 128-bit loads (conflict-free at
+// this stride when 8 consecutive entries are read by 8 lanes).
+struct __align__(16) LogEnt {
+  int vm, an, pu, k;
+  double ac, am, lc, lm, rc, rm, yc, ym;
+};
+
 struct Cand {  // one candidate VM with its state at the result's version
-  double f, ac, am, lc, lm, rc, rm;
-  int vm, e, an, pu;
+  double f;
+  VmState st;
+  int vm, e;
 };
 
 struct SpecOut {
-  int type, s, n, complete;  // type: Q_JOB / Q_END / Q_EXIT (the commit warp waits on the result flag only)
+  int type, s, n, complete;  // type: Q_JOB / Q_END / Q_EXIT (the commit warps wait on the result flag only)
   double zf;                 // bound: every unchanged VM outside c[] is no better than (zf, zv)
   int zv, pad;
   Cand c[KC];                // unsorted
 };
 
 struct ResolverShared {
-  // commit log, SoA
-  int32_t l_vm[LOGN];
-  double l_ac[LOGN], l_am[LOGN], l_lc[LOGN], l_lm[LOGN], l_rc[LOGN], l_rm[LOGN];
-  int32_t l_an[LOGN], l_pu[LOGN];
-  int32_t l_k[LOGN], l_pu0[LOGN];   // considerable index of the placed job, ports used before it
+  LogEnt log[LOGN];
   QEntry q[RING];
-  SpecOut res[RING + 1];          // [RING] = the commit warp's own fallback slot
+  SpecOut res[RING + 1];          // [RING] = the commit warps' fallback slot
   volatile int q_seq[RING];       // g+1 once queue entry g is filled
   volatile int res_seq[RING];     // g+1 once the result of entry g is ready
-  volatile int ncommit;           // log entries written
-  volatile int gdone;             // queue entries consumed by the commit warp
+  // chain word: (entries consumed by the commit warps) << 32 | (log entries written)
+  volatile unsigned long long chain;
   volatile int exit_g;            // queue index of the EXIT entry (-1 while running)
   int ticket;                     // next queue entry for the spec warps
   volatile int lo_ring[4];        // lo_ring[b & 3] = log size at the start of block b
@@ -572,6 +611,31 @@ struct ResolverShared {
   volatile int out_done, blk_c0, last_b;  // END bookkeeping shared by the commit warps
   unsigned long long n_rescan, n_trunc;
 };
+
+__device__ __forceinline__ int chain_gdone(unsigned long long w) { return (int)(w >> 32); }
+__device__ __forceinline__ int chain_ncommit(unsigned long long w) { return (int)(unsigned)w; }
+__device__ __forceinline__ unsigned long long chain_pack(int gdone, int ncommit) {
+  return ((unsigned long long)(unsigned)gdone << 32) | (unsigned)ncommit;
+}
+
+__device__ __forceinline__ VmState load_log(const LogEnt* e, int& vm, int& k) {
+  const int4 h = *reinterpret_cast<const int4*>(e);
+  const double2 a0 = *reinterpret_cast<const double2*>(&e->ac);
+  const double2 a1 = *reinterpret_cast<const double2*>(&e->lc);
+  const double2 a2 = *reinterpret_cast<const double2*>(&e->rc);
+  const double2 a3 = *reinterpret_cast<const double2*>(&e->yc);
+  VmState st;
+  vm = h.x; st.an = h.y; st.pu = h.z; k = h.w;
+  st.ac = a0.x; st.am = a0.y; st.lc = a1.x; st.lm = a1.y; st.rc = a2.x; st.rm = a2.y; st.yc = a3.x; st.ym = a3.y;
+  return st;
+}
+__device__ __forceinline__ void store_log(LogEnt* e, int vm, int k, const VmState& st) {
+  *reinterpret_cast<int4*>(e) = make_int4(vm, st.an, st.pu, k);
+  *reinterpret_cast<double2*>(&e->ac) = make_double2(st.ac, st.am);
+  *reinterpret_cast<double2*>(&e->lc) = make_double2(st.lc, st.lm);
+  *reinterpret_cast<double2*>(&e->rc) = make_double2(st.rc, st.rm);
+  *reinterpret_cast<double2*>(&e->yc) = make_double2(st.yc, st.ym);
+}
 
 // A lane's working set during a spec: a sorted list of candidates plus two
 // "sentinels" that bound everything the lane is responsible for but does not
@@ -617,24 +681,18 @@ struct LaneList {
   }
 };
 
-template <bool CONSTR>
-__device__ __forceinline__ double eval_log(const MatchArgs& a, const JobRegs& r, const ResolverShared& S,
-                                           int idx, int vm) {
-  return eval_vm<CONSTR>(a, r, vm, S.l_ac[idx], S.l_am[idx], S.l_an[idx], S.l_pu[idx], S.l_lc[idx],
-                         S.l_lm[idx], S.l_rc[idx], S.l_rm[idx], false);
-}
 
-// Sorted top-`depth` candidates of one job against the state at version s
-// (warp-wide).  Sentinel hits in the first `exact_rounds` rounds are resolved by
-// an exact chunk re-scan; later ones truncate the list (complete = 0).
+// Candidate set of one job against the state at version s (warp-wide): up to
+// `depth` VMs such that everything left out is no better than the bound z.
+// Sentinel hits while fewer than `exact_n` candidates are out are resolved by an
+// exact chunk re-scan; later ones truncate the set (complete = 0).
 template <bool CONSTR>
 __device__ __forceinline__ void spec_job(const MatchArgs& a, ResolverShared& S, const Latest latest, const QEntry& qe,
-                                         const int s, const int depth, const int exact_rounds, SpecOut& out) {
+                                         const int s, const int depth, const int exact_n, SpecOut& out) {
   const int lane = threadIdx.x & 31;
   JobRegs r;
   r.c = qe.jc; r.m = qe.jm; r.g = qe.jg; r.ports = qe.jports; r.j = qe.jj;
   const int lo = qe.lo, blk = qe.blk;
-  const VmDyn* snapd = a.dyn.d[blk & 1];
   const unsigned char* rowp = a.rows + ((size_t)(blk & 1) * a.bmax + qe.row) * ROW_BYTES;
   LaneList L;
   L.init();
@@ -656,13 +714,10 @@ __device__ __forceinline__ void spec_job(const MatchArgs& a, ResolverShared& S, 
   }
   // every VM committed since the snapshot, at its state as of version s
   for (int e = lo + lane; e < s; e += 32) {
-    const int idx = e & (LOGN - 1);
-    const int vm = S.l_vm[idx];
-    if (latest.get(vm) == e) L.insert(eval_log<CONSTR>(a, r, S, idx, vm), vm, e);
+    int vm, k;
+    const VmState st = load_log(&S.log[e & (LOGN - 1)], vm, k);
+    if (latest.get(vm) == e) L.insert(eval_vm<CONSTR>(a, r, vm, st, false), vm, e);
   }
-  // Candidate set: up to `depth` VMs such that everything left out is worse than the
-  // bound z (the best entry or sentinel still exposed by some lane).  The set is NOT
-  // sorted: heads that beat everything any lane keeps back are taken all at once.
   int n = 0, complete = 0;
   double cf = 0.0;
   int cv = 0, ce = -1;  // lane q keeps candidate q
@@ -689,20 +744,15 @@ __device__ __forceinline__ void spec_job(const MatchArgs& a, ResolverShared& S, 
       // a sentinel dominates every head: the lane that holds it
       const int wl = __ffs(__ballot_sync(0xffffffffu, rf == mf && rv == mv)) - 1;
       const bool wcb = __shfl_sync(0xffffffffu, (s_cb && rf == sf && rv == sv) ? 1 : 0, wl) != 0;
-      if (!wcb || n >= exact_rounds) { if (lane == 0) atomicAdd(&S.n_trunc, 1ull); break; }
+      if (!wcb || n >= exact_n) { if (lane == 0) atomicAdd(&S.n_trunc, 1ull); break; }
       // exact re-scan of chunk wl: clean VMs strictly worse than its row's last entry
       const double bf = __shfl_sync(0xffffffffu, L.cbf, wl);
       const int bv = __shfl_sync(0xffffffffu, L.cbv, wl);
       if (lane == wl) { L.cbf = 0.0; L.cbv = 0x7fffffff; }
-      const double2* st2 = reinterpret_cast<const double2*>(a.of.vs);
-      const double2* dy2 = reinterpret_cast<const double2*>(snapd);
       for (int v = 32 * wl + lane; v < a.of.O; v += 32 * 32) {  // tiles wl, wl + 32, ...
         if (latest.get(v) >= lo) continue;
-        const double2 s0 = __ldg(st2 + 2 * v), s1 = __ldg(st2 + 2 * v + 1);
-        const double2 d0 = __ldcg(dy2 + 2 * v);
-        int2 d1 = make_int2(0, 0);
-        if (CONSTR) d1 = __ldcg(reinterpret_cast<const int2*>(dy2 + 2 * v + 1));
-        const double x = eval_vm<CONSTR>(a, r, v, d0.x, d0.y, d1.x, d1.y, s0.x, s0.y, s1.x, s1.y, false);
+        const VmState st = load_snap<CONSTR>(a, blk, v);
+        const double x = eval_vm<CONSTR>(a, r, v, st, false);
         if (x > 0.0 && better(bf, bv, x, v)) L.insert(x, v, -1);
       }
       if (lane == 0) atomicAdd(&S.n_rescan, 1ull);
@@ -741,90 +791,57 @@ __device__ __forceinline__ void spec_job(const MatchArgs& a, ResolverShared& S, 
   if (lane < n) {
     Cand& c = out.c[lane];
     c.f = cf; c.vm = cv; c.e = ce;
-    if (ce >= 0) {
-      const int idx = ce & (LOGN - 1);
-      c.ac = S.l_ac[idx]; c.am = S.l_am[idx]; c.lc = S.l_lc[idx]; c.lm = S.l_lm[idx];
-      c.rc = S.l_rc[idx]; c.rm = S.l_rm[idx]; c.an = S.l_an[idx]; c.pu = S.l_pu[idx];
-    } else {
-      const double2* st2 = reinterpret_cast<const double2*>(a.of.vs + cv);
-      const double2 s0 = __ldg(st2), s1 = __ldg(st2 + 1);
-      const double2 d0 = __ldcg(reinterpret_cast<const double2*>(snapd + cv));
-      int2 d1 = make_int2(0, 0);
-      if (CONSTR) d1 = __ldcg(reinterpret_cast<const int2*>(snapd + cv) + 2);
-      c.ac = d0.x; c.am = d0.y; c.an = d1.x; c.pu = d1.y;
-      c.lc = s0.x; c.lm = s0.y; c.rc = s1.x; c.rm = s1.y;
-    }
+    if (ce >= 0) { int vm, k; c.st = load_log(&S.log[ce & (LOGN - 1)], vm, k); }
+    else c.st = load_snap<CONSTR>(a, blk, cv);
   }
   if (lane == 0) { out.type = Q_JOB; out.s = s; out.n = n; out.complete = complete; out.zf = zf; out.zv = zv; }
   __syncwarp();
 }
 
-// Exact placement of a group-constrained job against the live state (commit warp).
-// Returns the winning VM (or -1); the winner's pre-placement state lands in `w`.
-template <bool CONSTR>
-__device__ __noinline__ int resolve_group_job(const MatchArgs& a, ResolverShared& S, const Latest latest,
-                                 const QEntry& qe, Cand& w) {
-  const int lane = threadIdx.x & 31;
-  JobRegs r;
-  r.c = qe.jc; r.m = qe.jm; r.g = qe.jg; r.ports = qe.jports; r.j = qe.jj;
-  const VmDyn* snapd = a.dyn.d[qe.blk & 1];
-  const double2* st2 = reinterpret_cast<const double2*>(a.of.vs);
-  const double2* dy2 = reinterpret_cast<const double2*>(snapd);
-  double cf = 0.0;
-  int cv = 0x7fffffff, ce = -1;
-  for (int v = lane; v < a.of.O; v += 32) {
-    const int e = latest.get(v);
-    double f;
-    if (e >= qe.lo) {
-      const int idx = e & (LOGN - 1);
-      f = eval_vm<CONSTR>(a, r, v, S.l_ac[idx], S.l_am[idx], S.l_an[idx], S.l_pu[idx], S.l_lc[idx],
-                          S.l_lm[idx], S.l_rc[idx], S.l_rm[idx], true);
-    } else {
-      const double2 s0 = __ldg(st2 + 2 * v), s1 = __ldg(st2 + 2 * v + 1);
-      const double2 d0 = __ldcg(dy2 + 2 * v);
-      int2 d1 = make_int2(0, 0);
-      if (CONSTR) d1 = __ldcg(reinterpret_cast<const int2*>(dy2 + 2 * v + 1));
-      f = eval_vm<CONSTR>(a, r, v, d0.x, d0.y, d1.x, d1.y, s0.x, s0.y, s1.x, s1.y, true);
-    }
-    if (f > cf) { cf = f; cv = v; ce = e >= qe.lo ? e : -1; }  // v ascends per lane: strict > keeps the lowest
-  }
-  unsigned wk;
-  int wl;
-  const double wf = warp_argmax(cf, (unsigned)cv, wk, wl);
-  if (!(wf > 0.0)) return -1;
-  const int wv = (int)wk;
-  const int we = __shfl_sync(0xffffffffu, ce, wl);
-  w.f = wf; w.vm = wv; w.e = we;
-  if (we >= 0) {
-    const int idx = we & (LOGN - 1);
-    w.ac = S.l_ac[idx]; w.am = S.l_am[idx]; w.lc = S.l_lc[idx]; w.lm = S.l_lm[idx];
-    w.rc = S.l_rc[idx]; w.rm = S.l_rm[idx]; w.an = S.l_an[idx]; w.pu = S.l_pu[idx];
-  } else {
-    const double2 s0 = __ldg(st2 + 2 * wv), s1 = __ldg(st2 + 2 * wv + 1);
-    const double2 d0 = __ldcg(dy2 + 2 * wv);
-    int2 d1 = make_int2(0, 0);
-    if (CONSTR) d1 = __ldcg(reinterpret_cast<const int2*>(dy2 + 2 * wv + 1));
-    w.ac = d0.x; w.am = d0.y; w.an = d1.x; w.pu = d1.y;
-    w.lc = s0.x; w.lm = s0.y; w.rc = s1.x; w.rm = s1.y;
-  }
-  return wv;
-}
-
-// the commit warp's rare exact recomputation, kept out of its hot loop
+// the commit warps' rare exact recomputation, kept out of their hot loop
 template <bool CONSTR>
 __device__ __noinline__ void spec_job_fallback(const MatchArgs& a, ResolverShared& S, const Latest latest,
                                                const QEntry& qe, const int s) {
   spec_job<CONSTR>(a, S, latest, qe, s, 1, 1, S.res[RING]);
 }
 
-// ---- driver warp: feasibility flags -> in-order queue
+// Exact placement of a group-constrained job against the live state (commit warp).
+// Returns the winning VM (or -1); the winner's pre-placement state lands in `w`.
+template <bool CONSTR>
+__device__ __noinline__ int resolve_group_job(const MatchArgs& a, ResolverShared& S, const Latest latest,
+                                              const QEntry& qe, VmState& w) {
+  const int lane = threadIdx.x & 31;
+  JobRegs r;
+  r.c = qe.jc; r.m = qe.jm; r.g = qe.jg; r.ports = qe.jports; r.j = qe.jj;
+  double cf = 0.0;
+  int cv = 0x7fffffff;
+  for (int v = lane; v < a.of.O; v += 32) {
+    const int e = latest.get(v);
+    VmState st;
+    if (e >= qe.lo) { int vm, k; st = load_log(&S.log[e & (LOGN - 1)], vm, k); }
+    else st = load_snap<CONSTR>(a, qe.blk, v);
+    const double f = eval_vm<CONSTR>(a, r, v, st, true);
+    if (f > cf) { cf = f; cv = v; }  // v ascends per lane: strict > keeps the lowest
+  }
+  unsigned wk;
+  int wl;
+  const double wf = warp_argmax(cf, (unsigned)cv, wk, wl);
+  if (!(wf > 0.0)) return -1;
+  const int wv = (int)wk;
+  const int we = latest.get(wv);
+  if (we >= qe.lo) { int vm, k; w = load_log(&S.log[we & (LOGN - 1)], vm, k); }
+  else w = load_snap<CONSTR>(a, qe.blk, wv);
+  return wv;
+}
+
+// ---- driver warp: feasibility stamps -> in-order queue
 template <bool CONSTR>
 __device__ void driver_warp(const MatchArgs& a, ResolverShared& S) {
   const int lane = threadIdx.x & 31;
   int g = 0;
   unsigned long long skipped = 0;
-  auto wait_slot = [&](int gi) {  // slot of gi is free once entry gi - RING is consumed
-    while (S.gdone <= gi - a.lookahead) __nanosleep(a.poll_ns);
+  auto wait_slot = [&](int gi) {  // entry gi may be filled once entry gi - lookahead is consumed
+    while (chain_gdone(S.chain) <= gi - a.lookahead) __nanosleep(a.poll_ns);
   };
   for (int b = 0;; b++) {
     while (S.bk_known < b + 1) __nanosleep(20);  // block b's bounds are set two block ends ahead
@@ -904,7 +921,7 @@ __device__ void spec_warp(const MatchArgs& a, ResolverShared& S, const Latest la
       __nanosleep(a.poll_ns);
     }
     if (quit) return;
-    fence_cta();
+    compiler_barrier();
     const QEntry qe = S.q[slot];
     if (qe.type == Q_EXIT) return;
     if (qe.type != Q_JOB) continue;
@@ -914,15 +931,15 @@ __device__ void spec_warp(const MatchArgs& a, ResolverShared& S, const Latest la
       if (lane == 0) S.res_seq[slot] = g + 1;
       continue;
     }
-    const int s = S.ncommit;
-    fence_cta();
+    const int s = chain_ncommit(S.chain);
+    compiler_barrier();
     spec_job<CONSTR>(a, S, latest, qe, s, KC, 2, S.res[slot]);
     fence_cta();
     if (lane == 0) S.res_seq[slot] = g + 1;
   }
 }
 
-// ---- commit warp
+// ---- commit warps
 // argmax over lanes of (f desc, v asc) with an early exit when the high words
 // of the fitness already single out one lane (the common case).
 __device__ __forceinline__ double warp_argmax_fast(double f, int v, int& wv, int& wl) {
@@ -945,17 +962,10 @@ __device__ __forceinline__ double warp_argmax_fast(double f, int v, int& wv, int
   return __shfl_sync(0xffffffffu, f, wl);
 }
 
-// NCW commit warps share the serial chain: entry g belongs to warp g % NCW.  While
-// its predecessors are still being decided the owner already re-evaluates every
-// VM committed since its result's version (one lane per log entry), so at its
-// turn only the newest entry is left: per-job latency on the chain = one fitness
-// evaluation + one warp argmax + the log append.
-constexpr int NCW = 4;
-
 template <bool CONSTR, bool PROF>
 __device__ void commit_warp(const MatchArgs& a, ResolverShared& S, const Latest latest, const int cw) {
   const int lane = threadIdx.x & 31;
-  unsigned long long n_fast = 0, n_group = 0, n_matched = 0, n_fallback = 0;
+  unsigned long long n_fast = 0, n_group = 0, n_matched = 0, n_fallback = 0, n_slow_turn = 0;
   unsigned long long prof[6] = {0, 0, 0, 0, 0, 0};
   const long long t_start = clock64();
   for (int g = cw;; g += NCW) {
@@ -973,31 +983,31 @@ __device__ void commit_warp(const MatchArgs& a, ResolverShared& S, const Latest 
     const int type = R->type;
     if (PROF) prof[0] += (unsigned long long)(clock64() - t0);
     if (type == Q_EXIT) {
-      while (S.gdone != g) __nanosleep(20);
+      while (chain_gdone(S.chain) != g) __nanosleep(20);
       if (lane == 0) a.stats[14] = (unsigned long long)(clock64() - t_start);
       break;
     }
     if (type == Q_END) {
-      while (S.gdone != g) __nanosleep(20);
+      unsigned long long w;
+      while (chain_gdone(w = S.chain) != g) __nanosleep(20);
       compiler_barrier();
       long long t4 = PROF ? clock64() : 0;
       // publish the newest state of every VM touched in this or the previous block
       // into the buffer the evaluators read for block blk+2; write the block's results
       const int b = S.q[slot].blk, lo = S.q[slot].lo;
-      const int c = S.ncommit, out_done = S.out_done;
+      const int c = chain_ncommit(w), out_done = S.out_done;
       VmDyn* pub = a.dyn.d[b & 1];
       for (int e = lo + lane; e < c; e += 32) {
-        const int idx = e & (LOGN - 1);
-        const int vm = S.l_vm[idx];
+        int vm, k;
+        const VmState st = load_log(&S.log[e & (LOGN - 1)], vm, k);
         if (latest.get(vm) == e) {
-          __stcg(reinterpret_cast<double2*>(pub + vm), make_double2(S.l_ac[idx], S.l_am[idx]));
-          __stcg(reinterpret_cast<int2*>(pub + vm) + 2, make_int2(S.l_an[idx], S.l_pu[idx]));
+          __stcg(reinterpret_cast<double2*>(pub + vm), make_double2(st.ac, st.am));
+          if (CONSTR) __stcg(reinterpret_cast<int2*>(a.dyn.n[b & 1] + vm), make_int2(st.an, st.pu));
         }
         if (e >= out_done) {  // results of this block's placements
-          const int k = S.l_k[idx];
           a.assign[k] = vm;
           a.fail[k] = COOK_FAIL_NONE;
-          a.ports_start[k] = S.l_pu0[idx];
+          a.ports_start[k] = CONSTR ? st.pu - a.kports[k] : 0;
         }
       }
       __syncwarp();
@@ -1020,7 +1030,7 @@ __device__ void commit_warp(const MatchArgs& a, ResolverShared& S, const Latest 
         S.bk_known = b + 3;
         __threadfence();
         asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(a.published), "r"((unsigned)(b + 1)) : "memory");
-        S.gdone = g + 1;
+        S.chain = chain_pack(g + 1, c);
       }
       __syncwarp();
       if (PROF) prof[4] += (unsigned long long)(clock64() - t4);
@@ -1031,95 +1041,20 @@ __device__ void commit_warp(const MatchArgs& a, ResolverShared& S, const Latest 
     r.c = qe.jc; r.m = qe.jm; r.g = CONSTR ? qe.jg : 0.0; r.ports = CONSTR ? qe.jports : 0; r.j = qe.jj;
     const int k = qe.k;
     const bool grp = CONSTR && qe.grp;
-    // The lane that holds the winner's pre-placement state appends the log entry.
-    int wv = -1, writer = 0, c = 0;
-    bool from_y = true;
-    Cand y;  // this lane's listed candidate (or the uniform winner of the slow paths)
-    Cand x;  // this lane's log entry (VM changed since the result's version)
-    x.vm = 0; x.ac = x.am = x.lc = x.lm = x.rc = x.rm = 0.0; x.an = x.pu = 0;
-    y = x;
-    long long t2 = 0;
     if (grp) {
-      while (S.gdone != g) __nanosleep(20);
+      unsigned long long w;
+      while (chain_gdone(w = S.chain) != g) __nanosleep(20);
       compiler_barrier();
-      t2 = PROF ? clock64() : 0;
-      c = S.ncommit;
+      const int c = chain_ncommit(w);
       const QEntry q2 = qe;
-      wv = resolve_group_job<CONSTR>(a, S, latest, q2, y);  // y uniform across lanes
+      VmState ws;
+      const int wv = resolve_group_job<CONSTR>(a, S, latest, q2, ws);  // uniform across lanes
       n_group++;
-    } else {
-      const int s = R->s, n = R->n;
-      const bool r_complete = R->complete != 0;
-      const double r_zf = R->zf;
-      const int r_zv = R->zv;
-      const int el = s + lane;
-      y = R->c[lane & (KC - 1)];
-      static_assert(KC <= 32 && (KC & (KC - 1)) == 0, "one candidate per lane");
-      double xf = 0.0;
-      int c_seen = s;
-      long long t1 = PROF ? clock64() : 0;
-      // (1) follow the log until it is this entry's turn
-      while (true) {
-        const int gd = S.gdone;  // the turn flag is read BEFORE the log size
-        const bool mine = gd == g;
-        const int c_now = S.ncommit;
-        compiler_barrier();
-        if (gd < g - 1 && c_now == c_seen) { __nanosleep(60); continue; }  // only the next in line polls hard
-        if (c_now > c_seen) {
-          if (el >= c_seen && el < c_now) {
-            const int idx = el & (LOGN - 1);
-            x.vm = S.l_vm[idx];
-            x.ac = S.l_ac[idx]; x.am = S.l_am[idx]; x.lc = S.l_lc[idx]; x.lm = S.l_lm[idx];
-            x.rc = S.l_rc[idx]; x.rm = S.l_rm[idx]; x.an = S.l_an[idx]; x.pu = S.l_pu[idx];
-            xf = eval_vm<CONSTR>(a, r, x.vm, x.ac, x.am, x.an, x.pu, x.lc, x.lm, x.rc, x.rm, false);
-          }
-          c_seen = c_now;
-        }
-        if (mine) break;
-      }
-      c = c_seen;
-      t2 = PROF ? clock64() : 0;
-      if (PROF) prof[1] += (unsigned long long)(t2 - t1);
-      // (2) decide: newest valid log entry per VM, or an unchanged listed candidate
-      const bool xin = el < c && xf > 0.0 && latest.get(x.vm) == el;
-      const bool ok = lane < n && latest.get(y.vm) < s;
-      const bool use_y = ok && (!xin || better(y.f, y.vm, xf, x.vm));
-      const double lf = use_y ? y.f : (xin ? xf : 0.0);
-      const int lv = use_y ? y.vm : (xin ? x.vm : 0x7fffffff);
-      int xv, wl;
-      const double wf = warp_argmax_fast(lf, lv, xv, wl);
-      // every unchanged VM outside the candidate set is no better than the bound z:
-      // the winner is exact when the set is complete or it beats z
-      const bool exact = r_complete || (wf > 0.0 && better(wf, xv, r_zf, r_zv));
-      if (exact) {
-        n_fast++;
-        if (wf > 0.0) { wv = xv; writer = wl; from_y = use_y; }
-      } else {
-        // recompute at the current version (exact): its one candidate is the answer
-        const QEntry q2 = qe;
-        spec_job_fallback<CONSTR>(a, S, latest, q2, c);
-        if (S.res[RING].n > 0) { y = S.res[RING].c[0]; wv = y.vm; writer = 0; from_y = true; }
-        n_fallback++;
-      }
-    }
-    if (wv >= 0) {
-      if (lane == writer) {
-        const int idx = c & (LOGN - 1);
-        S.l_vm[idx] = wv;
-        if (from_y) {
-          S.l_ac[idx] = y.ac + r.c; S.l_am[idx] = y.am + r.m;
-          S.l_lc[idx] = y.lc; S.l_lm[idx] = y.lm; S.l_rc[idx] = y.rc; S.l_rm[idx] = y.rm;
-          S.l_an[idx] = y.an + 1; S.l_pu[idx] = y.pu + r.ports; S.l_pu0[idx] = y.pu;
-        } else {
-          S.l_ac[idx] = x.ac + r.c; S.l_am[idx] = x.am + r.m;
-          S.l_lc[idx] = x.lc; S.l_lm[idx] = x.lm; S.l_rc[idx] = x.rc; S.l_rm[idx] = x.rm;
-          S.l_an[idx] = x.an + 1; S.l_pu[idx] = x.pu + r.ports; S.l_pu0[idx] = x.pu;
-        }
-        S.l_k[idx] = k;
-        latest.set(wv, c);
-        fence_cta();
-        S.ncommit = c + 1;
-        if (grp) {
+      if (lane == 0) {
+        if (wv >= 0) {
+          ws.ac = ws.ac + r.c; ws.am = ws.am + r.m; ws.an += 1; ws.pu += r.ports;
+          store_log(&S.log[c & (LOGN - 1)], wv, k, ws);
+          latest.set(wv, c);
           for (int q = a.jb.group_off[r.j]; q < a.jb.group_off[r.j + 1]; q++) {
             const int gi = a.jb.group_idx[q];
             const int n = __ldcg(a.gr.gp_n + gi);
@@ -1129,18 +1064,175 @@ __device__ void commit_warp(const MatchArgs& a, ResolverShared& S, const Latest 
           __threadfence();  // the next group job may run on another commit warp
         }
         fence_cta();
-        S.gdone = g + 1;
+        S.chain = chain_pack(g + 1, c + (wv >= 0 ? 1 : 0));
       }
-      n_matched++;
-    } else if (lane == 0) {
-      S.gdone = g + 1;  // assign / fail keep their defaults (-1, COOK_FAIL_CONSTRAINT)
+      if (wv >= 0) n_matched++;
+      __syncwarp();
+      continue;
     }
+    // ---- plain job
+    const int s = R->s, n = R->n;
+    const bool r_complete = R->complete != 0;
+    const double r_zf = R->zf;
+    const int r_zv = R->zv;
+    const int el = s + lane;
+    const double yf = lane < n ? R->c[lane & (KC - 1)].f : 0.0;   // this lane's listed candidate
+    const int yv = lane < n ? R->c[lane & (KC - 1)].vm : 0x7fffffff;
+    static_assert(KC <= 32 && (KC & (KC - 1)) == 0, "one candidate per lane");
+    // Uniform (same in every lane) exact top-`d` of the valid items known so far: log
+    // entries [s, c_seen) still newest for their VM + listed candidates unchanged since s.
+    // src >= 0: log entry index, src < 0: ~candidate index.  `more`: valid items exist
+    // outside the list.
+    double f0 = 0.0, f1 = 0.0, f2 = 0.0;
+    int v0 = 0x7fffffff, v1 = 0x7fffffff, v2 = 0x7fffffff, s0 = 0, s1 = 0, s2 = 0, d = 0;
+    bool more = false, have = false;
+    int c_seen = s;
+    long long t1 = PROF ? clock64() : 0;
+    unsigned long long w;
+    int c = 0;
+    while (true) {
+      w = S.chain;
+      compiler_barrier();
+      const int gd = chain_gdone(w);
+      const int c_now = chain_ncommit(w);
+      const bool mine = gd == g;
+      if (!have) {
+        // (a) first look: one lane per log entry committed since s, three argmax rounds
+        double xf = 0.0;
+        int x_vm = 0x7fffffff;
+        if (el < c_now) {
+          int kk;
+          const VmState x = load_log(&S.log[el & (LOGN - 1)], x_vm, kk);
+          xf = eval_vm<CONSTR>(a, r, x_vm, x, false);
+        }
+        c_seen = c_now;
+        bool xin = el < c_seen && xf > 0.0 && latest.get(x_vm) == el;
+        bool ok = lane < n && latest.get(yv) < s;
+        const int nvalid = __popc(__ballot_sync(0xffffffffu, xin)) + __popc(__ballot_sync(0xffffffffu, ok));
+        more = nvalid > 3;
+        d = min(nvalid, 3);
+#pragma unroll
+        for (int rnd = 0; rnd < 3; rnd++) {
+          const bool use_y = ok && (!xin || better(yf, yv, xf, x_vm));
+          const double lf = use_y ? yf : (xin ? xf : 0.0);
+          const int lv = use_y ? yv : (xin ? x_vm : 0x7fffffff);
+          int bv, bl;
+          const double bf = warp_argmax_fast(lf, lv, bv, bl);
+          const bool by = __shfl_sync(0xffffffffu, use_y ? 1 : 0, bl) != 0;
+          const int bs = by ? ~bl : s + bl;
+          if (rnd == 0) { f0 = bf; v0 = bv; s0 = bs; }
+          if (rnd == 1) { f1 = bf; v1 = bv; s1 = bs; }
+          if (rnd == 2) { f2 = bf; v2 = bv; s2 = bs; }
+          if (lane == bl) { if (use_y) ok = false; else xin = false; }
+        }
+        have = true;
+        if (mine) n_slow_turn++;
+        continue;
+      }
+      if (mine && c_now <= c_seen + 1) { c = c_now; break; }
+      if (c_now > c_seen) {
+        // (b) one more entry, not the last before the turn: every lane evaluates it (uniform)
+        // and the list is updated without a warp collective
+        int nvm, kk;
+        const VmState ne = load_log(&S.log[c_seen & (LOGN - 1)], nvm, kk);
+        const double nf = eval_vm<CONSTR>(a, r, nvm, ne, false);
+        const int nsrc = c_seen;
+        c_seen++;
+        // the entry supersedes whatever was known about its VM
+        if (d > 0 && v0 == nvm) { f0 = f1; v0 = v1; s0 = s1; f1 = f2; v1 = v2; s1 = s2; d--; }
+        else if (d > 1 && v1 == nvm) { f1 = f2; v1 = v2; s1 = s2; d--; }
+        else if (d > 2 && v2 == nvm) { d--; }
+        if (nf > 0.0) {
+          if (d > 0 && better(nf, nvm, f0, v0)) {
+            f2 = f1; v2 = v1; s2 = s1; f1 = f0; v1 = v0; s1 = s0; f0 = nf; v0 = nvm; s0 = nsrc;
+            if (d == 3) more = true; else d++;
+          } else if (d > 1 && better(nf, nvm, f1, v1)) {
+            f2 = f1; v2 = v1; s2 = s1; f1 = nf; v1 = nvm; s1 = nsrc;
+            if (d == 3) more = true; else d++;
+          } else if (d > 2 && better(nf, nvm, f2, v2)) {
+            f2 = nf; v2 = nvm; s2 = nsrc; more = true;
+          } else if (!more && d < 3) {  // nothing hidden: it is the next best
+            if (d == 0) { f0 = nf; v0 = nvm; s0 = nsrc; }
+            else if (d == 1) { f1 = nf; v1 = nvm; s1 = nsrc; }
+            else { f2 = nf; v2 = nvm; s2 = nsrc; }
+            d++;
+          } else {
+            more = true;
+          }
+        }
+        continue;
+      }
+      if (gd < g - 1) __nanosleep(40);  // only the next in line polls hard
+    }
+    long long t2 = PROF ? clock64() : 0;
+    if (PROF) prof[1] += (unsigned long long)(t2 - t1);
+    // ---- the turn: c == c_seen (nothing new) or c == c_seen + 1 (one new entry)
+    VmState ne;
+    ne.ac = ne.am = ne.lc = ne.lm = ne.rc = ne.rm = ne.yc = ne.ym = 0.0; ne.an = ne.pu = 0;
+    int ne_vm = -1;
+    double nf = 0.0;
+    if (c > c_seen) {  // uniform: every lane evaluates the newest entry
+      int kk;
+      ne = load_log(&S.log[c_seen & (LOGN - 1)], ne_vm, kk);
+      nf = eval_vm<CONSTR>(a, r, ne_vm, ne, false);
+    }
+    // best old item that the newest entry did not supersede
+    const bool first = !(d > 0 && v0 == ne_vm);
+    const bool known = first ? (d > 0 || !more) : (d > 1 || !more);  // that rank is known (possibly "none")
+    const double pf = first ? (d > 0 ? f0 : 0.0) : (d > 1 ? f1 : 0.0);
+    const int pv = first ? (d > 0 ? v0 : 0x7fffffff) : (d > 1 ? v1 : 0x7fffffff);
+    const int ps = first ? s0 : s1;
+    const bool take_new = nf > 0.0 && better(nf, ne_vm, pf, pv);
+    const double wf = take_new ? nf : pf;
+    const int wv0 = take_new ? ne_vm : pv;
+    // every unchanged VM outside the candidate set is no better than the bound z: the
+    // winner is exact when its rank is known and the set is complete or it beats z
+    const bool exact = known && (r_complete || (wf > 0.0 && better(wf, wv0, r_zf, r_zv)));
+    int wv = -1;
+    if (exact) {
+      n_fast++;
+      if (wf > 0.0) {
+        wv = wv0;
+        if (!take_new) {  // the winner's state: its log entry or its candidate record
+          int vm2, kk;
+          if (ps >= 0) ne = load_log(&S.log[ps & (LOGN - 1)], vm2, kk);
+          else ne = R->c[(~ps) & (KC - 1)].st;
+        }
+        if (lane == 0) {
+          ne.ac = ne.ac + r.c; ne.am = ne.am + r.m; ne.an += 1; ne.pu += r.ports;
+          store_log(&S.log[c & (LOGN - 1)], wv, k, ne);
+          latest.set(wv, c);
+          fence_cta();
+          S.chain = chain_pack(g + 1, c + 1);
+        }
+      } else if (lane == 0) {
+        S.chain = chain_pack(g + 1, c);  // assign / fail keep their defaults (-1, COOK_FAIL_CONSTRAINT)
+      }
+    } else {
+      // recompute at the current version (exact): its one candidate is the answer
+      const QEntry q2 = qe;
+      spec_job_fallback<CONSTR>(a, S, latest, q2, c);
+      n_fallback++;
+      const bool got = S.res[RING].n > 0;
+      if (lane == 0) {
+        if (got) {
+          Cand z = S.res[RING].c[0];
+          z.st.ac = z.st.ac + r.c; z.st.am = z.st.am + r.m; z.st.an += 1; z.st.pu += r.ports;
+          store_log(&S.log[c & (LOGN - 1)], z.vm, k, z.st);
+          latest.set(z.vm, c);
+          fence_cta();
+        }
+        S.chain = chain_pack(g + 1, c + (got ? 1 : 0));
+      }
+      if (got) wv = 0;
+    }
+    if (wv >= 0) n_matched++;
     __syncwarp();
     if (PROF) prof[2] += (unsigned long long)(clock64() - t2);
   }
   if (lane == 0) {
     atomicAdd(a.stats + 0, n_fast); atomicAdd(a.stats + 2, n_group); atomicAdd(a.stats + 3, n_matched);
-    atomicAdd(a.stats + 4, n_fallback);
+    atomicAdd(a.stats + 4, n_fallback); atomicAdd(a.stats + 7, n_slow_turn);
     if (cw == 0) { a.stats[1] = S.n_rescan; a.stats[5] = S.n_trunc; }
     for (int i = 0; i < 6; i++) atomicAdd(a.stats + 8 + i, prof[i]);
   }
@@ -1162,9 +1254,9 @@ __global__ void __launch_bounds__(RES_THREADS, 1) match_kernel(MatchArgs a) {
     const int warp = threadIdx.x >> 5;
     for (int i = threadIdx.x; i < a.of.O; i += RES_THREADS) latest.set(i, -1);
     if (threadIdx.x < RING) { S.q_seq[threadIdx.x] = 0; S.res_seq[threadIdx.x] = 0; }
-    for (int i = threadIdx.x; i < LOGN; i += RES_THREADS) S.l_vm[i] = 0;
+    for (int i = threadIdx.x; i < LOGN; i += RES_THREADS) S.log[i].vm = 0;
     if (threadIdx.x == 0) {
-      S.ncommit = 0; S.gdone = 0; S.exit_g = -1; S.ticket = 0;
+      S.chain = 0ull; S.exit_g = -1; S.ticket = 0;
       S.lo_ring[0] = S.lo_ring[1] = S.lo_ring[2] = S.lo_ring[3] = 0;
       S.bk_ring[0] = 0; S.bk_ring[1] = a.B; S.bk_ring[2] = 2 * a.B; S.bk_known = 2;  // = host-initialised bk0[0..2]
       S.out_done = 0; S.blk_c0 = 0; S.last_b = a.B;
@@ -1211,8 +1303,17 @@ __global__ void __launch_bounds__(RES_THREADS, 1) match_kernel(MatchArgs a) {
       __syncthreads();  // bk_s is rewritten for the next block
       if (k0 >= a.n_cons) break;
       long long w1 = clock64();
-      for (int k = k0 + (int)blockIdx.x - 1; k < k1; k += n_eval)
-        evaluate_row<CONSTR, PROF>(a, k, b, k - k0, es, ep);
+      // the next row's job columns are fetched while this row is scored
+      int k = k0 + (int)blockIdx.x - 1;
+      JobRegs rn;
+      bool gn = false;
+      if (k < k1) { rn = load_job<CONSTR>(a, k); gn = CONSTR && (a.kflags[k] & 1); }
+      for (; k < k1; k += n_eval) {
+        const JobRegs r = rn;
+        const bool grp = gn;
+        if (k + n_eval < k1) { rn = load_job<CONSTR>(a, k + n_eval); gn = CONSTR && (a.kflags[k + n_eval] & 1); }
+        evaluate_row<CONSTR, PROF>(a, r, grp, b, k - k0, es, ep);
+      }
       wait += (unsigned long long)(w1 - w0);
       const unsigned long long dt = (unsigned long long)(clock64() - w1);
       work += dt;
@@ -1475,6 +1576,22 @@ __global__ void gather_offers_kernel(const int32_t* perm, int O, const double* c
   vs[v] = x;
 }
 
+// per-cycle reset of the dynamic state (both buffers) + the reciprocals of the fitness
+// denominators (static for the cycle)
+__global__ void init_dyn_kernel(const VmStatic* vs, int O, VmDyn* d0, VmDyn* d1, VmCnt* n0, VmCnt* n1) {
+  int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= O) return;
+  const VmStatic x = vs[v];
+  VmDyn d;
+  d.ac = 0.0; d.am = 0.0;
+  d.yc = safe_rcp(x.lc + x.rc);
+  d.ym = safe_rcp(x.lm + x.rm);
+  d0[v] = d; d1[v] = d;
+  VmCnt c;
+  c.an = 0; c.pu = 0;
+  n0[v] = c; n1[v] = c;
+}
+
 __global__ void ports_total_kernel(const int32_t* off, const int32_t* b, const int32_t* e, int O,
                                    int32_t* total) {
   int o = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1647,6 +1764,7 @@ static int32_t build_plan(cook_pool* pool, MatchPlan* mp, const int32_t* ranked_
   sz.add<int32_t>(O + 1);
   sz.add<unsigned long long>(32); sz.add<int32_t>(16);
   sz.add<VmStatic>(O + 1); sz.add<VmDyn>(O + 1); sz.add<VmDyn>(O + 1); sz.add<int>(O + 1);
+  sz.add<VmCnt>(O + 1); sz.add<VmCnt>(O + 1);
   CK(pool, ar.reserve(sz.off + (1 << 18)));
   ar.reset();
 
@@ -1737,6 +1855,7 @@ static int32_t build_plan(cook_pool* pool, MatchPlan* mp, const int32_t* ranked_
   memset(&ma, 0, sizeof(ma));
   for (int b = 0; b < 2; b++) {
     ma.dyn.d[b] = ar.take<VmDyn>(O + 1);
+    ma.dyn.n[b] = ar.take<VmCnt>(O + 1);
   }
   mp->d_pos = ar.take<int32_t>(n_ranked + 1);
   mp->d_tmp = ar.take<int32_t>(n_ranked + 1);
@@ -1793,9 +1912,6 @@ static int32_t run_plan(cook_pool* pool, MatchPlan* mp, int32_t* out_considerabl
   ConsArgs& ca = mp->ca;
   int launches = 0;
   // ---- reset of per-cycle dynamic state
-  for (int b = 0; b < 2; b++) {
-    CK(pool, cudaMemsetAsync(ma.dyn.d[b], 0, sizeof(VmDyn) * (O + 1), st));
-  }
   if (ma.gr.gp_n) CK(pool, cudaMemsetAsync(ma.gr.gp_n, 0, sizeof(int32_t) * (mp->G + 1), st));
   CK(pool, cudaMemsetAsync(mp->d_seg_s, 0, sizeof(int32_t) * (U + 1), st));
   CK(pool, cudaMemsetAsync(mp->d_seg_e, 0, sizeof(int32_t) * (U + 1), st));
@@ -1815,6 +1931,8 @@ static int32_t run_plan(cook_pool* pool, MatchPlan* mp, int32_t* out_considerabl
   if (O > 0) {
     gather_offers_kernel<<<(O + TB - 1) / TB, TB, 0, st>>>(mp->d_perm, O, mp->d_oc, mp->d_om, mp->d_orc,
                                                            mp->d_orm, mp->d_vs);
+    launches++;
+    init_dyn_kernel<<<(O + TB - 1) / TB, TB, 0, st>>>(mp->d_vs, O, ma.dyn.d[0], ma.dyn.d[1], ma.dyn.n[0], ma.dyn.n[1]);
     launches++;
     if (mp->d_ports_total) {
       ports_total_kernel<<<(O + TB - 1) / TB, TB, 0, st>>>(ma.of.port_off, ma.of.port_begin,
@@ -1912,7 +2030,7 @@ static int32_t run_plan(cook_pool* pool, MatchPlan* mp, int32_t* out_considerabl
   CK(pool, cudaStreamSynchronize(st));
   if (prof_on) {
     const char* nm[24] = {"fast", "chunk_rescan", "group_jobs", "matched", "fallbacks", "trunc_specs",
-                          "skipped", "-", "c_wait_result", "c_follow_log", "c_decide_commit", "c_to_argmax",
+                          "skipped", "slow_turns", "c_wait_result", "c_follow_log", "c_decide_commit", "c_to_argmax",
                           "c_end_block", "c_to_select", "res_total", "-", "eval_work", "eval_wait",
                           "eval_loop", "eval_sync", "eval_merge", "eval_work_q1", "eval_rowslots_q1", "blocks"};
     for (int i = 0; i < 24; i++) fprintf(stderr, "[cook_prof] %-14s %llu\n", nm[i], hstats[i]);

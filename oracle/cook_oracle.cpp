@@ -854,3 +854,53 @@ extern "C" int32_t oracle_rebalance(int32_t dru_mode, const cook_running_soa* ru
   *out_n = n_dec;
   return COOK_OK;
 }
+
+// ---------------------------------------------------------------------------
+// Check used by tests/test_fastdiv.py: the CUDA kernels divide by the (static)
+// fitness denominators through their correctly rounded reciprocals,
+//   y = RN(1/den), q0 = x*y, q = fma(fma(-den, q0, x), y, q0)
+// (cook_b200/csrc/match.cu div_y).  This counts the inputs for which that differs
+// from the IEEE quotient x/den the reference computes (clojure `/` on doubles,
+// via Fenzo's cpuMemBinPacker) over three families: Cook's value grids, random
+// doubles, and denominators with (nearly) all-ones significands.
+#include <cmath>
+static inline double fastdiv_q(double x, double den, double y) {
+  const double q0 = x * y;
+  return std::fma(std::fma(-den, q0, x), y, q0);
+}
+extern "C" int64_t oracle_check_fastdiv(int64_t n_random, uint64_t seed) {
+  int64_t bad = 0;
+  uint64_t s = seed ? seed : 88172645463325252ull;
+  auto rnd = [&]() { s ^= s << 13; s ^= s >> 7; s ^= s << 17; return s; };
+  auto rd = [&](int emin, int emax) {
+    const uint64_t m = rnd() & ((1ull << 52) - 1);
+    const int e = emin + (int)(rnd() % (uint64_t)(emax - emin + 1));
+    const uint64_t bits = ((uint64_t)(e + 1023) << 52) | m;
+    double d;
+    memcpy(&d, &bits, 8);
+    return d;
+  };
+  for (int bi = 1; bi <= 512; bi++)
+    for (int ai = 1; ai <= 1024; ai++) {
+      const double b = bi * 0.5, x = ai * 0.5;
+      if (fastdiv_q(x, b, 1.0 / b) != x / b) bad++;
+    }
+  for (int bi = 1; bi <= 2048; bi++)
+    for (int ai = 1; ai <= 2048; ai++) {
+      const double b = bi * 512.0, x = ai * 512.0;
+      if (fastdiv_q(x, b, 1.0 / b) != x / b) bad++;
+    }
+  for (int64_t i = 0; i < n_random; i++) {
+    const double x = rd(-20, 30), b = rd(-20, 30);
+    if (fastdiv_q(x, b, 1.0 / b) != x / b) bad++;
+  }
+  for (int64_t i = 0; i < n_random / 4; i++) {
+    const uint64_t m = ((1ull << 52) - 1) - (rnd() % 4);
+    const uint64_t bits = ((uint64_t)(1023 + (int)(rnd() % 20)) << 52) | m;
+    double b;
+    memcpy(&b, &bits, 8);
+    const double x = rd(-5, 25);
+    if (fastdiv_q(x, b, 1.0 / b) != x / b) bad++;
+  }
+  return bad;
+}
