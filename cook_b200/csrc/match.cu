@@ -140,6 +140,7 @@ struct MatchArgs {
   int lookahead;              // queue entries in flight (<= RING)
   int poll_ns;                // back-off of the resolver's shared-memory polling loops
   int max_spec_warp;          // spec warps are the non-commit, non-driver warps below this id
+  int spec_rounds;            // candidate batches per spec result
 };
 
 // ------------------------------------------------------------------ helpers
@@ -394,8 +395,8 @@ __device__ __forceinline__ void cp_async_commit_wait_all() {
 // The static VM table {lease cpus/mem, running cpus/mem} lives in shared memory
 // (SoA, loaded once per CTA) when it fits; the dynamic state is read from L2 with
 // all loads of a batch in flight.
-constexpr int NW = RES_THREADS / 32;
-static_assert(32 % NW == 0, "a warp owns 32 / NW chunks");
+constexpr int NW = 16;  // evaluator warps per CTA (warps beyond NW only exist for the resolver CTA's roles)
+static_assert(32 % NW == 0 && NW * 32 <= RES_THREADS, "a warp owns 32 / NW chunks");
 constexpr int CPW = 32 / NW;  // chunks per warp
 
 __device__ __forceinline__ bool better(double f, int v, double g, int w) {
@@ -546,11 +547,11 @@ __device__ void evaluate_row(const MatchArgs& a, const JobRegs& r, const bool gr
 // the newest entry per VM, monotone), so nothing is ever cleared: a VM is dirty
 // with respect to a block's snapshot iff latest[x] >= lo, lo = log size at the
 // start of the previous block.
-constexpr int MAXB = 256;             // max jobs per block
+constexpr int MAXB = 512;             // max jobs per block
 constexpr int LOGN = 2 * MAXB;        // commit-log ring (entries of two blocks)
 constexpr int RING = 32;              // queue entries / spec results in flight
 constexpr int KC = 16;                // candidates per spec result
-constexpr int LK = 8;                 // entries a lane keeps while building a result
+constexpr int LK = 4;                 // entries a lane keeps while building a result
 constexpr int NCW = 4;                // commit warps
 
 enum { Q_JOB = 0, Q_END = 1, Q_EXIT = 2 };
@@ -646,10 +647,11 @@ struct LaneList {
   int v[LK], e[LK];
   double cbf, dbf;
   int cbv, dbv;
+  bool cb_real;  // the cb sentinel is itself a clean VM of the chunk with exactly that fitness
   __device__ __forceinline__ void init() {
 #pragma unroll
     for (int i = 0; i < LK; i++) { f[i] = 0.0; v[i] = 0x7fffffff; e[i] = -1; }
-    cbf = dbf = 0.0; cbv = dbv = 0x7fffffff;
+    cbf = dbf = 0.0; cbv = dbv = 0x7fffffff; cb_real = false;
   }
   // x is better than every listed entry (row entries are pushed worst first)
   __device__ __forceinline__ void push_front(double x, int xv, int xe) {
@@ -703,13 +705,17 @@ __device__ __forceinline__ void spec_job(const MatchArgs& a, ResolverShared& S, 
     int v[TOPK];
 #pragma unroll
     for (int i = 0; i < TOPK; i++) { f[i] = __ldcg(rf + i * 32 + lane); v[i] = __ldcg(rv + i * 32 + lane); }
-    if (f[TOPK - 1] > 0.0) { L.cbf = f[TOPK - 1]; L.cbv = v[TOPK - 1]; }  // full list: the rest is worse
-    static_assert(LK >= TOPK, "a lane's list must hold its whole row chunk");
+    if (f[TOPK - 1] > 0.0) { L.cbf = f[TOPK - 1]; L.cbv = v[TOPK - 1]; }  // full row: the rest of the chunk is worse
 #pragma unroll
     for (int i = TOPK - 1; i >= 0; i--) {  // worst first: every push lands in front
       const bool live = f[i] > 0.0;
       const int vi = live ? v[i] : 0;
-      if (live && latest.get(vi) < lo) L.push_front(f[i], vi, -1);
+      if (live && latest.get(vi) < lo) {
+        // a full list drops its worst entry; drops come in improving order, so the last one
+        // dropped is the best clean VM of the chunk that is not listed: it becomes the bound
+        if (L.f[LK - 1] > 0.0) { L.cbf = L.f[LK - 1]; L.cbv = L.v[LK - 1]; L.cb_real = true; }
+        L.push_front(f[i], vi, -1);
+      }
     }
   }
   // every VM committed since the snapshot, at its state as of version s
@@ -721,7 +727,8 @@ __device__ __forceinline__ void spec_job(const MatchArgs& a, ResolverShared& S, 
   int n = 0, complete = 0;
   double cf = 0.0;
   int cv = 0, ce = -1;  // lane q keeps candidate q
-  while (n < depth) {
+  int takes = 0;        // batches taken: later batches add one candidate each, so they are capped
+  while (n < depth && (depth == 1 || takes < a.spec_rounds)) {
     const double hf = L.f[0];
     const int hv = L.v[0];
     // the lane's better sentinel
@@ -748,7 +755,10 @@ __device__ __forceinline__ void spec_job(const MatchArgs& a, ResolverShared& S, 
       // exact re-scan of chunk wl: clean VMs strictly worse than its row's last entry
       const double bf = __shfl_sync(0xffffffffu, L.cbf, wl);
       const int bv = __shfl_sync(0xffffffffu, L.cbv, wl);
-      if (lane == wl) { L.cbf = 0.0; L.cbv = 0x7fffffff; }
+      if (lane == wl) {
+        if (L.cb_real) L.insert(L.cbf, L.cbv, -1);  // the bound itself is a clean candidate
+        L.cbf = 0.0; L.cbv = 0x7fffffff; L.cb_real = false;
+      }
       for (int v = 32 * wl + lane; v < a.of.O; v += 32 * 32) {  // tiles wl, wl + 32, ...
         if (latest.get(v) >= lo) continue;
         const VmState st = load_snap<CONSTR>(a, blk, v);
@@ -775,6 +785,7 @@ __device__ __forceinline__ void spec_job(const MatchArgs& a, ResolverShared& S, 
     if (t >= 0 && t < cnt) { cf = xf; cv = xv; ce = xe; }
     if ((q >> lane) & 1u) L.pop();
     n += cnt;
+    takes++;
   }
   // bound: the best entry or sentinel still exposed
   double zf;
@@ -1031,6 +1042,7 @@ __device__ void commit_warp(const MatchArgs& a, ResolverShared& S, const Latest 
         __threadfence();
         asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(a.published), "r"((unsigned)(b + 1)) : "memory");
         S.chain = chain_pack(g + 1, c);
+        if (PROF && S.bk_ring[b & 7] < a.n_cons / 4) a.stats[15] = (unsigned long long)(clock64() - t_start);  // timeline: end of the first quarter
       }
       __syncwarp();
       if (PROF) prof[4] += (unsigned long long)(clock64() - t4);
@@ -1264,7 +1276,7 @@ __global__ void __launch_bounds__(RES_THREADS, 1) match_kernel(MatchArgs a) {
     }
     __syncthreads();
     // warps 0, 4, 8, 12 share one scheduler (warp id mod 4): the commit warps keep it to themselves
-    if ((warp & 3) == 0 && (warp >> 2) < NCW) commit_warp<CONSTR, PROF>(a, S, latest, warp >> 2);
+    if ((warp & 3) == 0) { if ((warp >> 2) < NCW) commit_warp<CONSTR, PROF>(a, S, latest, warp >> 2); }
     else if (warp == 1) driver_warp<CONSTR>(a, S);
     else if (warp < a.max_spec_warp) spec_warp<CONSTR>(a, S, latest);
   } else {
@@ -1282,6 +1294,7 @@ __global__ void __launch_bounds__(RES_THREADS, 1) match_kernel(MatchArgs a) {
       es.lc = lc; es.lm = lm; es.rc = rc; es.rm = rm;
     }
     __shared__ int bk_s[2];
+    if ((threadIdx.x >> 5) >= NW) return;  // only NW warps score rows (exited threads do not block the barriers)
     const int n_eval = gridDim.x - 1;
     unsigned long long work = 0, wait = 0, work_q1 = 0, rows_q1 = 0, nblk_seen = 0;
     unsigned long long ep[3] = {0, 0, 0};
@@ -1377,6 +1390,13 @@ __global__ void __launch_bounds__(128) cons_user_kernel(ConsArgs a, const int32_
   double am = a.u_mem ? a.u_mem[u] : 0.0, ag = a.u_gpus ? a.u_gpus[u] : 0.0;
   const double qn = a.q_count[u], qc = a.q_cpus[u], qm = a.q_mem[u], qg = a.q_gpus[u];
   const int tokens = a.tokens ? a.tokens[u] : 0x7fffffff;
+  // No quota on any resource (quota.clj default = Double/MAX_VALUE) and no rate limit in
+  // force: every finite running sum passes, so the order-dependent fold is not needed.
+  const double dmax = 1.7976931348623157e308;
+  if (qn >= dmax && qc >= dmax && qm >= dmax && qg >= dmax && !a.enforce_rate_limit) {
+    for (int p = s + lane; p < e; p += 32) keep[pos_by_user[p]] = 1;
+    return;
+  }
   int seen = 0;
   for (int base = s; base < e; base += 32) {
     int p = base + lane;
@@ -1721,7 +1741,7 @@ static int32_t build_plan(cook_pool* pool, MatchPlan* mp, const int32_t* ranked_
     for (int j = 0; j < J && !constr_eff; j++) constr_eff = jobs->ports[j] != 0;
 
   // blocks: B jobs at the start, then sized by the resolver to ~btarget placements per block
-  int B = 64, bmin = 64, bmax = MAXB, btarget = 48;
+  int B = 64, bmin = 64, bmax = MAXB, btarget = 32;
   if (const char* eb = getenv("COOK_MATCH_B")) { int v = atoi(eb); if (v >= 8 && v <= MAXB) B = v; }
   if (const char* eb = getenv("COOK_MATCH_BMIN")) { int v = atoi(eb); if (v >= 8 && v <= MAXB) bmin = v; }
   if (const char* eb = getenv("COOK_MATCH_BMAX")) { int v = atoi(eb); if (v >= 8 && v <= MAXB) bmax = v; }
@@ -1891,9 +1911,11 @@ static int32_t build_plan(cook_pool* pool, MatchPlan* mp, const int32_t* ranked_
   ma.published = reinterpret_cast<unsigned*>(mp->d_counters + 8); ma.stats = mp->d_stats;
   ma.isolate_commit = 1;
   if (const char* ei = getenv("COOK_ISOLATE")) ma.isolate_commit = atoi(ei);
-  ma.lookahead = 16;
+  ma.lookahead = 20;
   ma.poll_ns = 200;
   ma.max_spec_warp = RES_THREADS / 32;
+  ma.spec_rounds = 4;
+  if (const char* er = getenv("COOK_SPEC_ROUNDS")) ma.spec_rounds = atoi(er);
   if (const char* ew = getenv("COOK_MAX_SPEC_WARP")) ma.max_spec_warp = atoi(ew);
   if (const char* ep = getenv("COOK_POLL_NS")) ma.poll_ns = atoi(ep);
   if (const char* el = getenv("COOK_LOOKAHEAD")) { int v = atoi(el); if (v >= 2 && v <= RING) ma.lookahead = v; }
@@ -2031,7 +2053,7 @@ static int32_t run_plan(cook_pool* pool, MatchPlan* mp, int32_t* out_considerabl
   if (prof_on) {
     const char* nm[24] = {"fast", "chunk_rescan", "group_jobs", "matched", "fallbacks", "trunc_specs",
                           "skipped", "slow_turns", "c_wait_result", "c_follow_log", "c_decide_commit", "c_to_argmax",
-                          "c_end_block", "c_to_select", "res_total", "-", "eval_work", "eval_wait",
+                          "c_end_block", "c_to_select", "res_total", "res_q1_done", "eval_work", "eval_wait",
                           "eval_loop", "eval_sync", "eval_merge", "eval_work_q1", "eval_rowslots_q1", "blocks"};
     for (int i = 0; i < 24; i++) fprintf(stderr, "[cook_prof] %-14s %llu\n", nm[i], hstats[i]);
   }

@@ -148,3 +148,44 @@ def test_rebalance_parity_random(gpu, oracle, seed, nr, np_, nh, nu):
     dg = gpu.rebalance(*args, groups=t["groups"])
     assert len(do) > 0
     assert dg == do
+
+
+def test_c3_shape_four_pools_parity(gpu, oracle):
+    """BASELINE config #3 at 1:10 scale: 100k jobs over 4 pools (40/30/20/10 %), 2k nodes,
+    host-placement + gpu/ports constraints, groups.  Every pool bit-identical to the oracle;
+    plus the size-independent invariants checked on the GPU result itself."""
+    from cook_b200.engine import GpuEngine
+    shapes = [(40_000, 800), (30_000, 600), (20_000, 400), (10_000, 200)]
+    for p, (nj, no) in enumerate(shapes):
+        t = traces.gen_c3_pool(300 + p, nj, no, 500, nj // 5)
+        ranked = oracle.rank(t["running"], t["pending"], t["users"])["ranked"]
+        prm = traces.match_params(nj, host_lifetime_mins=t["host_lifetime_mins"])
+        eng = GpuEngine(pool_name=f"pool-{p}")
+        try:
+            mg = eng.match(ranked, t["jobs"], t["offers"], t["users"], prm, groups=t["groups"], max_ports=2)
+        finally:
+            eng.close()
+        mo = oracle.match(ranked, t["jobs"], t["offers"], t["users"], prm, groups=t["groups"], max_ports=2)
+        assert np.array_equal(mg["considerable"], mo["considerable"])
+        assert np.array_equal(mg["assign"], mo["assign"]), p
+        assert np.array_equal(mg["ports"], mo["ports"])
+        # invariants: nothing over-committed, every placed job respects its resources
+        placed = mg["assign"] >= 0
+        cpus = np.zeros(no); mem = np.zeros(no)
+        jc, jm = t["jobs"].col("cpus"), t["jobs"].col("mem")
+        np.add.at(cpus, mg["assign"][placed], jc[mg["considerable"][placed]])
+        np.add.at(mem, mg["assign"][placed], jm[mg["considerable"][placed]])
+        assert (cpus <= t["offers"].col("cpus")).all() and (mem <= t["offers"].col("mem")).all()
+        assert mg["stats"]["n_matched"] == int(placed.sum()) > 0
+
+
+def test_prefix_property_at_c2_size(gpu):
+    """Size-independent property of the exact greedy: the placements of the first N jobs do
+    not depend on the jobs behind them (checked GPU against GPU on the 100k x 5k trace)."""
+    t = traces.gen_c2()
+    ranked = gpu.rank(t["running"], t["pending"], t["users"])["ranked"]
+    full = gpu.match(ranked, t["jobs"], t["offers"], t["users"], traces.match_params(100_000))
+    for n in (1, 777, 20_000):
+        part = gpu.match(ranked, t["jobs"], t["offers"], t["users"], traces.match_params(n))
+        assert np.array_equal(part["assign"], full["assign"][:n])
+        assert np.array_equal(part["considerable"], full["considerable"][:n])

@@ -12,3 +12,36 @@ def test_match_golden_oracle(oracle):
 @pytest.mark.gpu
 def test_match_golden_gpu(gpu):
     check_all(gpu)
+
+
+def test_constraint_truth_tables_oracle(oracle):
+    from constraint_golden_cases import check_all as check_constraints
+    check_constraints(oracle)
+
+
+@pytest.mark.gpu
+def test_constraint_truth_tables_gpu(gpu):
+    from constraint_golden_cases import check_all as check_constraints
+    check_constraints(gpu)
+
+
+def test_considerable_golden_oracle(oracle):
+    from considerable_golden_cases import check_all as check_considerable
+    check_considerable(oracle)
+
+
+@pytest.mark.gpu
+def test_considerable_golden_gpu(gpu):
+    from considerable_golden_cases import check_all as check_considerable
+    check_considerable(gpu)
+
+
+def test_rebalance_constraint_golden_oracle(oracle):
+    from rebalance_constraint_golden import check_all as check_reb
+    check_reb(oracle)
+
+
+@pytest.mark.gpu
+def test_rebalance_constraint_golden_gpu(gpu):
+    from rebalance_constraint_golden import check_all as check_reb
+    check_reb(gpu)
