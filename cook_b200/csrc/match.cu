@@ -126,6 +126,8 @@ struct MatchArgs {
   int host_lifetime_mins;
   unsigned char* rows;     // [2][B][ROW_BYTES]: f[TOPK][32] f64 then v[TOPK][32] i32
   const double* kg;        // gathered gpus per k (constraint kernel)
+  const double* smin_c;    // suffix minima of kc / km: the smallest request among jobs k..n_cons-1
+  const double* smin_m;
   const int32_t* kports;   // gathered port counts per k
   int32_t* feas;           // [2][bmax] block + 1 once any VM is feasible for the row at the snapshot
   int vs_in_smem;          // evaluators keep the static VM table in shared memory
@@ -140,7 +142,8 @@ struct MatchArgs {
   int lookahead;              // queue entries in flight (<= RING)
   int poll_ns;                // back-off of the resolver's shared-memory polling loops
   int max_spec_warp;          // spec warps are the non-commit, non-driver warps below this id
-  int spec_rounds;            // candidate batches per spec result
+  int spec_rounds;            // (unused)
+  int spec_kmin;              // candidate rounds stop once this many candidates are out
 };
 
 // ------------------------------------------------------------------ helpers
@@ -426,9 +429,17 @@ struct EvalStatic {  // static VM table in shared memory (SoA), or null => globa
   const double* lc; const double* lm; const double* rc; const double* rm;
 };
 
+// per-CTA exchange buffer: every warp's per-lane partial lists of one row
+struct EvalShared {
+  double f[NW][TOPK][32];
+  int32_t v[NW][TOPK][32];
+  int any[NW];
+};
+
 template <bool CONSTR, bool PROF>
 __device__ void evaluate_row(const MatchArgs& a, const JobRegs& r, const bool grp, int blk, int ib,
-                             const EvalStatic& es, unsigned long long* ep) {
+                             const EvalStatic& es, EvalShared& E, const unsigned long long live,
+                             unsigned long long* ep) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   long long e0 = PROF ? clock64() : 0;
   const double2* st2 = reinterpret_cast<const double2*>(a.of.vs);
@@ -436,70 +447,102 @@ __device__ void evaluate_row(const MatchArgs& a, const JobRegs& r, const bool gr
   unsigned char* row = a.rows + ((size_t)(blk & 1) * a.bmax + ib) * ROW_BYTES;
   double* rf = reinterpret_cast<double*>(row);
   int32_t* rv = reinterpret_cast<int32_t*>(row + ROW_V_OFF);
-  bool any = grp;  // group jobs are resolved against live group state, their rows stay empty
+  // (1) every warp scans its tiles (32 consecutive VMs, coalesced): VM v belongs to chunk
+  // v mod 32 = lane, so equal-fitness runs of consecutive VMs spread over all chunks
+  double f[TOPK];
+  int vv[TOPK];
+#pragma unroll
+  for (int i = 0; i < TOPK; i++) { f[i] = 0.0; vv[i] = 0x7fffffff; }
   if (!grp) {
     const int O = a.of.O;
-#pragma unroll 1
-    for (int ci = 0; ci < CPW; ci++) {
-      const int c = warp + ci * NW;
-      double f[TOPK];
-      int vv[TOPK];
+    constexpr int U = 4;  // VMs in flight per lane
+    int ui = 0;  // index of the lane's VM (bit of `live`)
+    for (int base = 32 * warp; base < O; base += U * 32 * NW, ui += U) {  // warp-uniform trip count
+      const int v0 = base + lane;
+      // VMs that cannot take even the smallest remaining job are dead for the rest of the
+      // cycle: a lane (and often the whole warp) skips their loads
+      const unsigned lb = ui < 64 ? (unsigned)((live >> ui) & ((1u << U) - 1u)) : ((1u << U) - 1u);
+      if (!__any_sync(0xffffffffu, lb != 0u)) continue;
+      VmState st[U];
 #pragma unroll
-      for (int i = 0; i < TOPK; i++) { f[i] = 0.0; vv[i] = 0x7fffffff; }
-      constexpr int U = 4;  // VMs in flight per lane
-      for (int v0 = 32 * c + lane; v0 < O; v0 += U * 1024) {
-        VmState st[U];
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-          const int v = v0 + u * 1024;
-          st[u].ac = st[u].am = st[u].yc = st[u].ym = st[u].lc = st[u].lm = st[u].rc = st[u].rm = 0.0;
-          st[u].an = st[u].pu = 0;
-          if (v < O) {
-            const double2 d0 = __ldcg(dy2 + 2 * v), d1 = __ldcg(dy2 + 2 * v + 1);
-            st[u].ac = d0.x; st[u].am = d0.y; st[u].yc = d1.x; st[u].ym = d1.y;
-            if (CONSTR) {
-              const int2 cn = __ldcg(reinterpret_cast<const int2*>(a.dyn.n[blk & 1] + v));
-              st[u].an = cn.x; st[u].pu = cn.y;
-            }
-            if (es.lc) { st[u].lc = es.lc[v]; st[u].lm = es.lm[v]; st[u].rc = es.rc[v]; st[u].rm = es.rm[v]; }
-            else {
-              const double2 s0 = __ldg(st2 + 2 * v), s1 = __ldg(st2 + 2 * v + 1);
-              st[u].lc = s0.x; st[u].lm = s0.y; st[u].rc = s1.x; st[u].rm = s1.y;
-            }
+      for (int u = 0; u < U; u++) {
+        const int v = v0 + u * 32 * NW;
+        st[u].ac = st[u].am = st[u].yc = st[u].ym = st[u].lc = st[u].lm = st[u].rc = st[u].rm = 0.0;
+        st[u].an = st[u].pu = 0;
+        if (v < O && ((lb >> u) & 1u)) {
+          const double2 d0 = __ldcg(dy2 + 2 * v), d1 = __ldcg(dy2 + 2 * v + 1);
+          st[u].ac = d0.x; st[u].am = d0.y; st[u].yc = d1.x; st[u].ym = d1.y;
+          if (CONSTR) {
+            const int2 cn = __ldcg(reinterpret_cast<const int2*>(a.dyn.n[blk & 1] + v));
+            st[u].an = cn.x; st[u].pu = cn.y;
+          }
+          if (es.lc) { st[u].lc = es.lc[v]; st[u].lm = es.lm[v]; st[u].rc = es.rc[v]; st[u].rm = es.rm[v]; }
+          else {
+            const double2 s0 = __ldg(st2 + 2 * v), s1 = __ldg(st2 + 2 * v + 1);
+            st[u].lc = s0.x; st[u].lm = s0.y; st[u].rc = s1.x; st[u].rm = s1.y;
           }
         }
+      }
 #pragma unroll
-        for (int u = 0; u < U; u++) {
-          const int v = v0 + u * 1024;
-          if (v >= O) break;
-          const double x = eval_vm<CONSTR>(a, r, v, st[u], false);
-          if (x > f[TOPK - 1]) {  // v ascends within a lane: strict > keeps the lower v on ties
-            f[TOPK - 1] = x; vv[TOPK - 1] = v;
+      for (int u = 0; u < U; u++) {
+        const int v = v0 + u * 32 * NW;
+        if (v >= O) break;
+        if (!((lb >> u) & 1u)) continue;
+        const double x = eval_vm<CONSTR>(a, r, v, st[u], false);
+        if (x > f[TOPK - 1]) {  // v ascends within a lane: strict > keeps the lower v on ties
+          f[TOPK - 1] = x; vv[TOPK - 1] = v;
 #pragma unroll
-            for (int i = TOPK - 1; i > 0; i--) {
-              if (f[i] > f[i - 1]) {
-                double tf = f[i]; f[i] = f[i - 1]; f[i - 1] = tf;
-                int tv = vv[i]; vv[i] = vv[i - 1]; vv[i - 1] = tv;
-              }
+          for (int i = TOPK - 1; i > 0; i--) {
+            if (f[i] > f[i - 1]) {
+              double tf = f[i]; f[i] = f[i - 1]; f[i - 1] = tf;
+              int tv = vv[i]; vv[i] = vv[i - 1]; vv[i - 1] = tv;
             }
           }
         }
       }
-      // the chunk's sorted top-TOPK: lane i ends up with entry i
+    }
+  }
+  const bool wany = __any_sync(0xffffffffu, f[0] > 0.0);
+  if (wany) {
+#pragma unroll
+    for (int i = 0; i < TOPK; i++) { E.f[warp][i][lane] = f[i]; E.v[warp][i][lane] = vv[i]; }
+  }
+  if (lane == 0) E.any[warp] = wany ? 1 : 0;
+  long long e1 = PROF ? clock64() : 0;
+  __syncthreads();
+  // (2) warp w merges chunks w, w + NW, ...: the NW partial lists of a chunk (sorted, TOPK
+  // each) are spread over the lanes, TOPK warp-argmax rounds emit the chunk's sorted list
+  bool any = false;
+#pragma unroll
+  for (int w = 0; w < NW; w++) any |= E.any[w] != 0;
+  if (any) {
+    constexpr int PER = NW * TOPK / 32;  // entries per lane
+    static_assert(NW * TOPK % 32 == 0 && TOPK % PER == 0, "partial lists split evenly over the lanes");
+#pragma unroll 1
+    for (int ci = 0; ci < CPW; ci++) {
+      const int c = warp + ci * NW;
+      const int sw = lane / (TOPK / PER), so = (lane % (TOPK / PER)) * PER;  // source warp, first entry
+      double lf[PER];
+      int lv[PER];
+#pragma unroll
+      for (int j = 0; j < PER; j++) {
+        const bool has = E.any[sw] != 0;
+        lf[j] = has ? E.f[sw][so + j][c] : 0.0;
+        lv[j] = has ? E.v[sw][so + j][c] : 0x7fffffff;
+      }
       double of = 0.0;
       int ov = -1;
 #pragma unroll 1
       for (int i = 0; i < TOPK; i++) {
         unsigned wk;
         int wl;
-        const double wf = warp_argmax(f[0], (unsigned)vv[0], wk, wl);
+        const double wf = warp_argmax(lf[0], (unsigned)lv[0], wk, wl);
         if (!(wf > 0.0)) break;
-        any = true;
         if (lane == i) { of = wf; ov = (int)wk; }
         if (lane == wl) {
 #pragma unroll
-          for (int q = 0; q < TOPK - 1; q++) { f[q] = f[q + 1]; vv[q] = vv[q + 1]; }
-          f[TOPK - 1] = 0.0; vv[TOPK - 1] = 0x7fffffff;
+          for (int q = 0; q < PER - 1; q++) { lf[q] = lf[q + 1]; lv[q] = lv[q + 1]; }
+          lf[PER - 1] = 0.0; lv[PER - 1] = 0x7fffffff;
         }
       }
       if (lane < TOPK) {
@@ -508,18 +551,19 @@ __device__ void evaluate_row(const MatchArgs& a, const JobRegs& r, const bool gr
       }
     }
   }
-  long long e1 = PROF ? clock64() : 0;
-  __syncwarp();
-  if (lane == 0) {
-    // feasibility stamp: block + 1 (stale stamps of the buffer's previous blocks are smaller)
-    if (any) atomicMax(a.feas + (size_t)(blk & 1) * a.bmax + ib, blk + 1);
-    // one arrival per (row, warp); the release orders the warp's row stores (made
-    // visible to this lane by the __syncwarp above) before the count
+  long long e2 = PROF ? clock64() : 0;
+  __syncthreads();  // row complete; E may be rewritten
+  if (threadIdx.x == 0) {
+    // feasibility stamp: block + 1 (stale stamps of the buffer's previous blocks are smaller);
+    // group jobs are resolved against live group state, their rows stay empty
+    if (any || grp) atomicMax(a.feas + (size_t)(blk & 1) * a.bmax + ib, blk + 1);
+    // the release orders the CTA's row stores (made visible to this thread by the barrier)
     asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(a.rows_ready + blk), "r"(1u) : "memory");
   }
   if (PROF) {
     long long e3 = clock64();
-    ep[0] += (unsigned long long)(e1 - e0); ep[2] += (unsigned long long)(e3 - e1);
+    ep[0] += (unsigned long long)(e1 - e0); ep[1] += (unsigned long long)(e2 - e1);
+    ep[2] += (unsigned long long)(e3 - e2);
   }
 }
 
@@ -551,8 +595,14 @@ constexpr int MAXB = 512;             // max jobs per block
 constexpr int LOGN = 2 * MAXB;        // commit-log ring (entries of two blocks)
 constexpr int RING = 32;              // queue entries / spec results in flight
 constexpr int KC = 16;                // candidates per spec result
-constexpr int LK = 4;                 // entries a lane keeps while building a result
-constexpr int NCW = 4;                // commit warps
+#ifndef COOK_LK
+#define COOK_LK 4
+#endif
+constexpr int LK = COOK_LK;           // entries a lane keeps while building a result
+#ifndef COOK_NCW
+#define COOK_NCW 3
+#endif
+constexpr int NCW = COOK_NCW;         // commit warps
 
 enum { Q_JOB = 0, Q_END = 1, Q_EXIT = 2 };
 
@@ -592,8 +642,8 @@ struct Cand {  // one candidate VM with its state at the result's version
 struct SpecOut {
   int type, s, n, complete;  // type: Q_JOB / Q_END / Q_EXIT (the commit warps wait on the result flag only)
   double zf;                 // bound: every unchanged VM outside c[] is no better than (zf, zv)
-  int zv, pad;
-  Cand c[KC];                // unsorted
+  int zv, z_real;            // z_real: (zf, zv) is the exact fitness of VM zv (state in c[KC]), not just a bound
+  Cand c[KC + 1];            // unsorted; c[KC] = the bound VM when z_real
 };
 
 struct ResolverShared {
@@ -724,23 +774,34 @@ __device__ __forceinline__ void spec_job(const MatchArgs& a, ResolverShared& S, 
     const VmState st = load_log(&S.log[e & (LOGN - 1)], vm, k);
     if (latest.get(vm) == e) L.insert(eval_vm<CONSTR>(a, r, vm, st, false), vm, e);
   }
+  // ---- selection.  A lane exposes its best entry not yet taken (its head) and keeps back
+  // the next one and its sentinels.  Every head that beats everything any lane keeps back is
+  // safe to take, all such heads at once; rounds repeat until at least `kmin` candidates
+  // are out (the later rounds add few).  The set is unsorted; what is left defines z.
   int n = 0, complete = 0;
-  double cf = 0.0;
-  int cv = 0, ce = -1;  // lane q keeps candidate q
-  int takes = 0;        // batches taken: later batches add one candidate each, so they are capped
-  while (n < depth && (depth == 1 || takes < a.spec_rounds)) {
-    const double hf = L.f[0];
-    const int hv = L.v[0];
-    // the lane's better sentinel
+  unsigned taken = 0u;  // bit j: this lane's entry j went into the set
+  auto store_cand = [&](int slot, double f, int vm, int e) {
+    Cand& c = out.c[slot];
+    c.f = f; c.vm = vm; c.e = e;
+    if (e >= 0) { int vm2, k2; c.st = load_log(&S.log[e & (LOGN - 1)], vm2, k2); }
+    else c.st = load_snap<CONSTR>(a, blk, vm);
+  };
+  const int kmin = depth == 1 ? 1 : min(a.spec_kmin, depth);
+  while (n < kmin) {
+    // head = first entry not taken, nx = the one after it
+    double hf = 0.0, nf2 = 0.0;
+    int hv = 0x7fffffff, he = -1, nv2 = 0x7fffffff, hj = LK;
+#pragma unroll
+    for (int j = LK - 1; j >= 0; j--)
+      if (L.f[j] > 0.0 && !((taken >> j) & 1u)) { nf2 = hf; nv2 = hv; hf = L.f[j]; hv = L.v[j]; he = L.e[j]; hj = j; }
     double sf = L.cbf;
     int sv = L.cbv;
     bool s_cb = true;
     if (L.dbf > 0.0 && better(L.dbf, L.dbv, sf, sv)) { sf = L.dbf; sv = L.dbv; s_cb = false; }
     const bool head_sent = sf > 0.0 && better(sf, sv, hf, hv);  // head hidden behind a sentinel
-    // what the lane keeps back when its head is taken
-    double rf = sf;
+    double rf = sf;  // what the lane keeps back when its head is taken
     int rv = sv;
-    if (!head_sent && L.f[1] > 0.0 && better(L.f[1], L.v[1], rf, rv)) { rf = L.f[1]; rv = L.v[1]; }
+    if (!head_sent && nf2 > 0.0 && better(nf2, nv2, rf, rv)) { rf = nf2; rv = nv2; }
     const double mf = warp_max_f64(rf);
     const int mv = (int)__reduce_min_sync(0xffffffffu, (rf == mf && mf > 0.0) ? (unsigned)rv : 0xffffffffu);
     const bool qual = !head_sent && hf > 0.0 && (!(mf > 0.0) || better(hf, hv, mf, mv));
@@ -752,14 +813,16 @@ __device__ __forceinline__ void spec_job(const MatchArgs& a, ResolverShared& S, 
       const int wl = __ffs(__ballot_sync(0xffffffffu, rf == mf && rv == mv)) - 1;
       const bool wcb = __shfl_sync(0xffffffffu, (s_cb && rf == sf && rv == sv) ? 1 : 0, wl) != 0;
       if (!wcb || n >= exact_n) { if (lane == 0) atomicAdd(&S.n_trunc, 1ull); break; }
-      // exact re-scan of chunk wl: clean VMs strictly worse than its row's last entry
+      // exact re-scan of chunk wl: clean VMs strictly worse than its bound
       const double bf = __shfl_sync(0xffffffffu, L.cbf, wl);
       const int bv = __shfl_sync(0xffffffffu, L.cbv, wl);
       if (lane == wl) {
         if (L.cb_real) L.insert(L.cbf, L.cbv, -1);  // the bound itself is a clean candidate
         L.cbf = 0.0; L.cbv = 0x7fffffff; L.cb_real = false;
       }
-      for (int v = 32 * wl + lane; v < a.of.O; v += 32 * 32) {  // tiles wl, wl + 32, ...
+      // NB: inserts shift list positions; nothing of lane wl has been taken yet in that case
+      // only if its head was hidden from the start, which is when a chunk bound can dominate
+      for (int v = wl + 32 * lane; v < a.of.O; v += 32 * 32) {  // chunk wl = VMs v with v mod 32 == wl
         if (latest.get(v) >= lo) continue;
         const VmState st = load_snap<CONSTR>(a, blk, v);
         const double x = eval_vm<CONSTR>(a, r, v, st, false);
@@ -777,35 +840,39 @@ __device__ __forceinline__ void spec_job(const MatchArgs& a, ResolverShared& S, 
       q = 1u << wl;
       cnt = 1;
     }
-    const int t = lane - n;  // receiver t takes the head of the (t+1)-th qualifying lane
-    const int src = (t >= 0 && t < cnt) ? (int)__fns(q, 0, t + 1) : 0;
-    const double xf = __shfl_sync(0xffffffffu, hf, src);
-    const int xv = __shfl_sync(0xffffffffu, hv, src);
-    const int xe = __shfl_sync(0xffffffffu, L.e[0], src);
-    if (t >= 0 && t < cnt) { cf = xf; cv = xv; ce = xe; }
-    if ((q >> lane) & 1u) L.pop();
+    if ((q >> lane) & 1u) {
+      store_cand(n + __popc(q & ((1u << lane) - 1u)), hf, hv, he);
+      taken |= 1u << hj;
+    }
     n += cnt;
-    takes++;
   }
-  // bound: the best entry or sentinel still exposed
+  // bound: the best entry not taken or sentinel of any lane
   double zf;
-  int zv;
+  int zv, z_real = 0;
   {
-    double ef = L.f[0];
-    int ev = L.v[0];
-    if (L.cbf > 0.0 && better(L.cbf, L.cbv, ef, ev)) { ef = L.cbf; ev = L.cbv; }
-    if (L.dbf > 0.0 && better(L.dbf, L.dbv, ef, ev)) { ef = L.dbf; ev = L.dbv; }
+    double ef = 0.0;
+    int ev = 0x7fffffff, ee = -1;
+    bool head = false;  // the exposure is a real entry (not a sentinel)
+#pragma unroll
+    for (int j = LK - 1; j >= 0; j--)
+      if (L.f[j] > 0.0 && !((taken >> j) & 1u)) { ef = L.f[j]; ev = L.v[j]; ee = L.e[j]; head = true; }
+    if (L.cbf > 0.0 && better(L.cbf, L.cbv, ef, ev)) { ef = L.cbf; ev = L.cbv; head = false; }
+    if (L.dbf > 0.0 && better(L.dbf, L.dbv, ef, ev)) { ef = L.dbf; ev = L.dbv; head = false; }
     zf = warp_max_f64(ef);
     zv = (int)__reduce_min_sync(0xffffffffu, (ef == zf && zf > 0.0) ? (unsigned)ev : 0xffffffffu);
     if (!(zf > 0.0)) complete = 1;
+    else {
+      // when the bound is a real entry it is the best VM outside the set: the commit warp
+      // may take it directly if everything it knows is worse (instead of recomputing)
+      const unsigned hm = __ballot_sync(0xffffffffu, ef == zf && ev == zv);
+      const unsigned rm = __ballot_sync(0xffffffffu, ef == zf && ev == zv && head);
+      if (hm == rm && hm != 0u) {  // no sentinel ties with it
+        z_real = 1;
+        if (lane == __ffs(rm) - 1) store_cand(KC, zf, zv, ee);
+      }
+    }
   }
-  if (lane < n) {
-    Cand& c = out.c[lane];
-    c.f = cf; c.vm = cv; c.e = ce;
-    if (ce >= 0) { int vm, k; c.st = load_log(&S.log[ce & (LOGN - 1)], vm, k); }
-    else c.st = load_snap<CONSTR>(a, blk, cv);
-  }
-  if (lane == 0) { out.type = Q_JOB; out.s = s; out.n = n; out.complete = complete; out.zf = zf; out.zv = zv; }
+  if (lane == 0) { out.type = Q_JOB; out.s = s; out.n = n; out.complete = complete; out.zf = zf; out.zv = zv; out.z_real = z_real; }
   __syncwarp();
 }
 
@@ -860,7 +927,7 @@ __device__ void driver_warp(const MatchArgs& a, ResolverShared& S) {
     if (k0 >= a.n_cons) break;
     const int nj = min(S.bk_ring[(b + 1) & 7], a.n_cons) - k0;
     if (lane == 0)
-      while (ld_acquire_u32(a.rows_ready + b) < (unsigned)nj * NW) __nanosleep(20);
+      while (ld_acquire_u32(a.rows_ready + b) < (unsigned)nj) __nanosleep(20);
     __syncwarp();
     // rows b ready => END(b-2) was processed => the start of block b-1 is recorded
     const int lo = b == 0 ? 0 : S.lo_ring[(b - 1) & 3];
@@ -976,7 +1043,7 @@ __device__ __forceinline__ double warp_argmax_fast(double f, int v, int& wv, int
 template <bool CONSTR, bool PROF>
 __device__ void commit_warp(const MatchArgs& a, ResolverShared& S, const Latest latest, const int cw) {
   const int lane = threadIdx.x & 31;
-  unsigned long long n_fast = 0, n_group = 0, n_matched = 0, n_fallback = 0, n_slow_turn = 0;
+  unsigned long long n_fast = 0, n_group = 0, n_matched = 0, n_fallback = 0, n_slow_turn = 0, n_ztake = 0;
   unsigned long long prof[6] = {0, 0, 0, 0, 0, 0};
   const long long t_start = clock64();
   for (int g = cw;; g += NCW) {
@@ -1200,8 +1267,23 @@ __device__ void commit_warp(const MatchArgs& a, ResolverShared& S, const Latest 
     // every unchanged VM outside the candidate set is no better than the bound z: the
     // winner is exact when its rank is known and the set is complete or it beats z
     const bool exact = known && (r_complete || (wf > 0.0 && better(wf, wv0, r_zf, r_zv)));
+    // everything known is worse than the bound, the bound is a real VM and nothing touched it
+    // since s: it is the best VM outside the set, hence the winner
+    const bool take_z = !exact && known && R->z_real != 0 && ne_vm != r_zv && latest.get(r_zv) < s;
     int wv = -1;
-    if (exact) {
+    if (take_z) {
+      n_fast++;
+      n_ztake++;
+      wv = r_zv;
+      ne = R->c[KC].st;
+      if (lane == 0) {
+        ne.ac = ne.ac + r.c; ne.am = ne.am + r.m; ne.an += 1; ne.pu += r.ports;
+        store_log(&S.log[c & (LOGN - 1)], wv, k, ne);
+        latest.set(wv, c);
+        fence_cta();
+        S.chain = chain_pack(g + 1, c + 1);
+      }
+    } else if (exact) {
       n_fast++;
       if (wf > 0.0) {
         wv = wv0;
@@ -1223,7 +1305,9 @@ __device__ void commit_warp(const MatchArgs& a, ResolverShared& S, const Latest 
     } else {
       // recompute at the current version (exact): its one candidate is the answer
       const QEntry q2 = qe;
+      const long long tf0 = PROF ? clock64() : 0;
       spec_job_fallback<CONSTR>(a, S, latest, q2, c);
+      if (PROF) prof[5] += (unsigned long long)(clock64() - tf0);
       n_fallback++;
       const bool got = S.res[RING].n > 0;
       if (lane == 0) {
@@ -1244,7 +1328,7 @@ __device__ void commit_warp(const MatchArgs& a, ResolverShared& S, const Latest 
   }
   if (lane == 0) {
     atomicAdd(a.stats + 0, n_fast); atomicAdd(a.stats + 2, n_group); atomicAdd(a.stats + 3, n_matched);
-    atomicAdd(a.stats + 4, n_fallback); atomicAdd(a.stats + 7, n_slow_turn);
+    atomicAdd(a.stats + 4, n_fallback); atomicAdd(a.stats + 7, n_slow_turn); atomicAdd(a.stats + 24, n_ztake);
     if (cw == 0) { a.stats[1] = S.n_rescan; a.stats[5] = S.n_trunc; }
     for (int i = 0; i < 6; i++) atomicAdd(a.stats + 8 + i, prof[i]);
   }
@@ -1276,14 +1360,21 @@ __global__ void __launch_bounds__(RES_THREADS, 1) match_kernel(MatchArgs a) {
     }
     __syncthreads();
     // warps 0, 4, 8, 12 share one scheduler (warp id mod 4): the commit warps keep it to themselves
+#ifdef COOK_SPREAD  // A/B: one commit warp per scheduler instead of all on scheduler 0
+    if (warp < NCW) commit_warp<CONSTR, PROF>(a, S, latest, warp);
+    else if (warp == NCW) driver_warp<CONSTR>(a, S);
+    else if (warp < a.max_spec_warp) spec_warp<CONSTR>(a, S, latest);
+#else
     if ((warp & 3) == 0) { if ((warp >> 2) < NCW) commit_warp<CONSTR, PROF>(a, S, latest, warp >> 2); }
     else if (warp == 1) driver_warp<CONSTR>(a, S);
     else if (warp < a.max_spec_warp) spec_warp<CONSTR>(a, S, latest);
+#endif
   } else {
     EvalStatic es;
     es.lc = es.lm = es.rc = es.rm = nullptr;
+    EvalShared& E = *reinterpret_cast<EvalShared*>(smem_raw);
     if (a.vs_in_smem) {  // static VM table -> shared memory, SoA (conflict-free 64-bit reads)
-      double* base = reinterpret_cast<double*>(smem_raw);
+      double* base = reinterpret_cast<double*>(smem_raw + ((sizeof(EvalShared) + 127) & ~size_t(127)));
       const size_t O = (size_t)a.of.O;
       double* lc = base; double* lm = base + O; double* rc = base + 2 * O; double* rm = base + 3 * O;
       for (int v = threadIdx.x; v < a.of.O; v += RES_THREADS) {
@@ -1294,6 +1385,7 @@ __global__ void __launch_bounds__(RES_THREADS, 1) match_kernel(MatchArgs a) {
       es.lc = lc; es.lm = lm; es.rc = rc; es.rm = rm;
     }
     __shared__ int bk_s[2];
+    __shared__ double smin_s[2];
     if ((threadIdx.x >> 5) >= NW) return;  // only NW warps score rows (exited threads do not block the barriers)
     const int n_eval = gridDim.x - 1;
     unsigned long long work = 0, wait = 0, work_q1 = 0, rows_q1 = 0, nblk_seen = 0;
@@ -1309,13 +1401,33 @@ __global__ void __launch_bounds__(RES_THREADS, 1) match_kernel(MatchArgs a) {
         }
         bk_s[0] = __ldcg(a.bk0 + b);
         bk_s[1] = __ldcg(a.bk0 + b + 1);
+        if (bk_s[0] < a.n_cons) { smin_s[0] = a.smin_c[bk_s[0]]; smin_s[1] = a.smin_m[bk_s[0]]; }
       }
       __syncthreads();
       const int k0 = bk_s[0];
       const int k1 = min(bk_s[1], a.n_cons);
+      const double minc = smin_s[0], minm = smin_s[1];
       __syncthreads();  // bk_s is rewritten for the next block
       if (k0 >= a.n_cons) break;
       long long w1 = clock64();
+      // live mask of the lane's VMs for this block's snapshot (bit u: VM 32*warp + lane + 32*NW*u):
+      // dead = even the smallest request among the jobs from k0 on does not fit (exact: the
+      // assigned amounts only grow within a cycle)
+      unsigned long long live = ~0ull;
+      if (a.of.O <= 64 * 32 * NW) {
+        live = 0ull;
+        const double2* dyb = reinterpret_cast<const double2*>(a.dyn.d[b & 1]);
+        const double2* stb = reinterpret_cast<const double2*>(a.of.vs);
+        int u = 0;
+        for (int v = 32 * (threadIdx.x >> 5) + (threadIdx.x & 31); v < a.of.O; v += 32 * NW, u++) {
+          const double2 d0 = __ldcg(dyb + 2 * v);
+          double lc, lm;
+          if (es.lc) { lc = es.lc[v]; lm = es.lm[v]; }
+          else { const double2 s0 = __ldg(stb + 2 * v); lc = s0.x; lm = s0.y; }
+          const bool dead = (d0.x + minc > lc) | (d0.y + minm > lm);
+          if (!dead) live |= 1ull << u;
+        }
+      }
       // the next row's job columns are fetched while this row is scored
       int k = k0 + (int)blockIdx.x - 1;
       JobRegs rn;
@@ -1325,7 +1437,7 @@ __global__ void __launch_bounds__(RES_THREADS, 1) match_kernel(MatchArgs a) {
         const JobRegs r = rn;
         const bool grp = gn;
         if (k + n_eval < k1) { rn = load_job<CONSTR>(a, k + n_eval); gn = CONSTR && (a.kflags[k + n_eval] & 1); }
-        evaluate_row<CONSTR, PROF>(a, r, grp, b, k - k0, es, ep);
+        evaluate_row<CONSTR, PROF>(a, r, grp, b, k - k0, es, E, live, ep);
       }
       wait += (unsigned long long)(w1 - w0);
       const unsigned long long dt = (unsigned long long)(clock64() - w1);
@@ -1596,6 +1708,27 @@ __global__ void gather_offers_kernel(const int32_t* perm, int O, const double* c
   vs[v] = x;
 }
 
+// suffix minima of the considerable jobs' requests (one CTA; n is at most a few million)
+__global__ void __launch_bounds__(1024) suffix_min_kernel(const double* kc, const double* km, int n,
+                                                          double* sc, double* sm) {
+  __shared__ double tc[1024], tm[1024];
+  const int t = threadIdx.x;
+  const int per = (n + 1023) / 1024;
+  const int lo = min(n, t * per), hi = min(n, lo + per);
+  double mc = 1.7976931348623157e308, mm = mc;
+  for (int k = hi - 1; k >= lo; k--) { mc = fmin(mc, kc[k]); mm = fmin(mm, km[k]); }
+  tc[t] = mc; tm[t] = mm;
+  __syncthreads();
+  // minimum over the threads to the right (serial over 1024 entries by one thread is fine here)
+  if (t == 0) {
+    double rc = 1.7976931348623157e308, rm = rc;
+    for (int i = 1023; i >= 0; i--) { const double c = tc[i], m = tm[i]; tc[i] = rc; tm[i] = rm; rc = fmin(rc, c); rm = fmin(rm, m); }
+  }
+  __syncthreads();
+  mc = tc[t]; mm = tm[t];
+  for (int k = hi - 1; k >= lo; k--) { mc = fmin(mc, kc[k]); mm = fmin(mm, km[k]); sc[k] = mc; sm[k] = mm; }
+}
+
 // per-cycle reset of the dynamic state (both buffers) + the reciprocals of the fitness
 // denominators (static for the cycle)
 __global__ void init_dyn_kernel(const VmStatic* vs, int O, VmDyn* d0, VmDyn* d1, VmCnt* n0, VmCnt* n1) {
@@ -1686,6 +1819,7 @@ struct MatchPlan {
   unsigned long long* d_stats = nullptr;
   int32_t* d_counters = nullptr;
   int* d_latest = nullptr;
+  double *d_smin_c = nullptr, *d_smin_m = nullptr;
   size_t max_blocks = 0;
   int32_t bk_init[3] = {0, 0, 0};
 };
@@ -1785,6 +1919,7 @@ static int32_t build_plan(cook_pool* pool, MatchPlan* mp, const int32_t* ranked_
   sz.add<unsigned long long>(32); sz.add<int32_t>(16);
   sz.add<VmStatic>(O + 1); sz.add<VmDyn>(O + 1); sz.add<VmDyn>(O + 1); sz.add<int>(O + 1);
   sz.add<VmCnt>(O + 1); sz.add<VmCnt>(O + 1);
+  sz.add<double>(NC + 1); sz.add<double>(NC + 1);
   CK(pool, ar.reserve(sz.off + (1 << 18)));
   ar.reset();
 
@@ -1891,6 +2026,9 @@ static int32_t build_plan(cook_pool* pool, MatchPlan* mp, const int32_t* ranked_
   mp->d_kports = ar.take<int32_t>(NC + bmax + 1);
   ma.kg = mp->d_kg; ma.kports = mp->d_kports;
   ma.feas = ar.take<int32_t>(2 * bmax + 16);
+  mp->d_smin_c = ar.take<double>(NC + 1);
+  mp->d_smin_m = ar.take<double>(NC + 1);
+  ma.smin_c = mp->d_smin_c; ma.smin_m = mp->d_smin_m;
   ma.rows_ready = ar.take<unsigned>(max_blocks + 8);
   ma.bk0 = ar.take<int32_t>(max_blocks + 8);
   mp->max_blocks = max_blocks;
@@ -1914,7 +2052,9 @@ static int32_t build_plan(cook_pool* pool, MatchPlan* mp, const int32_t* ranked_
   ma.lookahead = 20;
   ma.poll_ns = 200;
   ma.max_spec_warp = RES_THREADS / 32;
-  ma.spec_rounds = 4;
+  ma.spec_rounds = 16;
+  ma.spec_kmin = 12;
+  if (const char* ek = getenv("COOK_KMIN")) ma.spec_kmin = atoi(ek);
   if (const char* er = getenv("COOK_SPEC_ROUNDS")) ma.spec_rounds = atoi(er);
   if (const char* ew = getenv("COOK_MAX_SPEC_WARP")) ma.max_spec_warp = atoi(ew);
   if (const char* ep = getenv("COOK_POLL_NS")) ma.poll_ns = atoi(ep);
@@ -2001,6 +2141,8 @@ static int32_t run_plan(cook_pool* pool, MatchPlan* mp, int32_t* out_considerabl
       CK(pool, cudaMemsetAsync(ma.assign, 0xff, sizeof(int32_t) * n_cons, st));
       CK(pool, cudaMemsetAsync(ma.fail, COOK_FAIL_NO_OFFERS, n_cons, st));
     } else {
+      suffix_min_kernel<<<1, 1024, 0, st>>>(mp->d_kc, mp->d_km, n_cons, mp->d_smin_c, mp->d_smin_m);
+      launches++;
       // defaults for feasible-but-unplaced jobs; the kernel overwrites placed and skipped ones
       CK(pool, cudaMemsetAsync(ma.assign, 0xff, sizeof(int32_t) * n_cons, st));
       CK(pool, cudaMemsetAsync(ma.fail, COOK_FAIL_CONSTRAINT, n_cons, st));
@@ -2011,9 +2153,11 @@ static int32_t run_plan(cook_pool* pool, MatchPlan* mp, int32_t* out_considerabl
       if (res_base + sizeof(int) * (size_t)O <= 200 * 1024) smem = std::max(smem, res_base + sizeof(int) * (size_t)O);
       else ma.latest_global = mp->d_latest;
       // evaluator CTAs: the static VM table (4 f64 per VM, SoA) when it fits
-      ma.vs_in_smem = (size_t)O * 32 <= 220 * 1024 ? 1 : 0;
+      const size_t ev_base = (sizeof(EvalShared) + 127) & ~size_t(127);
+      smem = std::max(smem, ev_base);
+      ma.vs_in_smem = ev_base + (size_t)O * 32 <= 224 * 1024 ? 1 : 0;
       if (getenv("COOK_NO_SMEM_STATIC")) ma.vs_in_smem = 0;
-      if (ma.vs_in_smem) smem = std::max(smem, (size_t)O * 32);
+      if (ma.vs_in_smem) smem = std::max(smem, ev_base + (size_t)O * 32);
       void* kfn = mp->constr ? (prof_on ? (void*)match_kernel<true, true> : (void*)match_kernel<true, false>)
                              : (prof_on ? (void*)match_kernel<false, true> : (void*)match_kernel<false, false>);
       CK(pool, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -2051,11 +2195,11 @@ static int32_t run_plan(cook_pool* pool, MatchPlan* mp, int32_t* out_considerabl
   CK(pool, cudaEventRecord(pool->ev[4], st));
   CK(pool, cudaStreamSynchronize(st));
   if (prof_on) {
-    const char* nm[24] = {"fast", "chunk_rescan", "group_jobs", "matched", "fallbacks", "trunc_specs",
+    const char* nm[25] = {"fast", "chunk_rescan", "group_jobs", "matched", "fallbacks", "trunc_specs",
                           "skipped", "slow_turns", "c_wait_result", "c_follow_log", "c_decide_commit", "c_to_argmax",
-                          "c_end_block", "c_to_select", "res_total", "res_q1_done", "eval_work", "eval_wait",
-                          "eval_loop", "eval_sync", "eval_merge", "eval_work_q1", "eval_rowslots_q1", "blocks"};
-    for (int i = 0; i < 24; i++) fprintf(stderr, "[cook_prof] %-14s %llu\n", nm[i], hstats[i]);
+                          "c_end_block", "c_fallback", "res_total", "res_q1_done", "eval_work", "eval_wait",
+                          "eval_loop", "eval_sync", "eval_merge", "eval_work_q1", "eval_rowslots_q1", "blocks", "z_takes"};
+    for (int i = 0; i < 25; i++) fprintf(stderr, "[cook_prof] %-14s %llu\n", nm[i], hstats[i]);
   }
   if (out_stats) {
     out_stats->n_considerable = n_cons;

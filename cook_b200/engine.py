@@ -48,7 +48,9 @@ class _CallShapes:
                 abi.MatchStats())
 
 
-def load_library(path=LIB_PATH):
+def load_library(path=None):
+    # COOK_GPU_LIB: A/B builds of the same library (tools/ only); never a CPU fallback
+    path = path or os.environ.get("COOK_GPU_LIB", LIB_PATH)
     if not os.path.exists(path):
         raise FileNotFoundError(
             f"{path} not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
