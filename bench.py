@@ -271,7 +271,7 @@ def run_reference(args):
     ranked = ora.rank(t["running"], t["pending"], t["users"])["ranked"]
     # "all the host threads it can use": the per-task VM loop (5k offers) stops
     # scaling well before 128 threads; pick the fastest count on a short probe.
-    probe = traces.match_params(4000)
+    probe = traces.match_params(20000)  # long enough that per-job thread hand-off costs show
     best = (0.0, 1)
     for th in sorted({1, 2, 4, 8, 16, 32, 64, min(avail, 64)}):
         if th > avail:

@@ -1708,25 +1708,40 @@ __global__ void gather_offers_kernel(const int32_t* perm, int O, const double* c
   vs[v] = x;
 }
 
-// suffix minima of the considerable jobs' requests (one CTA; n is at most a few million)
-__global__ void __launch_bounds__(1024) suffix_min_kernel(const double* kc, const double* km, int n,
-                                                          double* sc, double* sm) {
-  __shared__ double tc[1024], tm[1024];
-  const int t = threadIdx.x;
-  const int per = (n + 1023) / 1024;
-  const int lo = min(n, t * per), hi = min(n, lo + per);
-  double mc = 1.7976931348623157e308, mm = mc;
-  for (int k = hi - 1; k >= lo; k--) { mc = fmin(mc, kc[k]); mm = fmin(mm, km[k]); }
-  tc[t] = mc; tm[t] = mm;
-  __syncthreads();
-  // minimum over the threads to the right (serial over 1024 entries by one thread is fine here)
-  if (t == 0) {
-    double rc = 1.7976931348623157e308, rm = rc;
-    for (int i = 1023; i >= 0; i--) { const double c = tc[i], m = tm[i]; tc[i] = rc; tm[i] = rm; rc = fmin(rc, c); rm = fmin(rm, m); }
+// suffix minima of the considerable jobs' requests: block-local reverse scans, then every
+// block folds in the minima of the blocks to its right
+constexpr int SMIN_TB = 256;
+__global__ void __launch_bounds__(SMIN_TB) suffix_min_local_kernel(const double* kc, const double* km, int n,
+                                                                   double* sc, double* sm, double* bc, double* bm) {
+  __shared__ double wc[SMIN_TB / 32], wm[SMIN_TB / 32];
+  const double INF = 1.7976931348623157e308;
+  const int k = blockIdx.x * SMIN_TB + threadIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double c = k < n ? kc[k] : INF, m = k < n ? km[k] : INF;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {  // reverse inclusive scan inside the warp
+    const double oc = __shfl_down_sync(0xffffffffu, c, o), om = __shfl_down_sync(0xffffffffu, m, o);
+    if (lane + o < 32) { c = fmin(c, oc); m = fmin(m, om); }
   }
+  if (lane == 0) { wc[warp] = c; wm[warp] = m; }
   __syncthreads();
-  mc = tc[t]; mm = tm[t];
-  for (int k = hi - 1; k >= lo; k--) { mc = fmin(mc, kc[k]); mm = fmin(mm, km[k]); sc[k] = mc; sm[k] = mm; }
+  for (int w = warp + 1; w < SMIN_TB / 32; w++) { c = fmin(c, wc[w]); m = fmin(m, wm[w]); }
+  if (k < n) { sc[k] = c; sm[k] = m; }
+  if (threadIdx.x == 0) { bc[blockIdx.x] = c; bm[blockIdx.x] = m; }
+}
+__global__ void __launch_bounds__(SMIN_TB) suffix_min_apply_kernel(int n, int nblocks, double* sc, double* sm,
+                                                                   const double* bc, const double* bm) {
+  __shared__ double wc[SMIN_TB / 32], wm[SMIN_TB / 32];
+  const double INF = 1.7976931348623157e308;
+  double c = INF, m = INF;
+  for (int j = blockIdx.x + 1 + threadIdx.x; j < nblocks; j += SMIN_TB) { c = fmin(c, bc[j]); m = fmin(m, bm[j]); }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { c = fmin(c, __shfl_xor_sync(0xffffffffu, c, o)); m = fmin(m, __shfl_xor_sync(0xffffffffu, m, o)); }
+  if ((threadIdx.x & 31) == 0) { wc[threadIdx.x >> 5] = c; wm[threadIdx.x >> 5] = m; }
+  __syncthreads();
+  c = INF; m = INF;
+  for (int w = 0; w < SMIN_TB / 32; w++) { c = fmin(c, wc[w]); m = fmin(m, wm[w]); }
+  const int k = blockIdx.x * SMIN_TB + threadIdx.x;
+  if (k < n) { sc[k] = fmin(sc[k], c); sm[k] = fmin(sm[k], m); }
 }
 
 // per-cycle reset of the dynamic state (both buffers) + the reciprocals of the fitness
@@ -1819,7 +1834,7 @@ struct MatchPlan {
   unsigned long long* d_stats = nullptr;
   int32_t* d_counters = nullptr;
   int* d_latest = nullptr;
-  double *d_smin_c = nullptr, *d_smin_m = nullptr;
+  double *d_smin_c = nullptr, *d_smin_m = nullptr, *d_smin_bc = nullptr, *d_smin_bm = nullptr;
   size_t max_blocks = 0;
   int32_t bk_init[3] = {0, 0, 0};
 };
@@ -1919,7 +1934,7 @@ static int32_t build_plan(cook_pool* pool, MatchPlan* mp, const int32_t* ranked_
   sz.add<unsigned long long>(32); sz.add<int32_t>(16);
   sz.add<VmStatic>(O + 1); sz.add<VmDyn>(O + 1); sz.add<VmDyn>(O + 1); sz.add<int>(O + 1);
   sz.add<VmCnt>(O + 1); sz.add<VmCnt>(O + 1);
-  sz.add<double>(NC + 1); sz.add<double>(NC + 1);
+  sz.add<double>(NC + 1); sz.add<double>(NC + 1); sz.add<double>(NC / 256 + 2); sz.add<double>(NC / 256 + 2);
   CK(pool, ar.reserve(sz.off + (1 << 18)));
   ar.reset();
 
@@ -2028,6 +2043,8 @@ static int32_t build_plan(cook_pool* pool, MatchPlan* mp, const int32_t* ranked_
   ma.feas = ar.take<int32_t>(2 * bmax + 16);
   mp->d_smin_c = ar.take<double>(NC + 1);
   mp->d_smin_m = ar.take<double>(NC + 1);
+  mp->d_smin_bc = ar.take<double>(NC / 256 + 2);
+  mp->d_smin_bm = ar.take<double>(NC / 256 + 2);
   ma.smin_c = mp->d_smin_c; ma.smin_m = mp->d_smin_m;
   ma.rows_ready = ar.take<unsigned>(max_blocks + 8);
   ma.bk0 = ar.take<int32_t>(max_blocks + 8);
@@ -2141,8 +2158,14 @@ static int32_t run_plan(cook_pool* pool, MatchPlan* mp, int32_t* out_considerabl
       CK(pool, cudaMemsetAsync(ma.assign, 0xff, sizeof(int32_t) * n_cons, st));
       CK(pool, cudaMemsetAsync(ma.fail, COOK_FAIL_NO_OFFERS, n_cons, st));
     } else {
-      suffix_min_kernel<<<1, 1024, 0, st>>>(mp->d_kc, mp->d_km, n_cons, mp->d_smin_c, mp->d_smin_m);
-      launches++;
+      {
+        const int nsb = (n_cons + SMIN_TB - 1) / SMIN_TB;
+        suffix_min_local_kernel<<<nsb, SMIN_TB, 0, st>>>(mp->d_kc, mp->d_km, n_cons, mp->d_smin_c, mp->d_smin_m,
+                                                         mp->d_smin_bc, mp->d_smin_bm);
+        suffix_min_apply_kernel<<<nsb, SMIN_TB, 0, st>>>(n_cons, nsb, mp->d_smin_c, mp->d_smin_m, mp->d_smin_bc,
+                                                         mp->d_smin_bm);
+        launches += 2;
+      }
       // defaults for feasible-but-unplaced jobs; the kernel overwrites placed and skipped ones
       CK(pool, cudaMemsetAsync(ma.assign, 0xff, sizeof(int32_t) * n_cons, st));
       CK(pool, cudaMemsetAsync(ma.fail, COOK_FAIL_CONSTRAINT, n_cons, st));
