@@ -189,3 +189,17 @@ def test_prefix_property_at_c2_size(gpu):
         part = gpu.match(ranked, t["jobs"], t["offers"], t["users"], traces.match_params(n))
         assert np.array_equal(part["assign"], full["assign"][:n])
         assert np.array_equal(part["considerable"], full["considerable"][:n])
+
+
+@pytest.mark.parametrize("seed,nj,no", [(71, 3000, 7000), (72, 1500, 45000)])
+def test_wide_offer_tables(gpu, oracle, seed, nj, no):
+    """Offer tables beyond the shared-memory fast paths: 7k offers (static VM table read from
+    L2 instead of shared memory), 45k offers (newest-log-entry table in global memory, no
+    live-VM mask): same assignments as the oracle."""
+    t = traces.gen_pool(seed, nj, no, 50, 500)
+    ranked = oracle.rank(t["running"], t["pending"], t["users"])["ranked"]
+    prm = traces.match_params(nj)
+    mg = gpu.match(ranked, t["jobs"], t["offers"], t["users"], prm)
+    mo = oracle.match(ranked, t["jobs"], t["offers"], t["users"], prm)
+    assert np.array_equal(mg["considerable"], mo["considerable"])
+    assert np.array_equal(mg["assign"], mo["assign"])
