@@ -5,28 +5,27 @@
 // good-enough-fitness >= 1.0 (every VM evaluated for every task).
 //
 // Exactness on a parallel machine.  Fenzo places requests one at a
-// time; each placement mutates one VM and may change every later argmax.  The
-// kernel keeps that order but splits the work:
+// time; each placement mutates one VM and may change every later argmax.  One
+// persistent cooperative launch keeps that order and splits the work:
 //
-//   evaluators (all CTAs but #0): for a block of B jobs, one warp per job scans
-//     ALL offers against a SNAPSHOT of the dynamic VM state and keeps, per lane
-//     (= chunk of offers v == lane mod 32), the best two (fitness, v) pairs.
-//   resolver (warp 0 of CTA 0): walks the jobs in rank order.  VMs touched since
-//     the snapshot ("dirty", <= 2B of them, state in shared memory) are
-//     re-evaluated exactly; every other VM is unchanged, so the row's best
-//     clean candidate per chunk is still exact.  If a chunk's two candidates
-//     are both dirty, its remaining VMs are bounded above by the second
-//     candidate's fitness; the chunk is re-scanned only when that bound could
-//     beat the winner.  Jobs whose constraints depend on same-cycle placements
-//     of other jobs (groups) take a full re-scan against current state.
+//   evaluators (all CTAs but #0): one CTA per job scores ALL offers against a
+//     SNAPSHOT of the dynamic VM state and emits, per chunk of offers (VM v is in
+//     chunk v mod 32), the sorted top-TOPK (fitness, v) pairs: the job's ROW.
+//   resolver (CTA 0): walks the jobs in rank order.  Every placement is appended to
+//     a commit LOG in shared memory; VMs in the log since the row's snapshot are
+//     re-evaluated exactly, every other VM is unchanged, so the row's clean
+//     candidates are still exact.  Warp roles (driver / spec / commit) pipeline
+//     that work; only "evaluate the job on the VM the previous job just changed,
+//     compare, append" is serial (see the resolver section below and DESIGN.md 4).
 //
-//   The two roles are software-pipelined: while the resolver places block t the
+//   The two sides are software-pipelined: while the resolver places block t the
 //   evaluators score block t+1 against the state published after block t-1
-//   (double-buffered), one grid barrier per block.
+//   (double-buffered snapshot, two monotone counters, no grid barrier).
 //
 // Tie-break: equal fitness => lowest hostname (offers are index-sorted by
-// name_rank on upload, so "lowest v").  All f64 ops are IEEE (div.rn.f64,
-// -fmad=false): identical to oracle/cook_oracle.cpp eval_pair bit for bit.
+// name_rank on upload, so "lowest v").  All f64 ops are IEEE in the reference's
+// order (-fmad=false; divisions via correctly rounded reciprocals, see div_y):
+// identical to oracle/cook_oracle.cpp eval_pair bit for bit.
 #include <cooperative_groups.h>
 
 #include <algorithm>
@@ -138,11 +137,9 @@ struct MatchArgs {
   uint8_t* fail;           // [n_cons]
   unsigned long long* stats;  // [0]=fast [1]=chunk rescans [2]=group jobs [3]=matched [4]=fallbacks [5]=truncated specs [6]=skipped
   int* latest_global;         // newest-log-entry table when it does not fit in shared memory
-  int isolate_commit;         // keep the warps that share the commit warp's scheduler idle
   int lookahead;              // queue entries in flight (<= RING)
   int poll_ns;                // back-off of the resolver's shared-memory polling loops
   int max_spec_warp;          // spec warps are the non-commit, non-driver warps below this id
-  int spec_rounds;            // (unused)
   int spec_kmin;              // candidate rounds stop once this many candidates are out
 };
 
@@ -346,44 +343,6 @@ __device__ __forceinline__ VmState load_snap(const MatchArgs& a, int blk, int v)
     st.an = c.x; st.pu = c.y;
   }
   return st;
-}
-
-// ------------------------------------------------------------- PTX helpers
-__device__ __forceinline__ unsigned smem_u32(const void* p) {
-  return (unsigned)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "WAIT_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra DONE_%=;\n\t"
-      "bra WAIT_%=;\n\t"
-      "DONE_%=:\n\t}"
-      ::"r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-}
-// TMA (bulk async copy engine): global -> shared, completion on an mbarrier.
-__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, unsigned bytes,
-                                            unsigned long long* bar) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-      ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
-      : "memory");
-}
-__device__ __forceinline__ void cp_async16_cg(void* dst_smem, const void* src_gmem) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem)
-               : "memory");
-}
-__device__ __forceinline__ void cp_async_commit_wait_all() {
-  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
 }
 
 // ------------------------------------------------------------- evaluators
@@ -600,7 +559,7 @@ constexpr int KC = 16;                // candidates per spec result
 #endif
 constexpr int LK = COOK_LK;           // entries a lane keeps while building a result
 #ifndef COOK_NCW
-#define COOK_NCW 3
+#define COOK_NCW 4
 #endif
 constexpr int NCW = COOK_NCW;         // commit warps
 
@@ -1043,7 +1002,7 @@ __device__ __forceinline__ double warp_argmax_fast(double f, int v, int& wv, int
 template <bool CONSTR, bool PROF>
 __device__ void commit_warp(const MatchArgs& a, ResolverShared& S, const Latest latest, const int cw) {
   const int lane = threadIdx.x & 31;
-  unsigned long long n_fast = 0, n_group = 0, n_matched = 0, n_fallback = 0, n_slow_turn = 0, n_ztake = 0;
+  unsigned long long n_fast = 0, n_group = 0, n_matched = 0, n_fallback = 0, n_slow_turn = 0, n_ztake = 0, n_relook = 0;
   unsigned long long prof[6] = {0, 0, 0, 0, 0, 0};
   const long long t_start = clock64();
   for (int g = cw;; g += NCW) {
@@ -1162,13 +1121,19 @@ __device__ void commit_warp(const MatchArgs& a, ResolverShared& S, const Latest 
     // entries [s, c_seen) still newest for their VM + listed candidates unchanged since s.
     // src >= 0: log entry index, src < 0: ~candidate index.  `more`: valid items exist
     // outside the list.
-    double f0 = 0.0, f1 = 0.0, f2 = 0.0;
-    int v0 = 0x7fffffff, v1 = 0x7fffffff, v2 = 0x7fffffff, s0 = 0, s1 = 0, s2 = 0, d = 0;
+    // depth 3: with NCW owners up to NCW - 1 entries appear between the first look and the turn; a
+    // deeper list costs more on every job than the rare exact recomputation it avoids (measured)
+    constexpr int TD = 3;
+    double tf[TD];
+    int tv[TD], ts[TD], d = 0;
+#pragma unroll
+    for (int i = 0; i < TD; i++) { tf[i] = 0.0; tv[i] = 0x7fffffff; ts[i] = 0; }
     bool more = false, have = false;
     int c_seen = s;
     long long t1 = PROF ? clock64() : 0;
     unsigned long long w;
     int c = 0;
+  relook:
     while (true) {
       w = S.chain;
       compiler_barrier();
@@ -1176,7 +1141,7 @@ __device__ void commit_warp(const MatchArgs& a, ResolverShared& S, const Latest 
       const int c_now = chain_ncommit(w);
       const bool mine = gd == g;
       if (!have) {
-        // (a) first look: one lane per log entry committed since s, three argmax rounds
+        // (a) first look: one lane per log entry committed since s, TD argmax rounds
         double xf = 0.0;
         int x_vm = 0x7fffffff;
         if (el < c_now) {
@@ -1188,20 +1153,17 @@ __device__ void commit_warp(const MatchArgs& a, ResolverShared& S, const Latest 
         bool xin = el < c_seen && xf > 0.0 && latest.get(x_vm) == el;
         bool ok = lane < n && latest.get(yv) < s;
         const int nvalid = __popc(__ballot_sync(0xffffffffu, xin)) + __popc(__ballot_sync(0xffffffffu, ok));
-        more = nvalid > 3;
-        d = min(nvalid, 3);
+        more = nvalid > TD;
+        d = min(nvalid, TD);
 #pragma unroll
-        for (int rnd = 0; rnd < 3; rnd++) {
+        for (int rnd = 0; rnd < TD; rnd++) {
           const bool use_y = ok && (!xin || better(yf, yv, xf, x_vm));
           const double lf = use_y ? yf : (xin ? xf : 0.0);
           const int lv = use_y ? yv : (xin ? x_vm : 0x7fffffff);
           int bv, bl;
           const double bf = warp_argmax_fast(lf, lv, bv, bl);
           const bool by = __shfl_sync(0xffffffffu, use_y ? 1 : 0, bl) != 0;
-          const int bs = by ? ~bl : s + bl;
-          if (rnd == 0) { f0 = bf; v0 = bv; s0 = bs; }
-          if (rnd == 1) { f1 = bf; v1 = bv; s1 = bs; }
-          if (rnd == 2) { f2 = bf; v2 = bv; s2 = bs; }
+          tf[rnd] = bf; tv[rnd] = bv; ts[rnd] = by ? ~bl : s + bl;
           if (lane == bl) { if (use_y) ok = false; else xin = false; }
         }
         have = true;
@@ -1218,23 +1180,29 @@ __device__ void commit_warp(const MatchArgs& a, ResolverShared& S, const Latest 
         const int nsrc = c_seen;
         c_seen++;
         // the entry supersedes whatever was known about its VM
-        if (d > 0 && v0 == nvm) { f0 = f1; v0 = v1; s0 = s1; f1 = f2; v1 = v2; s1 = s2; d--; }
-        else if (d > 1 && v1 == nvm) { f1 = f2; v1 = v2; s1 = s2; d--; }
-        else if (d > 2 && v2 == nvm) { d--; }
+        bool hit = false;
+#pragma unroll
+        for (int i = 0; i < TD; i++) {
+          hit = hit || (i < d && tv[i] == nvm);
+          if (hit && i + 1 < TD) { tf[i] = tf[i + 1]; tv[i] = tv[i + 1]; ts[i] = ts[i + 1]; }
+        }
+        if (hit) d--;
         if (nf > 0.0) {
-          if (d > 0 && better(nf, nvm, f0, v0)) {
-            f2 = f1; v2 = v1; s2 = s1; f1 = f0; v1 = v0; s1 = s0; f0 = nf; v0 = nvm; s0 = nsrc;
-            if (d == 3) more = true; else d++;
-          } else if (d > 1 && better(nf, nvm, f1, v1)) {
-            f2 = f1; v2 = v1; s2 = s1; f1 = nf; v1 = nvm; s1 = nsrc;
-            if (d == 3) more = true; else d++;
-          } else if (d > 2 && better(nf, nvm, f2, v2)) {
-            f2 = nf; v2 = nvm; s2 = nsrc; more = true;
-          } else if (!more && d < 3) {  // nothing hidden: it is the next best
-            if (d == 0) { f0 = nf; v0 = nvm; s0 = nsrc; }
-            else if (d == 1) { f1 = nf; v1 = nvm; s1 = nsrc; }
-            else { f2 = nf; v2 = nvm; s2 = nsrc; }
-            d++;
+          // position: before the first listed item it beats; behind all of them only if
+          // nothing is hidden (then it is the next best)
+          int pos = TD;
+#pragma unroll
+          for (int i = TD - 1; i >= 0; i--)
+            if (i < d && better(nf, nvm, tf[i], tv[i])) pos = i;
+          if (pos == TD && !more && d < TD) pos = d;
+          if (pos < TD) {
+            if (d == TD) more = true; else d++;   // the last listed item falls out of a full list
+#pragma unroll
+            for (int i = TD - 1; i > 0; i--)
+              if (i > pos) { tf[i] = tf[i - 1]; tv[i] = tv[i - 1]; ts[i] = ts[i - 1]; }
+#pragma unroll
+            for (int i = 0; i < TD; i++)
+              if (i == pos) { tf[i] = nf; tv[i] = nvm; ts[i] = nsrc; }
           } else {
             more = true;
           }
@@ -1256,11 +1224,18 @@ __device__ void commit_warp(const MatchArgs& a, ResolverShared& S, const Latest 
       nf = eval_vm<CONSTR>(a, r, ne_vm, ne, false);
     }
     // best old item that the newest entry did not supersede
-    const bool first = !(d > 0 && v0 == ne_vm);
+    const bool first = !(d > 0 && tv[0] == ne_vm);
     const bool known = first ? (d > 0 || !more) : (d > 1 || !more);  // that rank is known (possibly "none")
-    const double pf = first ? (d > 0 ? f0 : 0.0) : (d > 1 ? f1 : 0.0);
-    const int pv = first ? (d > 0 ? v0 : 0x7fffffff) : (d > 1 ? v1 : 0x7fffffff);
-    const int ps = first ? s0 : s1;
+    if (!known) {
+      // the short list ran dry (its items were superseded one after the other): look at all
+      // lanes' items again at the current version; the list is exact again afterwards
+      have = false;
+      n_relook++;
+      goto relook;
+    }
+    const double pf = first ? (d > 0 ? tf[0] : 0.0) : (d > 1 ? tf[1] : 0.0);
+    const int pv = first ? (d > 0 ? tv[0] : 0x7fffffff) : (d > 1 ? tv[1] : 0x7fffffff);
+    const int ps = first ? ts[0] : ts[1];
     const bool take_new = nf > 0.0 && better(nf, ne_vm, pf, pv);
     const double wf = take_new ? nf : pf;
     const int wv0 = take_new ? ne_vm : pv;
@@ -1328,7 +1303,7 @@ __device__ void commit_warp(const MatchArgs& a, ResolverShared& S, const Latest 
   }
   if (lane == 0) {
     atomicAdd(a.stats + 0, n_fast); atomicAdd(a.stats + 2, n_group); atomicAdd(a.stats + 3, n_matched);
-    atomicAdd(a.stats + 4, n_fallback); atomicAdd(a.stats + 7, n_slow_turn); atomicAdd(a.stats + 24, n_ztake);
+    atomicAdd(a.stats + 4, n_fallback); atomicAdd(a.stats + 7, n_slow_turn); atomicAdd(a.stats + 24, n_ztake); atomicAdd(a.stats + 25, n_relook);
     if (cw == 0) { a.stats[1] = S.n_rescan; a.stats[5] = S.n_trunc; }
     for (int i = 0; i < 6; i++) atomicAdd(a.stats + 8 + i, prof[i]);
   }
@@ -1360,7 +1335,7 @@ __global__ void __launch_bounds__(RES_THREADS, 1) match_kernel(MatchArgs a) {
     }
     __syncthreads();
     // warps 0, 4, 8, 12 share one scheduler (warp id mod 4): the commit warps keep it to themselves
-#ifdef COOK_SPREAD  // A/B: one commit warp per scheduler instead of all on scheduler 0
+#ifndef COOK_PACKED  // one commit warp per scheduler (A/B: COOK_PACKED puts them all on scheduler 0)
     if (warp < NCW) commit_warp<CONSTR, PROF>(a, S, latest, warp);
     else if (warp == NCW) driver_warp<CONSTR>(a, S);
     else if (warp < a.max_spec_warp) spec_warp<CONSTR>(a, S, latest);
@@ -2064,15 +2039,11 @@ static int32_t build_plan(cook_pool* pool, MatchPlan* mp, const int32_t* ranked_
   ma.B = B; ma.bmin = bmin; ma.bmax = bmax; ma.btarget = btarget;
   ma.host_lifetime_mins = params->host_lifetime_mins;
   ma.published = reinterpret_cast<unsigned*>(mp->d_counters + 8); ma.stats = mp->d_stats;
-  ma.isolate_commit = 1;
-  if (const char* ei = getenv("COOK_ISOLATE")) ma.isolate_commit = atoi(ei);
   ma.lookahead = 20;
   ma.poll_ns = 200;
   ma.max_spec_warp = RES_THREADS / 32;
-  ma.spec_rounds = 16;
   ma.spec_kmin = 12;
   if (const char* ek = getenv("COOK_KMIN")) ma.spec_kmin = atoi(ek);
-  if (const char* er = getenv("COOK_SPEC_ROUNDS")) ma.spec_rounds = atoi(er);
   if (const char* ew = getenv("COOK_MAX_SPEC_WARP")) ma.max_spec_warp = atoi(ew);
   if (const char* ep = getenv("COOK_POLL_NS")) ma.poll_ns = atoi(ep);
   if (const char* el = getenv("COOK_LOOKAHEAD")) { int v = atoi(el); if (v >= 2 && v <= RING) ma.lookahead = v; }
@@ -2218,11 +2189,11 @@ static int32_t run_plan(cook_pool* pool, MatchPlan* mp, int32_t* out_considerabl
   CK(pool, cudaEventRecord(pool->ev[4], st));
   CK(pool, cudaStreamSynchronize(st));
   if (prof_on) {
-    const char* nm[25] = {"fast", "chunk_rescan", "group_jobs", "matched", "fallbacks", "trunc_specs",
+    const char* nm[26] = {"fast", "chunk_rescan", "group_jobs", "matched", "fallbacks", "trunc_specs",
                           "skipped", "slow_turns", "c_wait_result", "c_follow_log", "c_decide_commit", "c_to_argmax",
                           "c_end_block", "c_fallback", "res_total", "res_q1_done", "eval_work", "eval_wait",
-                          "eval_loop", "eval_sync", "eval_merge", "eval_work_q1", "eval_rowslots_q1", "blocks", "z_takes"};
-    for (int i = 0; i < 25; i++) fprintf(stderr, "[cook_prof] %-14s %llu\n", nm[i], hstats[i]);
+                          "eval_loop", "eval_sync", "eval_merge", "eval_work_q1", "eval_rowslots_q1", "blocks", "z_takes", "relooks"};
+    for (int i = 0; i < 26; i++) fprintf(stderr, "[cook_prof] %-14s %llu\n", nm[i], hstats[i]);
   }
   if (out_stats) {
     out_stats->n_considerable = n_cons;
