@@ -412,7 +412,7 @@ __device__ void evaluate_row(const MatchArgs& a, const JobRegs& r, const bool gr
   int vv[TOPK];
 #pragma unroll
   for (int i = 0; i < TOPK; i++) { f[i] = 0.0; vv[i] = 0x7fffffff; }
-  if (!grp) {
+  {
     const int O = a.of.O;
     constexpr int U = 4;  // VMs in flight per lane
     int ui = 0;  // index of the lane's VM (bit of `live`)
@@ -513,9 +513,10 @@ __device__ void evaluate_row(const MatchArgs& a, const JobRegs& r, const bool gr
   long long e2 = PROF ? clock64() : 0;
   __syncthreads();  // row complete; E may be rewritten
   if (threadIdx.x == 0) {
-    // feasibility stamp: block + 1 (stale stamps of the buffer's previous blocks are smaller);
-    // group jobs are resolved against live group state, their rows stay empty
-    if (any || grp) atomicMax(a.feas + (size_t)(blk & 1) * a.bmax + ib, blk + 1);
+    // feasibility stamp: block + 1 (stale stamps of the buffer's previous blocks are smaller).
+    // Group constraints are not applied here (they depend on same-cycle placements): the row of
+    // a group job lists its best VMs without them and the resolver filters against live state.
+    if (any) atomicMax(a.feas + (size_t)(blk & 1) * a.bmax + ib, blk + 1);
     // the release orders the CTA's row stores (made visible to this thread by the barrier)
     asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(a.rows_ready + blk), "r"(1u) : "memory");
   }
@@ -601,6 +602,7 @@ struct Cand {  // one candidate VM with its state at the result's version
 struct SpecOut {
   int type, s, n, complete;  // type: Q_JOB / Q_END / Q_EXIT (the commit warps wait on the result flag only)
   double zf;                 // bound: every unchanged VM outside c[] is no better than (zf, zv)
+  int gver, pad;             // group-state version the result was computed against (group jobs)
   int zv, z_real;            // z_real: (zf, zv) is the exact fitness of VM zv (state in c[KC]), not just a bound
   Cand c[KC + 1];            // unsorted; c[KC] = the bound VM when z_real
 };
@@ -693,6 +695,15 @@ struct LaneList {
 };
 
 
+// Sum of the placed-member counts of the job's groups: changes iff a member of one of the job's
+// groups is placed (counts only grow), so equal sums => the group state a result was computed
+// against is still current.
+__device__ __forceinline__ int group_version(const MatchArgs& a, int j) {
+  int v = 0;
+  for (int q = a.jb.group_off[j]; q < a.jb.group_off[j + 1]; q++) v += __ldcg(a.gr.gp_n + a.jb.group_idx[q]);
+  return v;
+}
+
 // Candidate set of one job against the state at version s (warp-wide): up to
 // `depth` VMs such that everything left out is no better than the bound z.
 // Sentinel hits while fewer than `exact_n` candidates are out are resolved by an
@@ -704,6 +715,8 @@ __device__ __forceinline__ void spec_job(const MatchArgs& a, ResolverShared& S, 
   JobRegs r;
   r.c = qe.jc; r.m = qe.jm; r.g = qe.jg; r.ports = qe.jports; r.j = qe.jj;
   const int lo = qe.lo, blk = qe.blk;
+  const bool wg = CONSTR && qe.grp;  // group constraints against the live group state
+  const int gver = wg ? group_version(a, r.j) : 0;  // read BEFORE any group state is used
   const unsigned char* rowp = a.rows + ((size_t)(blk & 1) * a.bmax + qe.row) * ROW_BYTES;
   LaneList L;
   L.init();
@@ -719,7 +732,7 @@ __device__ __forceinline__ void spec_job(const MatchArgs& a, ResolverShared& S, 
     for (int i = TOPK - 1; i >= 0; i--) {  // worst first: every push lands in front
       const bool live = f[i] > 0.0;
       const int vi = live ? v[i] : 0;
-      if (live && latest.get(vi) < lo) {
+      if (live && latest.get(vi) < lo && (!wg || group_pass(a, r, vi))) {
         // a full list drops its worst entry; drops come in improving order, so the last one
         // dropped is the best clean VM of the chunk that is not listed: it becomes the bound
         if (L.f[LK - 1] > 0.0) { L.cbf = L.f[LK - 1]; L.cbv = L.v[LK - 1]; L.cb_real = true; }
@@ -731,7 +744,7 @@ __device__ __forceinline__ void spec_job(const MatchArgs& a, ResolverShared& S, 
   for (int e = lo + lane; e < s; e += 32) {
     int vm, k;
     const VmState st = load_log(&S.log[e & (LOGN - 1)], vm, k);
-    if (latest.get(vm) == e) L.insert(eval_vm<CONSTR>(a, r, vm, st, false), vm, e);
+    if (latest.get(vm) == e) L.insert(eval_vm<CONSTR>(a, r, vm, st, wg), vm, e);
   }
   // ---- selection.  A lane exposes its best entry not yet taken (its head) and keeps back
   // the next one and its sentinels.  Every head that beats everything any lane keeps back is
@@ -784,7 +797,7 @@ __device__ __forceinline__ void spec_job(const MatchArgs& a, ResolverShared& S, 
       for (int v = wl + 32 * lane; v < a.of.O; v += 32 * 32) {  // chunk wl = VMs v with v mod 32 == wl
         if (latest.get(v) >= lo) continue;
         const VmState st = load_snap<CONSTR>(a, blk, v);
-        const double x = eval_vm<CONSTR>(a, r, v, st, false);
+        const double x = eval_vm<CONSTR>(a, r, v, st, wg);
         if (x > 0.0 && better(bf, bv, x, v)) L.insert(x, v, -1);
       }
       if (lane == 0) atomicAdd(&S.n_rescan, 1ull);
@@ -831,7 +844,7 @@ __device__ __forceinline__ void spec_job(const MatchArgs& a, ResolverShared& S, 
       }
     }
   }
-  if (lane == 0) { out.type = Q_JOB; out.s = s; out.n = n; out.complete = complete; out.zf = zf; out.zv = zv; out.z_real = z_real; }
+  if (lane == 0) { out.type = Q_JOB; out.s = s; out.n = n; out.complete = complete; out.zf = zf; out.zv = zv; out.z_real = z_real; out.gver = gver; }
   __syncwarp();
 }
 
@@ -891,10 +904,17 @@ __device__ void driver_warp(const MatchArgs& a, ResolverShared& S) {
     // rows b ready => END(b-2) was processed => the start of block b-1 is recorded
     const int lo = b == 0 ? 0 : S.lo_ring[(b - 1) & 3];
     const int32_t* feas = a.feas + (size_t)(b & 1) * a.bmax;
-    for (int base = 0; base < nj; base += 32) {
+    // all stamps of the block in one L2 round trip (a block has at most MAXB rows)
+    int stamp[MAXB / 32];
+#pragma unroll
+    for (int t = 0; t < MAXB / 32; t++) stamp[t] = (t * 32 + lane) < nj ? __ldcg(feas + t * 32 + lane) : 0;
+#pragma unroll
+    for (int t = 0; t < MAXB / 32; t++) {
+      const int base = t * 32;
+      if (base >= nj) break;
       const int i = base + lane;
       const bool valid = i < nj;
-      const bool fz = valid && __ldcg(feas + i) == b + 1;
+      const bool fz = valid && stamp[t] == b + 1;
       // jobs with no feasible VM at the snapshot are unplaceable now too (resources
       // and count constraints only tighten within a cycle): skip them wholesale.
       if (valid && !fz) { a.assign[k0 + i] = -1; a.fail[k0 + i] = COOK_FAIL_RESOURCES; }
@@ -962,12 +982,6 @@ __device__ void spec_warp(const MatchArgs& a, ResolverShared& S, const Latest la
     const QEntry qe = S.q[slot];
     if (qe.type == Q_EXIT) return;
     if (qe.type != Q_JOB) continue;
-    if (qe.grp) {  // resolved by the commit warp against live group state
-      if (lane == 0) { S.res[slot].type = Q_JOB; S.res[slot].n = 0; S.res[slot].complete = 0; S.res[slot].s = 0; }
-      fence_cta();
-      if (lane == 0) S.res_seq[slot] = g + 1;
-      continue;
-    }
     const int s = chain_ncommit(S.chain);
     compiler_barrier();
     spec_job<CONSTR>(a, S, latest, qe, s, KC, 2, S.res[slot]);
@@ -1079,35 +1093,16 @@ __device__ void commit_warp(const MatchArgs& a, ResolverShared& S, const Latest 
     r.c = qe.jc; r.m = qe.jm; r.g = CONSTR ? qe.jg : 0.0; r.ports = CONSTR ? qe.jports : 0; r.j = qe.jj;
     const int k = qe.k;
     const bool grp = CONSTR && qe.grp;
-    if (grp) {
-      unsigned long long w;
-      while (chain_gdone(w = S.chain) != g) __nanosleep(20);
-      compiler_barrier();
-      const int c = chain_ncommit(w);
-      const QEntry q2 = qe;
-      VmState ws;
-      const int wv = resolve_group_job<CONSTR>(a, S, latest, q2, ws);  // uniform across lanes
-      n_group++;
-      if (lane == 0) {
-        if (wv >= 0) {
-          ws.ac = ws.ac + r.c; ws.am = ws.am + r.m; ws.an += 1; ws.pu += r.ports;
-          store_log(&S.log[c & (LOGN - 1)], wv, k, ws);
-          latest.set(wv, c);
-          for (int q = a.jb.group_off[r.j]; q < a.jb.group_off[r.j + 1]; q++) {
-            const int gi = a.jb.group_idx[q];
-            const int n = __ldcg(a.gr.gp_n + gi);
-            __stcg(a.gr.gp_vm + a.gr.gp_off[gi] + n, wv);
-            __stcg(a.gr.gp_n + gi, n + 1);
-          }
-          __threadfence();  // the next group job may run on another commit warp
-        }
-        fence_cta();
-        S.chain = chain_pack(g + 1, c + (wv >= 0 ? 1 : 0));
+    auto join_groups = [&](int wv) {  // lane 0: record the placement in the job's groups
+      for (int q = a.jb.group_off[r.j]; q < a.jb.group_off[r.j + 1]; q++) {
+        const int gi = a.jb.group_idx[q];
+        const int n = __ldcg(a.gr.gp_n + gi);
+        __stcg(a.gr.gp_vm + a.gr.gp_off[gi] + n, wv);
+        __threadfence();  // the member is visible before the count that covers it
+        __stcg(a.gr.gp_n + gi, n + 1);
       }
-      if (wv >= 0) n_matched++;
-      __syncwarp();
-      continue;
-    }
+      __threadfence();
+    };
     // ---- plain job
     const int s = R->s, n = R->n;
     const bool r_complete = R->complete != 0;
@@ -1147,7 +1142,7 @@ __device__ void commit_warp(const MatchArgs& a, ResolverShared& S, const Latest 
         if (el < c_now) {
           int kk;
           const VmState x = load_log(&S.log[el & (LOGN - 1)], x_vm, kk);
-          xf = eval_vm<CONSTR>(a, r, x_vm, x, false);
+          xf = eval_vm<CONSTR>(a, r, x_vm, x, grp);
         }
         c_seen = c_now;
         bool xin = el < c_seen && xf > 0.0 && latest.get(x_vm) == el;
@@ -1176,7 +1171,7 @@ __device__ void commit_warp(const MatchArgs& a, ResolverShared& S, const Latest 
         // and the list is updated without a warp collective
         int nvm, kk;
         const VmState ne = load_log(&S.log[c_seen & (LOGN - 1)], nvm, kk);
-        const double nf = eval_vm<CONSTR>(a, r, nvm, ne, false);
+        const double nf = eval_vm<CONSTR>(a, r, nvm, ne, grp);
         const int nsrc = c_seen;
         c_seen++;
         // the entry supersedes whatever was known about its VM
@@ -1221,7 +1216,7 @@ __device__ void commit_warp(const MatchArgs& a, ResolverShared& S, const Latest 
     if (c > c_seen) {  // uniform: every lane evaluates the newest entry
       int kk;
       ne = load_log(&S.log[c_seen & (LOGN - 1)], ne_vm, kk);
-      nf = eval_vm<CONSTR>(a, r, ne_vm, ne, false);
+      nf = eval_vm<CONSTR>(a, r, ne_vm, ne, grp);
     }
     // best old item that the newest entry did not supersede
     const bool first = !(d > 0 && tv[0] == ne_vm);
@@ -1246,18 +1241,30 @@ __device__ void commit_warp(const MatchArgs& a, ResolverShared& S, const Latest 
     // since s: it is the best VM outside the set, hence the winner
     const bool take_z = !exact && known && R->z_real != 0 && ne_vm != r_zv && latest.get(r_zv) < s;
     int wv = -1;
-    if (take_z) {
+    auto append = [&](int vm, VmState st) {  // lane 0: the placement becomes log entry c
+      st.ac = st.ac + r.c; st.am = st.am + r.m; st.an += 1; st.pu += r.ports;
+      store_log(&S.log[c & (LOGN - 1)], vm, k, st);
+      latest.set(vm, c);
+      if (grp) join_groups(vm);
+      fence_cta();
+      S.chain = chain_pack(g + 1, c + 1);
+    };
+    if (grp && group_version(a, r.j) != R->gver) {
+      // a member of one of the job's groups was placed since the result was computed: the group
+      // constraints it was filtered with are stale => exact full scan against the live state
+      const QEntry q2 = qe;
+      VmState ws;
+      wv = resolve_group_job<CONSTR>(a, S, latest, q2, ws);  // uniform across lanes
+      n_group++;
+      if (lane == 0) {
+        if (wv >= 0) append(wv, ws);
+        else S.chain = chain_pack(g + 1, c);
+      }
+    } else if (take_z) {
       n_fast++;
       n_ztake++;
       wv = r_zv;
-      ne = R->c[KC].st;
-      if (lane == 0) {
-        ne.ac = ne.ac + r.c; ne.am = ne.am + r.m; ne.an += 1; ne.pu += r.ports;
-        store_log(&S.log[c & (LOGN - 1)], wv, k, ne);
-        latest.set(wv, c);
-        fence_cta();
-        S.chain = chain_pack(g + 1, c + 1);
-      }
+      if (lane == 0) append(wv, R->c[KC].st);
     } else if (exact) {
       n_fast++;
       if (wf > 0.0) {
@@ -1267,13 +1274,7 @@ __device__ void commit_warp(const MatchArgs& a, ResolverShared& S, const Latest 
           if (ps >= 0) ne = load_log(&S.log[ps & (LOGN - 1)], vm2, kk);
           else ne = R->c[(~ps) & (KC - 1)].st;
         }
-        if (lane == 0) {
-          ne.ac = ne.ac + r.c; ne.am = ne.am + r.m; ne.an += 1; ne.pu += r.ports;
-          store_log(&S.log[c & (LOGN - 1)], wv, k, ne);
-          latest.set(wv, c);
-          fence_cta();
-          S.chain = chain_pack(g + 1, c + 1);
-        }
+        if (lane == 0) append(wv, ne);
       } else if (lane == 0) {
         S.chain = chain_pack(g + 1, c);  // assign / fail keep their defaults (-1, COOK_FAIL_CONSTRAINT)
       }
@@ -1286,14 +1287,8 @@ __device__ void commit_warp(const MatchArgs& a, ResolverShared& S, const Latest 
       n_fallback++;
       const bool got = S.res[RING].n > 0;
       if (lane == 0) {
-        if (got) {
-          Cand z = S.res[RING].c[0];
-          z.st.ac = z.st.ac + r.c; z.st.am = z.st.am + r.m; z.st.an += 1; z.st.pu += r.ports;
-          store_log(&S.log[c & (LOGN - 1)], z.vm, k, z.st);
-          latest.set(z.vm, c);
-          fence_cta();
-        }
-        S.chain = chain_pack(g + 1, c + (got ? 1 : 0));
+        if (got) append(S.res[RING].c[0].vm, S.res[RING].c[0].st);
+        else S.chain = chain_pack(g + 1, c);
       }
       if (got) wv = 0;
     }
@@ -1836,10 +1831,17 @@ static int32_t build_plan(cook_pool* pool, MatchPlan* mp, const int32_t* ranked_
   mp->valid = false;
   mp->h2d_bytes = 0;
   // host-side prep: offers sorted by hostname rank (tie-break order)
-  std::vector<int32_t> perm(O);
-  std::iota(perm.begin(), perm.end(), 0);
-  std::sort(perm.begin(), perm.end(),
-            [&](int32_t x, int32_t y) { return offers->name_rank[x] < offers->name_rank[y]; });
+  std::vector<int32_t> perm(O, -1);
+  bool dense = true;  // name_rank is normally a permutation of 0..O-1: invert it directly
+  for (int i = 0; i < O && dense; i++) {
+    const int32_t r = offers->name_rank[i];
+    if (r < 0 || r >= O || perm[r] >= 0) dense = false; else perm[r] = i;
+  }
+  if (!dense) {
+    std::iota(perm.begin(), perm.end(), 0);
+    std::stable_sort(perm.begin(), perm.end(),
+                     [&](int32_t x, int32_t y) { return offers->name_rank[x] < offers->name_rank[y]; });
+  }
   // per-group capacity of the placed list = #member jobs
   const int G = groups ? groups->n_groups : 0;
   std::vector<int32_t> gp_off(G + 1, 0);
