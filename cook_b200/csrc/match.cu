@@ -52,6 +52,15 @@ struct __align__(32) VmStatic { double lc, lm, rc, rm; };
 struct __align__(32) VmDyn { double ac, am, yc, ym; };
 struct __align__(8) VmCnt { int an, pu; };  // tasks assigned this cycle, ports used (constraint kernel)
 
+// Offer-side inputs of the hard constraints, one 48 B record per VM (rank space).
+struct __align__(16) VmCons {
+  int hostname_id, location, max_tasks, num_tasks;          // -1 = absent (location, max_tasks)
+  int run_count, flags, gpu_lo, ports_total;                // flags: bit0 k8s, bit1 reserved, bits 8.. #gpu models
+  long long host_start;                                     // -1 = absent
+  int disk_lo, disk_n;
+};
+enum { VC_K8S = 1, VC_RESERVED = 2 };
+
 struct VmState {  // everything one fit evaluation needs about a VM
   double ac, am, lc, lm, rc, rm, yc, ym;
   int an, pu;
@@ -93,6 +102,10 @@ struct OfferDev {
   const int64_t* host_start;
   int n_attr_cols; const int32_t* attr;
   const uint8_t* reserved;
+  // rank space (index v), built on the device per cycle: everything the constraints need
+  // about a VM in three 128-bit loads + the attribute table gathered by v
+  const struct VmCons* vc;
+  const int32_t* attr_v;   // [n_attr_cols][O]
 };
 
 struct GroupDev {
@@ -187,61 +200,69 @@ __device__ __forceinline__ double csr_lookup(const int32_t* off, const int32_t* 
 __device__ bool constraints_pass(const MatchArgs& a, const JobRegs& r, int v, int an) {
   const JobDev& jb = a.jb;
   const OfferDev& of = a.of;
-  const int o = of.perm[v];
   const int j = r.j;
+  // the VM's record: three independent 128-bit loads, issued before any check
+  const int4* vcp = reinterpret_cast<const int4*>(of.vc + v);
+  const int4 c0 = __ldg(vcp), c1 = __ldg(vcp + 1), c2 = __ldg(vcp + 2);
+  const int hostname = c0.x, location = c0.y, max_tasks = c0.z, num_tasks = c0.w;
+  const int run_count = c1.x, flags = c1.y, gpu_lo = c1.z;
+  const long long host_start = ((long long)(unsigned)c2.y << 32) | (unsigned)c2.x;
+  const int disk_lo = c2.z, disk_n = c2.w;
+  const int gpu_n = flags >> 8;
   if (jb.ckpt_location && jb.ckpt_location[j] >= 0) {
-    int loc = of.location ? of.location[o] : -1;
-    if (loc != jb.ckpt_location[j]) return false;
+    if (location != jb.ckpt_location[j]) return false;
   }
-  if (jb.est_end_ms && jb.est_end_ms[j] >= 0 && of.host_start && of.host_start[o] >= 0) {
-    long long death = 1000LL * of.host_start[o] + 60000LL * a.host_lifetime_mins;
+  if (jb.est_end_ms && jb.est_end_ms[j] >= 0 && host_start >= 0) {
+    long long death = 1000LL * host_start + 60000LL * a.host_lifetime_mins;
     if (!(jb.est_end_ms[j] < death)) return false;
   }
   if (jb.attr_off) {
     for (int k = jb.attr_off[j]; k < jb.attr_off[j + 1]; k++) {
       int col = jb.attr_col[k], val = jb.attr_val[k];
       if (col < 0 || col >= of.n_attr_cols) return false;
-      int hv = of.attr[(size_t)col * of.O + o];
+      int hv = of.attr_v[(size_t)col * of.O + v];
       if (val <= 0 || hv != val) return false;
     }
   }
-  const bool k8s = of.is_k8s && of.is_k8s[o];
+  const bool k8s = flags & VC_K8S;
   if (jb.disk_request && jb.disk_request[j] >= 0.0 && k8s) {
-    double space = csr_lookup(of.disk_off, of.disk_type, of.disk_space, o,
-                              jb.disk_type ? jb.disk_type[j] : -1);
+    const int want = jb.disk_type ? jb.disk_type[j] : -1;
+    double space = 0.0;
+    for (int i = 0; i < disk_n; i++)
+      if (of.disk_type[disk_lo + i] == want) { space = of.disk_space[disk_lo + i]; break; }
     if (!(space >= jb.disk_request[j])) return false;
   }
   if (k8s) {
     if (r.g > 0.0) {
-      double have = csr_lookup(of.gpu_off, of.gpu_model, of.gpu_count, o,
-                               jb.gpu_model ? jb.gpu_model[j] : -1);
-      int on_vm = (of.run_count ? of.run_count[o] : 0) + an;
+      const int want = jb.gpu_model ? jb.gpu_model[j] : -1;
+      double have = 0.0;
+      for (int i = 0; i < gpu_n; i++)
+        if (of.gpu_model[gpu_lo + i] == want) { have = of.gpu_count[gpu_lo + i]; break; }
+      int on_vm = run_count + an;
       if (!(have == r.g && on_vm == 0)) return false;
     } else {
-      int nmodels = of.gpu_off ? of.gpu_off[o + 1] - of.gpu_off[o] : 0;
-      if (nmodels != 0) return false;
+      if (gpu_n != 0) return false;
     }
   } else if (!(r.g == 0.0)) {
     return false;
   }
   if (jb.novel_off) {
-    int h = of.hostname_id[o];
     for (int k = jb.novel_off[j]; k < jb.novel_off[j + 1]; k++)
-      if (jb.novel_host[k] == h) return false;
+      if (jb.novel_host[k] == hostname) return false;
   }
-  if (of.max_tasks && of.max_tasks[o] >= 0) {
-    int total = (of.num_tasks ? of.num_tasks[o] : 0) + an;
-    if (!(total < of.max_tasks[o])) return false;
+  if (max_tasks >= 0) {
+    int total = num_tasks + an;
+    if (!(total < max_tasks)) return false;
   }
-  if (of.reserved && of.reserved[o]) {
+  if (flags & VC_RESERVED) {
     int mine = jb.reserved_host ? jb.reserved_host[j] : -1;
-    if (mine != of.hostname_id[o]) return false;
+    if (mine != hostname) return false;
   }
   return true;
 }
 
 __device__ __forceinline__ int vm_attr(const OfferDev& of, int col, int v) {
-  return (col >= 0 && col < of.n_attr_cols) ? of.attr[(size_t)col * of.O + of.perm[v]] : 0;
+  return (col >= 0 && col < of.n_attr_cols) ? of.attr_v[(size_t)col * of.O + v] : 0;
 }
 
 // Group constraints (constraints.clj:586-678) against the CURRENT group state
@@ -256,7 +277,7 @@ __device__ bool group_pass(const MatchArgs& a, const JobRegs& r, int v) {
     const int c0 = gr.cot_off[g], c1 = gr.cot_off[g + 1];
     const int p0 = gr.gp_off[g], pn = __ldcg(gr.gp_n + g);
     if (kind == COOK_GROUP_UNIQUE) {
-      const int h = of.hostname_id[of.perm[v]];
+      const int h = of.vc[v].hostname_id;
       for (int c = c0; c < c1; c++)
         if (gr.cot_host[c] == h) return false;
       for (int p = 0; p < pn; p++)
@@ -318,7 +339,7 @@ __device__ __forceinline__ double eval_vm(const MatchArgs& a, const JobRegs& r, 
     if (st.ac + r.c > st.lc) return 0.0;
     if (st.am + r.m > st.lm) return 0.0;
     if (r.ports > 0) {
-      int tot = a.of.ports_total ? a.of.ports_total[a.of.perm[v]] : 0;
+      const int tot = a.of.vc[v].ports_total;
       if (r.ports > tot - st.pu) return 0.0;
     }
     if (!constraints_pass(a, r, v, st.an)) return 0.0;
@@ -1714,6 +1735,28 @@ __global__ void __launch_bounds__(SMIN_TB) suffix_min_apply_kernel(int n, int nb
   if (k < n) { sc[k] = fmin(sc[k], c); sm[k] = fmin(sm[k], m); }
 }
 
+// offer-side constraint inputs gathered into rank space (one record per VM) + attribute table
+__global__ void gather_cons_kernel(OfferDev of, VmCons* vc, int32_t* attr_v) {
+  int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= of.O) return;
+  const int o = of.perm[v];
+  VmCons c;
+  c.hostname_id = of.hostname_id ? of.hostname_id[o] : -1;
+  c.location = of.location ? of.location[o] : -1;
+  c.max_tasks = of.max_tasks ? of.max_tasks[o] : -1;
+  c.num_tasks = of.num_tasks ? of.num_tasks[o] : 0;
+  c.run_count = of.run_count ? of.run_count[o] : 0;
+  const int gn = of.gpu_off ? of.gpu_off[o + 1] - of.gpu_off[o] : 0;
+  c.flags = ((of.is_k8s && of.is_k8s[o]) ? VC_K8S : 0) | ((of.reserved && of.reserved[o]) ? VC_RESERVED : 0) | (gn << 8);
+  c.gpu_lo = of.gpu_off ? of.gpu_off[o] : 0;
+  c.ports_total = of.ports_total ? of.ports_total[o] : 0;
+  c.host_start = of.host_start ? of.host_start[o] : -1;
+  c.disk_lo = of.disk_off ? of.disk_off[o] : 0;
+  c.disk_n = of.disk_off ? of.disk_off[o + 1] - of.disk_off[o] : 0;
+  vc[v] = c;
+  for (int col = 0; col < of.n_attr_cols; col++) attr_v[(size_t)col * of.O + v] = of.attr[(size_t)col * of.O + o];
+}
+
 // per-cycle reset of the dynamic state (both buffers) + the reciprocals of the fitness
 // denominators (static for the cycle)
 __global__ void init_dyn_kernel(const VmStatic* vs, int O, VmDyn* d0, VmDyn* d1, VmCnt* n0, VmCnt* n1) {
@@ -1798,6 +1841,8 @@ struct MatchPlan {
   double* d_kg = nullptr;
   int32_t* d_kports = nullptr;
   int32_t* d_ports_total = nullptr;
+  VmCons* d_vc = nullptr;
+  int32_t* d_attr_v = nullptr;
   int32_t *d_cons = nullptr, *d_out_assign = nullptr, *d_out_ports = nullptr, *d_used = nullptr;
   double *d_kc = nullptr, *d_km = nullptr;
   uint8_t* d_kflags = nullptr;
@@ -1911,6 +1956,7 @@ static int32_t build_plan(cook_pool* pool, MatchPlan* mp, const int32_t* ranked_
   sz.add<unsigned long long>(32); sz.add<int32_t>(16);
   sz.add<VmStatic>(O + 1); sz.add<VmDyn>(O + 1); sz.add<VmDyn>(O + 1); sz.add<int>(O + 1);
   sz.add<VmCnt>(O + 1); sz.add<VmCnt>(O + 1);
+  sz.add<VmCons>(O + 1); sz.add<int32_t>((size_t)offers->n_attr_cols * O + 1);
   sz.add<double>(NC + 1); sz.add<double>(NC + 1); sz.add<double>(NC / 256 + 2); sz.add<double>(NC / 256 + 2);
   CK(pool, ar.reserve(sz.off + (1 << 18)));
   ar.reset();
@@ -1966,6 +2012,9 @@ static int32_t build_plan(cook_pool* pool, MatchPlan* mp, const int32_t* ranked_
   { int64_t* p; UP(p, offers->host_start_time, O); of.host_start = p; }
   of.n_attr_cols = offers->attr ? offers->n_attr_cols : 0;
   if (of.n_attr_cols > 0) { int32_t* p; UP(p, offers->attr, (size_t)of.n_attr_cols * O); of.attr = p; }
+  mp->d_vc = ar.take<VmCons>(O + 1);
+  mp->d_attr_v = ar.take<int32_t>((size_t)of.n_attr_cols * O + 1);
+  of.vc = mp->d_vc; of.attr_v = mp->d_attr_v;
   if ((jb.novel_off || of.reserved || (G && jb.group_off)) && !of.hostname_id)
     return set_err(pool, COOK_E_BADARG, "cook_match: hostname_id column required by constraints");
 
@@ -2089,6 +2138,10 @@ static int32_t run_plan(cook_pool* pool, MatchPlan* mp, int32_t* out_considerabl
     if (mp->d_ports_total) {
       ports_total_kernel<<<(O + TB - 1) / TB, TB, 0, st>>>(ma.of.port_off, ma.of.port_begin,
                                                            ma.of.port_end, O, mp->d_ports_total);
+      launches++;
+    }
+    if (mp->constr) {
+      gather_cons_kernel<<<(O + TB - 1) / TB, TB, 0, st>>>(ma.of, mp->d_vc, mp->d_attr_v);
       launches++;
     }
   }
