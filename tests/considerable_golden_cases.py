@@ -26,7 +26,46 @@ def _considerable(eng, jobs, quota, num_considerable, plugin_accept=1, tokens=No
     return [int(x) for x in m["considerable"]]
 
 
+def _k9(eng, jobs, users_of, quota, usage, pool_quota, nc=10):
+    """jobs: [(cpus, mem)], users_of: user index per job; quota/usage: per-user dicts of lists."""
+    J = len(jobs)
+    nu = max(users_of) + 1
+    jb = abi.JobsSoA(n=J, user=np.array(users_of, np.int32), cpus=np.array([j[0] for j in jobs], float),
+                     mem=np.array([j[1] for j in jobs], float), gpus=np.zeros(J),
+                     allowed=np.ones(J, np.uint8), plugin_accept=np.ones(J, np.uint8))
+    of = abi.OffersSoA(n=1, hostname_id=np.zeros(1, np.int32), name_rank=np.zeros(1, np.int32),
+                       cpus=np.array([1.0]), mem=np.array([1.0]), run_cpus=np.zeros(1), run_mem=np.zeros(1),
+                       run_count=np.zeros(1, np.int32), n_attr_cols=0)
+    users = abi.make_users(nu, quota={k: np.array(v, float) for k, v in quota.items()} if quota else None,
+                           usage={k: np.array(v, float) for k, v in usage.items()})
+    pq = abi.make_pool_quota(pool_quota) if pool_quota else None
+    m = eng.match(np.arange(J, dtype=np.int32), jb, of, users, traces.match_params(nc), pool_quota=pq)
+    return [int(x) for x in m["considerable"]]
+
+
+def check_k9(eng):
+    """K9: test/cook/test/tools.clj:763-816 (pool quota, user quota, user quota before pool quota)."""
+    q4 = [(2, 2048), (1, 1024), (3, 4096), (1, 1024)]
+    use = {"count": [1], "cpus": [2], "mem": [1024]}
+    big = 1e18
+    # filter-based-on-pool-quota (:763-778); the running usage counts against the pool quota
+    for pq, expect in [({"count": 1, "cpus": 2, "mem": 1024, "gpus": big}, []),
+                       ({"count": 10, "cpus": 20, "mem": 32768, "gpus": big}, [0, 1, 2, 3]),
+                       ({"count": 4, "cpus": 20, "mem": 6144, "gpus": big}, [0, 1])]:
+        assert _k9(eng, q4, [0, 0, 0, 0], None, use, pq) == expect, ("K9 pool", pq)
+    # filter-based-on-user-quota (:780-797)
+    for uq, expect in [({"count": [1], "cpus": [2], "mem": [1024]}, []),
+                       ({"count": [10], "cpus": [20], "mem": [32768]}, [0, 1, 2, 3]),
+                       ({"count": [4], "cpus": [20], "mem": [6144]}, [0, 1])]:
+        assert _k9(eng, q4, [0, 0, 0, 0], uq, use, None) == expect, ("K9 user", uq)
+    # filter-pending-jobs-for-quota (:799-816): user quota filters first => [job-1 job-4]
+    got = _k9(eng, [(1, 1)] * 4, [0, 0, 0, 1], {"count": [2, 2], "cpus": [100, 100], "mem": [100, 100]},
+              {"count": [1, 1], "cpus": [1, 1], "mem": [1, 1]}, {"count": 4, "cpus": 100, "mem": 100, "gpus": big})
+    assert got == [0, 3], ("K9 order", got)
+
+
 def check_all(eng):
+    check_k9(eng)
     big = {"count": 10, "cpus": 50, "mem": 32768, "gpus": 10}
     # every job deferred by the launch plugin => nothing considerable
     assert _considerable(eng, NON_GPU, big, 5, plugin_accept=0) == []

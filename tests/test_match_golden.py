@@ -45,3 +45,33 @@ def test_rebalance_constraint_golden_oracle(oracle):
 def test_rebalance_constraint_golden_gpu(gpu):
     from rebalance_constraint_golden import check_all as check_reb
     check_reb(gpu)
+
+
+def _k17(eng):
+    """K17: test/cook/test/rebalancer.clj:55-113 (init-state): DRU of 8 running tasks, share
+    mem 25 / cpus 25; the rebalancer's priority map lists them by descending DRU."""
+    import numpy as np
+    from cook_b200 import abi
+    from cook_b200.engine import _empty_tasks
+    run = [("ljin", 10, 10), ("ljin", 5, 5), ("ljin", 15, 25), ("ljin", 25, 15),
+           ("wzhao", 8, 8), ("wzhao", 10, 10), ("wzhao", 10, 10), ("wzhao", 10, 10)]   # (user, mem, cpus)
+    uid = {"ljin": 0, "wzhao": 1}
+    R = len(run)
+    t = abi.make_tasks(user=np.array([uid[r[0]] for r in run], np.int32), priority=np.full(R, 50, np.int32),
+                       start_time=np.full(R, 1_600_000_000_000, np.int64),
+                       task_id=np.arange(1000, 1000 + R, dtype=np.int64), job_id=np.arange(1, R + 1, dtype=np.int64),
+                       cpus=np.array([float(r[2]) for r in run]), mem=np.array([float(r[1]) for r in run]))
+    users = abi.make_users(2, div_mem=np.full(2, 25.0), div_cpus=np.full(2, 25.0), div_gpus=np.full(2, 1.0))
+    out = eng.rank(t, _empty_tasks(), users)
+    assert np.allclose(out["dru"][:R], [0.4, 0.6, 1.6, 2.2, 0.32, 0.72, 1.12, 1.52], rtol=1e-12, atol=0)
+    # ascending merge order reversed = [t4 t3 t8 t7 t6 t2 t1 t5]
+    assert [int(x) for x in out["order"][::-1]] == [3, 2, 7, 6, 5, 1, 0, 4]
+
+
+def test_init_state_dru_golden_oracle(oracle):
+    _k17(oracle)
+
+
+@pytest.mark.gpu
+def test_init_state_dru_golden_gpu(gpu):
+    _k17(gpu)
