@@ -113,7 +113,7 @@ class MatchParams(C.Structure):
     _fields_ = [("num_considerable", C.c_int32), ("enforce_rate_limit", C.c_int32),
                 ("host_lifetime_mins", C.c_int32), ("fitness_kind", C.c_int32),
                 ("good_enough_fitness", C.c_double), ("reuse_resident", C.c_int32),
-                ("reserved0", C.c_int32)]
+                ("max_ctas", C.c_int32)]
 
 
 class MatchStats(C.Structure):

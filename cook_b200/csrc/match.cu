@@ -2106,7 +2106,7 @@ static int32_t build_plan(cook_pool* pool, MatchPlan* mp, const int32_t* ranked_
 
 static int32_t run_plan(cook_pool* pool, MatchPlan* mp, int32_t* out_considerable,
                         int32_t* out_assign, int32_t* out_ports, uint8_t* out_fail_reason,
-                        cook_match_stats* out_stats, bool uploaded) {
+                        cook_match_stats* out_stats, bool uploaded, int max_ctas) {
   cudaStream_t st = pool->stream;
   const int O = mp->O, U = mp->U, n_ranked = mp->n_ranked, max_ports = mp->max_ports;
   MatchArgs& ma = mp->ma;
@@ -2211,6 +2211,7 @@ static int32_t run_plan(cook_pool* pool, MatchPlan* mp, int32_t* out_considerabl
                              : (prof_on ? (void*)match_kernel<false, true> : (void*)match_kernel<false, false>);
       CK(pool, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       int grid = pool->sm_count;
+      if (max_ctas > 0) grid = std::min(grid, max_ctas);  // pools sharing one GPU
       int occ = 0;
       CK(pool, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kfn, RES_THREADS, smem));
       if (occ < 1) return set_err(pool, COOK_E_CUDA, "cook_match: kernel does not fit on an SM");
@@ -2311,5 +2312,6 @@ extern "C" int32_t cook_match(cook_pool* pool, const int32_t* ranked_idx, int32_
                             params, max_ports);
     if (rc != COOK_OK) { mp->valid = false; return rc; }
   }
-  return run_plan(pool, mp, out_considerable, out_assign, out_ports, out_fail_reason, out_stats, !reuse);
+  return run_plan(pool, mp, out_considerable, out_assign, out_ports, out_fail_reason, out_stats, !reuse,
+                  params->max_ctas);
 }

@@ -110,9 +110,9 @@ def gen_c2(seed=2, n_jobs=100_000, n_offers=5_000, n_users=1_000, n_running=20_0
     return gen_pool(seed, n_jobs, n_offers, n_users, n_running)
 
 
-def match_params(num_considerable, enforce_rate_limit=0, host_lifetime_mins=0, reuse_resident=0):
+def match_params(num_considerable, enforce_rate_limit=0, host_lifetime_mins=0, reuse_resident=0, max_ctas=0):
     return abi.MatchParams(int(num_considerable), int(enforce_rate_limit), int(host_lifetime_mins),
-                           0, 1.0, int(reuse_resident), 0)
+                           0, 1.0, int(reuse_resident), int(max_ctas))
 
 
 def add_constraints(t, seed, *, n_attr_cols=8, attr_card=(3, 6, 24, 2, 2, 4, 5, 7), frac_attr=0.30,

@@ -244,7 +244,11 @@ typedef struct {
                                     cook_match on this handle and still in HBM:
                                     skip the upload stage (columnar-mirror mode,
                                     SURVEY §8f-1); error if nothing is resident */
-  int32_t reserved0;
+  int32_t max_ctas;              /* 0 = the whole GPU.  > 0: the matcher kernel uses at
+                                    most this many thread blocks (one per SM), so several
+                                    pools of one GPU can run their cycles side by side
+                                    (Cook's pools are independent, scheduler.clj:2425-2466);
+                                    results do not depend on it                           */
 } cook_match_params;
 
 enum { /* out_fail_reason codes (first failing check on the LAST VM evaluated

@@ -203,3 +203,33 @@ def test_wide_offer_tables(gpu, oracle, seed, nj, no):
     mo = oracle.match(ranked, t["jobs"], t["offers"], t["users"], prm)
     assert np.array_equal(mg["considerable"], mo["considerable"])
     assert np.array_equal(mg["assign"], mo["assign"])
+
+
+def test_pools_side_by_side_on_one_gpu(oracle):
+    """Four pools run their cycles concurrently on one GPU (37 thread blocks each, one host
+    thread per pool as in Cook's per-pool match loops): same results as the oracle."""
+    import threading
+    from cook_b200.engine import GpuEngine
+    shapes = [(12_000, 600), (9_000, 500), (6_000, 300), (3_000, 150)]
+    pools = []
+    for p, (nj, no) in enumerate(shapes):
+        t = traces.gen_c3_pool(400 + p, nj, no, 200, nj // 5)
+        ranked = oracle.rank(t["running"], t["pending"], t["users"])["ranked"]
+        prm = traces.match_params(nj, host_lifetime_mins=t["host_lifetime_mins"], max_ctas=37)
+        pools.append((t, ranked, prm, GpuEngine(pool_name=f"pool-{p}")))
+    out = [None] * len(pools)
+
+    def cycle(i):
+        t, ranked, prm, eng = pools[i]
+        out[i] = eng.match(ranked, t["jobs"], t["offers"], t["users"], prm, groups=t["groups"], max_ports=2)
+
+    for rep in range(2):
+        th = [threading.Thread(target=cycle, args=(i,)) for i in range(len(pools))]
+        [x.start() for x in th]
+        [x.join() for x in th]
+        for i, (t, ranked, prm, eng) in enumerate(pools):
+            mo = oracle.match(ranked, t["jobs"], t["offers"], t["users"], prm, groups=t["groups"], max_ports=2)
+            assert np.array_equal(out[i]["assign"], mo["assign"]), (rep, i)
+            assert np.array_equal(out[i]["ports"], mo["ports"])
+    for _, _, _, eng in pools:
+        eng.close()
