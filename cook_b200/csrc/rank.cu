@@ -125,7 +125,11 @@ __global__ void __launch_bounds__(128) user_fold_kernel(
   if (e <= s) return;
   const double md = uc.div_mem[u], cd = uc.div_cpus[u], gd = uc.div_gpus[u];
   const double qn = uc.q_count[u], qc = uc.q_cpus[u], qm = uc.q_mem[u], qg = uc.q_gpus[u];
-  double am = 0.0, ac = 0.0, ag = 0.0;  // carried cumulative sums (identical in all lanes)
+  // The three cumulative sums are independent serial chains: lanes 0..2 run one each over
+  // the batch staged in shared memory (carried in `acc`), then every lane reads its prefix.
+  __shared__ double fold_s[4][3][32];
+  double (*fs)[32] = fold_s[threadIdx.x >> 5];
+  double acc = 0.0;
   int over = 0;
   bool cut = false;
   int kept = 0;
@@ -137,15 +141,17 @@ __global__ void __launch_bounds__(128) user_fold_kernel(
       int ti = idx[p];
       xm = t.mem[ti]; xc = t.cpus[ti]; xg = t.gpus[ti];
     }
-    double mym = 0.0, myc = 0.0, myg = 0.0;
+    fs[0][lane] = xm; fs[1][lane] = xc; fs[2][lane] = xg;
+    __syncwarp();
     int cntn = min(32, e - base);
-#pragma unroll 4
-    for (int l = 0; l < cntn; l++) {
-      am = am + __shfl_sync(0xffffffffu, xm, l);
-      ac = ac + __shfl_sync(0xffffffffu, xc, l);
-      ag = ag + __shfl_sync(0xffffffffu, xg, l);
-      if (lane == l) { mym = am; myc = ac; myg = ag; }
+    if (lane < 3) {
+      double* row = fs[lane];
+#pragma unroll 8
+      for (int l = 0; l < cntn; l++) { acc = acc + row[l]; row[l] = acc; }
     }
+    __syncwarp();
+    const double mym = fs[0][lane], myc = fs[1][lane], myg = fs[2][lane];
+    __syncwarp();
     // scheduler.clj:2057-2071: keep while #violating prefixes <= limit
     bool viol = false;
     if (p < e) {
@@ -176,20 +182,24 @@ __global__ void __launch_bounds__(128) user_fold_kernel(
 struct QueueFilterArgs {
   const int32_t* pos_sorted;  // positions (into user-sorted array) in merge order
   const int32_t* idx;         // sorted position -> combined task index
-  int n_kept;
+  const int32_t* n_kept;      // device: tasks that survived limit-over-quota-jobs
   int R;                      // running count (combined index >= R => pending)
   const double* cpus;         // combined columns
   const double* mem;
   const double* gpus;
-  cook_pool_quota pool_q, group_q;
-  double pool_usage[4];       // filled by pool_usage_kernel
-  double group_usage[4];
   int filter_offensive;
   double off_mem, off_cpus;
   int32_t* out_order;         // combined task index per emitted task
   int32_t* out_ranked;        // pending indices surviving all filters
   int32_t* out_n;
+  // queue-order scratch (one entry per emitted task)
+  int32_t* ti_at;
+  uint8_t* flag;              // pending job still in the queue after the filters so far
+  double *xc, *xm, *xg;       // its request (0 for running tasks)
+  int32_t* blk_cnt;           // per block of QF_TB entries: survivors, then exclusive offsets
 };
+
+constexpr int QF_TB = 256;
 
 // Σ running usage of the pool (scheduler.clj:2118-2123) in input order.
 __global__ void pool_usage_kernel(const double* cpus, const double* mem, const double* gpus, int R,
@@ -210,61 +220,117 @@ __global__ void pool_usage_kernel(const double* cpus, const double* mem, const d
   if (lane == 0) { out4[0] = (double)R; out4[1] = ac; out4[2] = am; out4[3] = ag; }
 }
 
-// K5: single warp; stable, order-preserving sequence of filters
-// (tools.clj:654-668 filter-sequential: state advances for rejected jobs too).
-__global__ void queue_filter_kernel(QueueFilterArgs a, const double* pool_usage_dev) {
-  const int lane = threadIdx.x;
-  double pc = pool_usage_dev[1], pm = pool_usage_dev[2], pg = pool_usage_dev[3], pn = pool_usage_dev[0];
-  double gc = a.group_usage[1], gm = a.group_usage[2], gg = a.group_usage[3], gn = a.group_usage[0];
-  int n_out = 0;
-  for (int base = 0; base < a.n_kept; base += 32) {
-    int i = base + lane;
-    bool valid = i < a.n_kept;
-    int ti = -1;
-    if (valid) {
-      ti = a.idx[a.pos_sorted[i]];
-      if (a.out_order) a.out_order[i] = ti;
+// K5 step 1: the merged order as task indices, with each pending job's request
+// laid out in queue order so that the sequential filters below stream it.
+__global__ void __launch_bounds__(QF_TB) qf_gather_kernel(QueueFilterArgs a) {
+  const int i = blockIdx.x * QF_TB + threadIdx.x;
+  if (i >= *a.n_kept) return;
+  const int ti = a.idx[a.pos_sorted[i]];
+  if (a.out_order) a.out_order[i] = ti;
+  const bool pend = ti >= a.R;
+  a.ti_at[i] = ti;
+  a.flag[i] = pend;
+  a.xc[i] = pend ? a.cpus[ti] : 0.0;
+  a.xm[i] = pend ? a.mem[ti] : 0.0;
+  a.xg[i] = pend ? a.gpus[ti] : 0.0;
+}
+
+// K5 step 2, once per enabled quota (pool, then quota group): tools.clj:654-668
+// filter-sequential -- the usage advances for every job that reaches the filter,
+// kept or not, in queue order, with the reference's left-fold association.  The
+// four running sums are four independent serial chains: one thread each over a
+// chunk staged in shared memory (a job that did not reach the filter adds 0.0,
+// which leaves a sum unchanged); everything else is parallel.
+constexpr int QF_CH = 1024;
+__global__ void __launch_bounds__(QF_CH) qf_quota_kernel(QueueFilterArgs a, cook_pool_quota q,
+                                                         const double* usage4) {
+  __shared__ double s[4][QF_CH];
+  const int tid = threadIdx.x, n = *a.n_kept;
+  const int chain = tid >> 5;                       // chain k runs on lane 0 of warp k
+  double acc = (tid & 31) == 0 && chain < 4 ? usage4[chain] : 0.0;
+  for (int base = 0; base < n; base += QF_CH) {
+    const int i = base + tid, cnt = min(QF_CH, n - base);
+    bool f = false;
+    if (i < n) {
+      f = a.flag[i];
+      s[0][tid] = f ? 1.0 : 0.0;
+      s[1][tid] = f ? a.xc[i] : 0.0;
+      s[2][tid] = f ? a.xm[i] : 0.0;
+      s[3][tid] = f ? a.xg[i] : 0.0;
     }
-    bool pend = valid && ti >= a.R;
-    double xc = 0.0, xm = 0.0, xg = 0.0;
-    if (pend) { xc = a.cpus[ti]; xm = a.mem[ti]; xg = a.gpus[ti]; }
-    bool keep = pend;
-    if (a.pool_q.enabled) {
-      unsigned mask = __ballot_sync(0xffffffffu, keep);
-      double mc = 0, mm = 0, mg = 0, mn = 0;
-      while (mask) {
-        int l = __ffs(mask) - 1;
-        mask &= mask - 1;
-        pn = pn + 1.0;
-        pc = pc + __shfl_sync(0xffffffffu, xc, l);
-        pm = pm + __shfl_sync(0xffffffffu, xm, l);
-        pg = pg + __shfl_sync(0xffffffffu, xg, l);
-        if (lane == l) { mc = pc; mm = pm; mg = pg; mn = pn; }
-      }
-      if (keep)
-        keep = mn <= a.pool_q.count && mc <= a.pool_q.cpus && mm <= a.pool_q.mem && mg <= a.pool_q.gpus;
+    __syncthreads();
+    if ((tid & 31) == 0 && chain < 4) {
+      double* row = s[chain];
+#pragma unroll 8
+      for (int j = 0; j < cnt; j++) { acc = acc + row[j]; row[j] = acc; }
     }
-    if (a.group_q.enabled) {
-      unsigned mask = __ballot_sync(0xffffffffu, keep);
-      double mc = 0, mm = 0, mg = 0, mn = 0;
-      while (mask) {
-        int l = __ffs(mask) - 1;
-        mask &= mask - 1;
-        gn = gn + 1.0;
-        gc = gc + __shfl_sync(0xffffffffu, xc, l);
-        gm = gm + __shfl_sync(0xffffffffu, xm, l);
-        gg = gg + __shfl_sync(0xffffffffu, xg, l);
-        if (lane == l) { mc = gc; mm = gm; mg = gg; mn = gn; }
-      }
-      if (keep)
-        keep = mn <= a.group_q.count && mc <= a.group_q.cpus && mm <= a.group_q.mem && mg <= a.group_q.gpus;
-    }
-    if (keep && a.filter_offensive && (xm > a.off_mem || xc > a.off_cpus)) keep = false;
-    unsigned kb = __ballot_sync(0xffffffffu, keep);
-    if (keep) a.out_ranked[n_out + __popc(kb & ((1u << lane) - 1u))] = ti - a.R;
-    n_out += __popc(kb);
+    __syncthreads();
+    if (f && !(s[0][tid] <= q.count && s[1][tid] <= q.cpus && s[2][tid] <= q.mem && s[3][tid] <= q.gpus))
+      a.flag[i] = 0;
+    __syncthreads();
   }
-  if (lane == 0) *a.out_n = n_out;
+}
+
+// K5 step 3: offensive-job filter (scheduler.clj:2198-2229) and order-preserving
+// compaction of the survivors: per-block counts, one scan, scatter.
+__global__ void __launch_bounds__(QF_TB) qf_count_kernel(QueueFilterArgs a) {
+  const int i = blockIdx.x * QF_TB + threadIdx.x, n = *a.n_kept;
+  bool keep = false;
+  if (i < n) {
+    keep = a.flag[i];
+    if (keep && a.filter_offensive && (a.xm[i] > a.off_mem || a.xc[i] > a.off_cpus)) {
+      keep = false;
+      a.flag[i] = 0;
+    }
+  }
+  const int c = __syncthreads_count(keep);
+  if (threadIdx.x == 0) a.blk_cnt[blockIdx.x] = c;
+}
+
+__global__ void __launch_bounds__(1024) qf_scan_kernel(QueueFilterArgs a, int nblk_max) {
+  __shared__ int wsum[32];
+  __shared__ int carry_s;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int nblk = (*a.n_kept + QF_TB - 1) / QF_TB;
+  if (tid == 0) carry_s = 0;
+  __syncthreads();
+  for (int base = 0; base < nblk && base < nblk_max; base += 1024) {
+    const int b = base + tid;
+    const int v = b < nblk ? a.blk_cnt[b] : 0;
+    int x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+    if (lane == 31) wsum[w] = x;
+    __syncthreads();
+    if (w == 0) {
+      int t = wsum[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, t, o); if (lane >= o) t += y; }
+      wsum[lane] = t;
+    }
+    __syncthreads();
+    const int carry = carry_s;
+    const int incl = x + (w ? wsum[w - 1] : 0);
+    if (b < nblk) a.blk_cnt[b] = carry + incl - v;
+    __syncthreads();
+    if (tid == 1023) carry_s = carry + incl;
+    __syncthreads();
+  }
+  if (tid == 0) *a.out_n = carry_s;
+}
+
+__global__ void __launch_bounds__(QF_TB) qf_scatter_kernel(QueueFilterArgs a) {
+  __shared__ int wcnt[QF_TB / 32];
+  const int i = blockIdx.x * QF_TB + threadIdx.x, n = *a.n_kept;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const bool keep = i < n && a.flag[i];
+  const unsigned kb = __ballot_sync(0xffffffffu, keep);
+  if (lane == 0) wcnt[w] = __popc(kb);
+  __syncthreads();
+  if (blockIdx.x * QF_TB >= n) return;
+  int off = a.blk_cnt[blockIdx.x];
+  for (int k = 0; k < w; k++) off += wcnt[k];
+  if (keep) a.out_ranked[off + __popc(kb & ((1u << lane) - 1u))] = a.ti_at[i] - a.R;
 }
 
 template <class T>
@@ -310,6 +376,9 @@ extern "C" int32_t cook_rank(cook_pool* pool, const cook_tasks_soa* running,
   sz.add<double>(8);
   sz.add<int32_t>(8);
   sz.add<double>(N + 1);                                 // dru by task (output)
+  for (int k = 0; k < 3; k++) sz.add<double>(N + 1);     // queue-order requests
+  sz.add<int32_t>(N + 1); sz.add<uint8_t>(N + 1);        // queue-order task index, flags
+  sz.add<int32_t>(N / QF_TB + 2);
   CK(pool, ar.reserve(sz.off + 4096));
   ar.reset();
 
@@ -369,35 +438,42 @@ extern "C" int32_t cook_rank(cook_pool* pool, const cook_tasks_soa* running,
   iota_kernel<<<nb, TB, 0, st>>>(d_pos, N);
   CK(pool, csort::sort_indices(d_pos, d_tmp, N,
                                LessMerge{d_dru_at, d_user_at, d_seg_start, d_name_rank}, st));
-  pool_usage_kernel<<<1, 32, 0, st>>>(d_cpus, d_mem, d_gpus, R, d_pool_usage);
-  int32_t n_kept = 0;
-  CK(pool, cudaMemcpyAsync(&n_kept, d_counters, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-  CK(pool, cudaStreamSynchronize(st));
   QueueFilterArgs qa;
-  qa.pos_sorted = d_pos; qa.idx = d_idx; qa.n_kept = n_kept; qa.R = R;
+  qa.pos_sorted = d_pos; qa.idx = d_idx; qa.n_kept = d_counters; qa.R = R;
   qa.cpus = d_cpus; qa.mem = d_mem; qa.gpus = d_gpus;
-  cook_pool_quota off{0, 0, 0, 0, 0};
-  qa.pool_q = pool_quota ? *pool_quota : off;
-  qa.group_q = (group_quota && group_usage) ? *group_quota : off;
-  for (int k = 0; k < 4; k++) qa.group_usage[k] = group_usage ? group_usage[k] : 0.0;
   qa.filter_offensive = params->filter_offensive;
   qa.off_mem = params->offensive_max_mem_mb; qa.off_cpus = params->offensive_max_cpus;
   qa.out_order = d_out_order; qa.out_ranked = d_out_ranked; qa.out_n = d_counters + 1;
-  queue_filter_kernel<<<1, 32, 0, st>>>(qa, d_pool_usage);
+  qa.ti_at = ar.take<int32_t>(N + 1); qa.flag = ar.take<uint8_t>(N + 1);
+  qa.xc = ar.take<double>(N + 1); qa.xm = ar.take<double>(N + 1); qa.xg = ar.take<double>(N + 1);
+  const int qnb = (N + QF_TB - 1) / QF_TB;
+  qa.blk_cnt = ar.take<int32_t>(qnb + 1);
+  if (!qa.blk_cnt) return set_err(pool, COOK_E_OOM, "cook_rank: arena exhausted");
+  qf_gather_kernel<<<qnb, QF_TB, 0, st>>>(qa);
+  if (pool_quota && pool_quota->enabled) {
+    pool_usage_kernel<<<1, 32, 0, st>>>(d_cpus, d_mem, d_gpus, R, d_pool_usage);
+    qf_quota_kernel<<<1, QF_CH, 0, st>>>(qa, *pool_quota, d_pool_usage);
+  }
+  if (group_quota && group_usage && group_quota->enabled) {
+    CK(pool, cudaMemcpyAsync(d_pool_usage + 4, group_usage, sizeof(double) * 4, cudaMemcpyHostToDevice, st));
+    qf_quota_kernel<<<1, QF_CH, 0, st>>>(qa, *group_quota, d_pool_usage + 4);
+  }
+  qf_count_kernel<<<qnb, QF_TB, 0, st>>>(qa);
+  qf_scan_kernel<<<1, 1024, 0, st>>>(qa, qnb);
+  qf_scatter_kernel<<<qnb, QF_TB, 0, st>>>(qa);
+  if (out_dru) scatter_dru_kernel<<<nb, TB, 0, st>>>(d_idx, d_dru_at, N, d_dru_task);
   CK(pool, cudaGetLastError());
-  int32_t n_out = 0;
-  CK(pool, cudaMemcpyAsync(&n_out, d_counters + 1, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  int32_t h_counters[2] = {0, 0};
+  CK(pool, cudaMemcpyAsync(h_counters, d_counters, sizeof(int32_t) * 2, cudaMemcpyDeviceToHost, st));
   CK(pool, cudaStreamSynchronize(st));
+  const int32_t n_kept = h_counters[0], n_out = h_counters[1];
   if (n_out > 0)
     CK(pool, cudaMemcpyAsync(out_ranked_idx, d_out_ranked, sizeof(int32_t) * n_out,
                              cudaMemcpyDeviceToHost, st));
   if (out_order && n_kept > 0)
     CK(pool, cudaMemcpyAsync(out_order, d_out_order, sizeof(int32_t) * n_kept,
                              cudaMemcpyDeviceToHost, st));
-  if (out_dru) {
-    scatter_dru_kernel<<<nb, TB, 0, st>>>(d_idx, d_dru_at, N, d_dru_task);
-    CK(pool, cudaMemcpyAsync(out_dru, d_dru_task, sizeof(double) * N, cudaMemcpyDeviceToHost, st));
-  }
+  if (out_dru) CK(pool, cudaMemcpyAsync(out_dru, d_dru_task, sizeof(double) * N, cudaMemcpyDeviceToHost, st));
   CK(pool, cudaStreamSynchronize(st));
   *out_n = n_out;
   if (out_order_n) *out_order_n = n_kept;

@@ -681,12 +681,30 @@ bool reb_host_passes(const cook_jobs_soa* jb, int j, const cook_host_table* ht, 
 
 }  // namespace
 
-extern "C" int32_t oracle_rebalance(int32_t dru_mode, const cook_running_soa* running,
+// Test-only view into the rebalancer state, for the reference tests that read
+// it directly: compute-pending-default-job-dru (K18, test/cook/test/rebalancer.clj:115-157)
+// and next-state (K21, :813-988).  With n_forced > 0 the decision search is
+// skipped and the given decisions are applied with next-state (:270-309), as
+// the reference test does.
+struct oracle_reb_trace {
+  int32_t n_forced;
+  const cook_decision* forced;     // pending_idx, host, victim slice, mem/cpus/gpus
+  const int32_t* forced_victims;
+  double* pending_dru;             // [pending->n], NaN for jobs the walk did not reach
+  double* task_dru;                // [R + max_preemption] after the last transition
+  uint8_t* task_alive;             // same length
+  int32_t* order;                  // task->scored-task key order (priority map) afterwards
+  int32_t* n_order;
+  uint8_t* has_spare;              // [H] host->spare-resources afterwards
+  double *spare_mem, *spare_cpus, *spare_gpus;
+};
+
+static int32_t rebalance_impl(int32_t dru_mode, const cook_running_soa* running,
                                     const cook_jobs_soa* pending, const int64_t* pending_job_id,
                                     const int32_t* pending_priority, const cook_host_table* hosts,
                                     const cook_groups* groups, const cook_user_table* users,
                                     const cook_rebalance_params* prm, cook_decision* out_dec,
-                                    int32_t* out_victims, int32_t* out_n) {
+                                    int32_t* out_victims, int32_t* out_n, const oracle_reb_trace* tr) {
   if (!running || !pending || !hosts || !users || !prm || !out_dec || !out_victims || !out_n) return COOK_E_BADARG;
   if (dru_mode != 0) return COOK_E_UNSUPPORTED_CONSTRAINT;
   const int R = running->t.n, H = hosts->n, U = users->n_users;
@@ -717,7 +735,12 @@ extern "C" int32_t oracle_rebalance(int32_t dru_mode, const cook_running_soa* ru
   const double DMAX = std::numeric_limits<double>::max();
   int n_dec = 0, n_vict = 0;
   // rebalancer.clj:442-458: walk the pending jobs while preemptions remain
-  for (int p = 0; p < pending->n && n_dec < prm->max_preemption; p++) {
+  if (tr && tr->pending_dru)
+    for (int p = 0; p < pending->n; p++) tr->pending_dru[p] = std::numeric_limits<double>::quiet_NaN();
+  const int n_walk = (tr && tr->n_forced > 0) ? tr->n_forced : pending->n;
+  for (int w = 0; w < n_walk && n_dec < prm->max_preemption; w++) {
+    const bool forced = tr && tr->n_forced > 0;
+    const int p = forced ? tr->forced[w].pending_idx : w;
     const int pu = pending->user[p];
     const double pmem = pending->mem[p], pcpus = pending->cpus[p], pgpus = pending->gpus ? pending->gpus[p] : 0.0;
     // job-below-quota :210-220
@@ -736,6 +759,7 @@ extern "C" int32_t oracle_rebalance(int32_t dru_mode, const cook_running_soa* ru
     }
     const double pd_mem = nearest + pmem / users->div_mem[pu], pd_cpu = nearest + pcpus / users->div_cpus[pu];
     const double pending_dru = pd_mem > pd_cpu ? pd_mem : pd_cpu;
+    if (tr && tr->pending_dru) tr->pending_dru[p] = pending_dru;
     // victims in priority-map order: (-dru, user) ascending (:252-256); equal
     // (dru, user) is unordered in the reference => OURS: later same-user position first
     std::vector<int> order;
@@ -823,6 +847,11 @@ extern "C" int32_t oracle_rebalance(int32_t dru_mode, const cook_running_soa* ru
         consider(st.tasks[t].dru);
       }
     }
+    if (forced) {  // the test hands next-state its decision (:906, :931, :951)
+      const cook_decision& f = tr->forced[w];
+      found = true; best_host = f.host; best_dru = f.dru; best_mem = f.mem; best_cpus = f.cpus; best_gpus = f.gpus;
+      best_tasks.assign(tr->forced_victims + f.victim_begin, tr->forced_victims + f.victim_begin + f.victim_count);
+    }
     if (!found) continue;
     // ---- next-state :270-309
     cook_decision& d = out_dec[n_dec];
@@ -854,7 +883,53 @@ extern "C" int32_t oracle_rebalance(int32_t dru_mode, const cook_running_soa* ru
     n_dec++;
   }
   *out_n = n_dec;
+  if (tr) {
+    const int nt = (int)st.tasks.size();
+    std::vector<int> pos_in_user(nt, 0);
+    for (int u = 0; u < U; u++)
+      for (size_t i = 0; i < st.by_user[u].size(); i++) pos_in_user[st.by_user[u][i]] = (int)i;
+    std::vector<int> order;
+    for (int t = 0; t < nt; t++) {
+      if (tr->task_dru) tr->task_dru[t] = st.tasks[t].dru;
+      if (tr->task_alive) tr->task_alive[t] = st.tasks[t].alive;
+      if (st.tasks[t].alive) order.push_back(t);
+    }
+    std::sort(order.begin(), order.end(), [&](int a, int b) {  // same rule as the victim order above
+      const RTask &x = st.tasks[a], &y = st.tasks[b];
+      if (x.dru != y.dru) return x.dru > y.dru;
+      if (x.user != y.user) return users->name_rank[x.user] < users->name_rank[y.user];
+      return pos_in_user[a] > pos_in_user[b];
+    });
+    if (tr->order) for (size_t i = 0; i < order.size(); i++) tr->order[i] = order[i];
+    if (tr->n_order) *tr->n_order = (int)order.size();
+    for (int h = 0; h < H; h++) {
+      if (tr->has_spare) tr->has_spare[h] = st.has_spare[h];
+      if (tr->spare_mem) tr->spare_mem[h] = st.spare_mem[h];
+      if (tr->spare_cpus) tr->spare_cpus[h] = st.spare_cpus[h];
+      if (tr->spare_gpus) tr->spare_gpus[h] = st.spare_gpus[h];
+    }
+  }
   return COOK_OK;
+}
+
+extern "C" int32_t oracle_rebalance(int32_t dru_mode, const cook_running_soa* running,
+                                    const cook_jobs_soa* pending, const int64_t* pending_job_id,
+                                    const int32_t* pending_priority, const cook_host_table* hosts,
+                                    const cook_groups* groups, const cook_user_table* users,
+                                    const cook_rebalance_params* prm, cook_decision* out_dec,
+                                    int32_t* out_victims, int32_t* out_n) {
+  return rebalance_impl(dru_mode, running, pending, pending_job_id, pending_priority, hosts, groups, users, prm,
+                        out_dec, out_victims, out_n, nullptr);
+}
+
+extern "C" int32_t oracle_rebalance_trace(int32_t dru_mode, const cook_running_soa* running,
+                                          const cook_jobs_soa* pending, const int64_t* pending_job_id,
+                                          const int32_t* pending_priority, const cook_host_table* hosts,
+                                          const cook_groups* groups, const cook_user_table* users,
+                                          const cook_rebalance_params* prm, cook_decision* out_dec,
+                                          int32_t* out_victims, int32_t* out_n, const oracle_reb_trace* tr) {
+  return rebalance_impl(dru_mode, running, pending, pending_job_id, pending_priority, hosts, groups, users, prm,
+                        out_dec, out_victims, out_n, tr);
 }
 
 // ---------------------------------------------------------------------------

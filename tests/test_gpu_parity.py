@@ -126,6 +126,30 @@ def test_constraint_kernel_parity(gpu, oracle, seed, nj, no, nu, nr, kw):
     assert mg["stats"]["n_matched"] == mo["stats"]["n_matched"] > 0
 
 
+def test_rank_golden_on_gpu():
+    """The reference's own ranking known answers (K1-K8: DRU values, merged order, quota
+    filters, GPU-mode shares) through the CUDA path."""
+    import json
+    import os
+    from cook_b200.engine import GpuEngine
+    from golden_util import check_rank_case
+    here = os.path.dirname(os.path.abspath(__file__))
+    with open(os.path.join(here, "golden", "rank_golden.json")) as f:
+        cases = json.load(f)
+    engines = {}
+
+    def factory(mode):
+        if mode not in engines:
+            engines[mode] = GpuEngine(pool_name="golden-%d" % mode, dru_mode=mode)
+        return engines[mode]
+    try:
+        for case in cases:
+            check_rank_case(case, factory)
+    finally:
+        for e in engines.values():
+            e.close()
+
+
 def test_rebalance_golden_on_gpu(gpu):
     """The reference's own rebalancer known answers (K19, K22) through the CUDA path."""
     import json
