@@ -3,21 +3,24 @@
 // Replaces init-state (rebalancer.clj:222-266), compute-pending-default-job-dru
 // (:182-208), compute-preemption-decision (:320-407), next-state (:270-309) and
 // the rebalance loop (:434-467).  Decisions are inherently sequential (H6); the
-// work INSIDE a decision is data-parallel over the running tasks and hosts:
+// work INSIDE a decision is data-parallel over the running tasks and hosts, and
+// the state is kept incrementally between decisions:
 //
-//   per state change (init + after every decision):
-//     S1 comparator sort of live tasks by (user name, -priority, start, task id,
+//   once:
+//     S1 comparator sort of the tasks by (user name, -priority, start, task id,
 //        job id)                                  -> per-user order (tools.clj:614-641)
-//     S2 warp-per-user left fold                  -> cumulative DRU (dru.clj:50-66)
-//     S3 comparator sort by (host name, dru desc, user name, position desc)
-//                                                 -> per-host victim order (:252-256, :349)
+//     S2 warp-per-user left fold                  -> cumulative sums + DRU (dru.clj:50-66)
+//     S3 tasks grouped by host (a task never changes host)
 //   per pending job:
 //     P1 warp fold over the job's user            -> job-below-quota, nearest dru
 //     P2 host kernel                              -> constraints per host (:358-377)
-//     P3 thread-per-host segment walk             -> [spare ; victims] prefix sums,
-//        best sufficient prefix per host (:380-403)
+//     P3 warp per host: [spare ; eligible victims by desc dru] prefix sums by
+//        repeated warp selection of the next victim, best sufficient prefix (:380-403)
 //     P4 argmax over hosts (max dru, ties -> greatest hostname = `max-key` last wins)
-//     P5 apply (single thread)                    -> next-state
+//     P5 apply: next-state -- victims die in place (a dead task adds 0.0 to every
+//        fold), the job's task is inserted into its user's order, and only the
+//        users that changed are re-folded, from the first position that changed
+//        (dru.clj:128-144 next-task->scored-task).
 //
 // GPU DRU mode is rejected: the reference itself throws there (see oracle).
 #include "common.cuh"
@@ -28,15 +31,14 @@ namespace {
 struct RTasks {  // capacity R + max_preemption; synthetic tasks appended
   int32_t* user; int32_t* prio; int64_t* start; int64_t* tid; int64_t* jid;
   double* cpus; double* mem; double* gpus; int32_t* host; uint8_t* alive; double* dru;
-  int32_t* pos;  // position inside the user's sorted list
+  int32_t* pos;        // position inside the user's sorted list (dead tasks keep their slot)
+  double* cm; double* cc;  // cumulative mem / cpus of the user up to and including this slot
 };
 
-struct LessUser {
+struct LessUser {  // keys only: dead tasks keep their place
   RTasks t;
   const int32_t* name_rank;
   __device__ bool operator()(int32_t a, int32_t b) const {
-    bool la = t.alive[a], lb = t.alive[b];
-    if (la != lb) return la;  // dead tasks last
     int ua = name_rank[t.user[a]], ub = name_rank[t.user[b]];
     if (ua != ub) return ua < ub;
     int pa = -t.prio[a], pb = -t.prio[b];
@@ -48,23 +50,11 @@ struct LessUser {
   }
 };
 
-// (sort-by first) over hosts, then priority-map order inside a host:
-// (-dru, user name); equal (dru, user): later same-user position first (ours).
-struct LessHostDru {
+struct LessHost {
   RTasks t;
-  const int32_t* user_rank;
-  const int32_t* host_rank;
   __device__ bool operator()(int32_t a, int32_t b) const {
-    bool la = t.alive[a], lb = t.alive[b];
-    if (la != lb) return la;
-    if (!la) return a < b;
-    int ha = host_rank[t.host[a]], hb = host_rank[t.host[b]];
+    int ha = t.host[a], hb = t.host[b];
     if (ha != hb) return ha < hb;
-    double da = t.dru[a], db = t.dru[b];
-    if (da != db) return da > db;
-    int ua = user_rank[t.user[a]], ub = user_rank[t.user[b]];
-    if (ua != ub) return ua < ub;
-    if (t.pos[a] != t.pos[b]) return t.pos[a] > t.pos[b];
     return a < b;
   }
 };
@@ -77,30 +67,49 @@ __global__ void iota_r(int32_t* p, int n) {
 __global__ void user_seg_kernel(const int32_t* ord, RTasks t, int n, int32_t* seg_start, int32_t* seg_end) {
   int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n) return;
-  int i = ord[p];
-  if (!t.alive[i]) return;
-  int u = t.user[i];
-  bool first = p == 0 || t.user[ord[p - 1]] != u;
-  bool last = p == n - 1 || !t.alive[ord[p + 1]] || t.user[ord[p + 1]] != u;
-  if (first) seg_start[u] = p;
-  if (last) seg_end[u] = p + 1;
+  int u = t.user[ord[p]];
+  if (p == 0 || t.user[ord[p - 1]] != u) seg_start[u] = p;
+  if (p == n - 1 || t.user[ord[p + 1]] != u) seg_end[u] = p + 1;
 }
 
-// dru.clj:50-66 for every user: lane-serial left fold (exact association).
+// Users to re-fold after a decision, written by apply_kernel.
+struct Refold {
+  int32_t n;
+  int32_t q_ins;       // where the new task went into the user order
+  int32_t pu;          // its user
+  int32_t user[64];    // victims of one decision sit on one host; more than 63 distinct
+  int32_t from[64];    //   users fall back to `all` (from = segment start)
+  int32_t all;
+};
+
+// dru.clj:50-66: lane-serial left fold (exact association) of the users in `rf`
+// (or of every user when rf == nullptr), restarted at the first slot that changed.
 __global__ void __launch_bounds__(128) user_dru_kernel(const int32_t* ord, RTasks t, const double* div_mem,
                                                        const double* div_cpus, const int32_t* seg_start,
-                                                       const int32_t* seg_end, int n_users) {
-  const int u = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+                                                       const int32_t* seg_end, int n_users, const Refold* rf) {
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  if (u >= n_users) return;
+  const bool all = rf == nullptr || rf->all;
+  if (w >= (all ? n_users : rf->n)) return;
+  const int u = all ? w : rf->user[w];
   const int s = seg_start[u], e = seg_end[u];
   if (e <= s) return;
+  int f = s;
+  if (!all) {
+    f = rf->from[w];
+    if (f == 0x7fffffff) f = rf->q_ins;           // only the insertion touches this user
+    else if (f >= rf->q_ins) f++;                 // slots at and after the insertion moved by one
+    if (u == rf->pu) f = min(f, rf->q_ins);
+    f = min(max(f, s), e);
+  }
   const double md = div_mem[u], cd = div_cpus[u];
   double am = 0.0, ac = 0.0;
-  for (int base = s; base < e; base += 32) {
+  if (f > s) { int j = ord[f - 1]; am = t.cm[j]; ac = t.cc[j]; }
+  for (int base = f; base < e; base += 32) {
     int p = base + lane;
     int i = p < e ? ord[p] : -1;
-    double xm = i >= 0 ? t.mem[i] : 0.0, xc = i >= 0 ? t.cpus[i] : 0.0;
+    const bool live = i >= 0 && t.alive[i];
+    double xm = live ? t.mem[i] : 0.0, xc = live ? t.cpus[i] : 0.0;
     double mym = 0.0, myc = 0.0;
     int cntn = min(32, e - base);
     for (int l = 0; l < cntn; l++) {
@@ -109,6 +118,7 @@ __global__ void __launch_bounds__(128) user_dru_kernel(const int32_t* ord, RTask
       if (lane == l) { mym = am; myc = ac; }
     }
     if (i >= 0) {
+      t.cm[i] = mym; t.cc[i] = myc;
       double a = mym / md, b = myc / cd;
       t.dru[i] = a > b ? a : b;
       t.pos[i] = p - s;
@@ -162,10 +172,12 @@ __global__ void pending_kernel(const int32_t* ord, RTasks t, PendCols pc, int p,
   for (int base = s; base < e; base += 32) {
     int q = base + lane;
     int i = q < e ? ord[q] : -1;
+    if (i >= 0 && !t.alive[i]) i = -1;   // preempted earlier in this cycle: adds 0.0, is no neighbour
     double xc = i >= 0 ? t.cpus[i] : 0.0, xm = i >= 0 ? t.mem[i] : 0.0, xg = i >= 0 ? t.gpus[i] : 0.0;
+    double xn = i >= 0 ? 1.0 : 0.0;
     int cntn = min(32, e - base);
     for (int l = 0; l < cntn; l++) {
-      an = an + 1.0;
+      an = an + __shfl_sync(0xffffffffu, xn, l);
       ac = ac + __shfl_sync(0xffffffffu, xc, l);
       am = am + __shfl_sync(0xffffffffu, xm, l);
       ag = ag + __shfl_sync(0xffffffffu, xg, l);
@@ -285,17 +297,13 @@ __global__ void host_ok_kernel(PendCols pc, int p, HostCols hc, GroupCols gc, co
   ok[h] = pass ? 1 : 0;
 }
 
-// host segments of the (host, dru desc) order
+// host segments of the tasks grouped by host
 __global__ void host_seg_kernel(const int32_t* hord, RTasks t, int n, int32_t* hs, int32_t* he) {
   int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n) return;
-  int i = hord[p];
-  if (!t.alive[i]) return;
-  int h = t.host[i];
-  bool first = p == 0 || t.host[hord[p - 1]] != h;
-  bool last = p == n - 1 || !t.alive[hord[p + 1]] || t.host[hord[p + 1]] != h;
-  if (first) hs[h] = p;
-  if (last) he[h] = p + 1;
+  int h = t.host[hord[p]];
+  if (p == 0 || t.host[hord[p - 1]] != h) hs[h] = p;
+  if (p == n - 1 || t.host[hord[p + 1]] != h) he[h] = p + 1;
 }
 
 struct HostBest {  // best sufficient prefix of one host
@@ -303,70 +311,151 @@ struct HostBest {  // best sufficient prefix of one host
   int32_t n_victims;  // -1: no candidate
 };
 
-// P3: thread per host.  [spare ; victims by desc dru] prefix sums in the
-// reference's left-fold order; first sufficient prefix has the highest dru of the
-// host; longer prefixes with the SAME dru win the max-key tie (last wins).
-__global__ void host_best_kernel(const int32_t* hord, RTasks t, HostCols hc, PendCols pc, int p,
-                                 const PendScalars* ps, const uint8_t* ok, const int32_t* hs,
-                                 const int32_t* he, double min_diff, double safe, HostBest* out) {
-  int h = blockIdx.x * blockDim.x + threadIdx.x;
-  if (h >= hc.H) return;
+// Priority-map order inside a host (:252-256, :349): (-dru, user name); equal
+// (dru, user): later same-user position first (ours), then the lower index.
+struct VKey {
+  double dru; int32_t urank, pos, idx;   // idx < 0: none
+};
+__device__ __forceinline__ bool vkey_before(const VKey& a, const VKey& b) {
+  if (b.idx < 0) return a.idx >= 0;
+  if (a.idx < 0) return false;
+  if (a.dru != b.dru) return a.dru > b.dru;
+  if (a.urank != b.urank) return a.urank < b.urank;
+  if (a.pos != b.pos) return a.pos > b.pos;
+  return a.idx < b.idx;
+}
+__device__ __forceinline__ VKey vkey_shfl_xor(const VKey& k, int o) {
+  VKey r;
+  r.dru = __shfl_xor_sync(0xffffffffu, k.dru, o);
+  r.urank = __shfl_xor_sync(0xffffffffu, k.urank, o);
+  r.pos = __shfl_xor_sync(0xffffffffu, k.pos, o);
+  r.idx = __shfl_xor_sync(0xffffffffu, k.idx, o);
+  return r;
+}
+
+struct SelArgs {
+  const int32_t* hord; const int32_t* hs; const int32_t* he;
+  RTasks t; int R; int n_tasks;             // synthetic tasks are R .. n_tasks-1
+  HostCols hc; PendCols pc; const int32_t* user_rank;
+  const PendScalars* ps; double min_diff, safe;
+};
+
+// P3 for one host, one warp: [spare ; victims by desc dru] prefix sums in the
+// reference's left-fold order.  The next victim is chosen by a warp-wide argmax
+// over the eligible tasks that come after the previous one; the first sufficient
+// prefix has the highest dru of the host, longer prefixes with the SAME dru win
+// the max-key tie (last wins).  With `emit` the first n_emit victims are written
+// in ascending dru order (:397 conj onto a list).
+__device__ HostBest host_select(const SelArgs& a, int p, int h, int lane, int32_t* emit, int n_emit) {
   HostBest b;
   b.dru = 0.0; b.mem = b.cpus = b.gpus = 0.0; b.n_victims = -1;
-  if (ok[h]) {
-    const double pm = pc.mem[p], pcpu = pc.cpus[p], pg = pc.gpus ? pc.gpus[p] : 0.0;
-    const int pu = pc.user[p];
-    const bool below = ps->below_quota != 0;
-    const double pend = ps->pending_dru;
-    double sm = 0.0, sc = 0.0, sg = 0.0;
-    int nv = 0;
-    bool have = false;
-    double cur = 0.0;
-    auto consider = [&](double dru) {
-      if (sm >= pm && sc >= pcpu && (pg > 0.0 ? sg >= pg : true)) {
-        if (!have || dru >= cur) { have = true; cur = dru; b.dru = dru; b.mem = sm; b.cpus = sc; b.gpus = sg; b.n_victims = nv; }
-      }
-    };
-    if (hc.has_spare[h]) {
-      sg = sg + hc.spare_gpus[h]; sm = sm + hc.spare_mem[h]; sc = sc + hc.spare_cpus[h];
-      consider(1.7976931348623157e308);
+  const double pm = a.pc.mem[p], pcpu = a.pc.cpus[p], pg = a.pc.gpus ? a.pc.gpus[p] : 0.0;
+  const int pu = a.pc.user[p];
+  const bool below = a.ps->below_quota != 0;
+  const double pend = a.ps->pending_dru;
+  const int s0 = a.hs[h], seg = a.he[h] - s0, n_items = seg + (a.n_tasks - a.R);
+  auto item = [&](int k) -> int {
+    int i = k < seg ? a.hord[s0 + k] : a.R + (k - seg);
+    if (k >= seg && a.t.host[i] != h) return -1;
+    if (!a.t.alive[i]) return -1;
+    double d = a.t.dru[i];
+    if (!(below || a.t.user[i] == pu)) return -1;
+    if (d < a.safe) return -1;
+    if (!((d - pend) > a.min_diff)) return -1;
+    return i;
+  };
+  double sm = 0.0, sc = 0.0, sg = 0.0;
+  int nv = 0;
+  bool have = false;
+  double cur = 0.0;
+  auto consider = [&](double dru) {
+    if (sm >= pm && sc >= pcpu && (pg > 0.0 ? sg >= pg : true)) {
+      if (!have || dru >= cur) { have = true; cur = dru; b.dru = dru; b.mem = sm; b.cpus = sc; b.gpus = sg; b.n_victims = nv; }
     }
-    for (int q = hs[h]; q < he[h]; q++) {
-      int i = hord[q];
-      double d = t.dru[i];
-      if (!(below || t.user[i] == pu)) continue;
-      if (d < safe) continue;
-      if (!((d - pend) > min_diff)) continue;
-      if (have && d < cur) break;  // later prefixes only have smaller dru
-      sg = sg + t.gpus[i]; sm = sm + t.mem[i]; sc = sc + t.cpus[i];
-      nv++;
-      consider(d);
-    }
+  };
+  if (a.hc.has_spare[h]) {
+    sg = sg + a.hc.spare_gpus[h]; sm = sm + a.hc.spare_mem[h]; sc = sc + a.hc.spare_cpus[h];
+    consider(1.7976931348623157e308);
   }
-  out[h] = b;
+  if (!emit) {  // cannot reach the request with everything eligible (any summation order, wide margin)?
+    double tm = 0.0, tc = 0.0, tg = 0.0;
+    for (int k = lane; k < n_items; k += 32) {
+      int i = item(k);
+      if (i >= 0) { tm += a.t.mem[i]; tc += a.t.cpus[i]; tg += a.t.gpus[i]; }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      tm += __shfl_xor_sync(0xffffffffu, tm, o); tc += __shfl_xor_sync(0xffffffffu, tc, o);
+      tg += __shfl_xor_sync(0xffffffffu, tg, o);
+    }
+    const double slack = 1.0 + 1e-6;
+    if (!have && ((sm + tm) * slack < pm || (sc + tc) * slack < pcpu || (pg > 0.0 && (sg + tg) * slack < pg))) return b;
+  }
+  VKey last;
+  last.idx = -1; last.dru = 0.0; last.urank = 0; last.pos = 0;
+  bool first = true;
+  while (true) {
+    if (emit && nv >= n_emit) break;
+    VKey best;
+    best.idx = -1; best.dru = 0.0; best.urank = 0; best.pos = 0;
+    for (int k = lane; k < n_items; k += 32) {
+      int i = item(k);
+      if (i < 0) continue;
+      VKey c;
+      c.dru = a.t.dru[i]; c.urank = a.user_rank[a.t.user[i]]; c.pos = a.t.pos[i]; c.idx = i;
+      if (!first && !vkey_before(last, c)) continue;   // already taken
+      if (vkey_before(c, best)) best = c;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      VKey other = vkey_shfl_xor(best, o);
+      if (vkey_before(other, best)) best = other;
+    }
+    if (best.idx < 0) break;
+    if (have && best.dru < cur) break;   // later prefixes only have smaller dru
+    const int i = best.idx;
+    sg = sg + a.t.gpus[i]; sm = sm + a.t.mem[i]; sc = sc + a.t.cpus[i];
+    if (emit && lane == 0) emit[n_emit - 1 - nv] = i;
+    nv++;
+    consider(best.dru);
+    last = best;
+    first = false;
+  }
+  return b;
+}
+
+__global__ void __launch_bounds__(256) host_best_kernel(SelArgs a, int p, const uint8_t* ok, HostBest* out) {
+  const int h = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (h >= a.hc.H) return;
+  HostBest b;
+  b.dru = 0.0; b.mem = b.cpus = b.gpus = 0.0; b.n_victims = -1;
+  if (ok[h]) b = host_select(a, p, h, lane, nullptr, 0);
+  if (lane == 0) out[h] = b;
 }
 
 struct ApplyArgs {
-  RTasks t; HostCols hc; PendCols pc;
-  const int32_t* hord; const int32_t* hs; const int32_t* he;
-  const PendScalars* ps; const HostBest* best;
-  double min_diff, safe;
+  SelArgs sel;
+  const HostBest* best;
+  const int32_t* uord; const int32_t* us;   // user order and segment starts (before the insertion)
   int32_t* n_tasks;        // live + dead task count (grows by one per decision)
   int32_t* n_dec; int32_t* n_vict; int32_t* preempted_hosts; int32_t* n_preempted;
   cook_decision* dec; int32_t* victims;
+  uint8_t* has_task;
   int32_t* changed;        // out: 1 if a decision was made
+  Refold* rf;
 };
 
 // P4 + P5: argmax over hosts (max dru; ties -> greatest hostname) and next-state.
-__global__ void apply_kernel(ApplyArgs a, int p) {
+__global__ void __launch_bounds__(256) apply_kernel(ApplyArgs a, int p) {
   __shared__ double s_dru[256];
   __shared__ int s_rank[256];
   __shared__ int s_host[256];
   const int tid = threadIdx.x;
+  const HostCols& hc = a.sel.hc;
+  const PendCols& pc = a.sel.pc;
+  RTasks t = a.sel.t;
   double bd = -1.0; int br = -1, bh = -1;
-  for (int h = tid; h < a.hc.H; h += blockDim.x) {
+  for (int h = tid; h < hc.H; h += blockDim.x) {
     if (a.best[h].n_victims < 0) continue;
-    double d = a.best[h].dru; int r = a.hc.name_rank[h];
+    double d = a.best[h].dru; int r = hc.name_rank[h];
     if (d > bd || (d == bd && r > br)) { bd = d; br = r; bh = h; }
   }
   s_dru[tid] = bd; s_rank[tid] = br; s_host[tid] = bh;
@@ -378,44 +467,71 @@ __global__ void apply_kernel(ApplyArgs a, int p) {
     }
     __syncthreads();
   }
-  if (tid != 0) return;
+  if (tid >= 32) return;
   const int h = s_host[0];
-  *a.changed = 0;
-  if (h < 0) return;
+  if (h < 0) {
+    if (tid == 0) *a.changed = 0;
+    return;
+  }
   const HostBest b = a.best[h];
+  const int vb = *a.n_vict;
+  // the victims again (same selection), stored in ascending dru order
+  if (b.n_victims > 0) host_select(a.sel, p, h, tid, a.victims + vb, b.n_victims);
+  __syncwarp();
+  if (tid != 0) return;
   const int di = *a.n_dec;
   cook_decision d;
   d.pending_idx = p; d.host = h; d.dru = b.dru; d.mem = b.mem; d.cpus = b.cpus; d.gpus = b.gpus;
-  d.victim_begin = *a.n_vict; d.victim_count = b.n_victims;
-  // collect the victims again (same filter, same order), store ascending dru
-  const int pu = a.pc.user[p];
-  const bool below = a.ps->below_quota != 0;
-  int got = 0;
-  for (int q = a.hs[h]; q < a.he[h] && got < b.n_victims; q++) {
-    int i = a.hord[q];
-    double dr = a.t.dru[i];
-    if (!(below || a.t.user[i] == pu)) continue;
-    if (dr < a.safe) continue;
-    if (!((dr - a.ps->pending_dru) > a.min_diff)) continue;
-    a.victims[d.victim_begin + (b.n_victims - 1 - got)] = i;
-    a.t.alive[i] = 0;
-    a.preempted_hosts[(*a.n_preempted)++] = a.t.host[i];
-    got++;
+  d.victim_begin = vb; d.victim_count = b.n_victims;
+  const int pu = pc.user[p];
+  Refold& rf = *a.rf;
+  rf.n = 0; rf.all = 0; rf.pu = pu;
+  bool pu_listed = false;
+  for (int k = b.n_victims - 1; k >= 0; k--) {     // selection order
+    const int i = a.victims[vb + k];
+    t.alive[i] = 0;
+    a.preempted_hosts[(*a.n_preempted)++] = t.host[i];
+    const int u = t.user[i], from = a.us[u] + t.pos[i];
+    int e = 0;
+    while (e < rf.n && rf.user[e] != u) e++;
+    if (e < rf.n) rf.from[e] = min(rf.from[e], from);
+    else if (rf.n < 63) { rf.user[rf.n] = u; rf.from[rf.n] = from; rf.n++; }
+    else rf.all = 1;
+    if (u == pu) pu_listed = true;
   }
-  *a.n_vict += b.n_victims;
+  if (!pu_listed) { rf.user[rf.n] = pu; rf.from[rf.n] = 0x7fffffff; rf.n++; }
+  *a.n_vict = vb + b.n_victims;
   a.dec[di] = d;
   *a.n_dec = di + 1;
   // synthetic running task of the pending job on host h (create-task-ent :hostname)
-  const int ni = (*a.n_tasks)++;
-  a.t.user[ni] = pu; a.t.prio[ni] = a.pc.prio[p]; a.t.start[ni] = 0x7fffffffffffffffLL;
-  a.t.tid[ni] = -1; a.t.jid[ni] = a.pc.jid[p];
-  a.t.cpus[ni] = a.pc.cpus[p]; a.t.mem[ni] = a.pc.mem[p]; a.t.gpus[ni] = a.pc.gpus ? a.pc.gpus[p] : 0.0;
-  a.t.host[ni] = h; a.t.alive[ni] = 1; a.t.dru[ni] = 0.0; a.t.pos[ni] = 0;
-  a.hc.has_spare[h] = 1;
-  a.hc.spare_mem[h] = b.mem - a.pc.mem[p];
-  a.hc.spare_gpus[h] = b.gpus - (a.pc.gpus ? a.pc.gpus[p] : 0.0);
-  a.hc.spare_cpus[h] = b.cpus - a.pc.cpus[p];
+  const int n = *a.n_tasks, ni = n;
+  *a.n_tasks = n + 1;
+  t.user[ni] = pu; t.prio[ni] = pc.prio[p]; t.start[ni] = 0x7fffffffffffffffLL;
+  t.tid[ni] = -1; t.jid[ni] = pc.jid[p];
+  t.cpus[ni] = pc.cpus[p]; t.mem[ni] = pc.mem[p]; t.gpus[ni] = pc.gpus ? pc.gpus[p] : 0.0;
+  t.host[ni] = h; t.alive[ni] = 1; t.dru[ni] = 0.0; t.pos[ni] = 0; t.cm[ni] = 0.0; t.cc[ni] = 0.0;
+  a.has_task[h] = 1;
+  hc.has_spare[h] = 1;
+  hc.spare_mem[h] = b.mem - pc.mem[p];
+  hc.spare_gpus[h] = b.gpus - (pc.gpus ? pc.gpus[p] : 0.0);
+  hc.spare_cpus[h] = b.cpus - pc.cpus[p];
+  // where the new task goes in the user order: after every task that is not greater
+  LessUser less{t, a.sel.user_rank};
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (less(ni, a.uord[mid])) hi = mid; else lo = mid + 1;
+  }
+  rf.q_ins = lo;
   *a.changed = 1;
+}
+
+// uord with the new task inserted at rf->q_ins (out of place)
+__global__ void insert_kernel(const int32_t* src, int32_t* dst, int n, int ni, const Refold* rf) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j > n) return;
+  const int q = rf->q_ins;
+  dst[j] = j < q ? src[j] : (j == q ? ni : src[j - 1]);
 }
 
 }  // namespace
@@ -446,8 +562,9 @@ extern "C" int32_t cook_rebalance(cook_pool* pool, const cook_running_soa* runni
   const int G = groups ? groups->n_groups : 0;
   Sizer sz;
   for (int k = 0; k < 6; k++) sz.add<int64_t>(CAP);  // generous: covers int32/int64/double columns
-  for (int k = 0; k < 8; k++) sz.add<double>(CAP);
+  for (int k = 0; k < 10; k++) sz.add<double>(CAP);
   for (int k = 0; k < 8; k++) sz.add<int32_t>(CAP);
+  sz.add<Refold>(2);
   for (int k = 0; k < 12; k++) sz.add<double>(std::max(U, H) + 1);
   for (int k = 0; k < 16; k++) sz.add<int32_t>(std::max(U, H) + 2);
   size_t csr_h = (hosts->gpu_off ? hosts->gpu_off[H] : 0) + (hosts->disk_off ? hosts->disk_off[H] : 0);
@@ -470,7 +587,8 @@ extern "C" int32_t cook_rebalance(cook_pool* pool, const cook_running_soa* runni
   t.tid = ar.take<int64_t>(CAP); t.jid = ar.take<int64_t>(CAP); t.cpus = ar.take<double>(CAP);
   t.mem = ar.take<double>(CAP); t.gpus = ar.take<double>(CAP); t.host = ar.take<int32_t>(CAP);
   t.alive = ar.take<uint8_t>(CAP); t.dru = ar.take<double>(CAP); t.pos = ar.take<int32_t>(CAP);
-  if (!t.pos) return set_err(pool, COOK_E_OOM, "cook_rebalance: arena exhausted");
+  t.cm = ar.take<double>(CAP); t.cc = ar.take<double>(CAP);
+  if (!t.cc) return set_err(pool, COOK_E_OOM, "cook_rebalance: arena exhausted");
   const cook_tasks_soa& rt = running->t;
 #define CPY(dst, src, T) if (R) CK(pool, cudaMemcpyAsync(dst, src, sizeof(T) * R, cudaMemcpyHostToDevice, st))
   CPY(t.user, rt.user, int32_t); CPY(t.prio, rt.priority, int32_t); CPY(t.start, rt.start_time, int64_t);
@@ -549,50 +667,60 @@ extern "C" int32_t cook_rebalance(cook_pool* pool, const cook_running_soa* runni
   int32_t* d_vict = ar.take<int32_t>(CAP + MP);
   int32_t* d_pre = ar.take<int32_t>(CAP + MP);
   PendScalars* d_ps = ar.take<PendScalars>(4);
+  Refold* d_rf = ar.take<Refold>(1);
   int32_t* d_cnt = ar.take<int32_t>(64);  // [0] n_tasks [1] n_dec [2] n_vict [3] n_preempted [4] changed
   if (!d_cnt) return set_err(pool, COOK_E_OOM, "cook_rebalance: arena exhausted");
-  int32_t h_cnt[8] = {R, 0, 0, 0, 1, 0, 0, 0};
+  int32_t h_cnt[8] = {R, 0, 0, 0, 0, 0, 0, 0};
   CK(pool, cudaMemcpyAsync(d_cnt, h_cnt, sizeof(h_cnt), cudaMemcpyHostToDevice, st));
 
   const int TB = 256;
+  // ---- init-state: user order + DRU of every user, tasks grouped by host
+  CK(pool, cudaMemsetAsync(d_us, 0, sizeof(int32_t) * (U + 1), st));
+  CK(pool, cudaMemsetAsync(d_ue, 0, sizeof(int32_t) * (U + 1), st));
+  CK(pool, cudaMemsetAsync(d_hs, 0, sizeof(int32_t) * (H + 1), st));
+  CK(pool, cudaMemsetAsync(d_he, 0, sizeof(int32_t) * (H + 1), st));
+  CK(pool, cudaMemsetAsync(d_has_task, 0, H + 1, st));
+  if (R > 0) {
+    iota_r<<<(R + TB - 1) / TB, TB, 0, st>>>(d_ord, R);
+    CK(pool, csort::sort_indices(d_ord, d_tmp, R, LessUser{t, d_urank}, st));
+    user_seg_kernel<<<(R + TB - 1) / TB, TB, 0, st>>>(d_ord, t, R, d_us, d_ue);
+    user_dru_kernel<<<(U + 3) / 4, 128, 0, st>>>(d_ord, t, d_divm, d_divc, d_us, d_ue, U, nullptr);
+    iota_r<<<(R + TB - 1) / TB, TB, 0, st>>>(d_hord, R);
+    CK(pool, csort::sort_indices(d_hord, d_tmp, R, LessHost{t}, st));
+    host_seg_kernel<<<(R + TB - 1) / TB, TB, 0, st>>>(d_hord, t, R, d_hs, d_he);
+    host_has_task_kernel<<<(R + TB - 1) / TB, TB, 0, st>>>(t, R, d_has_task);
+  }
+  SelArgs sa;
+  sa.hord = d_hord; sa.hs = d_hs; sa.he = d_he; sa.t = t; sa.R = R; sa.n_tasks = R;
+  sa.hc = hc; sa.pc = pc; sa.user_rank = d_urank; sa.ps = d_ps;
+  sa.min_diff = prm->min_dru_diff; sa.safe = prm->safe_dru_threshold;
   int n_tasks = R, n_dec = 0;
-  bool dirty = true;
   for (int p = 0; p < P && n_dec < MP; p++) {
-    if (dirty) {  // S1-S3: state changed => per-user order, DRU, per-host victim order
-      const int n = n_tasks;
-      CK(pool, cudaMemsetAsync(d_us, 0, sizeof(int32_t) * (U + 1), st));
-      CK(pool, cudaMemsetAsync(d_ue, 0, sizeof(int32_t) * (U + 1), st));
-      CK(pool, cudaMemsetAsync(d_hs, 0, sizeof(int32_t) * (H + 1), st));
-      CK(pool, cudaMemsetAsync(d_he, 0, sizeof(int32_t) * (H + 1), st));
-      CK(pool, cudaMemsetAsync(d_has_task, 0, H + 1, st));
-      if (n > 0) {
-        iota_r<<<(n + TB - 1) / TB, TB, 0, st>>>(d_ord, n);
-        CK(pool, csort::sort_indices(d_ord, d_tmp, n, LessUser{t, d_urank}, st));
-        user_seg_kernel<<<(n + TB - 1) / TB, TB, 0, st>>>(d_ord, t, n, d_us, d_ue);
-        user_dru_kernel<<<(U + 3) / 4, 128, 0, st>>>(d_ord, t, d_divm, d_divc, d_us, d_ue, U);
-        iota_r<<<(n + TB - 1) / TB, TB, 0, st>>>(d_hord, n);
-        CK(pool, csort::sort_indices(d_hord, d_tmp, n, LessHostDru{t, d_urank, hc.name_rank}, st));
-        host_seg_kernel<<<(n + TB - 1) / TB, TB, 0, st>>>(d_hord, t, n, d_hs, d_he);
-        host_has_task_kernel<<<(n + TB - 1) / TB, TB, 0, st>>>(t, n, d_has_task);
-      }
-      dirty = false;
-    }
     pending_kernel<<<1, 32, 0, st>>>(d_ord, t, pc, p, d_us, d_ue, d_qn, d_qc, d_qm, d_qg, d_divm, d_divc, d_ps);
     host_ok_kernel<<<(H + TB - 1) / TB, TB, 0, st>>>(pc, p, hc, gc, d_has_task, d_pre, d_cnt + 3,
                                                      prm->host_lifetime_mins, d_ok);
-    host_best_kernel<<<(H + TB - 1) / TB, TB, 0, st>>>(d_hord, t, hc, pc, p, d_ps, d_ok, d_hs, d_he,
-                                                       prm->min_dru_diff, prm->safe_dru_threshold, d_best);
+    sa.n_tasks = n_tasks;
+    host_best_kernel<<<(H + 7) / 8, 256, 0, st>>>(sa, p, d_ok, d_best);
     ApplyArgs aa;
-    aa.t = t; aa.hc = hc; aa.pc = pc; aa.hord = d_hord; aa.hs = d_hs; aa.he = d_he; aa.ps = d_ps;
-    aa.best = d_best; aa.min_diff = prm->min_dru_diff; aa.safe = prm->safe_dru_threshold;
+    aa.sel = sa; aa.best = d_best; aa.uord = d_ord; aa.us = d_us;
     aa.n_tasks = d_cnt; aa.n_dec = d_cnt + 1; aa.n_vict = d_cnt + 2; aa.preempted_hosts = d_pre;
-    aa.n_preempted = d_cnt + 3; aa.dec = d_dec; aa.victims = d_vict; aa.changed = d_cnt + 4;
+    aa.n_preempted = d_cnt + 3; aa.dec = d_dec; aa.victims = d_vict; aa.has_task = d_has_task;
+    aa.changed = d_cnt + 4; aa.rf = d_rf;
     apply_kernel<<<1, 256, 0, st>>>(aa, p);
     CK(pool, cudaGetLastError());
     CK(pool, cudaMemcpyAsync(h_cnt, d_cnt, sizeof(int32_t) * 5, cudaMemcpyDeviceToHost, st));
     CK(pool, cudaStreamSynchronize(st));
-    n_tasks = h_cnt[0]; n_dec = h_cnt[1];
-    dirty = h_cnt[4] != 0;
+    n_dec = h_cnt[1];
+    if (h_cnt[4] != 0) {  // next-state: the new task enters its user's order, changed users are re-folded
+      const int n = n_tasks, ni = n_tasks;
+      insert_kernel<<<(n + 1 + TB - 1) / TB, TB, 0, st>>>(d_ord, d_tmp, n, ni, d_rf);
+      CK(pool, cudaMemcpyAsync(d_ord, d_tmp, sizeof(int32_t) * (n + 1), cudaMemcpyDeviceToDevice, st));
+      CK(pool, cudaMemsetAsync(d_us, 0, sizeof(int32_t) * (U + 1), st));
+      CK(pool, cudaMemsetAsync(d_ue, 0, sizeof(int32_t) * (U + 1), st));
+      user_seg_kernel<<<(n + 1 + TB - 1) / TB, TB, 0, st>>>(d_ord, t, n + 1, d_us, d_ue);
+      user_dru_kernel<<<(U + 3) / 4, 128, 0, st>>>(d_ord, t, d_divm, d_divc, d_us, d_ue, U, d_rf);
+    }
+    n_tasks = h_cnt[0];
   }
   if (n_dec > 0) {
     CK(pool, cudaMemcpyAsync(out_decisions, d_dec, sizeof(cook_decision) * n_dec, cudaMemcpyDeviceToHost, st));
