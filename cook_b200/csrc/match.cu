@@ -64,6 +64,10 @@ enum { VC_K8S = 1, VC_RESERVED = 2 };
 struct VmState {  // everything one fit evaluation needs about a VM
   double ac, am, lc, lm, rc, rm, yc, ym;
   int an, pu;
+  // constraint kernel, resolver only: the static inputs of the count-dependent checks
+  int room;   // max-tasks-per-host minus tasks already on the host (INT_MAX = no limit)
+  int occ;    // tasks running on the host before this cycle (a gpu job needs occ + an == 0)
+  int ptot;   // ports offered
 };
 
 struct JobDev {   // columns in ORIGINAL job index space (may be null)
@@ -143,6 +147,11 @@ struct MatchArgs {
   const int32_t* kports;   // gathered port counts per k
   int32_t* feas;           // [2][bmax] block + 1 once any VM is feasible for the row at the snapshot
   int vs_in_smem;          // evaluators keep the static VM table in shared memory
+  // constraint kernel: one bit per (row, VM) = "the VM passed every check at the row's snapshot"
+  // (two blocks of rows, like `rows`); all checks only tighten within a cycle, so the resolver
+  // re-evaluates a changed VM as bit && resources && the three count-dependent checks
+  unsigned* sbits;
+  int sb_words;            // words per row = ceil(O / 32); 0 in the plain kernel
   unsigned* rows_ready;    // [nblk] rows scored per block
   unsigned* published;     // # blocks resolved and published
   int32_t* assign;         // [n_cons] v (rank space) or -1
@@ -359,12 +368,39 @@ __device__ __forceinline__ VmState load_snap(const MatchArgs& a, int blk, int v)
   st.ac = d0.x; st.am = d0.y; st.yc = d1.x; st.ym = d1.y;
   st.lc = s0.x; st.lm = s0.y; st.rc = s1.x; st.rm = s1.y;
   st.an = 0; st.pu = 0;
+  st.room = 0x7fffffff; st.occ = 0; st.ptot = 0;
   if (CONSTR) {
     const int2 c = __ldcg(reinterpret_cast<const int2*>(a.dyn.n[blk & 1] + v));
     st.an = c.x; st.pu = c.y;
+    const int4* vcp = reinterpret_cast<const int4*>(a.of.vc + v);
+    const int4 c0 = __ldg(vcp), c1 = __ldg(vcp + 1);   // {.., max_tasks, num_tasks}, {run_count, .., ports_total}
+    st.room = c0.z >= 0 ? c0.z - c0.w : 0x7fffffff;
+    st.occ = c1.x; st.ptot = c1.w;
   }
   return st;
 }
+
+// Resolver-side evaluation of (job, VM v) against an explicit state.  Constraint kernel:
+// `sbit` is the evaluators' verdict for the pair at the row's snapshot (every static check
+// passed and the VM fitted then); resources and the count-dependent checks -- ports, a gpu
+// job's empty host, max-tasks-per-host -- only tighten during a cycle, so the verdict at
+// the new state is sbit && those checks, with no constraint input read from global memory.
+template <bool CONSTR>
+__device__ __forceinline__ double eval_res(const MatchArgs& a, const JobRegs& r, int v, const VmState& st,
+                                           bool with_groups, bool sbit) {
+  if (CONSTR) {
+    if (!sbit) return 0.0;
+    if (st.ac + r.c > st.lc) return 0.0;
+    if (st.am + r.m > st.lm) return 0.0;
+    if (r.ports > 0 && r.ports > st.ptot - st.pu) return 0.0;
+    if (r.g > 0.0 && st.occ + st.an != 0) return 0.0;
+    if (!(st.an < st.room)) return 0.0;
+    if (with_groups && !group_pass(a, r, v)) return 0.0;
+  }
+  return fit_fitness(r.c, r.m, st);
+}
+__device__ __forceinline__ bool sb_global(const unsigned* row, int v) { return (__ldcg(row + (v >> 5)) >> (v & 31)) & 1u; }
+__device__ __forceinline__ bool sb_shared(const unsigned* row, int v) { return (row[v >> 5] >> (v & 31)) & 1u; }
 
 // ------------------------------------------------------------- evaluators
 // One CTA scores one job against ALL offers of a snapshot.  The offers are cut
@@ -427,6 +463,7 @@ __device__ void evaluate_row(const MatchArgs& a, const JobRegs& r, const bool gr
   unsigned char* row = a.rows + ((size_t)(blk & 1) * a.bmax + ib) * ROW_BYTES;
   double* rf = reinterpret_cast<double*>(row);
   int32_t* rv = reinterpret_cast<int32_t*>(row + ROW_V_OFF);
+  unsigned* sbrow = CONSTR ? a.sbits + ((size_t)(blk & 1) * a.bmax + ib) * a.sb_words : nullptr;
   // (1) every warp scans its tiles (32 consecutive VMs, coalesced): VM v belongs to chunk
   // v mod 32 = lane, so equal-fitness runs of consecutive VMs spread over all chunks
   double f[TOPK];
@@ -442,7 +479,10 @@ __device__ void evaluate_row(const MatchArgs& a, const JobRegs& r, const bool gr
       // VMs that cannot take even the smallest remaining job are dead for the rest of the
       // cycle: a lane (and often the whole warp) skips their loads
       const unsigned lb = ui < 64 ? (unsigned)((live >> ui) & ((1u << U) - 1u)) : ((1u << U) - 1u);
-      if (!__any_sync(0xffffffffu, lb != 0u)) continue;
+      if (!__any_sync(0xffffffffu, lb != 0u)) {
+        if (CONSTR && lane < U && base + lane * 32 * NW < O) __stcg(sbrow + (base >> 5) + lane * NW, 0u);
+        continue;
+      }
       VmState st[U];
 #pragma unroll
       for (int u = 0; u < U; u++) {
@@ -466,9 +506,13 @@ __device__ void evaluate_row(const MatchArgs& a, const JobRegs& r, const bool gr
 #pragma unroll
       for (int u = 0; u < U; u++) {
         const int v = v0 + u * 32 * NW;
-        if (v >= O) break;
-        if (!((lb >> u) & 1u)) continue;
-        const double x = eval_vm<CONSTR>(a, r, v, st[u], false);
+        if (base + u * 32 * NW >= O) break;   // warp-uniform: the tile does not exist
+        double x = 0.0;
+        if (v < O && ((lb >> u) & 1u)) x = eval_vm<CONSTR>(a, r, v, st[u], false);
+        if (CONSTR) {
+          const unsigned m = __ballot_sync(0xffffffffu, x > 0.0);
+          if (lane == 0) __stcg(sbrow + (base >> 5) + u * NW, m);
+        }
         if (x > f[TOPK - 1]) {  // v ascends within a lane: strict > keeps the lower v on ties
           f[TOPK - 1] = x; vv[TOPK - 1] = v;
 #pragma unroll
@@ -630,6 +674,7 @@ struct SpecOut {
 
 struct ResolverShared {
   LogEnt log[LOGN];
+  int4 logx[LOGN];                // constraint kernel: {room, occ, ptot, -} of the entry's VM
   QEntry q[RING];
   SpecOut res[RING + 1];          // [RING] = the commit warps' fallback slot
   volatile int q_seq[RING];       // g+1 once queue entry g is filled
@@ -651,7 +696,9 @@ __device__ __forceinline__ unsigned long long chain_pack(int gdone, int ncommit)
   return ((unsigned long long)(unsigned)gdone << 32) | (unsigned)ncommit;
 }
 
-__device__ __forceinline__ VmState load_log(const LogEnt* e, int& vm, int& k) {
+template <bool CONSTR>
+__device__ __forceinline__ VmState load_log(const ResolverShared& S, int idx, int& vm, int& k) {
+  const LogEnt* e = &S.log[idx & (LOGN - 1)];
   const int4 h = *reinterpret_cast<const int4*>(e);
   const double2 a0 = *reinterpret_cast<const double2*>(&e->ac);
   const double2 a1 = *reinterpret_cast<const double2*>(&e->lc);
@@ -660,14 +707,22 @@ __device__ __forceinline__ VmState load_log(const LogEnt* e, int& vm, int& k) {
   VmState st;
   vm = h.x; st.an = h.y; st.pu = h.z; k = h.w;
   st.ac = a0.x; st.am = a0.y; st.lc = a1.x; st.lm = a1.y; st.rc = a2.x; st.rm = a2.y; st.yc = a3.x; st.ym = a3.y;
+  st.room = 0x7fffffff; st.occ = 0; st.ptot = 0;
+  if (CONSTR) {
+    const int4 x = S.logx[idx & (LOGN - 1)];
+    st.room = x.x; st.occ = x.y; st.ptot = x.z;
+  }
   return st;
 }
-__device__ __forceinline__ void store_log(LogEnt* e, int vm, int k, const VmState& st) {
+template <bool CONSTR>
+__device__ __forceinline__ void store_log(ResolverShared& S, int idx, int vm, int k, const VmState& st) {
+  LogEnt* e = &S.log[idx & (LOGN - 1)];
   *reinterpret_cast<int4*>(e) = make_int4(vm, st.an, st.pu, k);
   *reinterpret_cast<double2*>(&e->ac) = make_double2(st.ac, st.am);
   *reinterpret_cast<double2*>(&e->lc) = make_double2(st.lc, st.lm);
   *reinterpret_cast<double2*>(&e->rc) = make_double2(st.rc, st.rm);
   *reinterpret_cast<double2*>(&e->yc) = make_double2(st.yc, st.ym);
+  if (CONSTR) S.logx[idx & (LOGN - 1)] = make_int4(st.room, st.occ, st.ptot, 0);
 }
 
 // A lane's working set during a spec: a sorted list of candidates plus two
@@ -739,6 +794,7 @@ __device__ __forceinline__ void spec_job(const MatchArgs& a, ResolverShared& S, 
   const bool wg = CONSTR && qe.grp;  // group constraints against the live group state
   const int gver = wg ? group_version(a, r.j) : 0;  // read BEFORE any group state is used
   const unsigned char* rowp = a.rows + ((size_t)(blk & 1) * a.bmax + qe.row) * ROW_BYTES;
+  const unsigned* sbrow = CONSTR ? a.sbits + ((size_t)(blk & 1) * a.bmax + qe.row) * a.sb_words : nullptr;
   LaneList L;
   L.init();
   {
@@ -764,8 +820,8 @@ __device__ __forceinline__ void spec_job(const MatchArgs& a, ResolverShared& S, 
   // every VM committed since the snapshot, at its state as of version s
   for (int e = lo + lane; e < s; e += 32) {
     int vm, k;
-    const VmState st = load_log(&S.log[e & (LOGN - 1)], vm, k);
-    if (latest.get(vm) == e) L.insert(eval_vm<CONSTR>(a, r, vm, st, wg), vm, e);
+    const VmState st = load_log<CONSTR>(S, e, vm, k);
+    if (latest.get(vm) == e) L.insert(eval_res<CONSTR>(a, r, vm, st, wg, CONSTR ? sb_global(sbrow, vm) : true), vm, e);
   }
   // ---- selection.  A lane exposes its best entry not yet taken (its head) and keeps back
   // the next one and its sentinels.  Every head that beats everything any lane keeps back is
@@ -776,7 +832,7 @@ __device__ __forceinline__ void spec_job(const MatchArgs& a, ResolverShared& S, 
   auto store_cand = [&](int slot, double f, int vm, int e) {
     Cand& c = out.c[slot];
     c.f = f; c.vm = vm; c.e = e;
-    if (e >= 0) { int vm2, k2; c.st = load_log(&S.log[e & (LOGN - 1)], vm2, k2); }
+    if (e >= 0) { int vm2, k2; c.st = load_log<CONSTR>(S, e, vm2, k2); }
     else c.st = load_snap<CONSTR>(a, blk, vm);
   };
   const int kmin = depth == 1 ? 1 : min(a.spec_kmin, depth);
@@ -817,8 +873,9 @@ __device__ __forceinline__ void spec_job(const MatchArgs& a, ResolverShared& S, 
       // only if its head was hidden from the start, which is when a chunk bound can dominate
       for (int v = wl + 32 * lane; v < a.of.O; v += 32 * 32) {  // chunk wl = VMs v with v mod 32 == wl
         if (latest.get(v) >= lo) continue;
+        if (CONSTR && !sb_global(sbrow, v)) continue;
         const VmState st = load_snap<CONSTR>(a, blk, v);
-        const double x = eval_vm<CONSTR>(a, r, v, st, wg);
+        const double x = eval_res<CONSTR>(a, r, v, st, wg, true);
         if (x > 0.0 && better(bf, bv, x, v)) L.insert(x, v, -1);
       }
       if (lane == 0) atomicAdd(&S.n_rescan, 1ull);
@@ -884,14 +941,15 @@ __device__ __noinline__ int resolve_group_job(const MatchArgs& a, ResolverShared
   const int lane = threadIdx.x & 31;
   JobRegs r;
   r.c = qe.jc; r.m = qe.jm; r.g = qe.jg; r.ports = qe.jports; r.j = qe.jj;
+  const unsigned* sbrow = CONSTR ? a.sbits + ((size_t)(qe.blk & 1) * a.bmax + qe.row) * a.sb_words : nullptr;
   double cf = 0.0;
   int cv = 0x7fffffff;
   for (int v = lane; v < a.of.O; v += 32) {
     const int e = latest.get(v);
     VmState st;
-    if (e >= qe.lo) { int vm, k; st = load_log(&S.log[e & (LOGN - 1)], vm, k); }
+    if (e >= qe.lo) { int vm, k; st = load_log<CONSTR>(S, e, vm, k); }
     else st = load_snap<CONSTR>(a, qe.blk, v);
-    const double f = eval_vm<CONSTR>(a, r, v, st, true);
+    const double f = eval_res<CONSTR>(a, r, v, st, true, CONSTR ? sb_global(sbrow, v) : true);
     if (f > cf) { cf = f; cv = v; }  // v ascends per lane: strict > keeps the lowest
   }
   unsigned wk;
@@ -900,7 +958,7 @@ __device__ __noinline__ int resolve_group_job(const MatchArgs& a, ResolverShared
   if (!(wf > 0.0)) return -1;
   const int wv = (int)wk;
   const int we = latest.get(wv);
-  if (we >= qe.lo) { int vm, k; w = load_log(&S.log[we & (LOGN - 1)], vm, k); }
+  if (we >= qe.lo) { int vm, k; w = load_log<CONSTR>(S, we, vm, k); }
   else w = load_snap<CONSTR>(a, qe.blk, wv);
   return wv;
 }
@@ -1035,7 +1093,8 @@ __device__ __forceinline__ double warp_argmax_fast(double f, int v, int& wv, int
 }
 
 template <bool CONSTR, bool PROF>
-__device__ void commit_warp(const MatchArgs& a, ResolverShared& S, const Latest latest, const int cw) {
+__device__ void commit_warp(const MatchArgs& a, ResolverShared& S, const Latest latest, const int cw,
+                            unsigned* sbw) {  // sbw: this warp's copy of the current job's verdict bits
   const int lane = threadIdx.x & 31;
   unsigned long long n_fast = 0, n_group = 0, n_matched = 0, n_fallback = 0, n_slow_turn = 0, n_ztake = 0, n_relook = 0;
   unsigned long long prof[6] = {0, 0, 0, 0, 0, 0};
@@ -1071,7 +1130,7 @@ __device__ void commit_warp(const MatchArgs& a, ResolverShared& S, const Latest 
       VmDyn* pub = a.dyn.d[b & 1];
       for (int e = lo + lane; e < c; e += 32) {
         int vm, k;
-        const VmState st = load_log(&S.log[e & (LOGN - 1)], vm, k);
+        const VmState st = load_log<CONSTR>(S, e, vm, k);
         if (latest.get(vm) == e) {
           __stcg(reinterpret_cast<double2*>(pub + vm), make_double2(st.ac, st.am));
           if (CONSTR) __stcg(reinterpret_cast<int2*>(a.dyn.n[b & 1] + vm), make_int2(st.an, st.pu));
@@ -1114,6 +1173,11 @@ __device__ void commit_warp(const MatchArgs& a, ResolverShared& S, const Latest 
     r.c = qe.jc; r.m = qe.jm; r.g = CONSTR ? qe.jg : 0.0; r.ports = CONSTR ? qe.jports : 0; r.j = qe.jj;
     const int k = qe.k;
     const bool grp = CONSTR && qe.grp;
+    if (CONSTR) {  // the job's verdict bits: global -> shared, before anything is evaluated
+      const unsigned* sbrow = a.sbits + ((size_t)(qe.blk & 1) * a.bmax + qe.row) * a.sb_words;
+      for (int wd = lane; wd < a.sb_words; wd += 32) sbw[wd] = __ldcg(sbrow + wd);
+      __syncwarp();
+    }
     auto join_groups = [&](int wv) {  // lane 0: record the placement in the job's groups
       for (int q = a.jb.group_off[r.j]; q < a.jb.group_off[r.j + 1]; q++) {
         const int gi = a.jb.group_idx[q];
@@ -1162,8 +1226,8 @@ __device__ void commit_warp(const MatchArgs& a, ResolverShared& S, const Latest 
         int x_vm = 0x7fffffff;
         if (el < c_now) {
           int kk;
-          const VmState x = load_log(&S.log[el & (LOGN - 1)], x_vm, kk);
-          xf = eval_vm<CONSTR>(a, r, x_vm, x, grp);
+          const VmState x = load_log<CONSTR>(S, el, x_vm, kk);
+          xf = eval_res<CONSTR>(a, r, x_vm, x, grp, CONSTR ? sb_shared(sbw, x_vm) : true);
         }
         c_seen = c_now;
         bool xin = el < c_seen && xf > 0.0 && latest.get(x_vm) == el;
@@ -1191,8 +1255,8 @@ __device__ void commit_warp(const MatchArgs& a, ResolverShared& S, const Latest 
         // (b) one more entry, not the last before the turn: every lane evaluates it (uniform)
         // and the list is updated without a warp collective
         int nvm, kk;
-        const VmState ne = load_log(&S.log[c_seen & (LOGN - 1)], nvm, kk);
-        const double nf = eval_vm<CONSTR>(a, r, nvm, ne, grp);
+        const VmState ne = load_log<CONSTR>(S, c_seen, nvm, kk);
+        const double nf = eval_res<CONSTR>(a, r, nvm, ne, grp, CONSTR ? sb_shared(sbw, nvm) : true);
         const int nsrc = c_seen;
         c_seen++;
         // the entry supersedes whatever was known about its VM
@@ -1232,12 +1296,13 @@ __device__ void commit_warp(const MatchArgs& a, ResolverShared& S, const Latest 
     // ---- the turn: c == c_seen (nothing new) or c == c_seen + 1 (one new entry)
     VmState ne;
     ne.ac = ne.am = ne.lc = ne.lm = ne.rc = ne.rm = ne.yc = ne.ym = 0.0; ne.an = ne.pu = 0;
+    ne.room = 0x7fffffff; ne.occ = 0; ne.ptot = 0;
     int ne_vm = -1;
     double nf = 0.0;
     if (c > c_seen) {  // uniform: every lane evaluates the newest entry
       int kk;
-      ne = load_log(&S.log[c_seen & (LOGN - 1)], ne_vm, kk);
-      nf = eval_vm<CONSTR>(a, r, ne_vm, ne, grp);
+      ne = load_log<CONSTR>(S, c_seen, ne_vm, kk);
+      nf = eval_res<CONSTR>(a, r, ne_vm, ne, grp, CONSTR ? sb_shared(sbw, ne_vm) : true);
     }
     // best old item that the newest entry did not supersede
     const bool first = !(d > 0 && tv[0] == ne_vm);
@@ -1264,7 +1329,7 @@ __device__ void commit_warp(const MatchArgs& a, ResolverShared& S, const Latest 
     int wv = -1;
     auto append = [&](int vm, VmState st) {  // lane 0: the placement becomes log entry c
       st.ac = st.ac + r.c; st.am = st.am + r.m; st.an += 1; st.pu += r.ports;
-      store_log(&S.log[c & (LOGN - 1)], vm, k, st);
+      store_log<CONSTR>(S, c, vm, k, st);
       latest.set(vm, c);
       if (grp) join_groups(vm);
       fence_cta();
@@ -1292,7 +1357,7 @@ __device__ void commit_warp(const MatchArgs& a, ResolverShared& S, const Latest 
         wv = wv0;
         if (!take_new) {  // the winner's state: its log entry or its candidate record
           int vm2, kk;
-          if (ps >= 0) ne = load_log(&S.log[ps & (LOGN - 1)], vm2, kk);
+          if (ps >= 0) ne = load_log<CONSTR>(S, ps, vm2, kk);
           else ne = R->c[(~ps) & (KC - 1)].st;
         }
         if (lane == 0) append(wv, ne);
@@ -1336,7 +1401,9 @@ __global__ void __launch_bounds__(RES_THREADS, 1) match_kernel(MatchArgs a) {
   if (blockIdx.x == 0) {
     ResolverShared& S = *reinterpret_cast<ResolverShared*>(smem_raw);
     Latest latest;
-    latest.s = reinterpret_cast<int*>(smem_raw + ((sizeof(ResolverShared) + 15) & ~size_t(15)));
+    const size_t res_base = (sizeof(ResolverShared) + 15) & ~size_t(15);
+    unsigned* sbw_base = reinterpret_cast<unsigned*>(smem_raw + res_base);   // NCW rows of verdict bits
+    latest.s = reinterpret_cast<int*>(smem_raw + res_base + (((size_t)NCW * a.sb_words * 4 + 15) & ~size_t(15)));
     latest.g = a.latest_global;
     const int warp = threadIdx.x >> 5;
     for (int i = threadIdx.x; i < a.of.O; i += RES_THREADS) latest.set(i, -1);
@@ -1352,11 +1419,11 @@ __global__ void __launch_bounds__(RES_THREADS, 1) match_kernel(MatchArgs a) {
     __syncthreads();
     // warps 0, 4, 8, 12 share one scheduler (warp id mod 4): the commit warps keep it to themselves
 #ifndef COOK_PACKED  // one commit warp per scheduler (A/B: COOK_PACKED puts them all on scheduler 0)
-    if (warp < NCW) commit_warp<CONSTR, PROF>(a, S, latest, warp);
+    if (warp < NCW) commit_warp<CONSTR, PROF>(a, S, latest, warp, sbw_base + (size_t)warp * a.sb_words);
     else if (warp == NCW) driver_warp<CONSTR>(a, S);
     else if (warp < a.max_spec_warp) spec_warp<CONSTR>(a, S, latest);
 #else
-    if ((warp & 3) == 0) { if ((warp >> 2) < NCW) commit_warp<CONSTR, PROF>(a, S, latest, warp >> 2); }
+    if ((warp & 3) == 0) { if ((warp >> 2) < NCW) commit_warp<CONSTR, PROF>(a, S, latest, warp >> 2, sbw_base + (size_t)(warp >> 2) * a.sb_words); }
     else if (warp == 1) driver_warp<CONSTR>(a, S);
     else if (warp < a.max_spec_warp) spec_warp<CONSTR>(a, S, latest);
 #endif
@@ -1949,6 +2016,7 @@ static int32_t build_plan(cook_pool* pool, MatchPlan* mp, const int32_t* ranked_
   sz.add<uint8_t>(n_ranked + 1);
   sz.add<int32_t>(NC + 1); sz.add<double>(NC + 1); sz.add<double>(NC + 1); sz.add<uint8_t>(NC + 1);
   sz.add<unsigned char>((size_t)2 * bmax * ROW_BYTES); sz.add<double>(NC + bmax + 1); sz.add<int32_t>(NC + bmax + 1);
+  sz.add<unsigned>((size_t)2 * bmax * ((O + 31) / 32) + 4);
   sz.add<int32_t>(2 * bmax + 16); sz.add<unsigned>(max_blocks + 8); sz.add<int32_t>(max_blocks + 8);
   sz.add<int32_t>(NC + 1); sz.add<int32_t>(NC + 1); sz.add<uint8_t>(NC + 1);
   sz.add<int32_t>(NC + 1); sz.add<int32_t>((size_t)NC * std::max(max_ports, 1) + 1);
@@ -2063,6 +2131,7 @@ static int32_t build_plan(cook_pool* pool, MatchPlan* mp, const int32_t* ranked_
   mp->d_km = ar.take<double>(NC + 1);
   mp->d_kflags = ar.take<uint8_t>(NC + 1);
   ma.rows = ar.take<unsigned char>((size_t)2 * bmax * ROW_BYTES);
+  ma.sbits = ar.take<unsigned>((size_t)2 * bmax * ((O + 31) / 32) + 4);
   mp->d_kg = ar.take<double>(NC + bmax + 1);
   mp->d_kports = ar.take<int32_t>(NC + bmax + 1);
   ma.kg = mp->d_kg; ma.kports = mp->d_kports;
@@ -2196,7 +2265,9 @@ static int32_t run_plan(cook_pool* pool, MatchPlan* mp, int32_t* out_considerabl
       CK(pool, cudaMemsetAsync(ma.assign, 0xff, sizeof(int32_t) * n_cons, st));
       CK(pool, cudaMemsetAsync(ma.fail, COOK_FAIL_CONSTRAINT, n_cons, st));
       // resolver CTA: shared structures + the per-VM newest-log-entry table (global when too big)
-      const size_t res_base = (sizeof(ResolverShared) + 15) & ~size_t(15);
+      ma.sb_words = mp->constr ? (O + 31) / 32 : 0;
+      const size_t res_base = ((sizeof(ResolverShared) + 15) & ~size_t(15)) +
+                              (((size_t)NCW * ma.sb_words * 4 + 15) & ~size_t(15));
       size_t smem = res_base;
       ma.latest_global = nullptr;
       if (res_base + sizeof(int) * (size_t)O <= 200 * 1024) smem = std::max(smem, res_base + sizeof(int) * (size_t)O);

@@ -478,52 +478,63 @@ __global__ void __launch_bounds__(256) apply_kernel(ApplyArgs a, int p) {
   // the victims again (same selection), stored in ascending dru order
   if (b.n_victims > 0) host_select(a.sel, p, h, tid, a.victims + vb, b.n_victims);
   __syncwarp();
-  if (tid != 0) return;
-  const int di = *a.n_dec;
-  cook_decision d;
-  d.pending_idx = p; d.host = h; d.dru = b.dru; d.mem = b.mem; d.cpus = b.cpus; d.gpus = b.gpus;
-  d.victim_begin = vb; d.victim_count = b.n_victims;
+  const int n = *a.n_tasks, ni = n;
   const int pu = pc.user[p];
   Refold& rf = *a.rf;
-  rf.n = 0; rf.all = 0; rf.pu = pu;
-  bool pu_listed = false;
-  for (int k = b.n_victims - 1; k >= 0; k--) {     // selection order
-    const int i = a.victims[vb + k];
-    t.alive[i] = 0;
-    a.preempted_hosts[(*a.n_preempted)++] = t.host[i];
-    const int u = t.user[i], from = a.us[u] + t.pos[i];
-    int e = 0;
-    while (e < rf.n && rf.user[e] != u) e++;
-    if (e < rf.n) rf.from[e] = min(rf.from[e], from);
-    else if (rf.n < 63) { rf.user[rf.n] = u; rf.from[rf.n] = from; rf.n++; }
-    else rf.all = 1;
-    if (u == pu) pu_listed = true;
+  if (tid == 0) {
+    const int di = *a.n_dec;
+    cook_decision d;
+    d.pending_idx = p; d.host = h; d.dru = b.dru; d.mem = b.mem; d.cpus = b.cpus; d.gpus = b.gpus;
+    d.victim_begin = vb; d.victim_count = b.n_victims;
+    rf.n = 0; rf.all = 0; rf.pu = pu;
+    bool pu_listed = false;
+    for (int k = b.n_victims - 1; k >= 0; k--) {     // selection order
+      const int i = a.victims[vb + k];
+      t.alive[i] = 0;
+      a.preempted_hosts[(*a.n_preempted)++] = t.host[i];
+      const int u = t.user[i], from = a.us[u] + t.pos[i];
+      int e = 0;
+      while (e < rf.n && rf.user[e] != u) e++;
+      if (e < rf.n) rf.from[e] = min(rf.from[e], from);
+      else if (rf.n < 63) { rf.user[rf.n] = u; rf.from[rf.n] = from; rf.n++; }
+      else rf.all = 1;
+      if (u == pu) pu_listed = true;
+    }
+    if (!pu_listed) { rf.user[rf.n] = pu; rf.from[rf.n] = 0x7fffffff; rf.n++; }
+    *a.n_vict = vb + b.n_victims;
+    a.dec[di] = d;
+    *a.n_dec = di + 1;
+    // synthetic running task of the pending job on host h (create-task-ent :hostname)
+    *a.n_tasks = n + 1;
+    t.user[ni] = pu; t.prio[ni] = pc.prio[p]; t.start[ni] = 0x7fffffffffffffffLL;
+    t.tid[ni] = -1; t.jid[ni] = pc.jid[p];
+    t.cpus[ni] = pc.cpus[p]; t.mem[ni] = pc.mem[p]; t.gpus[ni] = pc.gpus ? pc.gpus[p] : 0.0;
+    t.host[ni] = h; t.alive[ni] = 1; t.dru[ni] = 0.0; t.pos[ni] = 0; t.cm[ni] = 0.0; t.cc[ni] = 0.0;
+    a.has_task[h] = 1;
+    hc.has_spare[h] = 1;
+    hc.spare_mem[h] = b.mem - pc.mem[p];
+    hc.spare_gpus[h] = b.gpus - (pc.gpus ? pc.gpus[p] : 0.0);
+    hc.spare_cpus[h] = b.cpus - pc.cpus[p];
   }
-  if (!pu_listed) { rf.user[rf.n] = pu; rf.from[rf.n] = 0x7fffffff; rf.n++; }
-  *a.n_vict = vb + b.n_victims;
-  a.dec[di] = d;
-  *a.n_dec = di + 1;
-  // synthetic running task of the pending job on host h (create-task-ent :hostname)
-  const int n = *a.n_tasks, ni = n;
-  *a.n_tasks = n + 1;
-  t.user[ni] = pu; t.prio[ni] = pc.prio[p]; t.start[ni] = 0x7fffffffffffffffLL;
-  t.tid[ni] = -1; t.jid[ni] = pc.jid[p];
-  t.cpus[ni] = pc.cpus[p]; t.mem[ni] = pc.mem[p]; t.gpus[ni] = pc.gpus ? pc.gpus[p] : 0.0;
-  t.host[ni] = h; t.alive[ni] = 1; t.dru[ni] = 0.0; t.pos[ni] = 0; t.cm[ni] = 0.0; t.cc[ni] = 0.0;
-  a.has_task[h] = 1;
-  hc.has_spare[h] = 1;
-  hc.spare_mem[h] = b.mem - pc.mem[p];
-  hc.spare_gpus[h] = b.gpus - (pc.gpus ? pc.gpus[p] : 0.0);
-  hc.spare_cpus[h] = b.cpus - pc.cpus[p];
+  __syncwarp();
   // where the new task goes in the user order: after every task that is not greater
+  // (32-ary search: the predicate "new task < uord[q]" is monotone in q)
   LessUser less{t, a.sel.user_rank};
   int lo = 0, hi = n;
   while (lo < hi) {
-    int mid = (lo + hi) >> 1;
-    if (less(ni, a.uord[mid])) hi = mid; else lo = mid + 1;
+    const int step = (hi - lo + 31) / 32;
+    const int q = lo + tid * step;
+    const bool pred = q < hi ? less(ni, a.uord[q]) : true;
+    const unsigned m = __ballot_sync(0xffffffffu, pred);
+    const int L = m ? __ffs(m) - 1 : 32;
+    const int nlo = L > 0 ? lo + (L - 1) * step + 1 : lo;
+    const int nhi = L < 32 ? min(hi, lo + L * step) : hi;
+    lo = min(nlo, nhi); hi = nhi;
   }
-  rf.q_ins = lo;
-  *a.changed = 1;
+  if (tid == 0) {
+    rf.q_ins = lo;
+    *a.changed = 1;
+  }
 }
 
 // uord with the new task inserted at rf->q_ins (out of place)
