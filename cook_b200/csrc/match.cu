@@ -604,13 +604,20 @@ __device__ void evaluate_row(const MatchArgs& a, const JobRegs& r, const bool gr
 //                     an exact re-evaluation of every VM committed since the row's
 //                     snapshot (the commit LOG, an append-only ring), plus a bound z
 //                     on everything left out.
-//   commit (warps 0,4,8,12) own the entries round-robin and form the serial chain.
-//                     Before its turn the owner re-evaluates the VMs committed since
-//                     s (one lane per log entry) and reduces its lanes' items to the
-//                     best two (b1, b2).  At its turn exactly the newest log entry is
-//                     new: every lane evaluates it redundantly, the winner is the
-//                     better of it and b1 (b2 if the entry re-used b1's VM) - no warp
-//                     collective on the chain - and is appended to the log.
+//   commit (warps 0..3, one per SM scheduler) own the entries round-robin and form
+//                     the serial chain.  Before its turn the owner re-evaluates the VMs
+//                     committed since s (one lane per log entry) and reduces its lanes'
+//                     items to an exact, warp-uniform top-3; entries that appear while it
+//                     waits are folded in with scalar code.  At its turn exactly the newest
+//                     log entry is new: every lane evaluates it redundantly, the winner is
+//                     the better of it and the best listed item it did not supersede - no
+//                     warp collective on the chain - and is appended to the log.
+//
+// Constraint kernel: the evaluators also emit one verdict bit per (job, VM) ("passed every
+// check at the row's snapshot"); all checks only tighten within a cycle, so the resolver
+// re-evaluates a changed VM as bit && resources && the count-dependent checks whose static
+// inputs travel with the log entry (eval_res) - it reads no constraint input from global
+// memory.  Group constraints stay dynamic (group_pass against the live group state).
 //
 // Validity of a log entry e for VM x is `latest[x] == e` (latest[] = index of
 // the newest entry per VM, monotone), so nothing is ever cleared: a VM is dirty
