@@ -257,3 +257,52 @@ def test_pools_side_by_side_on_one_gpu(oracle):
             assert np.array_equal(out[i]["ports"], mo["ports"])
     for _, _, _, eng in pools:
         eng.close()
+
+
+@pytest.mark.parametrize("seed,nj,no", [(81, 2500, 7000), (82, 1200, 45000), (83, 3000, 5121)])
+def test_wide_offer_tables_with_constraints(gpu, oracle, seed, nj, no):
+    """The constraint kernel beyond the shared-memory fast paths: verdict-bit rows of 220 / 1407 /
+    161 words, newest-log-entry table in global memory (45k offers), a last tile of one VM (5121)."""
+    t = traces.gen_c3_pool(seed, nj, no, 60, nj // 5)
+    ranked = oracle.rank(t["running"], t["pending"], t["users"])["ranked"]
+    prm = traces.match_params(nj, host_lifetime_mins=t["host_lifetime_mins"])
+    mo = oracle.match(ranked, t["jobs"], t["offers"], t["users"], prm, groups=t["groups"], max_ports=2)
+    mg = gpu.match(ranked, t["jobs"], t["offers"], t["users"], prm, groups=t["groups"], max_ports=2)
+    assert np.array_equal(mg["considerable"], mo["considerable"])
+    assert np.array_equal(mg["assign"], mo["assign"])
+    assert np.array_equal(mg["ports"], mo["ports"])
+    assert mg["stats"]["n_matched"] == mo["stats"]["n_matched"] > 0
+
+
+@pytest.mark.parametrize("frac_pool,frac_group", [(0.5, 0.8), (0.9, 0.3), (0.0, 0.5), (2.0, 2.0)])
+def test_rank_queue_filters_parity(gpu, oracle, frac_pool, frac_group):
+    """Pool quota, quota group and offensive-job filters binding at different depths of a queue
+    that spans several 1024-entry chunks of the sequential filter passes (tools.clj:654-668)."""
+    t = traces.gen_pool(91, 5000, 16, 80, 1500)
+    tot = float(np.sum(t["pending"].col("cpus"))) + float(np.sum(t["running"].col("cpus")))
+    q = lambda f: abi.make_pool_quota(dict(count=1e12, cpus=round(f * tot), mem=1e15, gpus=1e12))
+    kw = dict(pool_quota=q(frac_pool), group_quota=q(frac_group), group_usage=np.array([7.0, 33.0, 4096.0, 0.0]),
+              params=abi.RankParams(100, 1, 20000.0, 6.0))
+    rg = gpu.rank(t["running"], t["pending"], t["users"], **kw)
+    ro = oracle.rank(t["running"], t["pending"], t["users"], **kw)
+    assert np.array_equal(rg["ranked"], ro["ranked"])
+    assert np.array_equal(rg["order"], ro["order"])
+    assert _same_dru(rg["dru"], ro["dru"])
+
+
+def test_rank_and_rebalance_degenerate_inputs(gpu, oracle):
+    """No pending jobs / no running tasks: empty queue, rebalancer decisions on spare resources only."""
+    t = traces.gen_pool(92, 300, 16, 10, 200)
+    from cook_b200.engine import _empty_tasks
+    rg = gpu.rank(t["running"], _empty_tasks(), t["users"])
+    ro = oracle.rank(t["running"], _empty_tasks(), t["users"])
+    assert len(rg["ranked"]) == len(ro["ranked"]) == 0 and np.array_equal(rg["order"], ro["order"])
+    rg = gpu.rank(None, t["pending"], t["users"])
+    ro = oracle.rank(None, t["pending"], t["users"])
+    assert np.array_equal(rg["ranked"], ro["ranked"])
+    r = traces.gen_rebalance(93, 0, 12, 20, 8, constraints=False)
+    args = (r["running"], r["pending"], r["pending_job_id"], r["pending_priority"], r["hosts"], r["users"], r["params"])
+    assert gpu.rebalance(*args) == oracle.rebalance(*args)
+    r = traces.gen_rebalance(94, 3000, 0, 50, 20, constraints=False)
+    args = (r["running"], r["pending"], r["pending_job_id"], r["pending_priority"], r["hosts"], r["users"], r["params"])
+    assert gpu.rebalance(*args) == oracle.rebalance(*args) == []
