@@ -274,19 +274,28 @@ def run_reference(args):
     # "all the host threads it can use": the per-task VM loop (5k offers) stops
     # scaling well before 128 threads; pick the fastest count on a short probe.
     probe = traces.match_params(20000)  # long enough that per-job thread hand-off costs show
-    best = (0.0, 1)
+    rates = []
     for th in sorted({1, 2, 4, 8, 16, 32, 64, min(avail, 64)}):
         if th > avail:
             continue
         tp = time.perf_counter()
         mp_ = ora.match(ranked, t["jobs"], t["offers"], t["users"], probe, threads=th)
+        rates.append((mp_["stats"]["evals"] / (time.perf_counter() - tp), th))
+    sample_jobs = t["jobs"].n  # the whole workload per step (a few seconds)
+    prm = traces.match_params(sample_jobs)
+    # the tail of the queue (jobs that fit nowhere) is cheap per job and favours fewer threads
+    # than the probe: time one full pass for the two best probe counts and for one thread,
+    # keep the fastest (these passes are the warm-up)
+    cands = sorted({th for _, th in sorted(rates, reverse=True)[:2]} | {1})
+    best = (0.0, 1)
+    for th in cands:
+        tp = time.perf_counter()
+        mp_ = ora.match(ranked, t["jobs"], t["offers"], t["users"], prm, threads=th)
         rate = mp_["stats"]["evals"] / (time.perf_counter() - tp)
         if rate > best[0]:
             best = (rate, th)
     cores = best[1]
-    sample_jobs = t["jobs"].n  # the whole workload per step (about 1-2 s on 8 cores)
-    prm = traces.match_params(sample_jobs)
-    for _ in range(args.warmup):
+    for _ in range(max(0, args.warmup - len(cands))):
         ora.match(ranked, t["jobs"], t["offers"], t["users"], prm, threads=cores)
     t0 = time.perf_counter()
     evals = 0

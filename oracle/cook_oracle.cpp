@@ -35,6 +35,12 @@
 
 #include "../include/cook_gpu.h"
 
+static inline void cpu_relax() {
+#if defined(__x86_64__) || defined(__i386__)
+  __builtin_ia32_pause();
+#endif
+}
+
 namespace {
 
 struct Usage {
@@ -483,8 +489,10 @@ static int32_t oracle_match_impl(const int32_t* ranked_idx, int32_t n_ranked, co
   };
   const int T = std::max(1, std::min(n_threads, 64));
   std::vector<Partial> parts(T);
-  std::atomic<int> gen{0}, done{0}, cur_job{-1};
-  std::atomic<bool> stop{false};
+  // one cache line per flag: the workers spin on `gen` while the finished ones bump `done`
+  struct alignas(64) Flag { std::atomic<int> v{0}; };
+  Flag gen_f, done_f, job_f, stop_f;
+  std::atomic<int>&gen = gen_f.v, &done = done_f.v, &cur_job = job_f.v, &stop = stop_f.v;
   std::vector<std::thread> workers;
   for (int t = 1; t < T; t++)
     workers.emplace_back([&, t]() {
@@ -492,6 +500,7 @@ static int32_t oracle_match_impl(const int32_t* ranked_idx, int32_t n_ranked, co
       while (true) {
         while (gen.load(std::memory_order_acquire) == seen) {
           if (stop.load(std::memory_order_relaxed)) return;
+          cpu_relax();
         }
         seen++;
         int j = cur_job.load(std::memory_order_relaxed);
@@ -508,7 +517,7 @@ static int32_t oracle_match_impl(const int32_t* ranked_idx, int32_t n_ranked, co
     }
     scan(j, 0, (int)((long long)O * 1 / T), parts[0]);
     if (T > 1)
-      while (done.load(std::memory_order_acquire) != T - 1) {}
+      while (done.load(std::memory_order_acquire) != T - 1) cpu_relax();
     int best = -1;
     double best_fit = 0.0;
     bool any_res_ok = false;
@@ -554,7 +563,7 @@ static int32_t oracle_match_impl(const int32_t* ranked_idx, int32_t n_ranked, co
       for (int p = 0; p < max_ports; p++) out_ports[(size_t)k * max_ports + p] = -1;
     }
   }
-  stop.store(true);
+  stop.store(1);
   for (auto& w : workers) w.join();
   if (st) {
     std::memset(st, 0, sizeof(*st));
