@@ -10,8 +10,8 @@
 // file is a line-by-line restatement of the cited Clojure sources, PINNED
 // against the reference's own known-answer tests transcribed in tests/golden/
 // and tests/*_golden*.py (K1-K8 rank, K9/K14 considerable jobs, K10/K12/K13/K15
-// matcher sets, K11/K16 constraint truth tables, K17 init-state, K19/K20/K22
-// rebalancer).  The Fenzo rules (section "FENZO" below) are restated from the
+// matcher sets, K11/K16 constraint truth tables, K17 init-state, K18 pending-job
+// DRU, K19/K20/K22 rebalancer decisions, K21 next-state).  The Fenzo rules (section "FENZO" below) are restated from the
 // published Netflix/Fenzo 0.10.0 algorithm; they are pinned by Cook's
 // set-level tests only (K10, K12, K13, K15): job->host parity with a real
 // Fenzo is UNPINNED (no test in the reference reads hostnames of multi-host

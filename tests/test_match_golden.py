@@ -75,3 +75,10 @@ def test_init_state_dru_golden_oracle(oracle):
 @pytest.mark.gpu
 def test_init_state_dru_golden_gpu(gpu):
     _k17(gpu)
+
+
+def test_handle_offers_golden_oracle(oracle):
+    """K15 (test/cook/test/scheduler/scheduler.clj:1947-2239): launched job sets and offer counts of
+    handle-resource-offers! against the real Fenzo, for the Mesos and the Kubernetes offer tables."""
+    import handle_offers_golden_cases
+    assert handle_offers_golden_cases.check_all(oracle) == 2 * (13 + 1) + 2 * (13 + 6)
