@@ -706,6 +706,9 @@ struct oracle_reb_trace {
   int32_t* n_order;
   uint8_t* has_spare;              // [H] host->spare-resources afterwards
   double *spare_mem, *spare_cpus, *spare_gpus;
+  int32_t forced_only;             // 1: walk only the forced jobs (K21); 0: the forced jobs take their
+                                   // given decision, every other pending job is searched as usual (K20:
+                                   // "one host has already been preempted this cycle")
 };
 
 static int32_t rebalance_impl(int32_t dru_mode, const cook_running_soa* running,
@@ -746,10 +749,16 @@ static int32_t rebalance_impl(int32_t dru_mode, const cook_running_soa* running,
   // rebalancer.clj:442-458: walk the pending jobs while preemptions remain
   if (tr && tr->pending_dru)
     for (int p = 0; p < pending->n; p++) tr->pending_dru[p] = std::numeric_limits<double>::quiet_NaN();
-  const int n_walk = (tr && tr->n_forced > 0) ? tr->n_forced : pending->n;
+  const bool any_forced = tr && tr->n_forced > 0;
+  const bool forced_only = any_forced && tr->forced_only != 0;
+  const int n_walk = forced_only ? tr->n_forced : pending->n;
   for (int w = 0; w < n_walk && n_dec < prm->max_preemption; w++) {
-    const bool forced = tr && tr->n_forced > 0;
-    const int p = forced ? tr->forced[w].pending_idx : w;
+    const int p = forced_only ? tr->forced[w].pending_idx : w;
+    const cook_decision* fdec = nullptr;
+    if (any_forced)
+      for (int q = 0; q < tr->n_forced; q++)
+        if (tr->forced[q].pending_idx == p) fdec = &tr->forced[q];
+    const bool forced = fdec != nullptr;
     const int pu = pending->user[p];
     const double pmem = pending->mem[p], pcpus = pending->cpus[p], pgpus = pending->gpus ? pending->gpus[p] : 0.0;
     // job-below-quota :210-220
@@ -857,7 +866,7 @@ static int32_t rebalance_impl(int32_t dru_mode, const cook_running_soa* running,
       }
     }
     if (forced) {  // the test hands next-state its decision (:906, :931, :951)
-      const cook_decision& f = tr->forced[w];
+      const cook_decision& f = *fdec;
       found = true; best_host = f.host; best_dru = f.dru; best_mem = f.mem; best_cpus = f.cpus; best_gpus = f.gpus;
       best_tasks.assign(tr->forced_victims + f.victim_begin, tr->forced_victims + f.victim_begin + f.victim_count);
     }

@@ -99,7 +99,7 @@ class OracleEngine:
         return decisions_to_list(dec, vict, n.value)
 
     def rebalance_trace(self, running, pending, pending_job_id, pending_priority, hosts, users, params,
-                        forced=None):
+                        forced=None, forced_only=True, groups=None):
         """Rebalancer state as the reference's own tests read it (K18 pending DRU, K21 next-state).
         forced: [(pending_idx, host, [victims], mem, cpus, gpus)] applied with next-state instead
         of searching."""
@@ -108,7 +108,8 @@ class OracleEngine:
                         ("forced_victims", abi.P_I32), ("pending_dru", abi.P_F64),
                         ("task_dru", abi.P_F64), ("task_alive", abi.P_U8), ("order", abi.P_I32),
                         ("n_order", C.POINTER(C.c_int32)), ("has_spare", abi.P_U8),
-                        ("spare_mem", abi.P_F64), ("spare_cpus", abi.P_F64), ("spare_gpus", abi.P_F64)]
+                        ("spare_mem", abi.P_F64), ("spare_cpus", abi.P_F64), ("spare_gpus", abi.P_F64),
+                        ("forced_only", C.c_int32)]
         pj = np.ascontiguousarray(pending_job_id, np.int64)
         pp = np.ascontiguousarray(pending_priority, np.int32)
         mp = max(params.max_preemption, 1)
@@ -129,10 +130,11 @@ class OracleEngine:
         tr = Trace(len(forced), fdec, abi.ptr(fv, abi.P_I32), abi.ptr(pdru, abi.P_F64),
                    abi.ptr(tdru, abi.P_F64), abi.ptr(alive, abi.P_U8), abi.ptr(order, abi.P_I32),
                    C.pointer(n_order), abi.ptr(hs, abi.P_U8), abi.ptr(sm, abi.P_F64),
-                   abi.ptr(sc, abi.P_F64), abi.ptr(sg, abi.P_F64))
+                   abi.ptr(sc, abi.P_F64), abi.ptr(sg, abi.P_F64), 1 if forced_only else 0)
         rc = self.lib.oracle_rebalance_trace(int(self.dru_mode), C.byref(running), C.byref(pending),
                                              abi.ptr(pj, abi.P_I64), abi.ptr(pp, abi.P_I32),
-                                             C.byref(hosts), None, C.byref(users), C.byref(params), dec,
+                                             C.byref(hosts), C.byref(groups) if groups is not None else None,
+                                             C.byref(users), C.byref(params), dec,
                                              abi.ptr(vict, abi.P_I32), C.byref(n), C.byref(tr))
         if rc != 0:
             raise RuntimeError(f"oracle_rebalance_trace rc={rc}")

@@ -82,3 +82,10 @@ def test_handle_offers_golden_oracle(oracle):
     handle-resource-offers! against the real Fenzo, for the Mesos and the Kubernetes offer tables."""
     import handle_offers_golden_cases
     assert handle_offers_golden_cases.check_all(oracle) == 2 * (13 + 1) + 2 * (13 + 6)
+
+
+def test_rebalance_balanced_and_quota_golden_oracle(oracle):
+    """K20, second half (test/cook/test/rebalancer.clj:673-811): balanced host-placement groups (one
+    with a host already preempted in the cycle) and the over-quota rule (dru 100.0, own task)."""
+    import rebalance_constraint_golden
+    assert rebalance_constraint_golden.check_balanced_and_quota(oracle) == 3
