@@ -709,6 +709,7 @@ struct oracle_reb_trace {
   int32_t forced_only;             // 1: walk only the forced jobs (K21); 0: the forced jobs take their
                                    // given decision, every other pending job is searched as usual (K20:
                                    // "one host has already been preempted this cycle")
+  uint8_t* below_quota;            // [pending->n] job-below-quota (:210-220) for the jobs the walk reached
 };
 
 static int32_t rebalance_impl(int32_t dru_mode, const cook_running_soa* running,
@@ -767,6 +768,7 @@ static int32_t rebalance_impl(int32_t dru_mode, const cook_running_soa* running,
     for (int t : st.by_user[pu]) add_usage(fu, st.tasks[t].cpus, st.tasks[t].mem, st.tasks[t].gpus);
     const bool below = below_quota(users->quota_count[pu], users->quota_cpus[pu], users->quota_mem[pu],
                                    users->quota_gpus[pu], fu);
+    if (tr && tr->below_quota) tr->below_quota[p] = below ? 1 : 0;
     // compute-pending-default-job-dru :182-208: nearest = last task <= synthetic pending task
     RTask synth{pu, pending_priority[p], -1, std::numeric_limits<int64_t>::max(), -1, pending_job_id[p],
                 pcpus, pmem, pgpus, 0.0, true};

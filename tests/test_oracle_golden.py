@@ -6,6 +6,7 @@ import os
 import numpy as np
 import pytest
 
+from cook_b200 import abi
 from golden_util import check_rank_case
 
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -101,3 +102,20 @@ def test_next_state_golden(k):
     assert out["order"] == order, (cite, out["order"])
     assert np.allclose(out["order_dru"], drus, rtol=1e-12, atol=0), (cite, out["order_dru"])
     assert out["spare"] == {hid[h]: v for h, v in spare.items()}, (cite, out["spare"])
+
+
+def test_job_below_quota_golden():
+    """test/cook/test/rebalancer.clj:1368-1397: testA has a count quota of 1 and one running task, so
+    its waiting job is not below quota; testB (no quota) is."""
+    from golden_util import rebalance_inputs
+    from oracle.pyoracle import OracleEngine
+    run = [_rj("testA", 10, 1, "hostA"), _rj("testB", 10, 1, "hostA")]
+    pend = [_pj("testA", 10, 1), _pj("testB", 10, 1)]
+    inp = rebalance_inputs(_reb_case(run, pend, {}, min_dru_diff=1e9))
+    big = np.finfo(np.float64).max
+    users = abi.make_users(2, name_rank=np.arange(2, dtype=np.int32), div_mem=np.full(2, 25.0), div_cpus=np.full(2, 25.0),
+                           div_gpus=np.ones(2), quota=dict(count=np.array([1.0, big]), cpus=np.full(2, big),
+                                                           mem=np.full(2, big), gpus=np.full(2, big)))
+    out = OracleEngine().rebalance_trace(inp["running"], inp["pending"], inp["pending_job_id"],
+                                         inp["pending_priority"], inp["hosts"], users, inp["params"])
+    assert out["below_quota"] == [False, True]
