@@ -119,3 +119,20 @@ def test_job_below_quota_golden():
     out = OracleEngine().rebalance_trace(inp["running"], inp["pending"], inp["pending_job_id"],
                                          inp["pending_priority"], inp["hosts"], users, inp["params"])
     assert out["below_quota"] == [False, True]
+
+
+def test_filter_offensive_jobs_golden():
+    """R7, test/cook/test/scheduler/scheduler.clj:857-888: constraints {memory-gb 10, cpus 5}; a 12 GB
+    job and a 6-cpu job are offensive, the 8 GB / 4 cpu job stays in the queue."""
+    from cook_b200.engine import _empty_tasks
+    from oracle.pyoracle import OracleEngine
+    mem = np.array([1024.0 * 12.0, 1024.0 * 8.0, 1024.0 * 8.0])
+    cpus = np.array([4.0, 6.0, 4.0])
+    pending = abi.make_tasks(user=np.zeros(3, np.int32), priority=np.full(3, 50, np.int32),
+                             start_time=np.full(3, abi.INT64_MAX, np.int64), task_id=np.full(3, -1, np.int64),
+                             job_id=np.arange(1, 4, dtype=np.int64), cpus=cpus, mem=mem)
+    users = abi.make_users(1)
+    out = OracleEngine().rank(_empty_tasks(), pending, users, params=abi.RankParams(100, 1, 1024.0 * 10.0, 5.0))
+    assert list(out["ranked"]) == [2]
+    out = OracleEngine().rank(_empty_tasks(), pending, users, params=abi.RankParams(100, 0, 0.0, 0.0))
+    assert sorted(out["ranked"]) == [0, 1, 2]
