@@ -1,4 +1,5 @@
-"""Times the other rows of the path (rank R1-R7, rebalancer B1-B6, and the matcher on a
+"""(Lives under tests/ because it uses the oracle as the checker beside every measurement.)
+Times the other rows of the path (rank R1-R7, rebalancer B1-B6, and the matcher on a
 full config-#3 pool) through the C ABI with HOST buffers, next to the CPU restatement on the
 same inputs, and checks that the results are identical.  Writes one JSON object to
 gpurun_out/path_measurements.json.  `PROF_NO_GPU=1` runs the generators and the CPU side only
@@ -13,7 +14,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from cook_b200 import traces  # noqa: E402
-from oracle.pyoracle import OracleEngine, build  # noqa: E402  (tools/: measurement beside the product)
+from oracle.pyoracle import OracleEngine, build  # noqa: E402
 
 NO_GPU = os.environ.get("PROF_NO_GPU") == "1"
 SCALE = float(os.environ.get("PROF_SCALE", "1"))
