@@ -50,6 +50,10 @@ def test_product_does_not_import_the_oracle():
             continue
         txt = open(os.path.join(ROOT, "cook_b200", "csrc", fn)).read()
         assert "cook_oracle" not in txt.replace("oracle/cook_oracle.cpp", "") and "#include \"../../oracle" not in txt
+    for fn in os.listdir(os.path.join(ROOT, "tools")):   # profiling harnesses: product only
+        if fn.endswith(".py"):
+            txt = open(os.path.join(ROOT, "tools", fn)).read()
+            assert "import oracle" not in txt and "from oracle" not in txt and "libcookoracle" not in txt, fn
 
 
 def test_lpt_assignment():
