@@ -19,6 +19,7 @@ struct cook_ctx {
 struct Arena {
   char* base = nullptr;
   size_t cap = 0, off = 0;
+  bool failed = false;  // sticky: some take() since the last reset() did not fit
   cudaError_t reserve(size_t bytes) {
     if (bytes <= cap) return cudaSuccess;
     if (base) cudaFree(base);
@@ -29,11 +30,11 @@ struct Arena {
     if (e == cudaSuccess) cap = want;
     return e;
   }
-  void reset() { off = 0; }
+  void reset() { off = 0; failed = false; }
   template <class T>
   T* take(size_t n) {
     size_t bytes = (n * sizeof(T) + 255) & ~size_t(255);
-    if (off + bytes > cap) return nullptr;
+    if (off + bytes > cap) { failed = true; return nullptr; }
     T* p = reinterpret_cast<T*>(base + off);
     off += bytes;
     return p;

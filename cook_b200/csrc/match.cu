@@ -161,8 +161,18 @@ struct MatchArgs {
   int* latest_global;         // newest-log-entry table when it does not fit in shared memory
   int lookahead;              // queue entries in flight (<= RING)
   int poll_ns;                // back-off of the resolver's shared-memory polling loops
-  int max_spec_warp;          // spec warps are the non-commit, non-driver warps below this id
+  int max_spec_warp;          // spec warps of a spec CTA are warps 2 .. max_spec_warp - 1
   int spec_kmin;              // candidate rounds stop once this many candidates are out
+  // ---- spec CTAs (blocks 1 .. n_spec): the resolver's log, replicated through global memory
+  int n_spec;                 // thread blocks that only compute candidate sets
+  struct LogEnt* glog;        // [LOGN] copy of the commit log (publisher warp -> follower warps)
+  int4* glogx;                // [LOGN] constraint kernel: {room, occ, ptot, -}
+  unsigned long long* gchain; // the chain word as published (entries below its log size are in glog)
+  int32_t* lo_g;              // [max blocks] lo_g[b] = log size at the start of block b
+  struct SpecOut* gres;       // [GRING] candidate sets on their way to the resolver (fetched with cp.async.bulk)
+  unsigned* gres_seq;         // [GRING] g + 1 once the result of queue entry g is complete
+  int32_t* dead_blk;          // b + 1 once no VM can take even the smallest request from block b on
+  int32_t* dead_k0;           // first job of that block (-1 while unknown): finalize marks the rest
 };
 
 // ------------------------------------------------------------------ helpers
@@ -176,6 +186,46 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void st_release_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// ---- mbarrier + bulk async copy (TMA engine, no tensor map): the resolver receives the
+// spec CTAs' candidate sets with cp.async.bulk completing on an mbarrier its commit warps sleep on
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// potentially blocking: the warp sleeps in hardware until the phase completes or ~hint_ns pass
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, unsigned parity, unsigned hint_ns) {
+  unsigned ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(hint_ns) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 
 struct JobRegs {  // per-job values the hot loop keeps in registers
   double c, m, g;
@@ -626,6 +676,8 @@ __device__ void evaluate_row(const MatchArgs& a, const JobRegs& r, const bool gr
 constexpr int MAXB = 512;             // max jobs per block
 constexpr int LOGN = 2 * MAXB;        // commit-log ring (entries of two blocks)
 constexpr int RING = 32;              // queue entries / spec results in flight
+constexpr int GRING = 64;             // candidate sets in flight between the spec CTAs and the resolver (global)
+constexpr int MAX_SPEC_CTAS = 8;
 constexpr int KC = 16;                // candidates per spec result
 #ifndef COOK_LK
 #define COOK_LK 4
@@ -671,7 +723,7 @@ struct Cand {  // one candidate VM with its state at the result's version
   int vm, e;
 };
 
-struct SpecOut {
+struct __align__(16) SpecOut {
   int type, s, n, complete;  // type: Q_JOB / Q_END / Q_EXIT (the commit warps wait on the result flag only)
   double zf;                 // bound: every unchanged VM outside c[] is no better than (zf, zv)
   int gver, pad;             // group-state version the result was computed against (group jobs)
@@ -679,13 +731,18 @@ struct SpecOut {
   Cand c[KC + 1];            // unsorted; c[KC] = the bound VM when z_real
 };
 
+static_assert(sizeof(SpecOut) % 16 == 0, "candidate sets travel with cp.async.bulk (16 B granules)");
+static_assert(RING == 32, "the fetcher warp owns one result slot per lane");
+
+// Shared state of the resolver CTA; the spec CTAs keep a replica of the log / queue part.
 struct ResolverShared {
   LogEnt log[LOGN];
   int4 logx[LOGN];                // constraint kernel: {room, occ, ptot, -} of the entry's VM
   QEntry q[RING];
   SpecOut res[RING + 1];          // [RING] = the commit warps' fallback slot
+  unsigned long long res_bar[RING];  // mbarrier per result slot: phase (g / RING) & 1 completes when the
+                                     // result of entry g has landed (bulk copy) or the entry is END / EXIT
   volatile int q_seq[RING];       // g+1 once queue entry g is filled
-  volatile int res_seq[RING];     // g+1 once the result of entry g is ready
   // chain word: (entries consumed by the commit warps) << 32 | (log entries written)
   volatile unsigned long long chain;
   volatile int exit_g;            // queue index of the EXIT entry (-1 while running)
@@ -694,7 +751,6 @@ struct ResolverShared {
   volatile int bk_ring[8];        // bk_ring[b & 7] = first job of block b
   volatile int bk_known;          // blocks 0..bk_known have their first job recorded
   volatile int out_done, blk_c0, last_b;  // END bookkeeping shared by the commit warps
-  unsigned long long n_rescan, n_trunc;
 };
 
 __device__ __forceinline__ int chain_gdone(unsigned long long w) { return (int)(w >> 32); }
@@ -868,7 +924,7 @@ __device__ __forceinline__ void spec_job(const MatchArgs& a, ResolverShared& S, 
       // a sentinel dominates every head: the lane that holds it
       const int wl = __ffs(__ballot_sync(0xffffffffu, rf == mf && rv == mv)) - 1;
       const bool wcb = __shfl_sync(0xffffffffu, (s_cb && rf == sf && rv == sv) ? 1 : 0, wl) != 0;
-      if (!wcb || n >= exact_n) { if (lane == 0) atomicAdd(&S.n_trunc, 1ull); break; }
+      if (!wcb || n >= exact_n) { if (lane == 0) atomicAdd(a.stats + 5, 1ull); break; }
       // exact re-scan of chunk wl: clean VMs strictly worse than its bound
       const double bf = __shfl_sync(0xffffffffu, L.cbf, wl);
       const int bv = __shfl_sync(0xffffffffu, L.cbv, wl);
@@ -885,7 +941,7 @@ __device__ __forceinline__ void spec_job(const MatchArgs& a, ResolverShared& S, 
         const double x = eval_res<CONSTR>(a, r, v, st, wg, true);
         if (x > 0.0 && better(bf, bv, x, v)) L.insert(x, v, -1);
       }
-      if (lane == 0) atomicAdd(&S.n_rescan, 1ull);
+      if (lane == 0) atomicAdd(a.stats + 1, 1ull);
       continue;
     }
     int cnt = __popc(q);
@@ -971,7 +1027,9 @@ __device__ __noinline__ int resolve_group_job(const MatchArgs& a, ResolverShared
 }
 
 // ---- driver warp: feasibility stamps -> in-order queue
-template <bool CONSTR>
+// The resolver CTA runs the driver; every spec CTA runs a replica (REMOTE) that derives the same
+// queue from the same global inputs (stamps, block bounds, lo_g) and fills only its local ring.
+template <bool CONSTR, bool REMOTE>
 __device__ void driver_warp(const MatchArgs& a, ResolverShared& S) {
   const int lane = threadIdx.x & 31;
   int g = 0;
@@ -980,15 +1038,44 @@ __device__ void driver_warp(const MatchArgs& a, ResolverShared& S) {
     while (chain_gdone(S.chain) <= gi - a.lookahead) __nanosleep(a.poll_ns);
   };
   for (int b = 0;; b++) {
-    while (S.bk_known < b + 1) __nanosleep(20);  // block b's bounds are set two block ends ahead
-    const int k0 = S.bk_ring[b & 7];
+    int k0, k1;
+    if (!REMOTE) {
+      while (S.bk_known < b + 1) __nanosleep(20);  // block b's bounds are set two block ends ahead
+      k0 = S.bk_ring[b & 7];
+      k1 = S.bk_ring[(b + 1) & 7];
+    } else {
+      if (b >= 2) {  // bk0[b], bk0[b+1] and lo_g[b-1] are written before `published` reaches b - 1
+        if (lane == 0) {
+          while ((int)ld_relaxed_u32(a.published) < b - 1) __nanosleep(64);
+          __threadfence();
+        }
+        __syncwarp();
+      }
+      k0 = __ldcg(a.bk0 + b);
+      k1 = __ldcg(a.bk0 + b + 1);
+    }
     if (k0 >= a.n_cons) break;
-    const int nj = min(S.bk_ring[(b + 1) & 7], a.n_cons) - k0;
-    if (lane == 0)
-      while (ld_acquire_u32(a.rows_ready + b) < (unsigned)nj) __nanosleep(20);
-    __syncwarp();
+    const int nj = min(k1, a.n_cons) - k0;
+    // the evaluators stop as soon as no VM can take even the smallest request left (exact: the
+    // assigned amounts only grow): everything from this block on is unplaceable
+    int dead = 0;
+    if (lane == 0) {
+      while (ld_acquire_u32(a.rows_ready + b) < (unsigned)nj) {
+        const int db = (int)ld_relaxed_u32(reinterpret_cast<const unsigned*>(a.dead_blk));
+        if (db != 0 && db - 1 <= b) { dead = 1; break; }
+        __nanosleep(20);
+      }
+    }
+    dead = __shfl_sync(0xffffffffu, dead, 0);
+    if (dead) {
+      if (!REMOTE && lane == 0) {
+        skipped += (unsigned long long)(a.n_cons - k0);
+        *a.dead_k0 = k0;
+      }
+      break;
+    }
     // rows b ready => END(b-2) was processed => the start of block b-1 is recorded
-    const int lo = b == 0 ? 0 : S.lo_ring[(b - 1) & 3];
+    const int lo = b == 0 ? 0 : (REMOTE ? __ldcg(a.lo_g + b - 1) : S.lo_ring[(b - 1) & 3]);
     const int32_t* feas = a.feas + (size_t)(b & 1) * a.bmax;
     // all stamps of the block in one L2 round trip (a block has at most MAXB rows)
     int stamp[MAXB / 32];
@@ -1003,7 +1090,7 @@ __device__ void driver_warp(const MatchArgs& a, ResolverShared& S) {
       const bool fz = valid && stamp[t] == b + 1;
       // jobs with no feasible VM at the snapshot are unplaceable now too (resources
       // and count constraints only tighten within a cycle): skip them wholesale.
-      if (valid && !fz) { a.assign[k0 + i] = -1; a.fail[k0 + i] = COOK_FAIL_RESOURCES; }
+      if (!REMOTE && valid && !fz) { a.assign[k0 + i] = -1; a.fail[k0 + i] = COOK_FAIL_RESOURCES; }
       const unsigned mask = __ballot_sync(0xffffffffu, fz);
       skipped += __popc(__ballot_sync(0xffffffffu, valid && !fz));
       if (fz) {
@@ -1028,10 +1115,10 @@ __device__ void driver_warp(const MatchArgs& a, ResolverShared& S) {
       wait_slot(g);
       QEntry& q = S.q[g & (RING - 1)];
       q.type = Q_END; q.blk = b; q.k = -1; q.lo = lo; q.grp = 0;
-      S.res[g & (RING - 1)].type = Q_END;
+      if (!REMOTE) S.res[g & (RING - 1)].type = Q_END;
       fence_cta();
       S.q_seq[g & (RING - 1)] = g + 1;
-      S.res_seq[g & (RING - 1)] = g + 1;
+      if (!REMOTE) mbar_arrive(&S.res_bar[g & (RING - 1)]);
     }
     g++;
     __syncwarp();
@@ -1039,23 +1126,25 @@ __device__ void driver_warp(const MatchArgs& a, ResolverShared& S) {
   if (lane == 0) {
     wait_slot(g);
     S.q[g & (RING - 1)].type = Q_EXIT;
-    S.res[g & (RING - 1)].type = Q_EXIT;
+    if (!REMOTE) S.res[g & (RING - 1)].type = Q_EXIT;
     fence_cta();
     S.q_seq[g & (RING - 1)] = g + 1;
-    S.res_seq[g & (RING - 1)] = g + 1;
+    if (!REMOTE) mbar_arrive(&S.res_bar[g & (RING - 1)]);
     S.exit_g = g;
-    a.stats[6] = skipped;
+    if (!REMOTE) a.stats[6] = skipped;
   }
 }
 
-// ---- spec warps
+// ---- spec warps (spec CTA ci of n_spec): entries g = ci, ci + n_spec, ... of the queue.  The
+// candidate set goes to global memory; the resolver's fetcher warp pulls it into its result ring.
 template <bool CONSTR>
-__device__ void spec_warp(const MatchArgs& a, ResolverShared& S, const Latest latest) {
+__device__ void spec_warp(const MatchArgs& a, ResolverShared& S, const Latest latest, const int ci) {
   const int lane = threadIdx.x & 31;
   while (true) {
-    int g = 0;
-    if (lane == 0) g = atomicAdd(&S.ticket, 1);
-    g = __shfl_sync(0xffffffffu, g, 0);
+    int t = 0;
+    if (lane == 0) t = atomicAdd(&S.ticket, 1);
+    t = __shfl_sync(0xffffffffu, t, 0);
+    const int g = t * a.n_spec + ci;
     const int slot = g & (RING - 1);
     bool quit = false;
     while (S.q_seq[slot] != g + 1) {
@@ -1070,9 +1159,124 @@ __device__ void spec_warp(const MatchArgs& a, ResolverShared& S, const Latest la
     if (qe.type != Q_JOB) continue;
     const int s = chain_ncommit(S.chain);
     compiler_barrier();
-    spec_job<CONSTR>(a, S, latest, qe, s, KC, 2, S.res[slot]);
-    fence_cta();
-    if (lane == 0) S.res_seq[slot] = g + 1;
+    spec_job<CONSTR>(a, S, latest, qe, s, KC, 2, a.gres[g & (GRING - 1)]);
+    __threadfence();  // every lane's part of the result is out before the flag
+    __syncwarp();
+    if (lane == 0) st_release_u32(a.gres_seq + (g & (GRING - 1)), (unsigned)(g + 1));
+  }
+}
+
+// ---- publisher warp (resolver CTA): copies new log entries to global memory and then publishes
+// the chain word they belong to; off the chain, batches whatever accumulated since its last pass.
+template <bool CONSTR>
+__device__ void publisher_warp(const MatchArgs& a, ResolverShared& S) {
+  const int lane = threadIdx.x & 31;
+  int p = 0;
+  unsigned long long last = 0ull;
+  while (true) {
+    const unsigned long long w = S.chain;
+    compiler_barrier();
+    if (w != last) {
+      const int c = chain_ncommit(w);
+      for (int base = p; base < c; base += 6) {  // 6 entries x 5 granules of 16 B per pass
+        const int e = base + lane / 5, ch = lane % 5;
+        if (lane < 30 && e < c) {
+          const int4 v = reinterpret_cast<const int4*>(&S.log[e & (LOGN - 1)])[ch];
+          __stcg(reinterpret_cast<int4*>(a.glog + (e & (LOGN - 1))) + ch, v);
+        }
+      }
+      if (CONSTR)
+        for (int e = p + lane; e < c; e += 32) __stcg(a.glogx + (e & (LOGN - 1)), S.logx[e & (LOGN - 1)]);
+      __threadfence();
+      __syncwarp();
+      if (lane == 0) st_release_u64(a.gchain, w);
+      p = c;
+      last = w;
+    } else {
+      __nanosleep(40);
+    }
+    const int xg = S.exit_g;
+    if (xg >= 0 && chain_gdone(last) >= xg) return;
+  }
+}
+
+// ---- follower warp (spec CTA): keeps the CTA's replica of the log, latest[] and the chain word
+// up to date.  The replica may lag: a candidate set computed against version s is valid for any
+// s (the owner folds every entry >= s), lag only shifts work to the owner's first look.
+template <bool CONSTR>
+__device__ void follower_warp(const MatchArgs& a, ResolverShared& S, const Latest latest) {
+  const int lane = threadIdx.x & 31;
+  int p = 0;
+  unsigned long long last = 0ull;
+  while (true) {
+    unsigned long long w = 0ull;
+    if (lane == 0) w = ld_relaxed_u64(a.gchain);
+    w = __shfl_sync(0xffffffffu, w, 0);
+    if (w != last) {
+      __threadfence();  // acquire: the entries below the published log size are visible
+      const int c = chain_ncommit(w);
+      for (int base = p; base < c; base += 6) {
+        const int e = base + lane / 5, ch = lane % 5;
+        if (lane < 30 && e < c) {
+          const int4 v = __ldcg(reinterpret_cast<const int4*>(a.glog + (e & (LOGN - 1))) + ch);
+          reinterpret_cast<int4*>(&S.log[e & (LOGN - 1)])[ch] = v;
+        }
+      }
+      if (CONSTR)
+        for (int e = p + lane; e < c; e += 32) S.logx[e & (LOGN - 1)] = __ldcg(a.glogx + (e & (LOGN - 1)));
+      __syncwarp();
+      if (lane == 0) {
+        for (int e = p; e < c; e++) latest.set(S.log[e & (LOGN - 1)].vm, e);  // in order: the newest entry wins
+        fence_cta();
+        S.chain = w;
+      }
+      __syncwarp();
+      p = c;
+      last = w;
+    } else {
+      __nanosleep(40);
+    }
+    const int xg = S.exit_g;
+    if (xg >= 0 && chain_gdone(last) >= xg) return;
+  }
+}
+
+// ---- fetcher warp (resolver CTA): lane l owns result slot l.  Once the queue entry of its next
+// g is known to be a job it polls the spec CTAs' flag for g and then moves the candidate set
+// global -> shared with ONE bulk async copy that completes on the slot's mbarrier: the commit
+// warps sleep on that barrier instead of polling.
+__device__ void fetcher_warp(const MatchArgs& a, ResolverShared& S) {
+  const int lane = threadIdx.x & 31;
+  int g = lane;
+  bool have_q = false, done = false;
+  while (true) {
+    if (!done && !have_q) {
+      if (S.q_seq[lane] == g + 1) {
+        compiler_barrier();
+        const int type = S.q[lane].type;
+        if (type == Q_JOB) have_q = true;
+        else if (type == Q_EXIT) done = true;
+        else g += RING;
+      } else {
+        const int xg = S.exit_g;
+        if (xg >= 0 && g > xg) done = true;
+      }
+    }
+    bool issued = false;
+    if (!done && have_q) {
+      const int gi = g & (GRING - 1);
+      if (ld_relaxed_u32(a.gres_seq + gi) == (unsigned)(g + 1)) {
+        __threadfence();             // acquire the spec warp's stores ...
+        fence_proxy_async_global();  // ... and order them before the async proxy's read
+        mbar_arrive_expect_tx(&S.res_bar[lane], (unsigned)sizeof(SpecOut));
+        bulk_g2s(&S.res[lane], a.gres + gi, (unsigned)sizeof(SpecOut), &S.res_bar[lane]);
+        have_q = false;
+        g += RING;
+        issued = true;
+      }
+    }
+    if (__all_sync(0xffffffffu, done)) return;
+    if (!__any_sync(0xffffffffu, issued)) __nanosleep(a.poll_ns);
   }
 }
 
@@ -1110,13 +1314,13 @@ __device__ void commit_warp(const MatchArgs& a, ResolverShared& S, const Latest 
     const int slot = g & (RING - 1);
     long long t0 = PROF ? clock64() : 0;
     bool quit = false;
-    while (S.res_seq[slot] != g + 1) {
+    // the result of entry g lands in res[slot] by bulk copy (or the driver marks END / EXIT) and
+    // completes phase (g / RING) & 1 of the slot's mbarrier: the warp sleeps in hardware
+    while (!mbar_try_wait(&S.res_bar[slot], (unsigned)(g >> 5) & 1u, 2000u)) {
       const int xg = S.exit_g;
       if (xg >= 0 && g > xg) { quit = true; break; }
-      __nanosleep(a.poll_ns);
     }
     if (quit) break;
-    compiler_barrier();
     const SpecOut* R = &S.res[slot];
     const int type = R->type;
     if (PROF) prof[0] += (unsigned long long)(clock64() - t0);
@@ -1164,6 +1368,7 @@ __device__ void commit_warp(const MatchArgs& a, ResolverShared& S, const Latest 
         const int end2 = S.bk_ring[(b + 2) & 7] + nbn;   // = first job of block b+3
         S.bk_ring[(b + 3) & 7] = end2;
         __stcg(a.bk0 + b + 3, end2);
+        __stcg(a.lo_g + b + 1, c);   // the spec CTAs' driver replicas read the block's lo from here
         fence_cta();
         S.bk_known = b + 3;
         __threadfence();
@@ -1392,7 +1597,6 @@ __device__ void commit_warp(const MatchArgs& a, ResolverShared& S, const Latest 
   if (lane == 0) {
     atomicAdd(a.stats + 0, n_fast); atomicAdd(a.stats + 2, n_group); atomicAdd(a.stats + 3, n_matched);
     atomicAdd(a.stats + 4, n_fallback); atomicAdd(a.stats + 7, n_slow_turn); atomicAdd(a.stats + 24, n_ztake); atomicAdd(a.stats + 25, n_relook);
-    if (cw == 0) { a.stats[1] = S.n_rescan; a.stats[5] = S.n_trunc; }
     for (int i = 0; i < 6; i++) atomicAdd(a.stats + 8 + i, prof[i]);
   }
 }
@@ -1405,35 +1609,39 @@ __device__ void commit_warp(const MatchArgs& a, ResolverShared& S, const Latest 
 template <bool CONSTR, bool PROF>
 __global__ void __launch_bounds__(RES_THREADS, 1) match_kernel(MatchArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  if (blockIdx.x == 0) {
+  const int ns = a.n_spec;
+  if ((int)blockIdx.x <= ns) {
+    // block 0: the resolver; blocks 1..ns: spec CTAs with a replica of the resolver's log
     ResolverShared& S = *reinterpret_cast<ResolverShared*>(smem_raw);
     Latest latest;
     const size_t res_base = (sizeof(ResolverShared) + 15) & ~size_t(15);
     unsigned* sbw_base = reinterpret_cast<unsigned*>(smem_raw + res_base);   // NCW rows of verdict bits
     latest.s = reinterpret_cast<int*>(smem_raw + res_base + (((size_t)NCW * a.sb_words * 4 + 15) & ~size_t(15)));
-    latest.g = a.latest_global;
+    latest.g = a.latest_global ? a.latest_global + (size_t)blockIdx.x * (size_t)(a.of.O + 1) : nullptr;
     const int warp = threadIdx.x >> 5;
     for (int i = threadIdx.x; i < a.of.O; i += RES_THREADS) latest.set(i, -1);
-    if (threadIdx.x < RING) { S.q_seq[threadIdx.x] = 0; S.res_seq[threadIdx.x] = 0; }
+    if (threadIdx.x < RING) S.q_seq[threadIdx.x] = 0;
     for (int i = threadIdx.x; i < LOGN; i += RES_THREADS) S.log[i].vm = 0;
     if (threadIdx.x == 0) {
       S.chain = 0ull; S.exit_g = -1; S.ticket = 0;
       S.lo_ring[0] = S.lo_ring[1] = S.lo_ring[2] = S.lo_ring[3] = 0;
       S.bk_ring[0] = 0; S.bk_ring[1] = a.B; S.bk_ring[2] = 2 * a.B; S.bk_known = 2;  // = host-initialised bk0[0..2]
       S.out_done = 0; S.blk_c0 = 0; S.last_b = a.B;
-      S.n_rescan = 0; S.n_trunc = 0;
+      for (int i = 0; i < RING; i++) mbar_init(&S.res_bar[i], 1u);
+      fence_proxy_async_smem();  // the barriers are visible to the async proxy (bulk copies complete on them)
     }
     __syncthreads();
-    // warps 0, 4, 8, 12 share one scheduler (warp id mod 4): the commit warps keep it to themselves
-#ifndef COOK_PACKED  // one commit warp per scheduler (A/B: COOK_PACKED puts them all on scheduler 0)
-    if (warp < NCW) commit_warp<CONSTR, PROF>(a, S, latest, warp, sbw_base + (size_t)warp * a.sb_words);
-    else if (warp == NCW) driver_warp<CONSTR>(a, S);
-    else if (warp < a.max_spec_warp) spec_warp<CONSTR>(a, S, latest);
-#else
-    if ((warp & 3) == 0) { if ((warp >> 2) < NCW) commit_warp<CONSTR, PROF>(a, S, latest, warp >> 2, sbw_base + (size_t)(warp >> 2) * a.sb_words); }
-    else if (warp == 1) driver_warp<CONSTR>(a, S);
-    else if (warp < a.max_spec_warp) spec_warp<CONSTR>(a, S, latest);
-#endif
+    if (blockIdx.x == 0) {
+      // warps 0..3 sit on different schedulers (warp id mod 4): one commit warp each
+      if (warp < NCW) commit_warp<CONSTR, PROF>(a, S, latest, warp, sbw_base + (size_t)warp * a.sb_words);
+      else if (warp == NCW) driver_warp<CONSTR, false>(a, S);
+      else if (warp == NCW + 1) publisher_warp<CONSTR>(a, S);
+      else if (warp == NCW + 2) fetcher_warp(a, S);
+    } else {
+      if (warp == 0) follower_warp<CONSTR>(a, S, latest);
+      else if (warp == 1) driver_warp<CONSTR, true>(a, S);
+      else if (warp < a.max_spec_warp) spec_warp<CONSTR>(a, S, latest, (int)blockIdx.x - 1);
+    }
   } else {
     EvalStatic es;
     es.lc = es.lm = es.rc = es.rm = nullptr;
@@ -1452,7 +1660,8 @@ __global__ void __launch_bounds__(RES_THREADS, 1) match_kernel(MatchArgs a) {
     __shared__ int bk_s[2];
     __shared__ double smin_s[2];
     if ((threadIdx.x >> 5) >= NW) return;  // only NW warps score rows (exited threads do not block the barriers)
-    const int n_eval = gridDim.x - 1;
+    const int n_eval = gridDim.x - 1 - ns;
+    const int ei = (int)blockIdx.x - 1 - ns;   // this evaluator's index
     unsigned long long work = 0, wait = 0, work_q1 = 0, rows_q1 = 0, nblk_seen = 0;
     unsigned long long ep[3] = {0, 0, 0};
     for (int b = 0;; b++) {
@@ -1492,9 +1701,15 @@ __global__ void __launch_bounds__(RES_THREADS, 1) match_kernel(MatchArgs a) {
           const bool dead = (d0.x + minc > lc) | (d0.y + minm > lm);
           if (!dead) live |= 1ull << u;
         }
+        // every CTA sees all VMs: when none is live nothing from k0 on can ever be placed
+        // (state only tightens) - all evaluators stop here and the drivers end the cycle
+        if (!__syncthreads_or(live != 0ull)) {
+          if (threadIdx.x == 0) atomicMax(a.dead_blk, b + 1);
+          break;
+        }
       }
       // the next row's job columns are fetched while this row is scored
-      int k = k0 + (int)blockIdx.x - 1;
+      int k = k0 + ei;
       JobRegs rn;
       bool gn = false;
       if (k < k1) { rn = load_job<CONSTR>(a, k); gn = CONSTR && (a.kflags[k] & 1); }
@@ -1509,7 +1724,7 @@ __global__ void __launch_bounds__(RES_THREADS, 1) match_kernel(MatchArgs a) {
       work += dt;
       if (PROF) { if (k0 < a.n_cons / 4) { work_q1 += dt; rows_q1 += (k1 - k0 + n_eval - 1) / n_eval; } nblk_seen++; }
     }
-    if (blockIdx.x == 1 && threadIdx.x == 0) {
+    if (ei == 0 && threadIdx.x == 0) {
       a.stats[16] = work; a.stats[17] = wait;
       if (PROF) { a.stats[18] = ep[0]; a.stats[19] = ep[1]; a.stats[20] = ep[2]; a.stats[21] = work_q1; a.stats[22] = rows_q1; a.stats[23] = nblk_seen; }
     }
@@ -1862,6 +2077,9 @@ __global__ void finalize_kernel(MatchArgs a, int32_t* out_assign, int32_t* out_p
                                 int32_t* used_flag) {
   int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= a.n_cons) return;
+  // the cycle ended early: from dead_k0 on no VM could take even the smallest request left
+  const int dk = *a.dead_k0;
+  if (dk >= 0 && k >= dk) a.fail[k] = COOK_FAIL_RESOURCES;
   int v = a.assign[k];
   int o = v >= 0 ? a.of.perm[v] : -1;
   out_assign[k] = o;
@@ -1923,6 +2141,8 @@ struct MatchPlan {
   unsigned long long* d_stats = nullptr;
   int32_t* d_counters = nullptr;
   int* d_latest = nullptr;
+  unsigned long long* d_gchain = nullptr;
+  size_t lo_g_n = 0;
   double *d_smin_c = nullptr, *d_smin_m = nullptr, *d_smin_bc = nullptr, *d_smin_bm = nullptr;
   size_t max_blocks = 0;
   int32_t bk_init[3] = {0, 0, 0};
@@ -2033,6 +2253,8 @@ static int32_t build_plan(cook_pool* pool, MatchPlan* mp, const int32_t* ranked_
   sz.add<VmCnt>(O + 1); sz.add<VmCnt>(O + 1);
   sz.add<VmCons>(O + 1); sz.add<int32_t>((size_t)offers->n_attr_cols * O + 1);
   sz.add<double>(NC + 1); sz.add<double>(NC + 1); sz.add<double>(NC / 256 + 2); sz.add<double>(NC / 256 + 2);
+  sz.add<LogEnt>(LOGN); sz.add<int4>(LOGN); sz.add<unsigned long long>(4); sz.add<int32_t>(max_blocks + 8);
+  sz.add<SpecOut>(GRING); sz.add<unsigned>(GRING); sz.add<int>((size_t)(MAX_SPEC_CTAS + 1) * (O + 1));
   CK(pool, ar.reserve(sz.off + (1 << 18)));
   ar.reset();
 
@@ -2159,14 +2381,23 @@ static int32_t build_plan(cook_pool* pool, MatchPlan* mp, const int32_t* ranked_
   mp->d_used = ar.take<int32_t>(O + 1);
   mp->d_stats = ar.take<unsigned long long>(32);
   mp->d_counters = ar.take<int32_t>(16);
-  mp->d_latest = ar.take<int>(O + 1);
-  if (!mp->d_counters || !mp->d_latest) return set_err(pool, COOK_E_OOM, "cook_match: arena exhausted");
+  mp->d_latest = ar.take<int>((size_t)(MAX_SPEC_CTAS + 1) * (O + 1));
+  ma.glog = ar.take<LogEnt>(LOGN);
+  ma.glogx = ar.take<int4>(LOGN);
+  mp->d_gchain = ar.take<unsigned long long>(4);
+  ma.gchain = mp->d_gchain;
+  ma.lo_g = ar.take<int32_t>(max_blocks + 8);
+  mp->lo_g_n = max_blocks + 8;
+  ma.gres = ar.take<SpecOut>(GRING);
+  ma.gres_seq = ar.take<unsigned>(GRING);
+  if (ar.failed) return set_err(pool, COOK_E_OOM, "cook_match: arena exhausted");
   ma.jb = jb; ma.of = of; ma.gr = gr;
   ma.cons = mp->d_cons; ma.kc = mp->d_kc; ma.km = mp->d_km; ma.kflags = mp->d_kflags;
   ma.B = B; ma.bmin = bmin; ma.bmax = bmax; ma.btarget = btarget;
   ma.host_lifetime_mins = params->host_lifetime_mins;
   ma.published = reinterpret_cast<unsigned*>(mp->d_counters + 8); ma.stats = mp->d_stats;
-  ma.lookahead = 20;
+  ma.dead_blk = mp->d_counters + 9; ma.dead_k0 = mp->d_counters + 10;
+  ma.lookahead = 24;
   ma.poll_ns = 200;
   ma.max_spec_warp = RES_THREADS / 32;
   ma.spec_kmin = 12;
@@ -2195,6 +2426,10 @@ static int32_t run_plan(cook_pool* pool, MatchPlan* mp, int32_t* out_considerabl
   CK(pool, cudaMemsetAsync(mp->d_used, 0, sizeof(int32_t) * (O + 1), st));
   CK(pool, cudaMemsetAsync(mp->d_stats, 0, sizeof(unsigned long long) * 32, st));
   CK(pool, cudaMemsetAsync(mp->d_counters, 0, sizeof(int32_t) * 16, st));
+  CK(pool, cudaMemsetAsync(mp->d_counters + 10, 0xff, sizeof(int32_t), st));   // dead_k0 = -1
+  CK(pool, cudaMemsetAsync(mp->d_gchain, 0, sizeof(unsigned long long) * 4, st));
+  CK(pool, cudaMemsetAsync(ma.gres_seq, 0, sizeof(unsigned) * GRING, st));
+  CK(pool, cudaMemsetAsync(ma.lo_g, 0, sizeof(int32_t) * 4, st));
   CK(pool, cudaMemsetAsync(ma.rows_ready, 0, sizeof(unsigned) * (mp->max_blocks + 8), st));
   CK(pool, cudaMemsetAsync(ma.feas, 0, sizeof(int32_t) * (2 * (size_t)mp->ma.bmax + 16), st));
   {  // first three block bounds; the resolver appends the rest while it runs
@@ -2293,7 +2528,13 @@ static int32_t run_plan(cook_pool* pool, MatchPlan* mp, int32_t* out_considerabl
       int occ = 0;
       CK(pool, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kfn, RES_THREADS, smem));
       if (occ < 1) return set_err(pool, COOK_E_CUDA, "cook_match: kernel does not fit on an SM");
-      if (grid < 2) grid = 2;
+      // roles: block 0 resolves, blocks 1..n_spec compute candidate sets, the rest score rows
+      if (grid < 3) grid = 3;
+      int n_spec = 3;
+      if (const char* es = getenv("COOK_NSPEC")) n_spec = atoi(es);
+      n_spec = std::max(1, std::min(n_spec, std::min(MAX_SPEC_CTAS, std::max(1, grid / 8))));
+      n_spec = std::min(n_spec, grid - 2);
+      ma.n_spec = n_spec;
       void* kargs[] = {&ma};
       CK(pool, cudaLaunchCooperativeKernel(kfn, dim3(grid), dim3(RES_THREADS), kargs, smem, st));
       launches++;
