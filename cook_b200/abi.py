@@ -129,6 +129,18 @@ class MatchStats(C.Structure):
         return {n: getattr(self, n) for n, _ in self._fields_}
 
 
+class PhaseStats(C.Structure):
+    _fields_ = [("ms_h2d", C.c_double), ("ms_device", C.c_double), ("ms_d2h", C.c_double),
+                ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64), ("n_launches", C.c_int32),
+                ("reserved0", C.c_int32)]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_ if n != "reserved0"}
+
+
+PHASE_RANK, PHASE_MATCH, PHASE_REBALANCE, PHASE_EXCHANGE = 0, 1, 2, 3
+
+
 class RunningSoA(_SoA):
     _fields_ = [("t", TasksSoA), ("host", P_I32)]
 

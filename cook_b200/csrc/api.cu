@@ -65,6 +65,7 @@ int32_t cook_pool_close(cook_pool* p) {
   cudaSetDevice(p->device);
   if (p->stream) cudaStreamSynchronize(p->stream);
   p->arena.release();
+  if (p->xchg) cudaFree(p->xchg);
   if (p->match_plan && p->match_plan_free) p->match_plan_free(p->match_plan);
   for (auto& e : p->ev)
     if (e) cudaEventDestroy(e);
@@ -77,6 +78,12 @@ int32_t cook_last_error(cook_pool* p, char* buf, int32_t len) {
   if (!p || !buf || len <= 0) return COOK_E_BADARG;
   strncpy(buf, p->err, (size_t)len - 1);
   buf[len - 1] = 0;
+  return COOK_OK;
+}
+
+int32_t cook_last_stats(cook_pool* p, int32_t phase, cook_phase_stats* out) {
+  if (!p || !out || phase < 0 || phase > 3) return COOK_E_BADARG;
+  *out = p->phase[phase];
   return COOK_OK;
 }
 
@@ -98,6 +105,44 @@ int32_t cook_allgather_usage(void* comm, void* stream, const double* local_dev, 
   const int ncclFloat64 = 8;  // ncclDataType_t: ncclDouble
   int rc = fn(local_dev, out_dev, (size_t)n_doubles, ncclFloat64, comm, stream);
   return rc == 0 ? COOK_OK : COOK_E_NCCL;
+}
+
+static void* nccl_sym(const char* name) {
+  static void* h = nullptr;
+  if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  return h ? dlsym(h, name) : nullptr;
+}
+struct nccl_uid { char b[128]; };
+int32_t cook_comm_unique_id(uint8_t out_id[128]) {
+  if (!out_id) return COOK_E_BADARG;
+  typedef int (*fn_t)(nccl_uid*);
+  fn_t fn = (fn_t)nccl_sym("ncclGetUniqueId");
+  if (!fn) return COOK_E_NCCL;
+  nccl_uid u;
+  if (fn(&u) != 0) return COOK_E_NCCL;
+  memcpy(out_id, u.b, 128);
+  return COOK_OK;
+}
+int32_t cook_comm_init(const uint8_t id[128], int32_t rank, int32_t world, int32_t device, void** out_comm) {
+  if (!id || !out_comm || rank < 0 || world <= 0 || rank >= world) return COOK_E_BADARG;
+  typedef int (*fn_t)(void**, int, nccl_uid, int);
+  fn_t fn = (fn_t)nccl_sym("ncclCommInitRank");
+  if (!fn) return COOK_E_NCCL;
+  if (cudaSetDevice(device) != cudaSuccess) return COOK_E_CUDA;
+  nccl_uid u;
+  memcpy(u.b, id, 128);
+  void* comm = nullptr;
+  if (fn(&comm, world, u, rank) != 0) return COOK_E_NCCL;
+  *out_comm = comm;
+  return COOK_OK;
+}
+int32_t cook_comm_destroy(void* comm) {
+  if (!comm) return COOK_E_BADARG;
+  typedef int (*fn_t)(void*);
+  fn_t fn = (fn_t)nccl_sym("ncclCommDestroy");
+  if (!fn) return COOK_E_NCCL;
+  return fn(comm) == 0 ? COOK_OK : COOK_E_NCCL;
 }
 
 }  // extern "C"

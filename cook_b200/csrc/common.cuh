@@ -60,7 +60,10 @@ struct cook_pool {
   int device = 0;
   int sm_count = 0;
   cudaStream_t stream = nullptr;
-  cudaEvent_t ev[8] = {};
+  cudaEvent_t ev[20] = {};
+  cook_phase_stats phase[4] = {};        // last rank / match / rebalance / exchange call
+  double* xchg = nullptr;                // exchange buffers: [n_pad] local + [world * n_pad] gathered
+  size_t xchg_cap = 0;
   Arena arena;
   void* pinned = nullptr;  // small pinned scratch for result scalars
   size_t pinned_cap = 0;

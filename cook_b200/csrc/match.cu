@@ -29,6 +29,7 @@
 #include <cooperative_groups.h>
 
 #include <algorithm>
+#include <mutex>
 #include <numeric>
 
 #include "common.cuh"
@@ -2102,6 +2103,39 @@ __global__ void finalize_kernel(MatchArgs a, int32_t* out_assign, int32_t* out_p
   }
 }
 
+// ---- usage delta of a match round: jobs placed this cycle, per user
+__global__ void placed_flag_kernel(const int32_t* cons, const int32_t* out_assign, int n_cons, uint8_t* placed_job) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n_cons && out_assign[k] >= 0) placed_job[cons[k]] = 1;
+}
+// warp per user: left fold over the user's queued jobs in queue order (pos_by_user), placed jobs only
+__global__ void __launch_bounds__(128) usage_delta_kernel(ConsArgs a, const int32_t* pos_by_user, const int32_t* seg_start,
+                                                          const int32_t* seg_end, const uint8_t* placed_job,
+                                                          double* delta /* [n_users][4] */) {
+  const int u = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (u >= a.n_users) return;
+  const int s = seg_start[u], e = seg_end[u];
+  double dn = 0.0, dc = 0.0, dm = 0.0, dg = 0.0;
+  for (int base = s; base < e; base += 32) {
+    const int p = base + lane;
+    double xn = 0.0, xc = 0.0, xm = 0.0, xg = 0.0;
+    if (p < e) {
+      const int j = a.ranked[pos_by_user[p]];
+      if (placed_job[j]) { xn = 1.0; xc = a.jb.cpus[j]; xm = a.jb.mem[j]; xg = a.jb.gpus ? a.jb.gpus[j] : 0.0; }
+    }
+    const unsigned any = __ballot_sync(0xffffffffu, xn != 0.0);
+    for (unsigned m = any; m; m &= m - 1) {   // only the placed ones add (x + 0.0 == x anyway)
+      const int l = __ffs(m) - 1;
+      dn = dn + __shfl_sync(0xffffffffu, xn, l);
+      dc = dc + __shfl_sync(0xffffffffu, xc, l);
+      dm = dm + __shfl_sync(0xffffffffu, xm, l);
+      dg = dg + __shfl_sync(0xffffffffu, xg, l);
+    }
+  }
+  if (lane == 0) { delta[4 * u] = dn; delta[4 * u + 1] = dc; delta[4 * u + 2] = dm; delta[4 * u + 3] = dg; }
+}
+
 __global__ void count_flags_kernel(const int32_t* flags, int n, int32_t* out) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   int v = (i < n && flags[i]) ? 1 : 0;
@@ -2128,6 +2162,8 @@ struct MatchPlan {
   // scratch
   int32_t *d_perm = nullptr, *d_pos = nullptr, *d_tmp = nullptr, *d_seg_s = nullptr, *d_seg_e = nullptr;
   uint8_t* d_keep = nullptr;
+  uint8_t* d_placed = nullptr;
+  int last_n_cons = 0;
   double *d_oc = nullptr, *d_om = nullptr, *d_orc = nullptr, *d_orm = nullptr;
   VmStatic* d_vs = nullptr;
   double* d_kg = nullptr;
@@ -2217,7 +2253,7 @@ static int32_t build_plan(cook_pool* pool, MatchPlan* mp, const int32_t* ranked_
   sz.add<int32_t>(n_ranked);
   for (int k = 0; k < 3; k++) sz.add<double>(J + 1);
   sz.add<int32_t>(J + 1); sz.add<int32_t>(J + 1);
-  sz.add<uint8_t>(J + 1); sz.add<uint8_t>(J + 1);
+  sz.add<uint8_t>(J + 1); sz.add<uint8_t>(J + 1); sz.add<uint8_t>(J + 1);
   size_t csr_j = (jobs->novel_off ? jobs->novel_off[J] : 0) + 2 * (size_t)(jobs->attr_off ? jobs->attr_off[J] : 0) + n_memb;
   sz.add<int32_t>(4 * (size_t)(J + 2) + csr_j + 64);
   sz.add<double>(J + 1); sz.add<int32_t>(3 * (size_t)(J + 1)); sz.add<int64_t>(J + 1);
@@ -2355,6 +2391,7 @@ static int32_t build_plan(cook_pool* pool, MatchPlan* mp, const int32_t* ranked_
   mp->d_seg_s = ar.take<int32_t>(U + 1);
   mp->d_seg_e = ar.take<int32_t>(U + 1);
   mp->d_keep = ar.take<uint8_t>(n_ranked + 1);
+  mp->d_placed = ar.take<uint8_t>(J + 1);
   mp->d_cons = ar.take<int32_t>(NC + 1);
   mp->d_kc = ar.take<double>(NC + 1);
   mp->d_km = ar.take<double>(NC + 1);
@@ -2397,14 +2434,14 @@ static int32_t build_plan(cook_pool* pool, MatchPlan* mp, const int32_t* ranked_
   ma.host_lifetime_mins = params->host_lifetime_mins;
   ma.published = reinterpret_cast<unsigned*>(mp->d_counters + 8); ma.stats = mp->d_stats;
   ma.dead_blk = mp->d_counters + 9; ma.dead_k0 = mp->d_counters + 10;
-  ma.lookahead = 24;
+  ma.lookahead = 31;   // measured on C2: 12 -> 28.6 ms, 24 -> 18.7 ms, 31 -> 18.2 ms (the results' way back is long)
   ma.poll_ns = 200;
   ma.max_spec_warp = RES_THREADS / 32;
   ma.spec_kmin = 12;
   if (const char* ek = getenv("COOK_KMIN")) ma.spec_kmin = atoi(ek);
   if (const char* ew = getenv("COOK_MAX_SPEC_WARP")) ma.max_spec_warp = atoi(ew);
   if (const char* ep = getenv("COOK_POLL_NS")) ma.poll_ns = atoi(ep);
-  if (const char* el = getenv("COOK_LOOKAHEAD")) { int v = atoi(el); if (v >= 2 && v <= RING) ma.lookahead = v; }
+  if (const char* el = getenv("COOK_LOOKAHEAD")) { int v = atoi(el); if (v >= 2 && v <= RING - 1) ma.lookahead = v; }
   mp->J = J; mp->O = O; mp->U = U; mp->n_ranked = n_ranked; mp->NC = NC; mp->max_ports = max_ports;
   mp->G = G; mp->B = B; mp->constr = constr_eff; mp->n_memb = n_memb;
   mp->valid = true;
@@ -2522,7 +2559,23 @@ static int32_t run_plan(cook_pool* pool, MatchPlan* mp, int32_t* out_considerabl
       if (ma.vs_in_smem) smem = std::max(smem, ev_base + (size_t)O * 32);
       void* kfn = mp->constr ? (prof_on ? (void*)match_kernel<true, true> : (void*)match_kernel<true, false>)
                              : (prof_on ? (void*)match_kernel<false, true> : (void*)match_kernel<false, false>);
-      CK(pool, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      {
+        // The attribute belongs to the function on the device, not to this handle, and handles of
+        // one GPU may run concurrently: raise it monotonically under a process-wide lock so that
+        // a pool with a smaller offer table never lowers it under another pool's launch.
+        static std::mutex mu;
+        static int cur[16][4] = {};
+        std::lock_guard<std::mutex> lk(mu);
+        const int vi = (mp->constr ? 2 : 0) + (prof_on ? 1 : 0), di = pool->device & 15;
+        if ((int)smem > cur[di][vi]) {
+          int optin = 0;
+          CK(pool, cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, pool->device));
+          const int want = std::max((int)smem, optin);
+          CK(pool, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, std::min(want, optin)));
+          cur[di][vi] = std::min(want, optin);
+        }
+        if ((int)smem > cur[di][vi]) return set_err(pool, COOK_E_CUDA, "cook_match: shared memory request exceeds the device limit");
+      }
       int grid = pool->sm_count;
       if (max_ctas > 0) grid = std::min(grid, max_ctas);  // pools sharing one GPU
       int occ = 0;
@@ -2569,6 +2622,16 @@ static int32_t run_plan(cook_pool* pool, MatchPlan* mp, int32_t* out_considerabl
                           "c_end_block", "c_fallback", "res_total", "res_q1_done", "eval_work", "eval_wait",
                           "eval_loop", "eval_sync", "eval_merge", "eval_work_q1", "eval_rowslots_q1", "blocks", "z_takes", "relooks"};
     for (int i = 0; i < 26; i++) fprintf(stderr, "[cook_prof] %-14s %llu\n", nm[i], hstats[i]);
+  }
+  mp->last_n_cons = n_cons;
+  {
+    cook_phase_stats& ps = pool->phase[COOK_PHASE_MATCH];
+    ps.ms_h2d = uploaded ? ev_ms(pool->ev[0], pool->ev[1]) : 0.0;
+    ps.ms_device = ev_ms(pool->ev[1], pool->ev[3]);
+    ps.ms_d2h = ev_ms(pool->ev[3], pool->ev[4]);
+    ps.h2d_bytes = uploaded ? mp->h2d_bytes : 0;
+    ps.d2h_bytes = (int64_t)n_cons * (8 + (out_fail_reason ? 1 : 0) + (out_ports ? 4 * (int64_t)max_ports : 0)) + 44;
+    ps.n_launches = launches;
   }
   if (out_stats) {
     out_stats->n_considerable = n_cons;
@@ -2633,4 +2696,56 @@ extern "C" int32_t cook_match(cook_pool* pool, const int32_t* ranked_idx, int32_
   }
   return run_plan(pool, mp, out_considerable, out_assign, out_ports, out_fail_reason, out_stats, !reuse,
                   params->max_ctas);
+}
+
+
+// §8e: usage delta of this handle's last match round (device) -> one all-gather -> host.
+extern "C" int32_t cook_exchange_usage(cook_pool* pool, void* comm, int32_t world, int32_t n_pad,
+                                       double* out_all) {
+  if (!pool || !out_all || world <= 0 || n_pad <= 0) return set_err(pool, COOK_E_BADARG, "cook_exchange_usage: bad argument");
+  CK(pool, cudaSetDevice(pool->device));
+  cudaStream_t st = pool->stream;
+  MatchPlan* mp = static_cast<MatchPlan*>(pool->match_plan);
+  const bool have = mp && mp->valid;
+  if (have && 4 * mp->U > n_pad) return set_err(pool, COOK_E_BADARG, "cook_exchange_usage: n_pad < 4 * n_users");
+  const size_t need = (size_t)(world + 1) * n_pad;
+  if (need > pool->xchg_cap) {
+    if (pool->xchg) cudaFree(pool->xchg);
+    pool->xchg = nullptr; pool->xchg_cap = 0;
+    CK(pool, cudaMalloc(&pool->xchg, need * sizeof(double)));
+    pool->xchg_cap = need;
+  }
+  double* d_local = pool->xchg;
+  double* d_all = pool->xchg + n_pad;
+  int launches = 0;
+  CK(pool, cudaEventRecord(pool->ev[16], st));
+  CK(pool, cudaMemsetAsync(d_local, 0, sizeof(double) * n_pad, st));
+  if (have && mp->last_n_cons > 0) {
+    const int TB = 256, nc = mp->last_n_cons;
+    CK(pool, cudaMemsetAsync(mp->d_placed, 0, mp->J + 1, st));
+    placed_flag_kernel<<<(nc + TB - 1) / TB, TB, 0, st>>>(mp->d_cons, mp->d_out_assign, nc, mp->d_placed);
+    usage_delta_kernel<<<(mp->U + 3) / 4, 128, 0, st>>>(mp->ca, mp->d_pos, mp->d_seg_s, mp->d_seg_e, mp->d_placed, d_local);
+    launches += 2;
+    CK(pool, cudaGetLastError());
+  }
+  if (world > 1 && comm) {
+    int32_t rc = cook_allgather_usage(comm, st, d_local, d_all, n_pad);
+    if (rc != COOK_OK) return set_err(pool, rc, "cook_exchange_usage: ncclAllGather failed");
+    launches += 1;
+  } else {
+    d_all = d_local;
+    if (world != 1) return set_err(pool, COOK_E_BADARG, "cook_exchange_usage: world > 1 needs a communicator");
+  }
+  CK(pool, cudaEventRecord(pool->ev[17], st));
+  CK(pool, cudaMemcpyAsync(out_all, d_all, sizeof(double) * (size_t)world * n_pad, cudaMemcpyDeviceToHost, st));
+  CK(pool, cudaEventRecord(pool->ev[18], st));
+  CK(pool, cudaStreamSynchronize(st));
+  cook_phase_stats& ps = pool->phase[COOK_PHASE_EXCHANGE];
+  ps.ms_h2d = 0.0;
+  ps.ms_device = ev_ms(pool->ev[16], pool->ev[17]);
+  ps.ms_d2h = ev_ms(pool->ev[17], pool->ev[18]);
+  ps.h2d_bytes = 0;
+  ps.d2h_bytes = (int64_t)sizeof(double) * world * n_pad;
+  ps.n_launches = launches;
+  return COOK_OK;
 }

@@ -382,6 +382,7 @@ extern "C" int32_t cook_rank(cook_pool* pool, const cook_tasks_soa* running,
   CK(pool, ar.reserve(sz.off + 4096));
   ar.reset();
 
+  CK(pool, cudaEventRecord(pool->ev[8], st));
   TaskCols t;
   int32_t *d_user, *d_prio; int64_t *d_start, *d_tid, *d_jid; double *d_cpus, *d_mem, *d_gpus;
   CK(pool, upload2(ar, st, running->user, R, pending->user, J, &d_user));
@@ -424,6 +425,7 @@ extern "C" int32_t cook_rank(cook_pool* pool, const cook_tasks_soa* running,
   CK(pool, cudaMemsetAsync(d_seg_end, 0, sizeof(int32_t) * U, st));
   CK(pool, cudaMemsetAsync(d_counters, 0, sizeof(int32_t) * 8, st));
 
+  CK(pool, cudaEventRecord(pool->ev[9], st));
   const int TB = 256, nb = (N + TB - 1) / TB;
   iota_kernel<<<nb, TB, 0, st>>>(d_idx, N);
   CK(pool, csort::sort_indices(d_idx, d_tmp, N, LessUserTask{t, d_name_rank}, st));
@@ -463,6 +465,7 @@ extern "C" int32_t cook_rank(cook_pool* pool, const cook_tasks_soa* running,
   qf_scatter_kernel<<<qnb, QF_TB, 0, st>>>(qa);
   if (out_dru) scatter_dru_kernel<<<nb, TB, 0, st>>>(d_idx, d_dru_at, N, d_dru_task);
   CK(pool, cudaGetLastError());
+  CK(pool, cudaEventRecord(pool->ev[10], st));
   int32_t h_counters[2] = {0, 0};
   CK(pool, cudaMemcpyAsync(h_counters, d_counters, sizeof(int32_t) * 2, cudaMemcpyDeviceToHost, st));
   CK(pool, cudaStreamSynchronize(st));
@@ -474,7 +477,19 @@ extern "C" int32_t cook_rank(cook_pool* pool, const cook_tasks_soa* running,
     CK(pool, cudaMemcpyAsync(out_order, d_out_order, sizeof(int32_t) * n_kept,
                              cudaMemcpyDeviceToHost, st));
   if (out_dru) CK(pool, cudaMemcpyAsync(out_dru, d_dru_task, sizeof(double) * N, cudaMemcpyDeviceToHost, st));
+  CK(pool, cudaEventRecord(pool->ev[11], st));
   CK(pool, cudaStreamSynchronize(st));
+  {
+    cook_phase_stats& ps = pool->phase[COOK_PHASE_RANK];
+    ps.ms_h2d = ev_ms(pool->ev[8], pool->ev[9]);
+    ps.ms_device = ev_ms(pool->ev[9], pool->ev[10]);
+    ps.ms_d2h = ev_ms(pool->ev[10], pool->ev[11]);
+    ps.h2d_bytes = (int64_t)N * 56 + (int64_t)U * (4 + 7 * 8);   // task columns (56 B per task) + user tables
+    ps.d2h_bytes = (int64_t)n_out * 4 + (out_order ? (int64_t)n_kept * 4 : 0) + (out_dru ? (int64_t)N * 8 : 0) + 8;
+    int nl = 0;
+    for (long long w = csort::TILE; w < N; w <<= 1) nl += 2;   // the two sorts' merge passes
+    ps.n_launches = nl + 12;
+  }
   *out_n = n_out;
   if (out_order_n) *out_order_n = n_kept;
   return COOK_OK;

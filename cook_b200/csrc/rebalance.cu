@@ -593,6 +593,7 @@ extern "C" int32_t cook_rebalance(cook_pool* pool, const cook_running_soa* runni
   CK(pool, ar.reserve(sz.off + (1 << 16)));
   ar.reset();
 
+  CK(pool, cudaEventRecord(pool->ev[12], st));
   RTasks t;
   t.user = ar.take<int32_t>(CAP); t.prio = ar.take<int32_t>(CAP); t.start = ar.take<int64_t>(CAP);
   t.tid = ar.take<int64_t>(CAP); t.jid = ar.take<int64_t>(CAP); t.cpus = ar.take<double>(CAP);
@@ -684,6 +685,7 @@ extern "C" int32_t cook_rebalance(cook_pool* pool, const cook_running_soa* runni
   int32_t h_cnt[8] = {R, 0, 0, 0, 0, 0, 0, 0};
   CK(pool, cudaMemcpyAsync(d_cnt, h_cnt, sizeof(h_cnt), cudaMemcpyHostToDevice, st));
 
+  CK(pool, cudaEventRecord(pool->ev[13], st));
   const int TB = 256;
   // ---- init-state: user order + DRU of every user, tasks grouped by host
   CK(pool, cudaMemsetAsync(d_us, 0, sizeof(int32_t) * (U + 1), st));
@@ -733,11 +735,23 @@ extern "C" int32_t cook_rebalance(cook_pool* pool, const cook_running_soa* runni
     }
     n_tasks = h_cnt[0];
   }
+  CK(pool, cudaEventRecord(pool->ev[14], st));
   if (n_dec > 0) {
     CK(pool, cudaMemcpyAsync(out_decisions, d_dec, sizeof(cook_decision) * n_dec, cudaMemcpyDeviceToHost, st));
     if (h_cnt[2] > 0)
       CK(pool, cudaMemcpyAsync(out_victims, d_vict, sizeof(int32_t) * h_cnt[2], cudaMemcpyDeviceToHost, st));
     CK(pool, cudaStreamSynchronize(st));
+  }
+  CK(pool, cudaEventRecord(pool->ev[15], st));
+  CK(pool, cudaStreamSynchronize(st));
+  {
+    cook_phase_stats& ps = pool->phase[COOK_PHASE_REBALANCE];
+    ps.ms_h2d = ev_ms(pool->ev[12], pool->ev[13]);
+    ps.ms_device = ev_ms(pool->ev[13], pool->ev[14]);
+    ps.ms_d2h = ev_ms(pool->ev[14], pool->ev[15]);
+    ps.h2d_bytes = (int64_t)R * 60 + (int64_t)P * 48 + (int64_t)H * 48 + (int64_t)U * 60;
+    ps.d2h_bytes = (int64_t)n_dec * (int64_t)sizeof(cook_decision) + (int64_t)h_cnt[2] * 4;
+    ps.n_launches = 0;
   }
   *out_n = n_dec;
   return COOK_OK;

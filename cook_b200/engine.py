@@ -59,7 +59,8 @@ def load_library(path=None):
     lib.cook_gpu_version.restype = C.c_char_p
     for name in ("cook_gpu_init", "cook_gpu_shutdown", "cook_pool_open", "cook_pool_close",
                  "cook_last_error", "cook_rank", "cook_match", "cook_rebalance",
-                 "cook_allgather_usage"):
+                 "cook_allgather_usage", "cook_last_stats", "cook_comm_unique_id", "cook_comm_init",
+                 "cook_comm_destroy", "cook_exchange_usage"):
         getattr(lib, name).restype = C.c_int32
     return lib
 
@@ -154,6 +155,42 @@ class GpuEngine:
         if rc != 0:
             self._err(rc)
         return decisions_to_list(dec, vict, n.value)
+
+
+    # -- phase timing / §8e exchange ----------------------------------------
+    def last_stats(self, phase):
+        ps = abi.PhaseStats()
+        rc = self.lib.cook_last_stats(self.pool, int(phase), C.byref(ps))
+        if rc != 0:
+            self._err(rc)
+        return ps.as_dict()
+
+    def exchange_usage(self, n_users_pad, comm=None, world=1):
+        """Per-user usage delta of the last match round on this handle, computed on the device and
+        all-gathered over `comm` (a cook_comm_init handle).  Returns [world, n_users_pad, 4]."""
+        n_pad = 4 * int(n_users_pad)
+        out = np.zeros(world * n_pad, np.float64)
+        rc = self.lib.cook_exchange_usage(self.pool, comm, int(world), n_pad, abi.ptr(out, abi.P_F64))
+        if rc != 0:
+            self._err(rc)
+        return out.reshape(world, n_users_pad, 4)
+
+
+def comm_unique_id(lib):
+    buf = (C.c_uint8 * 128)()
+    rc = lib.cook_comm_unique_id(buf)
+    if rc != 0:
+        raise CookError(rc, "cook_comm_unique_id (is libnccl loadable?)")
+    return bytes(buf)
+
+
+def comm_init(lib, uid, rank, world, device):
+    comm = C.c_void_p()
+    buf = (C.c_uint8 * 128).from_buffer_copy(uid)
+    rc = lib.cook_comm_init(buf, int(rank), int(world), int(device), C.byref(comm))
+    if rc != 0:
+        raise CookError(rc, "cook_comm_init")
+    return comm
 
 
 def decisions_to_list(dec, vict, n):

@@ -296,3 +296,197 @@ def gen_rebalance(seed, n_running, n_pending, n_hosts, n_users, *, max_preemptio
     return dict(running=running, pending=abi.JobsSoA(**jkw), pending_job_id=pend["job_id"],
                 pending_priority=pend["priority"], hosts=abi.HostTable(**hkw), users=users, groups=groups,
                 params=abi.RebalanceParams(max_preemption, min_dru_diff, safe_dru_threshold, 0))
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE configs #3-#5 at their stated sizes (SURVEY §8d table).  A config is a list of
+# independent pools (Cook's shard axis, scheduler.clj:2488-2517); every pool carries its own
+# rank + match (+ rebalance) inputs.  Pool sizes follow the 40/30/20/10 % split (C3/C4) and a
+# Zipf split over 16 pools (C5); nodes split in the same proportion.
+C3_SPLIT = (0.4, 0.3, 0.2, 0.1)
+
+
+def pool_sizes(config):
+    """[(jobs, offers, users, running)] per pool for 'c3' / 'c4' / 'c5'."""
+    if config in ("c3", "c4"):
+        run = 200_000 if config == "c3" else 400_000
+        return [(int(1_000_000 * f), int(20_000 * f), int(5_000 * f), int(run * f)) for f in C3_SPLIT]
+    if config == "c5":
+        w = 1.0 / np.arange(1, 17) ** 0.5
+        w /= w.sum()
+        jobs = np.floor(10_000_000 * w / 1000).astype(int) * 1000
+        jobs[0] += 10_000_000 - jobs.sum()
+        return [(int(j), max(500, int(round(100_000 * j / 1e7))), max(100, int(round(20_000 * j / 1e7))),
+                 int(round(2_000_000 * j / 1e7))) for j in jobs]
+    raise ValueError(config)
+
+
+def gen_config_pool(config, p, scale=1.0):
+    """Pool p of BASELINE config 'c3' | 'c4' | 'c5' (scale < 1 shrinks every dimension: the
+    CPU-runnable miniature of the same shape).  Returns the gen_c3_pool() dict plus 'quota'
+    tables that bind for ~10 % of the users and, for c4/c5, a 'rebalance'
+    entry (gen_rebalance dict sized to the pool)."""
+    nj, no, nu, nr = pool_sizes(config)[p]
+    nj, no, nu, nr = (max(8, int(nj * scale)), max(4, int(no * scale)), max(2, int(nu * scale)),
+                      max(1, int(nr * scale)))
+    seed = {"c3": 3000, "c4": 4000, "c5": 5000}[config] + 17 * p
+    t = gen_pool(seed, nj, no, nu, nr)
+    add_constraints_fast(t, seed + 1)
+    rng = np.random.Generator(np.random.PCG64(seed + 2))
+    # 10 % of the users carry count / cpu quotas that bind
+    bind = rng.random(nu) < 0.10
+    quota = {"count": np.where(bind, rng.integers(20, 400, nu), 1e12).astype(float),
+             "cpus": np.where(bind, rng.integers(50, 2000, nu), 1e12).astype(float)}
+    usage = {k: t["users"].col("usage_" + k) for k in ("count", "cpus", "mem", "gpus")}
+    t["users"] = abi.make_users(nu, name_rank=t["users"].col("name_rank"), div_mem=t["users"].col("div_mem"),
+                                div_cpus=t["users"].col("div_cpus"), div_gpus=np.full(nu, 1.0),
+                                quota=quota, usage=usage)
+    if config in ("c4", "c5"):
+        t["rebalance"] = gen_rebalance(seed + 3, nr, max(8, int(400 * (nj / 250_000))), no, nu,
+                                       max_preemption=128, min_dru_diff=0.5, safe_dru_threshold=1.0)
+    t["config"] = config
+    t["pool"] = p
+    return t
+
+
+def add_constraints_fast(t, seed, *, n_attr_cols=8, attr_card=(3, 6, 24, 2, 2, 4, 5, 7), frac_attr=0.30,
+                         frac_gpu_nodes=0.05, frac_gpu_jobs=0.02, frac_port_jobs=0.03,
+                         frac_port_nodes=0.25, frac_group_jobs=0.05, group_size=(4, 24),
+                         frac_novel=0.10, max_tasks=110, frac_k8s=0.75, frac_reserved=0.01,
+                         frac_est=0.05, frac_ckpt=0.02, frac_disk=0.05, n_models=2, n_locations=3,
+                         host_lifetime_mins=1440, n_running_cotasks=3):
+    """Vectorised twin of add_constraints() (same column semantics and fractions, different random
+    stream) for the million-job pools: no per-job Python loop."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    jobs, offers = t["jobs"], t["offers"]
+    J, O = jobs.n, offers.n
+    card = np.array([attr_card[c % len(attr_card)] for c in range(n_attr_cols)])
+    # ---- offers
+    is_k8s = (rng.random(O) < frac_k8s).astype(np.uint8)
+    attr = (rng.integers(0, 1 << 30, (n_attr_cols, O)) % card[:, None] + 1).astype(np.int32)
+    attr[rng.random((n_attr_cols, O)) < 0.05] = 0
+
+    def csr_one(mask, vals, dtype=np.int32):   # <= 1 entry per row
+        off = np.zeros(len(mask) + 1, np.int32)
+        off[1:] = np.cumsum(mask)
+        return off, np.ascontiguousarray(vals[mask], dtype)
+
+    gpu_node = (rng.random(O) < frac_gpu_nodes) & (is_k8s == 1)
+    gpu_off, gpu_model = csr_one(gpu_node, rng.integers(0, n_models, O))
+    _, gpu_count = csr_one(gpu_node, rng.choice(np.array([1.0, 2.0, 4.0, 8.0]), O), np.float64)
+    port_node = (rng.random(O) < frac_port_nodes) & (is_k8s == 0)
+    port_off = np.zeros(O + 1, np.int32)
+    port_off[1:] = np.cumsum(2 * port_node)
+    npn = int(port_node.sum())
+    port_begin = np.tile(np.array([31000, 31500], np.int32), npn)
+    port_end = np.tile(np.array([31009, 31504], np.int32), npn)
+    k8 = is_k8s == 1
+    disk_off = np.zeros(O + 1, np.int32)
+    disk_off[1:] = np.cumsum(2 * k8)
+    nk = int(k8.sum())
+    disk_type = np.tile(np.array([0, 1], np.int32), nk)
+    disk_space = np.stack([rng.integers(10, 200, nk) * 1024.0, rng.integers(0, 50, nk) * 1024.0], 1).reshape(-1)
+    num_tasks = rng.integers(0, max_tasks + 5, O).astype(np.int32)
+    max_t = np.where(rng.random(O) < 0.9, max_tasks, -1).astype(np.int32)
+    location = rng.integers(0, n_locations, O).astype(np.int32)
+    host_start = np.where(rng.random(O) < 0.7, 1_600_000_000 + rng.integers(0, 86400, O), -1).astype(np.int64)
+    reserved = (rng.random(O) < frac_reserved).astype(np.uint8)
+    hostname_id = offers.col("hostname_id")
+    cols = {n: offers.col(n) for n in ("hostname_id", "name_rank", "cpus", "mem", "run_cpus", "run_mem", "run_count")}
+    t["offers"] = abi.OffersSoA(n=O, **cols, port_off=port_off, port_begin=port_begin, port_end=port_end,
+                                is_k8s=is_k8s, location=location, gpu_off=gpu_off, gpu_model=gpu_model,
+                                gpu_count=gpu_count, disk_off=disk_off, disk_type=disk_type,
+                                disk_space=disk_space, max_tasks=max_t, num_tasks=num_tasks,
+                                host_start_time=host_start, n_attr_cols=n_attr_cols,
+                                attr=attr.reshape(-1), reserved=reserved)
+    # ---- jobs
+    gpus = np.where(rng.random(J) < frac_gpu_jobs, rng.choice(np.array([1.0, 2.0, 4.0, 8.0]), J), 0.0)
+    gmodel = np.where(gpus > 0, rng.integers(0, n_models, J), -1).astype(np.int32)
+    ports = np.where(rng.random(J) < frac_port_jobs, rng.integers(1, 3, J), 0).astype(np.int32)
+    # user-defined EQUALS: 0, 1 or 2 (distinct columns) per job
+    na = np.where(rng.random(J) < frac_attr, rng.integers(1, 3, J), 0).astype(np.int32)
+    attr_off = np.zeros(J + 1, np.int32)
+    attr_off[1:] = np.cumsum(na)
+    owner = np.repeat(np.arange(J), na)
+    first = np.concatenate([[True], owner[1:] != owner[:-1]]) if len(owner) else np.zeros(0, bool)
+    c1 = rng.integers(0, n_attr_cols, len(owner))
+    c2 = (c1 + rng.integers(1, n_attr_cols, len(owner))) % n_attr_cols     # differs from the first column
+    prev = np.roll(c1, 1)
+    attr_col = np.where(first, c1, np.where(c2 == prev, (c2 + 1) % n_attr_cols, c2)).astype(np.int32)
+    attr_col = np.where(~first & (attr_col == prev), (attr_col + 1) % n_attr_cols, attr_col).astype(np.int32)
+    attr_val = (rng.integers(0, 1 << 30, len(owner)) % card[attr_col] + 1).astype(np.int32)
+    attr_val[rng.random(len(owner)) >= 0.97] = -1
+    # novel-host: 1..3 distinct previous hosts for 10 % of the jobs
+    nn = np.where(rng.random(J) < frac_novel, rng.integers(1, 4, J), 0).astype(np.int32)
+    nn = np.minimum(nn, O)
+    novel_off = np.zeros(J + 1, np.int32)
+    novel_off[1:] = np.cumsum(nn)
+    ownn = np.repeat(np.arange(J), nn)
+    pos = np.arange(len(ownn)) - novel_off[ownn]               # 0..2 within the job
+    base = rng.integers(0, O, J)
+    step = rng.integers(1, max(2, O // 3), J)
+    novel_host = hostname_id[(base[ownn] + pos * step[ownn]) % O].astype(np.int32) if len(ownn) else np.zeros(0, np.int32)
+    if O < 8:   # tiny tables: fall back to exact de-duplication
+        keep = np.ones(len(ownn), bool)
+        for j in np.unique(ownn):
+            idx = np.where(ownn == j)[0]
+            _, f = np.unique(novel_host[idx], return_index=True)
+            keep[idx] = False
+            keep[idx[f]] = True
+        novel_host = novel_host[keep]
+        nn = np.bincount(ownn[keep], minlength=J).astype(np.int32)
+        novel_off[1:] = np.cumsum(nn)
+    now_ms = 1_600_050_000_000
+    est = np.where(rng.random(J) < frac_est, now_ms + rng.integers(1, 48 * 3600_000, J), -1).astype(np.int64)
+    ckpt = np.where(rng.random(J) < frac_ckpt, rng.integers(0, n_locations, J), -1).astype(np.int32)
+    res_hosts = hostname_id[reserved == 1]
+    reserved_host = np.full(J, -1, np.int32)
+    if len(res_hosts):
+        pick = rng.random(J) < 0.01
+        reserved_host[pick] = rng.choice(res_hosts, size=int(pick.sum()))
+    disk_req = np.where(rng.random(J) < frac_disk, rng.integers(1, 64, J) * 1024.0, -1.0)
+    disk_typ = rng.integers(0, 2, J).astype(np.int32)
+    # groups: consecutive runs of a random permutation, sizes in group_size
+    n_gj = int(J * frac_group_jobs)
+    members = rng.permutation(J)[:n_gj]
+    sizes = []
+    left = n_gj
+    while left > 0:
+        sz = min(left, int(rng.integers(group_size[0], group_size[1] + 1)))
+        sizes.append(sz)
+        left -= sz
+    G = len(sizes)
+    group_of = np.full(J, -1, np.int32)
+    if G:
+        group_of[members] = np.repeat(np.arange(G, dtype=np.int32), sizes)
+    has_g = group_of >= 0
+    group_off = np.zeros(J + 1, np.int32)
+    group_off[1:] = np.cumsum(has_g)
+    group_idx = group_of[has_g]
+    base_j = {n: jobs.col(n) for n in ("user", "cpus", "mem", "allowed", "plugin_accept")}
+    t["jobs"] = abi.JobsSoA(n=J, **base_j, gpus=gpus, ports=ports, novel_off=novel_off, novel_host=novel_host,
+                            gpu_model=gmodel, disk_request=disk_req, disk_type=disk_typ,
+                            attr_off=attr_off, attr_col=attr_col, attr_val=attr_val, est_end_ms=est,
+                            ckpt_location=ckpt, reserved_host=reserved_host,
+                            group_off=group_off, group_idx=group_idx)
+    t["host_lifetime_mins"] = host_lifetime_mins
+    if G == 0:
+        t["groups"] = None
+        return None
+    r = rng.random(G)
+    kinds = np.where(r < 0.6, abi.GROUP_UNIQUE, np.where(r < 0.85, abi.GROUP_BALANCED, abi.GROUP_ATTR_EQUALS)).astype(np.int32)
+    acols = rng.integers(0, min(3, n_attr_cols), G).astype(np.int32)
+    mins = rng.integers(1, 4, G).astype(np.int32)
+    ncot = np.minimum(rng.integers(0, n_running_cotasks + 1, G), O).astype(np.int32)
+    cot_off = np.zeros(G + 1, np.int32)
+    cot_off[1:] = np.cumsum(ncot)
+    owg = np.repeat(np.arange(G), ncot)
+    posg = np.arange(len(owg)) - cot_off[owg]
+    bg = rng.integers(0, O, G)
+    sg = rng.integers(1, max(2, O // 4), G)
+    cot_idx = (bg[owg] + posg * sg[owg]) % O if len(owg) else np.zeros(0, np.int64)
+    cot_host = hostname_id[cot_idx].astype(np.int32) if len(owg) else np.zeros(0, np.int32)
+    cot_attr = attr[acols[owg], cot_idx].astype(np.int32) if len(owg) else np.zeros(0, np.int32)
+    t["groups"] = abi.Groups(n_groups=G, kind=kinds, attr_col=acols, minimum=mins, cot_off=cot_off,
+                             cot_hostname_id=cot_host, cot_attr_val=cot_attr)
+    return t["groups"]

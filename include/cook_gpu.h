@@ -361,6 +361,21 @@ int32_t cook_rebalance(cook_pool* pool, const cook_running_soa* running,
                        cook_decision* out_decisions, int32_t* out_victims,
                        int32_t* out_n);
 
+/* ------------------------------------------------------------ phase timing */
+/* Device-side timing of the last call of each kind on this handle (CUDA events on the
+ * pool's stream): what bench.py's `phases` block and roofline lines are computed from. */
+enum { COOK_PHASE_RANK = 0, COOK_PHASE_MATCH = 1, COOK_PHASE_REBALANCE = 2, COOK_PHASE_EXCHANGE = 3 };
+typedef struct {
+  double ms_h2d;      /* upload stage                                              */
+  double ms_device;   /* kernels (for the exchange: delta kernels + the collective) */
+  double ms_d2h;      /* result download                                           */
+  int64_t h2d_bytes;
+  int64_t d2h_bytes;
+  int32_t n_launches;
+  int32_t reserved0;
+} cook_phase_stats;
+int32_t cook_last_stats(cook_pool* pool, int32_t phase, cook_phase_stats* out);
+
 /* ----------------------------------------------------------------- multi-GPU */
 /* §8e: after a pool's match round every rank contributes its pools' usage
  * deltas {count,cpus,mem,gpus} per user; one ncclAllGather over NVLink makes
@@ -370,6 +385,26 @@ int32_t cook_rebalance(cook_pool* pool, const cook_running_soa* running,
  * local/out are DEVICE pointers: local[n_doubles], out[world*n_doubles].    */
 int32_t cook_allgather_usage(void* nccl_comm, void* stream, const double* local_dev,
                              double* out_dev, int64_t n_doubles);
+
+/* Communicator plumbing for hosts without their own NCCL binding (the JVM): rank 0 calls
+ * cook_comm_unique_id, ships the 128 bytes to every rank over its own control plane (Cook:
+ * ZooKeeper / the leader's REST endpoint; bench.py: torch.distributed broadcast), every rank
+ * calls cook_comm_init (ncclCommInitRank on `device`).                                      */
+int32_t cook_comm_unique_id(uint8_t out_id[128]);
+int32_t cook_comm_init(const uint8_t id[128], int32_t rank, int32_t world, int32_t device,
+                       void** out_comm);
+int32_t cook_comm_destroy(void* comm);
+
+/* The exchange step as one call.  Computes, ON THE DEVICE, the per-user usage delta
+ * {count,cpus,mem,gpus} of the jobs the last cook_match on this handle placed (left fold per
+ * user in queue order: same association as generate-user-usage-map scheduler.clj:711-727
+ * would produce for those tasks), then all-gathers it over `comm` on the pool's stream and
+ * copies the result to the host:
+ *   out_all[world][n_pad]   n_pad >= 4 * n_users doubles per rank ([user][4], zero padded)
+ * A handle that has not matched yet contributes zeros.  world == 1 (or comm == NULL) skips
+ * the collective.  Every rank must call it the same number of times with the same n_pad.   */
+int32_t cook_exchange_usage(cook_pool* pool, void* comm, int32_t world, int32_t n_pad,
+                            double* out_all);
 
 #ifdef __cplusplus
 }
