@@ -105,9 +105,13 @@ def gen_c1(seed=1):
                     big_share_frac=0.0, used_fraction=False, zipf=None, prio_p=(0.0, 1.0, 0.0))
 
 
-def gen_c2(seed=2, n_jobs=100_000, n_offers=5_000, n_users=1_000, n_running=20_000):
-    """BASELINE config #2: 100k jobs x 5k offers, cpu+mem fit only, 1 pool."""
-    return gen_pool(seed, n_jobs, n_offers, n_users, n_running)
+def gen_c2(seed=2, n_jobs=100_000, n_offers=5_000, n_users=1_000, n_running=20_000, offer_scale=1):
+    """BASELINE config #2: 100k jobs x 5k offers, cpu+mem fit only, 1 pool.  offer_scale > 1 is the
+    NON-SATURATING variant bench.py reports beside it: the same jobs against offers with that many
+    times the capacity (6 => every job is placeable), which exposes the matcher's dependency-chain
+    bound instead of the cluster filling up after a quarter of the queue."""
+    types = tuple((c * offer_scale, m * offer_scale) for c, m in ((16, 65536), (32, 131072), (64, 262144), (96, 393216)))
+    return gen_pool(seed, n_jobs, n_offers, n_users, n_running, offer_types=types)
 
 
 def match_params(num_considerable, enforce_rate_limit=0, host_lifetime_mins=0, reuse_resident=0, max_ctas=0):

@@ -1,0 +1,184 @@
+"""-m gpu: BASELINE configs #3, #4, #5 at their STATED sizes through the CUDA path, bit-identical to
+the oracle (assignments, ports, considerable sets, rank order, preemption decisions and victims);
+the device-side usage exchange; pools of different size sharing one GPU; a repeated-cycle stress
+test of the matcher's lock-free pipeline."""
+import os
+import threading
+
+import numpy as np
+import pytest
+
+from cook_b200 import abi, sharding, traces
+
+pytestmark = pytest.mark.gpu
+
+
+def _same_dru(a, b):
+    return np.array_equal(np.nan_to_num(a, nan=-1.0), np.nan_to_num(b, nan=-1.0))
+
+
+def _cycle_parity(gpu, oracle, t, threads=0, rebalance=False):
+    rg = gpu.rank(t["running"], t["pending"], t["users"])
+    ro = oracle.rank(t["running"], t["pending"], t["users"])
+    assert np.array_equal(rg["ranked"], ro["ranked"])
+    assert _same_dru(rg["dru"], ro["dru"])
+    prm = traces.match_params(t["jobs"].n, host_lifetime_mins=t["host_lifetime_mins"])
+    mg = gpu.match(rg["ranked"], t["jobs"], t["offers"], t["users"], prm, groups=t["groups"], max_ports=2)
+    mo = oracle.match(ro["ranked"], t["jobs"], t["offers"], t["users"], prm, groups=t["groups"], max_ports=2,
+                      threads=threads or min(64, os.cpu_count() or 1))
+    assert np.array_equal(mg["considerable"], mo["considerable"])
+    assert np.array_equal(mg["assign"], mo["assign"])
+    assert np.array_equal(mg["ports"], mo["ports"])
+    assert mg["stats"]["n_matched"] == mo["stats"]["n_matched"] > 0
+    assert mg["stats"]["evals"] == mo["stats"]["evals"]
+    if rebalance:
+        r = t["rebalance"]
+        dg = gpu.rebalance(r["running"], r["pending"], r["pending_job_id"], r["pending_priority"], r["hosts"],
+                           r["users"], r["params"], groups=r["groups"])
+        do = oracle.rebalance(r["running"], r["pending"], r["pending_job_id"], r["pending_priority"], r["hosts"],
+                              r["users"], r["params"], groups=r["groups"])
+        assert len(dg) == len(do) > 0
+        for a, b in zip(dg, do):
+            assert (a["pending_idx"], a["host"], a["victims"]) == (b["pending_idx"], b["host"], b["victims"])
+            assert (a["dru"], a["mem"], a["cpus"], a["gpus"]) == (b["dru"], b["mem"], b["cpus"], b["gpus"])
+    return mg
+
+
+@pytest.mark.parametrize("p", [0, 1, 2, 3])
+def test_c3_full_size_pools(gpu, oracle, p):
+    """BASELINE config #3 at stated size: 1M jobs x 20k nodes in 4 pools (400k x 8k, 300k x 6k,
+    200k x 4k, 100k x 2k), every constraint kind, user quotas binding for ~10 % of the users."""
+    t = traces.gen_config_pool("c3", p)
+    assert (t["jobs"].n, t["offers"].n) == traces.pool_sizes("c3")[p][:2]
+    _cycle_parity(gpu, oracle, t)
+
+
+@pytest.mark.parametrize("p", [0, 3])
+def test_c4_full_size_pools_with_rebalancer(gpu, oracle, p):
+    """BASELINE config #4: config #3's pools with 400k running tasks in total (160k / 40k in these
+    two pools) + the rebalancer sweep, max-preemption 128: decisions and victims identical."""
+    t = traces.gen_config_pool("c4", p)
+    _cycle_parity(gpu, oracle, t, rebalance=True)
+
+
+def test_c5_one_full_size_pool(gpu, oracle):
+    """BASELINE config #5: one of the 16 pools at stated size (pool 5: ~614k jobs x ~6.1k nodes,
+    ~123k running tasks): rank + match + rebalance, bit-identical."""
+    sizes = traces.pool_sizes("c5")
+    assert sum(s[0] for s in sizes) == 10_000_000 and len(sizes) == 16
+    t = traces.gen_config_pool("c5", 5)
+    assert t["jobs"].n > 500_000
+    _cycle_parity(gpu, oracle, t, rebalance=True)
+
+
+def test_usage_exchange_device_delta(gpu, oracle):
+    """cook_exchange_usage (world 1): the per-user usage delta computed on the device equals the host
+    restatement (sharding.usage_delta) of generate-user-usage-map over the placed jobs."""
+    t = traces.gen_pool(71, 20000, 800, 150, 3000)
+    ranked = gpu.rank(t["running"], t["pending"], t["users"])["ranked"]
+    m = gpu.match(ranked, t["jobs"], t["offers"], t["users"], traces.match_params(20000))
+    got = gpu.exchange_usage(160)            # padded to 160 users
+    assert got.shape == (1, 160, 4)
+    j = t["jobs"]
+    want = sharding.usage_delta(m["considerable"], m["assign"], j.col("user"), j.col("cpus"), j.col("mem"),
+                                j.col("gpus"), 150)
+    assert np.array_equal(got[0, :150], want)
+    assert not got[0, 150:].any()
+    assert want[:, 0].sum() == m["stats"]["n_matched"]
+    s = gpu.last_stats(abi.PHASE_EXCHANGE)
+    assert s["n_launches"] == 2 and s["ms_device"] > 0.0
+
+
+def test_exchange_feeds_next_rank(gpu, oracle):
+    """The exchange's result is CONSUMED: two pools of one quota group; the usage gathered after pool
+    A's match round is pool B's group_usage in the next rank cycle, and decides how deep B's queue
+    survives the quota-group filter (scheduler.clj:2125-2157) - identical to the oracle fed with the
+    host-side delta."""
+    from cook_b200.engine import GpuEngine
+    ta = traces.gen_pool(81, 8000, 400, 60, 1000)
+    tb = traces.gen_pool(82, 6000, 300, 60, 800)
+    eb = GpuEngine(pool_name="group-b")
+    try:
+        ra = gpu.rank(ta["running"], ta["pending"], ta["users"])["ranked"]
+        ma = gpu.match(ra, ta["jobs"], ta["offers"], ta["users"], traces.match_params(8000))
+        g = gpu.exchange_usage(60)[0]                      # [60, 4]
+        tot = g.sum(axis=0)
+        j = ta["jobs"]
+        want = sharding.usage_delta(ma["considerable"], ma["assign"], j.col("user"), j.col("cpus"), j.col("mem"),
+                                    j.col("gpus"), 60).sum(axis=0)
+        assert np.array_equal(tot, want) and tot[0] > 0
+        gq = abi.make_pool_quota({"count": tot[0] + 500, "cpus": tot[1] + 1500, "mem": tot[2] + 6.0e6, "gpus": 1e9})
+        rb_g = eb.rank(tb["running"], tb["pending"], tb["users"], group_quota=gq, group_usage=tot)
+        rb_o = oracle.rank(tb["running"], tb["pending"], tb["users"], group_quota=gq, group_usage=want)
+        assert np.array_equal(rb_g["ranked"], rb_o["ranked"])
+        rb_0 = oracle.rank(tb["running"], tb["pending"], tb["users"], group_quota=gq, group_usage=np.zeros(4))
+        assert 0 < len(rb_g["ranked"]) < len(rb_0["ranked"])   # the gathered usage really cut the queue
+    finally:
+        eb.close()
+
+
+def test_pools_of_different_size_side_by_side(oracle):
+    """Handles of one GPU may run concurrently (cook_gpu.h): pools with DIFFERENT offer counts (hence
+    different dynamic shared-memory needs) matched from two host threads, many times, stay correct -
+    the kernel attribute is raised monotonically, never lowered under another pool's launch."""
+    from cook_b200.engine import GpuEngine
+    shapes = [(91, 6000, 300, 40, 500), (92, 9000, 2400, 60, 900)]
+    ts = [traces.gen_pool(*s) for s in shapes]
+    want = []
+    for t in ts:
+        r = oracle.rank(t["running"], t["pending"], t["users"])["ranked"]
+        want.append((r, oracle.match(r, t["jobs"], t["offers"], t["users"], traces.match_params(t["jobs"].n))["assign"]))
+    engs = [GpuEngine(pool_name=f"side-{i}") for i in range(2)]
+    errs = []
+
+    def work(i):
+        try:
+            for _ in range(12):
+                m = engs[i].match(want[i][0], ts[i]["jobs"], ts[i]["offers"], ts[i]["users"],
+                                  traces.match_params(ts[i]["jobs"].n, max_ctas=60))
+                if not np.array_equal(m["assign"], want[i][1]):
+                    errs.append((i, "assignments differ"))
+        except Exception as e:   # noqa: BLE001
+            errs.append((i, repr(e)))
+    th = [threading.Thread(target=work, args=(i,)) for i in range(2)]
+    for x in th:
+        x.start()
+    for x in th:
+        x.join()
+    for e in engs:
+        e.close()
+    assert not errs, errs
+
+
+def test_matcher_stress_repeated_cycles(oracle):
+    """A lock-free pipeline needs more than one green run: 200 C2-shaped cycles with the
+    pipeline's knobs varied (queue depth, candidates per result, spec CTAs, grid size), every one
+    bit-identical to the oracle."""
+    from cook_b200.engine import GpuEngine
+    t = traces.gen_c2(seed=5, n_jobs=30_000, n_offers=1_500, n_users=300, n_running=5_000)
+    ranked = oracle.rank(t["running"], t["pending"], t["users"])["ranked"]
+    want = oracle.match(ranked, t["jobs"], t["offers"], t["users"], traces.match_params(30_000))["assign"]
+    knobs = [{}, {"COOK_LOOKAHEAD": "8"}, {"COOK_LOOKAHEAD": "31"}, {"COOK_KMIN": "6"}, {"COOK_KMIN": "16"},
+             {"COOK_NSPEC": "1"}, {"COOK_NSPEC": "6"}, {"COOK_MATCH_B": "16", "COOK_MATCH_BMIN": "16"},
+             {"COOK_MATCH_TARGET": "8"}, {"COOK_POLL_NS": "20"}]
+    eng = GpuEngine(pool_name="stress")
+    saved = {k: os.environ.get(k) for kn in knobs for k in kn}
+    try:
+        n = 0
+        for rep in range(20):
+            for i, kn in enumerate(knobs):
+                for k in saved:
+                    os.environ.pop(k, None)
+                os.environ.update(kn)
+                ctas = [0, 0, 37, 9, 148, 3][(rep + i) % 6]
+                m = eng.match(ranked, t["jobs"], t["offers"], t["users"], traces.match_params(30_000, max_ctas=ctas))
+                assert np.array_equal(m["assign"], want), (rep, kn, ctas)
+                n += 1
+        assert n == 200
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+        eng.close()

@@ -84,6 +84,13 @@ def test_handle_offers_golden_oracle(oracle):
     assert handle_offers_golden_cases.check_all(oracle) == 2 * (13 + 1) + 2 * (13 + 6)
 
 
+@pytest.mark.gpu
+def test_handle_offers_golden_gpu(gpu):
+    """K15 in full through the CUDA path (the same 66 assertions)."""
+    import handle_offers_golden_cases
+    assert handle_offers_golden_cases.check_all(gpu) == 2 * (13 + 1) + 2 * (13 + 6)
+
+
 def test_rebalance_balanced_and_quota_golden_oracle(oracle):
     """K20, second half (test/cook/test/rebalancer.clj:673-811): balanced host-placement groups (one
     with a host already preempted in the cycle) and the over-quota rule (dru 100.0, own task)."""
