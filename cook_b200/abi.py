@@ -166,6 +166,16 @@ class Decision(C.Structure):
                 ("gpus", C.c_double)]
 
 
+class RebTrace(C.Structure):
+    """cook_reb_trace (include/cook_gpu.h): rebalancer state as the reference's own tests read it."""
+    _fields_ = [("n_forced", C.c_int32), ("forced", C.POINTER(Decision)),
+                ("forced_victims", P_I32), ("pending_dru", P_F64),
+                ("task_dru", P_F64), ("task_alive", P_U8), ("order", P_I32),
+                ("n_order", C.POINTER(C.c_int32)), ("has_spare", P_U8),
+                ("spare_mem", P_F64), ("spare_cpus", P_F64), ("spare_gpus", P_F64),
+                ("forced_only", C.c_int32), ("below_quota", P_U8)]
+
+
 class GpuConfig(C.Structure):
     _fields_ = [("n_devices", C.c_int32), ("device_ids", P_I32)]
 

@@ -2570,6 +2570,9 @@ static int32_t run_plan(cook_pool* pool, MatchPlan* mp, int32_t* out_considerabl
         if ((int)smem > cur[di][vi]) {
           int optin = 0;
           CK(pool, cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, pool->device));
+          cudaFuncAttributes fa;
+          CK(pool, cudaFuncGetAttributes(&fa, kfn));
+          optin -= (int)fa.sharedSizeBytes;   // the opt-in limit covers static + dynamic shared memory
           const int want = std::max((int)smem, optin);
           CK(pool, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, std::min(want, optin)));
           cur[di][vi] = std::min(want, optin);

@@ -11,18 +11,23 @@
 //        job id)                                  -> per-user order (tools.clj:614-641)
 //     S2 warp-per-user left fold                  -> cumulative sums + DRU (dru.clj:50-66)
 //     S3 tasks grouped by host (a task never changes host)
-//   per pending job:
-//     P1 warp fold over the job's user            -> job-below-quota, nearest dru
-//     P2 host kernel                              -> constraints per host (:358-377)
+//   per pending job, inside ONE persistent cooperative kernel (no host round trip):
+//     P1 32-ary search for the nearest task (+ the quota fold when a quota can bind)
+//                                                 -> job-below-quota, pending dru
+//     P2 constraints per host (:358-377)
 //     P3 warp per host: [spare ; eligible victims by desc dru] prefix sums by
 //        repeated warp selection of the next victim, best sufficient prefix (:380-403)
 //     P4 argmax over hosts (max dru, ties -> greatest hostname = `max-key` last wins)
-//     P5 apply: next-state -- victims die in place (a dead task adds 0.0 to every
+//     P5 next-state -- victims die in place (a dead task adds 0.0 to every
 //        fold), the job's task is inserted into its user's order, and only the
 //        users that changed are re-folded, from the first position that changed
 //        (dru.clj:128-144 next-task->scored-task).
 //
 // GPU DRU mode is rejected: the reference itself throws there (see oracle).
+#include <cooperative_groups.h>
+
+#include <algorithm>
+
 #include "common.cuh"
 #include "sort.cuh"
 
@@ -72,7 +77,7 @@ __global__ void user_seg_kernel(const int32_t* ord, RTasks t, int n, int32_t* se
   if (p == n - 1 || t.user[ord[p + 1]] != u) seg_end[u] = p + 1;
 }
 
-// Users to re-fold after a decision, written by apply_kernel.
+// Users to re-fold after a decision, written by the kernel's next-state step.
 struct Refold {
   int32_t n;
   int32_t q_ins;       // where the new task went into the user order
@@ -156,54 +161,6 @@ struct PendScalars {  // per pending job, device resident
   double pending_dru;
 };
 
-// P1: job-below-quota (:210-220) and pending dru (:182-208) for pending job p.
-__global__ void pending_kernel(const int32_t* ord, RTasks t, PendCols pc, int p, const int32_t* seg_start,
-                               const int32_t* seg_end, const double* q_count, const double* q_cpus,
-                               const double* q_mem, const double* q_gpus, const double* div_mem,
-                               const double* div_cpus, PendScalars* out) {
-  const int lane = threadIdx.x;
-  const int u = pc.user[p];
-  const int s = seg_start[u], e = seg_end[u];
-  const double pm = pc.mem[p], pcpu = pc.cpus[p], pg = pc.gpus ? pc.gpus[p] : 0.0;
-  double an = 1.0, ac = pcpu, am = pm, ag = pg;  // (conj running-jobs p): p first
-  double nearest = 0.0;
-  const int pprio = -pc.prio[p];
-  const long long pj = pc.jid[p];
-  for (int base = s; base < e; base += 32) {
-    int q = base + lane;
-    int i = q < e ? ord[q] : -1;
-    if (i >= 0 && !t.alive[i]) i = -1;   // preempted earlier in this cycle: adds 0.0, is no neighbour
-    double xc = i >= 0 ? t.cpus[i] : 0.0, xm = i >= 0 ? t.mem[i] : 0.0, xg = i >= 0 ? t.gpus[i] : 0.0;
-    double xn = i >= 0 ? 1.0 : 0.0;
-    int cntn = min(32, e - base);
-    for (int l = 0; l < cntn; l++) {
-      an = an + __shfl_sync(0xffffffffu, xn, l);
-      ac = ac + __shfl_sync(0xffffffffu, xc, l);
-      am = am + __shfl_sync(0xffffffffu, xm, l);
-      ag = ag + __shfl_sync(0xffffffffu, xg, l);
-    }
-    // task <= synthetic pending task [-prio, Long/MAX, nil(-1), job id] ?
-    bool le = false;
-    if (i >= 0) {
-      int tp = -t.prio[i];
-      if (tp != pprio) le = tp < pprio;
-      else if (t.start[i] != 0x7fffffffffffffffLL) le = true;
-      else if (t.tid[i] != -1) le = false;  // nil < any id
-      else le = t.jid[i] <= pj;
-    }
-    unsigned m = __ballot_sync(0xffffffffu, le);
-    if (m) {
-      int last = 31 - __clz(m);
-      nearest = __shfl_sync(0xffffffffu, i >= 0 ? t.dru[i] : 0.0, last);
-    }
-  }
-  if (lane == 0) {
-    out->below_quota = (an <= q_count[u] && ac <= q_cpus[u] && am <= q_mem[u] && ag <= q_gpus[u]) ? 1 : 0;
-    double a = nearest + pm / div_mem[u], b = nearest + pcpu / div_cpus[u];
-    out->pending_dru = a > b ? a : b;
-  }
-}
-
 __device__ __forceinline__ double csr_get(const int32_t* off, const int32_t* key, const double* val, int o, int k) {
   if (!off) return 0.0;
   for (int i = off[o]; i < off[o + 1]; i++)
@@ -215,86 +172,6 @@ __device__ __forceinline__ double csr_get(const int32_t* off, const int32_t* key
 __global__ void host_has_task_kernel(RTasks t, int n, uint8_t* has_task) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n && t.alive[i]) has_task[t.host[i]] = 1;
-}
-
-// P2: constraints of pending job p on every host (constraints.clj:504-515, :680-697)
-__global__ void host_ok_kernel(PendCols pc, int p, HostCols hc, GroupCols gc, const uint8_t* has_task,
-                               const int32_t* preempted_hosts, const int32_t* n_preempted,
-                               int host_lifetime_mins, uint8_t* ok) {
-  int h = blockIdx.x * blockDim.x + threadIdx.x;
-  if (h >= hc.H) return;
-  const bool have = has_task[h] != 0;
-  bool pass = true;
-  if (have && pc.novel_off)
-    for (int k = pc.novel_off[p]; k < pc.novel_off[p + 1]; k++)
-      if (pc.novel_host[k] == hc.hostname_id[h]) pass = false;
-  const bool k8s = have && hc.is_k8s && hc.is_k8s[h];
-  const double g = pc.gpus ? pc.gpus[p] : 0.0;
-  if (k8s) {
-    if (g > 0.0) {
-      double hv = csr_get(hc.gpu_off, hc.gpu_model, hc.gpu_count, h, pc.gpu_model ? pc.gpu_model[p] : -1);
-      if (!(hv == g)) pass = false;
-    } else {
-      int nm = hc.gpu_off ? hc.gpu_off[h + 1] - hc.gpu_off[h] : 0;
-      if (nm != 0) pass = false;
-    }
-  } else if (!(g == 0.0)) {
-    pass = false;
-  }
-  if (pc.disk_request && pc.disk_request[p] >= 0.0 && k8s) {
-    double space = csr_get(hc.disk_off, hc.disk_type, hc.disk_space, h, pc.disk_type ? pc.disk_type[p] : -1);
-    if (!(space >= pc.disk_request[p])) pass = false;
-  }
-  if (pc.attr_off)
-    for (int k = pc.attr_off[p]; k < pc.attr_off[p + 1]; k++) {
-      int col = pc.attr_col[k], val = pc.attr_val[k];
-      if (!have || col < 0 || col >= hc.n_attr_cols) { pass = false; continue; }
-      int hv = hc.attr[(size_t)col * hc.H + h];
-      if (val <= 0 || hv != val) pass = false;
-    }
-  if (pc.est_end_ms && pc.est_end_ms[p] >= 0 && have && hc.host_start && hc.host_start[h] >= 0) {
-    long long death = 1000LL * hc.host_start[h] + 60000LL * host_lifetime_mins;
-    if (!(pc.est_end_ms[p] < death)) pass = false;
-  }
-  if (pc.ckpt_location && pc.ckpt_location[p] >= 0) {
-    int loc = (have && hc.location) ? hc.location[h] : -1;
-    if (loc != pc.ckpt_location[p]) pass = false;
-  }
-  if (pass && pc.group_off && gc.n > 0) {
-    const int np = *n_preempted;
-    for (int k = pc.group_off[p]; k < pc.group_off[p + 1] && pass; k++) {
-      const int gi = pc.group_idx[k];
-      const int kind = gc.kind[gi];
-      const int col = gc.attr_col ? gc.attr_col[gi] : -1;
-      const int c0 = gc.cot_off[gi], c1 = gc.cot_off[gi + 1];
-      auto hattr = [&](int hh) { return (col >= 0 && col < hc.n_attr_cols) ? hc.attr[(size_t)col * hc.H + hh] : 0; };
-      if (kind == COOK_GROUP_UNIQUE) {
-        if (!have) { pass = false; break; }
-        const int hn = hc.hostname_id[h];
-        for (int q = 0; q < np; q++) if (hc.hostname_id[preempted_hosts[q]] == hn) pass = false;
-        for (int c = c0; c < c1; c++) if (gc.cot_host[c] == hn) pass = false;
-      } else {
-        const int n = np + (c1 - c0);
-        if (n == 0) continue;
-        auto val_at = [&](int i) { return i < np ? hattr(preempted_hosts[i]) : gc.cot_attr[c0 + i - np]; };
-        const int target = have ? hattr(h) : 0;
-        int tf = 0;
-        for (int i = 0; i < n; i++) tf += (val_at(i) == target);
-        if (kind == COOK_GROUP_ATTR_EQUALS) { if (tf == 0) pass = false; }
-        else if (tf != 0) {
-          int mn = 0x7fffffff, mx = 0, distinct = 0;
-          for (int i = 0; i < n; i++) {
-            int vi = val_at(i), f = 0; bool first = true;
-            for (int q = 0; q < n; q++) { int vq = val_at(q); if (vq == vi) { f++; if (q < i) first = false; } }
-            if (first) { distinct++; mn = min(mn, f); mx = max(mx, f); }
-          }
-          if (gc.minimum[gi] > distinct) mn = 0;
-          if (!(mn == mx || tf < mx)) pass = false;
-        }
-      }
-    }
-  }
-  ok[h] = pass ? 1 : 0;
 }
 
 // host segments of the tasks grouped by host
@@ -422,139 +299,410 @@ __device__ HostBest host_select(const SelArgs& a, int p, int h, int lane, int32_
   return b;
 }
 
-__global__ void __launch_bounds__(256) host_best_kernel(SelArgs a, int p, const uint8_t* ok, HostBest* out) {
-  const int h = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (h >= a.hc.H) return;
-  HostBest b;
-  b.dru = 0.0; b.mem = b.cpus = b.gpus = 0.0; b.n_victims = -1;
-  if (ok[h]) b = host_select(a, p, h, lane, nullptr, 0);
-  if (lane == 0) out[h] = b;
-}
+// ------------------------------------------------------------------ the persistent loop
+// The walk over the pending jobs (rebalancer.clj:442-458) as ONE cooperative launch: the host
+// never synchronises inside the cycle.  Per pending job:
+//   A  every CTA: pending scalars (binary search for the nearest task; the quota fold only when
+//      the user has a finite quota), then host constraints + best sufficient prefix for the CTA's
+//      hosts (warp per host) and a CTA-level argmax                      -> grid.sync
+//   B  CTA 0: argmax over the CTAs, victims of the winner, next-state bookkeeping, insertion
+//      point of the job's synthetic task in the user order               -> grid.sync
+//   C  (only after a decision) every CTA: user order with the new task (double buffered), user
+//      segments, re-fold of the users that changed                      -> grid.sync
+namespace cg = cooperative_groups;
 
-struct ApplyArgs {
-  SelArgs sel;
-  const HostBest* best;
-  const int32_t* uord; const int32_t* us;   // user order and segment starts (before the insertion)
-  int32_t* n_tasks;        // live + dead task count (grows by one per decision)
-  int32_t* n_dec; int32_t* n_vict; int32_t* preempted_hosts; int32_t* n_preempted;
+struct CtaBest { double dru; int32_t rank, host; };
+
+struct RebArgs {
+  RTasks t; int R;
+  int32_t* ord[2]; int32_t* us[2]; int32_t* ue[2];
+  const int32_t* hord; const int32_t* hs; const int32_t* he;
+  HostCols hc; PendCols pc; GroupCols gc;
+  int P, U, MP;
+  const int32_t* user_rank;
+  const double *div_mem, *div_cpus, *q_count, *q_cpus, *q_mem, *q_gpus;
+  uint8_t* has_task; int32_t* preempted_hosts;
+  double min_diff, safe; int host_lifetime_mins;
+  HostBest* best;        // [H]
+  CtaBest* cta_best;     // [grid]
   cook_decision* dec; int32_t* victims;
-  uint8_t* has_task;
-  int32_t* changed;        // out: 1 if a decision was made
+  int32_t* cnt;          // [0] n_tasks [1] n_dec [2] n_vict [3] n_preempted [4] changed
   Refold* rf;
+  PendScalars* ps_all;   // [P] scalars of every job the walk reached (below_quota = -1: not reached)
+  int n_forced; const cook_decision* forced; const int32_t* forced_victims; int forced_only;
 };
 
-// P4 + P5: argmax over hosts (max dru; ties -> greatest hostname) and next-state.
-__global__ void __launch_bounds__(256) apply_kernel(ApplyArgs a, int p) {
-  __shared__ double s_dru[256];
-  __shared__ int s_rank[256];
-  __shared__ int s_host[256];
-  const int tid = threadIdx.x;
-  const HostCols& hc = a.sel.hc;
-  const PendCols& pc = a.sel.pc;
-  RTasks t = a.sel.t;
-  double bd = -1.0; int br = -1, bh = -1;
-  for (int h = tid; h < hc.H; h += blockDim.x) {
-    if (a.best[h].n_victims < 0) continue;
-    double d = a.best[h].dru; int r = hc.name_rank[h];
-    if (d > bd || (d == bd && r > br)) { bd = d; br = r; bh = h; }
-  }
-  s_dru[tid] = bd; s_rank[tid] = br; s_host[tid] = bh;
-  __syncthreads();
-  for (int s = blockDim.x / 2; s > 0; s >>= 1) {
-    if (tid < s) {
-      double d = s_dru[tid + s]; int r = s_rank[tid + s];
-      if (d > s_dru[tid] || (d == s_dru[tid] && r > s_rank[tid])) { s_dru[tid] = d; s_rank[tid] = r; s_host[tid] = s_host[tid + s]; }
-    }
-    __syncthreads();
-  }
-  if (tid >= 32) return;
-  const int h = s_host[0];
-  if (h < 0) {
-    if (tid == 0) *a.changed = 0;
-    return;
-  }
-  const HostBest b = a.best[h];
-  const int vb = *a.n_vict;
-  // the victims again (same selection), stored in ascending dru order
-  if (b.n_victims > 0) host_select(a.sel, p, h, tid, a.victims + vb, b.n_victims);
-  __syncwarp();
-  const int n = *a.n_tasks, ni = n;
-  const int pu = pc.user[p];
-  Refold& rf = *a.rf;
-  if (tid == 0) {
-    const int di = *a.n_dec;
-    cook_decision d;
-    d.pending_idx = p; d.host = h; d.dru = b.dru; d.mem = b.mem; d.cpus = b.cpus; d.gpus = b.gpus;
-    d.victim_begin = vb; d.victim_count = b.n_victims;
-    rf.n = 0; rf.all = 0; rf.pu = pu;
-    bool pu_listed = false;
-    for (int k = b.n_victims - 1; k >= 0; k--) {     // selection order
-      const int i = a.victims[vb + k];
-      t.alive[i] = 0;
-      a.preempted_hosts[(*a.n_preempted)++] = t.host[i];
-      const int u = t.user[i], from = a.us[u] + t.pos[i];
-      int e = 0;
-      while (e < rf.n && rf.user[e] != u) e++;
-      if (e < rf.n) rf.from[e] = min(rf.from[e], from);
-      else if (rf.n < 63) { rf.user[rf.n] = u; rf.from[rf.n] = from; rf.n++; }
-      else rf.all = 1;
-      if (u == pu) pu_listed = true;
-    }
-    if (!pu_listed) { rf.user[rf.n] = pu; rf.from[rf.n] = 0x7fffffff; rf.n++; }
-    *a.n_vict = vb + b.n_victims;
-    a.dec[di] = d;
-    *a.n_dec = di + 1;
-    // synthetic running task of the pending job on host h (create-task-ent :hostname)
-    *a.n_tasks = n + 1;
-    t.user[ni] = pu; t.prio[ni] = pc.prio[p]; t.start[ni] = 0x7fffffffffffffffLL;
-    t.tid[ni] = -1; t.jid[ni] = pc.jid[p];
-    t.cpus[ni] = pc.cpus[p]; t.mem[ni] = pc.mem[p]; t.gpus[ni] = pc.gpus ? pc.gpus[p] : 0.0;
-    t.host[ni] = h; t.alive[ni] = 1; t.dru[ni] = 0.0; t.pos[ni] = 0; t.cm[ni] = 0.0; t.cc[ni] = 0.0;
-    a.has_task[h] = 1;
-    hc.has_spare[h] = 1;
-    hc.spare_mem[h] = b.mem - pc.mem[p];
-    hc.spare_gpus[h] = b.gpus - (pc.gpus ? pc.gpus[p] : 0.0);
-    hc.spare_cpus[h] = b.cpus - pc.cpus[p];
-  }
-  __syncwarp();
-  // where the new task goes in the user order: after every task that is not greater
-  // (32-ary search: the predicate "new task < uord[q]" is monotone in q)
-  LessUser less{t, a.sel.user_rank};
-  int lo = 0, hi = n;
+// task <= synthetic pending task [-prio, Long/MAX, nil(-1), job id] (tools.clj:614-641) ?
+__device__ __forceinline__ bool task_le_pending(const RTasks& t, int i, int pprio, long long pj) {
+  const int tp = -t.prio[i];
+  if (tp != pprio) return tp < pprio;
+  if (t.start[i] != 0x7fffffffffffffffLL) return true;
+  if (t.tid[i] != -1) return false;  // nil < any id
+  return t.jid[i] <= pj;
+}
+
+// P1 for one warp: job-below-quota (:210-220) and pending dru (:182-208) of pending job p.
+__device__ void pending_scalars(const RebArgs& a, const int32_t* ord, const int32_t* us, const int32_t* ue, int p,
+                                PendScalars* out) {
+  const int lane = threadIdx.x & 31;
+  const RTasks& t = a.t;
+  const PendCols& pc = a.pc;
+  const int u = pc.user[p];
+  const int s = us[u], e = ue[u];
+  const double pm = pc.mem[p], pcpu = pc.cpus[p], pg = pc.gpus ? pc.gpus[p] : 0.0;
+  const int pprio = -pc.prio[p];
+  const long long pj = pc.jid[p];
+  // nearest: the last LIVE task of the user that sorts <= the synthetic task.  The predicate is
+  // monotone along the user's order => 32-ary search for the first task that is greater
+  int lo = s, hi = e;
   while (lo < hi) {
     const int step = (hi - lo + 31) / 32;
-    const int q = lo + tid * step;
-    const bool pred = q < hi ? less(ni, a.uord[q]) : true;
-    const unsigned m = __ballot_sync(0xffffffffu, pred);
+    const int q = lo + lane * step;
+    const bool gt = q < hi ? !task_le_pending(t, ord[q], pprio, pj) : true;
+    const unsigned m = __ballot_sync(0xffffffffu, gt);
     const int L = m ? __ffs(m) - 1 : 32;
     const int nlo = L > 0 ? lo + (L - 1) * step + 1 : lo;
     const int nhi = L < 32 ? min(hi, lo + L * step) : hi;
     lo = min(nlo, nhi); hi = nhi;
   }
-  if (tid == 0) {
-    rf.q_ins = lo;
-    *a.changed = 1;
+  double nearest = 0.0;   // walk back over tasks preempted earlier in this cycle
+  for (int base = lo; base > s; base -= 32) {
+    const int q = base - 1 - lane;
+    const bool live = q >= s && t.alive[ord[q]];
+    const unsigned m = __ballot_sync(0xffffffffu, live);
+    if (m) {
+      const int l = __ffs(m) - 1;
+      nearest = __shfl_sync(0xffffffffu, live ? t.dru[ord[q]] : 0.0, l);
+      break;
+    }
+  }
+  // job-below-quota: a left fold over (p, tasks in order); skipped when no quota can bind
+  const double qn = a.q_count[u], qc = a.q_cpus[u], qm = a.q_mem[u], qg = a.q_gpus[u];
+  const double dmax = 1.7976931348623157e308;
+  int below = 1;
+  if (!(qn >= dmax && qc >= dmax && qm >= dmax && qg >= dmax)) {
+    double an = 1.0, ac = pcpu, am = pm, ag = pg;  // (conj running-jobs p): p first
+    for (int base = s; base < e; base += 32) {
+      const int q = base + lane;
+      int i = q < e ? ord[q] : -1;
+      if (i >= 0 && !t.alive[i]) i = -1;   // preempted earlier in this cycle: adds 0.0
+      const double xc = i >= 0 ? t.cpus[i] : 0.0, xm = i >= 0 ? t.mem[i] : 0.0, xg = i >= 0 ? t.gpus[i] : 0.0;
+      const double xn = i >= 0 ? 1.0 : 0.0;
+      const int cntn = min(32, e - base);
+      for (int l = 0; l < cntn; l++) {
+        an = an + __shfl_sync(0xffffffffu, xn, l);
+        ac = ac + __shfl_sync(0xffffffffu, xc, l);
+        am = am + __shfl_sync(0xffffffffu, xm, l);
+        ag = ag + __shfl_sync(0xffffffffu, xg, l);
+      }
+    }
+    below = (an <= qn && ac <= qc && am <= qm && ag <= qg) ? 1 : 0;
+  }
+  if (lane == 0) {
+    out->below_quota = below;
+    const double x = nearest + pm / a.div_mem[u], y = nearest + pcpu / a.div_cpus[u];
+    out->pending_dru = x > y ? x : y;
   }
 }
 
-// uord with the new task inserted at rf->q_ins (out of place)
-__global__ void insert_kernel(const int32_t* src, int32_t* dst, int n, int ni, const Refold* rf) {
-  int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j > n) return;
-  const int q = rf->q_ins;
-  dst[j] = j < q ? src[j] : (j == q ? ni : src[j - 1]);
+// P2 for one host (every lane computes the same): constraints.clj:504-515, :680-697
+__device__ bool host_ok(const RebArgs& a, int p, int h, int np) {
+  const PendCols& pc = a.pc;
+  const HostCols& hc = a.hc;
+  const GroupCols& gc = a.gc;
+  const bool have = a.has_task[h] != 0;
+  bool pass = true;
+  if (have && pc.novel_off)
+    for (int k = pc.novel_off[p]; k < pc.novel_off[p + 1]; k++)
+      if (pc.novel_host[k] == hc.hostname_id[h]) pass = false;
+  const bool k8s = have && hc.is_k8s && hc.is_k8s[h];
+  const double g = pc.gpus ? pc.gpus[p] : 0.0;
+  if (k8s) {
+    if (g > 0.0) {
+      double hv = csr_get(hc.gpu_off, hc.gpu_model, hc.gpu_count, h, pc.gpu_model ? pc.gpu_model[p] : -1);
+      if (!(hv == g)) pass = false;
+    } else {
+      int nm = hc.gpu_off ? hc.gpu_off[h + 1] - hc.gpu_off[h] : 0;
+      if (nm != 0) pass = false;
+    }
+  } else if (!(g == 0.0)) {
+    pass = false;
+  }
+  if (pc.disk_request && pc.disk_request[p] >= 0.0 && k8s) {
+    double space = csr_get(hc.disk_off, hc.disk_type, hc.disk_space, h, pc.disk_type ? pc.disk_type[p] : -1);
+    if (!(space >= pc.disk_request[p])) pass = false;
+  }
+  if (pc.attr_off)
+    for (int k = pc.attr_off[p]; k < pc.attr_off[p + 1]; k++) {
+      int col = pc.attr_col[k], val = pc.attr_val[k];
+      if (!have || col < 0 || col >= hc.n_attr_cols) { pass = false; continue; }
+      int hv = hc.attr[(size_t)col * hc.H + h];
+      if (val <= 0 || hv != val) pass = false;
+    }
+  if (pc.est_end_ms && pc.est_end_ms[p] >= 0 && have && hc.host_start && hc.host_start[h] >= 0) {
+    long long death = 1000LL * hc.host_start[h] + 60000LL * a.host_lifetime_mins;
+    if (!(pc.est_end_ms[p] < death)) pass = false;
+  }
+  if (pc.ckpt_location && pc.ckpt_location[p] >= 0) {
+    int loc = (have && hc.location) ? hc.location[h] : -1;
+    if (loc != pc.ckpt_location[p]) pass = false;
+  }
+  if (pass && pc.group_off && gc.n > 0) {
+    for (int k = pc.group_off[p]; k < pc.group_off[p + 1] && pass; k++) {
+      const int gi = pc.group_idx[k];
+      const int kind = gc.kind[gi];
+      const int col = gc.attr_col ? gc.attr_col[gi] : -1;
+      const int c0 = gc.cot_off[gi], c1 = gc.cot_off[gi + 1];
+      auto hattr = [&](int hh) { return (col >= 0 && col < hc.n_attr_cols) ? hc.attr[(size_t)col * hc.H + hh] : 0; };
+      if (kind == COOK_GROUP_UNIQUE) {
+        if (!have) { pass = false; break; }
+        const int hn = hc.hostname_id[h];
+        for (int q = 0; q < np; q++) if (hc.hostname_id[a.preempted_hosts[q]] == hn) pass = false;
+        for (int c = c0; c < c1; c++) if (gc.cot_host[c] == hn) pass = false;
+      } else {
+        const int n = np + (c1 - c0);
+        if (n == 0) continue;
+        auto val_at = [&](int i) { return i < np ? hattr(a.preempted_hosts[i]) : gc.cot_attr[c0 + i - np]; };
+        const int target = have ? hattr(h) : 0;
+        int tf = 0;
+        for (int i = 0; i < n; i++) tf += (val_at(i) == target);
+        if (kind == COOK_GROUP_ATTR_EQUALS) { if (tf == 0) pass = false; }
+        else if (tf != 0) {
+          int mn = 0x7fffffff, mx = 0, distinct = 0;
+          for (int i = 0; i < n; i++) {
+            int vi = val_at(i), f = 0; bool first = true;
+            for (int q = 0; q < n; q++) { int vq = val_at(q); if (vq == vi) { f++; if (q < i) first = false; } }
+            if (first) { distinct++; mn = min(mn, f); mx = max(mx, f); }
+          }
+          if (gc.minimum[gi] > distinct) mn = 0;
+          if (!(mn == mx || tf < mx)) pass = false;
+        }
+      }
+    }
+  }
+  return pass;
+}
+
+__global__ void __launch_bounds__(256) rebalance_kernel(RebArgs a) {
+  cg::grid_group grid = cg::this_grid();
+  __shared__ PendScalars s_ps;
+  __shared__ double s_dru[8];
+  __shared__ int s_rank[8], s_host[8];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nw = blockDim.x >> 5;
+  const int gw = blockIdx.x * nw + warp, n_gw = gridDim.x * nw;
+  const int gt = blockIdx.x * blockDim.x + tid, n_gt = gridDim.x * blockDim.x;
+  const HostCols& hc = a.hc;
+  const PendCols& pc = a.pc;
+  RTasks t = a.t;
+  int cur = 0, n_tasks = a.R, n_dec = 0;
+  const bool forced_only = a.n_forced > 0 && a.forced_only != 0;
+  const int n_walk = forced_only ? a.n_forced : a.P;
+  for (int w = 0; w < n_walk && n_dec < a.MP; w++) {
+    const int p = forced_only ? a.forced[w].pending_idx : w;
+    int fi = -1;
+    for (int q = 0; q < a.n_forced; q++) if (a.forced[q].pending_idx == p) fi = q;
+    const int32_t* ord = a.ord[cur];
+    const int32_t* us = a.us[cur];
+    const int32_t* ue = a.ue[cur];
+    // ---- A: scalars of the job, then this CTA's hosts
+    if (warp == 0) {
+      pending_scalars(a, ord, us, ue, p, &s_ps);
+    }
+    __syncthreads();
+    if (blockIdx.x == 0 && tid == 0) a.ps_all[p] = s_ps;
+    SelArgs sa;
+    sa.hord = a.hord; sa.hs = a.hs; sa.he = a.he; sa.t = t; sa.R = a.R; sa.n_tasks = n_tasks;
+    sa.hc = hc; sa.pc = pc; sa.user_rank = a.user_rank; sa.ps = &s_ps;
+    sa.min_diff = a.min_diff; sa.safe = a.safe;
+    double bd = -1.0;
+    int br = -1, bh = -1;
+    if (fi < 0) {
+      const int np = a.cnt[3];
+      for (int h = gw; h < hc.H; h += n_gw) {
+        HostBest b;
+        b.dru = 0.0; b.mem = b.cpus = b.gpus = 0.0; b.n_victims = -1;
+        if (host_ok(a, p, h, np)) b = host_select(sa, p, h, lane, nullptr, 0);
+        if (lane == 0) a.best[h] = b;
+        if (b.n_victims >= 0) {
+          const int r = hc.name_rank[h];
+          if (b.dru > bd || (b.dru == bd && r > br)) { bd = b.dru; br = r; bh = h; }
+        }
+      }
+    }
+    if (lane == 0) { s_dru[warp] = bd; s_rank[warp] = br; s_host[warp] = bh; }
+    __syncthreads();
+    if (tid == 0) {
+      for (int q = 1; q < nw; q++)
+        if (s_dru[q] > bd || (s_dru[q] == bd && s_rank[q] > br)) { bd = s_dru[q]; br = s_rank[q]; bh = s_host[q]; }
+      CtaBest cb;
+      cb.dru = bd; cb.rank = br; cb.host = bh;
+      a.cta_best[blockIdx.x] = cb;
+    }
+    grid.sync();
+    // ---- B: argmax over the CTAs (max dru; ties -> greatest hostname), next-state
+    if (blockIdx.x == 0 && warp == 0) {
+      double d = -1.0;
+      int r = -1, h = -1;
+      for (int q = lane; q < (int)gridDim.x; q += 32) {
+        const CtaBest cb = a.cta_best[q];
+        if (cb.host >= 0 && (cb.dru > d || (cb.dru == d && cb.rank > r))) { d = cb.dru; r = cb.rank; h = cb.host; }
+      }
+      for (int o = 16; o > 0; o >>= 1) {
+        const double od = __shfl_xor_sync(0xffffffffu, d, o);
+        const int orr = __shfl_xor_sync(0xffffffffu, r, o), oh = __shfl_xor_sync(0xffffffffu, h, o);
+        if (oh >= 0 && (od > d || (od == d && orr > r))) { d = od; r = orr; h = oh; }
+      }
+      HostBest b;
+      b.dru = 0.0; b.mem = b.cpus = b.gpus = 0.0; b.n_victims = -1;
+      const int vb = a.cnt[2];
+      if (fi >= 0) {   // the decision is given (the reference's tests hand next-state its input)
+        const cook_decision f = a.forced[fi];
+        h = f.host; b.dru = f.dru; b.mem = f.mem; b.cpus = f.cpus; b.gpus = f.gpus; b.n_victims = f.victim_count;
+        for (int q = lane; q < f.victim_count; q += 32)
+          a.victims[vb + f.victim_count - 1 - q] = a.forced_victims[f.victim_begin + q];   // ascending dru
+        __syncwarp();
+      } else if (h >= 0) {
+        b = a.best[h];
+        // the victims again (same selection), stored in ascending dru order
+        if (b.n_victims > 0) host_select(sa, p, h, lane, a.victims + vb, b.n_victims);
+        __syncwarp();
+      }
+      if (h < 0) {
+        if (lane == 0) a.cnt[4] = 0;
+      } else {
+        const int n = n_tasks, ni = n;
+        const int pu = pc.user[p];
+        Refold& rf = *a.rf;
+        if (lane == 0) {
+          const int di = a.cnt[1];
+          cook_decision dd;
+          dd.pending_idx = p; dd.host = h; dd.dru = b.dru; dd.mem = b.mem; dd.cpus = b.cpus; dd.gpus = b.gpus;
+          dd.victim_begin = vb; dd.victim_count = b.n_victims;
+          rf.n = 0; rf.all = 0; rf.pu = pu;
+          bool pu_listed = false;
+          for (int k = b.n_victims - 1; k >= 0; k--) {     // selection order
+            const int i = a.victims[vb + k];
+            t.alive[i] = 0;
+            a.preempted_hosts[a.cnt[3]++] = t.host[i];
+            const int u = t.user[i], from = us[u] + t.pos[i];
+            int e = 0;
+            while (e < rf.n && rf.user[e] != u) e++;
+            if (e < rf.n) rf.from[e] = min(rf.from[e], from);
+            else if (rf.n < 63) { rf.user[rf.n] = u; rf.from[rf.n] = from; rf.n++; }
+            else rf.all = 1;
+            if (u == pu) pu_listed = true;
+          }
+          if (!pu_listed) { rf.user[rf.n] = pu; rf.from[rf.n] = 0x7fffffff; rf.n++; }
+          a.cnt[2] = vb + b.n_victims;
+          a.dec[di] = dd;
+          a.cnt[1] = di + 1;
+          // synthetic running task of the pending job on host h (create-task-ent :hostname)
+          a.cnt[0] = n + 1;
+          t.user[ni] = pu; t.prio[ni] = pc.prio[p]; t.start[ni] = 0x7fffffffffffffffLL;
+          t.tid[ni] = -1; t.jid[ni] = pc.jid[p];
+          t.cpus[ni] = pc.cpus[p]; t.mem[ni] = pc.mem[p]; t.gpus[ni] = pc.gpus ? pc.gpus[p] : 0.0;
+          t.host[ni] = h; t.alive[ni] = 1; t.dru[ni] = 0.0; t.pos[ni] = 0; t.cm[ni] = 0.0; t.cc[ni] = 0.0;
+          a.has_task[h] = 1;
+          hc.has_spare[h] = 1;
+          hc.spare_mem[h] = b.mem - pc.mem[p];
+          hc.spare_gpus[h] = b.gpus - (pc.gpus ? pc.gpus[p] : 0.0);
+          hc.spare_cpus[h] = b.cpus - pc.cpus[p];
+        }
+        __syncwarp();
+        // where the new task goes in the user order: after every task that is not greater
+        // (32-ary search: the predicate "new task < ord[q]" is monotone in q)
+        LessUser less{t, a.user_rank};
+        int lo = 0, hi = n;
+        while (lo < hi) {
+          const int step = (hi - lo + 31) / 32;
+          const int q = lo + lane * step;
+          const bool pred = q < hi ? less(ni, ord[q]) : true;
+          const unsigned m = __ballot_sync(0xffffffffu, pred);
+          const int L = m ? __ffs(m) - 1 : 32;
+          const int nlo = L > 0 ? lo + (L - 1) * step + 1 : lo;
+          const int nhi = L < 32 ? min(hi, lo + L * step) : hi;
+          lo = min(nlo, nhi); hi = nhi;
+        }
+        if (lane == 0) { rf.q_ins = lo; a.cnt[4] = 1; }
+      }
+      __threadfence();
+    }
+    grid.sync();
+    n_dec = a.cnt[1];
+    if (a.cnt[4] != 0) {
+      // ---- C: next-state.  New order / segments go to the other buffer; the changed users are
+      // re-folded reading the new order through the old one (no sync in between).
+      const int n = n_tasks, ni = n_tasks;
+      const Refold& rf = *a.rf;
+      const int q = rf.q_ins, pu = rf.pu;
+      int32_t* nord = a.ord[cur ^ 1];
+      int32_t* nus = a.us[cur ^ 1];
+      int32_t* nue = a.ue[cur ^ 1];
+      auto new_at = [&](int j) { return j < q ? ord[j] : (j == q ? ni : ord[j - 1]); };
+      for (int j = gt; j <= n; j += n_gt) {
+        const int i = new_at(j);
+        nord[j] = i;
+        const int u = t.user[i];
+        if (j == 0 || t.user[new_at(j - 1)] != u) nus[u] = j;
+        if (j == n || t.user[new_at(j + 1)] != u) nue[u] = j + 1;
+      }
+      const bool all = rf.all != 0;
+      const int n_fold = all ? a.U : rf.n;
+      for (int wv = gw; wv < n_fold; wv += n_gw) {
+        const int u = all ? wv : rf.user[wv];
+        int s = us[u], e = ue[u];
+        if (e <= s) { if (u != pu) continue; s = q; e = q + 1; }
+        else if (u == pu) e = e + 1;
+        else if (s >= q) { s++; e++; }
+        int f = s;
+        if (!all) {
+          f = rf.from[wv];
+          if (f == 0x7fffffff) f = q;           // only the insertion touches this user
+          else if (f >= q) f++;                 // slots at and after the insertion moved by one
+          if (u == pu) f = min(f, q);
+          f = min(max(f, s), e);
+        }
+        const double md = a.div_mem[u], cd = a.div_cpus[u];
+        double am = 0.0, ac = 0.0;
+        if (f > s) { const int j = new_at(f - 1); am = t.cm[j]; ac = t.cc[j]; }
+        for (int base = f; base < e; base += 32) {
+          const int pp = base + lane;
+          const int i = pp < e ? new_at(pp) : -1;
+          const bool live = i >= 0 && t.alive[i];
+          const double xm = live ? t.mem[i] : 0.0, xc = live ? t.cpus[i] : 0.0;
+          double mym = 0.0, myc = 0.0;
+          const int cntn = min(32, e - base);
+          for (int l = 0; l < cntn; l++) {
+            am = am + __shfl_sync(0xffffffffu, xm, l);
+            ac = ac + __shfl_sync(0xffffffffu, xc, l);
+            if (lane == l) { mym = am; myc = ac; }
+          }
+          if (i >= 0) {
+            t.cm[i] = mym; t.cc[i] = myc;
+            const double x = mym / md, y = myc / cd;
+            t.dru[i] = x > y ? x : y;
+            t.pos[i] = pp - s;
+          }
+        }
+      }
+      grid.sync();
+      cur ^= 1;
+      n_tasks = n_tasks + 1;
+    }
+  }
 }
 
 }  // namespace
 
 #define RUP(dst, src, n) CK(pool, upload(ar, st, (src), (size_t)(n), &(dst)))
 
-extern "C" int32_t cook_rebalance(cook_pool* pool, const cook_running_soa* running,
-                                  const cook_jobs_soa* pending, const int64_t* pending_job_id,
-                                  const int32_t* pending_priority, const cook_host_table* hosts,
-                                  const cook_groups* groups, const cook_user_table* users,
-                                  const cook_rebalance_params* prm, cook_decision* out_decisions,
-                                  int32_t* out_victims, int32_t* out_n) {
+static int32_t rebalance_run(cook_pool* pool, const cook_running_soa* running,
+                             const cook_jobs_soa* pending, const int64_t* pending_job_id,
+                             const int32_t* pending_priority, const cook_host_table* hosts,
+                             const cook_groups* groups, const cook_user_table* users,
+                             const cook_rebalance_params* prm, cook_decision* out_decisions,
+                             int32_t* out_victims, int32_t* out_n, const cook_reb_trace* tr) {
   if (!pool) return COOK_E_BADARG;
   if (!running || !pending || !pending_job_id || !pending_priority || !hosts || !users || !prm ||
       !out_decisions || !out_victims || !out_n)
@@ -589,7 +737,11 @@ extern "C" int32_t cook_rebalance(cook_pool* pool, const cook_running_soa* runni
   sz.add<int32_t>(csr_p + 64); sz.add<int64_t>(P + 1);
   if (G) { sz.add<int32_t>(6 * (size_t)(G + 2)); sz.add<int32_t>(2 * (size_t)(groups->cot_off ? groups->cot_off[G] : 0) + 64); }
   sz.add<HostBest>(H + 1); sz.add<cook_decision>(MP + 1); sz.add<int32_t>(CAP + MP);
-  sz.add<PendScalars>(4); sz.add<int32_t>(64);
+  sz.add<PendScalars>(P + 4); sz.add<int32_t>(64);
+  sz.add<int32_t>(CAP); sz.add<int32_t>(CAP + MP);               // second order buffer, preempted hosts
+  for (int k = 0; k < 2; k++) sz.add<int32_t>(U + 1);            // second segment buffers
+  sz.add<CtaBest>(pool->sm_count + 8);
+  if (tr && tr->n_forced > 0) { sz.add<cook_decision>(tr->n_forced + 1); sz.add<int32_t>(CAP + MP); }
   CK(pool, ar.reserve(sz.off + (1 << 16)));
   ar.reset();
 
@@ -669,30 +821,54 @@ extern "C" int32_t cook_rebalance(cook_pool* pool, const cook_running_soa* runni
     if (!gc.cot_off || !gc.kind) return set_err(pool, COOK_E_BADARG, "cook_rebalance: incomplete cook_groups");
   }
 
-  int32_t* d_ord = ar.take<int32_t>(CAP); int32_t* d_hord = ar.take<int32_t>(CAP);
+  int32_t* d_ord = ar.take<int32_t>(CAP); int32_t* d_ord2 = ar.take<int32_t>(CAP);
+  int32_t* d_hord = ar.take<int32_t>(CAP);
   int32_t* d_tmp = ar.take<int32_t>(CAP);
   int32_t* d_us = ar.take<int32_t>(U + 1); int32_t* d_ue = ar.take<int32_t>(U + 1);
+  int32_t* d_us2 = ar.take<int32_t>(U + 1); int32_t* d_ue2 = ar.take<int32_t>(U + 1);
   int32_t* d_hs = ar.take<int32_t>(H + 1); int32_t* d_he = ar.take<int32_t>(H + 1);
-  uint8_t* d_has_task = ar.take<uint8_t>(H + 1); uint8_t* d_ok = ar.take<uint8_t>(H + 1);
+  uint8_t* d_has_task = ar.take<uint8_t>(H + 1);
   HostBest* d_best = ar.take<HostBest>(H + 1);
+  CtaBest* d_cta = ar.take<CtaBest>(pool->sm_count + 8);
   cook_decision* d_dec = ar.take<cook_decision>(MP + 1);
   int32_t* d_vict = ar.take<int32_t>(CAP + MP);
   int32_t* d_pre = ar.take<int32_t>(CAP + MP);
-  PendScalars* d_ps = ar.take<PendScalars>(4);
+  PendScalars* d_ps = ar.take<PendScalars>(P + 4);
   Refold* d_rf = ar.take<Refold>(1);
   int32_t* d_cnt = ar.take<int32_t>(64);  // [0] n_tasks [1] n_dec [2] n_vict [3] n_preempted [4] changed
-  if (!d_cnt) return set_err(pool, COOK_E_OOM, "cook_rebalance: arena exhausted");
+  cook_decision* d_forced = nullptr;
+  int32_t* d_fvict = nullptr;
+  const int NF = tr ? tr->n_forced : 0;
+  if (NF > 0) {
+    int nfv = 0;
+    for (int q = 0; q < NF; q++) {
+      const cook_decision& f = tr->forced[q];
+      if (f.pending_idx < 0 || f.pending_idx >= P || f.host < 0 || f.host >= H || f.victim_count < 0 || f.victim_begin < 0)
+        return set_err(pool, COOK_E_BADARG, "cook_rebalance_trace: bad forced decision");
+      nfv = std::max(nfv, f.victim_begin + f.victim_count);
+    }
+    if (nfv > CAP + MP) return set_err(pool, COOK_E_BADARG, "cook_rebalance_trace: too many forced victims");
+    d_forced = ar.take<cook_decision>(NF + 1);
+    d_fvict = ar.take<int32_t>(CAP + MP);
+    if (d_forced) CK(pool, cudaMemcpyAsync(d_forced, tr->forced, sizeof(cook_decision) * NF, cudaMemcpyHostToDevice, st));
+    if (d_fvict && nfv > 0) CK(pool, cudaMemcpyAsync(d_fvict, tr->forced_victims, sizeof(int32_t) * nfv, cudaMemcpyHostToDevice, st));
+  }
+  if (ar.failed) return set_err(pool, COOK_E_OOM, "cook_rebalance: arena exhausted");
   int32_t h_cnt[8] = {R, 0, 0, 0, 0, 0, 0, 0};
   CK(pool, cudaMemcpyAsync(d_cnt, h_cnt, sizeof(h_cnt), cudaMemcpyHostToDevice, st));
+  CK(pool, cudaMemsetAsync(d_ps, 0xff, sizeof(PendScalars) * (P + 4), st));   // below_quota -1, dru NaN: not reached
 
   CK(pool, cudaEventRecord(pool->ev[13], st));
   const int TB = 256;
   // ---- init-state: user order + DRU of every user, tasks grouped by host
   CK(pool, cudaMemsetAsync(d_us, 0, sizeof(int32_t) * (U + 1), st));
   CK(pool, cudaMemsetAsync(d_ue, 0, sizeof(int32_t) * (U + 1), st));
+  CK(pool, cudaMemsetAsync(d_us2, 0, sizeof(int32_t) * (U + 1), st));
+  CK(pool, cudaMemsetAsync(d_ue2, 0, sizeof(int32_t) * (U + 1), st));
   CK(pool, cudaMemsetAsync(d_hs, 0, sizeof(int32_t) * (H + 1), st));
   CK(pool, cudaMemsetAsync(d_he, 0, sizeof(int32_t) * (H + 1), st));
   CK(pool, cudaMemsetAsync(d_has_task, 0, H + 1, st));
+  int launches = 0;
   if (R > 0) {
     iota_r<<<(R + TB - 1) / TB, TB, 0, st>>>(d_ord, R);
     CK(pool, csort::sort_indices(d_ord, d_tmp, R, LessUser{t, d_urank}, st));
@@ -702,45 +878,77 @@ extern "C" int32_t cook_rebalance(cook_pool* pool, const cook_running_soa* runni
     CK(pool, csort::sort_indices(d_hord, d_tmp, R, LessHost{t}, st));
     host_seg_kernel<<<(R + TB - 1) / TB, TB, 0, st>>>(d_hord, t, R, d_hs, d_he);
     host_has_task_kernel<<<(R + TB - 1) / TB, TB, 0, st>>>(t, R, d_has_task);
+    launches += 8;
+    for (long long w = csort::TILE; w < R; w <<= 1) launches += 2;
   }
-  SelArgs sa;
-  sa.hord = d_hord; sa.hs = d_hs; sa.he = d_he; sa.t = t; sa.R = R; sa.n_tasks = R;
-  sa.hc = hc; sa.pc = pc; sa.user_rank = d_urank; sa.ps = d_ps;
-  sa.min_diff = prm->min_dru_diff; sa.safe = prm->safe_dru_threshold;
-  int n_tasks = R, n_dec = 0;
-  for (int p = 0; p < P && n_dec < MP; p++) {
-    pending_kernel<<<1, 32, 0, st>>>(d_ord, t, pc, p, d_us, d_ue, d_qn, d_qc, d_qm, d_qg, d_divm, d_divc, d_ps);
-    host_ok_kernel<<<(H + TB - 1) / TB, TB, 0, st>>>(pc, p, hc, gc, d_has_task, d_pre, d_cnt + 3,
-                                                     prm->host_lifetime_mins, d_ok);
-    sa.n_tasks = n_tasks;
-    host_best_kernel<<<(H + 7) / 8, 256, 0, st>>>(sa, p, d_ok, d_best);
-    ApplyArgs aa;
-    aa.sel = sa; aa.best = d_best; aa.uord = d_ord; aa.us = d_us;
-    aa.n_tasks = d_cnt; aa.n_dec = d_cnt + 1; aa.n_vict = d_cnt + 2; aa.preempted_hosts = d_pre;
-    aa.n_preempted = d_cnt + 3; aa.dec = d_dec; aa.victims = d_vict; aa.has_task = d_has_task;
-    aa.changed = d_cnt + 4; aa.rf = d_rf;
-    apply_kernel<<<1, 256, 0, st>>>(aa, p);
-    CK(pool, cudaGetLastError());
-    CK(pool, cudaMemcpyAsync(h_cnt, d_cnt, sizeof(int32_t) * 5, cudaMemcpyDeviceToHost, st));
-    CK(pool, cudaStreamSynchronize(st));
-    n_dec = h_cnt[1];
-    if (h_cnt[4] != 0) {  // next-state: the new task enters its user's order, changed users are re-folded
-      const int n = n_tasks, ni = n_tasks;
-      insert_kernel<<<(n + 1 + TB - 1) / TB, TB, 0, st>>>(d_ord, d_tmp, n, ni, d_rf);
-      CK(pool, cudaMemcpyAsync(d_ord, d_tmp, sizeof(int32_t) * (n + 1), cudaMemcpyDeviceToDevice, st));
-      CK(pool, cudaMemsetAsync(d_us, 0, sizeof(int32_t) * (U + 1), st));
-      CK(pool, cudaMemsetAsync(d_ue, 0, sizeof(int32_t) * (U + 1), st));
-      user_seg_kernel<<<(n + 1 + TB - 1) / TB, TB, 0, st>>>(d_ord, t, n + 1, d_us, d_ue);
-      user_dru_kernel<<<(U + 3) / 4, 128, 0, st>>>(d_ord, t, d_divm, d_divc, d_us, d_ue, U, d_rf);
-    }
-    n_tasks = h_cnt[0];
+  // ---- the walk over the pending jobs: one cooperative launch, no host round trip inside
+  RebArgs ra;
+  ra.t = t; ra.R = R;
+  ra.ord[0] = d_ord; ra.ord[1] = d_ord2; ra.us[0] = d_us; ra.us[1] = d_us2; ra.ue[0] = d_ue; ra.ue[1] = d_ue2;
+  ra.hord = d_hord; ra.hs = d_hs; ra.he = d_he;
+  ra.hc = hc; ra.pc = pc; ra.gc = gc; ra.P = P; ra.U = U; ra.MP = MP;
+  ra.user_rank = d_urank; ra.div_mem = d_divm; ra.div_cpus = d_divc;
+  ra.q_count = d_qn; ra.q_cpus = d_qc; ra.q_mem = d_qm; ra.q_gpus = d_qg;
+  ra.has_task = d_has_task; ra.preempted_hosts = d_pre;
+  ra.min_diff = prm->min_dru_diff; ra.safe = prm->safe_dru_threshold; ra.host_lifetime_mins = prm->host_lifetime_mins;
+  ra.best = d_best; ra.cta_best = d_cta; ra.dec = d_dec; ra.victims = d_vict; ra.cnt = d_cnt; ra.rf = d_rf;
+  ra.ps_all = d_ps;
+  ra.n_forced = NF; ra.forced = d_forced; ra.forced_victims = d_fvict; ra.forced_only = tr ? tr->forced_only : 0;
+  {
+    int occ = 0;
+    CK(pool, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rebalance_kernel, 256, 0));
+    if (occ < 1) return set_err(pool, COOK_E_CUDA, "cook_rebalance: kernel does not fit on an SM");
+    // one CTA per SM is enough: the grid barrier is what the loop waits for, and it gets slower with more CTAs
+    int grid = std::min(pool->sm_count, std::max(1, (H + 7) / 8));
+    void* kargs[] = {&ra};
+    CK(pool, cudaLaunchCooperativeKernel((void*)rebalance_kernel, dim3(grid), dim3(256), kargs, 0, st));
+    launches++;
   }
   CK(pool, cudaEventRecord(pool->ev[14], st));
+  CK(pool, cudaMemcpyAsync(h_cnt, d_cnt, sizeof(int32_t) * 5, cudaMemcpyDeviceToHost, st));
+  CK(pool, cudaStreamSynchronize(st));
+  const int n_dec = h_cnt[1], n_tasks = h_cnt[0];
   if (n_dec > 0) {
     CK(pool, cudaMemcpyAsync(out_decisions, d_dec, sizeof(cook_decision) * n_dec, cudaMemcpyDeviceToHost, st));
     if (h_cnt[2] > 0)
       CK(pool, cudaMemcpyAsync(out_victims, d_vict, sizeof(int32_t) * h_cnt[2], cudaMemcpyDeviceToHost, st));
+  }
+  if (tr) {   // the state the reference's own tests read (K18 pending dru, K21 next-state, job-below-quota)
+    std::vector<PendScalars> hps(P);
+    std::vector<double> hdru(n_tasks);
+    std::vector<uint8_t> halive(n_tasks);
+    std::vector<int32_t> hpos(n_tasks), huser(n_tasks);
+    CK(pool, cudaMemcpyAsync(hps.data(), d_ps, sizeof(PendScalars) * P, cudaMemcpyDeviceToHost, st));
+    if (n_tasks > 0) {
+      CK(pool, cudaMemcpyAsync(hdru.data(), t.dru, sizeof(double) * n_tasks, cudaMemcpyDeviceToHost, st));
+      CK(pool, cudaMemcpyAsync(halive.data(), t.alive, n_tasks, cudaMemcpyDeviceToHost, st));
+      CK(pool, cudaMemcpyAsync(hpos.data(), t.pos, sizeof(int32_t) * n_tasks, cudaMemcpyDeviceToHost, st));
+      CK(pool, cudaMemcpyAsync(huser.data(), t.user, sizeof(int32_t) * n_tasks, cudaMemcpyDeviceToHost, st));
+    }
+    if (tr->has_spare) CK(pool, cudaMemcpyAsync(tr->has_spare, hc.has_spare, H, cudaMemcpyDeviceToHost, st));
+    if (tr->spare_mem) CK(pool, cudaMemcpyAsync(tr->spare_mem, hc.spare_mem, sizeof(double) * H, cudaMemcpyDeviceToHost, st));
+    if (tr->spare_cpus) CK(pool, cudaMemcpyAsync(tr->spare_cpus, hc.spare_cpus, sizeof(double) * H, cudaMemcpyDeviceToHost, st));
+    if (tr->spare_gpus) CK(pool, cudaMemcpyAsync(tr->spare_gpus, hc.spare_gpus, sizeof(double) * H, cudaMemcpyDeviceToHost, st));
     CK(pool, cudaStreamSynchronize(st));
+    for (int p = 0; p < P; p++) {
+      if (hps[p].below_quota < 0) continue;   // the walk did not reach this job
+      if (tr->pending_dru) tr->pending_dru[p] = hps[p].pending_dru;
+      if (tr->below_quota) tr->below_quota[p] = hps[p].below_quota ? 1 : 0;
+    }
+    std::vector<int32_t> order;
+    for (int i = 0; i < n_tasks; i++) {
+      if (tr->task_dru) tr->task_dru[i] = hdru[i];
+      if (tr->task_alive) tr->task_alive[i] = halive[i];
+      if (halive[i]) order.push_back(i);
+    }
+    // priority-map order (:252-256): (-dru, user name); equal (dru, user): later position first (ours)
+    std::sort(order.begin(), order.end(), [&](int x, int y) {
+      if (hdru[x] != hdru[y]) return hdru[x] > hdru[y];
+      if (huser[x] != huser[y]) return users->name_rank[huser[x]] < users->name_rank[huser[y]];
+      return hpos[x] > hpos[y];
+    });
+    if (tr->order) for (size_t i = 0; i < order.size(); i++) tr->order[i] = order[i];
+    if (tr->n_order) *tr->n_order = (int32_t)order.size();
   }
   CK(pool, cudaEventRecord(pool->ev[15], st));
   CK(pool, cudaStreamSynchronize(st));
@@ -750,9 +958,30 @@ extern "C" int32_t cook_rebalance(cook_pool* pool, const cook_running_soa* runni
     ps.ms_device = ev_ms(pool->ev[13], pool->ev[14]);
     ps.ms_d2h = ev_ms(pool->ev[14], pool->ev[15]);
     ps.h2d_bytes = (int64_t)R * 60 + (int64_t)P * 48 + (int64_t)H * 48 + (int64_t)U * 60;
-    ps.d2h_bytes = (int64_t)n_dec * (int64_t)sizeof(cook_decision) + (int64_t)h_cnt[2] * 4;
-    ps.n_launches = 0;
+    ps.d2h_bytes = (int64_t)n_dec * (int64_t)sizeof(cook_decision) + (int64_t)h_cnt[2] * 4 + 20;
+    ps.n_launches = launches;
   }
   *out_n = n_dec;
   return COOK_OK;
+}
+
+extern "C" int32_t cook_rebalance(cook_pool* pool, const cook_running_soa* running,
+                                  const cook_jobs_soa* pending, const int64_t* pending_job_id,
+                                  const int32_t* pending_priority, const cook_host_table* hosts,
+                                  const cook_groups* groups, const cook_user_table* users,
+                                  const cook_rebalance_params* prm, cook_decision* out_decisions,
+                                  int32_t* out_victims, int32_t* out_n) {
+  return rebalance_run(pool, running, pending, pending_job_id, pending_priority, hosts, groups, users, prm,
+                       out_decisions, out_victims, out_n, nullptr);
+}
+
+extern "C" int32_t cook_rebalance_trace(cook_pool* pool, const cook_running_soa* running,
+                                        const cook_jobs_soa* pending, const int64_t* pending_job_id,
+                                        const int32_t* pending_priority, const cook_host_table* hosts,
+                                        const cook_groups* groups, const cook_user_table* users,
+                                        const cook_rebalance_params* prm, cook_decision* out_decisions,
+                                        int32_t* out_victims, int32_t* out_n, const cook_reb_trace* tr) {
+  if (!tr) return set_err(pool, COOK_E_BADARG, "cook_rebalance_trace: null trace");
+  return rebalance_run(pool, running, pending, pending_job_id, pending_priority, hosts, groups, users, prm,
+                       out_decisions, out_victims, out_n, tr);
 }

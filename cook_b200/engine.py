@@ -60,7 +60,7 @@ def load_library(path=None):
     for name in ("cook_gpu_init", "cook_gpu_shutdown", "cook_pool_open", "cook_pool_close",
                  "cook_last_error", "cook_rank", "cook_match", "cook_rebalance",
                  "cook_allgather_usage", "cook_last_stats", "cook_comm_unique_id", "cook_comm_init",
-                 "cook_comm_destroy", "cook_exchange_usage"):
+                 "cook_comm_destroy", "cook_exchange_usage", "cook_rebalance_trace"):
         getattr(lib, name).restype = C.c_int32
     return lib
 
@@ -157,6 +157,15 @@ class GpuEngine:
         return decisions_to_list(dec, vict, n.value)
 
 
+    def rebalance_trace(self, running, pending, pending_job_id, pending_priority, hosts, users, params,
+                        forced=None, forced_only=True, groups=None):
+        """cook_rebalance_trace: the same walk plus the rebalancer state the reference's own tests read
+        (K18 pending DRU, K21 next-state, job-below-quota).  forced: [(pending_idx, host, [victims],
+        mem, cpus, gpus)] applied with next-state instead of being searched."""
+        return rebalance_trace_call(
+            lambda *a: self.lib.cook_rebalance_trace(self.pool, *a), self._err,
+            running, pending, pending_job_id, pending_priority, hosts, users, params, forced, forced_only, groups)
+
     # -- phase timing / §8e exchange ----------------------------------------
     def last_stats(self, phase):
         ps = abi.PhaseStats()
@@ -191,6 +200,45 @@ def comm_init(lib, uid, rank, world, device):
     if rc != 0:
         raise CookError(rc, "cook_comm_init")
     return comm
+
+
+def rebalance_trace_call(fn, on_error, running, pending, pending_job_id, pending_priority, hosts, users, params,
+                         forced, forced_only, groups):
+    """Argument packing of cook_rebalance_trace (`fn` binds the handle; the test suite's CPU checker
+    exports the same signature and reuses this packing)."""
+    pj = np.ascontiguousarray(pending_job_id, np.int64)
+    pp = np.ascontiguousarray(pending_priority, np.int32)
+    mp = max(params.max_preemption, 1)
+    R, P, H = running.t.n, pending.n, hosts.n
+    dec = (abi.Decision * mp)()
+    vict = np.full(R + mp, -1, np.int32)
+    n = C.c_int32(0)
+    forced = forced or []
+    fdec = (abi.Decision * max(len(forced), 1))()
+    fv = []
+    for i, (pi, h, vs, m, c, g) in enumerate(forced):
+        fdec[i] = abi.Decision(pi, h, len(fv), len(vs), 0.0, m, c, g)
+        fv += list(vs)
+    fv = np.array(fv + [0], np.int32)
+    pdru, tdru = np.full(max(P, 1), np.nan), np.zeros(R + mp)
+    alive, order, n_order = np.zeros(R + mp, np.uint8), np.zeros(R + mp, np.int32), C.c_int32(0)
+    hs, sm, sc, sg = np.zeros(H, np.uint8), np.zeros(H), np.zeros(H), np.zeros(H)
+    below = np.full(max(P, 1), 255, np.uint8)
+    tr = abi.RebTrace(len(forced), fdec, abi.ptr(fv, abi.P_I32), abi.ptr(pdru, abi.P_F64),
+                      abi.ptr(tdru, abi.P_F64), abi.ptr(alive, abi.P_U8), abi.ptr(order, abi.P_I32),
+                      C.pointer(n_order), abi.ptr(hs, abi.P_U8), abi.ptr(sm, abi.P_F64),
+                      abi.ptr(sc, abi.P_F64), abi.ptr(sg, abi.P_F64), 1 if forced_only else 0,
+                      abi.ptr(below, abi.P_U8))
+    rc = fn(C.byref(running), C.byref(pending), abi.ptr(pj, abi.P_I64), abi.ptr(pp, abi.P_I32),
+            C.byref(hosts), C.byref(groups) if groups is not None else None, C.byref(users),
+            C.byref(params), dec, abi.ptr(vict, abi.P_I32), C.byref(n), C.byref(tr))
+    if rc != 0:
+        on_error(rc)
+    k = n_order.value
+    return {"decisions": decisions_to_list(dec, vict, n.value), "pending_dru": pdru[:P],
+            "below_quota": [bool(b) if b != 255 else None for b in below[:P]],
+            "order": [int(x) for x in order[:k]], "order_dru": [float(tdru[t]) for t in order[:k]],
+            "spare": {h: (float(sm[h]), float(sc[h]), float(sg[h])) for h in range(H) if hs[h]}}
 
 
 def decisions_to_list(dec, vict, n):

@@ -361,6 +361,32 @@ int32_t cook_rebalance(cook_pool* pool, const cook_running_soa* running,
                        cook_decision* out_decisions, int32_t* out_victims,
                        int32_t* out_n);
 
+/* Diagnostic twin of cook_rebalance: the same walk, plus the rebalancer STATE the reference's own
+ * tests read (test/cook/test/rebalancer.clj:115-196 compute-pending-default-job-dru, :813-988
+ * next-state, :1368-1397 job-below-quota).  `forced` decisions are applied with next-state instead
+ * of being searched, as those tests hand compute-next-state a decision.  All pointers optional.  */
+typedef struct {
+  int32_t n_forced;
+  const cook_decision* forced;    /* pending_idx, host, victim slice, dru/mem/cpus/gpus            */
+  const int32_t* forced_victims;  /* running-task indices, in selection (descending dru) order     */
+  double* pending_dru;            /* [pending->n]; untouched for jobs the walk did not reach      */
+  double* task_dru;               /* [running->t.n + max_preemption] after the last transition    */
+  uint8_t* task_alive;            /* same length                                                  */
+  int32_t* order;                 /* task->scored-task key order (priority map) afterwards        */
+  int32_t* n_order;
+  uint8_t* has_spare;             /* [hosts->n] host->spare-resources afterwards                  */
+  double *spare_mem, *spare_cpus, *spare_gpus;
+  int32_t forced_only;            /* 1: walk only the forced jobs; 0: forced jobs take their given
+                                     decision, every other pending job is searched as usual       */
+  uint8_t* below_quota;           /* [pending->n] job-below-quota for the jobs the walk reached   */
+} cook_reb_trace;
+int32_t cook_rebalance_trace(cook_pool* pool, const cook_running_soa* running,
+                             const cook_jobs_soa* pending, const int64_t* pending_job_id,
+                             const int32_t* pending_priority, const cook_host_table* hosts,
+                             const cook_groups* groups, const cook_user_table* users,
+                             const cook_rebalance_params* params, cook_decision* out_decisions,
+                             int32_t* out_victims, int32_t* out_n, const cook_reb_trace* trace);
+
 /* ------------------------------------------------------------ phase timing */
 /* Device-side timing of the last call of each kind on this handle (CUDA events on the
  * pool's stream): what bench.py's `phases` block and roofline lines are computed from. */

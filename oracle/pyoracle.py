@@ -11,7 +11,7 @@ import subprocess
 import numpy as np
 
 from cook_b200 import abi
-from cook_b200.engine import _CallShapes, _empty_tasks, decisions_to_list
+from cook_b200.engine import _CallShapes, _empty_tasks, decisions_to_list, rebalance_trace_call
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcookoracle.so")
@@ -103,45 +103,8 @@ class OracleEngine:
         """Rebalancer state as the reference's own tests read it (K18 pending DRU, K21 next-state).
         forced: [(pending_idx, host, [victims], mem, cpus, gpus)] applied with next-state instead
         of searching."""
-        class Trace(C.Structure):
-            _fields_ = [("n_forced", C.c_int32), ("forced", C.POINTER(abi.Decision)),
-                        ("forced_victims", abi.P_I32), ("pending_dru", abi.P_F64),
-                        ("task_dru", abi.P_F64), ("task_alive", abi.P_U8), ("order", abi.P_I32),
-                        ("n_order", C.POINTER(C.c_int32)), ("has_spare", abi.P_U8),
-                        ("spare_mem", abi.P_F64), ("spare_cpus", abi.P_F64), ("spare_gpus", abi.P_F64),
-                        ("forced_only", C.c_int32), ("below_quota", abi.P_U8)]
-        pj = np.ascontiguousarray(pending_job_id, np.int64)
-        pp = np.ascontiguousarray(pending_priority, np.int32)
-        mp = max(params.max_preemption, 1)
-        R, P, H = running.t.n, pending.n, hosts.n
-        dec = (abi.Decision * mp)()
-        vict = np.full(R + mp, -1, np.int32)
-        n = C.c_int32(0)
-        forced = forced or []
-        fdec = (abi.Decision * max(len(forced), 1))()
-        fv = []
-        for i, (pi, h, vs, m, c, g) in enumerate(forced):
-            fdec[i] = abi.Decision(pi, h, len(fv), len(vs), 0.0, m, c, g)
-            fv += list(vs)
-        fv = np.array(fv + [0], np.int32)
-        pdru, tdru = np.zeros(P), np.zeros(R + mp)
-        alive, order, n_order = np.zeros(R + mp, np.uint8), np.zeros(R + mp, np.int32), C.c_int32(0)
-        hs, sm, sc, sg = np.zeros(H, np.uint8), np.zeros(H), np.zeros(H), np.zeros(H)
-        below = np.full(max(P, 1), 255, np.uint8)
-        tr = Trace(len(forced), fdec, abi.ptr(fv, abi.P_I32), abi.ptr(pdru, abi.P_F64),
-                   abi.ptr(tdru, abi.P_F64), abi.ptr(alive, abi.P_U8), abi.ptr(order, abi.P_I32),
-                   C.pointer(n_order), abi.ptr(hs, abi.P_U8), abi.ptr(sm, abi.P_F64),
-                   abi.ptr(sc, abi.P_F64), abi.ptr(sg, abi.P_F64), 1 if forced_only else 0,
-                   abi.ptr(below, abi.P_U8))
-        rc = self.lib.oracle_rebalance_trace(int(self.dru_mode), C.byref(running), C.byref(pending),
-                                             abi.ptr(pj, abi.P_I64), abi.ptr(pp, abi.P_I32),
-                                             C.byref(hosts), C.byref(groups) if groups is not None else None,
-                                             C.byref(users), C.byref(params), dec,
-                                             abi.ptr(vict, abi.P_I32), C.byref(n), C.byref(tr))
-        if rc != 0:
+        def err(rc):
             raise RuntimeError(f"oracle_rebalance_trace rc={rc}")
-        k = n_order.value
-        return {"decisions": decisions_to_list(dec, vict, n.value), "pending_dru": pdru,
-                "below_quota": [bool(b) if b != 255 else None for b in below[:P]],
-                "order": [int(x) for x in order[:k]], "order_dru": [float(tdru[t]) for t in order[:k]],
-                "spare": {h: (float(sm[h]), float(sc[h]), float(sg[h])) for h in range(H) if hs[h]}}
+        return rebalance_trace_call(
+            lambda *a: self.lib.oracle_rebalance_trace(int(self.dru_mode), *a), err,
+            running, pending, pending_job_id, pending_priority, hosts, users, params, forced, forced_only, groups)

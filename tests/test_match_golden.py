@@ -96,3 +96,10 @@ def test_rebalance_balanced_and_quota_golden_oracle(oracle):
     with a host already preempted in the cycle) and the over-quota rule (dru 100.0, own task)."""
     import rebalance_constraint_golden
     assert rebalance_constraint_golden.check_balanced_and_quota(oracle) == 3
+
+
+@pytest.mark.gpu
+def test_rebalance_balanced_and_quota_golden_gpu(gpu):
+    """K20, second half, through the CUDA path (cook_rebalance_trace applies the given first decision)."""
+    import rebalance_constraint_golden
+    assert rebalance_constraint_golden.check_balanced_and_quota(gpu) == 3

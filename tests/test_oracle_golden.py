@@ -54,7 +54,7 @@ def _pj(user, mem, cpus):
     return dict(user=user, mem=float(mem), cpus=float(cpus))
 
 
-def test_pending_job_dru_golden():
+def check_pending_job_dru(eng):
     """K18: test/cook/test/rebalancer.clj:115-157 compute-pending-default-job-dru = 1.92 / 0.8 / 2.6.
     (`:ucpus` in job4 and job11 is not a create-dummy-job key, so those jobs get the default 1.0
     cpus, testutil.clj:234-253.)  The GPU-mode half (:159-203) has no rebalancer behaviour to
@@ -65,10 +65,19 @@ def test_pending_job_dru_golden():
            _rj("wzhao", 8, 8, "h"), _rj("wzhao", 10, 10, "h"), _rj("wzhao", 10, 10, "h"), _rj("wzhao", 10, 10, "h")]
     pend = [_pj("wzhao", 10, 10), _pj("sunil", 20, 20), _pj("ljin", 10, 1)]
     inp = rebalance_inputs(_reb_case(run, pend, {}, min_dru_diff=1e9))   # nothing is preemptable: walk all jobs
-    out = OracleEngine().rebalance_trace(inp["running"], inp["pending"], inp["pending_job_id"],
-                                         inp["pending_priority"], inp["hosts"], inp["users"], inp["params"])
+    out = eng.rebalance_trace(inp["running"], inp["pending"], inp["pending_job_id"],
+                              inp["pending_priority"], inp["hosts"], inp["users"], inp["params"])
     assert out["decisions"] == []
     assert list(out["pending_dru"]) == [1.92, 0.8, 2.6]      # `(is (= 1.92 ...))`: exact
+
+
+def test_pending_job_dru_golden(oracle):
+    check_pending_job_dru(oracle)
+
+
+@pytest.mark.gpu
+def test_pending_job_dru_golden_gpu(gpu):
+    check_pending_job_dru(gpu)
 
 
 K21_RUN = [_rj("ljin", 10, 10, "hostA"), _rj("ljin", 5, 5, "hostA"), _rj("ljin", 15, 25, "hostB"),
@@ -87,8 +96,7 @@ K21 = [   # (cite, pending idx, host, victims, mem, cpus, expected key order, ex
 ]
 
 
-@pytest.mark.parametrize("k", K21, ids=[k[0] for k in K21])
-def test_next_state_golden(k):
+def check_next_state(eng, k):
     """K21: test/cook/test/rebalancer.clj:813-988 next-state: task->scored-task keys and scores and
     host->spare-resources after applying a given decision."""
     from golden_util import rebalance_inputs
@@ -96,15 +104,26 @@ def test_next_state_golden(k):
     cite, pidx, host, victims, mem, cpus, order, drus, spare = k
     inp = rebalance_inputs(_reb_case(K21_RUN, K21_PEND, {"hostA": (50.0, 50.0)}))
     hid = {h: i for i, h in enumerate(inp["hostnames"])}
-    out = OracleEngine().rebalance_trace(inp["running"], inp["pending"], inp["pending_job_id"],
-                                         inp["pending_priority"], inp["hosts"], inp["users"], inp["params"],
-                                         forced=[(pidx, hid[host], victims, mem, cpus, 0.0)])
+    out = eng.rebalance_trace(inp["running"], inp["pending"], inp["pending_job_id"],
+                              inp["pending_priority"], inp["hosts"], inp["users"], inp["params"],
+                              forced=[(pidx, hid[host], victims, mem, cpus, 0.0)])
     assert out["order"] == order, (cite, out["order"])
     assert np.allclose(out["order_dru"], drus, rtol=1e-12, atol=0), (cite, out["order_dru"])
     assert out["spare"] == {hid[h]: v for h, v in spare.items()}, (cite, out["spare"])
 
 
-def test_job_below_quota_golden():
+@pytest.mark.parametrize("k", K21, ids=[k[0] for k in K21])
+def test_next_state_golden(oracle, k):
+    check_next_state(oracle, k)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("k", K21, ids=[k[0] for k in K21])
+def test_next_state_golden_gpu(gpu, k):
+    check_next_state(gpu, k)
+
+
+def check_job_below_quota(eng):
     """test/cook/test/rebalancer.clj:1368-1397: testA has a count quota of 1 and one running task, so
     its waiting job is not below quota; testB (no quota) is."""
     from golden_util import rebalance_inputs
@@ -116,12 +135,21 @@ def test_job_below_quota_golden():
     users = abi.make_users(2, name_rank=np.arange(2, dtype=np.int32), div_mem=np.full(2, 25.0), div_cpus=np.full(2, 25.0),
                            div_gpus=np.ones(2), quota=dict(count=np.array([1.0, big]), cpus=np.full(2, big),
                                                            mem=np.full(2, big), gpus=np.full(2, big)))
-    out = OracleEngine().rebalance_trace(inp["running"], inp["pending"], inp["pending_job_id"],
-                                         inp["pending_priority"], inp["hosts"], users, inp["params"])
+    out = eng.rebalance_trace(inp["running"], inp["pending"], inp["pending_job_id"],
+                              inp["pending_priority"], inp["hosts"], users, inp["params"])
     assert out["below_quota"] == [False, True]
 
 
-def test_filter_offensive_jobs_golden():
+def test_job_below_quota_golden(oracle):
+    check_job_below_quota(oracle)
+
+
+@pytest.mark.gpu
+def test_job_below_quota_golden_gpu(gpu):
+    check_job_below_quota(gpu)
+
+
+def check_filter_offensive_jobs(eng):
     """R7, test/cook/test/scheduler/scheduler.clj:857-888: constraints {memory-gb 10, cpus 5}; a 12 GB
     job and a 6-cpu job are offensive, the 8 GB / 4 cpu job stays in the queue."""
     from cook_b200.engine import _empty_tasks
@@ -132,7 +160,16 @@ def test_filter_offensive_jobs_golden():
                              start_time=np.full(3, abi.INT64_MAX, np.int64), task_id=np.full(3, -1, np.int64),
                              job_id=np.arange(1, 4, dtype=np.int64), cpus=cpus, mem=mem)
     users = abi.make_users(1)
-    out = OracleEngine().rank(_empty_tasks(), pending, users, params=abi.RankParams(100, 1, 1024.0 * 10.0, 5.0))
+    out = eng.rank(_empty_tasks(), pending, users, params=abi.RankParams(100, 1, 1024.0 * 10.0, 5.0))
     assert list(out["ranked"]) == [2]
-    out = OracleEngine().rank(_empty_tasks(), pending, users, params=abi.RankParams(100, 0, 0.0, 0.0))
+    out = eng.rank(_empty_tasks(), pending, users, params=abi.RankParams(100, 0, 0.0, 0.0))
     assert sorted(out["ranked"]) == [0, 1, 2]
+
+
+def test_filter_offensive_jobs_golden(oracle):
+    check_filter_offensive_jobs(oracle)
+
+
+@pytest.mark.gpu
+def test_filter_offensive_jobs_golden_gpu(gpu):
+    check_filter_offensive_jobs(gpu)
