@@ -109,3 +109,53 @@ inline float ev_ms(cudaEvent_t a, cudaEvent_t b) {
   cudaEventElapsedTime(&ms, a, b);
   return ms;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Exact-grid fast path for the f64 running sums of the path (DRU prefix sums, quota filters).
+// The reference folds left to right (`reductions`, `reduce +`); a left fold is a serial chain.
+// When every addend is a multiple of 2^-10 and the total magnitude stays below 2^43, every partial
+// sum of every subset is exactly representable in f64, so ANY association produces the same bits
+// as the left fold - and a parallel scan is legal.  grid_check_kernel establishes that per call on
+// the device (no host round trip); the kernels take the scan path when it holds and keep the
+// serial, association-preserving chain otherwise (e.g. cpus = 0.1).  Datomic amounts in Cook are
+// MiB integers and cpus in halves in practice, so the fast path is the common one.
+struct GridFlag {
+  int bad;                      // != 0: some addend is off the 2^-10 grid (or not finite / too large)
+  unsigned long long max_bits;  // bit pattern of the largest |addend| (non-negative doubles order like their bits)
+};
+#ifdef __CUDACC__
+__device__ __forceinline__ bool grid_value_ok(double x) {
+  const double y = x * 1024.0;
+  return x >= 0.0 && x <= 1099511627776.0 && y == rint(y);
+}
+static __global__ void grid_check_kernel(const double* a, const double* b, const double* c, int n, GridFlag* f) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  bool bad = false;
+  double m = 0.0;
+  if (i < n) {
+    const double x = a ? a[i] : 0.0, y = b ? b[i] : 0.0, z = c ? c[i] : 0.0;
+    bad = !(grid_value_ok(x) && grid_value_ok(y) && grid_value_ok(z));
+    m = fmax(x, fmax(y, z));
+  }
+  const unsigned anyb = __ballot_sync(0xffffffffu, bad);
+  for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) {
+    if (anyb) atomicOr(&f->bad, 1);
+    if (m > 0.0) atomicMax(&f->max_bits, (unsigned long long)__double_as_longlong(m));
+  }
+}
+// the sums of `n` addends (plus a start value) are association-free
+__device__ __forceinline__ bool grid_exact(const GridFlag* f, long long n, double start = 0.0) {
+  if (!f || f->bad) return false;
+  const double m = __longlong_as_double((long long)f->max_bits);
+  return grid_value_ok(start) && ((double)(n + 1) * fmax(m, 1.0) + start) < 8796093022208.0;   // 2^43
+}
+__device__ __forceinline__ double warp_incl_scan(double x, const int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const double y = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= o) x = x + y;
+  }
+  return x;
+}
+#endif

@@ -1773,7 +1773,7 @@ __global__ void cons_seg_kernel(const int32_t* pos_by_user, const int32_t* ranke
 // user's queued jobs in queue order, starting from the user's running usage.
 __global__ void __launch_bounds__(128) cons_user_kernel(ConsArgs a, const int32_t* pos_by_user,
                                                         const int32_t* seg_start,
-                                                        const int32_t* seg_end, uint8_t* keep) {
+                                                        const int32_t* seg_end, uint8_t* keep, const GridFlag* gf) {
   const int u = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (u >= a.n_users) return;
@@ -1791,6 +1791,10 @@ __global__ void __launch_bounds__(128) cons_user_kernel(ConsArgs a, const int32_
     return;
   }
   int seen = 0;
+  // every partial sum exact (addends and start values on the 2^-10 grid, total below 2^43): a
+  // parallel scan yields the left fold's bits; otherwise the lane-serial chain keeps the association
+  const bool exact = grid_exact(gf, e - s, fmax(fmax(an, ac), fmax(am, ag))) && grid_value_ok(an) && grid_value_ok(ac) &&
+                     grid_value_ok(am) && grid_value_ok(ag);
   for (int base = s; base < e; base += 32) {
     int p = base + lane;
     double xc = 0, xm = 0, xg = 0;
@@ -1802,6 +1806,13 @@ __global__ void __launch_bounds__(128) cons_user_kernel(ConsArgs a, const int32_
     }
     double mc = 0, mm = 0, mg = 0, mn = 0;
     int cntn = min(32, e - base);
+    if (exact) {
+      mn = an + (double)(lane + 1);
+      mc = ac + warp_incl_scan(xc, lane); mm = am + warp_incl_scan(xm, lane); mg = ag + warp_incl_scan(xg, lane);
+      an = an + (double)cntn;
+      ac = __shfl_sync(0xffffffffu, mc, cntn - 1); am = __shfl_sync(0xffffffffu, mm, cntn - 1);
+      ag = __shfl_sync(0xffffffffu, mg, cntn - 1);
+    } else
     for (int l = 0; l < cntn; l++) {
       an = an + 1.0;
       ac = ac + __shfl_sync(0xffffffffu, xc, l);
@@ -2163,6 +2174,7 @@ struct MatchPlan {
   int32_t *d_perm = nullptr, *d_pos = nullptr, *d_tmp = nullptr, *d_seg_s = nullptr, *d_seg_e = nullptr;
   uint8_t* d_keep = nullptr;
   uint8_t* d_placed = nullptr;
+  GridFlag* d_gf = nullptr;
   int last_n_cons = 0;
   double *d_oc = nullptr, *d_om = nullptr, *d_orc = nullptr, *d_orm = nullptr;
   VmStatic* d_vs = nullptr;
@@ -2253,7 +2265,7 @@ static int32_t build_plan(cook_pool* pool, MatchPlan* mp, const int32_t* ranked_
   sz.add<int32_t>(n_ranked);
   for (int k = 0; k < 3; k++) sz.add<double>(J + 1);
   sz.add<int32_t>(J + 1); sz.add<int32_t>(J + 1);
-  sz.add<uint8_t>(J + 1); sz.add<uint8_t>(J + 1); sz.add<uint8_t>(J + 1);
+  sz.add<uint8_t>(J + 1); sz.add<uint8_t>(J + 1); sz.add<uint8_t>(J + 1); sz.add<GridFlag>(1);
   size_t csr_j = (jobs->novel_off ? jobs->novel_off[J] : 0) + 2 * (size_t)(jobs->attr_off ? jobs->attr_off[J] : 0) + n_memb;
   sz.add<int32_t>(4 * (size_t)(J + 2) + csr_j + 64);
   sz.add<double>(J + 1); sz.add<int32_t>(3 * (size_t)(J + 1)); sz.add<int64_t>(J + 1);
@@ -2392,6 +2404,7 @@ static int32_t build_plan(cook_pool* pool, MatchPlan* mp, const int32_t* ranked_
   mp->d_seg_e = ar.take<int32_t>(U + 1);
   mp->d_keep = ar.take<uint8_t>(n_ranked + 1);
   mp->d_placed = ar.take<uint8_t>(J + 1);
+  mp->d_gf = ar.take<GridFlag>(1);
   mp->d_cons = ar.take<int32_t>(NC + 1);
   mp->d_kc = ar.take<double>(NC + 1);
   mp->d_km = ar.take<double>(NC + 1);
@@ -2499,7 +2512,10 @@ static int32_t run_plan(cook_pool* pool, MatchPlan* mp, int32_t* out_considerabl
   for (long long w = csort::TILE; w < n_ranked; w <<= 1) launches++;
   cons_seg_kernel<<<(n_ranked + TB - 1) / TB, TB, 0, st>>>(mp->d_pos, ca.ranked, ca.jb.user, n_ranked,
                                                            mp->d_seg_s, mp->d_seg_e);
-  cons_user_kernel<<<(U + 3) / 4, 128, 0, st>>>(ca, mp->d_pos, mp->d_seg_s, mp->d_seg_e, mp->d_keep);
+  CK(pool, cudaMemsetAsync(mp->d_gf, 0, sizeof(GridFlag), st));
+  grid_check_kernel<<<(mp->J + TB - 1) / TB, TB, 0, st>>>(ca.jb.cpus, ca.jb.mem, ca.jb.gpus, mp->J, mp->d_gf);
+  cons_user_kernel<<<(U + 3) / 4, 128, 0, st>>>(ca, mp->d_pos, mp->d_seg_s, mp->d_seg_e, mp->d_keep, mp->d_gf);
+  launches++;
   if (ca.pool_q.enabled) {
     // global pool quota: an order-dependent f64 left fold over the survivors
     // (filter-sequential) => exact single-warp pass

@@ -116,7 +116,7 @@ struct UserCols {
 __global__ void __launch_bounds__(128) user_fold_kernel(
     const int32_t* __restrict__ idx, TaskCols t, UserCols uc, const int32_t* __restrict__ seg_start,
     const int32_t* __restrict__ seg_end, int n_users, int dru_mode, int max_over_quota,
-    double* __restrict__ dru_at, int32_t* n_kept_total) {
+    double* __restrict__ dru_at, int32_t* n_kept_total, const GridFlag* gf) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= n_users) return;
@@ -130,6 +130,8 @@ __global__ void __launch_bounds__(128) user_fold_kernel(
   __shared__ double fold_s[4][3][32];
   double (*fs)[32] = fold_s[threadIdx.x >> 5];
   double acc = 0.0;
+  double am = 0.0, ac = 0.0, ag = 0.0;   // carries of the scan path
+  const bool exact = grid_exact(gf, e - s);   // every partial sum is exact: a parallel scan gives the left fold's bits
   int over = 0;
   bool cut = false;
   int kept = 0;
@@ -141,17 +143,23 @@ __global__ void __launch_bounds__(128) user_fold_kernel(
       int ti = idx[p];
       xm = t.mem[ti]; xc = t.cpus[ti]; xg = t.gpus[ti];
     }
-    fs[0][lane] = xm; fs[1][lane] = xc; fs[2][lane] = xg;
-    __syncwarp();
-    int cntn = min(32, e - base);
-    if (lane < 3) {
-      double* row = fs[lane];
+    double mym, myc, myg;
+    if (exact) {
+      mym = am + warp_incl_scan(xm, lane); myc = ac + warp_incl_scan(xc, lane); myg = ag + warp_incl_scan(xg, lane);
+      am = __shfl_sync(0xffffffffu, mym, 31); ac = __shfl_sync(0xffffffffu, myc, 31); ag = __shfl_sync(0xffffffffu, myg, 31);
+    } else {
+      fs[0][lane] = xm; fs[1][lane] = xc; fs[2][lane] = xg;
+      __syncwarp();
+      int cntn = min(32, e - base);
+      if (lane < 3) {
+        double* row = fs[lane];
 #pragma unroll 8
-      for (int l = 0; l < cntn; l++) { acc = acc + row[l]; row[l] = acc; }
+        for (int l = 0; l < cntn; l++) { acc = acc + row[l]; row[l] = acc; }
+      }
+      __syncwarp();
+      mym = fs[0][lane]; myc = fs[1][lane]; myg = fs[2][lane];
+      __syncwarp();
     }
-    __syncwarp();
-    const double mym = fs[0][lane], myc = fs[1][lane], myg = fs[2][lane];
-    __syncwarp();
     // scheduler.clj:2057-2071: keep while #violating prefixes <= limit
     bool viol = false;
     if (p < e) {
@@ -203,10 +211,18 @@ constexpr int QF_TB = 256;
 
 // Σ running usage of the pool (scheduler.clj:2118-2123) in input order.
 __global__ void pool_usage_kernel(const double* cpus, const double* mem, const double* gpus, int R,
-                                  double* out4) {
-  // single warp, lane-serial fold => left-fold association
+                                  double* out4, const GridFlag* gf) {
+  // single warp, lane-serial fold => left-fold association (any association when the sums are exact)
   const int lane = threadIdx.x;
   double ac = 0.0, am = 0.0, ag = 0.0;
+  if (grid_exact(gf, R)) {
+    for (int i = lane; i < R; i += 32) { ac += cpus[i]; am += mem[i]; ag += gpus[i]; }
+    for (int o = 16; o > 0; o >>= 1) {
+      ac += __shfl_xor_sync(0xffffffffu, ac, o); am += __shfl_xor_sync(0xffffffffu, am, o); ag += __shfl_xor_sync(0xffffffffu, ag, o);
+    }
+    if (lane == 0) { out4[0] = (double)R; out4[1] = ac; out4[2] = am; out4[3] = ag; }
+    return;
+  }
   for (int base = 0; base < R; base += 32) {
     int i = base + lane;
     double xc = i < R ? cpus[i] : 0.0, xm = i < R ? mem[i] : 0.0, xg = i < R ? gpus[i] : 0.0;
@@ -243,10 +259,36 @@ __global__ void __launch_bounds__(QF_TB) qf_gather_kernel(QueueFilterArgs a) {
 // which leaves a sum unchanged); everything else is parallel.
 constexpr int QF_CH = 1024;
 __global__ void __launch_bounds__(QF_CH) qf_quota_kernel(QueueFilterArgs a, cook_pool_quota q,
-                                                         const double* usage4) {
+                                                         const double* usage4, const GridFlag* gf) {
   __shared__ double s[4][QF_CH];
   const int tid = threadIdx.x, n = *a.n_kept;
   const int chain = tid >> 5;                       // chain k runs on lane 0 of warp k
+  if (grid_exact(gf, n, fmax(fmax(usage4[0], usage4[1]), fmax(usage4[2], usage4[3]))) &&
+      grid_value_ok(usage4[0]) && grid_value_ok(usage4[1]) && grid_value_ok(usage4[2]) && grid_value_ok(usage4[3])) {
+    // every partial sum is exact: block-wide parallel scan of the four running sums, carried chunk to chunk
+    __shared__ double wsum[4][32];
+    const int lane = tid & 31, w = tid >> 5;
+    double carry[4] = {usage4[0], usage4[1], usage4[2], usage4[3]};
+    for (int base = 0; base < n; base += QF_CH) {
+      const int i = base + tid;
+      const bool f = i < n && a.flag[i];
+      double x[4] = {f ? 1.0 : 0.0, f ? a.xc[i] : 0.0, f ? a.xm[i] : 0.0, f ? a.xg[i] : 0.0};
+#pragma unroll
+      for (int k = 0; k < 4; k++) { x[k] = warp_incl_scan(x[k], lane); if (lane == 31) wsum[k][w] = x[k]; }
+      __syncthreads();
+      if (w < 4) { const double t = warp_incl_scan(wsum[w][lane], lane); wsum[w][lane] = t; }
+      __syncthreads();
+      bool ok = true;
+#pragma unroll
+      for (int k = 0; k < 4; k++) x[k] = carry[k] + ((w ? wsum[k][w - 1] : 0.0) + x[k]);
+      ok = x[0] <= q.count && x[1] <= q.cpus && x[2] <= q.mem && x[3] <= q.gpus;
+      if (f && !ok) a.flag[i] = 0;
+#pragma unroll
+      for (int k = 0; k < 4; k++) carry[k] = carry[k] + wsum[k][31];
+      __syncthreads();
+    }
+    return;
+  }
   double acc = (tid & 31) == 0 && chain < 4 ? usage4[chain] : 0.0;
   for (int base = 0; base < n; base += QF_CH) {
     const int i = base + tid, cnt = min(QF_CH, n - base);
@@ -378,7 +420,7 @@ extern "C" int32_t cook_rank(cook_pool* pool, const cook_tasks_soa* running,
   sz.add<double>(N + 1);                                 // dru by task (output)
   for (int k = 0; k < 3; k++) sz.add<double>(N + 1);     // queue-order requests
   sz.add<int32_t>(N + 1); sz.add<uint8_t>(N + 1);        // queue-order task index, flags
-  sz.add<int32_t>(N / QF_TB + 2);
+  sz.add<int32_t>(N / QF_TB + 2); sz.add<GridFlag>(1);
   CK(pool, ar.reserve(sz.off + 4096));
   ar.reset();
 
@@ -421,12 +463,16 @@ extern "C" int32_t cook_rank(cook_pool* pool, const cook_tasks_soa* running,
   double* d_dru_task = ar.take<double>(N + 1);
   if (!d_dru_task) return set_err(pool, COOK_E_OOM, "cook_rank: arena exhausted");
 
+  GridFlag* d_gf = ar.take<GridFlag>(1);
+  if (ar.failed) return set_err(pool, COOK_E_OOM, "cook_rank: arena exhausted");
+  CK(pool, cudaMemsetAsync(d_gf, 0, sizeof(GridFlag), st));
   CK(pool, cudaMemsetAsync(d_seg_start, 0, sizeof(int32_t) * U, st));
   CK(pool, cudaMemsetAsync(d_seg_end, 0, sizeof(int32_t) * U, st));
   CK(pool, cudaMemsetAsync(d_counters, 0, sizeof(int32_t) * 8, st));
 
   CK(pool, cudaEventRecord(pool->ev[9], st));
   const int TB = 256, nb = (N + TB - 1) / TB;
+  grid_check_kernel<<<nb, TB, 0, st>>>(d_cpus, d_mem, d_gpus, N, d_gf);
   iota_kernel<<<nb, TB, 0, st>>>(d_idx, N);
   CK(pool, csort::sort_indices(d_idx, d_tmp, N, LessUserTask{t, d_name_rank}, st));
   seg_bounds_kernel<<<nb, TB, 0, st>>>(d_idx, d_user, N, d_seg_start, d_seg_end, d_user_at);
@@ -435,7 +481,7 @@ extern "C" int32_t cook_rank(cook_pool* pool, const cook_tasks_soa* running,
     int blocks = (U + warps_per_block - 1) / warps_per_block;
     user_fold_kernel<<<blocks, warps_per_block * 32, 0, st>>>(
         d_idx, t, uc, d_seg_start, d_seg_end, U, pool->dru_mode, params->max_over_quota_jobs,
-        d_dru_at, d_counters);
+        d_dru_at, d_counters, d_gf);
   }
   iota_kernel<<<nb, TB, 0, st>>>(d_pos, N);
   CK(pool, csort::sort_indices(d_pos, d_tmp, N,
@@ -453,12 +499,12 @@ extern "C" int32_t cook_rank(cook_pool* pool, const cook_tasks_soa* running,
   if (!qa.blk_cnt) return set_err(pool, COOK_E_OOM, "cook_rank: arena exhausted");
   qf_gather_kernel<<<qnb, QF_TB, 0, st>>>(qa);
   if (pool_quota && pool_quota->enabled) {
-    pool_usage_kernel<<<1, 32, 0, st>>>(d_cpus, d_mem, d_gpus, R, d_pool_usage);
-    qf_quota_kernel<<<1, QF_CH, 0, st>>>(qa, *pool_quota, d_pool_usage);
+    pool_usage_kernel<<<1, 32, 0, st>>>(d_cpus, d_mem, d_gpus, R, d_pool_usage, d_gf);
+    qf_quota_kernel<<<1, QF_CH, 0, st>>>(qa, *pool_quota, d_pool_usage, d_gf);
   }
   if (group_quota && group_usage && group_quota->enabled) {
     CK(pool, cudaMemcpyAsync(d_pool_usage + 4, group_usage, sizeof(double) * 4, cudaMemcpyHostToDevice, st));
-    qf_quota_kernel<<<1, QF_CH, 0, st>>>(qa, *group_quota, d_pool_usage + 4);
+    qf_quota_kernel<<<1, QF_CH, 0, st>>>(qa, *group_quota, d_pool_usage + 4, d_gf);
   }
   qf_count_kernel<<<qnb, QF_TB, 0, st>>>(qa);
   qf_scan_kernel<<<1, 1024, 0, st>>>(qa, qnb);

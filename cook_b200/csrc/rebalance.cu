@@ -91,7 +91,8 @@ struct Refold {
 // (or of every user when rf == nullptr), restarted at the first slot that changed.
 __global__ void __launch_bounds__(128) user_dru_kernel(const int32_t* ord, RTasks t, const double* div_mem,
                                                        const double* div_cpus, const int32_t* seg_start,
-                                                       const int32_t* seg_end, int n_users, const Refold* rf) {
+                                                       const int32_t* seg_end, int n_users, const Refold* rf,
+                                                       const GridFlag* gf) {
   const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   const bool all = rf == nullptr || rf->all;
@@ -110,6 +111,7 @@ __global__ void __launch_bounds__(128) user_dru_kernel(const int32_t* ord, RTask
   const double md = div_mem[u], cd = div_cpus[u];
   double am = 0.0, ac = 0.0;
   if (f > s) { int j = ord[f - 1]; am = t.cm[j]; ac = t.cc[j]; }
+  const bool exact = grid_exact(gf, e - s);
   for (int base = f; base < e; base += 32) {
     int p = base + lane;
     int i = p < e ? ord[p] : -1;
@@ -117,6 +119,10 @@ __global__ void __launch_bounds__(128) user_dru_kernel(const int32_t* ord, RTask
     double xm = live ? t.mem[i] : 0.0, xc = live ? t.cpus[i] : 0.0;
     double mym = 0.0, myc = 0.0;
     int cntn = min(32, e - base);
+    if (exact) {   // association-free sums: parallel scan
+      mym = am + warp_incl_scan(xm, lane); myc = ac + warp_incl_scan(xc, lane);
+      am = __shfl_sync(0xffffffffu, mym, 31); ac = __shfl_sync(0xffffffffu, myc, 31);
+    } else
     for (int l = 0; l < cntn; l++) {
       am = am + __shfl_sync(0xffffffffu, xm, l);
       ac = ac + __shfl_sync(0xffffffffu, xc, l);
@@ -215,6 +221,7 @@ struct SelArgs {
   RTasks t; int R; int n_tasks;             // synthetic tasks are R .. n_tasks-1
   HostCols hc; PendCols pc; const int32_t* user_rank;
   const PendScalars* ps; double min_diff, safe;
+  const int32_t* syn_cnt;   // per host: synthetic tasks (jobs placed by earlier decisions) living there
 };
 
 // P3 for one host, one warp: [spare ; victims by desc dru] prefix sums in the
@@ -230,7 +237,8 @@ __device__ HostBest host_select(const SelArgs& a, int p, int h, int lane, int32_
   const int pu = a.pc.user[p];
   const bool below = a.ps->below_quota != 0;
   const double pend = a.ps->pending_dru;
-  const int s0 = a.hs[h], seg = a.he[h] - s0, n_items = seg + (a.n_tasks - a.R);
+  // the synthetic tasks are scanned only on the (few) hosts that hold one
+  const int s0 = a.hs[h], seg = a.he[h] - s0, n_items = seg + (a.syn_cnt[h] ? a.n_tasks - a.R : 0);
   auto item = [&](int k) -> int {
     int i = k < seg ? a.hord[s0 + k] : a.R + (k - seg);
     if (k >= seg && a.t.host[i] != h) return -1;
@@ -330,6 +338,8 @@ struct RebArgs {
   Refold* rf;
   PendScalars* ps_all;   // [P] scalars of every job the walk reached (below_quota = -1: not reached)
   int n_forced; const cook_decision* forced; const int32_t* forced_victims; int forced_only;
+  const GridFlag* gf;   // exact-grid flag of the task amounts (common.cuh)
+  int32_t* syn_cnt;     // [H]
 };
 
 // task <= synthetic pending task [-prio, Long/MAX, nil(-1), job id] (tools.clj:614-641) ?
@@ -382,6 +392,7 @@ __device__ void pending_scalars(const RebArgs& a, const int32_t* ord, const int3
   int below = 1;
   if (!(qn >= dmax && qc >= dmax && qm >= dmax && qg >= dmax)) {
     double an = 1.0, ac = pcpu, am = pm, ag = pg;  // (conj running-jobs p): p first
+    const bool exact = grid_exact(a.gf, e - s + 1) && grid_value_ok(pcpu) && grid_value_ok(pm) && grid_value_ok(pg);
     for (int base = s; base < e; base += 32) {
       const int q = base + lane;
       int i = q < e ? ord[q] : -1;
@@ -389,6 +400,14 @@ __device__ void pending_scalars(const RebArgs& a, const int32_t* ord, const int3
       const double xc = i >= 0 ? t.cpus[i] : 0.0, xm = i >= 0 ? t.mem[i] : 0.0, xg = i >= 0 ? t.gpus[i] : 0.0;
       const double xn = i >= 0 ? 1.0 : 0.0;
       const int cntn = min(32, e - base);
+      if (exact) {   // association-free sums: warp reduction
+        double rn = xn, rc = xc, rm = xm, rg = xg;
+        for (int o = 16; o > 0; o >>= 1) {
+          rn += __shfl_xor_sync(0xffffffffu, rn, o); rc += __shfl_xor_sync(0xffffffffu, rc, o);
+          rm += __shfl_xor_sync(0xffffffffu, rm, o); rg += __shfl_xor_sync(0xffffffffu, rg, o);
+        }
+        an += rn; ac += rc; am += rm; ag += rg;
+      } else
       for (int l = 0; l < cntn; l++) {
         an = an + __shfl_sync(0xffffffffu, xn, l);
         ac = ac + __shfl_sync(0xffffffffu, xc, l);
@@ -496,6 +515,7 @@ __global__ void __launch_bounds__(256) rebalance_kernel(RebArgs a) {
   const PendCols& pc = a.pc;
   RTasks t = a.t;
   int cur = 0, n_tasks = a.R, n_dec = 0;
+  long long tA = 0, tB = 0, tC = 0, tS = 0, t0 = clock64();   // CTA 0 / thread 0: cycles per phase (COOK_PROF)
   const bool forced_only = a.n_forced > 0 && a.forced_only != 0;
   const int n_walk = forced_only ? a.n_forced : a.P;
   for (int w = 0; w < n_walk && n_dec < a.MP; w++) {
@@ -514,7 +534,7 @@ __global__ void __launch_bounds__(256) rebalance_kernel(RebArgs a) {
     SelArgs sa;
     sa.hord = a.hord; sa.hs = a.hs; sa.he = a.he; sa.t = t; sa.R = a.R; sa.n_tasks = n_tasks;
     sa.hc = hc; sa.pc = pc; sa.user_rank = a.user_rank; sa.ps = &s_ps;
-    sa.min_diff = a.min_diff; sa.safe = a.safe;
+    sa.min_diff = a.min_diff; sa.safe = a.safe; sa.syn_cnt = a.syn_cnt;
     double bd = -1.0;
     int br = -1, bh = -1;
     if (fi < 0) {
@@ -539,7 +559,9 @@ __global__ void __launch_bounds__(256) rebalance_kernel(RebArgs a) {
       cb.dru = bd; cb.rank = br; cb.host = bh;
       a.cta_best[blockIdx.x] = cb;
     }
+    { const long long t1 = clock64(); tA += t1 - t0; t0 = t1; }
     grid.sync();
+    { const long long t1 = clock64(); tS += t1 - t0; t0 = t1; }
     // ---- B: argmax over the CTAs (max dru; ties -> greatest hostname), next-state
     if (blockIdx.x == 0 && warp == 0) {
       double d = -1.0;
@@ -604,6 +626,7 @@ __global__ void __launch_bounds__(256) rebalance_kernel(RebArgs a) {
           t.cpus[ni] = pc.cpus[p]; t.mem[ni] = pc.mem[p]; t.gpus[ni] = pc.gpus ? pc.gpus[p] : 0.0;
           t.host[ni] = h; t.alive[ni] = 1; t.dru[ni] = 0.0; t.pos[ni] = 0; t.cm[ni] = 0.0; t.cc[ni] = 0.0;
           a.has_task[h] = 1;
+          a.syn_cnt[h] += 1;
           hc.has_spare[h] = 1;
           hc.spare_mem[h] = b.mem - pc.mem[p];
           hc.spare_gpus[h] = b.gpus - (pc.gpus ? pc.gpus[p] : 0.0);
@@ -628,7 +651,9 @@ __global__ void __launch_bounds__(256) rebalance_kernel(RebArgs a) {
       }
       __threadfence();
     }
+    { const long long t1 = clock64(); tB += t1 - t0; t0 = t1; }
     grid.sync();
+    { const long long t1 = clock64(); tS += t1 - t0; t0 = t1; }
     n_dec = a.cnt[1];
     if (a.cnt[4] != 0) {
       // ---- C: next-state.  New order / segments go to the other buffer; the changed users are
@@ -666,6 +691,7 @@ __global__ void __launch_bounds__(256) rebalance_kernel(RebArgs a) {
         const double md = a.div_mem[u], cd = a.div_cpus[u];
         double am = 0.0, ac = 0.0;
         if (f > s) { const int j = new_at(f - 1); am = t.cm[j]; ac = t.cc[j]; }
+        const bool exact = grid_exact(a.gf, e - s);
         for (int base = f; base < e; base += 32) {
           const int pp = base + lane;
           const int i = pp < e ? new_at(pp) : -1;
@@ -673,6 +699,10 @@ __global__ void __launch_bounds__(256) rebalance_kernel(RebArgs a) {
           const double xm = live ? t.mem[i] : 0.0, xc = live ? t.cpus[i] : 0.0;
           double mym = 0.0, myc = 0.0;
           const int cntn = min(32, e - base);
+          if (exact) {   // association-free sums: parallel scan
+            mym = am + warp_incl_scan(xm, lane); myc = ac + warp_incl_scan(xc, lane);
+            am = __shfl_sync(0xffffffffu, mym, 31); ac = __shfl_sync(0xffffffffu, myc, 31);
+          } else
           for (int l = 0; l < cntn; l++) {
             am = am + __shfl_sync(0xffffffffu, xm, l);
             ac = ac + __shfl_sync(0xffffffffu, xc, l);
@@ -686,11 +716,14 @@ __global__ void __launch_bounds__(256) rebalance_kernel(RebArgs a) {
           }
         }
       }
+      { const long long t1 = clock64(); tC += t1 - t0; t0 = t1; }
       grid.sync();
+      { const long long t1 = clock64(); tS += t1 - t0; t0 = t1; }
       cur ^= 1;
       n_tasks = n_tasks + 1;
     }
   }
+  if (blockIdx.x == 0 && tid == 0) { a.cnt[8] = (int)(tA >> 10); a.cnt[9] = (int)(tB >> 10); a.cnt[10] = (int)(tC >> 10); a.cnt[11] = (int)(tS >> 10); }
 }
 
 }  // namespace
@@ -740,7 +773,7 @@ static int32_t rebalance_run(cook_pool* pool, const cook_running_soa* running,
   sz.add<PendScalars>(P + 4); sz.add<int32_t>(64);
   sz.add<int32_t>(CAP); sz.add<int32_t>(CAP + MP);               // second order buffer, preempted hosts
   for (int k = 0; k < 2; k++) sz.add<int32_t>(U + 1);            // second segment buffers
-  sz.add<CtaBest>(pool->sm_count + 8);
+  sz.add<CtaBest>(4 * pool->sm_count + 8); sz.add<GridFlag>(1); sz.add<int32_t>(H + 1);
   if (tr && tr->n_forced > 0) { sz.add<cook_decision>(tr->n_forced + 1); sz.add<int32_t>(CAP + MP); }
   CK(pool, ar.reserve(sz.off + (1 << 16)));
   ar.reset();
@@ -829,7 +862,7 @@ static int32_t rebalance_run(cook_pool* pool, const cook_running_soa* running,
   int32_t* d_hs = ar.take<int32_t>(H + 1); int32_t* d_he = ar.take<int32_t>(H + 1);
   uint8_t* d_has_task = ar.take<uint8_t>(H + 1);
   HostBest* d_best = ar.take<HostBest>(H + 1);
-  CtaBest* d_cta = ar.take<CtaBest>(pool->sm_count + 8);
+  CtaBest* d_cta = ar.take<CtaBest>(4 * pool->sm_count + 8);
   cook_decision* d_dec = ar.take<cook_decision>(MP + 1);
   int32_t* d_vict = ar.take<int32_t>(CAP + MP);
   int32_t* d_pre = ar.take<int32_t>(CAP + MP);
@@ -854,7 +887,14 @@ static int32_t rebalance_run(cook_pool* pool, const cook_running_soa* running,
     if (d_fvict && nfv > 0) CK(pool, cudaMemcpyAsync(d_fvict, tr->forced_victims, sizeof(int32_t) * nfv, cudaMemcpyHostToDevice, st));
   }
   if (ar.failed) return set_err(pool, COOK_E_OOM, "cook_rebalance: arena exhausted");
-  int32_t h_cnt[8] = {R, 0, 0, 0, 0, 0, 0, 0};
+  GridFlag* d_gf = ar.take<GridFlag>(1);
+  int32_t* d_syn = ar.take<int32_t>(H + 1);
+  if (ar.failed) return set_err(pool, COOK_E_OOM, "cook_rebalance: arena exhausted");
+  CK(pool, cudaMemsetAsync(d_gf, 0, sizeof(GridFlag), st));
+  CK(pool, cudaMemsetAsync(d_syn, 0, sizeof(int32_t) * (H + 1), st));
+  if (R > 0) grid_check_kernel<<<(R + 255) / 256, 256, 0, st>>>(t.cpus, t.mem, t.gpus, R, d_gf);
+  grid_check_kernel<<<(P + 255) / 256, 256, 0, st>>>(pc.cpus, pc.mem, pc.gpus, P, d_gf);
+  int32_t h_cnt[16] = {R, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   CK(pool, cudaMemcpyAsync(d_cnt, h_cnt, sizeof(h_cnt), cudaMemcpyHostToDevice, st));
   CK(pool, cudaMemsetAsync(d_ps, 0xff, sizeof(PendScalars) * (P + 4), st));   // below_quota -1, dru NaN: not reached
 
@@ -873,7 +913,7 @@ static int32_t rebalance_run(cook_pool* pool, const cook_running_soa* running,
     iota_r<<<(R + TB - 1) / TB, TB, 0, st>>>(d_ord, R);
     CK(pool, csort::sort_indices(d_ord, d_tmp, R, LessUser{t, d_urank}, st));
     user_seg_kernel<<<(R + TB - 1) / TB, TB, 0, st>>>(d_ord, t, R, d_us, d_ue);
-    user_dru_kernel<<<(U + 3) / 4, 128, 0, st>>>(d_ord, t, d_divm, d_divc, d_us, d_ue, U, nullptr);
+    user_dru_kernel<<<(U + 3) / 4, 128, 0, st>>>(d_ord, t, d_divm, d_divc, d_us, d_ue, U, nullptr, d_gf);
     iota_r<<<(R + TB - 1) / TB, TB, 0, st>>>(d_hord, R);
     CK(pool, csort::sort_indices(d_hord, d_tmp, R, LessHost{t}, st));
     host_seg_kernel<<<(R + TB - 1) / TB, TB, 0, st>>>(d_hord, t, R, d_hs, d_he);
@@ -892,14 +932,16 @@ static int32_t rebalance_run(cook_pool* pool, const cook_running_soa* running,
   ra.has_task = d_has_task; ra.preempted_hosts = d_pre;
   ra.min_diff = prm->min_dru_diff; ra.safe = prm->safe_dru_threshold; ra.host_lifetime_mins = prm->host_lifetime_mins;
   ra.best = d_best; ra.cta_best = d_cta; ra.dec = d_dec; ra.victims = d_vict; ra.cnt = d_cnt; ra.rf = d_rf;
-  ra.ps_all = d_ps;
+  ra.ps_all = d_ps; ra.gf = d_gf; ra.syn_cnt = d_syn;
   ra.n_forced = NF; ra.forced = d_forced; ra.forced_victims = d_fvict; ra.forced_only = tr ? tr->forced_only : 0;
   {
     int occ = 0;
     CK(pool, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rebalance_kernel, 256, 0));
     if (occ < 1) return set_err(pool, COOK_E_CUDA, "cook_rebalance: kernel does not fit on an SM");
-    // one CTA per SM is enough: the grid barrier is what the loop waits for, and it gets slower with more CTAs
-    int grid = std::min(pool->sm_count, std::max(1, (H + 7) / 8));
+    // a warp per host in the host phase: as many co-resident CTAs as help (<= 3 per SM)
+    int per_sm = 1;   // measured: more CTAs shorten the host phase but lengthen the barriers by as much
+    if (const char* e = getenv("COOK_REB_CTAS_PER_SM")) per_sm = std::max(1, std::min(occ, atoi(e)));
+    int grid = std::min(per_sm * pool->sm_count, std::max(1, (H + 7) / 8));
     void* kargs[] = {&ra};
     CK(pool, cudaLaunchCooperativeKernel((void*)rebalance_kernel, dim3(grid), dim3(256), kargs, 0, st));
     launches++;
@@ -907,6 +949,11 @@ static int32_t rebalance_run(cook_pool* pool, const cook_running_soa* running,
   CK(pool, cudaEventRecord(pool->ev[14], st));
   CK(pool, cudaMemcpyAsync(h_cnt, d_cnt, sizeof(int32_t) * 5, cudaMemcpyDeviceToHost, st));
   CK(pool, cudaStreamSynchronize(st));
+  if (getenv("COOK_PROF")) {
+    int32_t hp[4];
+    CK(pool, cudaMemcpy(hp, d_cnt + 8, sizeof(hp), cudaMemcpyDeviceToHost));
+    fprintf(stderr, "[cook_prof] rebalance kcycles (CTA 0): hosts %d  next-state %d  refold %d  grid-sync %d\n", hp[0], hp[1], hp[2], hp[3]);
+  }
   const int n_dec = h_cnt[1], n_tasks = h_cnt[0];
   if (n_dec > 0) {
     CK(pool, cudaMemcpyAsync(out_decisions, d_dec, sizeof(cook_decision) * n_dec, cudaMemcpyDeviceToHost, st));

@@ -182,3 +182,39 @@ def test_matcher_stress_repeated_cycles(oracle):
             else:
                 os.environ[k] = v
         eng.close()
+
+
+def test_off_grid_amounts_keep_the_left_fold(gpu, oracle):
+    """Amounts that are NOT on the binary grid (cpus 0.1, 0.3, ...): the association-free scan fast
+    path must not trigger; DRU scores, quota filters and rebalancer decisions stay bit-identical to
+    the oracle's left folds."""
+    rng = np.random.default_rng(123)
+    t = traces.gen_pool(61, 6000, 300, 25, 1500, cpus_choices=(0.1, 0.3, 0.7, 1.1, 2.9),
+                        mem_fn=lambda r, n: r.integers(1, 4000, size=n) / 7.0)
+    nu = 25
+    quota = {"count": rng.integers(50, 400, nu).astype(float), "cpus": rng.integers(20, 300, nu) + 0.1,
+             "mem": rng.integers(20000, 400000, nu) / 3.0, "gpus": np.full(nu, 1e9)}
+    usage = {k: t["users"].col("usage_" + k) for k in ("count", "cpus", "mem", "gpus")}
+    users = abi.make_users(nu, name_rank=t["users"].col("name_rank"), div_mem=t["users"].col("div_mem") / 3.0,
+                           div_cpus=t["users"].col("div_cpus") / 7.0, quota=quota, usage=usage)
+    pq = abi.make_pool_quota({"count": 3000, "cpus": 2500.3, "mem": 2.0e6 / 3.0, "gpus": 1e9})
+    prm_r = abi.RankParams(7, 0, 0.0, 0.0)
+    rg = gpu.rank(t["running"], t["pending"], users, pool_quota=pq, group_quota=pq, group_usage=np.array([3.0, 0.7, 11.0 / 7.0, 0.0]),
+                  params=prm_r)
+    ro = oracle.rank(t["running"], t["pending"], users, pool_quota=pq, group_quota=pq, group_usage=np.array([3.0, 0.7, 11.0 / 7.0, 0.0]),
+                     params=prm_r)
+    assert np.array_equal(rg["ranked"], ro["ranked"]) and _same_dru(rg["dru"], ro["dru"])
+    assert 0 < len(ro["ranked"]) < 6000
+    mg = gpu.match(ro["ranked"], t["jobs"], t["offers"], users, traces.match_params(6000), pool_quota=pq)
+    mo = oracle.match(ro["ranked"], t["jobs"], t["offers"], users, traces.match_params(6000), pool_quota=pq)
+    assert np.array_equal(mg["considerable"], mo["considerable"]) and np.array_equal(mg["assign"], mo["assign"])
+    r = traces.gen_rebalance(62, 8000, 60, 400, 80, max_preemption=20)
+    # knock the running tasks off the grid
+    rt = r["running"].col("t")
+    run2 = abi.RunningSoA(t=abi.make_tasks(user=rt.col("user"), priority=rt.col("priority"), start_time=rt.col("start_time"),
+                                           task_id=rt.col("task_id"), job_id=rt.col("job_id"),
+                                           cpus=rt.col("cpus") + 0.1, mem=rt.col("mem") / 3.0), host=r["running"].col("host"))
+    args = (run2, r["pending"], r["pending_job_id"], r["pending_priority"], r["hosts"], r["users"], r["params"])
+    dg = gpu.rebalance(*args, groups=r["groups"])
+    do = oracle.rebalance(*args, groups=r["groups"])
+    assert dg == do and len(do) > 0

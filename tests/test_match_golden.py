@@ -103,3 +103,17 @@ def test_rebalance_balanced_and_quota_golden_gpu(gpu):
     """K20, second half, through the CUDA path (cook_rebalance_trace applies the given first decision)."""
     import rebalance_constraint_golden
     assert rebalance_constraint_golden.check_balanced_and_quota(gpu) == 3
+
+
+def test_cycle_driver_golden_oracle(oracle):
+    """M5/M6: handle-resource-offers! as a whole (return value, launch-rate filter, reservations,
+    queue removal, scale-back) around the oracle."""
+    import cycle_golden_cases
+    assert cycle_golden_cases.check_state_machine()
+    assert cycle_golden_cases.check_all(oracle) == 9
+
+
+@pytest.mark.gpu
+def test_cycle_driver_golden_gpu(gpu):
+    import cycle_golden_cases
+    assert cycle_golden_cases.check_all(gpu) == 9
