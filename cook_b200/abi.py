@@ -166,6 +166,13 @@ class Decision(C.Structure):
                 ("gpus", C.c_double)]
 
 
+FAILC_N = 13
+
+
+class FailureCounts(C.Structure):
+    _fields_ = [("n_vms", C.c_int32), ("n_passed", C.c_int32), ("n_ports", C.c_int32), ("counts", C.c_int32 * FAILC_N)]
+
+
 class RebTrace(C.Structure):
     """cook_reb_trace (include/cook_gpu.h): rebalancer state as the reference's own tests read it."""
     _fields_ = [("n_forced", C.c_int32), ("forced", C.POINTER(Decision)),

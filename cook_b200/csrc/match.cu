@@ -2114,6 +2114,140 @@ __global__ void finalize_kernel(MatchArgs a, int32_t* out_assign, int32_t* out_p
   }
 }
 
+// ---- placement-failure summaries: why job k could not go to each VM at its turn.
+// One CTA per requested job; thread per VM.  The VM's state at the job's turn is rebuilt exactly:
+// a left fold, in queue order, over the earlier jobs of the cycle that were placed on it.
+__global__ void __launch_bounds__(256) explain_kernel(MatchArgs a, const int32_t* k_list, int n_list,
+                                                      cook_failure_counts* out) {
+  __shared__ int s_cnt[COOK_FAILC_N + 2];
+  const int k = k_list[blockIdx.x];
+  if (threadIdx.x < COOK_FAILC_N + 2) s_cnt[threadIdx.x] = 0;
+  __syncthreads();
+  if (k < 0 || k >= a.n_cons) {
+    if (threadIdx.x == 0) { cook_failure_counts z; memset(&z, 0, sizeof(z)); z.n_vms = -1; out[blockIdx.x] = z; }
+    return;
+  }
+  const int j = a.cons[k];
+  JobRegs r;
+  r.c = a.kc[k]; r.m = a.km[k]; r.j = j;
+  r.g = a.kg ? a.kg[k] : 0.0; r.ports = a.kports ? a.kports[k] : 0;
+  const bool has_cons = a.of.vc != nullptr && a.sb_words > 0;
+  const bool grp = has_cons && (a.kflags[k] & 1);
+  for (int v = threadIdx.x; v < a.of.O; v += blockDim.x) {
+    const VmStatic vs = a.of.vs[v];
+    double ac = 0.0, am = 0.0;
+    int an = 0, pu = 0;
+    for (int q = 0; q < k; q++)               // broadcast loads: every thread walks the same queue
+      if (a.assign[q] == v) { ac = ac + a.kc[q]; am = am + a.km[q]; an++; pu += a.kports ? a.kports[q] : 0; }
+    const bool no_c = ac + r.c > vs.lc, no_m = am + r.m > vs.lm;
+    bool no_p = false;
+    if (has_cons && r.ports > 0) no_p = r.ports > a.of.vc[v].ports_total - pu;
+    if (no_c) atomicAdd(&s_cnt[COOK_FAILC_CPUS], 1);
+    if (no_m) atomicAdd(&s_cnt[COOK_FAILC_MEM], 1);
+    if (no_p) atomicAdd(&s_cnt[COOK_FAILC_N + 1], 1);
+    if (no_c || no_m || no_p) continue;        // Fenzo evaluates constraints only when the resources fit
+    int first = -1;
+    if (has_cons) {
+      const JobDev& jb = a.jb;
+      const OfferDev& of = a.of;
+      const VmCons vc = of.vc[v];
+      const int gpu_n = vc.flags >> 8;
+      const bool k8s = vc.flags & VC_K8S;
+      if (jb.ckpt_location && jb.ckpt_location[j] >= 0 && vc.location != jb.ckpt_location[j]) first = 0;
+      if (first < 0 && jb.est_end_ms && jb.est_end_ms[j] >= 0 && vc.host_start >= 0) {
+        const long long death = 1000LL * vc.host_start + 60000LL * a.host_lifetime_mins;
+        if (!(jb.est_end_ms[j] < death)) first = 1;
+      }
+      if (first < 0 && jb.attr_off)
+        for (int q = jb.attr_off[j]; q < jb.attr_off[j + 1]; q++) {
+          const int col = jb.attr_col[q], val = jb.attr_val[q];
+          if (col < 0 || col >= of.n_attr_cols || val <= 0 || of.attr_v[(size_t)col * of.O + v] != val) { first = 2; break; }
+        }
+      if (first < 0 && jb.disk_request && jb.disk_request[j] >= 0.0 && k8s) {
+        const int want = jb.disk_type ? jb.disk_type[j] : -1;
+        double space = 0.0;
+        for (int i = 0; i < vc.disk_n; i++)
+          if (of.disk_type[vc.disk_lo + i] == want) { space = of.disk_space[vc.disk_lo + i]; break; }
+        if (!(space >= jb.disk_request[j])) first = 3;
+      }
+      if (first < 0) {
+        bool ok = true;
+        if (k8s) {
+          if (r.g > 0.0) {
+            const int want = jb.gpu_model ? jb.gpu_model[j] : -1;
+            double have = 0.0;
+            for (int i = 0; i < gpu_n; i++)
+              if (of.gpu_model[vc.gpu_lo + i] == want) { have = of.gpu_count[vc.gpu_lo + i]; break; }
+            ok = have == r.g && vc.run_count + an == 0;
+          } else ok = gpu_n == 0;
+        } else ok = r.g == 0.0;
+        if (!ok) first = 4;
+      }
+      if (first < 0 && jb.novel_off)
+        for (int q = jb.novel_off[j]; q < jb.novel_off[j + 1]; q++)
+          if (jb.novel_host[q] == vc.hostname_id) { first = 5; break; }
+      if (first < 0 && vc.max_tasks >= 0 && !(vc.num_tasks + an < vc.max_tasks)) first = 6;
+      if (first < 0 && (vc.flags & VC_RESERVED)) {
+        const int mine = jb.reserved_host ? jb.reserved_host[j] : -1;
+        if (mine != vc.hostname_id) first = 7;
+      }
+      if (first < 0 && grp) {
+        // group constraints against the cotasks Fenzo knew at the job's turn: running cotasks + members
+        // placed EARLIER in this cycle (rebuilt from the assignments of the jobs before k)
+        for (int q = jb.group_off[j]; q < jb.group_off[j + 1] && first < 0; q++) {
+          const int g = jb.group_idx[q];
+          const int kind = a.gr.kind[g];
+          const int c0 = a.gr.cot_off[g], c1 = a.gr.cot_off[g + 1];
+          const int col = a.gr.attr_col[g];
+          int tf = 0, n = 0, mn = 0x7fffffff, mx = 0, distinct = 0;
+          const int target = vm_attr(of, col, v);
+          auto member_vm = [&](int k2) -> int {   // VM of an earlier job of group g, or -1
+            if (!(a.kflags[k2] & 1) || a.assign[k2] < 0) return -1;
+            const int j2 = a.cons[k2];
+            for (int e = jb.group_off[j2]; e < jb.group_off[j2 + 1]; e++) if (jb.group_idx[e] == g) return a.assign[k2];
+            return -1;
+          };
+          if (kind == COOK_GROUP_UNIQUE) {
+            bool clash = false;
+            for (int c = c0; c < c1; c++) clash |= a.gr.cot_host[c] == vc.hostname_id;
+            for (int k2 = 0; k2 < k && !clash; k2++) clash = member_vm(k2) == v;
+            if (clash) first = 8;
+          } else {
+            // value frequencies over (running cotasks ++ earlier members): O(n^2) over a handful of values
+            int vals[64];   // members of one group known to Fenzo at the turn (cook_groups are small)
+            int nv = 0;
+            for (int c = c0; c < c1 && nv < 64; c++) vals[nv++] = a.gr.cot_attr[c];
+            for (int k2 = 0; k2 < k && nv < 64; k2++) { const int mv = member_vm(k2); if (mv >= 0) vals[nv++] = vm_attr(of, col, mv); }
+            n = nv;
+            for (int i = 0; i < n; i++) tf += vals[i] == target;
+            if (n > 0) {
+              if (kind == COOK_GROUP_ATTR_EQUALS) { if (tf == 0) first = 10; }
+              else if (tf != 0) {
+                for (int i = 0; i < n; i++) {
+                  int f = 0; bool fst = true;
+                  for (int e = 0; e < n; e++) if (vals[e] == vals[i]) { f++; if (e < i) fst = false; }
+                  if (fst) { distinct++; mn = min(mn, f); mx = max(mx, f); }
+                }
+                if (a.gr.minimum[g] > distinct) mn = 0;
+                if (!(mn == mx || tf < mx)) first = 9;
+              }
+            }
+          }
+        }
+      }
+    }
+    if (first >= 0) atomicAdd(&s_cnt[COOK_FAILC_FIRST_CONSTRAINT + first], 1);
+    else atomicAdd(&s_cnt[COOK_FAILC_N], 1);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    cook_failure_counts c;
+    c.n_vms = a.of.O; c.n_passed = s_cnt[COOK_FAILC_N]; c.n_ports = s_cnt[COOK_FAILC_N + 1];
+    for (int i = 0; i < COOK_FAILC_N; i++) c.counts[i] = s_cnt[i];
+    out[blockIdx.x] = c;
+  }
+}
+
 // ---- usage delta of a match round: jobs placed this cycle, per user
 __global__ void placed_flag_kernel(const int32_t* cons, const int32_t* out_assign, int n_cons, uint8_t* placed_job) {
   int k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -2766,5 +2900,33 @@ extern "C" int32_t cook_exchange_usage(cook_pool* pool, void* comm, int32_t worl
   ps.h2d_bytes = 0;
   ps.d2h_bytes = (int64_t)sizeof(double) * world * n_pad;
   ps.n_launches = launches;
+  return COOK_OK;
+}
+
+
+// §8f-3: per-job placement-failure counters of the last match on this handle.
+extern "C" int32_t cook_match_failures(cook_pool* pool, const int32_t* k_idx, int32_t n, cook_failure_counts* out) {
+  if (!pool || !k_idx || !out || n < 0) return set_err(pool, COOK_E_BADARG, "cook_match_failures: bad argument");
+  MatchPlan* mp = static_cast<MatchPlan*>(pool->match_plan);
+  if (!mp || !mp->valid || mp->last_n_cons <= 0)
+    return set_err(pool, COOK_E_BADARG, "cook_match_failures: no match round on this handle");
+  if (n == 0) return COOK_OK;
+  CK(pool, cudaSetDevice(pool->device));
+  cudaStream_t st = pool->stream;
+  int32_t* d_k = nullptr;
+  cook_failure_counts* d_out = nullptr;
+  CK(pool, cudaMalloc(&d_k, sizeof(int32_t) * n));
+  cudaError_t e = cudaMalloc(&d_out, sizeof(cook_failure_counts) * n);
+  if (e != cudaSuccess) { cudaFree(d_k); return set_err(pool, COOK_E_OOM, "cook_match_failures: out of memory"); }
+  cudaMemcpyAsync(d_k, k_idx, sizeof(int32_t) * n, cudaMemcpyHostToDevice, st);
+  MatchArgs ma = mp->ma;
+  ma.n_cons = mp->last_n_cons;
+  if (!mp->constr) ma.sb_words = 0;
+  explain_kernel<<<n, 256, 0, st>>>(ma, d_k, n, d_out);
+  cudaMemcpyAsync(out, d_out, sizeof(cook_failure_counts) * n, cudaMemcpyDeviceToHost, st);
+  e = cudaStreamSynchronize(st);
+  cudaFree(d_k);
+  cudaFree(d_out);
+  if (e != cudaSuccess) return set_err(pool, COOK_E_CUDA, "cook_match_failures: %s", cudaGetErrorString(e));
   return COOK_OK;
 }

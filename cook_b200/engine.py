@@ -60,7 +60,7 @@ def load_library(path=None):
     for name in ("cook_gpu_init", "cook_gpu_shutdown", "cook_pool_open", "cook_pool_close",
                  "cook_last_error", "cook_rank", "cook_match", "cook_rebalance",
                  "cook_allgather_usage", "cook_last_stats", "cook_comm_unique_id", "cook_comm_init",
-                 "cook_comm_destroy", "cook_exchange_usage", "cook_rebalance_trace"):
+                 "cook_comm_destroy", "cook_exchange_usage", "cook_rebalance_trace", "cook_match_failures"):
         getattr(lib, name).restype = C.c_int32
     return lib
 
@@ -138,6 +138,16 @@ class GpuEngine:
         return {"considerable": cons[:k].copy(), "assign": assign[:k].copy(),
                 "ports": ports[:k * max(max_ports, 1)].reshape(k, max(max_ports, 1)).copy(),
                 "fail": fail[:k].copy(), "stats": stats.as_dict()}
+
+    def match_failures(self, k_idx):
+        """cook_match_failures: per requested considerable job of the LAST match on this handle, the
+        per-reason host counts at the job's turn (see cook_b200.cycle.summarize_failures)."""
+        k = np.ascontiguousarray(k_idx, np.int32)
+        out = (abi.FailureCounts * max(len(k), 1))()
+        rc = self.lib.cook_match_failures(self.pool, abi.ptr(k, abi.P_I32), len(k), out)
+        if rc != 0:
+            self._err(rc)
+        return [{"n_vms": o.n_vms, "n_passed": o.n_passed, "n_ports": o.n_ports, "counts": list(o.counts)} for o in out[:len(k)]]
 
     # -- B1-B6 -------------------------------------------------------------
     def rebalance(self, running, pending, pending_job_id, pending_priority, hosts, users, params,

@@ -296,6 +296,28 @@ int32_t cook_match(cook_pool* pool, const int32_t* ranked_idx, int32_t n_ranked,
                    int32_t* out_assign, int32_t* out_ports, int32_t max_ports,
                    uint8_t* out_fail_reason, cook_match_stats* out_stats);
 
+/* Placement-failure summaries (fenzo_utils.clj:21-89, unscheduled.clj:77-107).
+ * For each requested considerable job k (index into the out_considerable order of the LAST cook_match
+ * on this handle) counts, over all offers, why the job could not go there AT ITS TURN - the VM
+ * state after every earlier job of the cycle was placed, exactly what Fenzo's TaskAssignmentResults
+ * of that scheduleOnce describe:
+ *   counts[COOK_FAILC_CPUS], counts[COOK_FAILC_MEM]  VMs whose cpus / mem did not suffice (a VM
+ *       short of both counts in both, like Fenzo's one AssignmentFailure per resource)
+ *   counts[COOK_FAILC_FIRST_CONSTRAINT + i]          VMs with enough resources whose FIRST failing
+ *       hard constraint was i, in Cook's evaluation order (constraints.clj:459-495):
+ *       checkpoint-locality, estimated-completion, user-defined, disk-host, gpu-host, novel-host,
+ *       max-tasks-per-host, rebalancer-reservation, unique / balanced / attribute-equals group
+ *   n_passed   VMs that failed nothing (0 for a job that stayed unplaced; ports shortage is a
+ *       resource failure without a message in Fenzo and is counted in n_ports only)            */
+enum { COOK_FAILC_CPUS = 0, COOK_FAILC_MEM = 1, COOK_FAILC_FIRST_CONSTRAINT = 2, COOK_FAILC_N = 13 };
+typedef struct {
+  int32_t n_vms;
+  int32_t n_passed;
+  int32_t n_ports;
+  int32_t counts[COOK_FAILC_N];
+} cook_failure_counts;
+int32_t cook_match_failures(cook_pool* pool, const int32_t* k_idx, int32_t n, cook_failure_counts* out);
+
 /* ---------------------------------------------------------------- rebalance */
 /* Running tasks with placement for the rebalancer (rebalancer.clj:222-266).  */
 typedef struct {

@@ -272,6 +272,8 @@ inline double csr_lookup(const int32_t* off, const int32_t* key, const double* v
 // One (job, VM) evaluation = Fenzo AssignableVirtualMachine.tryRequest:
 // resource fit, hard constraints, fitness (FENZO rules 3-4).  Returns fitness
 // (> 0) or 0.0 on failure; *res_fail set when the failure was a resource.
+thread_local int g_first_fail = -1;   // index of the first failing hard constraint of the last eval_pair (explain)
+inline double cfail(int i) { g_first_fail = i; return 0.0; }
 double eval_pair(const MatchState& s, int j, int v, bool* res_fail) {
   const cook_jobs_soa* jb = s.jobs;
   const cook_offers_soa* of = s.of;
@@ -282,31 +284,32 @@ double eval_pair(const MatchState& s, int j, int v, bool* res_fail) {
   int want_ports = jb->ports ? jb->ports[j] : 0;
   if (want_ports > s.ports_total[v] - s.ports_used[v]) return 0.0;
   *res_fail = false;
+  g_first_fail = -1;
   // FENZO 3b hard constraints, Cook's effective order (scheduler.clj:493-501,
   // constraints.clj:487-495): checkpoint-locality, estimated-completion,
   // user-defined, disk, gpu, novel-host, max-tasks-per-host, reservation, groups
   if (jb->ckpt_location && jb->ckpt_location[j] >= 0) {  // constraints.clj:201-240
     int loc = of->location ? of->location[v] : -1;
-    if (loc != jb->ckpt_location[j]) return 0.0;
+    if (loc != jb->ckpt_location[j]) return cfail(0);
   }
   if (jb->est_end_ms && jb->est_end_ms[j] >= 0 && of->host_start_time &&
       of->host_start_time[v] >= 0) {  // constraints.clj:385-401
     int64_t death = 1000 * of->host_start_time[v] + (int64_t)60 * 1000 * s.prm->host_lifetime_mins;
-    if (!(jb->est_end_ms[j] < death)) return 0.0;
+    if (!(jb->est_end_ms[j] < death)) return cfail(1);
   }
   if (jb->attr_off) {  // constraints.clj:355-376 user-defined EQUALS
     for (int k = jb->attr_off[j]; k < jb->attr_off[j + 1]; k++) {
       int col = jb->attr_col[k], val = jb->attr_val[k];
-      if (col < 0 || col >= of->n_attr_cols) return 0.0;
+      if (col < 0 || col >= of->n_attr_cols) return cfail(2);
       int hv = of->attr[(size_t)col * of->n + v];
-      if (val <= 0 || hv != val) return 0.0;
+      if (val <= 0 || hv != val) return cfail(2);
     }
   }
   bool k8s = of->is_k8s && of->is_k8s[v];
   if (jb->disk_request && jb->disk_request[j] >= 0.0 && k8s) {  // constraints.clj:164-186
     double space = csr_lookup(of->disk_off, of->disk_type, of->disk_space, v,
                               jb->disk_type ? jb->disk_type[j] : -1);
-    if (!(space >= jb->disk_request[j])) return 0.0;
+    if (!(space >= jb->disk_request[j])) return cfail(3);
   }
   {  // constraints.clj:122-157 gpu-host-constraint (always built)
     double g = jb->gpus ? jb->gpus[j] : 0.0;
@@ -315,26 +318,26 @@ double eval_pair(const MatchState& s, int j, int v, bool* res_fail) {
         double have = csr_lookup(of->gpu_off, of->gpu_model, of->gpu_count, v,
                                  jb->gpu_model ? jb->gpu_model[j] : -1);
         int on_vm = (of->run_count ? of->run_count[v] : 0) + s.asg_count[v];
-        if (!(have == g && on_vm == 0)) return 0.0;
+        if (!(have == g && on_vm == 0)) return cfail(4);
       } else {
         int nmodels = of->gpu_off ? of->gpu_off[v + 1] - of->gpu_off[v] : 0;
-        if (nmodels != 0) return 0.0;
+        if (nmodels != 0) return cfail(4);
       }
     } else if (!(g == 0.0)) {
-      return 0.0;
+      return cfail(4);
     }
   }
   if (jb->novel_off) {  // constraints.clj:68-94
     for (int k = jb->novel_off[j]; k < jb->novel_off[j + 1]; k++)
-      if (jb->novel_host[k] == of->hostname_id[v]) return 0.0;
+      if (jb->novel_host[k] == of->hostname_id[v]) return cfail(5);
   }
   if (of->max_tasks && of->max_tasks[v] >= 0) {  // constraints.clj:433-456
     int total = (of->num_tasks ? of->num_tasks[v] : 0) + s.asg_count[v];
-    if (!(total < of->max_tasks[v])) return 0.0;
+    if (!(total < of->max_tasks[v])) return cfail(6);
   }
   if (of->reserved && of->reserved[v]) {  // constraints.clj:242-252, scheduler.clj:645-653
     int mine = jb->reserved_host ? jb->reserved_host[j] : -1;
-    if (mine != of->hostname_id[v]) return 0.0;
+    if (mine != of->hostname_id[v]) return cfail(7);
   }
   if (jb->group_off && s.groups) {  // constraints.clj:586-678
     const cook_groups* gr = s.groups;
@@ -345,9 +348,9 @@ double eval_pair(const MatchState& s, int j, int v, bool* res_fail) {
       if (kind == COOK_GROUP_UNIQUE) {
         int h = of->hostname_id[v];
         for (int c = gr->cot_off[g]; c < gr->cot_off[g + 1]; c++)
-          if (gr->cot_hostname_id[c] == h) return 0.0;
+          if (gr->cot_hostname_id[c] == h) return cfail(8);
         for (int pv : placed)
-          if (of->hostname_id[pv] == h) return 0.0;
+          if (of->hostname_id[pv] == h) return cfail(8);
       } else {
         int col = gr->attr_col[g];
         auto vm_attr = [&](int vm) { return (col >= 0 && col < of->n_attr_cols) ? of->attr[(size_t)col * of->n + vm] : 0; };
@@ -362,11 +365,11 @@ double eval_pair(const MatchState& s, int j, int v, bool* res_fail) {
               int mn = std::numeric_limits<int>::max(), mx = 0;
               for (auto& kv : freq) { mn = std::min(mn, kv.second); mx = std::max(mx, kv.second); }
               if (gr->minimum[g] > (int)freq.size()) mn = 0;
-              if (!(mn == mx || it->second < mx)) return 0.0;
+              if (!(mn == mx || it->second < mx)) return cfail(9);
             }
           }
         } else {  // attribute-equals
-          if (!freq.empty() && freq.find(target) == freq.end()) return 0.0;
+          if (!freq.empty() && freq.find(target) == freq.end()) return cfail(10);
         }
       }
     }
@@ -445,6 +448,9 @@ int32_t oracle_considerable(const int32_t* ranked_idx, int32_t n_ranked,
 //  F6 on success the VM's assigned cpus/mem/ports/count advance; ports are the
 //     first n free ports scanning ranges in lease order.
 // ---------------------------------------------------------------------------
+struct ExplainReq { const int32_t* k_idx; int32_t n; cook_failure_counts* out; };
+static thread_local const ExplainReq* g_explain = nullptr;
+
 static int32_t oracle_match_impl(const int32_t* ranked_idx, int32_t n_ranked, const cook_jobs_soa* jobs,
                      const cook_offers_soa* offers, const cook_groups* groups,
                      const cook_user_table* users, const cook_pool_quota* pool_quota,
@@ -508,8 +514,31 @@ static int32_t oracle_match_impl(const int32_t* ranked_idx, int32_t n_ranked, co
         done.fetch_add(1, std::memory_order_release);
       }
     });
+  if (g_explain)
+    for (int q = 0; q < g_explain->n; q++) {
+      std::memset(&g_explain->out[q], 0, sizeof(cook_failure_counts));
+      g_explain->out[q].n_vms = (g_explain->k_idx[q] >= 0 && g_explain->k_idx[q] < nc) ? O : -1;
+    }
   for (int k = 0; k < nc; k++) {
     int j = out_considerable[k];
+    if (g_explain)   // fenzo_utils.clj:45-57: per VM, every short resource, else the first failing constraint
+      for (int q = 0; q < g_explain->n; q++) {
+        if (g_explain->k_idx[q] != k) continue;
+        cook_failure_counts& c = g_explain->out[q];
+        for (int v = 0; v < O; v++) {
+          const bool no_c = s.asg_cpus[v] + jobs->cpus[j] > offers->cpus[v];
+          const bool no_m = s.asg_mem[v] + jobs->mem[j] > offers->mem[v];
+          const bool no_p = (jobs->ports ? jobs->ports[j] : 0) > s.ports_total[v] - s.ports_used[v];
+          if (no_c) c.counts[COOK_FAILC_CPUS]++;
+          if (no_m) c.counts[COOK_FAILC_MEM]++;
+          if (no_p) c.n_ports++;
+          if (no_c || no_m || no_p) continue;
+          bool rf;
+          const double f = eval_pair(s, j, v, &rf);
+          if (f == 0.0 && g_first_fail >= 0) c.counts[COOK_FAILC_FIRST_CONSTRAINT + g_first_fail]++;
+          else c.n_passed++;
+        }
+      }
     if (T > 1) {
       done.store(0, std::memory_order_relaxed);
       cur_job.store(j, std::memory_order_relaxed);
@@ -586,6 +615,21 @@ int32_t oracle_match(const int32_t* ranked_idx, int32_t n_ranked, const cook_job
                      uint8_t* out_fail_reason, cook_match_stats* st) {
   return oracle_match_impl(ranked_idx, n_ranked, jobs, offers, groups, users, pool_quota, params,
                            out_considerable, out_assign, out_ports, max_ports, out_fail_reason, st, 1);
+}
+
+// TEST TWIN of cook_match_failures: the same match, counting at the requested jobs' turns.
+int32_t oracle_match_failures(const int32_t* ranked_idx, int32_t n_ranked, const cook_jobs_soa* jobs,
+                              const cook_offers_soa* offers, const cook_groups* groups,
+                              const cook_user_table* users, const cook_pool_quota* pool_quota,
+                              const cook_match_params* params, const int32_t* k_idx, int32_t n,
+                              cook_failure_counts* out) {
+  std::vector<int32_t> cons(std::max(1, params->num_considerable)), asg(std::max(1, params->num_considerable));
+  ExplainReq req{k_idx, n, out};
+  g_explain = &req;
+  int32_t rc = oracle_match_impl(ranked_idx, n_ranked, jobs, offers, groups, users, pool_quota, params, cons.data(),
+                                 asg.data(), nullptr, 0, nullptr, nullptr, 1);
+  g_explain = nullptr;
+  return rc;
 }
 
 int32_t oracle_match_mt(const int32_t* ranked_idx, int32_t n_ranked, const cook_jobs_soa* jobs,

@@ -98,6 +98,20 @@ class OracleEngine:
             raise RuntimeError(f"oracle_rebalance rc={rc}")
         return decisions_to_list(dec, vict, n.value)
 
+    def match_failures(self, ranked_idx, jobs, offers, users, params, k_idx, groups=None, pool_quota=None):
+        """Twin of GpuEngine.match + match_failures: the same match, counters at the requested turns."""
+        ranked_idx = np.ascontiguousarray(ranked_idx, np.int32)
+        pool_quota = pool_quota or abi.make_pool_quota(None)
+        k = np.ascontiguousarray(k_idx, np.int32)
+        out = (abi.FailureCounts * max(len(k), 1))()
+        self.lib.oracle_match_failures.restype = C.c_int32
+        rc = self.lib.oracle_match_failures(abi.ptr(ranked_idx, abi.P_I32), len(ranked_idx), C.byref(jobs), C.byref(offers),
+                                            C.byref(groups) if groups is not None else None, C.byref(users),
+                                            C.byref(pool_quota), C.byref(params), abi.ptr(k, abi.P_I32), len(k), out)
+        if rc != 0:
+            raise RuntimeError(f"oracle_match_failures rc={rc}")
+        return [{"n_vms": o.n_vms, "n_passed": o.n_passed, "n_ports": o.n_ports, "counts": list(o.counts)} for o in out[:len(k)]]
+
     def rebalance_trace(self, running, pending, pending_job_id, pending_priority, hosts, users, params,
                         forced=None, forced_only=True, groups=None):
         """Rebalancer state as the reference's own tests read it (K18 pending DRU, K21 next-state).

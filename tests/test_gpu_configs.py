@@ -218,3 +218,31 @@ def test_off_grid_amounts_keep_the_left_fold(gpu, oracle):
     dg = gpu.rebalance(*args, groups=r["groups"])
     do = oracle.rebalance(*args, groups=r["groups"])
     assert dg == do and len(do) > 0
+
+
+def test_placement_failure_summaries(gpu, oracle):
+    """per-reason host counts of unplaced (and a few placed) jobs AT THEIR TURN, through
+    the CUDA path, equal the oracle's counts from replaying the match; the summary has the
+    fenzo_utils.clj:45-57 shape."""
+    from cook_b200.cycle import CONSTRAINT_NAMES, summarize_failures
+    t = traces.gen_c3_pool(77, 6000, 400, 60, 1200, frac_group_jobs=0.25, group_size=(3, 12), frac_gpu_jobs=0.1,
+                           frac_gpu_nodes=0.3, frac_port_jobs=0.2)
+    ranked = oracle.rank(t["running"], t["pending"], t["users"])["ranked"]
+    prm = traces.match_params(6000, host_lifetime_mins=t["host_lifetime_mins"])
+    mg = gpu.match(ranked, t["jobs"], t["offers"], t["users"], prm, groups=t["groups"], max_ports=2)
+    unplaced = np.where(mg["assign"] < 0)[0]
+    placed = np.where(mg["assign"] >= 0)[0]
+    ks = np.concatenate([unplaced[:40], unplaced[-10:], placed[:5], placed[-5:]]).astype(np.int32)
+    fg = gpu.match_failures(ks)
+    fo = oracle.match_failures(ranked, t["jobs"], t["offers"], t["users"], prm, ks, groups=t["groups"])
+    assert fg == fo
+    seen = set()
+    for k, f in zip(ks, fg):
+        assert f["n_vms"] == 400
+        assert sum(f["counts"][2:]) + f["n_passed"] <= 400
+        if mg["assign"][k] < 0:
+            assert f["n_passed"] == 0               # an unplaced job failed on every VM
+        s = summarize_failures(f["counts"])
+        seen |= set(s.get("constraints", {}))
+        assert set(s) <= {"resources", "constraints"} and set(s.get("resources", {})) <= {"cpus", "mem"}
+    assert len(seen & set(CONSTRAINT_NAMES)) >= 3   # several kinds of constraint failure occur in the trace
