@@ -494,3 +494,29 @@ def add_constraints_fast(t, seed, *, n_attr_cols=8, attr_card=(3, 6, 24, 2, 2, 4
     t["groups"] = abi.Groups(n_groups=G, kind=kinds, attr_col=acols, minimum=mins, cot_off=cot_off,
                              cot_hostname_id=cot_host, cot_attr_val=cot_attr)
     return t["groups"]
+
+
+def dump_for_jvm(config, out_dir):
+    """Writes the C2 (or one pool of c3-c5) trace as little-endian column files + manifest.edn for
+    bench/jvm/run_reference.clj (the JVM harness that times the real Clojure + Fenzo path)."""
+    import os
+    os.makedirs(out_dir, exist_ok=True)
+    t = gen_c2() if config == "c2" else gen_config_pool(config, 0)
+    cols = {"pending_user": t["pending"].col("user"), "pending_cpus": t["pending"].col("cpus"),
+            "pending_mem": t["pending"].col("mem"), "pending_priority": t["pending"].col("priority"),
+            "running_user": t["running"].col("user"), "running_cpus": t["running"].col("cpus"),
+            "running_mem": t["running"].col("mem"), "offer_cpus": t["offers"].col("cpus"),
+            "offer_mem": t["offers"].col("mem"), "offer_name_rank": t["offers"].col("name_rank")}
+    for n, a in cols.items():
+        np.ascontiguousarray(a).astype(a.dtype.newbyteorder("<")).tofile(os.path.join(out_dir, n + ".bin"))
+    with open(os.path.join(out_dir, "manifest.edn"), "w") as f:
+        f.write("{:config \"%s\" :jobs %d :offers %d :users %d :running %d :num-considerable %d}\n" %
+                (config, t["jobs"].n, t["offers"].n, t["users"].n_users, t["running"].n, t["jobs"].n))
+
+
+if __name__ == "__main__":
+    import sys
+    if len(sys.argv) == 4 and sys.argv[1] == "--dump":
+        dump_for_jvm(sys.argv[2], sys.argv[3])
+    else:
+        print("usage: python -m cook_b200.traces --dump c2|c3|c4|c5 DIR")
