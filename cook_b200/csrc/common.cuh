@@ -104,6 +104,15 @@ inline cudaError_t upload(Arena& a, cudaStream_t s, const T* host, size_t n, T**
   return cudaMemcpyAsync(d, host, n * sizeof(T), cudaMemcpyHostToDevice, s);
 }
 
+// Host-side range check of an index column: a bad index from the shim must come back as
+// COOK_E_BADARG, not as an illegal-address fault that poisons the CUDA context of every pool.
+inline bool idx_in_range(const int32_t* col, size_t n, int32_t lo, int32_t hi_excl) {
+  if (!col) return true;
+  for (size_t i = 0; i < n; i++)
+    if (col[i] < lo || col[i] >= hi_excl) return false;
+  return true;
+}
+
 inline float ev_ms(cudaEvent_t a, cudaEvent_t b) {
   float ms = 0.f;
   cudaEventElapsedTime(&ms, a, b);

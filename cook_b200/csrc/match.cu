@@ -2830,6 +2830,15 @@ extern "C" int32_t cook_match(cook_pool* pool, const int32_t* ranked_idx, int32_
     return set_err(pool, COOK_E_BADARG, "cook_match: bad sizes");
   if (out_stats) memset(out_stats, 0, sizeof(*out_stats));
   if (n_ranked == 0 || NC == 0) return COOK_OK;
+  if (!params->reuse_resident) {   // index columns are dereferenced on the device: check them here
+    if (!idx_in_range(ranked_idx, n_ranked, 0, J)) return set_err(pool, COOK_E_BADARG, "cook_match: ranked_idx out of range");
+    if (!idx_in_range(jobs->user, J, 0, U)) return set_err(pool, COOK_E_BADARG, "cook_match: jobs.user out of range");
+    if (jobs->attr_off && !idx_in_range(jobs->attr_col, jobs->attr_off[J], 0, std::max(1, offers->n_attr_cols)))
+      return set_err(pool, COOK_E_BADARG, "cook_match: jobs.attr_col out of range");
+    if (!offers->name_rank && O > 0) return set_err(pool, COOK_E_BADARG, "cook_match: offers.name_rank required");
+    if (groups && !idx_in_range(groups->attr_col, groups->n_groups, -1, std::max(1, offers->n_attr_cols)))
+      return set_err(pool, COOK_E_BADARG, "cook_match: groups.attr_col out of range");
+  }
   CK(pool, cudaSetDevice(pool->device));
   if (!pool->match_plan) {
     pool->match_plan = new MatchPlan();

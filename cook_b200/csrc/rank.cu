@@ -400,6 +400,8 @@ extern "C" int32_t cook_rank(cook_pool* pool, const cook_tasks_soa* running,
     return set_err(pool, COOK_E_BADARG, "cook_rank: null argument");
   const int R = running->n, J = pending->n, N = R + J, U = users->n_users;
   if (R < 0 || J < 0 || U <= 0) return set_err(pool, COOK_E_BADARG, "cook_rank: bad sizes");
+  if (!idx_in_range(running->user, R, 0, U) || !idx_in_range(pending->user, J, 0, U))
+    return set_err(pool, COOK_E_BADARG, "cook_rank: task user index out of range");
   *out_n = 0;
   if (out_order_n) *out_order_n = 0;
   if (N == 0) return COOK_OK;

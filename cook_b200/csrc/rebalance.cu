@@ -747,6 +747,11 @@ static int32_t rebalance_run(cook_pool* pool, const cook_running_soa* running,
   const int MP = prm->max_preemption;
   *out_n = 0;
   if (P <= 0 || MP <= 0 || H <= 0) return COOK_OK;
+  if (!idx_in_range(running->t.user, R, 0, U) || !idx_in_range(pending->user, P, 0, U))
+    return set_err(pool, COOK_E_BADARG, "cook_rebalance: user index out of range");
+  if (!idx_in_range(running->host, R, 0, H)) return set_err(pool, COOK_E_BADARG, "cook_rebalance: running.host out of range");
+  if (groups && pending->group_off && !idx_in_range(pending->group_idx, pending->group_off[P], 0, groups->n_groups))
+    return set_err(pool, COOK_E_BADARG, "cook_rebalance: group index out of range");
   CK(pool, cudaSetDevice(pool->device));
   cudaStream_t st = pool->stream;
   Arena& ar = pool->arena;

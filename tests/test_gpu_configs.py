@@ -246,3 +246,24 @@ def test_placement_failure_summaries(gpu, oracle):
         seen |= set(s.get("constraints", {}))
         assert set(s) <= {"resources", "constraints"} and set(s.get("resources", {})) <= {"cpus", "mem"}
     assert len(seen & set(CONSTRAINT_NAMES)) >= 3   # several kinds of constraint failure occur in the trace
+
+
+def test_bad_index_columns_are_rejected_not_faulted(gpu):
+    """A bad index from the shim comes back as COOK_E_BADARG (-1); the context stays usable."""
+    from cook_b200.engine import CookError
+    t = traces.gen_pool(95, 500, 40, 9, 100)
+    ranked = gpu.rank(t["running"], t["pending"], t["users"])["ranked"]
+    bad = ranked.copy()
+    bad[3] = 10_000
+    with pytest.raises(CookError) as e:
+        gpu.match(bad, t["jobs"], t["offers"], t["users"], traces.match_params(500))
+    assert e.value.code == abi.COOK_E_BADARG
+    ju = t["jobs"].col("user").copy()
+    ju[7] = 99
+    jb = abi.JobsSoA(n=500, user=ju, cpus=t["jobs"].col("cpus"), mem=t["jobs"].col("mem"), gpus=t["jobs"].col("gpus"),
+                     ports=t["jobs"].col("ports"), allowed=t["jobs"].col("allowed"), plugin_accept=t["jobs"].col("plugin_accept"))
+    with pytest.raises(CookError) as e:
+        gpu.match(ranked, jb, t["offers"], t["users"], traces.match_params(500))
+    assert e.value.code == abi.COOK_E_BADARG
+    m = gpu.match(ranked, t["jobs"], t["offers"], t["users"], traces.match_params(500))   # still works
+    assert m["stats"]["n_considerable"] == len(ranked)
