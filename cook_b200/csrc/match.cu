@@ -148,6 +148,7 @@ struct MatchArgs {
   const int32_t* kports;   // gathered port counts per k
   int32_t* feas;           // [2][bmax] block + 1 once any VM is feasible for the row at the snapshot
   int vs_in_smem;          // evaluators keep the static VM table in shared memory
+  int sparse_ok;           // evaluators may score rows over the compacted live-VM lists (COOK_NO_SPARSE=1 disables)
   // constraint kernel: one bit per (row, VM) = "the VM passed every check at the row's snapshot"
   // (two blocks of rows, like `rows`); all checks only tighten within a cycle, so the resolver
   // re-evaluates a changed VM as bit && resources && the three count-dependent checks
@@ -503,10 +504,23 @@ struct EvalShared {
   int any[NW];
 };
 
+// Once most VMs are full, a row only has to look at the LIVE ones.  Per block every evaluator CTA
+// compacts the live VMs of each chunk (chunk = v mod 32 = lane) into a short list in shared
+// memory; when every list fits (SL_MAX entries) the rows of the block are scored over the lists
+// instead of over all tiles (rows of a saturated cluster: a handful of evaluations per thread).
+constexpr int SL_MAX = 64;        // live VMs per chunk in sparse mode
+constexpr int SBW_MAX = 1024;     // verdict-bit words staged in shared memory (sparse mode, constraint kernel)
+struct SparseLive {
+  unsigned short t[32][SL_MAX];   // tile index of the i-th live VM of chunk c: v = 32 * t + c
+  int cnt[32];
+  int maxc;                       // max over chunks; sparse mode iff maxc <= SL_MAX
+  unsigned sb[SBW_MAX];           // one row's verdict bits being assembled
+};
+
 template <bool CONSTR, bool PROF>
 __device__ void evaluate_row(const MatchArgs& a, const JobRegs& r, const bool grp, int blk, int ib,
                              const EvalStatic& es, EvalShared& E, const unsigned long long live,
-                             unsigned long long* ep) {
+                             unsigned long long* ep, SparseLive& SP, const bool sparse) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   long long e0 = PROF ? clock64() : 0;
   const double2* st2 = reinterpret_cast<const double2*>(a.of.vs);
@@ -521,7 +535,56 @@ __device__ void evaluate_row(const MatchArgs& a, const JobRegs& r, const bool gr
   int vv[TOPK];
 #pragma unroll
   for (int i = 0; i < TOPK; i++) { f[i] = 0.0; vv[i] = 0x7fffffff; }
-  {
+  if (sparse) {
+    if (CONSTR) {   // the row's verdict bits are assembled in shared memory (live VMs only; the rest is 0)
+      for (int wd = threadIdx.x; wd < a.sb_words; wd += NW * 32) SP.sb[wd] = 0u;
+      __syncthreads();
+    }
+    const int nl = SP.cnt[lane];
+    for (int i0 = warp; i0 < SP.maxc; i0 += 2 * NW) {   // warp-uniform trip count, two VMs in flight
+      VmState st[2];
+      int vq[2];
+#pragma unroll
+      for (int u = 0; u < 2; u++) {
+        const int i = i0 + u * NW;
+        vq[u] = i < nl ? 32 * (int)SP.t[lane][i] + lane : -1;
+        st[u].ac = st[u].am = st[u].yc = st[u].ym = st[u].lc = st[u].lm = st[u].rc = st[u].rm = 0.0;
+        st[u].an = st[u].pu = 0;
+        if (vq[u] >= 0) {
+          const int v = vq[u];
+          const double2 d0 = __ldcg(dy2 + 2 * v), d1 = __ldcg(dy2 + 2 * v + 1);
+          st[u].ac = d0.x; st[u].am = d0.y; st[u].yc = d1.x; st[u].ym = d1.y;
+          if (CONSTR) {
+            const int2 cn = __ldcg(reinterpret_cast<const int2*>(a.dyn.n[blk & 1] + v));
+            st[u].an = cn.x; st[u].pu = cn.y;
+          }
+          if (es.lc) { st[u].lc = es.lc[v]; st[u].lm = es.lm[v]; st[u].rc = es.rc[v]; st[u].rm = es.rm[v]; }
+          else {
+            const double2 s0 = __ldg(st2 + 2 * v), s1 = __ldg(st2 + 2 * v + 1);
+            st[u].lc = s0.x; st[u].lm = s0.y; st[u].rc = s1.x; st[u].rm = s1.y;
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 2; u++) {
+        const int v = vq[u];
+        double x = 0.0;
+        if (v >= 0) x = eval_vm<CONSTR>(a, r, v, st[u], false);
+        if (CONSTR && x > 0.0) atomicOr(&SP.sb[v >> 5], 1u << (v & 31));
+        // the lists are unordered: ties are resolved on v explicitly
+        if (x > 0.0 && better(x, v, f[TOPK - 1], vv[TOPK - 1])) {
+          f[TOPK - 1] = x; vv[TOPK - 1] = v;
+#pragma unroll
+          for (int i = TOPK - 1; i > 0; i--) {
+            if (better(f[i], vv[i], f[i - 1], vv[i - 1])) {
+              double tf = f[i]; f[i] = f[i - 1]; f[i - 1] = tf;
+              int tv = vv[i]; vv[i] = vv[i - 1]; vv[i - 1] = tv;
+            }
+          }
+        }
+      }
+    }
+  } else {
     const int O = a.of.O;
     constexpr int U = 4;  // VMs in flight per lane
     int ui = 0;  // index of the lane's VM (bit of `live`)
@@ -585,6 +648,8 @@ __device__ void evaluate_row(const MatchArgs& a, const JobRegs& r, const bool gr
   if (lane == 0) E.any[warp] = wany ? 1 : 0;
   long long e1 = PROF ? clock64() : 0;
   __syncthreads();
+  if (CONSTR && sparse)
+    for (int wd = threadIdx.x; wd < a.sb_words; wd += NW * 32) __stcg(sbrow + wd, SP.sb[wd]);
   // (2) warp w merges chunks w, w + NW, ...: the NW partial lists of a chunk (sorted, TOPK
   // each) are spread over the lanes, TOPK warp-argmax rounds emit the chunk's sorted list
   bool any = false;
@@ -1660,6 +1725,8 @@ __global__ void __launch_bounds__(RES_THREADS, 1) match_kernel(MatchArgs a) {
     }
     __shared__ int bk_s[2];
     __shared__ double smin_s[2];
+    SparseLive& SP = *reinterpret_cast<SparseLive*>(
+        smem_raw + ((sizeof(EvalShared) + 127) & ~size_t(127)) + (a.vs_in_smem ? (size_t)a.of.O * 32 : 0));
     if ((threadIdx.x >> 5) >= NW) return;  // only NW warps score rows (exited threads do not block the barriers)
     const int n_eval = gridDim.x - 1 - ns;
     const int ei = (int)blockIdx.x - 1 - ns;   // this evaluator's index
@@ -1709,6 +1776,26 @@ __global__ void __launch_bounds__(RES_THREADS, 1) match_kernel(MatchArgs a) {
           break;
         }
       }
+      // live VMs of every chunk compacted into shared memory; sparse mode when all lists fit
+      bool sparse = false;
+      if (a.of.O <= 64 * 32 * NW && a.sb_words <= SBW_MAX && a.sparse_ok) {
+        if (threadIdx.x < 32) SP.cnt[threadIdx.x] = 0;
+        __syncthreads();
+        const int ln = threadIdx.x & 31, wp = threadIdx.x >> 5;
+        for (unsigned long long m = live; m; m &= m - 1) {
+          const int u = __ffsll((long long)m) - 1;
+          const int pos = atomicAdd(&SP.cnt[ln], 1);
+          if (pos < SL_MAX) SP.t[ln][pos] = (unsigned short)(wp + NW * u);   // tile of VM 32 * (wp + NW * u) + ln
+        }
+        __syncthreads();
+        if (threadIdx.x < 32) {
+          int mx = SP.cnt[threadIdx.x];
+          for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+          if (threadIdx.x == 0) SP.maxc = mx;
+        }
+        __syncthreads();
+        sparse = SP.maxc <= SL_MAX;
+      }
       // the next row's job columns are fetched while this row is scored
       int k = k0 + ei;
       JobRegs rn;
@@ -1718,7 +1805,7 @@ __global__ void __launch_bounds__(RES_THREADS, 1) match_kernel(MatchArgs a) {
         const JobRegs r = rn;
         const bool grp = gn;
         if (k + n_eval < k1) { rn = load_job<CONSTR>(a, k + n_eval); gn = CONSTR && (a.kflags[k + n_eval] & 1); }
-        evaluate_row<CONSTR, PROF>(a, r, grp, b, k - k0, es, E, live, ep);
+        evaluate_row<CONSTR, PROF>(a, r, grp, b, k - k0, es, E, live, ep, SP, sparse);
       }
       wait += (unsigned long long)(w1 - w0);
       const unsigned long long dt = (unsigned long long)(clock64() - w1);
@@ -2703,10 +2790,10 @@ static int32_t run_plan(cook_pool* pool, MatchPlan* mp, int32_t* out_considerabl
       else ma.latest_global = mp->d_latest;
       // evaluator CTAs: the static VM table (4 f64 per VM, SoA) when it fits
       const size_t ev_base = (sizeof(EvalShared) + 127) & ~size_t(127);
-      smem = std::max(smem, ev_base);
-      ma.vs_in_smem = ev_base + (size_t)O * 32 <= 224 * 1024 ? 1 : 0;
+      ma.vs_in_smem = ev_base + (size_t)O * 32 + sizeof(SparseLive) <= 224 * 1024 ? 1 : 0;
       if (getenv("COOK_NO_SMEM_STATIC")) ma.vs_in_smem = 0;
-      if (ma.vs_in_smem) smem = std::max(smem, ev_base + (size_t)O * 32);
+      ma.sparse_ok = getenv("COOK_NO_SPARSE") ? 0 : 1;
+      smem = std::max(smem, ev_base + (ma.vs_in_smem ? (size_t)O * 32 : 0) + sizeof(SparseLive));
       void* kfn = mp->constr ? (prof_on ? (void*)match_kernel<true, true> : (void*)match_kernel<true, false>)
                              : (prof_on ? (void*)match_kernel<false, true> : (void*)match_kernel<false, false>);
       {
