@@ -1882,15 +1882,26 @@ __global__ void __launch_bounds__(128) cons_user_kernel(ConsArgs a, const int32_
   // parallel scan yields the left fold's bits; otherwise the lane-serial chain keeps the association
   const bool exact = grid_exact(gf, e - s, fmax(fmax(an, ac), fmax(am, ag))) && grid_value_ok(an) && grid_value_ok(ac) &&
                      grid_value_ok(am) && grid_value_ok(ag);
-  for (int base = s; base < e; base += 32) {
-    int p = base + lane;
-    double xc = 0, xm = 0, xg = 0;
-    int pos = -1;
-    if (p < e) {
-      pos = pos_by_user[p];
-      int j = a.ranked[pos];
-      xc = a.jb.cpus[j]; xm = a.jb.mem[j]; xg = a.jb.gpus ? a.jb.gpus[j] : 0.0;
-    }
+  for (int base0 = s; base0 < e; base0 += 128) {   // four chunks of gathers in flight
+   double xc4[4], xm4[4], xg4[4];
+   int pos4[4];
+#pragma unroll
+   for (int q = 0; q < 4; q++) {
+     const int p = base0 + 32 * q + lane;
+     xc4[q] = xm4[q] = xg4[q] = 0.0; pos4[q] = -1;
+     if (p < e) {
+       pos4[q] = pos_by_user[p];
+       const int j = a.ranked[pos4[q]];
+       xc4[q] = a.jb.cpus[j]; xm4[q] = a.jb.mem[j]; xg4[q] = a.jb.gpus ? a.jb.gpus[j] : 0.0;
+     }
+   }
+#pragma unroll
+   for (int q = 0; q < 4; q++) {
+    const int base = base0 + 32 * q;
+    if (base >= e) break;
+    const int p = base + lane;
+    const double xc = xc4[q], xm = xm4[q], xg = xg4[q];
+    const int pos = pos4[q];
     double mc = 0, mm = 0, mg = 0, mn = 0;
     int cntn = min(32, e - base);
     if (exact) {
@@ -1914,6 +1925,7 @@ __global__ void __launch_bounds__(128) cons_user_kernel(ConsArgs a, const int32_
     if (ok && limited && a.enforce_rate_limit) ok = false;
     if (p < e) keep[pos] = ok ? 1 : 0;
     seen += __popc(ob);
+   }
   }
 }
 
@@ -2343,26 +2355,45 @@ __global__ void placed_flag_kernel(const int32_t* cons, const int32_t* out_assig
 // warp per user: left fold over the user's queued jobs in queue order (pos_by_user), placed jobs only
 __global__ void __launch_bounds__(128) usage_delta_kernel(ConsArgs a, const int32_t* pos_by_user, const int32_t* seg_start,
                                                           const int32_t* seg_end, const uint8_t* placed_job,
-                                                          double* delta /* [n_users][4] */) {
+                                                          double* delta /* [n_users][4] */, const GridFlag* gf) {
   const int u = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (u >= a.n_users) return;
   const int s = seg_start[u], e = seg_end[u];
   double dn = 0.0, dc = 0.0, dm = 0.0, dg = 0.0;
-  for (int base = s; base < e; base += 32) {
-    const int p = base + lane;
-    double xn = 0.0, xc = 0.0, xm = 0.0, xg = 0.0;
-    if (p < e) {
-      const int j = a.ranked[pos_by_user[p]];
-      if (placed_job[j]) { xn = 1.0; xc = a.jb.cpus[j]; xm = a.jb.mem[j]; xg = a.jb.gpus ? a.jb.gpus[j] : 0.0; }
+  const bool exact = grid_exact(gf, e - s);
+  for (int base = s; base < e; base += 128) {   // four chunks of gathers in flight
+    double xn4[4], xc4[4], xm4[4], xg4[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const int p = base + 32 * q + lane;
+      xn4[q] = xc4[q] = xm4[q] = xg4[q] = 0.0;
+      if (p < e) {
+        const int j = a.ranked[pos_by_user[p]];
+        if (placed_job[j]) { xn4[q] = 1.0; xc4[q] = a.jb.cpus[j]; xm4[q] = a.jb.mem[j]; xg4[q] = a.jb.gpus ? a.jb.gpus[j] : 0.0; }
+      }
     }
-    const unsigned any = __ballot_sync(0xffffffffu, xn != 0.0);
-    for (unsigned m = any; m; m &= m - 1) {   // only the placed ones add (x + 0.0 == x anyway)
-      const int l = __ffs(m) - 1;
-      dn = dn + __shfl_sync(0xffffffffu, xn, l);
-      dc = dc + __shfl_sync(0xffffffffu, xc, l);
-      dm = dm + __shfl_sync(0xffffffffu, xm, l);
-      dg = dg + __shfl_sync(0xffffffffu, xg, l);
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      if (base + 32 * q >= e) break;
+      const double xn = xn4[q], xc = xc4[q], xm = xm4[q], xg = xg4[q];
+      if (exact) {   // association-free sums
+        double rn = xn, rc = xc, rm = xm, rg = xg;
+        for (int o = 16; o > 0; o >>= 1) {
+          rn += __shfl_xor_sync(0xffffffffu, rn, o); rc += __shfl_xor_sync(0xffffffffu, rc, o);
+          rm += __shfl_xor_sync(0xffffffffu, rm, o); rg += __shfl_xor_sync(0xffffffffu, rg, o);
+        }
+        dn += rn; dc += rc; dm += rm; dg += rg;
+      } else {
+        const unsigned any = __ballot_sync(0xffffffffu, xn != 0.0);
+        for (unsigned m = any; m; m &= m - 1) {   // only the placed ones add (x + 0.0 == x anyway)
+          const int l = __ffs(m) - 1;
+          dn = dn + __shfl_sync(0xffffffffu, xn, l);
+          dc = dc + __shfl_sync(0xffffffffu, xc, l);
+          dm = dm + __shfl_sync(0xffffffffu, xm, l);
+          dg = dg + __shfl_sync(0xffffffffu, xg, l);
+        }
+      }
     }
   }
   if (lane == 0) { delta[4 * u] = dn; delta[4 * u + 1] = dc; delta[4 * u + 2] = dm; delta[4 * u + 3] = dg; }
@@ -2973,7 +3004,7 @@ extern "C" int32_t cook_exchange_usage(cook_pool* pool, void* comm, int32_t worl
     const int TB = 256, nc = mp->last_n_cons;
     CK(pool, cudaMemsetAsync(mp->d_placed, 0, mp->J + 1, st));
     placed_flag_kernel<<<(nc + TB - 1) / TB, TB, 0, st>>>(mp->d_cons, mp->d_out_assign, nc, mp->d_placed);
-    usage_delta_kernel<<<(mp->U + 3) / 4, 128, 0, st>>>(mp->ca, mp->d_pos, mp->d_seg_s, mp->d_seg_e, mp->d_placed, d_local);
+    usage_delta_kernel<<<(mp->U + 3) / 4, 128, 0, st>>>(mp->ca, mp->d_pos, mp->d_seg_s, mp->d_seg_e, mp->d_placed, d_local, mp->d_gf);
     launches += 2;
     CK(pool, cudaGetLastError());
   }

@@ -136,13 +136,8 @@ __global__ void __launch_bounds__(128) user_fold_kernel(
   bool cut = false;
   int kept = 0;
   const double NaN = __longlong_as_double(0x7ff8000000000000LL);
-  for (int base = s; base < e; base += 32) {
-    int p = base + lane;
-    double xm = 0.0, xc = 0.0, xg = 0.0;
-    if (p < e) {
-      int ti = idx[p];
-      xm = t.mem[ti]; xc = t.cpus[ti]; xg = t.gpus[ti];
-    }
+  auto chunk = [&](const int base, const double xm, const double xc, const double xg) {
+    const int p = base + lane;
     double mym, myc, myg;
     if (exact) {
       mym = am + warp_incl_scan(xm, lane); myc = ac + warp_incl_scan(xc, lane); myg = ag + warp_incl_scan(xg, lane);
@@ -183,6 +178,28 @@ __global__ void __launch_bounds__(128) user_fold_kernel(
     kept += __popc(kb);
     over += __popc(vb);
     if (over > max_over_quota) cut = true;  // later batches are all beyond the cut
+  };
+  if (exact) {
+    // the gathers (idx -> amounts) are what a long segment waits for: four chunks in flight
+    for (int base = s; base < e; base += 128) {
+      double xm4[4], xc4[4], xg4[4];
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        const int p = base + 32 * q + lane;
+        xm4[q] = xc4[q] = xg4[q] = 0.0;
+        if (p < e) { const int ti = idx[p]; xm4[q] = t.mem[ti]; xc4[q] = t.cpus[ti]; xg4[q] = t.gpus[ti]; }
+      }
+#pragma unroll
+      for (int q = 0; q < 4; q++)
+        if (base + 32 * q < e) chunk(base + 32 * q, xm4[q], xc4[q], xg4[q]);
+    }
+  } else {
+    for (int base = s; base < e; base += 32) {
+      const int p = base + lane;
+      double xm = 0.0, xc = 0.0, xg = 0.0;
+      if (p < e) { const int ti = idx[p]; xm = t.mem[ti]; xc = t.cpus[ti]; xg = t.gpus[ti]; }
+      chunk(base, xm, xc, xg);
+    }
   }
   if (lane == 0 && kept) atomicAdd(n_kept_total, kept);
 }
