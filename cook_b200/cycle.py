@@ -220,3 +220,34 @@ def offers_from_cache(cache, hostname_ids, *, k8s=None):
                                 cpus=cpus, mem=mem, run_cpus=np.zeros(O), run_mem=np.zeros(O),
                                 run_count=np.zeros(O, np.int32), port_off=port_off, port_begin=port_begin,
                                 port_end=port_end, n_attr_cols=0, **kw)
+
+
+# ---- autoscaling job selection (scheduler.clj:1283-1335) --------------------------
+def max_jobs_for_autoscaling_scaled(number_considerable, number_unmatched, max_jobs_for_autoscaling, scale_factor):
+    """`(-> fraction-unmatched (* scale-factor) (min 1) (* max-jobs) int (max number-unmatched))` with
+    `fraction-unmatched = (/ (float unmatched) considerable)` (single precision, as in the reference)."""
+    frac = float(np.float32(number_unmatched) / np.float32(number_considerable)) if number_considerable > 0 else 0.0
+    return max(int(min(frac * scale_factor, 1.0) * max_jobs_for_autoscaling), number_unmatched)
+
+
+def autoscalable_jobs(engine, queue_after_match, jobs, users, *, number_considerable, number_unmatched,
+                      max_jobs_for_autoscaling=1000, scale_factor=1.0, pool_quota=None, enforce_rate_limit=0,
+                      recent_synthetic_pod_jobs=()):
+    """The quota-filtered prefix of the still-pending queue that autoscaling creates synthetic pods for:
+    `filter-pending-jobs-for-quota` (user quota -> launch-rate tokens -> pool quota, tools.clj:961-973)
+    over the queue WITHOUT the jobs just launched, `take` the scaled maximum, minus the jobs that got a
+    synthetic pod recently.  The filter is M0 without `job-allowed-to-start?` / the launch plugin, so it
+    runs on the device as a match against an EMPTY offer table (considerable set only, no matcher)."""
+    n = max_jobs_for_autoscaling_scaled(number_considerable, number_unmatched, max_jobs_for_autoscaling, scale_factor)
+    queue = np.ascontiguousarray(queue_after_match, np.int32)
+    if n <= 0 or len(queue) == 0:
+        return []
+    jk = {c: jobs.col(c) for c in ("user", "cpus", "mem", "gpus") if jobs.col(c) is not None}
+    plain = abi.JobsSoA(n=jobs.n, allowed=np.ones(jobs.n, np.uint8), plugin_accept=np.ones(jobs.n, np.uint8), **jk)
+    empty = abi.OffersSoA(n=0, hostname_id=np.zeros(1, np.int32), name_rank=np.zeros(1, np.int32), cpus=np.zeros(1),
+                          mem=np.zeros(1), run_cpus=np.zeros(1), run_mem=np.zeros(1), run_count=np.zeros(1, np.int32),
+                          n_attr_cols=0)
+    m = engine.match(queue, plain, empty, users, traces.match_params(min(n, len(queue)), enforce_rate_limit=enforce_rate_limit),
+                     pool_quota=pool_quota)
+    skip = set(recent_synthetic_pod_jobs)
+    return [int(j) for j in m["considerable"] if int(j) not in skip]

@@ -117,3 +117,28 @@ def check_state_machine():
     assert [l["hostname"] for l in c.expire(16_000)] == ["a"] and len(c.leases) == 1     # the first lease of a
     assert [l["hostname"] for l in c.expire(26_000)] == ["a"] and not c.leases
     return True
+
+
+def check_autoscaling(eng):
+    """SURVEY §8f-4 (scheduler.clj:1283-1335): the scaled maximum and the quota-filtered prefix."""
+    from cook_b200.cycle import autoscalable_jobs, max_jobs_for_autoscaling_scaled
+    # 20 % unmatched, scale factor 2.5, max 1000 -> 500; never fewer than the unmatched jobs themselves
+    assert max_jobs_for_autoscaling_scaled(100, 20, 1000, 2.5) == 500
+    assert max_jobs_for_autoscaling_scaled(100, 90, 1000, 2.5) == 1000
+    assert max_jobs_for_autoscaling_scaled(100, 90, 50, 1.0) == 90
+    assert max_jobs_for_autoscaling_scaled(0, 0, 1000, 2.5) == 0
+    # the eight K15 jobs of one user, quota {count 10 cpus 70 mem 32768}, usage {1, 2, 1024}: cpus run out after
+    # 3 + 13 + 7 + 11 + 5 + 19 = 58 (+2 used) <= 70, job-7 (1 cpu) and job-8 (2 cpus) still fit -> all eight;
+    # a quota of 40 cpus: job-5 would reach 41 > 40 - and filter-sequential advances the usage for rejected jobs too
+    # (tools.clj:654-668), so nothing after it passes either
+    q = np.arange(len(JOBS), dtype=np.int32)
+    got = autoscalable_jobs(eng, q, _jobs(), _users(), number_considerable=8, number_unmatched=8, max_jobs_for_autoscaling=100)
+    assert got == [0, 1, 2, 3, 4, 5, 6, 7]
+    got = autoscalable_jobs(eng, q, _jobs(), _users(quota=dict(count=10, cpus=40, mem=32768, gpus=10)),
+                            number_considerable=8, number_unmatched=8, max_jobs_for_autoscaling=100)
+    assert got == [0, 1, 2, 3]
+    # the queue after a match (jobs 0-3 launched), half unmatched, max 4 -> take 4 of the rest; recent synthetic pods dropped
+    got = autoscalable_jobs(eng, np.array([4, 5, 6, 7], np.int32), _jobs(), _users(), number_considerable=8, number_unmatched=4,
+                            max_jobs_for_autoscaling=4, scale_factor=1.0, recent_synthetic_pod_jobs=(5,))
+    assert got == [4, 6, 7]
+    return True

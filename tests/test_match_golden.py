@@ -111,9 +111,11 @@ def test_cycle_driver_golden_oracle(oracle):
     import cycle_golden_cases
     assert cycle_golden_cases.check_state_machine()
     assert cycle_golden_cases.check_all(oracle) == 9
+    assert cycle_golden_cases.check_autoscaling(oracle)
 
 
 @pytest.mark.gpu
 def test_cycle_driver_golden_gpu(gpu):
     import cycle_golden_cases
     assert cycle_golden_cases.check_all(gpu) == 9
+    assert cycle_golden_cases.check_autoscaling(gpu)
