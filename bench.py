@@ -227,7 +227,15 @@ def run_ours(args):
         # plane (here torch.distributed), everything else is libcookgpu + NCCL
         box = [comm_unique_id(lib) if rank == 0 else None]
         dist.broadcast_object_list(box, src=0)
-        comm = comm_init(lib, box[0], rank, world, local)
+        # NCCL announces its version on fd 1 at the first communicator: keep stdout to the one JSON line
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            comm = comm_init(lib, box[0], rank, world, local)
+        finally:
+            os.dup2(saved, 1)
+            os.close(saved)
 
     def barrier():
         torch.cuda.synchronize()
