@@ -216,12 +216,24 @@ __device__ __forceinline__ VKey vkey_shfl_xor(const VKey& k, int o) {
   return r;
 }
 
+// One packed record per running task IN HOST ORDER (position q of hord): everything the host phase
+// needs about a possible victim in three 128-bit loads, coalesced over the tasks of a host, instead
+// of five dependent gathers through the task index.  dru / pos are refreshed by the re-fold, a
+// victim's idx becomes -1.
+struct __align__(16) TaskHot {
+  double dru, mem, cpus, gpus;
+  int32_t urank, pos, idx, user;   // idx < 0: dead
+};
+
 struct SelArgs {
+  const TaskHot* hot;
   const int32_t* hord; const int32_t* hs; const int32_t* he;
   RTasks t; int R; int n_tasks;             // synthetic tasks are R .. n_tasks-1
   HostCols hc; PendCols pc; const int32_t* user_rank;
   const PendScalars* ps; double min_diff, safe;
   const int32_t* syn_cnt;   // per host: synthetic tasks (jobs placed by earlier decisions) living there
+  const int32_t* syn_head;  // per host: newest synthetic task (-1: none); chained through syn_next[task]
+  const int32_t* syn_next;
 };
 
 // P3 for one host, one warp: [spare ; victims by desc dru] prefix sums in the
@@ -238,7 +250,83 @@ __device__ HostBest host_select(const SelArgs& a, int p, int h, int lane, int32_
   const bool below = a.ps->below_quota != 0;
   const double pend = a.ps->pending_dru;
   // the synthetic tasks are scanned only on the (few) hosts that hold one
-  const int s0 = a.hs[h], seg = a.he[h] - s0, n_items = seg + (a.syn_cnt[h] ? a.n_tasks - a.R : 0);
+  const int s0 = a.hs[h], seg = a.he[h] - s0, n_syn = a.syn_cnt[h], n_items = seg + (n_syn ? a.n_tasks - a.R : 0);
+  if (seg + n_syn <= 64) {
+    // FAST PATH (almost every host): at most two tasks per lane, loaded once from the packed records and
+    // kept in registers over the sum pass and all selection rounds
+    double idru[2], imem[2], icpu[2], igpu[2];
+    int iur[2], ipos[2], iidx[2];
+    bool iok[2];
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+      const int k = lane + 32 * j;
+      iok[j] = false; idru[j] = imem[j] = icpu[j] = igpu[j] = 0.0; iur[j] = ipos[j] = 0; iidx[j] = -1;
+      if (k < seg + n_syn) {
+        int q = s0 + k;
+        if (k >= seg) {   // the (k - seg)-th synthetic task of the host: its record sits at its own index
+          q = a.syn_head[h];
+          for (int w = k - seg; w > 0; w--) q = a.syn_next[q];
+        }
+        const TaskHot r = a.hot[q];
+        idru[j] = r.dru; imem[j] = r.mem; icpu[j] = r.cpus; igpu[j] = r.gpus; iur[j] = r.urank; ipos[j] = r.pos; iidx[j] = r.idx;
+        iok[j] = r.idx >= 0 && (below || r.user == pu) && !(r.dru < a.safe) && ((r.dru - pend) > a.min_diff);
+      }
+    }
+    double sm = 0.0, sc = 0.0, sg = 0.0;
+    int nv = 0;
+    bool have = false;
+    double cur = 0.0;
+    auto consider = [&](double dru) {
+      if (sm >= pm && sc >= pcpu && (pg > 0.0 ? sg >= pg : true)) {
+        if (!have || dru >= cur) { have = true; cur = dru; b.dru = dru; b.mem = sm; b.cpus = sc; b.gpus = sg; b.n_victims = nv; }
+      }
+    };
+    if (a.hc.has_spare[h]) {
+      sg = sg + a.hc.spare_gpus[h]; sm = sm + a.hc.spare_mem[h]; sc = sc + a.hc.spare_cpus[h];
+      consider(1.7976931348623157e308);
+    }
+    if (!emit) {
+      double tm = (iok[0] ? imem[0] : 0.0) + (iok[1] ? imem[1] : 0.0), tc = (iok[0] ? icpu[0] : 0.0) + (iok[1] ? icpu[1] : 0.0),
+             tg = (iok[0] ? igpu[0] : 0.0) + (iok[1] ? igpu[1] : 0.0);
+      for (int o = 16; o > 0; o >>= 1) {
+        tm += __shfl_xor_sync(0xffffffffu, tm, o); tc += __shfl_xor_sync(0xffffffffu, tc, o);
+        tg += __shfl_xor_sync(0xffffffffu, tg, o);
+      }
+      const double slack = 1.0 + 1e-6;
+      if (!have && ((sm + tm) * slack < pm || (sc + tc) * slack < pcpu || (pg > 0.0 && (sg + tg) * slack < pg))) return b;
+    }
+    while (true) {
+      if (emit && nv >= n_emit) break;
+      VKey best;
+      best.idx = -1; best.dru = 0.0; best.urank = 0; best.pos = 0;
+      int bj = -1;
+#pragma unroll
+      for (int j = 0; j < 2; j++) {
+        if (!iok[j]) continue;
+        VKey c;
+        c.dru = idru[j]; c.urank = iur[j]; c.pos = ipos[j]; c.idx = iidx[j];
+        if (vkey_before(c, best)) { best = c; bj = j; }
+      }
+      const int mine = best.idx;
+      for (int o = 16; o > 0; o >>= 1) {
+        VKey other = vkey_shfl_xor(best, o);
+        if (vkey_before(other, best)) best = other;
+      }
+      if (best.idx < 0) break;
+      if (have && best.dru < cur) break;   // later prefixes only have smaller dru
+      // the owner of the winner supplies its amounts and retires the item
+      const bool won = mine == best.idx && bj >= 0;
+      const int wl = __ffs(__ballot_sync(0xffffffffu, won)) - 1;
+      double wm = 0.0, wc = 0.0, wg = 0.0;
+      if (won) { wm = bj ? imem[1] : imem[0]; wc = bj ? icpu[1] : icpu[0]; wg = bj ? igpu[1] : igpu[0]; if (bj) iok[1] = false; else iok[0] = false; }
+      wm = __shfl_sync(0xffffffffu, wm, wl); wc = __shfl_sync(0xffffffffu, wc, wl); wg = __shfl_sync(0xffffffffu, wg, wl);
+      sg = sg + wg; sm = sm + wm; sc = sc + wc;
+      if (emit && lane == 0) emit[n_emit - 1 - nv] = best.idx;
+      nv++;
+      consider(best.dru);
+    }
+    return b;
+  }
   auto item = [&](int k) -> int {
     int i = k < seg ? a.hord[s0 + k] : a.R + (k - seg);
     if (k >= seg && a.t.host[i] != h) return -1;
@@ -307,6 +395,17 @@ __device__ HostBest host_select(const SelArgs& a, int p, int h, int lane, int32_
   return b;
 }
 
+__global__ void hot_build_kernel(const int32_t* hord, RTasks t, const int32_t* user_rank, int n, TaskHot* hot, int32_t* hq) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n) return;
+  const int i = hord[q];
+  TaskHot r;
+  r.dru = t.dru[i]; r.mem = t.mem[i]; r.cpus = t.cpus[i]; r.gpus = t.gpus[i];
+  r.urank = user_rank[t.user[i]]; r.pos = t.pos[i]; r.idx = t.alive[i] ? i : -1; r.user = t.user[i];
+  hot[q] = r;
+  hq[i] = q;
+}
+
 // ------------------------------------------------------------------ the persistent loop
 // The walk over the pending jobs (rebalancer.clj:442-458) as ONE cooperative launch: the host
 // never synchronises inside the cycle.  Per pending job:
@@ -340,6 +439,11 @@ struct RebArgs {
   int n_forced; const cook_decision* forced; const int32_t* forced_victims; int forced_only;
   const GridFlag* gf;   // exact-grid flag of the task amounts (common.cuh)
   int32_t* syn_cnt;     // [H]
+  TaskHot* hot;         // [CAP] packed victim records: real tasks in host order, a synthetic task at its own index
+  int32_t* hq;          // [CAP] task -> its record
+  int32_t* syn_head;    // [H]
+  int32_t* syn_next;    // [CAP]
+  int32_t* preempted_hn; // hostname ids of preempted_hosts[]
 };
 
 // task <= synthetic pending task [-prio, Long/MAX, nil(-1), job id] (tools.clj:614-641) ?
@@ -424,8 +528,104 @@ __device__ void pending_scalars(const RebArgs& a, const int32_t* ord, const int3
   }
 }
 
+// The group constraints (constraints.clj:680-697) look at the host only through its attribute value
+// (or its hostname); the value histogram over [hosts preempted so far ; the cotasks] is the same for
+// every host of the walk step.  One warp per CTA builds it once per pending job (distinct values and
+// their frequencies, two table entries per lane), the hosts then need one table lookup each instead
+// of the O(n^2) frequency walk.  More than GP_MAXG groups on the job or more than GP_MAXV distinct
+// values: `slow`, and host_ok takes the scalar walk.
+constexpr int GP_MAXG = 4, GP_MAXV = 64;
+struct GroupPre {
+  int slow, ng;
+  int kind[GP_MAXG], col[GP_MAXG], n[GP_MAXG], distinct[GP_MAXG], mn[GP_MAXG], mx[GP_MAXG], c0[GP_MAXG], c1[GP_MAXG], minimum[GP_MAXG];
+  int val[GP_MAXG][GP_MAXV], freq[GP_MAXG][GP_MAXV];
+};
+
+__device__ void group_prepare(const RebArgs& a, int p, int np, GroupPre* G) {
+  const int lane = threadIdx.x & 31;
+  const PendCols& pc = a.pc;
+  const HostCols& hc = a.hc;
+  const GroupCols& gc = a.gc;
+  const int k0 = (pc.group_off && gc.n > 0) ? pc.group_off[p] : 0, k1 = (pc.group_off && gc.n > 0) ? pc.group_off[p + 1] : 0;
+  const int ng = k1 - k0;
+  int slow = ng > GP_MAXG ? 1 : 0;
+  for (int g = 0; g < ng && !slow; g++) {
+    const int gi = pc.group_idx[k0 + g];
+    const int kind = gc.kind[gi];
+    const int col = gc.attr_col ? gc.attr_col[gi] : -1;
+    const int c0 = gc.cot_off[gi], c1 = gc.cot_off[gi + 1];
+    const int n = np + (c1 - c0);
+    int v0 = 0, f0 = 0, v1 = 0, f1 = 0, nv = 0;   // this lane's table entries `lane` and `lane + 32`
+    if (kind != COOK_GROUP_UNIQUE) {
+      const bool colok = col >= 0 && col < hc.n_attr_cols;
+      for (int base = 0; base < n; base += 32) {
+        const int i = base + lane;
+        int v = 0;
+        if (i < n) v = i < np ? (colok ? hc.attr[(size_t)col * hc.H + a.preempted_hosts[i]] : 0) : gc.cot_attr[c0 + i - np];
+        const int cnt = min(32, n - base);
+        for (int l = 0; l < cnt; l++) {
+          const int vl = __shfl_sync(0xffffffffu, v, l);
+          const bool e0 = lane < nv && v0 == vl, e1 = lane + 32 < nv && v1 == vl;
+          if (e0) f0++;
+          if (e1) f1++;
+          if (!__any_sync(0xffffffffu, e0 || e1)) {
+            if (nv >= GP_MAXV) { slow = 1; break; }
+            if (lane == (nv & 31)) { if (nv < 32) { v0 = vl; f0 = 1; } else { v1 = vl; f1 = 1; } }
+            nv++;
+          }
+        }
+        if (slow) break;
+      }
+    }
+    int mn = 0x7fffffff, mx = 0;
+    if (lane < nv) { mn = min(mn, f0); mx = max(mx, f0); }
+    if (lane + 32 < nv) { mn = min(mn, f1); mx = max(mx, f1); }
+    for (int o = 16; o > 0; o >>= 1) { mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o)); mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o)); }
+    G->val[g][lane] = v0; G->freq[g][lane] = lane < nv ? f0 : 0;
+    G->val[g][lane + 32] = v1; G->freq[g][lane + 32] = lane + 32 < nv ? f1 : 0;
+    if (lane == 0) {
+      G->kind[g] = kind; G->col[g] = col; G->n[g] = n; G->distinct[g] = nv; G->mn[g] = mn; G->mx[g] = mx;
+      G->c0[g] = c0; G->c1[g] = c1; G->minimum[g] = gc.minimum[gi];
+    }
+  }
+  if (lane == 0) { G->slow = slow; G->ng = ng; }
+}
+
+// the group constraints of pending job p on host h through the prepared tables (whole warp)
+__device__ bool host_groups_ok(const RebArgs& a, const GroupPre& G, int h, int np, bool have) {
+  const int lane = threadIdx.x & 31;
+  const HostCols& hc = a.hc;
+  for (int g = 0; g < G.ng; g++) {
+    const int kind = G.kind[g];
+    if (kind == COOK_GROUP_UNIQUE) {
+      if (!have) return false;
+      const int hn = hc.hostname_id[h];
+      bool hit = false;
+      for (int q = lane; q < np; q += 32) hit |= a.preempted_hn[q] == hn;
+      for (int c = G.c0[g] + lane; c < G.c1[g]; c += 32) hit |= a.gc.cot_host[c] == hn;
+      if (__any_sync(0xffffffffu, hit)) return false;
+    } else {
+      if (G.n[g] == 0) continue;
+      const int col = G.col[g];
+      const int target = (have && col >= 0 && col < hc.n_attr_cols) ? hc.attr[(size_t)col * hc.H + h] : 0;
+      const int nv = G.distinct[g];
+      int e = 0;
+      if (lane < nv && G.val[g][lane] == target) e = G.freq[g][lane];
+      if (lane + 32 < nv && G.val[g][lane + 32] == target) e = G.freq[g][lane + 32];
+      const unsigned m = __ballot_sync(0xffffffffu, e > 0);
+      const int tf = m ? __shfl_sync(0xffffffffu, e, __ffs(m) - 1) : 0;
+      if (kind == COOK_GROUP_ATTR_EQUALS) { if (tf == 0) return false; }
+      else if (tf != 0) {
+        const int mn = G.minimum[g] > nv ? 0 : G.mn[g], mx = G.mx[g];
+        if (!(mn == mx || tf < mx)) return false;
+      }
+    }
+  }
+  return true;
+}
+
 // P2 for one host (every lane computes the same): constraints.clj:504-515, :680-697
-__device__ bool host_ok(const RebArgs& a, int p, int h, int np) {
+__device__ bool host_ok(const RebArgs& a, int p, int h, int np, const GroupPre& G) {
   const PendCols& pc = a.pc;
   const HostCols& hc = a.hc;
   const GroupCols& gc = a.gc;
@@ -466,6 +666,7 @@ __device__ bool host_ok(const RebArgs& a, int p, int h, int np) {
     int loc = (have && hc.location) ? hc.location[h] : -1;
     if (loc != pc.ckpt_location[p]) pass = false;
   }
+  if (pass && !G.slow) return host_groups_ok(a, G, h, np, have);
   if (pass && pc.group_off && gc.n > 0) {
     for (int k = pc.group_off[p]; k < pc.group_off[p + 1] && pass; k++) {
       const int gi = pc.group_idx[k];
@@ -505,6 +706,7 @@ __device__ bool host_ok(const RebArgs& a, int p, int h, int np) {
 __global__ void __launch_bounds__(256) rebalance_kernel(RebArgs a) {
   cg::grid_group grid = cg::this_grid();
   __shared__ PendScalars s_ps;
+  __shared__ GroupPre s_gp;
   __shared__ double s_dru[8];
   __shared__ int s_rank[8], s_host[8];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -529,12 +731,13 @@ __global__ void __launch_bounds__(256) rebalance_kernel(RebArgs a) {
     if (warp == 0) {
       pending_scalars(a, ord, us, ue, p, &s_ps);
     }
+    if (warp == nw - 1) group_prepare(a, p, a.cnt[3], &s_gp);
     __syncthreads();
     if (blockIdx.x == 0 && tid == 0) a.ps_all[p] = s_ps;
     SelArgs sa;
     sa.hord = a.hord; sa.hs = a.hs; sa.he = a.he; sa.t = t; sa.R = a.R; sa.n_tasks = n_tasks;
     sa.hc = hc; sa.pc = pc; sa.user_rank = a.user_rank; sa.ps = &s_ps;
-    sa.min_diff = a.min_diff; sa.safe = a.safe; sa.syn_cnt = a.syn_cnt;
+    sa.min_diff = a.min_diff; sa.safe = a.safe; sa.syn_cnt = a.syn_cnt; sa.hot = a.hot; sa.syn_head = a.syn_head; sa.syn_next = a.syn_next;
     double bd = -1.0;
     int br = -1, bh = -1;
     if (fi < 0) {
@@ -542,7 +745,7 @@ __global__ void __launch_bounds__(256) rebalance_kernel(RebArgs a) {
       for (int h = gw; h < hc.H; h += n_gw) {
         HostBest b;
         b.dru = 0.0; b.mem = b.cpus = b.gpus = 0.0; b.n_victims = -1;
-        if (host_ok(a, p, h, np)) b = host_select(sa, p, h, lane, nullptr, 0);
+        if (host_ok(a, p, h, np, s_gp)) b = host_select(sa, p, h, lane, nullptr, 0);
         if (lane == 0) a.best[h] = b;
         if (b.n_victims >= 0) {
           const int r = hc.name_rank[h];
@@ -606,6 +809,8 @@ __global__ void __launch_bounds__(256) rebalance_kernel(RebArgs a) {
           for (int k = b.n_victims - 1; k >= 0; k--) {     // selection order
             const int i = a.victims[vb + k];
             t.alive[i] = 0;
+            a.hot[a.hq[i]].idx = -1;
+            a.preempted_hn[a.cnt[3]] = hc.hostname_id[t.host[i]];
             a.preempted_hosts[a.cnt[3]++] = t.host[i];
             const int u = t.user[i], from = us[u] + t.pos[i];
             int e = 0;
@@ -627,6 +832,13 @@ __global__ void __launch_bounds__(256) rebalance_kernel(RebArgs a) {
           t.host[ni] = h; t.alive[ni] = 1; t.dru[ni] = 0.0; t.pos[ni] = 0; t.cm[ni] = 0.0; t.cc[ni] = 0.0;
           a.has_task[h] = 1;
           a.syn_cnt[h] += 1;
+          {
+            TaskHot r;
+            r.dru = 0.0; r.mem = pc.mem[p]; r.cpus = pc.cpus[p]; r.gpus = pc.gpus ? pc.gpus[p] : 0.0;
+            r.urank = a.user_rank[pu]; r.pos = 0; r.idx = ni; r.user = pu;
+            a.hot[ni] = r; a.hq[ni] = ni;
+            a.syn_next[ni] = a.syn_head[h]; a.syn_head[h] = ni;
+          }
           hc.has_spare[h] = 1;
           hc.spare_mem[h] = b.mem - pc.mem[p];
           hc.spare_gpus[h] = b.gpus - (pc.gpus ? pc.gpus[p] : 0.0);
@@ -711,8 +923,10 @@ __global__ void __launch_bounds__(256) rebalance_kernel(RebArgs a) {
           if (i >= 0) {
             t.cm[i] = mym; t.cc[i] = myc;
             const double x = mym / md, y = myc / cd;
-            t.dru[i] = x > y ? x : y;
+            const double dr = x > y ? x : y;
+            t.dru[i] = dr;
             t.pos[i] = pp - s;
+            { TaskHot& hr = a.hot[a.hq[i]]; hr.dru = dr; hr.pos = pp - s; }
           }
         }
       }
@@ -776,9 +990,10 @@ static int32_t rebalance_run(cook_pool* pool, const cook_running_soa* running,
   if (G) { sz.add<int32_t>(6 * (size_t)(G + 2)); sz.add<int32_t>(2 * (size_t)(groups->cot_off ? groups->cot_off[G] : 0) + 64); }
   sz.add<HostBest>(H + 1); sz.add<cook_decision>(MP + 1); sz.add<int32_t>(CAP + MP);
   sz.add<PendScalars>(P + 4); sz.add<int32_t>(64);
-  sz.add<int32_t>(CAP); sz.add<int32_t>(CAP + MP);               // second order buffer, preempted hosts
+  sz.add<int32_t>(CAP); sz.add<int32_t>(CAP + MP); sz.add<int32_t>(CAP + MP);   // second order buffer, preempted hosts (+ their hostname ids)
   for (int k = 0; k < 2; k++) sz.add<int32_t>(U + 1);            // second segment buffers
   sz.add<CtaBest>(4 * pool->sm_count + 8); sz.add<GridFlag>(1); sz.add<int32_t>(H + 1);
+  sz.add<TaskHot>(CAP); sz.add<int32_t>(CAP); sz.add<int32_t>(H + 1); sz.add<int32_t>(CAP);
   if (tr && tr->n_forced > 0) { sz.add<cook_decision>(tr->n_forced + 1); sz.add<int32_t>(CAP + MP); }
   CK(pool, ar.reserve(sz.off + (1 << 16)));
   ar.reset();
@@ -871,6 +1086,7 @@ static int32_t rebalance_run(cook_pool* pool, const cook_running_soa* running,
   cook_decision* d_dec = ar.take<cook_decision>(MP + 1);
   int32_t* d_vict = ar.take<int32_t>(CAP + MP);
   int32_t* d_pre = ar.take<int32_t>(CAP + MP);
+  int32_t* d_prehn = ar.take<int32_t>(CAP + MP);
   PendScalars* d_ps = ar.take<PendScalars>(P + 4);
   Refold* d_rf = ar.take<Refold>(1);
   int32_t* d_cnt = ar.take<int32_t>(64);  // [0] n_tasks [1] n_dec [2] n_vict [3] n_preempted [4] changed
@@ -894,9 +1110,14 @@ static int32_t rebalance_run(cook_pool* pool, const cook_running_soa* running,
   if (ar.failed) return set_err(pool, COOK_E_OOM, "cook_rebalance: arena exhausted");
   GridFlag* d_gf = ar.take<GridFlag>(1);
   int32_t* d_syn = ar.take<int32_t>(H + 1);
+  TaskHot* d_hot = ar.take<TaskHot>(CAP);
+  int32_t* d_hq = ar.take<int32_t>(CAP);
+  int32_t* d_synh = ar.take<int32_t>(H + 1);
+  int32_t* d_synn = ar.take<int32_t>(CAP);
   if (ar.failed) return set_err(pool, COOK_E_OOM, "cook_rebalance: arena exhausted");
   CK(pool, cudaMemsetAsync(d_gf, 0, sizeof(GridFlag), st));
   CK(pool, cudaMemsetAsync(d_syn, 0, sizeof(int32_t) * (H + 1), st));
+  CK(pool, cudaMemsetAsync(d_synh, 0xff, sizeof(int32_t) * (H + 1), st));
   if (R > 0) grid_check_kernel<<<(R + 255) / 256, 256, 0, st>>>(t.cpus, t.mem, t.gpus, R, d_gf);
   grid_check_kernel<<<(P + 255) / 256, 256, 0, st>>>(pc.cpus, pc.mem, pc.gpus, P, d_gf);
   int32_t h_cnt[16] = {R, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
@@ -923,7 +1144,8 @@ static int32_t rebalance_run(cook_pool* pool, const cook_running_soa* running,
     CK(pool, csort::sort_indices(d_hord, d_tmp, R, LessHost{t}, st));
     host_seg_kernel<<<(R + TB - 1) / TB, TB, 0, st>>>(d_hord, t, R, d_hs, d_he);
     host_has_task_kernel<<<(R + TB - 1) / TB, TB, 0, st>>>(t, R, d_has_task);
-    launches += 8;
+    hot_build_kernel<<<(R + TB - 1) / TB, TB, 0, st>>>(d_hord, t, d_urank, R, d_hot, d_hq);
+    launches += 9;
     for (long long w = csort::TILE; w < R; w <<= 1) launches += 2;
   }
   // ---- the walk over the pending jobs: one cooperative launch, no host round trip inside
@@ -934,10 +1156,10 @@ static int32_t rebalance_run(cook_pool* pool, const cook_running_soa* running,
   ra.hc = hc; ra.pc = pc; ra.gc = gc; ra.P = P; ra.U = U; ra.MP = MP;
   ra.user_rank = d_urank; ra.div_mem = d_divm; ra.div_cpus = d_divc;
   ra.q_count = d_qn; ra.q_cpus = d_qc; ra.q_mem = d_qm; ra.q_gpus = d_qg;
-  ra.has_task = d_has_task; ra.preempted_hosts = d_pre;
+  ra.has_task = d_has_task; ra.preempted_hosts = d_pre; ra.preempted_hn = d_prehn;
   ra.min_diff = prm->min_dru_diff; ra.safe = prm->safe_dru_threshold; ra.host_lifetime_mins = prm->host_lifetime_mins;
   ra.best = d_best; ra.cta_best = d_cta; ra.dec = d_dec; ra.victims = d_vict; ra.cnt = d_cnt; ra.rf = d_rf;
-  ra.ps_all = d_ps; ra.gf = d_gf; ra.syn_cnt = d_syn;
+  ra.ps_all = d_ps; ra.gf = d_gf; ra.syn_cnt = d_syn; ra.hot = d_hot; ra.hq = d_hq; ra.syn_head = d_synh; ra.syn_next = d_synn;
   ra.n_forced = NF; ra.forced = d_forced; ra.forced_victims = d_fvict; ra.forced_only = tr ? tr->forced_only : 0;
   {
     int occ = 0;
