@@ -85,6 +85,12 @@ struct Refold {
   int32_t user[64];    // victims of one decision sit on one host; more than 63 distinct
   int32_t from[64];    //   users fall back to `all` (from = segment start)
   int32_t all;
+  // for the element-wise re-fold (exact-grid amounts): the victims of the decision (user, slot in the
+  // OLD order, amounts) and the running sums just before the new task
+  int32_t n_vict;
+  int32_t vu[64], vs[64];
+  double vm[64], vc[64];
+  double base_m, base_c;
 };
 
 // dru.clj:50-66: lane-serial left fold (exact association) of the users in `rf`
@@ -92,7 +98,8 @@ struct Refold {
 __global__ void __launch_bounds__(128) user_dru_kernel(const int32_t* ord, RTasks t, const double* div_mem,
                                                        const double* div_cpus, const int32_t* seg_start,
                                                        const int32_t* seg_end, int n_users, const Refold* rf,
-                                                       const GridFlag* gf) {
+                                                       const GridFlag* gf, int n_scan) {
+  if (n_scan > 0 && grid_exact(gf, n_scan)) return;   // the order-wide scan below does it
   const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   const bool all = rf == nullptr || rf->all;
@@ -135,6 +142,71 @@ __global__ void __launch_bounds__(128) user_dru_kernel(const int32_t* ord, RTask
       t.pos[i] = p - s;
     }
   }
+}
+
+// The same fold for exact-grid amounts (any association gives the same bits, common.cuh): ONE
+// inclusive scan over the whole user order, a task's running sums are the scan at its slot minus the
+// scan just before its user's first slot.  A user with tens of thousands of tasks no longer sits on
+// one warp.  Three launches: tile scans, the tile totals, the per-task finish.
+constexpr int SCAN_TB = 256, SCAN_IPT = 8, SCAN_TILE = SCAN_TB * SCAN_IPT;
+
+__global__ void __launch_bounds__(SCAN_TB) order_scan_tiles(const int32_t* ord, RTasks t, int n, const GridFlag* gf,
+                                                            double* pm, double* pc, double* bt_m, double* bt_c) {
+  if (!grid_exact(gf, n)) return;
+  __shared__ double s_m[SCAN_TB / 32], s_c[SCAN_TB / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int p0 = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_IPT;
+  double xm[SCAN_IPT], xc[SCAN_IPT];
+#pragma unroll
+  for (int k = 0; k < SCAN_IPT; k++) {
+    const int p = p0 + k;
+    const int i = p < n ? ord[p] : -1;
+    const bool live = i >= 0 && t.alive[i];
+    xm[k] = live ? t.mem[i] : 0.0; xc[k] = live ? t.cpus[i] : 0.0;
+  }
+#pragma unroll
+  for (int k = 1; k < SCAN_IPT; k++) { xm[k] = xm[k - 1] + xm[k]; xc[k] = xc[k - 1] + xc[k]; }
+  const double im = warp_incl_scan(xm[SCAN_IPT - 1], lane), ic = warp_incl_scan(xc[SCAN_IPT - 1], lane);
+  if (lane == 31) { s_m[warp] = im; s_c[warp] = ic; }
+  __syncthreads();
+  double om = im - xm[SCAN_IPT - 1], oc = ic - xc[SCAN_IPT - 1];   // exact: both on the grid
+  for (int w = 0; w < warp; w++) { om = om + s_m[w]; oc = oc + s_c[w]; }
+#pragma unroll
+  for (int k = 0; k < SCAN_IPT; k++) {
+    const int p = p0 + k;
+    if (p < n) { pm[p] = om + xm[k]; pc[p] = oc + xc[k]; }
+  }
+  if (threadIdx.x == SCAN_TB - 1) { bt_m[blockIdx.x] = om + xm[SCAN_IPT - 1]; bt_c[blockIdx.x] = oc + xc[SCAN_IPT - 1]; }
+}
+
+// tile totals -> exclusive offsets, in place (one warp)
+__global__ void order_scan_totals(double* bt_m, double* bt_c, int nb, int n, const GridFlag* gf) {
+  if (!grid_exact(gf, n)) return;
+  const int lane = threadIdx.x;
+  double am = 0.0, ac = 0.0;
+  for (int base = 0; base < nb; base += 32) {
+    const int b = base + lane;
+    const double xm = b < nb ? bt_m[b] : 0.0, xc = b < nb ? bt_c[b] : 0.0;
+    const double im = am + warp_incl_scan(xm, lane), ic = ac + warp_incl_scan(xc, lane);
+    if (b < nb) { bt_m[b] = im - xm; bt_c[b] = ic - xc; }
+    am = __shfl_sync(0xffffffffu, im, 31); ac = __shfl_sync(0xffffffffu, ic, 31);
+  }
+}
+
+__global__ void order_dru_finish(const int32_t* ord, RTasks t, int n, const GridFlag* gf, const double* pm, const double* pc,
+                                 const double* bt_m, const double* bt_c, const int32_t* seg_start,
+                                 const double* div_mem, const double* div_cpus) {
+  if (!grid_exact(gf, n)) return;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  const int i = ord[p], u = t.user[i], s = seg_start[u];
+  const double gm = pm[p] + bt_m[p / SCAN_TILE], gc = pc[p] + bt_c[p / SCAN_TILE];
+  const double hm = s > 0 ? pm[s - 1] + bt_m[(s - 1) / SCAN_TILE] : 0.0, hcv = s > 0 ? pc[s - 1] + bt_c[(s - 1) / SCAN_TILE] : 0.0;
+  const double cm = gm - hm, cc = gc - hcv;
+  t.cm[i] = cm; t.cc[i] = cc;
+  const double a = cm / div_mem[u], b = cc / div_cpus[u];
+  t.dru[i] = a > b ? a : b;
+  t.pos[i] = p - s;
 }
 
 struct HostCols {
@@ -703,12 +775,14 @@ __device__ bool host_ok(const RebArgs& a, int p, int h, int np, const GroupPre& 
   return pass;
 }
 
-__global__ void __launch_bounds__(256) rebalance_kernel(RebArgs a) {
+constexpr int REB_TB = 512;   // 16 warps: a warp per host in the host phase, one CTA per SM at the barriers
+__global__ void __launch_bounds__(REB_TB) rebalance_kernel(RebArgs a) {
   cg::grid_group grid = cg::this_grid();
   __shared__ PendScalars s_ps;
   __shared__ GroupPre s_gp;
-  __shared__ double s_dru[8];
-  __shared__ int s_rank[8], s_host[8];
+  __shared__ int s_ru[64], s_rfrom[64];
+  __shared__ double s_dru[REB_TB / 32];
+  __shared__ int s_rank[REB_TB / 32], s_host[REB_TB / 32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nw = blockDim.x >> 5;
   const int gw = blockIdx.x * nw + warp, n_gw = gridDim.x * nw;
@@ -717,7 +791,7 @@ __global__ void __launch_bounds__(256) rebalance_kernel(RebArgs a) {
   const PendCols& pc = a.pc;
   RTasks t = a.t;
   int cur = 0, n_tasks = a.R, n_dec = 0;
-  long long tA = 0, tB = 0, tC = 0, tS = 0, t0 = clock64();   // CTA 0 / thread 0: cycles per phase (COOK_PROF)
+  long long tA = 0, tB = 0, tC = 0, tS = 0, tA0 = 0, tb[5] = {0, 0, 0, 0, 0}, t0 = clock64();   // CTA 0 / thread 0: cycles per phase (COOK_PROF)
   const bool forced_only = a.n_forced > 0 && a.forced_only != 0;
   const int n_walk = forced_only ? a.n_forced : a.P;
   for (int w = 0; w < n_walk && n_dec < a.MP; w++) {
@@ -733,6 +807,7 @@ __global__ void __launch_bounds__(256) rebalance_kernel(RebArgs a) {
     }
     if (warp == nw - 1) group_prepare(a, p, a.cnt[3], &s_gp);
     __syncthreads();
+    tA0 += clock64() - t0;
     if (blockIdx.x == 0 && tid == 0) a.ps_all[p] = s_ps;
     SelArgs sa;
     sa.hord = a.hord; sa.hs = a.hs; sa.he = a.he; sa.t = t; sa.R = a.R; sa.n_tasks = n_tasks;
@@ -778,6 +853,7 @@ __global__ void __launch_bounds__(256) rebalance_kernel(RebArgs a) {
         const int orr = __shfl_xor_sync(0xffffffffu, r, o), oh = __shfl_xor_sync(0xffffffffu, h, o);
         if (oh >= 0 && (od > d || (od == d && orr > r))) { d = od; r = orr; h = oh; }
       }
+      tb[4] += clock64() - t0;
       HostBest b;
       b.dru = 0.0; b.mem = b.cpus = b.gpus = 0.0; b.n_victims = -1;
       const int vb = a.cnt[2];
@@ -793,34 +869,59 @@ __global__ void __launch_bounds__(256) rebalance_kernel(RebArgs a) {
         if (b.n_victims > 0) host_select(sa, p, h, lane, a.victims + vb, b.n_victims);
         __syncwarp();
       }
+      long long tq = clock64();
+      tb[0] += tq - t0;
       if (h < 0) {
         if (lane == 0) a.cnt[4] = 0;
       } else {
         const int n = n_tasks, ni = n;
         const int pu = pc.user[p];
         Refold& rf = *a.rf;
+        // the victims, one per lane: dead, off their host's records, host noted as preempted; then the
+        // list of users to re-fold (merged through registers, table in shared memory)
+        const int nv = b.n_victims > 0 ? b.n_victims : 0;
+        const int np0 = a.cnt[3];
+        int rn = 0, rall = nv > 64 ? 1 : 0;
+        bool pu_listed = false;
+        for (int base = 0; base < nv; base += 32) {
+          const int kk = base + lane;   // selection order
+          int u = -1, from = 0;
+          if (kk < nv) {
+            const int i = a.victims[vb + nv - 1 - kk];
+            t.alive[i] = 0;
+            a.hot[a.hq[i]].idx = -1;
+            const int hh = t.host[i];
+            u = t.user[i]; from = us[u] + t.pos[i];
+            a.preempted_hn[np0 + kk] = hc.hostname_id[hh];
+            a.preempted_hosts[np0 + kk] = hh;
+            if (kk < 64) { rf.vu[kk] = u; rf.vs[kk] = from; rf.vm[kk] = t.mem[i]; rf.vc[kk] = t.cpus[i]; }
+          }
+          const int cntv = min(32, nv - base);
+          for (int l = 0; l < cntv; l++) {
+            const int ul = __shfl_sync(0xffffffffu, u, l), fl = __shfl_sync(0xffffffffu, from, l);
+            const bool e0 = lane < rn && s_ru[lane] == ul, e1 = lane + 32 < rn && s_ru[lane + 32] == ul;
+            if (e0) s_rfrom[lane] = min(s_rfrom[lane], fl);
+            if (e1) s_rfrom[lane + 32] = min(s_rfrom[lane + 32], fl);
+            if (!__any_sync(0xffffffffu, e0 || e1)) {
+              if (rn < 63) { if (lane == 0) { s_ru[rn] = ul; s_rfrom[rn] = fl; } rn++; }
+              else rall = 1;
+            }
+            if (ul == pu) pu_listed = true;
+            __syncwarp();
+          }
+        }
+        if (!pu_listed) { if (lane == 0) { s_ru[rn] = pu; s_rfrom[rn] = 0x7fffffff; } rn++; }
+        __syncwarp();
+        { const long long t1 = clock64(); tb[1] += t1 - tq; tq = t1; }
+        rf.user[lane] = s_ru[lane]; rf.user[lane + 32] = s_ru[lane + 32];
+        rf.from[lane] = s_rfrom[lane]; rf.from[lane + 32] = s_rfrom[lane + 32];
         if (lane == 0) {
           const int di = a.cnt[1];
           cook_decision dd;
           dd.pending_idx = p; dd.host = h; dd.dru = b.dru; dd.mem = b.mem; dd.cpus = b.cpus; dd.gpus = b.gpus;
           dd.victim_begin = vb; dd.victim_count = b.n_victims;
-          rf.n = 0; rf.all = 0; rf.pu = pu;
-          bool pu_listed = false;
-          for (int k = b.n_victims - 1; k >= 0; k--) {     // selection order
-            const int i = a.victims[vb + k];
-            t.alive[i] = 0;
-            a.hot[a.hq[i]].idx = -1;
-            a.preempted_hn[a.cnt[3]] = hc.hostname_id[t.host[i]];
-            a.preempted_hosts[a.cnt[3]++] = t.host[i];
-            const int u = t.user[i], from = us[u] + t.pos[i];
-            int e = 0;
-            while (e < rf.n && rf.user[e] != u) e++;
-            if (e < rf.n) rf.from[e] = min(rf.from[e], from);
-            else if (rf.n < 63) { rf.user[rf.n] = u; rf.from[rf.n] = from; rf.n++; }
-            else rf.all = 1;
-            if (u == pu) pu_listed = true;
-          }
-          if (!pu_listed) { rf.user[rf.n] = pu; rf.from[rf.n] = 0x7fffffff; rf.n++; }
+          rf.n = rn; rf.all = rall; rf.pu = pu; rf.n_vict = min(nv, 64);
+          a.cnt[3] = np0 + nv;
           a.cnt[2] = vb + b.n_victims;
           a.dec[di] = dd;
           a.cnt[1] = di + 1;
@@ -847,8 +948,10 @@ __global__ void __launch_bounds__(256) rebalance_kernel(RebArgs a) {
         __syncwarp();
         // where the new task goes in the user order: after every task that is not greater
         // (32-ary search: the predicate "new task < ord[q]" is monotone in q)
+        { const long long t1 = clock64(); tb[2] += t1 - tq; tq = t1; }
         LessUser less{t, a.user_rank};
-        int lo = 0, hi = n;
+        const int ps = us[pu], pe = ue[pu];
+        int lo = pe > ps ? ps : 0, hi = pe > ps ? pe : n;   // a user with tasks: inside its own segment
         while (lo < hi) {
           const int step = (hi - lo + 31) / 32;
           const int q = lo + lane * step;
@@ -859,7 +962,12 @@ __global__ void __launch_bounds__(256) rebalance_kernel(RebArgs a) {
           const int nhi = L < 32 ? min(hi, lo + L * step) : hi;
           lo = min(nlo, nhi); hi = nhi;
         }
-        if (lane == 0) { rf.q_ins = lo; a.cnt[4] = 1; }
+        if (lane == 0) {
+          rf.q_ins = lo; a.cnt[4] = 1;
+          const bool prev = pe > ps && lo > ps;
+          rf.base_m = prev ? t.cm[ord[lo - 1]] : 0.0; rf.base_c = prev ? t.cc[ord[lo - 1]] : 0.0;
+        }
+        { const long long t1 = clock64(); tb[3] += t1 - tq; tq = t1; }
       }
       __threadfence();
     }
@@ -886,6 +994,44 @@ __global__ void __launch_bounds__(256) rebalance_kernel(RebArgs a) {
       }
       const bool all = rf.all != 0;
       const int n_fold = all ? a.U : rf.n;
+      // a listed user with exact-grid amounts: every running sum moves by a constant (the victims at or
+      // before the slot leave, the new task joins), so the whole grid updates the slots independently.
+      // Anything else (`all`, off-grid amounts) is folded by one warp per user in the reference's order.
+      const double pmem = pc.mem[p], pcpus = pc.cpus[p];
+      for (int wv = 0; wv < (all ? 0 : n_fold); wv++) {
+        const int u = rf.user[wv];
+        int s = us[u], e = ue[u];
+        if (e <= s) { if (u != pu) continue; s = q; e = q + 1; }
+        else if (u == pu) e = e + 1;
+        else if (s >= q) { s++; e++; }
+        if (!grid_exact(a.gf, e - s)) continue;
+        int f = rf.from[wv];
+        if (f == 0x7fffffff) f = q;
+        else if (f >= q) f++;
+        if (u == pu) f = min(f, q);
+        f = min(max(f, s), e);
+        const double md = a.div_mem[u], cd = a.div_cpus[u];
+        const int nvict = rf.n_vict;
+        for (int pp = f + gt; pp < e; pp += n_gt) {
+          const int i = new_at(pp);
+          const bool is_new = u == pu && pp == q;
+          double bm = is_new ? rf.base_m : t.cm[i], bc = is_new ? rf.base_c : t.cc[i];
+          double dm = 0.0, dc = 0.0;
+          for (int k = 0; k < nvict; k++) {
+            if (rf.vu[k] != u) continue;
+            const int sv = rf.vs[k] >= q ? rf.vs[k] + 1 : rf.vs[k];
+            if (sv <= pp) { dm = dm + rf.vm[k]; dc = dc + rf.vc[k]; }
+          }
+          bm = bm - dm; bc = bc - dc;
+          if (u == pu && pp >= q) { bm = bm + pmem; bc = bc + pcpus; }
+          t.cm[i] = bm; t.cc[i] = bc;
+          const double x = bm / md, y = bc / cd;
+          const double dr = x > y ? x : y;
+          t.dru[i] = dr;
+          t.pos[i] = pp - s;
+          { TaskHot& hr = a.hot[a.hq[i]]; hr.dru = dr; hr.pos = pp - s; }
+        }
+      }
       for (int wv = gw; wv < n_fold; wv += n_gw) {
         const int u = all ? wv : rf.user[wv];
         int s = us[u], e = ue[u];
@@ -904,6 +1050,7 @@ __global__ void __launch_bounds__(256) rebalance_kernel(RebArgs a) {
         double am = 0.0, ac = 0.0;
         if (f > s) { const int j = new_at(f - 1); am = t.cm[j]; ac = t.cc[j]; }
         const bool exact = grid_exact(a.gf, e - s);
+        if (exact && !all) continue;   // done element-wise above
         for (int base = f; base < e; base += 32) {
           const int pp = base + lane;
           const int i = pp < e ? new_at(pp) : -1;
@@ -937,7 +1084,7 @@ __global__ void __launch_bounds__(256) rebalance_kernel(RebArgs a) {
       n_tasks = n_tasks + 1;
     }
   }
-  if (blockIdx.x == 0 && tid == 0) { a.cnt[8] = (int)(tA >> 10); a.cnt[9] = (int)(tB >> 10); a.cnt[10] = (int)(tC >> 10); a.cnt[11] = (int)(tS >> 10); }
+  if (blockIdx.x == 0 && tid == 0) { a.cnt[8] = (int)(tA >> 10); a.cnt[9] = (int)(tB >> 10); a.cnt[10] = (int)(tC >> 10); a.cnt[11] = (int)(tS >> 10); a.cnt[12] = (int)(tA0 >> 10); for (int k = 0; k < 5; k++) a.cnt[13 + k] = (int)(tb[k] >> 10); }
 }
 
 }  // namespace
@@ -994,6 +1141,7 @@ static int32_t rebalance_run(cook_pool* pool, const cook_running_soa* running,
   for (int k = 0; k < 2; k++) sz.add<int32_t>(U + 1);            // second segment buffers
   sz.add<CtaBest>(4 * pool->sm_count + 8); sz.add<GridFlag>(1); sz.add<int32_t>(H + 1);
   sz.add<TaskHot>(CAP); sz.add<int32_t>(CAP); sz.add<int32_t>(H + 1); sz.add<int32_t>(CAP);
+  sz.add<double>(CAP); sz.add<double>(CAP); sz.add<double>(CAP / SCAN_TILE + 2); sz.add<double>(CAP / SCAN_TILE + 2);
   if (tr && tr->n_forced > 0) { sz.add<cook_decision>(tr->n_forced + 1); sz.add<int32_t>(CAP + MP); }
   CK(pool, ar.reserve(sz.off + (1 << 16)));
   ar.reset();
@@ -1114,6 +1262,8 @@ static int32_t rebalance_run(cook_pool* pool, const cook_running_soa* running,
   int32_t* d_hq = ar.take<int32_t>(CAP);
   int32_t* d_synh = ar.take<int32_t>(H + 1);
   int32_t* d_synn = ar.take<int32_t>(CAP);
+  double* d_pm = ar.take<double>(CAP); double* d_pc = ar.take<double>(CAP);
+  double* d_btm = ar.take<double>(CAP / SCAN_TILE + 2); double* d_btc = ar.take<double>(CAP / SCAN_TILE + 2);
   if (ar.failed) return set_err(pool, COOK_E_OOM, "cook_rebalance: arena exhausted");
   CK(pool, cudaMemsetAsync(d_gf, 0, sizeof(GridFlag), st));
   CK(pool, cudaMemsetAsync(d_syn, 0, sizeof(int32_t) * (H + 1), st));
@@ -1139,7 +1289,14 @@ static int32_t rebalance_run(cook_pool* pool, const cook_running_soa* running,
     iota_r<<<(R + TB - 1) / TB, TB, 0, st>>>(d_ord, R);
     CK(pool, csort::sort_indices(d_ord, d_tmp, R, LessUser{t, d_urank}, st));
     user_seg_kernel<<<(R + TB - 1) / TB, TB, 0, st>>>(d_ord, t, R, d_us, d_ue);
-    user_dru_kernel<<<(U + 3) / 4, 128, 0, st>>>(d_ord, t, d_divm, d_divc, d_us, d_ue, U, nullptr, d_gf);
+    {
+      const int nb = (R + SCAN_TILE - 1) / SCAN_TILE;
+      order_scan_tiles<<<nb, SCAN_TB, 0, st>>>(d_ord, t, R, d_gf, d_pm, d_pc, d_btm, d_btc);
+      order_scan_totals<<<1, 32, 0, st>>>(d_btm, d_btc, nb, R, d_gf);
+      order_dru_finish<<<(R + TB - 1) / TB, TB, 0, st>>>(d_ord, t, R, d_gf, d_pm, d_pc, d_btm, d_btc, d_us, d_divm, d_divc);
+      launches += 3;
+    }
+    user_dru_kernel<<<(U + 3) / 4, 128, 0, st>>>(d_ord, t, d_divm, d_divc, d_us, d_ue, U, nullptr, d_gf, R);
     iota_r<<<(R + TB - 1) / TB, TB, 0, st>>>(d_hord, R);
     CK(pool, csort::sort_indices(d_hord, d_tmp, R, LessHost{t}, st));
     host_seg_kernel<<<(R + TB - 1) / TB, TB, 0, st>>>(d_hord, t, R, d_hs, d_he);
@@ -1163,23 +1320,28 @@ static int32_t rebalance_run(cook_pool* pool, const cook_running_soa* running,
   ra.n_forced = NF; ra.forced = d_forced; ra.forced_victims = d_fvict; ra.forced_only = tr ? tr->forced_only : 0;
   {
     int occ = 0;
-    CK(pool, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rebalance_kernel, 256, 0));
+    CK(pool, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rebalance_kernel, REB_TB, 0));
     if (occ < 1) return set_err(pool, COOK_E_CUDA, "cook_rebalance: kernel does not fit on an SM");
     // a warp per host in the host phase: as many co-resident CTAs as help (<= 3 per SM)
     int per_sm = 1;   // measured: more CTAs shorten the host phase but lengthen the barriers by as much
     if (const char* e = getenv("COOK_REB_CTAS_PER_SM")) per_sm = std::max(1, std::min(occ, atoi(e)));
-    int grid = std::min(per_sm * pool->sm_count, std::max(1, (H + 7) / 8));
+    int grid = std::min(per_sm * pool->sm_count, std::max(1, (H + REB_TB / 32 - 1) / (REB_TB / 32)));
     void* kargs[] = {&ra};
-    CK(pool, cudaLaunchCooperativeKernel((void*)rebalance_kernel, dim3(grid), dim3(256), kargs, 0, st));
+    CK(pool, cudaEventRecord(pool->ev[16], st));
+    CK(pool, cudaLaunchCooperativeKernel((void*)rebalance_kernel, dim3(grid), dim3(REB_TB), kargs, 0, st));
     launches++;
   }
   CK(pool, cudaEventRecord(pool->ev[14], st));
   CK(pool, cudaMemcpyAsync(h_cnt, d_cnt, sizeof(int32_t) * 5, cudaMemcpyDeviceToHost, st));
   CK(pool, cudaStreamSynchronize(st));
   if (getenv("COOK_PROF")) {
-    int32_t hp[4];
+    int32_t hp[10];
     CK(pool, cudaMemcpy(hp, d_cnt + 8, sizeof(hp), cudaMemcpyDeviceToHost));
-    fprintf(stderr, "[cook_prof] rebalance kcycles (CTA 0): hosts %d  next-state %d  refold %d  grid-sync %d\n", hp[0], hp[1], hp[2], hp[3]);
+    float pre = 0.f, walk = 0.f;
+    if (R > 0 && P > 0) { cudaEventElapsedTime(&pre, pool->ev[13], pool->ev[16]); cudaEventElapsedTime(&walk, pool->ev[16], pool->ev[14]); }
+    fprintf(stderr, "[cook_prof] rebalance kcycles (CTA 0): hosts %d (scalars+groups %d)  next-state %d  refold %d  grid-sync %d | setup %.3f ms walk %.3f ms\n",
+            hp[0], hp[4], hp[1], hp[2], hp[3], pre, walk);
+    fprintf(stderr, "[cook_prof]   next-state split: argmax+victim selection %d  victims %d  bookkeeping %d  insertion search %d (argmax alone %d)\n", hp[5], hp[6], hp[7], hp[8], hp[9]);
   }
   const int n_dec = h_cnt[1], n_tasks = h_cnt[0];
   if (n_dec > 0) {
