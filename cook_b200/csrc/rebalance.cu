@@ -492,6 +492,32 @@ namespace cg = cooperative_groups;
 
 struct CtaBest { double dru; int32_t rank, host; };
 
+// Barriers of the walk (co-residency comes from the cooperative launch).  Two counters that only grow and
+// one flag: after the host phase the CTAs ARRIVE and only CTA 0 waits for all of them; the others wait
+// for the flag CTA 0 raises after next-state; only the re-fold ends in a full barrier.  Pollers back off
+// (nanosleep) so that the lone next-state warp is not competing with 147 spinning CTAs for L2.
+struct WalkBar { unsigned arrive_a; unsigned flag_b; unsigned arrive_c; unsigned pad; };
+__device__ __forceinline__ unsigned bar_ld_acquire(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void bar_arrive(unsigned* p) {   // whole CTA
+  __syncthreads();
+  if (threadIdx.x == 0) { __threadfence(); asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p) : "memory"); }
+}
+__device__ __forceinline__ void bar_wait(const unsigned* p, unsigned target) {   // whole CTA
+  if (threadIdx.x == 0) {
+    while (bar_ld_acquire(p) < target) __nanosleep(20);
+    __threadfence();
+  }
+  __syncthreads();
+}
+__device__ __forceinline__ void bar_raise(unsigned* p, unsigned v) {   // whole CTA
+  __syncthreads();
+  if (threadIdx.x == 0) { __threadfence(); asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+}
+
 struct RebArgs {
   RTasks t; int R;
   int32_t* ord[2]; int32_t* us[2]; int32_t* ue[2];
@@ -516,6 +542,7 @@ struct RebArgs {
   int32_t* syn_head;    // [H]
   int32_t* syn_next;    // [CAP]
   int32_t* preempted_hn; // hostname ids of preempted_hosts[]
+  WalkBar* bar;
 };
 
 // task <= synthetic pending task [-prio, Long/MAX, nil(-1), job id] (tools.clj:614-641) ?
@@ -777,7 +804,8 @@ __device__ bool host_ok(const RebArgs& a, int p, int h, int np, const GroupPre& 
 
 constexpr int REB_TB = 512;   // 16 warps: a warp per host in the host phase, one CTA per SM at the barriers
 __global__ void __launch_bounds__(REB_TB) rebalance_kernel(RebArgs a) {
-  cg::grid_group grid = cg::this_grid();
+  unsigned n_a = 0, n_c = 0;   // barrier generations
+  const unsigned G = gridDim.x;
   __shared__ PendScalars s_ps;
   __shared__ GroupPre s_gp;
   __shared__ int s_ru[64], s_rfrom[64];
@@ -838,7 +866,9 @@ __global__ void __launch_bounds__(REB_TB) rebalance_kernel(RebArgs a) {
       a.cta_best[blockIdx.x] = cb;
     }
     { const long long t1 = clock64(); tA += t1 - t0; t0 = t1; }
-    grid.sync();
+    n_a++;
+    bar_arrive(&a.bar->arrive_a);
+    if (blockIdx.x == 0) bar_wait(&a.bar->arrive_a, n_a * G);
     { const long long t1 = clock64(); tS += t1 - t0; t0 = t1; }
     // ---- B: argmax over the CTAs (max dru; ties -> greatest hostname), next-state
     if (blockIdx.x == 0 && warp == 0) {
@@ -972,7 +1002,8 @@ __global__ void __launch_bounds__(REB_TB) rebalance_kernel(RebArgs a) {
       __threadfence();
     }
     { const long long t1 = clock64(); tB += t1 - t0; t0 = t1; }
-    grid.sync();
+    if (blockIdx.x == 0) bar_raise(&a.bar->flag_b, n_a);
+    else bar_wait(&a.bar->flag_b, n_a);
     { const long long t1 = clock64(); tS += t1 - t0; t0 = t1; }
     n_dec = a.cnt[1];
     if (a.cnt[4] != 0) {
@@ -1078,7 +1109,9 @@ __global__ void __launch_bounds__(REB_TB) rebalance_kernel(RebArgs a) {
         }
       }
       { const long long t1 = clock64(); tC += t1 - t0; t0 = t1; }
-      grid.sync();
+      n_c++;
+      bar_arrive(&a.bar->arrive_c);
+      bar_wait(&a.bar->arrive_c, n_c * G);
       { const long long t1 = clock64(); tS += t1 - t0; t0 = t1; }
       cur ^= 1;
       n_tasks = n_tasks + 1;
@@ -1140,7 +1173,7 @@ static int32_t rebalance_run(cook_pool* pool, const cook_running_soa* running,
   sz.add<int32_t>(CAP); sz.add<int32_t>(CAP + MP); sz.add<int32_t>(CAP + MP);   // second order buffer, preempted hosts (+ their hostname ids)
   for (int k = 0; k < 2; k++) sz.add<int32_t>(U + 1);            // second segment buffers
   sz.add<CtaBest>(4 * pool->sm_count + 8); sz.add<GridFlag>(1); sz.add<int32_t>(H + 1);
-  sz.add<TaskHot>(CAP); sz.add<int32_t>(CAP); sz.add<int32_t>(H + 1); sz.add<int32_t>(CAP);
+  sz.add<TaskHot>(CAP); sz.add<int32_t>(CAP); sz.add<int32_t>(H + 1); sz.add<int32_t>(CAP); sz.add<WalkBar>(1);
   sz.add<double>(CAP); sz.add<double>(CAP); sz.add<double>(CAP / SCAN_TILE + 2); sz.add<double>(CAP / SCAN_TILE + 2);
   if (tr && tr->n_forced > 0) { sz.add<cook_decision>(tr->n_forced + 1); sz.add<int32_t>(CAP + MP); }
   CK(pool, ar.reserve(sz.off + (1 << 16)));
@@ -1262,12 +1295,14 @@ static int32_t rebalance_run(cook_pool* pool, const cook_running_soa* running,
   int32_t* d_hq = ar.take<int32_t>(CAP);
   int32_t* d_synh = ar.take<int32_t>(H + 1);
   int32_t* d_synn = ar.take<int32_t>(CAP);
+  WalkBar* d_bar = ar.take<WalkBar>(1);
   double* d_pm = ar.take<double>(CAP); double* d_pc = ar.take<double>(CAP);
   double* d_btm = ar.take<double>(CAP / SCAN_TILE + 2); double* d_btc = ar.take<double>(CAP / SCAN_TILE + 2);
   if (ar.failed) return set_err(pool, COOK_E_OOM, "cook_rebalance: arena exhausted");
   CK(pool, cudaMemsetAsync(d_gf, 0, sizeof(GridFlag), st));
   CK(pool, cudaMemsetAsync(d_syn, 0, sizeof(int32_t) * (H + 1), st));
   CK(pool, cudaMemsetAsync(d_synh, 0xff, sizeof(int32_t) * (H + 1), st));
+  CK(pool, cudaMemsetAsync(d_bar, 0, sizeof(WalkBar), st));
   if (R > 0) grid_check_kernel<<<(R + 255) / 256, 256, 0, st>>>(t.cpus, t.mem, t.gpus, R, d_gf);
   grid_check_kernel<<<(P + 255) / 256, 256, 0, st>>>(pc.cpus, pc.mem, pc.gpus, P, d_gf);
   int32_t h_cnt[16] = {R, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
@@ -1316,7 +1351,7 @@ static int32_t rebalance_run(cook_pool* pool, const cook_running_soa* running,
   ra.has_task = d_has_task; ra.preempted_hosts = d_pre; ra.preempted_hn = d_prehn;
   ra.min_diff = prm->min_dru_diff; ra.safe = prm->safe_dru_threshold; ra.host_lifetime_mins = prm->host_lifetime_mins;
   ra.best = d_best; ra.cta_best = d_cta; ra.dec = d_dec; ra.victims = d_vict; ra.cnt = d_cnt; ra.rf = d_rf;
-  ra.ps_all = d_ps; ra.gf = d_gf; ra.syn_cnt = d_syn; ra.hot = d_hot; ra.hq = d_hq; ra.syn_head = d_synh; ra.syn_next = d_synn;
+  ra.ps_all = d_ps; ra.gf = d_gf; ra.syn_cnt = d_syn; ra.hot = d_hot; ra.hq = d_hq; ra.syn_head = d_synh; ra.syn_next = d_synn; ra.bar = d_bar;
   ra.n_forced = NF; ra.forced = d_forced; ra.forced_victims = d_fvict; ra.forced_only = tr ? tr->forced_only : 0;
   {
     int occ = 0;
