@@ -2352,10 +2352,34 @@ __global__ void placed_flag_kernel(const int32_t* cons, const int32_t* out_assig
   int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k < n_cons && out_assign[k] >= 0) placed_job[cons[k]] = 1;
 }
+// exact-grid amounts: the sums do not depend on the order, one atomic add per placed job and column
+// (lanes of a warp that share the user are combined first)
+__global__ void usage_delta_exact_kernel(ConsArgs a, const int32_t* cons, const int32_t* out_assign, int n_cons,
+                                         double* delta /* [n_users][4] */, const GridFlag* gf) {
+  if (!grid_exact(gf, n_cons)) return;
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const bool placed = k < n_cons && out_assign[k] >= 0;
+  const unsigned act = __ballot_sync(0xffffffffu, placed);
+  if (!placed) return;
+  const int j = cons[k], u = a.jb.user[j];
+  double xn = 1.0, xc = a.jb.cpus[j], xm = a.jb.mem[j], xg = a.jb.gpus ? a.jb.gpus[j] : 0.0;
+  const unsigned peers = __match_any_sync(act, u);
+  const int leader = __ffs(peers) - 1;
+  for (unsigned m = peers & ~(1u << leader); m; m &= m - 1) {   // the leader gathers its peers' amounts
+    const int l = __ffs(m) - 1;
+    const double yn = __shfl_sync(peers, xn, l), yc = __shfl_sync(peers, xc, l), ym = __shfl_sync(peers, xm, l), yg = __shfl_sync(peers, xg, l);
+    if (lane == leader) { xn = xn + yn; xc = xc + yc; xm = xm + ym; xg = xg + yg; }
+  }
+  if (lane == leader) {
+    atomicAdd(&delta[4 * u], xn); atomicAdd(&delta[4 * u + 1], xc); atomicAdd(&delta[4 * u + 2], xm); atomicAdd(&delta[4 * u + 3], xg);
+  }
+}
 // warp per user: left fold over the user's queued jobs in queue order (pos_by_user), placed jobs only
 __global__ void __launch_bounds__(128) usage_delta_kernel(ConsArgs a, const int32_t* pos_by_user, const int32_t* seg_start,
                                                           const int32_t* seg_end, const uint8_t* placed_job,
-                                                          double* delta /* [n_users][4] */, const GridFlag* gf) {
+                                                          double* delta /* [n_users][4] */, const GridFlag* gf, int n_cons) {
+  if (grid_exact(gf, n_cons)) return;   // usage_delta_exact_kernel did it
   const int u = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (u >= a.n_users) return;
@@ -3004,8 +3028,9 @@ extern "C" int32_t cook_exchange_usage(cook_pool* pool, void* comm, int32_t worl
     const int TB = 256, nc = mp->last_n_cons;
     CK(pool, cudaMemsetAsync(mp->d_placed, 0, mp->J + 1, st));
     placed_flag_kernel<<<(nc + TB - 1) / TB, TB, 0, st>>>(mp->d_cons, mp->d_out_assign, nc, mp->d_placed);
-    usage_delta_kernel<<<(mp->U + 3) / 4, 128, 0, st>>>(mp->ca, mp->d_pos, mp->d_seg_s, mp->d_seg_e, mp->d_placed, d_local, mp->d_gf);
-    launches += 2;
+    usage_delta_exact_kernel<<<(nc + TB - 1) / TB, TB, 0, st>>>(mp->ca, mp->d_cons, mp->d_out_assign, nc, d_local, mp->d_gf);
+    usage_delta_kernel<<<(mp->U + 3) / 4, 128, 0, st>>>(mp->ca, mp->d_pos, mp->d_seg_s, mp->d_seg_e, mp->d_placed, d_local, mp->d_gf, nc);
+    launches += 3;
     CK(pool, cudaGetLastError());
   }
   if (world > 1 && comm) {

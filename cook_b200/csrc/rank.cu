@@ -116,7 +116,8 @@ struct UserCols {
 __global__ void __launch_bounds__(128) user_fold_kernel(
     const int32_t* __restrict__ idx, TaskCols t, UserCols uc, const int32_t* __restrict__ seg_start,
     const int32_t* __restrict__ seg_end, int n_users, int dru_mode, int max_over_quota,
-    double* __restrict__ dru_at, int32_t* n_kept_total, const GridFlag* gf) {
+    double* __restrict__ dru_at, int32_t* n_kept_total, const GridFlag* gf, int n_scan) {
+  if (n_scan > 0 && grid_exact(gf, n_scan)) return;   // the order-wide scans below did it
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= n_users) return;
@@ -202,6 +203,154 @@ __global__ void __launch_bounds__(128) user_fold_kernel(
     }
   }
   if (lane == 0 && kept) atomicAdd(n_kept_total, kept);
+}
+
+// K3 for exact-grid amounts (common.cuh: any association gives the left fold's bits): the per-user
+// running sums are ONE inclusive scan over the whole sorted order minus the scan just before the
+// user's first slot, the over-quota count is a second scan over the violation flags.  No user, however
+// long its list, sits on one warp.  Five launches: amount tiles, their totals, violation tiles, their
+// totals, the finish (keep / dru / kept count).
+constexpr int OS_TB = 256, OS_IPT = 8, OS_TILE = OS_TB * OS_IPT;
+
+struct OrderScan {
+  const int32_t* idx; TaskCols t; UserCols uc;
+  const int32_t* user_at; const int32_t* seg_start;
+  int n, dru_mode, max_over_quota;
+  const GridFlag* gf;
+  double *pm, *pc, *pg;      // [n] tile-local inclusive sums
+  double *bm, *bc, *bg;      // [tiles] totals, then exclusive offsets
+  int32_t* pv; int32_t* bv;  // the same for the violation flags
+  double* dru_at; int32_t* n_kept_total;
+};
+
+__device__ __forceinline__ void os_user_sums(const OrderScan& a, int p, int s, double& m, double& c, double& g) {
+  const int tp = p / OS_TILE;
+  m = a.pm[p] + a.bm[tp]; c = a.pc[p] + a.bc[tp]; g = a.pg[p] + a.bg[tp];
+  if (s > 0) {
+    const int ts = (s - 1) / OS_TILE;
+    m = m - (a.pm[s - 1] + a.bm[ts]); c = c - (a.pc[s - 1] + a.bc[ts]); g = g - (a.pg[s - 1] + a.bg[ts]);
+  }
+}
+
+__global__ void __launch_bounds__(OS_TB) os_amount_tiles(OrderScan a) {
+  if (!grid_exact(a.gf, a.n)) return;
+  __shared__ double s_m[OS_TB / 32], s_c[OS_TB / 32], s_g[OS_TB / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int p0 = blockIdx.x * OS_TILE + threadIdx.x * OS_IPT;
+  double xm[OS_IPT], xc[OS_IPT], xg[OS_IPT];
+#pragma unroll
+  for (int k = 0; k < OS_IPT; k++) {
+    const int p = p0 + k;
+    xm[k] = xc[k] = xg[k] = 0.0;
+    if (p < a.n) { const int ti = a.idx[p]; xm[k] = a.t.mem[ti]; xc[k] = a.t.cpus[ti]; xg[k] = a.t.gpus[ti]; }
+  }
+#pragma unroll
+  for (int k = 1; k < OS_IPT; k++) { xm[k] = xm[k - 1] + xm[k]; xc[k] = xc[k - 1] + xc[k]; xg[k] = xg[k - 1] + xg[k]; }
+  const double im = warp_incl_scan(xm[OS_IPT - 1], lane), ic = warp_incl_scan(xc[OS_IPT - 1], lane),
+               ig = warp_incl_scan(xg[OS_IPT - 1], lane);
+  if (lane == 31) { s_m[warp] = im; s_c[warp] = ic; s_g[warp] = ig; }
+  __syncthreads();
+  double om = im - xm[OS_IPT - 1], oc = ic - xc[OS_IPT - 1], og = ig - xg[OS_IPT - 1];
+  for (int w = 0; w < warp; w++) { om = om + s_m[w]; oc = oc + s_c[w]; og = og + s_g[w]; }
+#pragma unroll
+  for (int k = 0; k < OS_IPT; k++) {
+    const int p = p0 + k;
+    if (p < a.n) { a.pm[p] = om + xm[k]; a.pc[p] = oc + xc[k]; a.pg[p] = og + xg[k]; }
+  }
+  if (threadIdx.x == OS_TB - 1) {
+    a.bm[blockIdx.x] = om + xm[OS_IPT - 1]; a.bc[blockIdx.x] = oc + xc[OS_IPT - 1]; a.bg[blockIdx.x] = og + xg[OS_IPT - 1];
+  }
+}
+
+__global__ void os_amount_totals(OrderScan a, int nb) {   // one warp: totals -> exclusive offsets
+  if (!grid_exact(a.gf, a.n)) return;
+  const int lane = threadIdx.x;
+  double am = 0.0, ac = 0.0, ag = 0.0;
+  for (int base = 0; base < nb; base += 32) {
+    const int b = base + lane;
+    const double xm = b < nb ? a.bm[b] : 0.0, xc = b < nb ? a.bc[b] : 0.0, xg = b < nb ? a.bg[b] : 0.0;
+    const double im = am + warp_incl_scan(xm, lane), ic = ac + warp_incl_scan(xc, lane), ig = ag + warp_incl_scan(xg, lane);
+    if (b < nb) { a.bm[b] = im - xm; a.bc[b] = ic - xc; a.bg[b] = ig - xg; }
+    am = __shfl_sync(0xffffffffu, im, 31); ac = __shfl_sync(0xffffffffu, ic, 31); ag = __shfl_sync(0xffffffffu, ig, 31);
+  }
+}
+
+// scheduler.clj:2057-2071: a prefix violates when (count, cpus, mem, gpus) is not within the quota
+__global__ void __launch_bounds__(OS_TB) os_violation_tiles(OrderScan a) {
+  if (!grid_exact(a.gf, a.n)) return;
+  __shared__ int s_v[OS_TB / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int p0 = blockIdx.x * OS_TILE + threadIdx.x * OS_IPT;
+  int v[OS_IPT];
+#pragma unroll
+  for (int k = 0; k < OS_IPT; k++) {
+    const int p = p0 + k;
+    v[k] = 0;
+    if (p < a.n) {
+      const int u = a.user_at[p], s = a.seg_start[u];
+      double m, c, g;
+      os_user_sums(a, p, s, m, c, g);
+      const double cnt = (double)(p - s + 1);
+      v[k] = !(cnt <= a.uc.q_count[u] && c <= a.uc.q_cpus[u] && m <= a.uc.q_mem[u] && g <= a.uc.q_gpus[u]) ? 1 : 0;
+    }
+  }
+#pragma unroll
+  for (int k = 1; k < OS_IPT; k++) v[k] += v[k - 1];
+  int iv = v[OS_IPT - 1];
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, iv, o); if (lane >= o) iv += y; }
+  if (lane == 31) s_v[warp] = iv;
+  __syncthreads();
+  int ov = iv - v[OS_IPT - 1];
+  for (int w = 0; w < warp; w++) ov += s_v[w];
+#pragma unroll
+  for (int k = 0; k < OS_IPT; k++) {
+    const int p = p0 + k;
+    if (p < a.n) a.pv[p] = ov + v[k];
+  }
+  if (threadIdx.x == OS_TB - 1) a.bv[blockIdx.x] = ov + v[OS_IPT - 1];
+}
+
+__global__ void os_violation_totals(OrderScan a, int nb) {
+  if (!grid_exact(a.gf, a.n)) return;
+  const int lane = threadIdx.x;
+  int acc = 0;
+  for (int base = 0; base < nb; base += 32) {
+    const int b = base + lane;
+    const int x = b < nb ? a.bv[b] : 0;
+    int iv = x;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, iv, o); if (lane >= o) iv += y; }
+    iv += acc;
+    if (b < nb) a.bv[b] = iv - x;
+    acc = __shfl_sync(0xffffffffu, iv, 31);
+  }
+}
+
+__global__ void __launch_bounds__(OS_TB) os_finish(OrderScan a) {
+  if (!grid_exact(a.gf, a.n)) return;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  bool keep = false;
+  if (p < a.n) {
+    const int u = a.user_at[p], s = a.seg_start[u];
+    int over = a.pv[p] + a.bv[p / OS_TILE];
+    if (s > 0) over -= a.pv[s - 1] + a.bv[(s - 1) / OS_TILE];
+    keep = over <= a.max_over_quota;
+    double d = __longlong_as_double(0x7ff8000000000000LL);
+    if (keep) {
+      double m, c, g;
+      os_user_sums(a, p, s, m, c, g);
+      if (a.dru_mode == 0) {
+        const double x = m / a.uc.div_mem[u], y = c / a.uc.div_cpus[u];
+        d = x > y ? x : y;
+      } else {
+        d = g / a.uc.div_gpus[u];
+      }
+    }
+    a.dru_at[p] = d;
+  }
+  const int kept = __syncthreads_count(keep);
+  if (threadIdx.x == 0 && kept) atomicAdd(a.n_kept_total, kept);
 }
 
 struct QueueFilterArgs {
@@ -440,6 +589,8 @@ extern "C" int32_t cook_rank(cook_pool* pool, const cook_tasks_soa* running,
   for (int k = 0; k < 3; k++) sz.add<double>(N + 1);     // queue-order requests
   sz.add<int32_t>(N + 1); sz.add<uint8_t>(N + 1);        // queue-order task index, flags
   sz.add<int32_t>(N / QF_TB + 2); sz.add<GridFlag>(1);
+  for (int k = 0; k < 3; k++) sz.add<double>(N + 1);     // order-wide scans: tile-local sums
+  sz.add<double>(3 * (N / OS_TILE + 2)); sz.add<int32_t>(N + 1); sz.add<int32_t>(N / OS_TILE + 2);
   CK(pool, ar.reserve(sz.off + 4096));
   ar.reset();
 
@@ -483,6 +634,10 @@ extern "C" int32_t cook_rank(cook_pool* pool, const cook_tasks_soa* running,
   if (!d_dru_task) return set_err(pool, COOK_E_OOM, "cook_rank: arena exhausted");
 
   GridFlag* d_gf = ar.take<GridFlag>(1);
+  const int os_nb = (N + OS_TILE - 1) / OS_TILE;
+  double* d_os_pm = ar.take<double>(N + 1); double* d_os_pc = ar.take<double>(N + 1); double* d_os_pg = ar.take<double>(N + 1);
+  double* d_os_b = ar.take<double>(3 * (os_nb + 1));
+  int32_t* d_os_pv = ar.take<int32_t>(N + 1); int32_t* d_os_bv = ar.take<int32_t>(os_nb + 1);
   if (ar.failed) return set_err(pool, COOK_E_OOM, "cook_rank: arena exhausted");
   CK(pool, cudaMemsetAsync(d_gf, 0, sizeof(GridFlag), st));
   CK(pool, cudaMemsetAsync(d_seg_start, 0, sizeof(int32_t) * U, st));
@@ -496,11 +651,21 @@ extern "C" int32_t cook_rank(cook_pool* pool, const cook_tasks_soa* running,
   CK(pool, csort::sort_indices(d_idx, d_tmp, N, LessUserTask{t, d_name_rank}, st));
   seg_bounds_kernel<<<nb, TB, 0, st>>>(d_idx, d_user, N, d_seg_start, d_seg_end, d_user_at);
   {
+    OrderScan os;
+    os.idx = d_idx; os.t = t; os.uc = uc; os.user_at = d_user_at; os.seg_start = d_seg_start;
+    os.n = N; os.dru_mode = pool->dru_mode; os.max_over_quota = params->max_over_quota_jobs; os.gf = d_gf;
+    os.pm = d_os_pm; os.pc = d_os_pc; os.pg = d_os_pg; os.bm = d_os_b; os.bc = d_os_b + os_nb + 1; os.bg = d_os_b + 2 * (os_nb + 1);
+    os.pv = d_os_pv; os.bv = d_os_bv; os.dru_at = d_dru_at; os.n_kept_total = d_counters;
+    os_amount_tiles<<<os_nb, OS_TB, 0, st>>>(os);
+    os_amount_totals<<<1, 32, 0, st>>>(os, os_nb);
+    os_violation_tiles<<<os_nb, OS_TB, 0, st>>>(os);
+    os_violation_totals<<<1, 32, 0, st>>>(os, os_nb);
+    os_finish<<<(N + OS_TB - 1) / OS_TB, OS_TB, 0, st>>>(os);
     int warps_per_block = 4;
     int blocks = (U + warps_per_block - 1) / warps_per_block;
     user_fold_kernel<<<blocks, warps_per_block * 32, 0, st>>>(
         d_idx, t, uc, d_seg_start, d_seg_end, U, pool->dru_mode, params->max_over_quota_jobs,
-        d_dru_at, d_counters, d_gf);
+        d_dru_at, d_counters, d_gf, N);
   }
   iota_kernel<<<nb, TB, 0, st>>>(d_pos, N);
   CK(pool, csort::sort_indices(d_pos, d_tmp, N,

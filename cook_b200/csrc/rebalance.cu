@@ -1362,7 +1362,7 @@ static int32_t rebalance_run(cook_pool* pool, const cook_running_soa* running,
     if (const char* e = getenv("COOK_REB_CTAS_PER_SM")) per_sm = std::max(1, std::min(occ, atoi(e)));
     int grid = std::min(per_sm * pool->sm_count, std::max(1, (H + REB_TB / 32 - 1) / (REB_TB / 32)));
     void* kargs[] = {&ra};
-    CK(pool, cudaEventRecord(pool->ev[16], st));
+    CK(pool, cudaEventRecord(pool->ev[19], st));
     CK(pool, cudaLaunchCooperativeKernel((void*)rebalance_kernel, dim3(grid), dim3(REB_TB), kargs, 0, st));
     launches++;
   }
@@ -1373,7 +1373,7 @@ static int32_t rebalance_run(cook_pool* pool, const cook_running_soa* running,
     int32_t hp[10];
     CK(pool, cudaMemcpy(hp, d_cnt + 8, sizeof(hp), cudaMemcpyDeviceToHost));
     float pre = 0.f, walk = 0.f;
-    if (R > 0 && P > 0) { cudaEventElapsedTime(&pre, pool->ev[13], pool->ev[16]); cudaEventElapsedTime(&walk, pool->ev[16], pool->ev[14]); }
+    if (R > 0 && P > 0) { cudaEventElapsedTime(&pre, pool->ev[13], pool->ev[19]); cudaEventElapsedTime(&walk, pool->ev[19], pool->ev[14]); }
     fprintf(stderr, "[cook_prof] rebalance kcycles (CTA 0): hosts %d (scalars+groups %d)  next-state %d  refold %d  grid-sync %d | setup %.3f ms walk %.3f ms\n",
             hp[0], hp[4], hp[1], hp[2], hp[3], pre, walk);
     fprintf(stderr, "[cook_prof]   next-state split: argmax+victim selection %d  victims %d  bookkeeping %d  insertion search %d (argmax alone %d)\n", hp[5], hp[6], hp[7], hp[8], hp[9]);
