@@ -1725,13 +1725,30 @@ __global__ void __launch_bounds__(RES_THREADS, 1) match_kernel(MatchArgs a) {
     }
     __shared__ int bk_s[2];
     __shared__ double smin_s[2];
+    __shared__ double red_c[NW], red_m[NW];
     SparseLive& SP = *reinterpret_cast<SparseLive*>(
         smem_raw + ((sizeof(EvalShared) + 127) & ~size_t(127)) + (a.vs_in_smem ? (size_t)a.of.O * 32 : 0));
     if ((threadIdx.x >> 5) >= NW) return;  // only NW warps score rows (exited threads do not block the barriers)
     const int n_eval = gridDim.x - 1 - ns;
     const int ei = (int)blockIdx.x - 1 - ns;   // this evaluator's index
-    unsigned long long work = 0, wait = 0, work_q1 = 0, rows_q1 = 0, nblk_seen = 0;
+    unsigned long long work = 0, wait = 0, work_q1 = 0, rows_q1 = 0, nblk_seen = 0, n_hopeless = 0;
     unsigned long long ep[3] = {0, 0, 0};
+    // largest capacities of the cluster (static): scale of the rounding margin of the row pre-test below
+    double capc = 0.0, capm = 0.0;
+    {
+      const double2* stb = reinterpret_cast<const double2*>(a.of.vs);
+      for (int v = threadIdx.x; v < a.of.O; v += NW * 32) {
+        double lc, lm;
+        if (es.lc) { lc = es.lc[v]; lm = es.lm[v]; }
+        else { const double2 s0 = __ldg(stb + 2 * v); lc = s0.x; lm = s0.y; }
+        capc = fmax(capc, lc); capm = fmax(capm, lm);
+      }
+      for (int o = 16; o > 0; o >>= 1) { capc = fmax(capc, __shfl_xor_sync(0xffffffffu, capc, o)); capm = fmax(capm, __shfl_xor_sync(0xffffffffu, capm, o)); }
+      if ((threadIdx.x & 31) == 0) { red_c[threadIdx.x >> 5] = capc; red_m[threadIdx.x >> 5] = capm; }
+      __syncthreads();
+      for (int w = 0; w < NW; w++) { capc = fmax(capc, red_c[w]); capm = fmax(capm, red_m[w]); }
+      __syncthreads();
+    }
     for (int b = 0;; b++) {
       long long w0 = clock64();
       // rows of block b need S_{b-2}: published >= b-1 (which also covers bk0[b], bk0[b+1])
@@ -1756,8 +1773,12 @@ __global__ void __launch_bounds__(RES_THREADS, 1) match_kernel(MatchArgs a) {
       // dead = even the smallest request among the jobs from k0 on does not fit (exact: the
       // assigned amounts only grow within a cycle)
       unsigned long long live = ~0ull;
+      // most room left on any live VM at this snapshot (cpus, mem): a job that asks for more than that
+      // fits nowhere, now or later in the cycle - its row is not scored at all (pre-test below)
+      double maxfc = 1.7976931348623157e308, maxfm = 1.7976931348623157e308;
       if (a.of.O <= 64 * 32 * NW) {
         live = 0ull;
+        double fc = -1.0, fm = -1.0;
         const double2* dyb = reinterpret_cast<const double2*>(a.dyn.d[b & 1]);
         const double2* stb = reinterpret_cast<const double2*>(a.of.vs);
         int u = 0;
@@ -1766,15 +1787,31 @@ __global__ void __launch_bounds__(RES_THREADS, 1) match_kernel(MatchArgs a) {
           double lc, lm;
           if (es.lc) { lc = es.lc[v]; lm = es.lm[v]; }
           else { const double2 s0 = __ldg(stb + 2 * v); lc = s0.x; lm = s0.y; }
-          const bool dead = (d0.x + minc > lc) | (d0.y + minm > lm);
-          if (!dead) live |= 1ull << u;
+          bool dead = (d0.x + minc > lc) | (d0.y + minm > lm);
+          bool special = false;   // a VM only jobs of a special kind can use: a reserved host, a k8s GPU node
+          if (CONSTR) {
+            const int4* vcp = reinterpret_cast<const int4*>(a.of.vc + v);
+            const int4 c0 = __ldg(vcp), c1 = __ldg(vcp + 1);
+            const int an = __ldcg(reinterpret_cast<const int*>(a.dyn.n[b & 1] + v));
+            // max-tasks-per-host reached (assigned counts only grow): no job can ever go there
+            if (c0.z >= 0 && !(c0.w + an < c0.z)) dead = true;
+            special = (c1.y & VC_RESERVED) || ((c1.y & VC_K8S) && (c1.y >> 8) != 0);
+          }
+          if (!dead) {
+            live |= 1ull << u;
+            if (!special) { fc = fmax(fc, lc - d0.x); fm = fmax(fm, lm - d0.y); }
+          }
         }
+        for (int o = 16; o > 0; o >>= 1) { fc = fmax(fc, __shfl_xor_sync(0xffffffffu, fc, o)); fm = fmax(fm, __shfl_xor_sync(0xffffffffu, fm, o)); }
+        if ((threadIdx.x & 31) == 0) { red_c[threadIdx.x >> 5] = fc; red_m[threadIdx.x >> 5] = fm; }
         // every CTA sees all VMs: when none is live nothing from k0 on can ever be placed
         // (state only tightens) - all evaluators stop here and the drivers end the cycle
         if (!__syncthreads_or(live != 0ull)) {
           if (threadIdx.x == 0) atomicMax(a.dead_blk, b + 1);
           break;
         }
+        maxfc = maxfm = -1.0;
+        for (int w = 0; w < NW; w++) { maxfc = fmax(maxfc, red_c[w]); maxfm = fmax(maxfm, red_m[w]); }
       }
       // live VMs of every chunk compacted into shared memory; sparse mode when all lists fit
       bool sparse = false;
@@ -1805,6 +1842,18 @@ __global__ void __launch_bounds__(RES_THREADS, 1) match_kernel(MatchArgs a) {
         const JobRegs r = rn;
         const bool grp = gn;
         if (k + n_eval < k1) { rn = load_job<CONSTR>(a, k + n_eval); gn = CONSTR && (a.kflags[k + n_eval] & 1); }
+        // pre-test (uniform over the CTA): the request exceeds the most room any live VM has, by more than
+        // any rounding of `assigned + request > limit` could hide (margin 1e-9 x scale against 2^-52) =>
+        // every VM fails the resource check; the row keeps its stale (infeasible) stamp
+        // (constraint kernel: the room is that of the VMs any job may use; a gpu job or a job holding a
+        // reservation could still go to a k8s GPU node / its reserved host and is always scored)
+        const bool plain = !CONSTR || (r.g == 0.0 && !(a.jb.reserved_host && a.jb.reserved_host[r.j] >= 0));
+        if (plain && ((r.c - maxfc) > 1e-9 * (capc + r.c) || (r.m - maxfm) > 1e-9 * (capm + r.m))) {
+          if (threadIdx.x == 0)
+            asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(a.rows_ready + b), "r"(1u) : "memory");
+          n_hopeless++;
+          continue;
+        }
         evaluate_row<CONSTR, PROF>(a, r, grp, b, k - k0, es, E, live, ep, SP, sparse);
       }
       wait += (unsigned long long)(w1 - w0);
@@ -1814,7 +1863,7 @@ __global__ void __launch_bounds__(RES_THREADS, 1) match_kernel(MatchArgs a) {
     }
     if (ei == 0 && threadIdx.x == 0) {
       a.stats[16] = work; a.stats[17] = wait;
-      if (PROF) { a.stats[18] = ep[0]; a.stats[19] = ep[1]; a.stats[20] = ep[2]; a.stats[21] = work_q1; a.stats[22] = rows_q1; a.stats[23] = nblk_seen; }
+      if (PROF) { a.stats[18] = ep[0]; a.stats[19] = ep[1]; a.stats[20] = ep[2]; a.stats[21] = work_q1; a.stats[22] = rows_q1; a.stats[23] = nblk_seen; a.stats[26] = n_hopeless; }
     }
   }
 }
@@ -2912,11 +2961,11 @@ static int32_t run_plan(cook_pool* pool, MatchPlan* mp, int32_t* out_considerabl
   CK(pool, cudaEventRecord(pool->ev[4], st));
   CK(pool, cudaStreamSynchronize(st));
   if (prof_on) {
-    const char* nm[26] = {"fast", "chunk_rescan", "group_jobs", "matched", "fallbacks", "trunc_specs",
+    const char* nm[27] = {"fast", "chunk_rescan", "group_jobs", "matched", "fallbacks", "trunc_specs",
                           "skipped", "slow_turns", "c_wait_result", "c_follow_log", "c_decide_commit", "c_to_argmax",
                           "c_end_block", "c_fallback", "res_total", "res_q1_done", "eval_work", "eval_wait",
-                          "eval_loop", "eval_sync", "eval_merge", "eval_work_q1", "eval_rowslots_q1", "blocks", "z_takes", "relooks"};
-    for (int i = 0; i < 26; i++) fprintf(stderr, "[cook_prof] %-14s %llu\n", nm[i], hstats[i]);
+                          "eval_loop", "eval_sync", "eval_merge", "eval_work_q1", "eval_rowslots_q1", "blocks", "z_takes", "relooks", "rows_pretest_ei0"};
+    for (int i = 0; i < 27; i++) fprintf(stderr, "[cook_prof] %-14s %llu\n", nm[i], hstats[i]);
   }
   mp->last_n_cons = n_cons;
   {
