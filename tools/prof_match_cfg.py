@@ -14,12 +14,24 @@ eng = GpuEngine()
 ranked = eng.rank(t["running"], t["pending"], t["users"])["ranked"]
 prm = traces.match_params(t["jobs"].n, host_lifetime_mins=t["host_lifetime_mins"])
 os.environ.pop("COOK_PROF", None)
-for _ in range(3):
-    m = eng.match(ranked, t["jobs"], t["offers"], t["users"], prm, groups=t["groups"], max_ports=2)
-    s = m["stats"]
-    print(cfg, p, "jobs", t["jobs"].n, "offers", t["offers"].n, "kernel_ms", round(s["ms_match_kernel"], 3),
-          "considerable_ms", round(s["ms_considerable"], 3), "match_ms", round(s["ms_match"], 3),
+ref = None
+for env in sys.argv[3:] or [""]:          # e.g. COOK_MATCH_TARGET=64,COOK_MATCH_BMIN=128
+    for kv in env.split(","):
+        if "=" in kv:
+            k, v = kv.split("=")
+            os.environ[k] = v
+    ms = []
+    for _ in range(3):
+        m = eng.match(ranked, t["jobs"], t["offers"], t["users"], prm, groups=t["groups"], max_ports=2)
+        s = m["stats"]
+        ms.append(round(s["ms_match_kernel"], 3))
+    if ref is None:
+        ref = m["assign"].copy()
+    print(cfg, p, "env", env, "jobs", t["jobs"].n, "offers", t["offers"].n, "kernel_ms", ms,
+          "same" if (m["assign"] == ref).all() else "DIFFERENT",
           {k: s[k] for k in ("n_considerable", "n_matched", "n_fast", "n_chunk_rescan", "n_full_rescan", "n_offers_used")}, flush=True)
+if not os.environ.get("PROF_DETAIL"):
+    sys.exit(0)
 os.environ["COOK_PROF"] = "1"
 m = eng.match(ranked, t["jobs"], t["offers"], t["users"], prm, groups=t["groups"], max_ports=2)
 print("prof_kernel_ms", round(m["stats"]["ms_match_kernel"], 3), flush=True)
