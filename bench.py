@@ -227,15 +227,7 @@ def run_ours(args):
         # plane (here torch.distributed), everything else is libcookgpu + NCCL
         box = [comm_unique_id(lib) if rank == 0 else None]
         dist.broadcast_object_list(box, src=0)
-        # NCCL announces its version on fd 1 at the first communicator: keep stdout to the one JSON line
-        sys.stdout.flush()
-        saved = os.dup(1)
-        os.dup2(2, 1)
-        try:
-            comm = comm_init(lib, box[0], rank, world, local)
-        finally:
-            os.dup2(saved, 1)
-            os.close(saved)
+        comm = comm_init(lib, box[0], rank, world, local)
 
     def barrier():
         torch.cuda.synchronize()
@@ -447,7 +439,7 @@ def run_ours(args):
             line["nonsaturating"] = nonsat
         if cpu:
             line["cpu_baseline"] = cpu
-        print(json.dumps(line), flush=True)
+        emit(line)
     for pr in pools:
         pr.eng.close()
     if idle:
@@ -519,7 +511,7 @@ def run_reference(args):
     sample = (f"one pool of the workload per step, rotating over its {len(pool_ids)} pool(s) "
               f"({evals / args.steps:.3g} evals per step): rank + match" + (" + rebalance" if has_reb else "") +
               f", {cores} threads, C++ restatement (not the JVM)")
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": "job x offer fit evals/sec per scheduling cycle",
         "value": v, "unit": "evals/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
@@ -528,10 +520,28 @@ def run_reference(args):
         "config": config_dict(cfg, world, plan),
         "cpu_baseline": {"value": v, "unit": "evals/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }), flush=True)
+    })
+
+
+_JSON_FD = None
+
+
+def emit(line):
+    """The run's ONE line of stdout.  Libraries write to fd 1 behind Python's back (NCCL announces its
+    version there at the first communicator, torch's or ours), so main() points fd 1 at stderr for the
+    whole run and the JSON line goes to the saved descriptor."""
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
 
 
 def main():
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
