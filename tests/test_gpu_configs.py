@@ -220,6 +220,33 @@ def test_off_grid_amounts_keep_the_left_fold(gpu, oracle):
     assert dg == do and len(do) > 0
 
 
+def test_row_pretest_borderline_requests(gpu, oracle):
+    """The evaluators skip a row whose request exceeds the most room left on any usable VM by more than a
+    guard margin (1e-9 x scale).  Requests that differ from each other - and so from the room left as
+    the cluster fills - by 1 ulp .. 1e-8 relative sit INSIDE that margin or just outside it: whatever
+    the pre-test decides, placements stay bit-identical to the oracle's exact `assigned + request >
+    limit` (cpu+mem kernel and constraint kernel, saturated clusters)."""
+    eps = (0.0, 2.3e-16, 1e-13, 3e-10, 0.9e-9, 1.1e-9, 2e-9, 1e-8, 1e-6)
+    cpus = tuple(b * (1.0 + e) for b in (0.5, 1.0, 2.0, 4.0) for e in eps)
+
+    def mem_fn(r, n):
+        base = 512.0 * r.integers(1, 33, size=n)
+        return base * (1.0 + r.choice(np.array(eps), size=n))
+    for constraints, seed in ((False, 301), (True, 302), (False, 303)):
+        t = traces.gen_pool(seed, 9000, 160, 30, 600, cpus_choices=cpus, mem_fn=mem_fn,
+                            constraints=constraints, n_attr_cols=4 if constraints else 0)
+        ro = oracle.rank(t["running"], t["pending"], t["users"])
+        rg = gpu.rank(t["running"], t["pending"], t["users"])
+        assert np.array_equal(rg["ranked"], ro["ranked"])
+        prm = traces.match_params(9000)
+        kw = dict(groups=t.get("groups"), max_ports=2) if constraints else {}
+        mg = gpu.match(ro["ranked"], t["jobs"], t["offers"], t["users"], prm, **kw)
+        mo = oracle.match(ro["ranked"], t["jobs"], t["offers"], t["users"], prm, **kw)
+        assert np.array_equal(mg["considerable"], mo["considerable"])
+        assert np.array_equal(mg["assign"], mo["assign"])
+        assert 0 < mo["stats"]["n_matched"] < 0.5 * mo["stats"]["n_considerable"]   # saturated: most rows are hopeless
+
+
 def test_placement_failure_summaries(gpu, oracle):
     """per-reason host counts of unplaced (and a few placed) jobs AT THEIR TURN, through
     the CUDA path, equal the oracle's counts from replaying the match; the summary has the
