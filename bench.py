@@ -154,7 +154,7 @@ def config_dict(config, world, plan):
             "l2": "flushed between timed iterations (512 MiB memset)",
             "parallelism": (f"pool-sharded x{world} (one pool per GPU, weak)" if config == "c2" else
                             f"{len(plan)} pools placed on {world} GPU(s) by LPT (strong)") +
-                           ", device-side usage delta + one ncclAllGather per pool slot per cycle"}
+                           ", device-side usage delta + ONE ncclAllGather per cycle for all of a rank's pools"}
 
 
 def GROUP_QUOTA():
@@ -211,7 +211,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     from cook_b200 import abi
-    from cook_b200.engine import GpuEngine, comm_init, comm_unique_id, load_library
+    from cook_b200.engine import GpuEngine, comm_init, comm_unique_id, exchange_usage_batch, load_library
 
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -252,7 +252,6 @@ def run_ours(args):
     mine = [p for p, r in plan if r == rank]
     slots = max(sum(1 for _, r in plan if r == g) for g in range(world))   # exchanges per cycle (same on all ranks)
     pools = [PoolRun(cfg, p, GpuEngine, local, pin=True) for p in mine]
-    idle = GpuEngine(pool_name="idle", device=local) if len(pools) < slots else None   # contributes zeros
     nu_pad = int(max_over_ranks(max([pr.nu for pr in pools] + [1])))
     flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device="cuda")  # > 126 MB L2
     has_reb = cfg in ("c4", "c5")
@@ -278,15 +277,16 @@ def run_ours(args):
                     dec += len(d)
                     s = pr.eng.last_stats(abi.PHASE_REBALANCE)
                     ph["rebalance"] += s["ms_device"]; h2d += s["h2d_bytes"]; d2h += s["d2h_bytes"]
-            eng = pr.eng if pr is not None else idle
-            g = eng.exchange_usage(nu_pad, comm=comm, world=world)     # [world, nu_pad, 4]
-            s = eng.last_stats(abi.PHASE_EXCHANGE)
-            ph["exchange"] += s["ms_device"]; ln += s["n_launches"]; d2h += s["d2h_bytes"]
-            # the collective's result is consumed: every pool's quota-group usage for the NEXT rank
-            # cycle is the sum of all pools' deltas (aggregate-quota-groups, scheduler.clj:2125-2132)
-            tot = g.sum(axis=(0, 1))
-            for q in pools:
-                q.group_usage = tot
+        # ONE exchange per cycle for all of this rank's pools (cook_exchange_usage_batch): LPT balances the
+        # SUM of a rank's pools; a collective per pool slot would make every slot as long as its slowest rank
+        g = exchange_usage_batch([q.eng for q in pools], nu_pad, n_slots=slots, comm=comm, world=world)   # [world, slots, nu_pad, 4]
+        s = pools[0].eng.last_stats(abi.PHASE_EXCHANGE)
+        ph["exchange"] += s["ms_device"]; ln += s["n_launches"]; d2h += s["d2h_bytes"]
+        # the collective's result is consumed: every pool's quota-group usage for the NEXT rank
+        # cycle is the sum of all pools' deltas (aggregate-quota-groups, scheduler.clj:2125-2132)
+        tot = g.sum(axis=(0, 1, 2))
+        for q in pools:
+            q.group_usage = tot
         return ph, ev, pl, ln, h2d, d2h, dec, last
 
     # ---------------- resident-input arm (value): upload once, then reuse_resident
@@ -442,8 +442,6 @@ def run_ours(args):
         emit(line)
     for pr in pools:
         pr.eng.close()
-    if idle:
-        idle.close()
     if comm is not None:
         lib.cook_comm_destroy(comm)
     if world > 1:

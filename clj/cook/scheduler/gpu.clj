@@ -161,3 +161,11 @@
   [handle comm world n-pad out]
   (check! handle (Native/exchangeUsage handle comm world n-pad out) "cook_exchange_usage")
   (.asDoubleBuffer ^ByteBuffer out))
+
+(defn exchange-usage-batch!
+  "§8e, once per cycle: the usage deltas of ALL pools this scheduler instance matched (handles in pool
+   order, `n-slots` = most pools any instance owns) in one all-gather.  Returns [world n-slots n-pad]."
+  [handles comm world n-pad n-slots out]
+  (check! (first handles) (Native/exchangeUsageBatch (long-array handles) comm world n-pad n-slots out)
+          "cook_exchange_usage_batch")
+  (.asDoubleBuffer ^ByteBuffer out))

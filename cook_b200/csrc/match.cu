@@ -3057,15 +3057,32 @@ extern "C" int32_t cook_match(cook_pool* pool, const int32_t* ranked_idx, int32_
 
 
 // §8e: usage delta of this handle's last match round (device) -> one all-gather -> host.
-extern "C" int32_t cook_exchange_usage(cook_pool* pool, void* comm, int32_t world, int32_t n_pad,
-                                       double* out_all) {
-  if (!pool || !out_all || world <= 0 || n_pad <= 0) return set_err(pool, COOK_E_BADARG, "cook_exchange_usage: bad argument");
-  CK(pool, cudaSetDevice(pool->device));
-  cudaStream_t st = pool->stream;
-  MatchPlan* mp = static_cast<MatchPlan*>(pool->match_plan);
+// the per-user usage delta of `src`'s last match round into d_local[n_pad] (zeroed by the caller), on stream st
+static int32_t usage_delta_launch(cook_pool* pool, cook_pool* src, cudaStream_t st, double* d_local, int32_t n_pad,
+                                  int* launches) {
+  MatchPlan* mp = static_cast<MatchPlan*>(src->match_plan);
   const bool have = mp && mp->valid;
   if (have && 4 * mp->U > n_pad) return set_err(pool, COOK_E_BADARG, "cook_exchange_usage: n_pad < 4 * n_users");
-  const size_t need = (size_t)(world + 1) * n_pad;
+  if (have && mp->last_n_cons > 0) {
+    const int TB = 256, nc = mp->last_n_cons;
+    CK(pool, cudaMemsetAsync(mp->d_placed, 0, mp->J + 1, st));
+    placed_flag_kernel<<<(nc + TB - 1) / TB, TB, 0, st>>>(mp->d_cons, mp->d_out_assign, nc, mp->d_placed);
+    usage_delta_exact_kernel<<<(nc + TB - 1) / TB, TB, 0, st>>>(mp->ca, mp->d_cons, mp->d_out_assign, nc, d_local, mp->d_gf);
+    usage_delta_kernel<<<(mp->U + 3) / 4, 128, 0, st>>>(mp->ca, mp->d_pos, mp->d_seg_s, mp->d_seg_e, mp->d_placed, d_local, mp->d_gf, nc);
+    *launches += 3;
+    CK(pool, cudaGetLastError());
+  }
+  return COOK_OK;
+}
+
+// deltas of n_pools handles of this rank (slot i = pools[i], the slots beyond n_pools stay zero), ONE all-gather
+static int32_t exchange_run(cook_pool* const* pools, int32_t n_pools, void* comm, int32_t world, int32_t n_pad,
+                            int32_t n_slots, double* out_all) {
+  cook_pool* pool = pools[0];
+  CK(pool, cudaSetDevice(pool->device));
+  cudaStream_t st = pool->stream;
+  const size_t per_rank = (size_t)n_slots * n_pad;
+  const size_t need = (size_t)(world + 1) * per_rank;
   if (need > pool->xchg_cap) {
     if (pool->xchg) cudaFree(pool->xchg);
     pool->xchg = nullptr; pool->xchg_cap = 0;
@@ -3073,21 +3090,18 @@ extern "C" int32_t cook_exchange_usage(cook_pool* pool, void* comm, int32_t worl
     pool->xchg_cap = need;
   }
   double* d_local = pool->xchg;
-  double* d_all = pool->xchg + n_pad;
+  double* d_all = pool->xchg + per_rank;
   int launches = 0;
   CK(pool, cudaEventRecord(pool->ev[16], st));
-  CK(pool, cudaMemsetAsync(d_local, 0, sizeof(double) * n_pad, st));
-  if (have && mp->last_n_cons > 0) {
-    const int TB = 256, nc = mp->last_n_cons;
-    CK(pool, cudaMemsetAsync(mp->d_placed, 0, mp->J + 1, st));
-    placed_flag_kernel<<<(nc + TB - 1) / TB, TB, 0, st>>>(mp->d_cons, mp->d_out_assign, nc, mp->d_placed);
-    usage_delta_exact_kernel<<<(nc + TB - 1) / TB, TB, 0, st>>>(mp->ca, mp->d_cons, mp->d_out_assign, nc, d_local, mp->d_gf);
-    usage_delta_kernel<<<(mp->U + 3) / 4, 128, 0, st>>>(mp->ca, mp->d_pos, mp->d_seg_s, mp->d_seg_e, mp->d_placed, d_local, mp->d_gf, nc);
-    launches += 3;
-    CK(pool, cudaGetLastError());
+  CK(pool, cudaMemsetAsync(d_local, 0, sizeof(double) * per_rank, st));
+  for (int i = 0; i < n_pools; i++) {
+    // the other handles' match rounds have completed (cook_match returns after its stream is idle):
+    // their result arrays are read from this handle's stream
+    int32_t rc = usage_delta_launch(pool, pools[i], st, d_local + (size_t)i * n_pad, n_pad, &launches);
+    if (rc != COOK_OK) return rc;
   }
   if (world > 1 && comm) {
-    int32_t rc = cook_allgather_usage(comm, st, d_local, d_all, n_pad);
+    int32_t rc = cook_allgather_usage(comm, st, d_local, d_all, (int64_t)per_rank);
     if (rc != COOK_OK) return set_err(pool, rc, "cook_exchange_usage: ncclAllGather failed");
     launches += 1;
   } else {
@@ -3095,7 +3109,7 @@ extern "C" int32_t cook_exchange_usage(cook_pool* pool, void* comm, int32_t worl
     if (world != 1) return set_err(pool, COOK_E_BADARG, "cook_exchange_usage: world > 1 needs a communicator");
   }
   CK(pool, cudaEventRecord(pool->ev[17], st));
-  CK(pool, cudaMemcpyAsync(out_all, d_all, sizeof(double) * (size_t)world * n_pad, cudaMemcpyDeviceToHost, st));
+  CK(pool, cudaMemcpyAsync(out_all, d_all, sizeof(double) * (size_t)world * per_rank, cudaMemcpyDeviceToHost, st));
   CK(pool, cudaEventRecord(pool->ev[18], st));
   CK(pool, cudaStreamSynchronize(st));
   cook_phase_stats& ps = pool->phase[COOK_PHASE_EXCHANGE];
@@ -3103,9 +3117,27 @@ extern "C" int32_t cook_exchange_usage(cook_pool* pool, void* comm, int32_t worl
   ps.ms_device = ev_ms(pool->ev[16], pool->ev[17]);
   ps.ms_d2h = ev_ms(pool->ev[17], pool->ev[18]);
   ps.h2d_bytes = 0;
-  ps.d2h_bytes = (int64_t)sizeof(double) * world * n_pad;
+  ps.d2h_bytes = (int64_t)sizeof(double) * world * (int64_t)per_rank;
   ps.n_launches = launches;
   return COOK_OK;
+}
+
+extern "C" int32_t cook_exchange_usage(cook_pool* pool, void* comm, int32_t world, int32_t n_pad, double* out_all) {
+  if (!pool || !out_all || world <= 0 || n_pad <= 0) return set_err(pool, COOK_E_BADARG, "cook_exchange_usage: bad argument");
+  cook_pool* one[1] = {pool};
+  return exchange_run(one, 1, comm, world, n_pad, 1, out_all);
+}
+
+extern "C" int32_t cook_exchange_usage_batch(cook_pool* const* pools, int32_t n_pools, void* comm, int32_t world,
+                                             int32_t n_pad, int32_t n_slots, double* out_all) {
+  if (!pools || n_pools <= 0 || !pools[0]) return COOK_E_BADARG;
+  cook_pool* pool = pools[0];
+  if (!out_all || world <= 0 || n_pad <= 0 || n_slots < n_pools)
+    return set_err(pool, COOK_E_BADARG, "cook_exchange_usage_batch: bad argument");
+  for (int i = 1; i < n_pools; i++)
+    if (!pools[i] || pools[i]->device != pool->device)
+      return set_err(pool, COOK_E_BADARG, "cook_exchange_usage_batch: the handles of one call live on one device");
+  return exchange_run(pools, n_pools, comm, world, n_pad, n_slots, out_all);
 }
 
 

@@ -60,7 +60,8 @@ def load_library(path=None):
     for name in ("cook_gpu_init", "cook_gpu_shutdown", "cook_pool_open", "cook_pool_close",
                  "cook_last_error", "cook_rank", "cook_match", "cook_rebalance",
                  "cook_allgather_usage", "cook_last_stats", "cook_comm_unique_id", "cook_comm_init",
-                 "cook_comm_destroy", "cook_exchange_usage", "cook_rebalance_trace", "cook_match_failures"):
+                 "cook_comm_destroy", "cook_exchange_usage", "cook_exchange_usage_batch", "cook_rebalance_trace",
+                 "cook_match_failures"):
         getattr(lib, name).restype = C.c_int32
     return lib
 
@@ -193,6 +194,23 @@ class GpuEngine:
         if rc != 0:
             self._err(rc)
         return out.reshape(world, n_users_pad, 4)
+
+
+def exchange_usage_batch(engines, n_users_pad, n_slots=None, comm=None, world=1):
+    """The exchange step for ALL the pools a rank ran in the cycle: their usage deltas (slot i =
+    engines[i], the slots beyond stay zero) travel in ONE all-gather (cook_exchange_usage_batch).
+    Returns [world, n_slots, n_users_pad, 4]."""
+    if not engines:
+        raise ValueError("exchange_usage_batch: at least one handle")
+    n_slots = len(engines) if n_slots is None else int(n_slots)
+    n_pad = 4 * int(n_users_pad)
+    out = np.zeros(world * n_slots * n_pad, np.float64)
+    handles = (C.c_void_p * len(engines))(*[e.pool for e in engines])
+    rc = engines[0].lib.cook_exchange_usage_batch(handles, len(engines), comm, int(world), n_pad, n_slots,
+                                                  abi.ptr(out, abi.P_F64))
+    if rc != 0:
+        engines[0]._err(rc)
+    return out.reshape(world, n_slots, n_users_pad, 4)
 
 
 def comm_unique_id(lib):

@@ -454,6 +454,16 @@ int32_t cook_comm_destroy(void* comm);
 int32_t cook_exchange_usage(cook_pool* pool, void* comm, int32_t world, int32_t n_pad,
                             double* out_all);
 
+/* The same for ALL the pools a rank ran in the cycle, with ONE all-gather per cycle instead of one
+ * per pool: pools placed on GPUs by LPT balance the SUM of a rank's pools, a collective per pool
+ * slot would make every slot as long as its slowest rank.  pools[i] fills slot i, slots
+ * n_pools .. n_slots-1 stay zero (ranks own different numbers of pools; n_slots is the same on
+ * every rank).  out_all[world][n_slots][n_pad].  The result feeds the NEXT cycle's cook_rank
+ * (group_usage), as aggregate-quota-groups scheduler.clj:2125-2132 does per cycle.  The handles
+ * of one call live on one device and are idle (their cook_match calls have returned).       */
+int32_t cook_exchange_usage_batch(cook_pool* const* pools, int32_t n_pools, void* comm, int32_t world,
+                                  int32_t n_pad, int32_t n_slots, double* out_all);
+
 #ifdef __cplusplus
 }
 #endif

@@ -189,3 +189,14 @@ JFN(jint, commDestroy)(JNIEnv* env, jclass k, jlong comm) { return cook_comm_des
 JFN(jint, exchangeUsage)(JNIEnv* env, jclass k, jlong pool, jlong comm, jint world, jint n_pad, jobject out_all) {
   return cook_exchange_usage((cook_pool*)(intptr_t)pool, (void*)(intptr_t)comm, world, n_pad, one(env, out_all));
 }
+/* all of this JVM's pools in one call: `pools` is a long[] of handles (one all-gather per cycle) */
+JFN(jint, exchangeUsageBatch)(JNIEnv* env, jclass k, jlongArray pools, jlong comm, jint world, jint n_pad, jint n_slots,
+                              jobject out_all) {
+  jsize n = (*env)->GetArrayLength(env, pools);
+  jlong* h = (*env)->GetLongArrayElements(env, pools, NULL);
+  cook_pool* p[64];
+  if (n > 64) n = 64;
+  for (jsize i = 0; i < n; i++) p[i] = (cook_pool*)(intptr_t)h[i];
+  (*env)->ReleaseLongArrayElements(env, pools, h, JNI_ABORT);
+  return cook_exchange_usage_batch(p, (int32_t)n, (void*)(intptr_t)comm, world, n_pad, n_slots, one(env, out_all));
+}

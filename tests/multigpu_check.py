@@ -52,11 +52,33 @@ rg = eng.rank(t["running"], t["pending"], t["users"], group_quota=gq, group_usag
 ro = ora.rank(t["running"], t["pending"], t["users"], group_quota=gq, group_usage=allh.sum(axis=(0, 1)))
 r0 = ora.rank(t["running"], t["pending"], t["users"], group_quota=gq, group_usage=np.zeros(4))
 assert np.array_equal(rg["ranked"], ro["ranked"]) and 0 < len(rg["ranked"]) < len(r0["ranked"])
+# the batched form (one all-gather per cycle for all of a rank's pools): rank r owns 1 + (r % 2) pools,
+# two slots everywhere; slot 0 = the pool above, slot 1 = a second small pool on the odd ranks, zeros elsewhere
+from cook_b200.engine import exchange_usage_batch
+engs = [eng]
+want2 = np.zeros((NU, 4))
+if rank % 2 == 1:
+    t2 = traces.gen_pool(700 + rank, 4_000, 200, NU, 500)
+    e2 = GpuEngine(pool_name=f"grp-{rank}-b", device=local)
+    r2 = e2.rank(t2["running"], t2["pending"], t2["users"])["ranked"]
+    m2 = e2.match(r2, t2["jobs"], t2["offers"], t2["users"], traces.match_params(t2["jobs"].n))
+    j2 = t2["jobs"]
+    want2 = sharding.usage_delta(m2["considerable"], m2["assign"], j2.col("user"), j2.col("cpus"), j2.col("mem"), j2.col("gpus"), NU)
+    engs.append(e2)
+eng.match(ranked, t["jobs"], t["offers"], t["users"], traces.match_params(t["jobs"].n))   # the round whose delta travels
+gb = exchange_usage_batch(engs, NU + 16, n_slots=2, comm=comm, world=world)               # [world, 2, NU + 16, 4]
+all2 = torch.zeros(world, NU, 4, dtype=torch.float64, device="cuda")
+dist.all_gather_into_tensor(all2.view(-1), torch.from_numpy(want2).cuda().reshape(-1))
+assert np.array_equal(gb[:, 0, :NU], allh), "batched exchange: slot 0 differs"
+assert np.array_equal(gb[:, 1, :NU], all2.cpu().numpy()), "batched exchange: slot 1 differs"
+assert not gb[:, :, NU:].any()
+for e in engs[1:]:
+    e.close()
 s = eng.last_stats(abi.PHASE_EXCHANGE)
 ok = torch.ones(1, device="cuda")
 dist.all_reduce(ok)
 if rank == 0:
-    print(f"MULTIGPU_OK world={world} exchange_ms={s['ms_device']:.3f} launches={s['n_launches']} "
+    print(f"MULTIGPU_OK world={world} batched=ok exchange_ms={s['ms_device']:.3f} launches={s['n_launches']} "
           f"placed={[int(x) for x in g[:, :, 0].sum(axis=1)]}", flush=True)
 eng.close()
 lib.cook_comm_destroy(comm)

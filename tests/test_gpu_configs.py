@@ -89,6 +89,31 @@ def test_usage_exchange_device_delta(gpu, oracle):
     assert s["n_launches"] == 3 and s["ms_device"] > 0.0
 
 
+def test_usage_exchange_batch_of_pools(gpu, oracle):
+    """cook_exchange_usage_batch (world 1): the deltas of several handles of one GPU in one call, slot i =
+    handle i, spare slots zero - the same numbers the per-pool call returns for each of them."""
+    from cook_b200.engine import GpuEngine, exchange_usage_batch
+    ta = traces.gen_pool(83, 9000, 400, 70, 1000)
+    tb = traces.gen_pool(84, 5000, 250, 40, 600)
+    eb = GpuEngine(pool_name="batch-b")
+    try:
+        for eng, t in ((gpu, ta), (eb, tb)):
+            r = eng.rank(t["running"], t["pending"], t["users"])["ranked"]
+            eng.match(r, t["jobs"], t["offers"], t["users"], traces.match_params(t["jobs"].n))
+        one_a, one_b = gpu.exchange_usage(80)[0], eb.exchange_usage(80)[0]
+        assert one_a[:, 0].sum() > 0 and one_b[:, 0].sum() > 0
+        got = exchange_usage_batch([gpu, eb], 80, n_slots=3)
+        assert got.shape == (1, 3, 80, 4)
+        assert np.array_equal(got[0, 0], one_a) and np.array_equal(got[0, 1], one_b)
+        assert not got[0, 2].any()
+        s = gpu.last_stats(abi.PHASE_EXCHANGE)
+        assert s["n_launches"] == 6 and s["d2h_bytes"] == 8 * 3 * 320
+        with pytest.raises(Exception):
+            exchange_usage_batch([gpu, eb], 80, n_slots=1)     # fewer slots than handles
+    finally:
+        eb.close()
+
+
 def test_exchange_feeds_next_rank(gpu, oracle):
     """The exchange's result is CONSUMED: two pools of one quota group; the usage gathered after pool
     A's match round is pool B's group_usage in the next rank cycle, and decides how deep B's queue
