@@ -125,7 +125,7 @@ def pool_plan(config, world):
     if config == "c2":
         return [(r, r) for r in range(world)]          # weak scaling: one C2 pool per GPU
     sizes = traces.pool_sizes(config)
-    owner = sharding.assign_pools_lpt([j * o for j, o, _, _ in sizes], world)
+    owner = sharding.assign_pools_lpt([sharding.pool_cycle_cost(j, o) for j, o, _, _ in sizes], world)
     return [(p, owner[p]) for p in range(len(sizes))]
 
 
