@@ -56,6 +56,18 @@ def aggregate_quota_groups(pool_usage, quota_groups):
     return out
 
 
+def stack_slots(deltas, n_slots, n_users_pad):
+    """Host twin of cook_exchange_usage_batch's layout: the deltas of a rank's pools ([n_users_p, 4] each)
+    as ONE table [n_slots, n_users_pad, 4], slot i = pool i, spare slots and spare users zero."""
+    if len(deltas) > n_slots:
+        raise ValueError("more pools than slots")
+    out = np.zeros((n_slots, n_users_pad, 4), np.float64)
+    for i, d in enumerate(deltas):
+        d = np.asarray(d, np.float64)
+        out[i, :d.shape[0]] = d
+    return out
+
+
 def exchange_usage(local, device=None):
     """All-gather of this rank's usage table (any shape, f64).  Returns
     [world, *local.shape].  Single process: returns local[None]."""

@@ -114,3 +114,64 @@ def test_usage_exchange_two_ranks_gloo():
     assert np.array_equal(all0, all1)
     assert np.array_equal(all0[0], d0) and np.array_equal(all0[1], d1)
     assert d0[:, 0].sum() > 0 and not np.array_equal(d0, d1)
+
+
+def _worker_slots(rank, world, port, q):
+    import torch.distributed as dist
+    from cook_b200 import traces
+    from cook_b200.sharding import exchange_usage, stack_slots, usage_delta
+    from oracle.pyoracle import OracleEngine
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    o = OracleEngine()
+    ds = []
+    for p in range(1 + rank):                       # rank 0 owns one pool, rank 1 two
+        t = traces.gen_pool(300 + 10 * rank + p, 600, 30, 8 + 2 * p, 80)
+        ranked = o.rank(t["running"], t["pending"], t["users"])["ranked"]
+        m = o.match(ranked, t["jobs"], t["offers"], t["users"], traces.match_params(600))
+        jb = t["jobs"]
+        ds.append(usage_delta(m["considerable"], m["assign"], jb.col("user"), jb.col("cpus"), jb.col("mem"),
+                              jb.col("gpus"), 8 + 2 * p))
+    allv = exchange_usage(stack_slots(ds, 2, 12))   # ONE collective per cycle for all pools of the rank
+    q.put((rank, ds, allv))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_usage_exchange_one_collective_per_cycle_gloo():
+    """world_size 2 on CPU, ranks owning different numbers of pools (the cook_exchange_usage_batch layout):
+    [world, n_slots, n_users_pad, 4], slot i = pool i of the rank, spare slots / users zero."""
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    ps = [ctx.Process(target=_worker_slots, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in range(2)], key=lambda x: x[0])
+    for p in ps:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (_, d0, all0), (_, d1, all1) = res
+    assert all0.shape == (2, 2, 12, 4) and np.array_equal(all0, all1)
+    assert np.array_equal(all0[0, 0, :8], d0[0]) and not all0[0, 0, 8:].any() and not all0[0, 1].any()
+    assert np.array_equal(all0[1, 0, :8], d1[0]) and np.array_equal(all0[1, 1, :10], d1[1]) and not all0[1, 1, 10:].any()
+    assert all0[..., 0].sum() == d0[0][:, 0].sum() + d1[0][:, 0].sum() + d1[1][:, 0].sum() > 0
+
+
+def test_pool_placement_follows_the_cost_model():
+    """LPT on sharding.pool_cycle_cost (node count, dearer per node above ~6k nodes): config #5's 16 pools on
+    4 GPUs land within 5 % of the ideal split, the largest pool gets a GPU of its own on 8."""
+    from cook_b200 import traces
+    from cook_b200.sharding import assign_pools_lpt, pool_cycle_cost
+    sizes = traces.pool_sizes("c5")
+    cost = [pool_cycle_cost(j, o) for j, o, _, _ in sizes]
+    assert cost == sorted(cost, reverse=True) and cost[0] / cost[-1] > 4.0
+    own = assign_pools_lpt(cost, 4)
+    load = [sum(c for c, g in zip(cost, own) if g == r) for r in range(4)]
+    assert max(load) <= 1.05 * sum(cost) / 4
+    assert sorted(own.count(r) for r in range(4)) == [3, 4, 4, 5]
+    own8 = assign_pools_lpt(cost, 8)
+    assert own8.count(own8[0]) == 1
