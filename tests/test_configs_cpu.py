@@ -74,3 +74,25 @@ def test_nonsaturating_c2_variant_places_everything(oracle):
     r = oracle.rank(t["running"], t["pending"], t["users"])["ranked"]
     m = oracle.match(r, t["jobs"], t["offers"], t["users"], traces.match_params(4000))
     assert m["stats"]["n_matched"] == 4000
+
+
+def test_reference_arm_prints_one_json_line():
+    """The driver's contract: `bench.py --impl reference` runs on the host cores alone and prints exactly ONE
+    line on stdout - the JSON with the arm's own cpu_baseline and e2e blocks (everything else, including what
+    libraries write to fd 1 behind Python's back, goes to stderr)."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=600, cwd=root)
+    assert p.returncode == 0, p.stderr[-2000:]
+    lines = p.stdout.splitlines()
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "evals/s" and d["value"] > 0 and d["steps"] == 1
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
+    import bench
+    assert d["config"] == bench.config_dict("c2", 1, bench.pool_plan("c2", 1))
