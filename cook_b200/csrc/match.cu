@@ -247,14 +247,6 @@ __device__ __forceinline__ JobRegs load_job(const MatchArgs& a, int k) {
   return r;
 }
 
-__device__ __forceinline__ double csr_lookup(const int32_t* off, const int32_t* key,
-                                             const double* val, int o, int k) {
-  if (!off) return 0.0;
-  for (int i = off[o]; i < off[o + 1]; i++)
-    if (key[i] == k) return val[i];
-  return 0.0;
-}
-
 // Static + count-dependent hard constraints of one (job, VM) pair, in Cook's
 // evaluation order (see oracle eval_pair; constraints.clj).  Group constraints
 // are handled by group_pass().  `an` = tasks assigned to the VM this cycle.
@@ -891,11 +883,6 @@ struct LaneList {
         int te = e[i]; e[i] = e[i - 1]; e[i - 1] = te;
       }
     }
-  }
-  __device__ __forceinline__ void pop() {
-#pragma unroll
-    for (int i = 0; i < LK - 1; i++) { f[i] = f[i + 1]; v[i] = v[i + 1]; e[i] = e[i + 1]; }
-    f[LK - 1] = 0.0; v[LK - 1] = 0x7fffffff; e[LK - 1] = -1;
   }
 };
 
