@@ -22,6 +22,7 @@ COOK_E_NCCL = -3
 COOK_E_OOM = -4
 COOK_E_UNSUPPORTED_CONSTRAINT = -5
 COOK_E_NO_DEVICE = -6
+COOK_E_TOO_LARGE = -7
 
 GROUP_UNIQUE, GROUP_BALANCED, GROUP_ATTR_EQUALS = 0, 1, 2
 FAIL_NONE, FAIL_RESOURCES, FAIL_CONSTRAINT, FAIL_NO_OFFERS = 0, 1, 2, 3

@@ -372,8 +372,11 @@ __device__ __forceinline__ double div_y(double x, double den, double y) {
   const double q0 = x * y;
   return fma(fma(-den, q0, x), y, q0);
 }
+// (y = 0 selects the IEEE division in div_y.)  The Markstein correction is proven for a faithful q0 and a
+// denominator whose significand is not all ones; such denominators take the plain division as well.
 __device__ __forceinline__ double safe_rcp(double den) {
-  return (den > 1e-100 && den < 1e100) ? 1.0 / den : 0.0;
+  const unsigned long long frac = (unsigned long long)__double_as_longlong(den) & 0x000fffffffffffffULL;
+  return (den > 1e-100 && den < 1e100 && frac != 0x000fffffffffffffULL) ? 1.0 / den : 0.0;
 }
 
 // FENZO 3a + 4 (see oracle): resource fit then cpuMemBinPacker fitness.
@@ -2909,7 +2912,10 @@ static int32_t run_plan(cook_pool* pool, MatchPlan* mp, int32_t* out_considerabl
           CK(pool, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, std::min(want, optin)));
           cur[di][vi] = std::min(want, optin);
         }
-        if ((int)smem > cur[di][vi]) return set_err(pool, COOK_E_CUDA, "cook_match: shared memory request exceeds the device limit");
+        if ((int)smem > cur[di][vi])
+          return set_err(pool, COOK_E_TOO_LARGE,
+                         "cook_match: the offer table does not fit the kernel's shared memory (constraint pools: the verdict-bit "
+                         "rows of the four owners bound a pool at about 130k offers) - split the pool");
       }
       int grid = pool->sm_count;
       if (max_ctas > 0) grid = std::min(grid, max_ctas);  // pools sharing one GPU

@@ -44,7 +44,10 @@ enum {
   COOK_E_NCCL = -3,
   COOK_E_OOM = -4,
   COOK_E_UNSUPPORTED_CONSTRAINT = -5,
-  COOK_E_NO_DEVICE = -6
+  COOK_E_NO_DEVICE = -6,
+  COOK_E_TOO_LARGE = -7   /* a table exceeds what the kernels keep on chip (e.g. a constraint pool of more
+                             than ~130k offers: its verdict-bit rows live in the resolver's shared memory);
+                             split the pool - nothing was computed */
 };
 
 typedef struct cook_ctx cook_ctx;   /* process-wide: devices (+ NCCL comm)   */

@@ -376,6 +376,11 @@ double eval_pair(const MatchState& s, int j, int v, bool* res_fail) {
   }
   // FENZO 4: cpuMemBinPacker = (cpuFit + memFit) / 2,
   // xFit = (req + Σassigned-this-cycle + Σrunning) / (leaseTotal + Σrunning)
+  // ASSOCIATION: Fenzo's calculateResourceFitness folds req + a1 + a2 + ... one previous assignment at a time;
+  // here (and in the CUDA path) Σassigned-this-cycle is kept as a running sum: (req + Σassigned) + Σrunning.
+  // Identical on the binary grid the ABI asks for (include/cook_gpu.h: amounts are multiples of 2^-10 with
+  // exact sums), possibly one ulp apart otherwise - with Fenzo absent from /root/reference that case cannot
+  // be pinned either way (header: job -> host against a real Fenzo is unpinned).
   double rc = of->run_cpus ? of->run_cpus[v] : 0.0, rm = of->run_mem ? of->run_mem[v] : 0.0;
   double cpu_fit = ((jb->cpus[j] + s.asg_cpus[v]) + rc) / (of->cpus[v] + rc);
   double mem_fit = ((jb->mem[j] + s.asg_mem[v]) + rm) / (of->mem[v] + rm);
